@@ -1,0 +1,461 @@
+"""Drop-in for `BESST.CreateGraph.PE` (reference CreateGraph.py:45-321).
+
+Same signature, same side effects on the four object dicts and on `param`,
+same lines written to `Information`, same returned `(G, G_prime)` networkx
+graphs -- but the per-record loop (:111-211), CreateEdge (:812-871), the
+PosDir calculators (:1024-1076) and the per-edge statistics of
+GiveScoreOnEdges (:498-614) run as sm_100a CUDA kernels behind the C ABI
+(include/besst_b200.h).  This module is the host side above that ABI: it
+flattens the objects into the contig table, calls the engine once, and then
+replays the reference's order-dependent post-filters (:237-321) on the CSR
+edge list it gets back.
+
+There is no CPU fallback: without the CUDA library `PE` raises.
+"""
+from __future__ import annotations
+
+import os
+import sys
+from collections import Counter
+from time import time
+
+import networkx as nx
+import numpy as np
+
+from . import abi
+from . import e_nr_links
+from .contig_table import ContigTable
+from .normal import MaxObsDistr
+from .objects import classes
+from .records import as_batch
+
+
+def _new_graph():
+    return nx.Graph()
+
+
+def _remove_nodes(graph, scaf):
+    graph.remove_nodes_from([(scaf, 'L'), (scaf, 'R')])
+
+
+def _sample_sd(values, mean):
+    # the reference's expression, evaluated left to right (CreateGraph.py:918)
+    n = float(len(values))
+    return (sum([x ** 2 - 2 * x * mean + mean ** 2 for x in values]) / (n - 1)) ** 0.5
+
+
+def CalculateStats(sorted_contig_lengths, sorted_contig_lengths_small, param, Information):
+    """N50/L50 (CreateGraph.py:874-896)."""
+    half = param.tot_assembly_length / 2.0
+    cur, nr, N50, L50 = 0, 0, 0, 0
+    for group in (sorted_contig_lengths, sorted_contig_lengths_small):
+        if N50 != 0:
+            break
+        for length in group:
+            cur += length
+            nr += 1
+            if cur >= half:
+                N50, L50 = length, nr
+                break
+    print('L50: ', L50, 'N50: ', N50, 'Initial contig assembly length: ', param.tot_assembly_length, file=Information)
+    return N50, L50
+
+
+def InitializeObjects(bam_file, Contigs, Scaffolds, param, Information, G_prime, small_contigs, small_scaffolds, C_dict):
+    """One contig + one single-contig scaffold per BAM reference present in the
+    FASTA, large if length >= contig_threshold (CreateGraph.py:729-786)."""
+    contig_cls, scaffold_cls = classes()
+    lengths = [int(x) for x in bam_file.lengths]
+    names = bam_file.references
+    seq_lengths = [len(s) for s in C_dict.values()]
+    param.tot_assembly_length = sum(seq_lengths)
+    N50, L50 = CalculateStats(sorted(seq_lengths, reverse=True), [], param, Information)
+    param.current_L50, param.current_N50 = L50, N50
+    threshold = param.contig_threshold
+    start = time()
+    for i, name in enumerate(names):
+        if (i + 1) % 100000 == 0:
+            print('Time adding 100k keys', time() - start, file=Information)
+            start = time()
+        if name not in C_dict:
+            continue
+        length = lengths[i]
+        large = length >= threshold
+        if not large and not length > 0:
+            continue
+        c = contig_cls(name)
+        c.length = length
+        c.sequence = C_dict.pop(name)
+        c.direction = True
+        c.position = 0
+        s = scaffold_cls(param.scaffold_indexer, [c], length)
+        c.scaffold = s.name
+        if large:
+            Contigs[name] = c
+            Scaffolds[s.name] = s
+        else:
+            small_contigs[name] = c
+            small_scaffolds[s.name] = s
+        param.scaffold_indexer += 1
+
+
+def CleanObjects(Contigs, Scaffolds, param, Information, small_contigs, small_scaffolds):
+    """Demote scaffolds shorter than this library's contig_threshold
+    (CreateGraph.py:788-810)."""
+    large = sorted((s.s_length for s in Scaffolds.values()), reverse=True)
+    small = sorted((s.s_length for s in small_scaffolds.values()), reverse=True)
+    N50, L50 = CalculateStats(large, small, param, Information)
+    param.current_L50, param.current_N50 = L50, N50
+    moved = 0
+    for name in list(Scaffolds.keys()):
+        s = Scaffolds[name]
+        if s.s_length < param.contig_threshold:
+            for c in s.contigs:
+                del Contigs[c.name]
+                small_contigs[c.name] = c
+            small_scaffolds[name] = s
+            del Scaffolds[name]
+            moved += 1
+    print('Nr of contigs/scaffolds that was singeled out due to length constraints ' + str(moved), file=Information)
+
+
+def InitializeGraph(dict_with_scaffolds, graph, Information):
+    """Two nodes per scaffold joined by an nr_links=None edge
+    (CreateGraph.py:710-722)."""
+    start = time()
+    for cnt, (name, s) in enumerate(dict_with_scaffolds.items(), 1):
+        graph.add_edge((name, 'L'), (name, 'R'), nr_links=None)
+        graph.nodes[(name, 'L')]['length'] = s.s_length
+        graph.nodes[(name, 'R')]['length'] = s.s_length
+        if cnt % 100000 == 0:
+            print('Total nr of keys added: ', cnt, 'Time for adding last 100 000 keys: ', time() - start, file=Information)
+            start = time()
+
+
+def _write_fasta(path, contigs):
+    with open(path, 'w') as fh:
+        for c in contigs:
+            print('>' + c.name, file=fh)
+            seq = c.sequence
+            for i in range(0, len(seq), 60):
+                print(seq[i:i + 60], file=fh)
+
+
+def _forget(contigs, Contigs, small_contigs):
+    for c in contigs:
+        if c.name in Contigs:
+            del Contigs[c.name]
+        else:
+            del small_contigs[c.name]
+
+
+def filter_low_coverage_contigs(Contigs, Scaffolds, G, param, G_prime, small_contigs, small_scaffolds, Information):
+    """-z_min filter (CreateGraph.py:407-433; GenerateOutput.py:68-79)."""
+    print('Removing low coverage contigs if -z_min specified..', file=Information)
+    low = []
+    for c in Contigs.values():
+        if c.coverage < param.lower_cov_cutoff:
+            low.append(c)
+            del Scaffolds[c.scaffold]
+            _remove_nodes(G, c.scaffold)
+            if param.extend_paths:
+                _remove_nodes(G_prime, c.scaffold)
+    for c in small_contigs.values():
+        if c.coverage < param.lower_cov_cutoff:
+            low.append(c)
+            del small_scaffolds[c.scaffold]
+            _remove_nodes(G_prime, c.scaffold)
+    _write_fasta(param.output_directory + '/low_coverage_contigs.fa', low)
+    _forget(low, Contigs, small_contigs)
+    print('Removed a total of: ', len(low), ' low coverage contigs. With coverage lower than ', param.lower_cov_cutoff, file=Information)
+
+
+def RemoveOutliers(mean_cov, std_dev, cov_list):
+    k = MaxObsDistr(len(cov_list), 0.95)
+    kept = [x for x in cov_list if x < mean_cov + k * std_dev and x < 2 * mean_cov]
+    return len(cov_list) > len(kept), kept
+
+
+def CalculateMeanCoverage(Contigs, Information, param):
+    """Mean/sd of coverage over the <=50000 longest large contigs with iterative
+    outlier removal (CreateGraph.py:898-949)."""
+    by_length = sorted(((c.length, name) for name, c in Contigs.items()), key=lambda t: t[0], reverse=True)[:50000]
+    cov = [Contigs[name].coverage for _, name in by_length if Contigs[name].coverage > 0]
+    if len(cov) <= 1:
+        sys.exit("Too few contigs to calculate coverage on. Got: {0} contigs. If you have specified  -z_min or --min_mapq, consider lower them. If not, check the BAM file for proper alignments. Exiting here before scaffolding...".format(len(cov)))
+    n = float(len(cov))
+    mean_cov = sum(cov) / n
+    std_dev = _sample_sd(cov, mean_cov)
+    print('Mean coverage before filtering out extreme observations = ', mean_cov, file=Information)
+    print('Std dev of coverage before filtering out extreme observations= ', std_dev, file=Information)
+    print('Number of contigs used in calc of coverage before filtering: ', n, file=Information)
+    again = True
+    while again:
+        again, kept = RemoveOutliers(mean_cov, std_dev, cov)
+        n = float(len(kept))
+        if n == 0 or sum(kept) == 0:
+            break
+        mean_cov = sum(kept) / n
+        std_dev = _sample_sd(kept, mean_cov)
+        cov = kept
+    print('Mean coverage after filtering = ', mean_cov, file=Information)
+    print('Std coverage after filtering = ', std_dev, file=Information)
+    print('Number of contigs used in calc of coverage after filtering: ', n, file=Information)
+    print('Length of longest contig in calc of coverage: ', by_length[0][0], file=Information)
+    print('Length of shortest contig in calc of coverage: ', by_length[-1][0], file=Information)
+    return mean_cov, std_dev
+
+
+def RepeatDetector(Contigs, Scaffolds, G, param, G_prime, small_contigs, small_scaffolds, Information):
+    """Coverage-based repeat removal (CreateGraph.py:959-1018;
+    GenerateOutput.py:47-66)."""
+    mean_cov, std_dev = param.mean_coverage, param.std_dev_coverage
+    k = MaxObsDistr(len(Contigs), 0.95)
+    thresh = param.cov_cutoff if param.cov_cutoff else max(mean_cov + k * std_dev, 2 * mean_cov - 3 * std_dev)
+    print('Detecting repeats..', file=Information)
+    repeats, count_hapl = [], 0
+    hapl_limit = None
+    if param.detect_haplotype:
+        hapl_limit = mean_cov / 2.0 + param.hapl_threshold * std_dev
+    for c in Contigs.values():
+        if c.coverage > thresh:
+            repeats.append(c)
+            del Scaffolds[c.scaffold]
+            _remove_nodes(G, c.scaffold)
+            if param.extend_paths:
+                _remove_nodes(G_prime, c.scaffold)
+        if hapl_limit is not None and c.coverage < hapl_limit:
+            count_hapl += 1
+            c.is_haplotype = True
+    for c in small_contigs.values():
+        if c.coverage > thresh:
+            repeats.append(c)
+            del small_scaffolds[c.scaffold]
+            _remove_nodes(G_prime, c.scaffold)
+        if hapl_limit is not None and c.coverage < hapl_limit:
+            count_hapl += 1
+            c.is_haplotype = True
+    with open(param.output_directory + '/repeats_log.tsv', 'w') as fh:
+        print("contig_accession\tlength\tcoverage\tcov/mean_cov(exp number of placements)\tlib_mean\tplacable", file=fh)
+        for c in sorted(repeats, key=lambda x: x.coverage, reverse=True):
+            placable = "Yes" if param.mean_ins_size > c.length else 'No'
+            print("{0}\t{1}\t{2}\t{3}\t{4}\t{5}".format(c.name, c.length, round(c.coverage, 1), round(c.coverage / param.mean_coverage, 0), round(param.mean_ins_size, 0), placable), file=fh)
+    _write_fasta(param.output_directory + '/repeats.fa', repeats)
+    _forget(repeats, Contigs, small_contigs)
+    print('Removed a total of: ', len(repeats), ' repeats. With coverage larger than ', thresh, file=Information)
+    if param.detect_haplotype:
+        print('Marked a total of: ', count_hapl, ' potential haplotypes.', file=Information)
+    return Contigs, Scaffolds, G
+
+
+def infer_spurious_link_count_threshold(G_prime, param):
+    """Expected link count over a gap of mean+sd-2r between two 100 kb contigs
+    -> param.expected_links_over_mean_plus_stddev (CreateGraph.py:323-353)."""
+    nr_nodes = nx.number_of_nodes(G_prime) / 2
+    ratio = param.contamination_ratio if param.contamination_ratio else 0
+    cov = param.mean_coverage * (1 - ratio)
+    link_params = e_nr_links.Param(param.mean_ins_size, param.std_dev_ins_size, cov, param.read_len, 0)
+    gap = param.mean_ins_size + param.std_dev_ins_size - 2 * param.read_len
+    expected = e_nr_links.ExpectedLinks(100000, 100000, gap, link_params)
+    link_counter = Counter(d['nr_links'] for _, _, d in G_prime.edges(data=True) if d['nr_links'] is not None)
+    total = 0
+    for link_number in sorted(link_counter, reverse=True):
+        total += link_counter[link_number]
+        print('Nodes: {0}.\t Total edges with over {1} links:{2}. \tAverage density: {3}'.format(nr_nodes, link_number, total, total / float(nr_nodes)), file=param.information_file)
+    param.expected_links_over_mean_plus_stddev = 5 if expected < 5 else int(expected)
+    print('Letting filtering threshold in high complexity regions be {0} for this library.'.format(param.expected_links_over_mean_plus_stddev), file=param.information_file)
+
+
+def _drop_low_support(graph, edgesupport):
+    removed = 0
+    for u, v, d in list(graph.edges(data=True)):
+        if d['nr_links'] is not None and d['nr_links'] < edgesupport:
+            graph.remove_edge(u, v)
+            removed += 1
+    return removed
+
+
+def remove_edges_below_threshold(graph, param):
+    """Order-dependent pruning of G_prime (CreateGraph.py:355-404): in
+    `graph.edges()` order, drop a weak edge only while both endpoints still have
+    more than 4 neighbours; then drop everything under -e."""
+    print('Remove edges in high complexity areas.', file=param.information_file)
+    limit = param.expected_links_over_mean_plus_stddev
+    weak = [(u, v) for u, v, d in graph.edges(data=True) if d['nr_links'] is not None and d['nr_links'] < limit]
+    removed = 0
+    adj = graph.adj
+    for u, v in weak:
+        if len(adj[u]) > 4 and len(adj[v]) > 4:
+            graph.remove_edge(u, v)
+            removed += 1
+    print('Removed total of {0} edges in high density areas.'.format(removed), file=param.information_file)
+    low = _drop_low_support(graph, param.edgesupport)
+    print('Removed an additional of {0} edges with low support from full graph G_prime of all contigs.'.format(low), file=param.information_file)
+
+
+def RemoveBugEdges(G, G_prime, res, table, param, Information):
+    """Drop edges whose fishy count (unmapped read1 with the mate on another
+    scaffold, CreateGraph.py:141-163) reaches their link count (:690-708)."""
+    removed = 0
+    for e in np.nonzero(res.fishy > 0)[0].tolist():
+        n0, n1 = table.node(int(res.edge_u[e])), table.node(int(res.edge_v[e]))
+        count = int(res.fishy[e])
+        if param.extend_paths:
+            if G_prime.has_edge(n0, n1) and count >= G_prime[n0][n1]['nr_links']:
+                G_prime.remove_edge(n0, n1)
+                removed += 1
+            if G.has_edge(n0, n1) and count >= G[n0][n1]['nr_links']:
+                G.remove_edge(n0, n1)
+        elif G.has_edge(n0, n1) and count >= G[n0][n1]['nr_links']:
+            G.remove_edge(n0, n1)
+            removed += 1
+    print('Number of BWA buggy edges removed: ', removed, file=Information)
+
+
+def _populate(G, G_prime, res, table, param, observations_as_list=True):
+    """Insert the CSR link edges into the networkx graphs in first-appearance
+    (BAM) order, with the attribute names/types CreateEdge uses
+    (CreateGraph.py:842-862)."""
+    scoring = not param.no_score
+    into_G = scoring
+    into_GP = param.no_score or param.extend_paths
+    order = np.argsort(res.first_idx, kind='stable')
+    names = table.scaffold_names
+    total = res.obs_u.astype(np.int64) + res.obs_v
+    conv = (lambda a: a.tolist()) if observations_as_list else (lambda a: a)
+    row_ptr = res.row_ptr
+    for e in order.tolist():
+        u, v = int(res.edge_u[e]), int(res.edge_v[e])
+        nu = (names[u >> 1], 'R' if u & 1 else 'L')
+        nv = (names[v >> 1], 'R' if v & 1 else 'L')
+        b, t = int(row_ptr[e]), int(row_ptr[e + 1])
+        nr, obs, obs_sq = int(res.nr_links[e]), int(res.obs_sum[e]), int(res.obs_sq[e])
+        if into_G and (res.flags[e] & abi.EDGE_LL):
+            G.add_edge(nv, nu, nr_links=nr, obs=obs, obs_sq=obs_sq, observations=conv(total[b:t]))
+            d = G[nu][nv]
+            d[nu[0]] = conv(res.obs_u[b:t])   # per-scaffold lists, keyed by scaffold name (:848-849)
+            d[nv[0]] = conv(res.obs_v[b:t])
+        if into_GP:
+            G_prime.add_edge(nv, nu, nr_links=nr, obs=obs, obs_sq=obs_sq, observations=conv(total[b:t]))
+
+
+def GiveScoreOnEdges(G, res, table, param, Information):
+    """Attach the engine's per-edge gap and score to the surviving G edges
+    (the arithmetic of CreateGraph.py:498-614 ran on the GPU)."""
+    if param.lognormal:
+        raise NotImplementedError("lognormal libraries: the reference's scoring branch (CreateGraph.py:485-493) "
+                                  "is a 'next' row (SURVEY.md 8f rank 3)")
+    index = {}
+    for e in np.nonzero(res.flags & abi.EDGE_SCORED)[0].tolist():
+        index[(int(res.edge_u[e]), int(res.edge_v[e]))] = e
+    for n0, n1, d in G.edges(data=True):
+        if d['nr_links'] is None:
+            continue
+        a, b = table.node_id(n0), table.node_id(n1)
+        e = index[(a, b) if a < b else (b, a)]
+        d['gap'] = int(res.gap[e])
+        if res.flags[e] & abi.EDGE_NEGGAP:
+            d['score'] = 0
+            continue
+        del d[n0[0]]
+        del d[n1[0]]
+        s = float(res.score[e])
+        d['score'] = s if s != 0.0 else 0
+    print('Number of significantly spurious edges:', 0, file=Information)
+
+
+def engine_params(param, halo=(-1, -1)):
+    return abi.make_params(param.orientation, param.min_mapq, param.read_len, param.mean_ins_size,
+                           param.std_dev_ins_size, param.ins_size_threshold,
+                           detect_duplicate=param.detect_duplicate, extend_paths=param.extend_paths,
+                           no_score=param.no_score, halo=halo)
+
+
+def PE(Contigs, Scaffolds, Information, C_dict, param, small_contigs, small_scaffolds, bam_file, engine=None):
+    G = _new_graph()
+    G_prime = _new_graph()
+    print('Parsing BAM file...', file=Information)
+    if param.first_lib:
+        start = time()
+        InitializeObjects(bam_file, Contigs, Scaffolds, param, Information, G_prime, small_contigs, small_scaffolds, C_dict)
+        print('Time initializing BESST objects: ', time() - start, file=Information)
+    else:
+        start = time()
+        CleanObjects(Contigs, Scaffolds, param, Information, small_contigs, small_scaffolds)
+        print('Time cleaning BESST objects for next library: ', time() - start, file=Information)
+
+    if len(Scaffolds) == 0:
+        if not os.path.isfile(param.output_directory + '/repeats.fa'):
+            open(param.output_directory + '/repeats.fa', 'w').close()
+        return (G, G_prime)
+
+    start = time()
+    if param.no_score:
+        InitializeGraph(small_scaffolds, G_prime, Information)
+        InitializeGraph(Scaffolds, G_prime, Information)
+    elif param.extend_paths:
+        InitializeGraph(Scaffolds, G, Information)
+        InitializeGraph(small_scaffolds, G_prime, Information)
+        InitializeGraph(Scaffolds, G_prime, Information)
+    else:
+        InitializeGraph(Scaffolds, G, Information)
+    print('Total time elapsed for initializing Graph: ', time() - start, file=Information)
+
+    print('Reading bam file and creating scaffold graph...', file=Information)
+    start = time()
+    if engine is None:
+        from .engine import default_engine
+        engine = default_engine()
+    batch = as_batch(bam_file)
+    table = ContigTable(bam_file.references, bam_file.lengths, Contigs, small_contigs, Scaffolds, small_scaffolds)
+    res = engine.graph_build(table, engine_params(param), batch)
+    _populate(G, G_prime, res, table, param)
+    cnt = res.counters
+    print('ELAPSED reading file:', time() - start, file=Information)
+    print('NR OF FISHY READ LINKS: ', int(cnt[abi.CNT_FISHY]), file=Information)
+    print('Number of USEFUL READS (reads mapping to different contigs uniquly): ', int(cnt[abi.CNT_COUNT]), file=Information)
+    print('Number of non unique reads (at least one read non-unique in read pair) that maps to different contigs (filtered out from scaffolding): ', int(cnt[abi.CNT_NON_UNIQUE]), file=Information)
+    print('Reads with too large insert size from "USEFUL READS" (filtered out): ', int(cnt[abi.CNT_TOO_LONG]), file=Information)
+    print('Initial number of edges in G (the graph with large contigs): ', G.number_of_edges(), file=Information)
+    print('Initial number of edges in G_prime (the full graph of all contigs before removal of repats): ', G_prime.number_of_edges(), file=Information)
+    if param.detect_duplicate:
+        print('Number of duplicated reads indicated and removed: ', int(cnt[abi.CNT_DUPLICATES]), file=Information)
+
+    # coverage of every contig under this library (CreateGraph.py:237-244)
+    tid_of = {name: i for i, name in enumerate(bam_file.references)}
+    for d in (Contigs, small_contigs):
+        for name, c in d.items():
+            tid = tid_of.get(name)
+            aligned = int(res.aligned_len[tid]) if tid is not None else 0
+            c.coverage = aligned / float(c.length)
+
+    if param.first_lib and param.lower_cov_cutoff:
+        filter_low_coverage_contigs(Contigs, Scaffolds, G, param, G_prime, small_contigs, small_scaffolds, Information)
+
+    param.mean_coverage, param.std_dev_coverage = CalculateMeanCoverage(Contigs, Information, param)
+    if param.first_lib:
+        Contigs, Scaffolds, G = RepeatDetector(Contigs, Scaffolds, G, param, G_prime, small_contigs, small_scaffolds, Information)
+    print('Number of edges in G (after repeat removal): ', G.number_of_edges(), file=Information)
+    print('Number of edges in G_prime (after repeat removal): ', G_prime.number_of_edges(), file=Information)
+
+    RemoveBugEdges(G, G_prime, res, table, param, Information)
+    print('Number of edges in G (after filtering for buggy flag stats reporting): ', G.number_of_edges(), file=Information)
+    print('Number of edges in G_prime  (after filtering for buggy flag stats reporting): ', G_prime.number_of_edges(), file=Information)
+
+    infer_spurious_link_count_threshold(G_prime, param)
+    if not param.edgesupport:
+        param.edgesupport = 5
+        print('Letting -e be {0} for this library.'.format(param.edgesupport), file=Information)
+    else:
+        print('User has set -e to be {0} for this library.'.format(param.edgesupport), file=Information)
+    removed = _drop_low_support(G, param.edgesupport)
+    print('Removed {0} edges from graph G of border contigs.'.format(removed), file=Information)
+    remove_edges_below_threshold(G_prime, param)
+
+    if not param.no_score:
+        GiveScoreOnEdges(G, res, table, param, Information)
+    print('Number of edges in G_prime  (after removing edges under -e threshold (if not specified, default is -e 3): ', G_prime.number_of_edges(), file=Information)
+    print("\n -------------------------------------------------------------\n", file=Information)
+    print('Nr of contigs/scaffolds included in this pass: ' + str(len(Scaffolds) + len(small_scaffolds)), file=Information)
+    print('Out of which {0} acts as border contigs.'.format(len(Scaffolds)), file=Information)
+    return (G, G_prime)

@@ -1,0 +1,157 @@
+"""Record batch: the struct-of-arrays view of a library's BAM records.
+
+This is the data format on the *input* side of the hot path.  The reference
+iterates `pysam.AlignedRead` objects one at a time (CreateGraph.py:111,
+libmetrics.py:63,257,293); the B200 engine consumes the same per-record fields
+as flat, coalescable arrays (one array per field, BAM file order).
+
+Field <-> pysam 0.8.4 attribute <-> BAM fixed-core field:
+
+    tid   rname   refID            int32
+    mtid  mrnm    next_refID       int32
+    pos   pos     pos (0-based)    int32
+    mpos  mpos    next_pos         int32
+    tlen  tlen    tlen             int32
+    qlen  qlen    l_seq minus leading/trailing soft clips   int32
+    flag  (is_reverse=0x10, mate_is_reverse=0x20, is_read1=0x40,
+           is_read2=0x80, is_unmapped=0x4, mate_is_unmapped=0x8,
+           is_secondary=0x100)                              uint16
+    mapq  mapq                                              uint8
+    rlen  rlen    l_seq (host only; read-length estimate, libmetrics.py:246-266)
+    alen  alen    reference span from CIGAR (host only, same block)
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import Optional, Sequence
+
+import numpy as np
+
+FLAG_UNMAPPED = 0x4
+FLAG_MATE_UNMAPPED = 0x8
+FLAG_REVERSE = 0x10
+FLAG_MATE_REVERSE = 0x20
+FLAG_READ1 = 0x40
+FLAG_READ2 = 0x80
+FLAG_SECONDARY = 0x100
+
+_DEVICE_FIELDS = (("tid", np.int32), ("mtid", np.int32), ("pos", np.int32),
+                  ("mpos", np.int32), ("tlen", np.int32), ("qlen", np.int32),
+                  ("flag", np.uint16), ("mapq", np.uint8))
+
+
+@dataclass
+class RecordBatch:
+    """SoA record batch in BAM order plus the header tables."""
+    tid: np.ndarray
+    mtid: np.ndarray
+    pos: np.ndarray
+    mpos: np.ndarray
+    tlen: np.ndarray
+    qlen: np.ndarray
+    flag: np.ndarray
+    mapq: np.ndarray
+    references: Sequence[str] = field(default_factory=list)
+    lengths: Sequence[int] = field(default_factory=list)
+    rlen: Optional[np.ndarray] = None   # only the first 1000 are ever read
+    alen: Optional[np.ndarray] = None
+
+    def __post_init__(self):
+        for name, dt in _DEVICE_FIELDS:
+            a = np.ascontiguousarray(getattr(self, name), dtype=dt)
+            setattr(self, name, a)
+        n = self.tid.shape[0]
+        for name, _ in _DEVICE_FIELDS:
+            if getattr(self, name).shape != (n,):
+                raise ValueError("record field %s has shape %s, expected (%d,)"
+                                 % (name, getattr(self, name).shape, n))
+
+    def __len__(self):
+        return int(self.tid.shape[0])
+
+    def slice(self, lo, hi):
+        kw = {name: getattr(self, name)[lo:hi] for name, _ in _DEVICE_FIELDS}
+        return RecordBatch(references=self.references, lengths=self.lengths,
+                           rlen=None if self.rlen is None else self.rlen[lo:hi],
+                           alen=None if self.alen is None else self.alen[lo:hi], **kw)
+
+    def select(self, mask):
+        kw = {name: getattr(self, name)[mask] for name, _ in _DEVICE_FIELDS}
+        return RecordBatch(references=self.references, lengths=self.lengths,
+                           rlen=None if self.rlen is None else self.rlen[mask],
+                           alen=None if self.alen is None else self.alen[mask], **kw)
+
+    def device_arrays(self):
+        return {name: getattr(self, name) for name, _ in _DEVICE_FIELDS}
+
+    def save(self, path):
+        np.savez_compressed(
+            path, references=np.array(list(self.references)),
+            lengths=np.asarray(self.lengths, dtype=np.int64),
+            rlen=np.zeros(0, np.int32) if self.rlen is None else self.rlen[:1000],
+            alen=np.zeros(0, np.int32) if self.alen is None else self.alen[:1000],
+            **self.device_arrays())
+
+    @staticmethod
+    def load(path):
+        z = np.load(path, allow_pickle=False)
+        kw = {name: z[name] for name, _ in _DEVICE_FIELDS}
+        rlen = z["rlen"] if z["rlen"].size else None
+        alen = z["alen"] if z["alen"].size else None
+        return RecordBatch(references=[str(s) for s in z["references"]],
+                           lengths=[int(x) for x in z["lengths"]],
+                           rlen=rlen, alen=alen, **kw)
+
+
+def from_alignments(reads, references, lengths):
+    """Build a batch from an iterable of pysam-like AlignedRead objects (the
+    production ingest path: `for r in pysam.Samfile(...)`)."""
+    cols = {k: [] for k in ("tid", "mtid", "pos", "mpos", "tlen", "qlen", "flag", "mapq", "rlen", "alen")}
+    for r in reads:
+        cols["tid"].append(r.rname)
+        cols["mtid"].append(r.mrnm)
+        cols["pos"].append(r.pos)
+        cols["mpos"].append(r.mpos)
+        cols["tlen"].append(r.tlen)
+        cols["qlen"].append(r.qlen)
+        cols["flag"].append(r.flag)
+        cols["mapq"].append(r.mapq)
+        cols["rlen"].append(r.rlen)
+        cols["alen"].append(r.alen if r.alen is not None else 0)
+    return RecordBatch(references=list(references), lengths=[int(x) for x in lengths],
+                       rlen=np.asarray(cols.pop("rlen"), np.int32),
+                       alen=np.asarray(cols.pop("alen"), np.int32), **cols)
+
+
+class BatchFile(object):
+    """Minimal `pysam.Samfile` look-alike over a decoded RecordBatch: what the
+    drop-in entry points read from their `bam_file` argument (`references`,
+    `lengths`, `reset`, `fetch`) plus the batch itself, so no per-record Python
+    iteration is needed."""
+
+    def __init__(self, batch):
+        self.record_batch = batch
+        self.references = tuple(batch.references)
+        self.lengths = tuple(int(x) for x in batch.lengths)
+
+    def reset(self):
+        return None
+
+    def fetch(self, reference=None, *a, **k):
+        if reference is not None and reference not in self.references:
+            raise ValueError("invalid reference %r" % (reference,))
+        return iter(())
+
+
+def as_batch(bam_file):
+    """RecordBatch behind a `bam_file` argument: a RecordBatch, anything
+    carrying `.record_batch`, or a pysam-like iterable of AlignedRead."""
+    if isinstance(bam_file, RecordBatch):
+        return bam_file
+    batch = getattr(bam_file, "record_batch", None)
+    if batch is not None:
+        return batch
+    batch = from_alignments(bam_file, bam_file.references, bam_file.lengths)
+    if hasattr(bam_file, "reset"):
+        bam_file.reset()
+    return batch

@@ -1,0 +1,237 @@
+/* besst_b200.h -- C ABI of the B200-native scaffold-graph construction and
+ * gap-estimation engine (drop-in for one hot path of ksahlin/BESST).
+ *
+ * The reference has no FFI on this path; the boundary is defined at its two
+ * Python call sites and the mathstats scalar functions, in the
+ * style of the reference's one ctypes precedent (BESST/diploid/wrapper_sw.py:12-24
+ * <-> BESST/diploid/lib/swmodule.cpp:20-28: ctypes.CDLL, extern "C", caller-
+ * allocated out-params, int return code, no exceptions).
+ *
+ *   entry point              replaces (reference file:line)
+ *   -----------------------  -------------------------------------------------
+ *   besst_set_contigs        the Contigs/Scaffolds/small_* dict lookups done per
+ *                            record in CreateGraph.py:118-130,170-206,819-829
+ *   besst_graph_build        CreateGraph.PE record loop :111-211, CreateEdge
+ *                            :812-871, PosDirCalculatorPE/MP :1024-1076, CheckDir
+ *                            :678-688, fishy counting :141-163, coverage :138-139,
+ *                            and the per-edge part of GiveScoreOnEdges :498-614
+ *   besst_graph_fetch        (marshalling of the above into caller memory)
+ *   besst_libmetrics         libmetrics.get_metrics sampling/trim/getdistr
+ *                            :283-356, get_contamination_metrics :49-131,
+ *                            bam_parser.is_proper_aligned_unique_innie/outie :22-29
+ *   besst_gapest_batch       mathstats param_est.GapEstimator / tr_sk_std_dev at
+ *                            CreateGraph.py:537,555; MakeScaffolds.py:449,453;
+ *                            order_contigs.py:300,308; pathgaps.py:108,204
+ *   besst_links_extract /    the two halves of besst_graph_build on either side
+ *   besst_links_to_graph     of the multi-GPU all-to-all
+ *
+ * Conventions: plain C; all pointers are caller-owned for the duration of the
+ * call; nothing is retained after return except inside the ctx; return 0 on
+ * success and a negative BESST_E_* code otherwise (message via
+ * besst_last_error); never exits or throws.  One ctx per process/GPU; a ctx is
+ * not thread-safe.
+ */
+#ifndef BESST_B200_H
+#define BESST_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BESST_ABI_VERSION 1
+
+#define BESST_OK 0
+#define BESST_E_INVALID -1  /* bad argument */
+#define BESST_E_CUDA -2     /* CUDA runtime error (message has the detail) */
+#define BESST_E_NOMEM -3
+#define BESST_E_STATE -4    /* call order violated (e.g. fetch before build) */
+#define BESST_E_NODEVICE -5 /* no usable CUDA device: there is NO CPU fallback */
+
+/* contig states (CreateGraph.py:127: "in Contigs or in small_contigs") */
+#define BESST_CTG_ABSENT 0
+#define BESST_CTG_LARGE 1 /* in Contigs, scaffold in Scaffolds */
+#define BESST_CTG_SMALL 2 /* in small_contigs, scaffold in small_scaffolds */
+
+/* One row per BAM reference id (tid).  32 bytes so a row is two 128-bit loads. */
+typedef struct besst_contig_row {
+    int32_t state;       /* BESST_CTG_* */
+    int32_t scaffold;    /* dense scaffold index: large scaffolds first, in the
+                            iteration order of the Scaffolds dict, then small ones */
+    int32_t direction;   /* Contig.direction (1 = True) */
+    int32_t position;    /* Contig.position */
+    int32_t length;      /* Contig.length */
+    int32_t scaf_length; /* Scaffold.s_length of its scaffold */
+    int32_t in_largest;  /* 1 if tid is among the 1000 longest references
+                            (libmetrics.py:231-233) */
+    int32_t reserved;
+} besst_contig_row;
+
+/* Struct-of-arrays record batch in BAM file order. */
+typedef struct besst_records {
+    int64_t n;
+    const int32_t* tid;   /* pysam rname */
+    const int32_t* mtid;  /* mrnm */
+    const int32_t* pos;
+    const int32_t* mpos;
+    const int32_t* tlen;  /* only read by besst_libmetrics */
+    const int32_t* qlen;
+    const uint16_t* flag;
+    const uint8_t* mapq;
+    int32_t on_device;    /* 0: host pointers (copied in), 1: device pointers */
+    int32_t reserved;
+} besst_records;
+
+#define BESST_ORIENT_FR 0
+#define BESST_ORIENT_RF 1
+#define BESST_ERF_AS7126 0 /* Abramowitz-Stegun 7.1.26, mathstats' erf */
+#define BESST_ERF_LIBM 1
+
+typedef struct besst_lib_params {
+    int32_t orientation;        /* BESST_ORIENT_* (param.orientation) */
+    int32_t min_mapq;           /* param.min_mapq */
+    int32_t detect_duplicate;   /* param.detect_duplicate */
+    int32_t extend_paths;       /* param.extend_paths */
+    int32_t no_score;           /* param.no_score */
+    int32_t erf_variant;        /* BESST_ERF_* */
+    double read_len;            /* param.read_len (may be non-integral) */
+    double mean_ins_size;       /* param.mean_ins_size */
+    double std_dev_ins_size;    /* param.std_dev_ins_size */
+    double ins_size_threshold;  /* param.ins_size_threshold */
+    /* multi-GPU halo: the (obs1,obs2) of the last CreateEdge call
+       made by any preceding rank, (-1,-1) for rank 0 / single GPU */
+    int32_t halo_prev_obs1;
+    int32_t halo_prev_obs2;
+} besst_lib_params;
+
+/* counters[] slots (Parameter.py:113-124 `counters`, CreateGraph.py:98-100) */
+#define BESST_CNT_COUNT 0           /* counter.count */
+#define BESST_CNT_NON_UNIQUE 1      /* counter.non_unique */
+#define BESST_CNT_NON_UNIQUE_SCAF 2 /* counter.non_unique_for_scaf */
+#define BESST_CNT_DUPLICATES 3      /* counter.nr_of_duplicates */
+#define BESST_CNT_TOO_LONG 4        /* counter.reads_with_too_long_insert */
+#define BESST_CNT_FISHY 5           /* ctr ("NR OF FISHY READ LINKS") */
+#define BESST_CNT_CALLS 6           /* records that reached CreateEdge */
+#define BESST_CNT_VALID 7           /* records with both contigs present */
+#define BESST_CNT_LAST_OBS1 8       /* (obs1,obs2) of the last CreateEdge call, */
+#define BESST_CNT_LAST_OBS2 9       /*   -1,-1 if none: the next rank's halo     */
+#define BESST_N_COUNTERS 16
+
+/* edge flags */
+#define BESST_EDGE_LL 1      /* both scaffolds large: edge of G (and of G_prime when extend_paths) */
+#define BESST_EDGE_SCORED 2  /* gap/score computed (LL edge and not no_score) */
+#define BESST_EDGE_NEGGAP 4  /* -gap > len: score = 0 and the per-scaffold lists are kept (CreateGraph.py:542-544) */
+#define BESST_EDGE_BIG 8     /* 2*sigma < len1 and 2*sigma < len2: GapEstimator used (:536) */
+#define BESST_EDGE_CPLX 16   /* (obs_sq - n*mean^2) < 0: reference would produce a complex sd (:561) */
+
+typedef struct besst_graph_sizes {
+    int64_t n_edges;   /* E: distinct link edges */
+    int64_t n_links;   /* Lk: accepted links = sum of nr_links */
+    int64_t n_contigs; /* C */
+    int64_t n_fishy;   /* distinct fishy node pairs */
+} besst_graph_sizes;
+
+/* Caller-allocated result arrays (host).  Edges are sorted by (edge_u, edge_v),
+ * edge_u < edge_v, node id = 2*scaffold + (side == 'R').  obs_u/obs_v are the
+ * per-scaffold observation lists (CreateGraph.py:848-849,853-854) in BAM order
+ * within each edge, obs_u on edge_u's scaffold; `observations` = obs_u+obs_v. */
+typedef struct besst_graph_out {
+    uint32_t* edge_u;    /* [E] */
+    uint32_t* edge_v;    /* [E] */
+    int32_t* nr_links;   /* [E] */
+    int64_t* obs_sum;    /* [E] 'obs' */
+    int64_t* obs_sq;     /* [E] 'obs_sq' */
+    int64_t* first_idx;  /* [E] ordinal (among accepted links, BAM order) of the
+                            edge's first link: edge insertion order */
+    int64_t* row_ptr;    /* [E+1] */
+    int32_t* gap;        /* [E] int(gap), valid if flags & SCORED */
+    double* score;       /* [E] valid if flags & SCORED */
+    double* ks;          /* [E] KS statistic (diagnostic), valid if SCORED and not NEGGAP */
+    double* sd_obs;      /* [E] sample sd (:561) */
+    double* sd_model;    /* [E] tr_sk_std_dev or 2**32 (:548-558) */
+    int32_t* fishy;      /* [E] fishy_edges count for this node pair (:161-162) */
+    uint8_t* flags;      /* [E] BESST_EDGE_* */
+    int32_t* obs_u;      /* [Lk] */
+    int32_t* obs_v;      /* [Lk] */
+    int64_t* aligned_len; /* [C] cont_aligned_len[contig][0] (:139) */
+    int64_t counters[BESST_N_COUNTERS];
+} besst_graph_out;
+
+/* Link tuple stream between the two halves (multi-GPU exchange unit, 16 B). */
+typedef struct besst_link_tuple {
+    uint32_t u;     /* canonical: u < v */
+    uint32_t v;
+    int32_t obs_u;
+    int32_t obs_v;
+} besst_link_tuple;
+
+typedef struct besst_libmetrics_out {
+    /* insert-size estimate (libmetrics.py:283-356); valid if want_isize */
+    int64_t n_samples;        /* len(ins_size_reads) before filtering */
+    int64_t n_trimmed;        /* after the AdjustInsertsizeDist loop */
+    double mean_before, sd_before;   /* :318-319 */
+    double mean_converged, sd_converged; /* :331-332 */
+    double skewness;          /* :340-341 */
+    double mu_adj, sigma_adj, skew_adj; /* getdistr :215-220 */
+    int64_t median_adj, mode_adj;       /* getdistr :189-211 */
+    int64_t n_bins;           /* len(adjusted_distribution) = max_isize+1 */
+    /* contamination (libmetrics.py:49-131) */
+    int64_t cont_mapped;      /* counter_total */
+    int64_t cont_n;           /* n_contamine after trim */
+    double cont_mean, cont_sd;
+    int64_t records_scanned;  /* records visited by the capped scans */
+} besst_libmetrics_out;
+
+typedef struct besst_ctx besst_ctx;
+
+int besst_abi_version(void);
+/* device < 0: use the current CUDA device */
+besst_ctx* besst_create(int device);
+void besst_destroy(besst_ctx* ctx);
+const char* besst_last_error(besst_ctx* ctx);
+
+int besst_set_contigs(besst_ctx* ctx, const besst_contig_row* rows, int64_t n_contigs,
+                      int64_t n_scaffolds, int64_t n_large_scaffolds);
+
+/* records -> CSR edges + per-edge statistics + gap/score, resident in HBM. */
+int besst_graph_build(besst_ctx* ctx, const besst_lib_params* params,
+                      const besst_records* records, besst_graph_sizes* sizes);
+/* copy the last build's result into caller-allocated host arrays */
+int besst_graph_fetch(besst_ctx* ctx, besst_graph_out* out);
+
+/* multi-GPU halves: extract leaves the accepted link tuples (BAM order) in HBM
+ * and reports how many; tuples_device returns the device pointer for the NCCL
+ * exchange; links_to_graph consumes an (exchanged) device tuple array. */
+int besst_links_extract(besst_ctx* ctx, const besst_lib_params* params,
+                        const besst_records* records, int64_t* n_tuples);
+int besst_links_tuples_device(besst_ctx* ctx, const besst_link_tuple** tuples, int64_t* n_tuples);
+int besst_links_fishy_device(besst_ctx* ctx, const uint64_t** keys, int64_t* n_keys);
+int besst_links_partials(besst_ctx* ctx, int64_t* aligned_len_host /*[C]*/, int64_t* counters_host /*[16]*/);
+int besst_links_to_graph(besst_ctx* ctx, const besst_lib_params* params,
+                         const besst_link_tuple* tuples_device, int64_t n_tuples,
+                         const uint64_t* fishy_keys_device, int64_t n_fishy_keys,
+                         besst_graph_sizes* sizes);
+
+/* library metrics: capped BAM-order sampling + histogram on the GPU, O(bins)
+ * statistics on the host side of the shim.  lengths = BAM header lengths.
+ * adjusted_distribution (optional, may be NULL) receives min(n_bins, cap) bins. */
+int besst_libmetrics(besst_ctx* ctx, const besst_lib_params* params, const besst_records* records,
+                     const int64_t* ref_lengths, int64_t n_refs, int32_t want_isize,
+                     besst_libmetrics_out* out, double* adjusted_distribution, int64_t cap);
+
+/* batched GapEstimator + tr_sk_std_dev (host arrays in, host arrays out) */
+int besst_gapest_batch(besst_ctx* ctx, const besst_lib_params* params, const double* mean_obs,
+                       const int32_t* len1, const int32_t* len2, int64_t n,
+                       int32_t* gap_out, double* sd_out);
+
+/* device-side timing of the last besst_graph_build, CUDA events on the
+ * library's stream: total and per-stage milliseconds */
+#define BESST_N_STAGES 8
+int besst_last_timing(besst_ctx* ctx, float* total_ms, float* stage_ms /*[BESST_N_STAGES]*/);
+int besst_kernel_launches(besst_ctx* ctx, int64_t* n_launches);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BESST_B200_H */
