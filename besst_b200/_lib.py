@@ -1,0 +1,62 @@
+"""ctypes loader for libbesst_b200.so -- the thin shim between the Python entry
+points and the CUDA engine, in the style of the reference's own ctypes
+precedent (BESST/diploid/wrapper_sw.py:12-24).  Fails loudly: there is no CPU
+fallback behind this module."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+from . import abi
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SO_PATH = os.path.join(HERE, "libbesst_b200.so")
+
+EXPORTS = ["besst_abi_version", "besst_create", "besst_destroy", "besst_last_error", "besst_set_contigs",
+           "besst_graph_build", "besst_graph_fetch", "besst_links_extract", "besst_links_tuples_device",
+           "besst_links_fishy_device", "besst_links_partials", "besst_links_to_graph", "besst_libmetrics",
+           "besst_gapest_batch", "besst_last_timing", "besst_kernel_launches"]
+
+_lib = None
+
+
+class BesstLibraryError(RuntimeError):
+    pass
+
+
+def load():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(SO_PATH):
+        raise BesstLibraryError(
+            "libbesst_b200.so is not built (%s). Build it with `python -m besst_b200.build` (needs nvcc, sm_100a). "
+            "There is no CPU fallback for this path." % SO_PATH)
+    L = C.CDLL(SO_PATH)
+    for name in EXPORTS:
+        if not hasattr(L, name):
+            raise BesstLibraryError("libbesst_b200.so does not export %s (stale build?)" % name)
+    vp, i64, i32 = C.c_void_p, C.c_int64, C.c_int32
+    L.besst_abi_version.restype = C.c_int
+    L.besst_create.restype = vp
+    L.besst_create.argtypes = [C.c_int]
+    L.besst_destroy.argtypes = [vp]
+    L.besst_last_error.restype = C.c_char_p
+    L.besst_last_error.argtypes = [vp]
+    L.besst_set_contigs.argtypes = [vp, vp, i64, i64, i64]
+    L.besst_graph_build.argtypes = [vp, C.POINTER(abi.LibParams), C.POINTER(abi.Records), C.POINTER(abi.GraphSizes)]
+    L.besst_graph_fetch.argtypes = [vp, C.POINTER(abi.GraphOut)]
+    L.besst_links_extract.argtypes = [vp, C.POINTER(abi.LibParams), C.POINTER(abi.Records), C.POINTER(i64)]
+    L.besst_links_tuples_device.argtypes = [vp, C.POINTER(vp), C.POINTER(i64)]
+    L.besst_links_fishy_device.argtypes = [vp, C.POINTER(vp), C.POINTER(i64)]
+    L.besst_links_partials.argtypes = [vp, vp, vp]
+    L.besst_links_to_graph.argtypes = [vp, C.POINTER(abi.LibParams), vp, i64, vp, i64, C.POINTER(abi.GraphSizes)]
+    L.besst_libmetrics.argtypes = [vp, C.POINTER(abi.LibParams), C.POINTER(abi.Records), vp, i64, i32,
+                                   C.POINTER(abi.LibMetricsOut), vp, i64]
+    L.besst_gapest_batch.argtypes = [vp, C.POINTER(abi.LibParams), vp, vp, vp, i64, vp, vp]
+    L.besst_last_timing.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_float)]
+    L.besst_kernel_launches.argtypes = [vp, C.POINTER(i64)]
+    if L.besst_abi_version() != abi.ABI_VERSION:
+        raise BesstLibraryError("ABI version mismatch: library %d, binding %d" % (L.besst_abi_version(), abi.ABI_VERSION))
+    _lib = L
+    return L

@@ -1,0 +1,57 @@
+"""Build libbesst_b200.so in-tree with nvcc for sm_100a (no JIT cache: the .so
+travels with the source tree).  `python -m besst_b200.build`"""
+from __future__ import annotations
+
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+SO = os.path.join(HERE, "libbesst_b200.so")
+ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
+COMMON = ["-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
+# per-file extra flags: the scoring math must round like the reference (no FMA contraction)
+SOURCES = [("besst_api.cu", []), ("besst_links.cu", []), ("besst_sort.cu", []),
+           ("besst_edges.cu", ["-fmad=false"]), ("besst_metrics.cu", [])]
+
+
+def _stale(target, deps):
+    if not os.path.exists(target):
+        return True
+    t = os.path.getmtime(target)
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build(force=False, verbose=False):
+    nvcc = os.environ.get("NVCC", "nvcc")
+    headers = [os.path.join(CSRC, "besst_internal.cuh"), os.path.join(HERE, "..", "include", "besst_b200.h")]
+    objdir = os.path.join(CSRC, "_obj")
+    os.makedirs(objdir, exist_ok=True)
+    objs, log = [], []
+    for name, extra in SOURCES:
+        src = os.path.join(CSRC, name)
+        obj = os.path.join(objdir, name.replace(".cu", ".o"))
+        if force or _stale(obj, [src] + headers):
+            cmd = [nvcc] + ARCH + COMMON + extra + ["-c", src, "-o", obj]
+            r = subprocess.run(cmd, capture_output=True, text=True)
+            log.append(r.stderr)
+            if r.returncode != 0:
+                sys.stderr.write(r.stdout + r.stderr)
+                raise RuntimeError("nvcc failed on %s" % name)
+            if verbose:
+                sys.stderr.write(r.stderr)
+        objs.append(obj)
+    if force or _stale(SO, objs):
+        cmd = [nvcc] + ARCH + ["-shared", "-o", SO] + objs
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            sys.stderr.write(r.stdout + r.stderr)
+            raise RuntimeError("link failed")
+    with open(os.path.join(objdir, "ptxas.log"), "a") as fh:
+        fh.write("".join(log))
+    return SO
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose=True))

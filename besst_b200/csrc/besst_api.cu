@@ -1,0 +1,280 @@
+// C ABI of libbesst_b200.so (include/besst_b200.h).  Host-side glue only: device
+// buffers, H2D/D2H marshalling, stage ordering on one CUDA stream, CUDA-event
+// timing.  There is no CPU implementation behind these entry points: without a
+// CUDA device besst_create fails.
+#include <string.h>
+
+#include <vector>
+
+#include "besst_internal.cuh"
+
+static thread_local std::string g_create_error;
+
+extern "C" int besst_abi_version(void) { return BESST_ABI_VERSION; }
+
+extern "C" besst_ctx* besst_create(int device) {
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        g_create_error = std::string("no usable CUDA device: ") + (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+        return nullptr;
+    }
+    if (device >= 0) {
+        e = cudaSetDevice(device);
+        if (e != cudaSuccess) { g_create_error = std::string("cudaSetDevice: ") + cudaGetErrorString(e); return nullptr; }
+    } else {
+        cudaGetDevice(&device);
+    }
+    besst_ctx* ctx = new besst_ctx();
+    ctx->device = device;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->sm_count = prop.multiProcessorCount;
+    e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) { g_create_error = std::string("cudaStreamCreate: ") + cudaGetErrorString(e); delete ctx; return nullptr; }
+    for (int i = 0; i <= BESST_N_STAGES; ++i) cudaEventCreate(&ctx->ev[i]);
+    return ctx;
+}
+
+extern "C" void besst_destroy(besst_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    DBuf* bufs[] = {&ctx->rows, &ctx->scaf_len, &ctx->rec_flag, &ctx->rec_mapq, &ctx->tuples, &ctx->fishy_keys, &ctx->aligned,
+                    &ctx->counters, &ctx->tile_state, &ctx->misc, &ctx->key_a, &ctx->key_b, &ctx->idx_a, &ctx->idx_b, &ctx->hist,
+                    &ctx->sort_state, &ctx->fishy_sorted, &ctx->fishy_tmp, &ctx->heads, &ctx->block_sums, &ctx->e_u, &ctx->e_v,
+                    &ctx->e_nr, &ctx->e_obs, &ctx->e_obs_sq, &ctx->e_first, &ctx->e_row_ptr, &ctx->e_gap, &ctx->e_score,
+                    &ctx->e_ks, &ctx->e_sd_obs, &ctx->e_sd_model, &ctx->e_fishy, &ctx->e_flags, &ctx->l_obs_u, &ctx->l_obs_v,
+                    &ctx->big_list, &ctx->big_scratch};
+    for (DBuf* b : bufs) b->release();
+    for (DBuf& b : ctx->rec_i32) b.release();
+    for (int i = 0; i <= BESST_N_STAGES; ++i) cudaEventDestroy(ctx->ev[i]);
+    cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+extern "C" const char* besst_last_error(besst_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+extern "C" int besst_set_contigs(besst_ctx* ctx, const besst_contig_row* rows, int64_t n_contigs, int64_t n_scaffolds,
+                                 int64_t n_large_scaffolds) {
+    if (!ctx) return BESST_E_INVALID;
+    if (n_contigs < 0 || n_scaffolds < 0 || n_large_scaffolds < 0 || n_large_scaffolds > n_scaffolds || (n_contigs > 0 && !rows) ||
+        n_scaffolds >= (1ll << 30) || n_contigs >= (1ll << 31)) {
+        ctx->err = "besst_set_contigs: bad sizes";
+        return BESST_E_INVALID;
+    }
+    std::vector<int32_t> slen((size_t)(n_scaffolds > 0 ? n_scaffolds : 1), 0);
+    for (int64_t c = 0; c < n_contigs; ++c) {
+        if (rows[c].state == BESST_CTG_ABSENT) continue;
+        if (rows[c].scaffold < 0 || rows[c].scaffold >= n_scaffolds) { ctx->err = "besst_set_contigs: scaffold index out of range"; return BESST_E_INVALID; }
+        slen[(size_t)rows[c].scaffold] = rows[c].scaf_length;
+    }
+    cudaSetDevice(ctx->device);
+    BESST_CUDA_TRY(ctx, ctx->rows.ensure(sizeof(besst_contig_row) * (size_t)(n_contigs > 0 ? n_contigs : 1)));
+    BESST_CUDA_TRY(ctx, ctx->scaf_len.ensure(4 * slen.size()));
+    if (n_contigs > 0)
+        BESST_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->rows.p, rows, sizeof(besst_contig_row) * (size_t)n_contigs, cudaMemcpyHostToDevice, ctx->stream));
+    BESST_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->scaf_len.p, slen.data(), 4 * slen.size(), cudaMemcpyHostToDevice, ctx->stream));
+    BESST_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->n_contigs = n_contigs; ctx->n_scaffolds = n_scaffolds; ctx->n_large = n_large_scaffolds;
+    ctx->have_links = ctx->have_graph = false;
+    return BESST_OK;
+}
+
+// host -> device staging of a record batch (no-op for device-resident batches)
+static int stage_records(besst_ctx* ctx, const besst_records* r, DeviceRecords* d, bool need_tlen, bool need_graph_cols) {
+    if (!r || r->n < 0) { ctx->err = "records: null or negative n"; return BESST_E_INVALID; }
+    d->n = r->n;
+    if (r->n > 0 && (!r->tid || !r->mtid || !r->flag || !r->mapq || (need_tlen && !r->tlen) ||
+                     (need_graph_cols && (!r->pos || !r->mpos || !r->qlen)))) {
+        ctx->err = "records: missing column";
+        return BESST_E_INVALID;
+    }
+    if (r->on_device) {
+        d->tid = r->tid; d->mtid = r->mtid; d->pos = r->pos; d->mpos = r->mpos; d->tlen = r->tlen; d->qlen = r->qlen;
+        d->flag = r->flag; d->mapq = r->mapq;
+        return BESST_OK;
+    }
+    const size_t n = (size_t)r->n, nz = n ? n : 1;
+    const int32_t* src[6] = {r->tid, r->mtid, r->pos, r->mpos, r->tlen, r->qlen};
+    const int32_t** dst[6] = {&d->tid, &d->mtid, &d->pos, &d->mpos, &d->tlen, &d->qlen};
+    for (int k = 0; k < 6; ++k) {
+        *dst[k] = nullptr;
+        if (!src[k]) continue;
+        BESST_CUDA_TRY(ctx, ctx->rec_i32[k].ensure(4 * nz));
+        if (n) BESST_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->rec_i32[k].p, src[k], 4 * n, cudaMemcpyHostToDevice, ctx->stream));
+        *dst[k] = ctx->rec_i32[k].as<int32_t>();
+    }
+    BESST_CUDA_TRY(ctx, ctx->rec_flag.ensure(2 * nz));
+    BESST_CUDA_TRY(ctx, ctx->rec_mapq.ensure(nz));
+    if (n) {
+        BESST_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->rec_flag.p, r->flag, 2 * n, cudaMemcpyHostToDevice, ctx->stream));
+        BESST_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->rec_mapq.p, r->mapq, n, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    d->flag = ctx->rec_flag.as<uint16_t>();
+    d->mapq = ctx->rec_mapq.as<uint8_t>();
+    return BESST_OK;
+}
+
+static int check_params(besst_ctx* ctx, const besst_lib_params* p) {
+    if (!p) { ctx->err = "params: null"; return BESST_E_INVALID; }
+    if (p->orientation != BESST_ORIENT_FR && p->orientation != BESST_ORIENT_RF) { ctx->err = "params: orientation must be fr or rf"; return BESST_E_INVALID; }
+    return BESST_OK;
+}
+
+extern "C" int besst_links_extract(besst_ctx* ctx, const besst_lib_params* params, const besst_records* records, int64_t* n_tuples) {
+    if (!ctx) return BESST_E_INVALID;
+    int rc = check_params(ctx, params);
+    if (rc) return rc;
+    cudaSetDevice(ctx->device);
+    ctx->have_links = ctx->have_graph = false;
+    ctx->n_stage_marks = 0;
+    besst_mark(ctx);
+    DeviceRecords d;
+    rc = stage_records(ctx, records, &d, false, true);
+    if (rc) return rc;
+    rc = besst_launch_extract(ctx, *params, d);
+    if (rc) return rc;
+    besst_mark(ctx);
+    if (n_tuples) *n_tuples = ctx->n_tuples;
+    return BESST_OK;
+}
+
+extern "C" int besst_links_tuples_device(besst_ctx* ctx, const besst_link_tuple** tuples, int64_t* n_tuples) {
+    if (!ctx || !ctx->have_links) { if (ctx) ctx->err = "no extracted links"; return BESST_E_STATE; }
+    *tuples = ctx->tuples.as<besst_link_tuple>();
+    *n_tuples = ctx->n_tuples;
+    return BESST_OK;
+}
+
+extern "C" int besst_links_fishy_device(besst_ctx* ctx, const uint64_t** keys, int64_t* n_keys) {
+    if (!ctx || !ctx->have_links) { if (ctx) ctx->err = "no extracted links"; return BESST_E_STATE; }
+    *keys = ctx->fishy_keys.as<uint64_t>();
+    *n_keys = ctx->n_fishy_keys;
+    return BESST_OK;
+}
+
+extern "C" int besst_links_partials(besst_ctx* ctx, int64_t* aligned_len_host, int64_t* counters_host) {
+    if (!ctx || !ctx->have_links) { if (ctx) ctx->err = "no extracted links"; return BESST_E_STATE; }
+    cudaSetDevice(ctx->device);
+    if (aligned_len_host && ctx->n_contigs > 0)
+        BESST_CUDA_TRY(ctx, cudaMemcpyAsync(aligned_len_host, ctx->aligned.p, 8 * (size_t)ctx->n_contigs, cudaMemcpyDeviceToHost, ctx->stream));
+    if (counters_host)
+        BESST_CUDA_TRY(ctx, cudaMemcpyAsync(counters_host, ctx->counters.p, 8 * BESST_N_COUNTERS, cudaMemcpyDeviceToHost, ctx->stream));
+    BESST_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return BESST_OK;
+}
+
+extern "C" int besst_links_to_graph(besst_ctx* ctx, const besst_lib_params* params, const besst_link_tuple* tuples_device,
+                                    int64_t n_tuples, const uint64_t* fishy_keys_device, int64_t n_fishy_keys,
+                                    besst_graph_sizes* sizes) {
+    if (!ctx) return BESST_E_INVALID;
+    int rc = check_params(ctx, params);
+    if (rc) return rc;
+    if (n_tuples < 0 || n_fishy_keys < 0 || (n_tuples > 0 && !tuples_device) || (n_fishy_keys > 0 && !fishy_keys_device)) {
+        ctx->err = "links_to_graph: bad arguments";
+        return BESST_E_INVALID;
+    }
+    cudaSetDevice(ctx->device);
+    rc = besst_launch_graph(ctx, *params, tuples_device, n_tuples, fishy_keys_device, n_fishy_keys);
+    if (rc) return rc;
+    if (sizes) {
+        sizes->n_edges = ctx->n_edges; sizes->n_links = ctx->n_links; sizes->n_contigs = ctx->n_contigs;
+        sizes->n_fishy = n_fishy_keys;
+    }
+    return BESST_OK;
+}
+
+extern "C" int besst_graph_build(besst_ctx* ctx, const besst_lib_params* params, const besst_records* records,
+                                 besst_graph_sizes* sizes) {
+    int64_t n = 0;
+    int rc = besst_links_extract(ctx, params, records, &n);
+    if (rc) return rc;
+    rc = besst_links_to_graph(ctx, params, ctx->tuples.as<besst_link_tuple>(), ctx->n_tuples, ctx->fishy_keys.as<uint64_t>(),
+                              ctx->n_fishy_keys, sizes);
+    if (rc) return rc;
+    ctx->ev_valid = true;
+    return BESST_OK;
+}
+
+extern "C" int besst_graph_fetch(besst_ctx* ctx, besst_graph_out* out) {
+    if (!ctx || !out) return BESST_E_INVALID;
+    if (!ctx->have_graph) { ctx->err = "besst_graph_fetch before a successful build"; return BESST_E_STATE; }
+    cudaSetDevice(ctx->device);
+    const size_t E = (size_t)ctx->n_edges, L = (size_t)ctx->n_links, C = (size_t)ctx->n_contigs;
+#define FETCH(field, buf, bytes)                                                                                      \
+    if (out->field && (bytes) > 0)                                                                                   \
+        BESST_CUDA_TRY(ctx, cudaMemcpyAsync(out->field, ctx->buf.p, (bytes), cudaMemcpyDeviceToHost, ctx->stream))
+    FETCH(edge_u, e_u, 4 * E); FETCH(edge_v, e_v, 4 * E); FETCH(nr_links, e_nr, 4 * E);
+    FETCH(obs_sum, e_obs, 8 * E); FETCH(obs_sq, e_obs_sq, 8 * E); FETCH(first_idx, e_first, 8 * E);
+    FETCH(row_ptr, e_row_ptr, 8 * (E + 1)); FETCH(gap, e_gap, 4 * E); FETCH(score, e_score, 8 * E);
+    FETCH(ks, e_ks, 8 * E); FETCH(sd_obs, e_sd_obs, 8 * E); FETCH(sd_model, e_sd_model, 8 * E);
+    FETCH(fishy, e_fishy, 4 * E); FETCH(flags, e_flags, E); FETCH(obs_u, l_obs_u, 4 * L); FETCH(obs_v, l_obs_v, 4 * L);
+#undef FETCH
+    if (out->aligned_len && C > 0 && ctx->have_links)
+        BESST_CUDA_TRY(ctx, cudaMemcpyAsync(out->aligned_len, ctx->aligned.p, 8 * C, cudaMemcpyDeviceToHost, ctx->stream));
+    memset(out->counters, 0, sizeof(out->counters));
+    if (ctx->have_links)
+        BESST_CUDA_TRY(ctx, cudaMemcpyAsync(out->counters, ctx->counters.p, 8 * BESST_N_COUNTERS, cudaMemcpyDeviceToHost, ctx->stream));
+    BESST_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return BESST_OK;
+}
+
+extern "C" int besst_gapest_batch(besst_ctx* ctx, const besst_lib_params* params, const double* mean_obs, const int32_t* len1,
+                                  const int32_t* len2, int64_t n, int32_t* gap_out, double* sd_out) {
+    if (!ctx) return BESST_E_INVALID;
+    int rc = check_params(ctx, params);
+    if (rc) return rc;
+    if (n < 0 || (n > 0 && (!mean_obs || !len1 || !len2 || !gap_out))) { ctx->err = "gapest_batch: bad arguments"; return BESST_E_INVALID; }
+    if (n == 0) return BESST_OK;
+    cudaSetDevice(ctx->device);
+    const size_t nn = (size_t)n;
+    BESST_CUDA_TRY(ctx, ctx->misc.ensure(nn * (8 + 4 + 4 + 4 + 8) + 64));
+    unsigned char* base = ctx->misc.as<unsigned char>();
+    double* d_mo = reinterpret_cast<double*>(base);
+    double* d_sd = reinterpret_cast<double*>(base + 8 * nn);
+    int32_t* d_l1 = reinterpret_cast<int32_t*>(base + 16 * nn);
+    int32_t* d_l2 = d_l1 + nn;
+    int32_t* d_gap = d_l2 + nn;
+    BESST_CUDA_TRY(ctx, cudaMemcpyAsync(d_mo, mean_obs, 8 * nn, cudaMemcpyHostToDevice, ctx->stream));
+    BESST_CUDA_TRY(ctx, cudaMemcpyAsync(d_l1, len1, 4 * nn, cudaMemcpyHostToDevice, ctx->stream));
+    BESST_CUDA_TRY(ctx, cudaMemcpyAsync(d_l2, len2, 4 * nn, cudaMemcpyHostToDevice, ctx->stream));
+    rc = besst_launch_gapest(ctx, *params, d_mo, d_l1, d_l2, n, d_gap, d_sd);
+    if (rc) return rc;
+    BESST_CUDA_TRY(ctx, cudaMemcpyAsync(gap_out, d_gap, 4 * nn, cudaMemcpyDeviceToHost, ctx->stream));
+    if (sd_out) BESST_CUDA_TRY(ctx, cudaMemcpyAsync(sd_out, d_sd, 8 * nn, cudaMemcpyDeviceToHost, ctx->stream));
+    BESST_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return BESST_OK;
+}
+
+extern "C" int besst_libmetrics(besst_ctx* ctx, const besst_lib_params* params, const besst_records* records,
+                                const int64_t* ref_lengths, int64_t n_refs, int32_t want_isize, besst_libmetrics_out* out,
+                                double* adjusted_distribution, int64_t cap) {
+    if (!ctx) return BESST_E_INVALID;
+    int rc = check_params(ctx, params);
+    if (rc) return rc;
+    if (!out || !ref_lengths || n_refs <= 0) { ctx->err = "libmetrics: bad arguments"; return BESST_E_INVALID; }
+    cudaSetDevice(ctx->device);
+    DeviceRecords d;
+    rc = stage_records(ctx, records, &d, true, false);
+    if (rc) return rc;
+    return besst_launch_libmetrics(ctx, *params, d, ref_lengths, n_refs, want_isize, out, adjusted_distribution, cap);
+}
+
+extern "C" int besst_last_timing(besst_ctx* ctx, float* total_ms, float* stage_ms) {
+    if (!ctx || !ctx->ev_valid || ctx->n_stage_marks < 2) { if (ctx) ctx->err = "no timed build"; return BESST_E_STATE; }
+    cudaSetDevice(ctx->device);
+    BESST_CUDA_TRY(ctx, cudaEventSynchronize(ctx->ev[ctx->n_stage_marks - 1]));
+    if (total_ms) BESST_CUDA_TRY(ctx, cudaEventElapsedTime(total_ms, ctx->ev[0], ctx->ev[ctx->n_stage_marks - 1]));
+    if (stage_ms)
+        for (int i = 0; i < BESST_N_STAGES; ++i) {
+            stage_ms[i] = 0.f;
+            if (i + 1 < ctx->n_stage_marks) BESST_CUDA_TRY(ctx, cudaEventElapsedTime(&stage_ms[i], ctx->ev[i], ctx->ev[i + 1]));
+        }
+    return BESST_OK;
+}
+
+extern "C" int besst_kernel_launches(besst_ctx* ctx, int64_t* n_launches) {
+    if (!ctx || !n_launches) return BESST_E_INVALID;
+    *n_launches = ctx->launches;
+    return BESST_OK;
+}

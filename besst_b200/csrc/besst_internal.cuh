@@ -1,0 +1,130 @@
+// Internal declarations shared by the .cu translation units of libbesst_b200.so.
+// Nothing here crosses the C ABI (include/besst_b200.h).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+
+#include "../../include/besst_b200.h"
+
+#define BESST_CUDA_TRY(ctx, expr)                                                           \
+    do {                                                                                    \
+        cudaError_t _e = (expr);                                                            \
+        if (_e != cudaSuccess) {                                                            \
+            (ctx)->err = std::string(#expr) + ": " + cudaGetErrorString(_e);                \
+            return BESST_E_CUDA;                                                            \
+        }                                                                                   \
+    } while (0)
+
+// grow-only device buffer
+struct DBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+    template <typename T>
+    T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+struct DeviceRecords {
+    int64_t n;
+    const int32_t *tid, *mtid, *pos, *mpos, *tlen, *qlen;
+    const uint16_t* flag;
+    const uint8_t* mapq;
+};
+
+// scalar constants of the per-edge scoring math, evaluated once on the host
+// with the same libm calls the oracle makes (pow), so both sides start from
+// identical fp64 values
+struct ScoreConsts {
+    double mean, sd, r;
+    double s2;        // 2**0.5 * sd
+    double v2;        // 2 * sd**2
+    double k;         // sd / (2*pi)**0.5
+    double gb_den;    // (2*pi)**0.5 * sd
+    double sd2, sd4, mean2;
+    double d_upper0, d_lower0;  // bisection bracket of GapEstimator
+    int erf_variant;
+};
+
+struct besst_ctx {
+    int device = 0;
+    int sm_count = 148;
+    cudaStream_t stream = nullptr;
+    std::string err;
+
+    // contig table
+    DBuf rows, scaf_len;
+    int64_t n_contigs = 0, n_scaffolds = 0, n_large = 0;
+
+    // staged records (host-pointer calls)
+    DBuf rec_i32[6], rec_flag, rec_mapq;
+
+    // link extraction
+    DBuf tuples, fishy_keys, aligned, counters, tile_state, misc;
+    int64_t tuples_cap = 0, fishy_cap = 0;
+    int64_t n_tuples = 0, n_fishy_keys = 0;
+    bool have_links = false;
+
+    // sort
+    DBuf key_a, key_b, idx_a, idx_b, hist, sort_state;
+
+    // CSR / per-edge results
+    DBuf fishy_sorted, fishy_tmp, heads, block_sums;
+    DBuf e_u, e_v, e_nr, e_obs, e_obs_sq, e_first, e_row_ptr, e_gap, e_score, e_ks, e_sd_obs, e_sd_model, e_fishy,
+        e_flags, l_obs_u, l_obs_v, big_list, big_scratch;
+    int64_t n_edges = 0, n_links = 0, n_fishy_pairs = 0;
+    bool have_graph = false;
+    besst_lib_params last_params;
+
+    // timing
+    cudaEvent_t ev[BESST_N_STAGES + 1];
+    bool ev_valid = false;
+    int n_stage_marks = 0;
+    int64_t launches = 0;
+};
+
+// ---- launchers (one per translation unit) ----------------------------------
+// links: records -> accepted link tuples (BAM order), coverage, fishy keys, counters
+int besst_launch_extract(besst_ctx* ctx, const besst_lib_params& p, const DeviceRecords& rec);
+
+// sort + CSR: tuples -> sorted (key, idx) -> edges
+int besst_launch_graph(besst_ctx* ctx, const besst_lib_params& p, const besst_link_tuple* d_tuples, int64_t n_tuples,
+                       const uint64_t* d_fishy, int64_t n_fishy);
+
+// radix sort of 64-bit keys with 32-bit payload (onesweep); returns which buffer holds the result
+int besst_radix_sort_pairs(besst_ctx* ctx, uint64_t* keys_a, uint64_t* keys_b, uint32_t* val_a, uint32_t* val_b,
+                           int64_t n, int key_bits, int* result_in_b);
+int besst_radix_sort_keys(besst_ctx* ctx, uint64_t* keys_a, uint64_t* keys_b, int64_t n, int key_bits,
+                          int* result_in_b);
+
+// per-edge statistics, KS, GapEst, score
+int besst_launch_edge_stats(besst_ctx* ctx, const besst_lib_params& p, const besst_link_tuple* d_tuples,
+                            const uint64_t* d_sorted_keys, const uint32_t* d_sorted_idx, int64_t n_links, int key_shift);
+int besst_launch_gapest(besst_ctx* ctx, const besst_lib_params& p, const double* d_mean_obs, const int32_t* d_len1,
+                        const int32_t* d_len2, int64_t n, int32_t* d_gap, double* d_sd);
+
+ScoreConsts besst_score_consts(const besst_lib_params& p);
+
+int besst_launch_libmetrics(besst_ctx* ctx, const besst_lib_params& p, const DeviceRecords& rec,
+                            const int64_t* ref_lengths, int64_t n_refs, int32_t want_isize, besst_libmetrics_out* out,
+                            double* adjusted_distribution, int64_t cap);
+
+static inline void besst_mark(besst_ctx* ctx) {
+    if (ctx->n_stage_marks <= BESST_N_STAGES) cudaEventRecord(ctx->ev[ctx->n_stage_marks++], ctx->stream);
+}

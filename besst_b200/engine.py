@@ -1,0 +1,150 @@
+"""CUDA engine: the Python face of the C ABI (one ctx per process / GPU)."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import abi
+from ._lib import BesstLibraryError, load
+
+STAGE_NAMES = ["extract_links", "radix_bucket", "segment_heads", "edge_reduce", "ks_gapest_score"]
+
+
+class CudaEngine(object):
+    name = "cuda"
+
+    def __init__(self, device=-1):
+        self._L = load()
+        self._ctx = self._L.besst_create(int(device))
+        if not self._ctx:
+            raise BesstLibraryError("besst_create failed: %s (no CPU fallback)"
+                                    % self._L.besst_last_error(None).decode())
+        self._table_id = None
+
+    def close(self):
+        if getattr(self, "_ctx", None):
+            self._L.besst_destroy(self._ctx)
+            self._ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc, what):
+        if rc < 0:
+            raise BesstLibraryError("%s failed (%d, %s): %s" % (
+                what, rc, abi.ERRORS.get(rc, "?"), self._L.besst_last_error(self._ctx).decode()))
+        return rc
+
+    # -- contig table ---------------------------------------------------------------
+    def set_contigs(self, rows, n_scaffolds, n_large_scaffolds):
+        rows = np.ascontiguousarray(rows, dtype=abi.CONTIG_ROW_DTYPE)
+        self._check(self._L.besst_set_contigs(self._ctx, rows.ctypes.data, rows.shape[0], int(n_scaffolds),
+                                              int(n_large_scaffolds)), "besst_set_contigs")
+        self._n_contigs = rows.shape[0]
+
+    def set_table(self, table):
+        self.set_contigs(table.rows, table.n_scaffolds, table.n_large_scaffolds)
+
+    # -- graph build ------------------------------------------------------------------
+    def build(self, params, records):
+        """records: abi.Records (host or device pointers).  Leaves the result in HBM."""
+        sizes = abi.GraphSizes()
+        self._check(self._L.besst_graph_build(self._ctx, C.byref(params), C.byref(records), C.byref(sizes)),
+                    "besst_graph_build")
+        return sizes
+
+    def fetch(self, sizes):
+        out, arrays = abi.alloc_graph_out(sizes)
+        self._check(self._L.besst_graph_fetch(self._ctx, C.byref(out)), "besst_graph_fetch")
+        return abi.graph_result(out, arrays)
+
+    def graph_build(self, table, params, batch):
+        """Host-buffer call used by CreateGraph.PE: table + RecordBatch in, GraphResult out."""
+        self.set_table(table)
+        keep = []
+        rec = abi.make_records(batch, keepalive=keep)
+        sizes = self.build(params, rec)
+        return self.fetch(sizes)
+
+    # -- the two halves around the multi-GPU exchange --------------------------------------
+    def links_extract(self, params, records):
+        n = C.c_int64()
+        self._check(self._L.besst_links_extract(self._ctx, C.byref(params), C.byref(records), C.byref(n)),
+                    "besst_links_extract")
+        return n.value
+
+    def links_device(self):
+        p, n = C.c_void_p(), C.c_int64()
+        self._check(self._L.besst_links_tuples_device(self._ctx, C.byref(p), C.byref(n)), "besst_links_tuples_device")
+        fp, fn = C.c_void_p(), C.c_int64()
+        self._check(self._L.besst_links_fishy_device(self._ctx, C.byref(fp), C.byref(fn)), "besst_links_fishy_device")
+        return (p.value or 0, n.value), (fp.value or 0, fn.value)
+
+    def links_partials(self):
+        aligned = np.zeros(self._n_contigs, dtype=np.int64)
+        counters = np.zeros(abi.N_COUNTERS, dtype=np.int64)
+        self._check(self._L.besst_links_partials(self._ctx, aligned.ctypes.data, counters.ctypes.data),
+                    "besst_links_partials")
+        return aligned, counters
+
+    def links_to_graph(self, params, tuples_ptr, n_tuples, fishy_ptr, n_fishy):
+        sizes = abi.GraphSizes()
+        self._check(self._L.besst_links_to_graph(self._ctx, C.byref(params), tuples_ptr, int(n_tuples), fishy_ptr,
+                                                 int(n_fishy), C.byref(sizes)), "besst_links_to_graph")
+        return sizes
+
+    # -- library metrics ------------------------------------------------------------------
+    def libmetrics(self, rows, params, batch, ref_lengths, want_isize, cap=1 << 20, records=None):
+        """-> (rc, abi.LibMetricsOut, adjusted_distribution).  rc == 1: fewer than
+        1001 insert-size samples (libmetrics.py:311-314)."""
+        self.set_contigs(rows, 1, 0)
+        keep = []
+        rec = records if records is not None else abi.make_records(batch, keepalive=keep)
+        lens = np.ascontiguousarray(ref_lengths, dtype=np.int64)
+        out = abi.LibMetricsOut()
+        adj = np.zeros(cap, dtype=np.float64)
+        rc = self._check(self._L.besst_libmetrics(self._ctx, C.byref(params), C.byref(rec), lens.ctypes.data,
+                                                  lens.shape[0], int(want_isize), C.byref(out), adj.ctypes.data, cap),
+                         "besst_libmetrics")
+        return rc, out, adj[:min(cap, out.n_bins)]
+
+    # -- batched GapEstimator --------------------------------------------------------------
+    def gapest_batch(self, params, mean_obs, len1, len2):
+        mean_obs = np.ascontiguousarray(mean_obs, dtype=np.float64)
+        len1 = np.ascontiguousarray(len1, dtype=np.int32)
+        len2 = np.ascontiguousarray(len2, dtype=np.int32)
+        gap = np.zeros(mean_obs.shape[0], dtype=np.int32)
+        sd = np.zeros(mean_obs.shape[0], dtype=np.float64)
+        self._check(self._L.besst_gapest_batch(self._ctx, C.byref(params), mean_obs.ctypes.data, len1.ctypes.data,
+                                               len2.ctypes.data, mean_obs.shape[0], gap.ctypes.data, sd.ctypes.data),
+                    "besst_gapest_batch")
+        return gap, sd
+
+    # -- timing / accounting -------------------------------------------------------------
+    def timing(self):
+        total = C.c_float()
+        stages = (C.c_float * abi.N_STAGES)()
+        self._check(self._L.besst_last_timing(self._ctx, C.byref(total), stages), "besst_last_timing")
+        return total.value, dict(zip(STAGE_NAMES, list(stages)[:len(STAGE_NAMES)]))
+
+    def kernel_launches(self):
+        n = C.c_int64()
+        self._check(self._L.besst_kernel_launches(self._ctx, C.byref(n)), "besst_kernel_launches")
+        return n.value
+
+
+_default = None
+
+
+def default_engine():
+    """Process-wide engine on the current CUDA device.  Raises if the CUDA
+    library or a GPU is missing -- the product path never falls back to a CPU
+    implementation."""
+    global _default
+    if _default is None:
+        _default = CudaEngine()
+    return _default
