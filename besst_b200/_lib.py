@@ -15,7 +15,8 @@ SO_PATH = os.path.join(HERE, "libbesst_b200.so")
 EXPORTS = ["besst_abi_version", "besst_create", "besst_destroy", "besst_last_error", "besst_set_contigs",
            "besst_graph_build", "besst_graph_fetch", "besst_links_extract", "besst_links_tuples_device",
            "besst_links_fishy_device", "besst_links_partials", "besst_links_to_graph", "besst_libmetrics",
-           "besst_gapest_batch", "besst_last_timing", "besst_kernel_launches"]
+           "besst_gapest_batch", "besst_last_timing", "besst_kernel_launches", "besst_set_profiling",
+           "besst_kernel_profile"]
 
 _lib = None
 
@@ -56,6 +57,8 @@ def load():
     L.besst_gapest_batch.argtypes = [vp, C.POINTER(abi.LibParams), vp, vp, vp, i64, vp, vp]
     L.besst_last_timing.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_float)]
     L.besst_kernel_launches.argtypes = [vp, C.POINTER(i64)]
+    L.besst_set_profiling.argtypes = [vp, C.c_int]
+    L.besst_kernel_profile.argtypes = [vp, vp, vp, i32]
     if L.besst_abi_version() != abi.ABI_VERSION:
         raise BesstLibraryError("ABI version mismatch: library %d, binding %d" % (L.besst_abi_version(), abi.ABI_VERSION))
     _lib = L

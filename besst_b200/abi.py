@@ -101,7 +101,7 @@ class GraphResult:
 def alloc_graph_out(sizes):
     """Allocate numpy result arrays for `sizes` and a GraphOut pointing at them."""
     dims = {"E": int(sizes.n_edges), "E1": int(sizes.n_edges) + 1, "L": int(sizes.n_links), "C": int(sizes.n_contigs)}
-    arrays = {name: np.zeros(dims[d], dtype=dt) for name, dt, d in _GRAPH_FIELDS}
+    arrays = {name: np.empty(dims[d], dtype=dt) for name, dt, d in _GRAPH_FIELDS}
     out = GraphOut()
     for name, _, _ in _GRAPH_FIELDS:
         setattr(out, name, arrays[name].ctypes.data)

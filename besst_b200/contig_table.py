@@ -62,3 +62,25 @@ class ContigTable(object):
 
     def node_id(self, node):
         return 2 * self.scaffold_index[node[0]] + (1 if node[1] == "R" else 0)
+
+
+def first_library_rows(lengths, contig_threshold):
+    """Vectorised equivalent of InitializeObjects (CreateGraph.py:729-786) +
+    ContigTable for a first library in which every reference is present in the
+    FASTA: one single-contig scaffold per reference, large iff length >=
+    contig_threshold.  Returns (rows, n_scaffolds, n_large_scaffolds)."""
+    lengths = np.asarray(lengths, dtype=np.int64)
+    large = lengths >= contig_threshold
+    small = (~large) & (lengths > 0)
+    rows = np.zeros(lengths.shape[0], dtype=CONTIG_ROW_DTYPE)
+    n_large = int(large.sum())
+    scaffold = np.zeros(lengths.shape[0], dtype=np.int64)
+    scaffold[large] = np.arange(n_large)
+    scaffold[small] = n_large + np.arange(int(small.sum()))
+    rows["state"] = np.where(large, CTG_LARGE, np.where(small, CTG_SMALL, 0))
+    rows["scaffold"] = scaffold
+    rows["direction"] = 1
+    rows["length"] = lengths
+    rows["scaf_length"] = lengths
+    rows["in_largest"] = largest_reference_mask(lengths)
+    return rows, n_large + int(small.sum()), n_large

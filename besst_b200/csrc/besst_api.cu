@@ -48,6 +48,7 @@ extern "C" void besst_destroy(besst_ctx* ctx) {
     for (DBuf* b : bufs) b->release();
     for (DBuf& b : ctx->rec_i32) b.release();
     for (int i = 0; i <= BESST_N_STAGES; ++i) cudaEventDestroy(ctx->ev[i]);
+    for (auto& e : ctx->prof_pool) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
     cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -128,6 +129,7 @@ extern "C" int besst_links_extract(besst_ctx* ctx, const besst_lib_params* param
     cudaSetDevice(ctx->device);
     ctx->have_links = ctx->have_graph = false;
     ctx->n_stage_marks = 0;
+    ctx->prof_used = 0;
     besst_mark(ctx);
     DeviceRecords d;
     rc = stage_records(ctx, records, &d, false, true);
@@ -277,4 +279,23 @@ extern "C" int besst_kernel_launches(besst_ctx* ctx, int64_t* n_launches) {
     if (!ctx || !n_launches) return BESST_E_INVALID;
     *n_launches = ctx->launches;
     return BESST_OK;
+}
+
+extern "C" int besst_set_profiling(besst_ctx* ctx, int enabled) {
+    if (!ctx) return BESST_E_INVALID;
+    ctx->prof = enabled != 0;
+    ctx->prof_used = 0;
+    return BESST_OK;
+}
+
+extern "C" int besst_kernel_profile(besst_ctx* ctx, int32_t* kernel_ids, float* ms, int32_t cap) {
+    if (!ctx || !kernel_ids || !ms || cap < 0) return BESST_E_INVALID;
+    cudaSetDevice(ctx->device);
+    BESST_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    int n = 0;
+    for (size_t i = 0; i < ctx->prof_used && n < cap; ++i, ++n) {
+        kernel_ids[n] = ctx->prof_pool[i].id;
+        BESST_CUDA_TRY(ctx, cudaEventElapsedTime(&ms[n], ctx->prof_pool[i].a, ctx->prof_pool[i].b));
+    }
+    return n;
 }

@@ -581,8 +581,7 @@ int besst_launch_gapest(besst_ctx* ctx, const besst_lib_params& p, const double*
     const ScoreConsts c = besst_score_consts(p);
     const long long threads = n * 4;
     const int grid = (int)((threads + 127) / 128);
-    k_gapest_batch<<<grid, 128, 0, ctx->stream>>>(c, d_mean_obs, d_len1, d_len2, n, d_gap, d_sd);
-    ctx->launches++;
+    { KTimer kt(ctx, BESST_K_GAPEST); k_gapest_batch<<<grid, 128, 0, ctx->stream>>>(c, d_mean_obs, d_len1, d_len2, n, d_gap, d_sd); }
     BESST_CUDA_TRY(ctx, cudaGetLastError());
     return BESST_OK;
 }
@@ -614,8 +613,7 @@ int besst_launch_graph(besst_ctx* ctx, const besst_lib_params& p, const besst_li
     if (n_fishy > 0) {
         BESST_CUDA_TRY(ctx, ctx->fishy_sorted.ensure(8 * (size_t)n_fishy));
         BESST_CUDA_TRY(ctx, ctx->fishy_tmp.ensure(8 * (size_t)n_fishy));
-        k_fishy_rekey<<<(int)((n_fishy + 255) / 256), 256, 0, ctx->stream>>>(reinterpret_cast<const u64*>(d_fishy), ctx->fishy_sorted.as<u64>(), n_fishy, bv);
-        ctx->launches++;
+        { KTimer kt(ctx, BESST_K_FISHY); k_fishy_rekey<<<(int)((n_fishy + 255) / 256), 256, 0, ctx->stream>>>(reinterpret_cast<const u64*>(d_fishy), ctx->fishy_sorted.as<u64>(), n_fishy, bv); }
         int fb = 0;
         rc = besst_radix_sort_keys(ctx, ctx->fishy_sorted.as<uint64_t>(), ctx->fishy_tmp.as<uint64_t>(), n_fishy, 2 * bv, &fb);
         if (rc) return rc;
@@ -627,9 +625,8 @@ int besst_launch_graph(besst_ctx* ctx, const besst_lib_params& p, const besst_li
     BESST_CUDA_TRY(ctx, ctx->block_sums.ensure(4 * (size_t)(n_blocks + 2)));
     u32 n_edges32 = 0;
     if (n > 0) {
-        k_head_count<<<n_blocks, HB_THREADS, 0, ctx->stream>>>(keys, n, ctx->block_sums.as<u32>());
-        k_scan_blocks<<<1, 1024, 0, ctx->stream>>>(ctx->block_sums.as<u32>(), n_blocks);
-        ctx->launches += 2;
+        { KTimer kt(ctx, BESST_K_HEADS); k_head_count<<<n_blocks, HB_THREADS, 0, ctx->stream>>>(keys, n, ctx->block_sums.as<u32>()); }
+        { KTimer kt(ctx, BESST_K_HEADS); k_scan_blocks<<<1, 1024, 0, ctx->stream>>>(ctx->block_sums.as<u32>(), n_blocks); }
         BESST_CUDA_TRY(ctx, cudaMemcpyAsync(&n_edges32, ctx->block_sums.as<u32>() + n_blocks, 4, cudaMemcpyDeviceToHost, ctx->stream));
         BESST_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     }
@@ -659,8 +656,7 @@ int besst_launch_graph(besst_ctx* ctx, const besst_lib_params& p, const besst_li
         ctx->have_graph = true;
         return BESST_OK;
     }
-    k_head_write<<<n_blocks, HB_THREADS, 0, ctx->stream>>>(keys, n, ctx->block_sums.as<u32>(), EA.row_ptr);
-    ctx->launches++;
+    { KTimer kt(ctx, BESST_K_HEADS); k_head_write<<<n_blocks, HB_THREADS, 0, ctx->stream>>>(keys, n, ctx->block_sums.as<u32>(), EA.row_ptr); }
     besst_mark(ctx);
 
     {
@@ -668,9 +664,9 @@ int besst_launch_graph(besst_ctx* ctx, const besst_lib_params& p, const besst_li
         int grid = (int)((warps * 32 + 255) / 256);
         const int max_grid = ctx->sm_count * 32;
         if (grid > max_grid) grid = max_grid;
+        KTimer kt(ctx, BESST_K_EDGE_REDUCE);
         k_edge_reduce<<<grid, 256, 0, ctx->stream>>>(EA, E, d_tuples, idx, keys, bv, fishy_sorted, n_fishy,
                                                      (u32)(2 * ctx->n_large));
-        ctx->launches++;
         BESST_CUDA_TRY(ctx, cudaGetLastError());
     }
     besst_mark(ctx);
@@ -692,9 +688,8 @@ int besst_launch_graph(besst_ctx* ctx, const besst_lib_params& p, const besst_li
         int grid = (int)((E + SC_WARPS - 1) / SC_WARPS);
         const int max_grid = ctx->sm_count * 16;
         if (grid > max_grid) grid = max_grid;
-        k_edge_score<<<grid, SC_WARPS * 32, 0, ctx->stream>>>(A);
-        k_edge_score_big<<<ctx->sm_count, SB_THREADS, 0, ctx->stream>>>(A);
-        ctx->launches += 2;
+        { KTimer kt(ctx, BESST_K_EDGE_SCORE); k_edge_score<<<grid, SC_WARPS * 32, 0, ctx->stream>>>(A); }
+        { KTimer kt(ctx, BESST_K_EDGE_SCORE); k_edge_score_big<<<ctx->sm_count, SB_THREADS, 0, ctx->stream>>>(A); }
         BESST_CUDA_TRY(ctx, cudaGetLastError());
     }
     besst_mark(ctx);

@@ -6,6 +6,7 @@
 #include <stdint.h>
 
 #include <string>
+#include <vector>
 
 #include "../../include/besst_b200.h"
 
@@ -92,6 +93,12 @@ struct besst_ctx {
     bool have_graph = false;
     besst_lib_params last_params;
 
+    // per-kernel profiling (optional)
+    bool prof = false;
+    struct ProfEntry { int id; cudaEvent_t a, b; };
+    std::vector<ProfEntry> prof_pool;
+    size_t prof_used = 0;
+
     // timing
     cudaEvent_t ev[BESST_N_STAGES + 1];
     bool ev_valid = false;
@@ -128,3 +135,27 @@ int besst_launch_libmetrics(besst_ctx* ctx, const besst_lib_params& p, const Dev
 static inline void besst_mark(besst_ctx* ctx) {
     if (ctx->n_stage_marks <= BESST_N_STAGES) cudaEventRecord(ctx->ev[ctx->n_stage_marks++], ctx->stream);
 }
+
+// RAII event pair around one kernel launch (no-op unless profiling is enabled)
+struct KTimer {
+    besst_ctx* c;
+    size_t slot;
+    bool on;
+    KTimer(besst_ctx* ctx, int id) : c(ctx), slot(0), on(ctx->prof) {
+        c->launches++;
+        if (!on) return;
+        if (c->prof_used == c->prof_pool.size()) {
+            besst_ctx::ProfEntry e;
+            e.id = id;
+            cudaEventCreate(&e.a);
+            cudaEventCreate(&e.b);
+            c->prof_pool.push_back(e);
+        }
+        slot = c->prof_used++;
+        c->prof_pool[slot].id = id;
+        cudaEventRecord(c->prof_pool[slot].a, c->stream);
+    }
+    ~KTimer() {
+        if (on) cudaEventRecord(c->prof_pool[slot].b, c->stream);
+    }
+};

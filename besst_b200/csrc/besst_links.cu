@@ -463,9 +463,9 @@ int besst_launch_extract(besst_ctx* ctx, const besst_lib_params& p, const Device
         P.eligA0 = ts; P.eligA1 = ts + stride; P.eligP0 = ts + 2 * stride; P.eligP1 = ts + 3 * stride; P.acc = ts + 4 * stride;
         P.n_tiles = n_tiles;
         if (n_tiles > 0) {
+            KTimer kt(ctx, BESST_K_EXTRACT);
             if (vec) k_extract_links<true><<<grid, K1_THREADS, 0, ctx->stream>>>(P);
             else k_extract_links<false><<<grid, K1_THREADS, 0, ctx->stream>>>(P);
-            ctx->launches++;
             BESST_CUDA_TRY(ctx, cudaGetLastError());
         }
         u64 g[3] = {0, 0, 0};

@@ -361,10 +361,9 @@ int besst_launch_libmetrics(besst_ctx* ctx, const besst_lib_params& p, const Dev
         P.lo = lo;
         P.hi = std::min<long long>(rec.n, lo + MT_CHUNK);
         const int n_tiles = (int)((P.hi - P.lo + MT_TILE - 1) / MT_TILE);
-        k_metrics_count<<<n_tiles, MT_THREADS, 0, ctx->stream>>>(P, cnt_a, cnt_b);
-        k_metrics_scan<<<1, 1024, 0, ctx->stream>>>(cnt_a, cnt_b, n_tiles);
-        k_metrics_hist<<<n_tiles, MT_THREADS, 0, ctx->stream>>>(P, cnt_a, cnt_b, base_isize, base_scope, hist_isize, hist_cont, n_bins, d_out);
-        ctx->launches += 3;
+        { KTimer kt(ctx, BESST_K_METRICS); k_metrics_count<<<n_tiles, MT_THREADS, 0, ctx->stream>>>(P, cnt_a, cnt_b); }
+        { KTimer kt(ctx, BESST_K_METRICS); k_metrics_scan<<<1, 1024, 0, ctx->stream>>>(cnt_a, cnt_b, n_tiles); }
+        { KTimer kt(ctx, BESST_K_METRICS); k_metrics_hist<<<n_tiles, MT_THREADS, 0, ctx->stream>>>(P, cnt_a, cnt_b, base_isize, base_scope, hist_isize, hist_cont, n_bins, d_out); }
         BESST_CUDA_TRY(ctx, cudaGetLastError());
         u32 tot[2];
         BESST_CUDA_TRY(ctx, cudaMemcpyAsync(&tot[0], cnt_a + n_tiles, 4, cudaMemcpyDeviceToHost, ctx->stream));

@@ -241,9 +241,8 @@ int sort_impl(besst_ctx* ctx, const besst_link_tuple* tuples, int bv, u64* keys_
     int hgrid = ctx->sm_count * 8;
     const long long max_blocks = (n + RS_THREADS - 1) / RS_THREADS;
     if (hgrid > max_blocks) hgrid = (int)max_blocks;
-    k_radix_hist<FROM_TUPLES><<<hgrid, RS_THREADS, 0, ctx->stream>>>(keys_a, tuples, bv, n, passes, ghist);
-    k_radix_scan_hist<<<passes, RS_RADIX, 0, ctx->stream>>>(ghist);
-    ctx->launches += 2;
+    { KTimer kt(ctx, BESST_K_RADIX_HIST); k_radix_hist<FROM_TUPLES><<<hgrid, RS_THREADS, 0, ctx->stream>>>(keys_a, tuples, bv, n, passes, ghist); }
+    { KTimer kt(ctx, BESST_K_RADIX_SCAN); k_radix_scan_hist<<<passes, RS_RADIX, 0, ctx->stream>>>(ghist); }
     BESST_CUDA_TRY(ctx, cudaGetLastError());
 
     const size_t smem = sizeof(SweepSmem);
@@ -266,6 +265,8 @@ int sort_impl(besst_ctx* ctx, const besst_link_tuple* tuples, int bv, u64* keys_
     u32* out_v = val_b;
     for (int p = 0; p < passes; ++p) {
         BESST_CUDA_TRY(ctx, cudaMemsetAsync(ctx->sort_state.p, 0, sizeof(u32) * (size_t)n_tiles * RS_RADIX, ctx->stream));
+        {
+        KTimer kt(ctx, BESST_K_RADIX_SWEEP);
         if (p == 0 && FROM_TUPLES)
             k_radix_sweep<true, true><<<grid, RS_THREADS, smem, ctx->stream>>>(
                 nullptr, nullptr, tuples, bv, out_k, out_v, n, 0, ghist, ctx->sort_state.as<u32>(), tickets + p, n_tiles);
@@ -273,7 +274,7 @@ int sort_impl(besst_ctx* ctx, const besst_link_tuple* tuples, int bv, u64* keys_
             k_radix_sweep<false, HAS_VAL><<<grid, RS_THREADS, smem, ctx->stream>>>(
                 in_k, in_v, nullptr, bv, out_k, out_v, n, 8 * p, ghist + p * RS_RADIX, ctx->sort_state.as<u32>(),
                 tickets + p, n_tiles);
-        ctx->launches++;
+        }
         BESST_CUDA_TRY(ctx, cudaGetLastError());
         // ping-pong: after the first pass from tuples the data lives in (keys_b, val_b)
         const u64* nk = out_k;

@@ -131,11 +131,24 @@ class CudaEngine(object):
         self._check(self._L.besst_last_timing(self._ctx, C.byref(total), stages), "besst_last_timing")
         return total.value, dict(zip(STAGE_NAMES, list(stages)[:len(STAGE_NAMES)]))
 
+    def set_profiling(self, on):
+        self._check(self._L.besst_set_profiling(self._ctx, int(bool(on))), "besst_set_profiling")
+
+    def kernel_profile(self, cap=256):
+        """[(kernel name, ms)] per launch of the last build (needs set_profiling(True))."""
+        ids = np.zeros(cap, dtype=np.int32)
+        ms = np.zeros(cap, dtype=np.float32)
+        n = self._check(self._L.besst_kernel_profile(self._ctx, ids.ctypes.data, ms.ctypes.data, cap), "besst_kernel_profile")
+        return [(KERNEL_NAMES[int(ids[i])], float(ms[i])) for i in range(n)]
+
     def kernel_launches(self):
         n = C.c_int64()
         self._check(self._L.besst_kernel_launches(self._ctx, C.byref(n)), "besst_kernel_launches")
         return n.value
 
+
+KERNEL_NAMES = ["k_extract_links", "k_radix_hist", "k_radix_scan_hist", "k_radix_sweep", "k_heads", "k_edge_reduce",
+                "k_edge_score", "k_fishy_rekey", "k_metrics", "k_gapest_batch"]
 
 _default = None
 

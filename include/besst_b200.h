@@ -22,6 +22,8 @@
  *   besst_gapest_batch       mathstats param_est.GapEstimator / tr_sk_std_dev at
  *                            CreateGraph.py:537,555; MakeScaffolds.py:449,453;
  *                            order_contigs.py:300,308; pathgaps.py:108,204
+ *   besst_libmetrics returns 1 (not an error) when fewer than 1001 insert-size
+ *   samples exist (libmetrics.py:311-314).
  *   besst_links_extract /    the two halves of besst_graph_build on either side
  *   besst_links_to_graph     of the multi-GPU all-to-all
  *
@@ -230,6 +232,24 @@ int besst_gapest_batch(besst_ctx* ctx, const besst_lib_params* params, const dou
 #define BESST_N_STAGES 8
 int besst_last_timing(besst_ctx* ctx, float* total_ms, float* stage_ms /*[BESST_N_STAGES]*/);
 int besst_kernel_launches(besst_ctx* ctx, int64_t* n_launches);
+
+/* per-kernel CUDA-event timing (for bench.py's roofline): when enabled every
+ * kernel launch of a build is bracketed by an event pair on the library's
+ * stream; besst_kernel_profile returns (kernel id, milliseconds) per launch of
+ * the last build, in launch order.  Returns the number of launches written. */
+#define BESST_K_EXTRACT 0      /* k_extract_links          (K1) */
+#define BESST_K_RADIX_HIST 1   /* k_radix_hist             (K3) */
+#define BESST_K_RADIX_SCAN 2   /* k_radix_scan_hist        (K3) */
+#define BESST_K_RADIX_SWEEP 3  /* k_radix_sweep, one per digit pass (K3) */
+#define BESST_K_HEADS 4        /* k_head_count/k_scan_blocks/k_head_write (K4) */
+#define BESST_K_EDGE_REDUCE 5  /* k_edge_reduce            (K4) */
+#define BESST_K_EDGE_SCORE 6   /* k_edge_score(+_big)      (K5/K6) */
+#define BESST_K_FISHY 7        /* k_fishy_rekey */
+#define BESST_K_METRICS 8      /* k_metrics_*              (K7) */
+#define BESST_K_GAPEST 9       /* k_gapest_batch           (K6) */
+#define BESST_N_KERNEL_IDS 10
+int besst_set_profiling(besst_ctx* ctx, int enabled);
+int besst_kernel_profile(besst_ctx* ctx, int32_t* kernel_ids, float* ms, int32_t cap);
 
 #ifdef __cplusplus
 }
