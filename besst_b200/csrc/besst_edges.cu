@@ -219,10 +219,10 @@ struct GTerms {
 __device__ __forceinline__ GTerms g_terms_quad(double d, const ScoreConsts& c, double c_min, double c_max) {
     const int q = threadIdx.x & 3;
     double X;
-    if (q == 0) X = d + 2 * c.r - c.mean;
+    if (q == 0) X = d + 2 * c.r - 1 - c.mean;
     else if (q == 1) X = c_min + d + c.r - c.mean;
     else if (q == 2) X = c_max + d + c.r - c.mean;
-    else X = c_min + c_max + d - c.mean;
+    else X = c_min + c_max + d + 1 - c.mean;
     const double z = X / c.s2;
     const double e = c.erf_variant == BESST_ERF_LIBM ? erf(z) : as_erf_dev(z);
     const double x = exp(-(X * X) / c.v2);

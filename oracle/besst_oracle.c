@@ -63,10 +63,10 @@ typedef struct { double g, gp, gb; } gterms;
 
 static gterms g_terms(double d, double mean, double sd, double c_min, double c_max, double r, int variant) {
     double s2 = pow(2.0, 0.5) * sd;
-    double A = d + 2 * r - mean;
+    double A = d + 2 * r - 1 - mean;
     double B = c_min + d + r - mean;
     double C = c_max + d + r - mean;
-    double D = c_min + c_max + d - mean;
+    double D = c_min + c_max + d + 1 - mean;
     double eA = erf_variant(A / s2, variant), eB = erf_variant(B / s2, variant);
     double eC = erf_variant(C / s2, variant), eD = erf_variant(D / s2, variant);
     double v2 = 2 * pow(sd, 2.0);

@@ -9,12 +9,15 @@ d; read length r; observation o = x - d; number of placements
   w(o) = o-2r+1            on [2r, c_min+r]
        = c_min-r+1         on [c_min+r, c_max+r]
        = c_min+c_max-o+1   on [c_max+r, c_min+c_max]
-g(d) = int w(x-d) phi(x) dx (closed form below), and the ML equation for n
-observations with mean obs:   mu - mean_obs = d + sigma^2 g'(d)/g(d).
+w is continuous and reaches zero at o = 2r-1 and o = c_min+c_max+1, so
+g(d) = int w(x-d) phi(x) dx integrates over x-mu in [A, D] with
+  A = d+2r-1-mu, B = c_min+d+r-mu, C = c_max+d+r-mu, D = c_min+c_max+d+1-mu
+(closed form below), and the ML equation for n observations with mean obs is
+  mu - mean_obs = d + sigma^2 g'(d)/g(d).
 
 PARITY UNPINNED: the package source is not available in this container; the
 closed forms below are derived from the model and checked against numerical
-quadrature in tests/test_oracle_math.py.  Division by an exactly-zero g(d)
+quadrature of that model in tests/test_oracle_math.py.  Division by an exactly-zero g(d)
 follows IEEE-754 (inf/nan) instead of raising, so that the C and CUDA
 restatements can agree with this file bit for bit in control flow.
 """
@@ -35,10 +38,10 @@ def _div(a, b):
 
 def _terms(d, mean, stdDev, c_min, c_max, readLen):
     s2 = (2 ** 0.5) * stdDev
-    A = d + 2 * readLen - mean
+    A = d + 2 * readLen - 1 - mean
     B = c_min + d + readLen - mean
     C = c_max + d + readLen - mean
-    D = c_min + c_max + d - mean
+    D = c_min + c_max + d + 1 - mean
     eA, eB, eC, eD = erf(A / s2), erf(B / s2), erf(C / s2), erf(D / s2)
     v2 = float(2 * stdDev ** 2)
     xA, xB, xC, xD = exp(-(A ** 2) / v2), exp(-(B ** 2) / v2), exp(-(C ** 2) / v2), exp(-(D ** 2) / v2)
