@@ -215,7 +215,8 @@ def run_ours(args):
     n_launch = {k: len(v) / args.steps for k, v in prof.items()}
     n_links, n_edges = int(sizes.n_links), int(sizes.n_edges)
     alg_bytes = {   # algorithmic bytes per launch of each kernel (DESIGN.md "Kernels")
-        "k_extract_links": RECORD_BYTES * n_rec + TUPLE_BYTES * n_links,
+        "k_extract_links": RECORD_BYTES * n_rec + TUPLE_BYTES * n_links + 48 * ((n_rec + 127) // 128),
+        "k_compact_tuples": 2 * TUPLE_BYTES * n_links + 8 * ((n_rec + 127) // 128),
         "k_radix_sweep": (12 + 12) * n_links,
         "k_radix_hist": 8 * n_links,
         "k_edge_reduce": (4 + 16 + 8) * n_links + 64 * n_edges,

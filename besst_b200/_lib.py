@@ -16,7 +16,8 @@ EXPORTS = ["besst_abi_version", "besst_create", "besst_destroy", "besst_last_err
            "besst_graph_build", "besst_graph_fetch", "besst_links_extract", "besst_links_tuples_device",
            "besst_links_fishy_device", "besst_links_partials", "besst_links_to_graph", "besst_libmetrics",
            "besst_gapest_batch", "besst_last_timing", "besst_kernel_launches", "besst_set_profiling",
-           "besst_kernel_profile"]
+           "besst_kernel_profile", "besst_links_partials_device", "besst_links_fetch", "besst_links_partition",
+           "besst_trsk_sd_batch", "besst_set_stream"]
 
 _lib = None
 
@@ -59,6 +60,11 @@ def load():
     L.besst_kernel_launches.argtypes = [vp, C.POINTER(i64)]
     L.besst_set_profiling.argtypes = [vp, C.c_int]
     L.besst_kernel_profile.argtypes = [vp, vp, vp, i32]
+    L.besst_links_partials_device.argtypes = [vp, C.POINTER(vp), C.POINTER(vp)]
+    L.besst_links_fetch.argtypes = [vp, vp, vp]
+    L.besst_links_partition.argtypes = [vp, i32, vp, vp, vp, vp]
+    L.besst_trsk_sd_batch.argtypes = [vp, C.POINTER(abi.LibParams), vp, vp, vp, i64, vp]
+    L.besst_set_stream.argtypes = [vp, vp]
     if L.besst_abi_version() != abi.ABI_VERSION:
         raise BesstLibraryError("ABI version mismatch: library %d, binding %d" % (L.besst_abi_version(), abi.ABI_VERSION))
     _lib = L

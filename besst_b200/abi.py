@@ -8,7 +8,7 @@ from dataclasses import dataclass
 
 import numpy as np
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 CTG_ABSENT, CTG_LARGE, CTG_SMALL = 0, 1, 2
 ORIENT_FR, ORIENT_RF = 0, 1

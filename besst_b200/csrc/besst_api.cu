@@ -29,8 +29,9 @@ extern "C" besst_ctx* besst_create(int device) {
     ctx->device = device;
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->sm_count = prop.multiProcessorCount;
-    e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+    e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) { g_create_error = std::string("cudaStreamCreate: ") + cudaGetErrorString(e); delete ctx; return nullptr; }
+    ctx->stream = ctx->own_stream;
     for (int i = 0; i <= BESST_N_STAGES; ++i) cudaEventCreate(&ctx->ev[i]);
     return ctx;
 }
@@ -39,7 +40,7 @@ extern "C" void besst_destroy(besst_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    DBuf* bufs[] = {&ctx->rows, &ctx->scaf_len, &ctx->rec_flag, &ctx->rec_mapq, &ctx->tuples, &ctx->fishy_keys, &ctx->aligned,
+    DBuf* bufs[] = {&ctx->rows, &ctx->rows_packed, &ctx->scratch_tuples, &ctx->tile_aggs, &ctx->part_state, &ctx->scaf_len, &ctx->rec_flag, &ctx->rec_mapq, &ctx->tuples, &ctx->fishy_keys, &ctx->aligned,
                     &ctx->counters, &ctx->tile_state, &ctx->misc, &ctx->key_a, &ctx->key_b, &ctx->idx_a, &ctx->idx_b, &ctx->hist,
                     &ctx->sort_state, &ctx->fishy_sorted, &ctx->fishy_tmp, &ctx->heads, &ctx->block_sums, &ctx->e_u, &ctx->e_v,
                     &ctx->e_nr, &ctx->e_obs, &ctx->e_obs_sq, &ctx->e_first, &ctx->e_row_ptr, &ctx->e_gap, &ctx->e_score,
@@ -49,7 +50,7 @@ extern "C" void besst_destroy(besst_ctx* ctx) {
     for (DBuf& b : ctx->rec_i32) b.release();
     for (int i = 0; i <= BESST_N_STAGES; ++i) cudaEventDestroy(ctx->ev[i]);
     for (auto& e : ctx->prof_pool) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
-    cudaStreamDestroy(ctx->stream);
+    cudaStreamDestroy(ctx->own_stream);
     delete ctx;
 }
 
@@ -59,19 +60,29 @@ extern "C" int besst_set_contigs(besst_ctx* ctx, const besst_contig_row* rows, i
                                  int64_t n_large_scaffolds) {
     if (!ctx) return BESST_E_INVALID;
     if (n_contigs < 0 || n_scaffolds < 0 || n_large_scaffolds < 0 || n_large_scaffolds > n_scaffolds || (n_contigs > 0 && !rows) ||
-        n_scaffolds >= (1ll << 30) || n_contigs >= (1ll << 31)) {
+        n_scaffolds >= (1ll << 29) || n_contigs >= (1ll << 31)) {
         ctx->err = "besst_set_contigs: bad sizes";
         return BESST_E_INVALID;
     }
     std::vector<int32_t> slen((size_t)(n_scaffolds > 0 ? n_scaffolds : 1), 0);
+    // packed 16-byte rows for the record kernel: one 128-bit gather per read end
+    //   x = scaffold << 3 | direction << 2 | state,  y = position,  z = length,  w = scaf_length
+    std::vector<int32_t> packed(4 * (size_t)(n_contigs > 0 ? n_contigs : 1), 0);
     for (int64_t c = 0; c < n_contigs; ++c) {
         if (rows[c].state == BESST_CTG_ABSENT) continue;
+        if (rows[c].state != BESST_CTG_LARGE && rows[c].state != BESST_CTG_SMALL) { ctx->err = "besst_set_contigs: bad contig state"; return BESST_E_INVALID; }
         if (rows[c].scaffold < 0 || rows[c].scaffold >= n_scaffolds) { ctx->err = "besst_set_contigs: scaffold index out of range"; return BESST_E_INVALID; }
         slen[(size_t)rows[c].scaffold] = rows[c].scaf_length;
+        packed[4 * (size_t)c + 0] = (int32_t)(((uint32_t)rows[c].scaffold << 3) | (rows[c].direction ? 4u : 0u) | (uint32_t)rows[c].state);
+        packed[4 * (size_t)c + 1] = rows[c].position;
+        packed[4 * (size_t)c + 2] = rows[c].length;
+        packed[4 * (size_t)c + 3] = rows[c].scaf_length;
     }
     cudaSetDevice(ctx->device);
     BESST_CUDA_TRY(ctx, ctx->rows.ensure(sizeof(besst_contig_row) * (size_t)(n_contigs > 0 ? n_contigs : 1)));
     BESST_CUDA_TRY(ctx, ctx->scaf_len.ensure(4 * slen.size()));
+    BESST_CUDA_TRY(ctx, ctx->rows_packed.ensure(4 * packed.size()));
+    BESST_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->rows_packed.p, packed.data(), 4 * packed.size(), cudaMemcpyHostToDevice, ctx->stream));
     if (n_contigs > 0)
         BESST_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->rows.p, rows, sizeof(besst_contig_row) * (size_t)n_contigs, cudaMemcpyHostToDevice, ctx->stream));
     BESST_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->scaf_len.p, slen.data(), 4 * slen.size(), cudaMemcpyHostToDevice, ctx->stream));
@@ -162,6 +173,69 @@ extern "C" int besst_links_partials(besst_ctx* ctx, int64_t* aligned_len_host, i
         BESST_CUDA_TRY(ctx, cudaMemcpyAsync(aligned_len_host, ctx->aligned.p, 8 * (size_t)ctx->n_contigs, cudaMemcpyDeviceToHost, ctx->stream));
     if (counters_host)
         BESST_CUDA_TRY(ctx, cudaMemcpyAsync(counters_host, ctx->counters.p, 8 * BESST_N_COUNTERS, cudaMemcpyDeviceToHost, ctx->stream));
+    BESST_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return BESST_OK;
+}
+
+extern "C" int besst_links_partials_device(besst_ctx* ctx, int64_t** aligned_len_device, int64_t** counters_device) {
+    if (!ctx || !ctx->have_links) { if (ctx) ctx->err = "no extracted links"; return BESST_E_STATE; }
+    if (aligned_len_device) *aligned_len_device = ctx->aligned.as<int64_t>();
+    if (counters_device) *counters_device = ctx->counters.as<int64_t>();
+    return BESST_OK;
+}
+
+extern "C" int besst_links_fetch(besst_ctx* ctx, besst_link_tuple* tuples_host, uint64_t* fishy_keys_host) {
+    if (!ctx || !ctx->have_links) { if (ctx) ctx->err = "no extracted links"; return BESST_E_STATE; }
+    cudaSetDevice(ctx->device);
+    if (tuples_host && ctx->n_tuples > 0)
+        BESST_CUDA_TRY(ctx, cudaMemcpyAsync(tuples_host, ctx->tuples.p, sizeof(besst_link_tuple) * (size_t)ctx->n_tuples, cudaMemcpyDeviceToHost, ctx->stream));
+    if (fishy_keys_host && ctx->n_fishy_keys > 0)
+        BESST_CUDA_TRY(ctx, cudaMemcpyAsync(fishy_keys_host, ctx->fishy_keys.p, 8 * (size_t)ctx->n_fishy_keys, cudaMemcpyDeviceToHost, ctx->stream));
+    BESST_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return BESST_OK;
+}
+
+extern "C" int besst_links_partition(besst_ctx* ctx, int32_t world, besst_link_tuple* out_tuples_device,
+                                     uint64_t* out_fishy_device, int64_t* tuple_counts, int64_t* fishy_counts) {
+    if (!ctx || !ctx->have_links) { if (ctx) ctx->err = "no extracted links"; return BESST_E_STATE; }
+    if (!tuple_counts || !fishy_counts || (ctx->n_tuples > 0 && !out_tuples_device) || (ctx->n_fishy_keys > 0 && !out_fishy_device)) {
+        ctx->err = "links_partition: bad arguments";
+        return BESST_E_INVALID;
+    }
+    cudaSetDevice(ctx->device);
+    return besst_launch_partition(ctx, world, out_tuples_device, out_fishy_device, tuple_counts, fishy_counts);
+}
+
+extern "C" int besst_set_stream(besst_ctx* ctx, void* cuda_stream) {
+    if (!ctx) return BESST_E_INVALID;
+    cudaSetDevice(ctx->device);
+    BESST_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->stream = cuda_stream ? reinterpret_cast<cudaStream_t>(cuda_stream) : ctx->own_stream;
+    ctx->use_caller_stream = cuda_stream != nullptr;
+    return BESST_OK;
+}
+
+extern "C" int besst_trsk_sd_batch(besst_ctx* ctx, const besst_lib_params* params, const double* gap, const int32_t* len1,
+                                   const int32_t* len2, int64_t n, double* sd_out) {
+    if (!ctx) return BESST_E_INVALID;
+    int rc = check_params(ctx, params);
+    if (rc) return rc;
+    if (n < 0 || (n > 0 && (!gap || !len1 || !len2 || !sd_out))) { ctx->err = "trsk_sd_batch: bad arguments"; return BESST_E_INVALID; }
+    if (n == 0) return BESST_OK;
+    cudaSetDevice(ctx->device);
+    const size_t nn = (size_t)n;
+    BESST_CUDA_TRY(ctx, ctx->misc.ensure(nn * (8 + 8 + 4 + 4) + 64));
+    unsigned char* base = ctx->misc.as<unsigned char>();
+    double* d_gap = reinterpret_cast<double*>(base);
+    double* d_sd = reinterpret_cast<double*>(base + 8 * nn);
+    int32_t* d_l1 = reinterpret_cast<int32_t*>(base + 16 * nn);
+    int32_t* d_l2 = d_l1 + nn;
+    BESST_CUDA_TRY(ctx, cudaMemcpyAsync(d_gap, gap, 8 * nn, cudaMemcpyHostToDevice, ctx->stream));
+    BESST_CUDA_TRY(ctx, cudaMemcpyAsync(d_l1, len1, 4 * nn, cudaMemcpyHostToDevice, ctx->stream));
+    BESST_CUDA_TRY(ctx, cudaMemcpyAsync(d_l2, len2, 4 * nn, cudaMemcpyHostToDevice, ctx->stream));
+    rc = besst_launch_trsk_sd(ctx, *params, d_gap, d_l1, d_l2, n, d_sd);
+    if (rc) return rc;
+    BESST_CUDA_TRY(ctx, cudaMemcpyAsync(sd_out, d_sd, 8 * nn, cudaMemcpyDeviceToHost, ctx->stream));
     BESST_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     return BESST_OK;
 }

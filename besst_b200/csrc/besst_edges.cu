@@ -553,6 +553,17 @@ __global__ void __launch_bounds__(128)
     }
 }
 
+__global__ void __launch_bounds__(128)
+    k_trsk_sd_batch(const ScoreConsts c, const double* __restrict__ gap, const int* __restrict__ len1,
+                    const int* __restrict__ len2, long long n, double* sd_out) {
+    const long long quad = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 2;
+    const bool active = quad < n;
+    const double d = active ? gap[quad] : 0.0;
+    const double l1 = active ? (double)len1[quad] : 1.0, l2 = active ? (double)len2[quad] : 1.0;
+    const double sd = tr_sk_std_dev_quad(c, l1, l2, d);
+    if (active && (threadIdx.x & 3) == 0) sd_out[quad] = sd;
+}
+
 int bits_for(uint64_t max_value) {
     int b = 1;
     while (b < 32 && (max_value >> b)) ++b;
@@ -582,6 +593,17 @@ int besst_launch_gapest(besst_ctx* ctx, const besst_lib_params& p, const double*
     const long long threads = n * 4;
     const int grid = (int)((threads + 127) / 128);
     { KTimer kt(ctx, BESST_K_GAPEST); k_gapest_batch<<<grid, 128, 0, ctx->stream>>>(c, d_mean_obs, d_len1, d_len2, n, d_gap, d_sd); }
+    BESST_CUDA_TRY(ctx, cudaGetLastError());
+    return BESST_OK;
+}
+
+int besst_launch_trsk_sd(besst_ctx* ctx, const besst_lib_params& p, const double* d_gap, const int32_t* d_len1,
+                         const int32_t* d_len2, int64_t n, double* d_sd) {
+    if (n == 0) return BESST_OK;
+    const ScoreConsts c = besst_score_consts(p);
+    const long long threads = n * 4;
+    const int grid = (int)((threads + 127) / 128);
+    { KTimer kt(ctx, BESST_K_GAPEST); k_trsk_sd_batch<<<grid, 128, 0, ctx->stream>>>(c, d_gap, d_len1, d_len2, n, d_sd); }
     BESST_CUDA_TRY(ctx, cudaGetLastError());
     return BESST_OK;
 }

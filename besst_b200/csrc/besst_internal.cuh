@@ -66,19 +66,21 @@ struct ScoreConsts {
 struct besst_ctx {
     int device = 0;
     int sm_count = 148;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr;      // the stream all work is ordered on
+    cudaStream_t own_stream = nullptr;  // created by besst_create
+    bool use_caller_stream = false;
     std::string err;
 
     // contig table
-    DBuf rows, scaf_len;
+    DBuf rows, rows_packed, scaf_len;
     int64_t n_contigs = 0, n_scaffolds = 0, n_large = 0;
 
     // staged records (host-pointer calls)
     DBuf rec_i32[6], rec_flag, rec_mapq;
 
     // link extraction
-    DBuf tuples, fishy_keys, aligned, counters, tile_state, misc;
-    int64_t tuples_cap = 0, fishy_cap = 0;
+    DBuf tuples, scratch_tuples, tile_aggs, fishy_keys, aligned, counters, tile_state, part_state, misc;
+    int64_t fishy_cap = 0;
     int64_t n_tuples = 0, n_fishy_keys = 0;
     bool have_links = false;
 
@@ -125,6 +127,10 @@ int besst_launch_edge_stats(besst_ctx* ctx, const besst_lib_params& p, const bes
                             const uint64_t* d_sorted_keys, const uint32_t* d_sorted_idx, int64_t n_links, int key_shift);
 int besst_launch_gapest(besst_ctx* ctx, const besst_lib_params& p, const double* d_mean_obs, const int32_t* d_len1,
                         const int32_t* d_len2, int64_t n, int32_t* d_gap, double* d_sd);
+int besst_launch_trsk_sd(besst_ctx* ctx, const besst_lib_params& p, const double* d_gap, const int32_t* d_len1,
+                         const int32_t* d_len2, int64_t n, double* d_sd);
+int besst_launch_partition(besst_ctx* ctx, int world, besst_link_tuple* out_tuples, uint64_t* out_fishy,
+                           int64_t* tuple_counts, int64_t* fishy_counts);
 
 ScoreConsts besst_score_consts(const besst_lib_params& p);
 

@@ -1,71 +1,88 @@
 // K1  records -> accepted link tuples in BAM order.
 //
-// One pass over the record SoA replaces the reference's per-record Python loop
-// (CreateGraph.py:111-211) together with CreateEdge's observation transform,
-// duplicate test and acceptance test (CreateGraph.py:812-871, 1024-1076), the
-// fishy-pair counting (:141-163, CheckDir :678-688), the coverage accumulation
-// (:138-139) and the `counters` bookkeeping (Parameter.py:113-124).
+// Replaces the reference's per-record Python loop (CreateGraph.py:111-211)
+// together with CreateEdge's observation transform, duplicate test and
+// acceptance test (CreateGraph.py:812-871, 1024-1076), the fishy-pair counting
+// (:141-163, CheckDir :678-688), the coverage accumulation (:138-139) and the
+// `counters` bookkeeping (Parameter.py:113-124).
 //
-// Design (HBM-bound streaming kernel, no tensor cores):
-//  * persistent CTAs (grid = SMs x resident CTAs), tiles of 1024 records handed
-//    out by an atomic ticket so that tile t-1 is always running when t starts;
-//  * 128-bit coalesced loads of the SoA columns (4 consecutive records/thread);
-//    the 32-byte contig rows are two 128-bit gathers that hit L1/L2 because the
-//    BAM is tid-sorted;
-//  * the only order-dependent state of the reference -- "previous CreateEdge
-//    call's (obs1,obs2)" -- is a rightmost-non-empty scan, done with warp
-//    shuffles inside the tile and a decoupled look-back across tiles
-//    (self-validating 64-bit words, no fences);
-//  * accepted tuples are compacted in BAM order (second decoupled look-back on
-//    the counts), staged in shared memory and written with 16-byte stores;
-//  * coverage uses __match_any_sync warp-aggregated 64-bit atomics; counters
-//    stay in registers for the life of the CTA.
+// Design (HBM-bound streaming, no tensor cores, no inter-CTA waiting):
+//
+//  k_extract_links   one WARP owns a tile of 128 consecutive records (4 per
+//      lane, 128-bit coalesced loads of the SoA columns; the contig table is a
+//      packed 16-byte row, one 128-bit gather per read end, L1/L2 resident
+//      because the BAM is tid-sorted).  No shared memory and no block barrier:
+//      latency is hidden purely by resident warps.  The only order-dependent
+//      state of the reference -- "(obs1,obs2) of the previous CreateEdge call"
+//      -- is a rightmost-non-empty scan: inside the tile it is done with warp
+//      shuffles; across tiles only the FIRST eligible record of a tile depends
+//      on earlier tiles, so the tile assumes "not a duplicate", writes its
+//      accepted tuples compacted into a tile-local slot of a scratch array and
+//      publishes a 48-byte aggregate (first/last eligible observation, count,
+//      what to undo if the first one turns out to be a duplicate).
+//  k_tile_reduce / k_chunk_resolve / k_tile_offsets   a two-level scan over the
+//      aggregates (1024 tiles per chunk) resolves every tile boundary: duplicate
+//      verdict, counter corrections, exact output offset.  O(N/128) work.
+//  k_compact_tuples  copies each tile's run to its final position (16-byte
+//      loads/stores), dropping a boundary duplicate.
+//
+// Coverage uses __match_any_sync warp-aggregated 64-bit atomics; counters stay
+// in registers for the life of a warp and are flushed once.
 #include "besst_internal.cuh"
 
 namespace {
 
-constexpr int K1_THREADS = 256;
-constexpr int K1_ITEMS = 4;
-constexpr int K1_TILE = K1_THREADS * K1_ITEMS;
-constexpr int K1_WARPS = K1_THREADS / 32;
-
 typedef unsigned long long u64;
+typedef unsigned int u32;
 
-struct Row {
-    int4 a;  // state, scaffold, direction, position
-    int4 b;  // length, scaf_length, in_largest, reserved
+constexpr int K1_THREADS = 256;
+constexpr int WT_ITEMS = 4;
+constexpr int WT = 32 * WT_ITEMS;   // records per warp tile
+constexpr int SC_THREADS = 1024;    // aggregates per scan chunk
+
+constexpr u32 AGG_HAS = 1u << 31;     // the tile holds at least one CreateEdge call
+constexpr u32 AGG_PASS = 1u << 30;    // its first call passes the acceptance test (:840)
+constexpr u32 AGG_SECOND = 1u << 29;  // ... and is followed by the second call into G_prime (:180-183)
+constexpr u32 AGG_MQ0 = 1u << 28;     // ... on a mapq-0 record (non_unique_for_scaf, :814-815)
+
+// Aggregate of a run of records (a tile, or a chunk of tiles): same shape at both scan levels.
+struct __align__(16) Agg {
+    u32 flags;
+    int first_o1, first_o2;   // (obs1,obs2) of the first CreateEdge call in the run
+    int last_o1, last_o2;     // ... of the last one
+    u32 cnt;                  // accepted tuples, the run's first call assumed not to be a duplicate
+    int dups, count_corr, toolong_corr, nus_corr;   // counter corrections already resolved inside the run
+    u32 pad0, pad1;
 };
+static_assert(sizeof(Agg) == 48, "Agg layout");
+
+struct ChunkIn {   // what a chunk receives from everything before it
+    int carry_o1, carry_o2;
+    u64 offset;
+};
+
+constexpr u64 OFF_DROP = 1ull << 63;   // tile_off flag: skip the tile's first scratch tuple
+constexpr u64 OFF_MASK = OFF_DROP - 1;
 
 struct K1Params {
     DeviceRecords rec;
-    const Row* rows;
+    const int4* rows;   // packed contig rows
     int n_contigs;
     int orientation, min_mapq, detect_dup, extend, scoring;
     double read_len, threshold;
-    int halo1, halo2;
-    besst_link_tuple* out;
-    long long out_cap;
+    besst_link_tuple* scratch;   // [n_tiles * WT]
+    Agg* aggs;                   // [n_tiles]
     u64* fishy;
     long long fishy_cap;
     u64* aligned;
     u64* counters;  // [BESST_N_COUNTERS]
-    u64* globals;   // [0]=ticket [1]=n_out [2]=n_fishy
-    u64 *eligA0, *eligA1, *eligP0, *eligP1, *acc;
-    int n_tiles;
+    u64* globals;   // [0]=n_out [1]=n_fishy
+    long long n_tiles;
 };
-
-constexpr u64 READY = 1ull << 63;
-constexpr u64 HAS = 1ull << 62;
-constexpr u64 ST_AGG = 1ull << 62;
-constexpr u64 ST_INC = 2ull << 62;
-constexpr u64 ST_MASK = 3ull << 62;
 
 struct Last {
     int has, o1, o2;
 };
-
-__device__ __forceinline__ u64 ld_vol(const u64* p) { return *reinterpret_cast<const volatile u64*>(p); }
-__device__ __forceinline__ void st_vol(u64* p, u64 v) { *reinterpret_cast<volatile u64*>(p) = v; }
 
 __device__ __forceinline__ Last warp_scan_last(Last v, int lane) {
     // inclusive scan of "rightmost non-empty"
@@ -104,110 +121,107 @@ __device__ __forceinline__ void pos_dir(int cdir, int read_fwd, int orientation,
     obs = __double2int_rz(o);
 }
 
+// sides only (CheckDir, CreateGraph.py:678-688)
+__device__ __forceinline__ int side_only(int cdir, int read_fwd, int orientation) {
+    int fwd = orientation == BESST_ORIENT_FR ? read_fwd : !read_fwd;
+    return (cdir && fwd) || (!cdir && !fwd);
+}
+
 template <bool VEC>
-__device__ __forceinline__ void load_i32x4(const int32_t* p, long long idx, long long n, int (&v)[K1_ITEMS]) {
+__device__ __forceinline__ void load_i32x4(const int32_t* p, long long idx, long long n, int (&v)[WT_ITEMS]) {
     if (VEC) {
         int4 t = __ldg(reinterpret_cast<const int4*>(p + idx));
         v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
     } else {
 #pragma unroll
-        for (int i = 0; i < K1_ITEMS; ++i) v[i] = (idx + i < n) ? __ldg(p + idx + i) : -1;
+        for (int i = 0; i < WT_ITEMS; ++i) v[i] = (idx + i < n) ? __ldg(p + idx + i) : -1;
     }
 }
 
+__device__ __forceinline__ int row_state(const int4& r) { return r.x & 3; }
+__device__ __forceinline__ int row_dir(const int4& r) { return (r.x >> 2) & 1; }
+__device__ __forceinline__ int row_scaf(const int4& r) { return (int)((u32)r.x >> 3); }
+
 template <bool VEC>
 __global__ void __launch_bounds__(K1_THREADS) k_extract_links(const K1Params P) {
-    __shared__ int s_tile;
-    __shared__ Last s_warp_last[K1_WARPS];
-    __shared__ Last s_pred;
-    __shared__ int s_warp_cnt[K1_WARPS];
-    __shared__ long long s_base;
     __shared__ u64 s_cnt[8];
-    __shared__ __align__(16) besst_link_tuple s_out[K1_TILE];
-
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
     int c_count = 0, c_nonuniq = 0, c_nonuniq_scaf = 0, c_dups = 0, c_toolong = 0, c_fishy = 0, c_calls = 0, c_valid = 0;
     if (threadIdx.x < 8) s_cnt[threadIdx.x] = 0;
+    const long long n = P.rec.n;
+    const long long warp_global = ((long long)blockIdx.x * K1_THREADS + threadIdx.x) >> 5;
+    const long long n_warps = ((long long)gridDim.x * K1_THREADS) >> 5;
 
-    for (;;) {
-        __syncthreads();  // protects s_tile / s_out / scan scratch of the previous tile
-        if (threadIdx.x == 0) s_tile = (int)atomicAdd(&P.globals[0], 1ull);
-        __syncthreads();
-        const int tile = s_tile;
-        if (tile >= P.n_tiles) break;
-        const long long idx0 = (long long)tile * K1_TILE + (long long)threadIdx.x * K1_ITEMS;
-        const long long n = P.rec.n;
-        const bool full = VEC && ((long long)(tile + 1) * K1_TILE <= n);
+    for (long long wt = warp_global; wt < P.n_tiles; wt += n_warps) {
+        const long long idx0 = wt * WT + (long long)lane * WT_ITEMS;
+        const bool full = VEC && ((wt + 1) * WT <= n);
 
-        int tid[K1_ITEMS], mtid[K1_ITEMS], qlen[K1_ITEMS];
-        unsigned flag[K1_ITEMS], mapq[K1_ITEMS];
+        int tid[WT_ITEMS], mtid[WT_ITEMS], qlen[WT_ITEMS];
+        u32 flag[WT_ITEMS], mapq[WT_ITEMS];
         if (full) {
             load_i32x4<true>(P.rec.tid, idx0, n, tid);
             load_i32x4<true>(P.rec.mtid, idx0, n, mtid);
             load_i32x4<true>(P.rec.qlen, idx0, n, qlen);
-            uint2 f = __ldg(reinterpret_cast<const uint2*>(P.rec.flag + idx0));
+            const uint2 f = __ldg(reinterpret_cast<const uint2*>(P.rec.flag + idx0));
             flag[0] = f.x & 0xffffu; flag[1] = f.x >> 16; flag[2] = f.y & 0xffffu; flag[3] = f.y >> 16;
-            unsigned m = __ldg(reinterpret_cast<const unsigned*>(P.rec.mapq + idx0));
+            const u32 m = __ldg(reinterpret_cast<const u32*>(P.rec.mapq + idx0));
             mapq[0] = m & 0xffu; mapq[1] = (m >> 8) & 0xffu; mapq[2] = (m >> 16) & 0xffu; mapq[3] = m >> 24;
         } else {
             load_i32x4<false>(P.rec.tid, idx0, n, tid);
             load_i32x4<false>(P.rec.mtid, idx0, n, mtid);
             load_i32x4<false>(P.rec.qlen, idx0, n, qlen);
 #pragma unroll
-            for (int i = 0; i < K1_ITEMS; ++i) {
+            for (int i = 0; i < WT_ITEMS; ++i) {
                 flag[i] = (idx0 + i < n) ? __ldg(P.rec.flag + idx0 + i) : 0u;
                 mapq[i] = (idx0 + i < n) ? __ldg(P.rec.mapq + idx0 + i) : 0u;
             }
         }
 
-        // ---- per-record classification ------------------------------------
-        bool elig[K1_ITEMS], cov[K1_ITEMS], ll[K1_ITEMS];
-        int o1[K1_ITEMS], o2[K1_ITEMS];
-        unsigned nu[K1_ITEMS], nv[K1_ITEMS];
-        bool need_pos = false;
-        int4 r1a[K1_ITEMS], r2a[K1_ITEMS];  // state, scaffold, direction, position
+        // ---- per-record classification (CreateGraph.py:118-206) ---------------------------
+        u32 elig = 0, ll = 0, cov = 0;   // one bit per item
 #pragma unroll
-        for (int i = 0; i < K1_ITEMS; ++i) {
-            elig[i] = false; cov[i] = false; ll[i] = false;
-            o1[i] = o2[i] = 0; nu[i] = nv[i] = 0;
-            bool ok = tid[i] >= 0 && mtid[i] >= 0 && tid[i] < P.n_contigs && mtid[i] < P.n_contigs;  // :118-124
+        for (int i = 0; i < WT_ITEMS; ++i) {
+            bool ok = tid[i] >= 0 && mtid[i] >= 0 && tid[i] < P.n_contigs && mtid[i] < P.n_contigs;       // :118-124
+            int4 r1 = make_int4(0, 0, 0, 0), r2 = r1;
             if (ok) {
-                r1a[i] = __ldg(reinterpret_cast<const int4*>(P.rows + tid[i]));
-                r2a[i] = __ldg(reinterpret_cast<const int4*>(P.rows + mtid[i]));
-                ok = r1a[i].x != BESST_CTG_ABSENT && r2a[i].x != BESST_CTG_ABSENT;                       // :127-130
+                r1 = __ldg(P.rows + tid[i]);
+                r2 = (mtid[i] == tid[i]) ? r1 : __ldg(P.rows + mtid[i]);
+                ok = row_state(r1) != BESST_CTG_ABSENT && row_state(r2) != BESST_CTG_ABSENT;              // :127-130
             }
             if (!ok) continue;
             c_valid++;
-            const unsigned f = flag[i];
+            const u32 f = flag[i];
             const bool unmapped = f & 0x4u, read1 = f & 0x40u, read2 = f & 0x80u;
             const int mq = (int)mapq[i];
-            cov[i] = (mq >= P.min_mapq) || mq == 0;                                                      // :138
-            const bool diff_scaf = r1a[i].y != r2a[i].y;
-            if (unmapped && read1 && diff_scaf) {                                                        // :141-163
-                int d1, d2, s1, s2;
-                pos_dir(r1a[i].z, !(f & 0x10u), P.orientation, 0, 0, 0, 0, 0.0, d1, s1);
-                pos_dir(r2a[i].z, !(f & 0x20u), P.orientation, 0, 0, 0, 0, 0.0, d2, s2);
-                unsigned n1 = 2u * (unsigned)r1a[i].y + (unsigned)s1, n2 = 2u * (unsigned)r2a[i].y + (unsigned)s2;
-                u64 key = n1 < n2 ? (((u64)n1 << 32) | n2) : (((u64)n2 << 32) | n1);
-                u64 slot = atomicAdd(&P.globals[2], 1ull);
+            if ((mq >= P.min_mapq) || mq == 0) cov |= 1u << i;                                            // :138
+            const bool diff_scaf = row_scaf(r1) != row_scaf(r2);
+            if (unmapped && read1 && diff_scaf) {                                                         // :141-163
+                const u32 n1 = 2u * (u32)row_scaf(r1) + (u32)side_only(row_dir(r1), !(f & 0x10u), P.orientation);
+                const u32 n2 = 2u * (u32)row_scaf(r2) + (u32)side_only(row_dir(r2), !(f & 0x20u), P.orientation);
+                const u64 key = n1 < n2 ? (((u64)n1 << 32) | n2) : (((u64)n2 << 32) | n1);
+                const u64 slot = atomicAdd(&P.globals[1], 1ull);
                 if ((long long)slot < P.fishy_cap) P.fishy[slot] = key;
                 c_fishy++;
             }
             const bool inter = tid[i] != mtid[i];
-            if (inter && mq == 0) c_nonuniq++;                                                           // :166-167
-            if (inter && read2 && !unmapped && mq >= P.min_mapq) {                                       // :169
-                const bool l1 = r1a[i].x == BESST_CTG_LARGE, l2 = r2a[i].x == BESST_CTG_LARGE;
+            if (inter && mq == 0) c_nonuniq++;                                                            // :166-167
+            if (inter && read2 && !unmapped && mq >= P.min_mapq) {                                        // :169
+                const bool l1 = row_state(r1) == BESST_CTG_LARGE, l2 = row_state(r2) == BESST_CTG_LARGE;
                 if (l1 && l2) {
-                    if (diff_scaf) { elig[i] = true; ll[i] = true; }                                     // :170
-                } else if (P.extend) {                                                                   // :184-206
-                    if (!(l1 || l2) ? diff_scaf : true) elig[i] = true;
+                    if (diff_scaf) { elig |= 1u << i; ll |= 1u << i; }                                    // :170
+                } else if (P.extend) {                                                                    // :184-206
+                    if (!(l1 || l2) ? diff_scaf : true) elig |= 1u << i;
                 }
             }
-            need_pos |= elig[i];
         }
 
-        if (__any_sync(0xffffffffu, need_pos)) {
-            int pos[K1_ITEMS], mpos[K1_ITEMS];
+        // ---- observations of the CreateEdge candidates (:816-833) --------------------------
+        int o1[WT_ITEMS], o2[WT_ITEMS];
+        u32 nu[WT_ITEMS], nv[WT_ITEMS];
+#pragma unroll
+        for (int i = 0; i < WT_ITEMS; ++i) { o1[i] = o2[i] = 0; nu[i] = nv[i] = 0; }
+        if (__any_sync(0xffffffffu, elig != 0)) {
+            int pos[WT_ITEMS], mpos[WT_ITEMS];
             if (full) {
                 load_i32x4<true>(P.rec.pos, idx0, n, pos);
                 load_i32x4<true>(P.rec.mpos, idx0, n, mpos);
@@ -216,192 +230,118 @@ __global__ void __launch_bounds__(K1_THREADS) k_extract_links(const K1Params P) 
                 load_i32x4<false>(P.rec.mpos, idx0, n, mpos);
             }
 #pragma unroll
-            for (int i = 0; i < K1_ITEMS; ++i) {
-                if (!elig[i]) continue;
+            for (int i = 0; i < WT_ITEMS; ++i) {
+                if (!(elig >> i & 1u)) continue;
+                const int4 r1 = __ldg(P.rows + tid[i]);    // L1 hits: gathered a moment ago
+                const int4 r2 = __ldg(P.rows + mtid[i]);
+                const u32 f = flag[i];
                 int s1, s2;
-                const unsigned f = flag[i];
-                // length, scaf_length live in the second half of the row: only link records need them
-                const int4 r1b = __ldg(reinterpret_cast<const int4*>(P.rows + tid[i]) + 1);
-                const int4 r2b = __ldg(reinterpret_cast<const int4*>(P.rows + mtid[i]) + 1);
-                pos_dir(r1a[i].z, !(f & 0x10u), P.orientation, r1a[i].w, pos[i], r1b.y, r1b.x, P.read_len, o1[i], s1);
-                pos_dir(r2a[i].z, !(f & 0x20u), P.orientation, r2a[i].w, mpos[i], r2b.y, r2b.x, P.read_len, o2[i], s2);
-                nu[i] = 2u * (unsigned)r1a[i].y + (unsigned)s1;
-                nv[i] = 2u * (unsigned)r2a[i].y + (unsigned)s2;
+                pos_dir(row_dir(r1), !(f & 0x10u), P.orientation, r1.y, pos[i], r1.w, r1.z, P.read_len, o1[i], s1);
+                pos_dir(row_dir(r2), !(f & 0x20u), P.orientation, r2.y, mpos[i], r2.w, r2.z, P.read_len, o2[i], s2);
+                nu[i] = 2u * (u32)row_scaf(r1) + (u32)s1;
+                nv[i] = 2u * (u32)row_scaf(r2) + (u32)s2;
             }
         }
 
-        // ---- coverage: warp-aggregated 64-bit atomics (:138-139) ------------
+        // ---- coverage: warp-aggregated 64-bit atomics (:138-139) ----------------------------
         {
             int t0 = -1, s0 = 0;
 #pragma unroll
-            for (int i = 0; i < K1_ITEMS; ++i)
-                if (cov[i]) {
+            for (int i = 0; i < WT_ITEMS; ++i)
+                if (cov >> i & 1u) {
                     if (t0 < 0) t0 = tid[i];
-                    if (tid[i] == t0) { s0 += qlen[i]; cov[i] = false; }
+                    if (tid[i] == t0) { s0 += qlen[i]; cov &= ~(1u << i); }
                 }
-            unsigned act = __ballot_sync(0xffffffffu, t0 >= 0);
+            const u32 act = __ballot_sync(0xffffffffu, t0 >= 0);
             if (t0 >= 0) {
-                unsigned peers = __match_any_sync(act, t0);
-                int sum = __reduce_add_sync(peers, s0);
+                const u32 peers = __match_any_sync(act, t0);
+                const int sum = __reduce_add_sync(peers, s0);
                 if (lane == __ffs(peers) - 1) atomicAdd(&P.aligned[t0], (u64)(long long)sum);
             }
+            if (__any_sync(0xffffffffu, cov != 0)) {   // a lane's 4 records straddle contigs: rare
 #pragma unroll
-            for (int i = 1; i < K1_ITEMS; ++i) {   // records of a second/third contig inside one thread: rare
-                unsigned rest = __ballot_sync(0xffffffffu, cov[i]);
-                if (rest && cov[i]) {
-                    unsigned peers = __match_any_sync(rest, tid[i]);
-                    int sum = __reduce_add_sync(peers, qlen[i]);
-                    if (lane == __ffs(peers) - 1) atomicAdd(&P.aligned[tid[i]], (u64)(long long)sum);
-                }
+                for (int i = 1; i < WT_ITEMS; ++i)
+                    if (cov >> i & 1u) atomicAdd(&P.aligned[tid[i]], (u64)(long long)qlen[i]);
             }
         }
 
-        // ---- previous CreateEdge call: rightmost-non-empty scan -------------
+        // ---- previous CreateEdge call inside the tile: rightmost-non-empty scan ---------------
         Last mine = {0, 0, 0};
 #pragma unroll
-        for (int i = 0; i < K1_ITEMS; ++i)
-            if (elig[i]) { mine.has = 1; mine.o1 = o1[i]; mine.o2 = o2[i]; }
-        Last incl = warp_scan_last(mine, lane);
-        Last excl;
-        excl.has = __shfl_up_sync(0xffffffffu, incl.has, 1);
-        excl.o1 = __shfl_up_sync(0xffffffffu, incl.o1, 1);
-        excl.o2 = __shfl_up_sync(0xffffffffu, incl.o2, 1);
-        if (lane == 0) excl.has = 0;
-        if (lane == 31) s_warp_last[warp] = incl;
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            Last tot = {0, 0, 0};
-            for (int w = 0; w < K1_WARPS; ++w)
-                if (s_warp_last[w].has) tot = s_warp_last[w];
-            // publish the tile-local value, then resolve the predecessor
-            st_vol(&P.eligA1[tile], READY | (u64)(unsigned)tot.o2);
-            st_vol(&P.eligA0[tile], READY | (tot.has ? HAS : 0) | (u64)(unsigned)tot.o1);
-            Last pred = {0, 0, 0};
-            int p = tile - 1;
-            while (p >= 0) {
-                u64 w0 = ld_vol(&P.eligP0[p]);
-                if (w0 & READY) {  // inclusive value of everything up to p
-                    u64 w1;
-                    do { w1 = ld_vol(&P.eligP1[p]); } while (!(w1 & READY));
-                    pred.has = (w0 & HAS) ? 1 : 0; pred.o1 = (int)(unsigned)w0; pred.o2 = (int)(unsigned)w1;
-                    break;
-                }
-                w0 = ld_vol(&P.eligA0[p]);
-                if (!(w0 & READY)) continue;  // spin on tile p
-                if (w0 & HAS) {
-                    u64 w1;
-                    do { w1 = ld_vol(&P.eligA1[p]); } while (!(w1 & READY));
-                    pred.has = 1; pred.o1 = (int)(unsigned)w0; pred.o2 = (int)(unsigned)w1;
-                    break;
-                }
-                --p;
-            }
-            Last inc = tot.has ? tot : pred;
-            st_vol(&P.eligP1[tile], READY | (u64)(unsigned)inc.o2);
-            st_vol(&P.eligP0[tile], READY | (inc.has ? HAS : 0) | (u64)(unsigned)inc.o1);
-            if (tile == P.n_tiles - 1) {  // halo for the next rank
-                P.counters[BESST_CNT_LAST_OBS1] = (u64)(long long)(inc.has ? inc.o1 : P.halo1);
-                P.counters[BESST_CNT_LAST_OBS2] = (u64)(long long)(inc.has ? inc.o2 : P.halo2);
-            }
-            s_pred = pred;
-        }
-        __syncthreads();
-        Last prev = s_pred;
-        for (int w = 0; w < warp; ++w)
-            if (s_warp_last[w].has) prev = s_warp_last[w];
-        if (excl.has) prev = excl;
-        int p1 = prev.has ? prev.o1 : P.halo1, p2 = prev.has ? prev.o2 : P.halo2;
+        for (int i = 0; i < WT_ITEMS; ++i)
+            if (elig >> i & 1u) { mine.has = 1; mine.o1 = o1[i]; mine.o2 = o2[i]; }
+        const Last incl = warp_scan_last(mine, lane);
+        Last prev;
+        prev.has = __shfl_up_sync(0xffffffffu, incl.has, 1);
+        prev.o1 = __shfl_up_sync(0xffffffffu, incl.o1, 1);
+        prev.o2 = __shfl_up_sync(0xffffffffu, incl.o2, 1);
+        if (lane == 0) prev.has = 0;
 
-        // ---- CreateEdge: duplicate test, acceptance test, counters (:835-870)
-        bool acc[K1_ITEMS];
-        int n_acc = 0;
+        // ---- CreateEdge: duplicate test, acceptance test, counters (:835-870) -------------------
+        // The tile's first call has no in-tile predecessor: assumed "not a duplicate" here and
+        // settled by the aggregate scan.
+        u32 acc = 0, first_flags = 0;
+        int first_o1 = 0, first_o2 = 0, n_acc = 0;
 #pragma unroll
-        for (int i = 0; i < K1_ITEMS; ++i) {
-            acc[i] = false;
-            if (!elig[i]) continue;
+        for (int i = 0; i < WT_ITEMS; ++i) {
+            if (!(elig >> i & 1u)) continue;
             c_calls++;
             const bool mq0 = mapq[i] == 0;
             if (mq0) c_nonuniq_scaf++;
-            const bool dup = (o1[i] == p1 && o2[i] == p2);
-            p1 = o1[i]; p2 = o2[i];
+            const bool dup = prev.has && o1[i] == prev.o1 && o2[i] == prev.o2;
             bool is_dupl = false;
             if (dup) { c_dups++; is_dupl = P.detect_dup; }
             const bool pass = (double)((long long)o1[i] + o2[i]) < P.threshold && o1[i] > 25 && o2[i] > 25;
-            if (!is_dupl) {
-                if (pass) { c_count++; acc[i] = true; n_acc++; } else c_toolong++;
+            const bool second = (ll >> i & 1u) && P.extend && P.scoring;
+            if (!prev.has) {   // only possible for the tile's first call
+                first_flags = AGG_HAS | (pass ? AGG_PASS : 0u) | (second ? AGG_SECOND : 0u) | (mq0 ? AGG_MQ0 : 0u);
+                first_o1 = o1[i]; first_o2 = o2[i];
             }
-            if (ll[i] && P.extend && P.scoring && !is_dupl) {  // second call into G_prime (:180-183)
-                if (mq0) c_nonuniq_scaf++;
-                const bool dup2 = (o1[i] == -1 && o2[i] == -1);
-                if (dup2) c_dups++;
-                if (!(dup2 && P.detect_dup)) { if (pass) c_count++; else c_toolong++; }
+            prev.has = 1; prev.o1 = o1[i]; prev.o2 = o2[i];
+            if (!is_dupl) {
+                if (pass) { c_count++; acc |= 1u << i; n_acc++; } else c_toolong++;
+                if (second) {   // second call into G_prime (:180-183); prev_obs was reset to -1
+                    if (mq0) c_nonuniq_scaf++;
+                    const bool dup2 = (o1[i] == -1 && o2[i] == -1);
+                    if (dup2) c_dups++;
+                    if (!(dup2 && P.detect_dup)) { if (pass) c_count++; else c_toolong++; }
+                }
             }
         }
 
-        // ---- ordered compaction of the accepted tuples ----------------------
+        // ---- ordered compaction into the tile's scratch slot ------------------------------------
         int incl_cnt = n_acc;
 #pragma unroll
         for (int off = 1; off < 32; off <<= 1) {
-            int t = __shfl_up_sync(0xffffffffu, incl_cnt, off);
+            const int t = __shfl_up_sync(0xffffffffu, incl_cnt, off);
             if (lane >= off) incl_cnt += t;
         }
-        if (lane == 31) s_warp_cnt[warp] = incl_cnt;
-        __syncthreads();
-        int tile_acc = 0, warp_off = 0;
+        long long dst = wt * WT + (incl_cnt - n_acc);
 #pragma unroll
-        for (int w = 0; w < K1_WARPS; ++w) {
-            if (w < warp) warp_off += s_warp_cnt[w];
-            tile_acc += s_warp_cnt[w];
+        for (int i = 0; i < WT_ITEMS; ++i)
+            if (acc >> i & 1u) {
+                int4 t;
+                if (nu[i] < nv[i]) { t.x = (int)nu[i]; t.y = (int)nv[i]; t.z = o1[i]; t.w = o2[i]; }
+                else { t.x = (int)nv[i]; t.y = (int)nu[i]; t.z = o2[i]; t.w = o1[i]; }
+                reinterpret_cast<int4*>(P.scratch)[dst++] = t;
+            }
+
+        // ---- aggregate ---------------------------------------------------------------------------
+        const u32 has_mask = __ballot_sync(0xffffffffu, first_flags != 0);
+        const int fl = has_mask ? __ffs(has_mask) - 1 : 0;
+        const u32 ff = __shfl_sync(0xffffffffu, first_flags, fl);
+        const int f1 = __shfl_sync(0xffffffffu, first_o1, fl), f2 = __shfl_sync(0xffffffffu, first_o2, fl);
+        const int l1v = __shfl_sync(0xffffffffu, incl.o1, 31), l2v = __shfl_sync(0xffffffffu, incl.o2, 31);
+        const int total = __shfl_sync(0xffffffffu, incl_cnt, 31);
+        if (lane == 0) {
+            int4* a = reinterpret_cast<int4*>(P.aggs + wt);
+            a[0] = make_int4((int)(has_mask ? ff : 0u), f1, f2, l1v);
+            a[1] = make_int4(l2v, total, 0, 0);
+            a[2] = make_int4(0, 0, 0, 0);
         }
-        if (warp == 0) {  // decoupled look-back on the accepted counts
-            if (lane == 0) st_vol(&P.acc[tile], (tile == 0 ? ST_INC : ST_AGG) | (u64)tile_acc);
-            long long excl_sum = 0;
-            if (tile > 0) {
-                int p = tile - 1 - lane;
-                for (;;) {
-                    u64 w;
-                    unsigned ready;
-                    do {
-                        w = (p >= 0) ? ld_vol(&P.acc[p]) : ST_INC;
-                        ready = __ballot_sync(0xffffffffu, (w & ST_MASK) != 0);
-                    } while (ready != 0xffffffffu);
-                    unsigned inc_mask = __ballot_sync(0xffffffffu, (w & ST_MASK) == ST_INC);
-                    long long v = (long long)(w & ~ST_MASK);
-                    if (inc_mask) {
-                        int first = __ffs(inc_mask) - 1;
-                        if (lane > first) v = 0;
-                    }
-#pragma unroll
-                    for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
-                    excl_sum += v;
-                    if (inc_mask) break;
-                    p -= 32;
-                }
-                if (lane == 0) st_vol(&P.acc[tile], ST_INC | (u64)(excl_sum + tile_acc));
-            }
-            if (lane == 0) {
-                s_base = excl_sum;
-                if (tile == P.n_tiles - 1) P.globals[1] = (u64)(excl_sum + tile_acc);
-            }
-        }
-        int local = warp_off + incl_cnt - n_acc;
-#pragma unroll
-        for (int i = 0; i < K1_ITEMS; ++i)
-            if (acc[i]) {
-                besst_link_tuple t;
-                if (nu[i] < nv[i]) { t.u = nu[i]; t.v = nv[i]; t.obs_u = o1[i]; t.obs_v = o2[i]; }
-                else { t.u = nv[i]; t.v = nu[i]; t.obs_u = o2[i]; t.obs_v = o1[i]; }
-                s_out[local++] = t;
-            }
-        __syncthreads();
-        const long long base = s_base;
-        const int4* src = reinterpret_cast<const int4*>(s_out);
-        int4* dst = reinterpret_cast<int4*>(P.out);
-        for (int j = threadIdx.x; j < tile_acc; j += K1_THREADS)
-            if (base + j < P.out_cap) dst[base + j] = src[j];
     }
 
-    // ---- flush the per-CTA counters -------------------------------------------
+    // ---- flush the per-thread counters ------------------------------------------------------------
     __syncthreads();
     const int local_cnt[8] = {c_count, c_nonuniq, c_nonuniq_scaf, c_dups, c_toolong, c_fishy, c_calls, c_valid};
 #pragma unroll
@@ -415,17 +355,401 @@ __global__ void __launch_bounds__(K1_THREADS) k_extract_links(const K1Params P) 
     if (threadIdx.x < 8 && s_cnt[threadIdx.x]) atomicAdd(&P.counters[threadIdx.x], s_cnt[threadIdx.x]);
 }
 
+// ---- scan over aggregates ------------------------------------------------------------------------
+// One block of SC_THREADS threads scans SC_THREADS aggregates: thread t owns aggregate t.  `carry`
+// is the last CreateEdge observation before the block's first aggregate (has = 0: unknown, the
+// block's first call stays unresolved and is described in the block's own aggregate).
+struct ScanResult {
+    u32 cnt_adj;      // accepted tuples of this aggregate after the boundary verdict
+    u64 excl;         // sum of cnt_adj over the preceding aggregates of the block
+    bool drop_first;  // boundary duplicate that was an accepted tuple: skip it
+    Last before;      // last CreateEdge call before this aggregate (has = 0: unknown)
+    Agg block;        // aggregate of the whole block (valid in every thread)
+};
+
+struct ScanSmem {
+    Last w_last[SC_THREADS / 32];
+    u32 w_cnt[SC_THREADS / 32];
+    int w_corr[4][SC_THREADS / 32];
+    int first_thread;
+    Agg first;
+};
+
+__device__ __forceinline__ ScanResult block_scan_aggs(const Agg& a, Last carry, int detect_dup, ScanSmem& S) {
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const bool has = a.flags & AGG_HAS;
+    Last mine = {has ? 1 : 0, a.last_o1, a.last_o2};
+    const Last incl = warp_scan_last(mine, lane);
+    Last excl;
+    excl.has = __shfl_up_sync(0xffffffffu, incl.has, 1);
+    excl.o1 = __shfl_up_sync(0xffffffffu, incl.o1, 1);
+    excl.o2 = __shfl_up_sync(0xffffffffu, incl.o2, 1);
+    if (lane == 0) excl.has = 0;
+    if (lane == 31) S.w_last[warp] = incl;
+    if (t == 0) S.first_thread = -1;
+    __syncthreads();
+    Last before = carry;
+    for (int w = 0; w < warp; ++w)
+        if (S.w_last[w].has) before = S.w_last[w];
+    if (!excl.has) excl = before;
+
+    // boundary verdict for this aggregate's first call
+    int dups = a.dups, count_corr = a.count_corr, toolong_corr = a.toolong_corr, nus_corr = a.nus_corr;
+    u32 cnt_adj = a.cnt;
+    bool drop_first = false;
+    if (has) {
+        if (excl.has) {
+            if (a.first_o1 == excl.o1 && a.first_o2 == excl.o2) {
+                dups += 1;
+                if (detect_dup) {   // the call returned early (:835-838): undo what the tile assumed
+                    const int calls = 1 + ((a.flags & AGG_SECOND) ? 1 : 0);
+                    if (a.flags & AGG_PASS) { count_corr -= calls; cnt_adj -= 1; drop_first = true; }
+                    else toolong_corr -= calls;
+                    if ((a.flags & AGG_SECOND) && (a.flags & AGG_MQ0)) nus_corr -= 1;
+                }
+            }
+        } else {
+            S.first_thread = t;   // unique: the first aggregate with a call and nothing known before it
+        }
+    }
+    // sums
+    u32 incl_cnt = cnt_adj;
+    int c0 = dups, c1 = count_corr, c2 = toolong_corr, c3 = nus_corr;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        const u32 v = __shfl_up_sync(0xffffffffu, incl_cnt, off);
+        if (lane >= off) incl_cnt += v;
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        c0 += __shfl_xor_sync(0xffffffffu, c0, off);
+        c1 += __shfl_xor_sync(0xffffffffu, c1, off);
+        c2 += __shfl_xor_sync(0xffffffffu, c2, off);
+        c3 += __shfl_xor_sync(0xffffffffu, c3, off);
+    }
+    if (lane == 31) S.w_cnt[warp] = incl_cnt;
+    if (lane == 0) { S.w_corr[0][warp] = c0; S.w_corr[1][warp] = c1; S.w_corr[2][warp] = c2; S.w_corr[3][warp] = c3; }
+    __syncthreads();
+    if (S.first_thread == t) S.first = a;
+    __syncthreads();
+    ScanResult R;
+    u64 pre = 0, tot = 0;
+    int s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+    Last blk_last = {0, 0, 0};
+    for (int w = 0; w < SC_THREADS / 32; ++w) {
+        if (w < warp) pre += S.w_cnt[w];
+        tot += S.w_cnt[w];
+        s0 += S.w_corr[0][w]; s1 += S.w_corr[1][w]; s2 += S.w_corr[2][w]; s3 += S.w_corr[3][w];
+        if (S.w_last[w].has) blk_last = S.w_last[w];
+    }
+    R.cnt_adj = cnt_adj;
+    R.excl = pre + incl_cnt - cnt_adj;
+    R.drop_first = drop_first;
+    R.before = excl;
+    R.block.flags = 0;
+    R.block.first_o1 = R.block.first_o2 = 0;
+    if (S.first_thread >= 0) {
+        R.block.flags = S.first.flags & (AGG_PASS | AGG_SECOND | AGG_MQ0);
+        R.block.first_o1 = S.first.first_o1;
+        R.block.first_o2 = S.first.first_o2;
+    }
+    if (blk_last.has) R.block.flags |= AGG_HAS;
+    // a block whose calls were all resolved against `carry` has no open first call; a block scanned
+    // without carry has one exactly when it has any call
+    R.block.last_o1 = blk_last.o1; R.block.last_o2 = blk_last.o2;
+    R.block.cnt = (u32)tot;
+    R.block.dups = s0; R.block.count_corr = s1; R.block.toolong_corr = s2; R.block.nus_corr = s3;
+    R.block.pad0 = R.block.pad1 = 0;
+    return R;
+}
+
+__device__ __forceinline__ Agg load_agg(const Agg* p, long long i, long long n) {
+    Agg a;
+    if (i < n) {
+        const int4* q = reinterpret_cast<const int4*>(p + i);
+        const int4 x = q[0], y = q[1], z = q[2];
+        a.flags = (u32)x.x; a.first_o1 = x.y; a.first_o2 = x.z; a.last_o1 = x.w;
+        a.last_o2 = y.x; a.cnt = (u32)y.y; a.dups = y.z; a.count_corr = y.w;
+        a.toolong_corr = z.x; a.nus_corr = z.y; a.pad0 = a.pad1 = 0;
+    } else {
+        a.flags = 0; a.first_o1 = a.first_o2 = a.last_o1 = a.last_o2 = 0; a.cnt = 0;
+        a.dups = a.count_corr = a.toolong_corr = a.nus_corr = 0; a.pad0 = a.pad1 = 0;
+    }
+    return a;
+}
+
+// level 0 -> level 1: one aggregate per chunk of SC_THREADS tiles
+__global__ void __launch_bounds__(SC_THREADS) k_tile_reduce(const Agg* __restrict__ aggs, long long n_tiles, Agg* chunk_aggs,
+                                                            int detect_dup) {
+    __shared__ ScanSmem S;
+    const long long i = (long long)blockIdx.x * SC_THREADS + threadIdx.x;
+    const Agg a = load_agg(aggs, i, n_tiles);
+    const Last none = {0, 0, 0};
+    const ScanResult R = block_scan_aggs(a, none, detect_dup, S);
+    if (threadIdx.x == 0) chunk_aggs[blockIdx.x] = R.block;
+}
+
+// level 1: one block walks the chunk aggregates in groups of SC_THREADS, carrying (last call,
+// offset, corrections); writes what every chunk receives, the totals and the next rank's halo
+__global__ void __launch_bounds__(SC_THREADS) k_chunk_resolve(const Agg* __restrict__ chunk_aggs, long long n_chunks,
+                                                              ChunkIn* chunk_in, u64* tile_off_end, int halo1, int halo2,
+                                                              int detect_dup, u64* counters, u64* globals) {
+    __shared__ ScanSmem S;
+    __shared__ Last s_carry;
+    __shared__ u64 s_off;
+    __shared__ long long s_corr[4];
+    if (threadIdx.x == 0) {
+        s_carry.has = 1; s_carry.o1 = halo1; s_carry.o2 = halo2;   // counters(..., prev_obs1=-1, prev_obs2=-1) :98
+        s_off = 0;
+        s_corr[0] = s_corr[1] = s_corr[2] = s_corr[3] = 0;
+    }
+    __syncthreads();
+    for (long long base = 0; base < n_chunks; base += SC_THREADS) {
+        const long long i = base + threadIdx.x;
+        const Agg a = load_agg(chunk_aggs, i, n_chunks);
+        const Last carry = s_carry;
+        const u64 off0 = s_off;
+        const ScanResult R = block_scan_aggs(a, carry, detect_dup, S);
+        if (i < n_chunks) {
+            ChunkIn in;
+            in.carry_o1 = R.before.o1; in.carry_o2 = R.before.o2; in.offset = off0 + R.excl;
+            chunk_in[i] = in;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            if (R.block.flags & AGG_HAS) { s_carry.o1 = R.block.last_o1; s_carry.o2 = R.block.last_o2; }
+            s_off = off0 + R.block.cnt;
+            s_corr[0] += R.block.dups; s_corr[1] += R.block.count_corr; s_corr[2] += R.block.toolong_corr;
+            s_corr[3] += R.block.nus_corr;
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        globals[0] = s_off;
+        *tile_off_end = s_off;
+        counters[BESST_CNT_DUPLICATES] += (u64)s_corr[0];
+        counters[BESST_CNT_COUNT] += (u64)s_corr[1];
+        counters[BESST_CNT_TOO_LONG] += (u64)s_corr[2];
+        counters[BESST_CNT_NON_UNIQUE_SCAF] += (u64)s_corr[3];
+        counters[BESST_CNT_LAST_OBS1] = (u64)(long long)s_carry.o1;
+        counters[BESST_CNT_LAST_OBS2] = (u64)(long long)s_carry.o2;
+    }
+}
+
+// level 0 again, now with what each chunk receives: exact output offset of every tile
+__global__ void __launch_bounds__(SC_THREADS) k_tile_offsets(const Agg* __restrict__ aggs, long long n_tiles,
+                                                             const ChunkIn* __restrict__ chunk_in, u64* tile_off,
+                                                             int detect_dup) {
+    __shared__ ScanSmem S;
+    const long long i = (long long)blockIdx.x * SC_THREADS + threadIdx.x;
+    const Agg a = load_agg(aggs, i, n_tiles);
+    const ChunkIn in = chunk_in[blockIdx.x];
+    const Last carry = {1, in.carry_o1, in.carry_o2};
+    const ScanResult R = block_scan_aggs(a, carry, detect_dup, S);
+    if (i < n_tiles) tile_off[i] = (in.offset + R.excl) | (R.drop_first ? OFF_DROP : 0ull);
+}
+
+// tile-local scratch runs -> the final BAM-ordered tuple array
+__global__ void __launch_bounds__(256) k_compact_tuples(const besst_link_tuple* __restrict__ scratch,
+                                                        const u64* __restrict__ tile_off, long long n_tiles,
+                                                        besst_link_tuple* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const long long warp_global = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
+    const int4* src_base = reinterpret_cast<const int4*>(scratch);
+    int4* dst_base = reinterpret_cast<int4*>(out);
+    for (long long wt = warp_global; wt < n_tiles; wt += n_warps) {
+        const u64 a = __ldg(tile_off + wt), b = __ldg(tile_off + wt + 1);
+        const long long off = (long long)(a & OFF_MASK);
+        const int cnt = (int)((long long)(b & OFF_MASK) - off);
+        const int4* src = src_base + wt * WT + ((a & OFF_DROP) ? 1 : 0);
+        for (int j = lane; j < cnt; j += 32) dst_base[off + j] = __ldg(src + j);
+    }
+}
+
+// ---- multi-GPU: stable partition of tuples / fishy keys by destination rank ----------------------
+// dest = hash(u, v) mod world.  Order inside a destination bucket is BAM order, so concatenating the
+// buckets received from ranks 0..W-1 reproduces the global BAM order per edge.
+constexpr int PT_THREADS = 256;
+constexpr int PT_ITEMS = 8;
+constexpr int PT_TILE = PT_THREADS * PT_ITEMS;
+constexpr int PT_MAX_WORLD = 16;
+
+__device__ __forceinline__ u32 edge_dest(u32 u, u32 v, int world) {
+    u64 x = ((u64)u << 32) | v;
+    x ^= x >> 33; x *= 0xff51afd7ed558ccdull; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ull; x ^= x >> 33;
+    return (u32)(x % (u64)world);
+}
+
+template <bool TUPLES>
+__device__ __forceinline__ u32 item_dest(const void* in, long long i, int world) {
+    if (TUPLES) {
+        const uint2 uv = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const besst_link_tuple*>(in) + i));
+        return edge_dest(uv.x, uv.y, world);
+    }
+    const u64 k = __ldg(reinterpret_cast<const u64*>(in) + i);
+    return edge_dest((u32)(k >> 32), (u32)k, world);
+}
+
+// per-tile destination histogram: counts[d * n_tiles + tile]
+template <bool TUPLES>
+__global__ void __launch_bounds__(PT_THREADS) k_partition_count(const void* __restrict__ in, long long n, int world,
+                                                                u32* __restrict__ counts, int n_tiles) {
+    __shared__ u32 s_h[PT_MAX_WORLD];
+    if (threadIdx.x < PT_MAX_WORLD) s_h[threadIdx.x] = 0;
+    __syncthreads();
+    const long long base = (long long)blockIdx.x * PT_TILE;
+    u32 local[PT_MAX_WORLD];
+#pragma unroll
+    for (int d = 0; d < PT_MAX_WORLD; ++d) local[d] = 0;
+#pragma unroll
+    for (int k = 0; k < PT_ITEMS; ++k) {
+        const long long i = base + k * PT_THREADS + threadIdx.x;
+        if (i < n) {
+            const u32 d = item_dest<TUPLES>(in, i, world);
+#pragma unroll
+            for (int q = 0; q < PT_MAX_WORLD; ++q) local[q] += (q == (int)d);
+        }
+    }
+#pragma unroll
+    for (int d = 0; d < PT_MAX_WORLD; ++d) {
+        u32 v = local[d];
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+        if ((threadIdx.x & 31) == 0 && v) atomicAdd(&s_h[d], v);
+    }
+    __syncthreads();
+    if (threadIdx.x < world) counts[(size_t)threadIdx.x * n_tiles + blockIdx.x] = s_h[threadIdx.x];
+}
+
+// exclusive scan of counts[0 .. len) in place (64-bit carry, single block); bucket totals -> totals[d]
+__global__ void __launch_bounds__(1024) k_partition_scan(u32* counts, int n_tiles, int world, u64* starts, u64* totals) {
+    __shared__ u64 s_w[32];
+    __shared__ u64 s_carry;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
+    for (int d = 0; d < world; ++d) {
+        const u64 bucket_start = s_carry;
+        if (threadIdx.x == 0) starts[d] = bucket_start;
+        u32* c = counts + (size_t)d * n_tiles;
+        for (int base = 0; base < n_tiles; base += 1024) {
+            const int i = base + threadIdx.x;
+            const u64 v = i < n_tiles ? c[i] : 0;
+            u64 incl = v;
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) {
+                const u64 t = __shfl_up_sync(0xffffffffu, incl, off);
+                if (lane >= off) incl += t;
+            }
+            if (lane == 31) s_w[warp] = incl;
+            __syncthreads();
+            u64 pre = 0, tot = 0;
+            for (int w = 0; w < 32; ++w) { if (w < warp) pre += s_w[w]; tot += s_w[w]; }
+            const u64 carry = s_carry;
+            // offsets inside a bucket fit 32 bits (n < 2^30); the bucket start is added by the scatter
+            if (i < n_tiles) c[i] = (u32)(carry - bucket_start + pre + incl - v);
+            __syncthreads();
+            if (threadIdx.x == 0) s_carry = carry + tot;
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) totals[d] = s_carry - bucket_start;
+    }
+}
+
+template <bool TUPLES>
+__global__ void __launch_bounds__(PT_THREADS) k_partition_scatter(const void* __restrict__ in, long long n, int world,
+                                                                  const u32* __restrict__ offs, int n_tiles,
+                                                                  const u64* __restrict__ starts, void* __restrict__ out) {
+    __shared__ u32 s_wcnt[PT_THREADS / 32][PT_MAX_WORLD];
+    __shared__ u64 s_base[PT_MAX_WORLD];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long base = (long long)blockIdx.x * PT_TILE + (long long)threadIdx.x * PT_ITEMS;   // blocked: keeps order
+    u32 dest[PT_ITEMS];
+    u32 local[PT_MAX_WORLD];
+#pragma unroll
+    for (int d = 0; d < PT_MAX_WORLD; ++d) local[d] = 0;
+#pragma unroll
+    for (int k = 0; k < PT_ITEMS; ++k) {
+        dest[k] = 0xffffffffu;
+        if (base + k < n) {
+            dest[k] = item_dest<TUPLES>(in, base + k, world);
+#pragma unroll
+            for (int q = 0; q < PT_MAX_WORLD; ++q) local[q] += (q == (int)dest[k]);
+        }
+    }
+    // exclusive scan over threads, per destination
+    u32 excl[PT_MAX_WORLD];
+#pragma unroll
+    for (int d = 0; d < PT_MAX_WORLD; ++d) {
+        u32 incl = local[d];
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const u32 t = __shfl_up_sync(0xffffffffu, incl, off);
+            if (lane >= off) incl += t;
+        }
+        excl[d] = incl - local[d];
+        if (lane == 31) s_wcnt[warp][d] = incl;
+    }
+    if (threadIdx.x < world) s_base[threadIdx.x] = starts[threadIdx.x] + offs[(size_t)threadIdx.x * n_tiles + blockIdx.x];
+    __syncthreads();
+#pragma unroll
+    for (int d = 0; d < PT_MAX_WORLD; ++d)
+        for (int w = 0; w < warp; ++w) excl[d] += s_wcnt[w][d];
+#pragma unroll
+    for (int k = 0; k < PT_ITEMS; ++k) {
+        if (dest[k] == 0xffffffffu) continue;
+        u32 r = 0;
+#pragma unroll
+        for (int q = 0; q < PT_MAX_WORLD; ++q)
+            if (q == (int)dest[k]) { r = excl[q]; excl[q] += 1; }
+        const u64 o = s_base[dest[k]] + r;
+        if (TUPLES) reinterpret_cast<int4*>(out)[o] = __ldg(reinterpret_cast<const int4*>(in) + base + k);
+        else reinterpret_cast<u64*>(out)[o] = __ldg(reinterpret_cast<const u64*>(in) + base + k);
+    }
+}
+
+template <bool TUPLES>
+int partition_impl(besst_ctx* ctx, const void* in, int64_t n, int world, void* out, int64_t* counts_host) {
+    for (int d = 0; d < world; ++d) counts_host[d] = 0;
+    if (n == 0) return BESST_OK;
+    const int n_tiles = (int)((n + PT_TILE - 1) / PT_TILE);
+    BESST_CUDA_TRY(ctx, ctx->part_state.ensure(4 * (size_t)n_tiles * world + 16 * PT_MAX_WORLD + 64));
+    u64* starts = ctx->part_state.as<u64>();
+    u64* totals = starts + PT_MAX_WORLD;
+    u32* counts = reinterpret_cast<u32*>(totals + PT_MAX_WORLD);
+    { KTimer kt(ctx, BESST_K_PARTITION); k_partition_count<TUPLES><<<n_tiles, PT_THREADS, 0, ctx->stream>>>(in, n, world, counts, n_tiles); }
+    { KTimer kt(ctx, BESST_K_PARTITION); k_partition_scan<<<1, 1024, 0, ctx->stream>>>(counts, n_tiles, world, starts, totals); }
+    { KTimer kt(ctx, BESST_K_PARTITION); k_partition_scatter<TUPLES><<<n_tiles, PT_THREADS, 0, ctx->stream>>>(in, n, world, counts, n_tiles, starts, out); }
+    BESST_CUDA_TRY(ctx, cudaGetLastError());
+    u64 h[PT_MAX_WORLD];
+    BESST_CUDA_TRY(ctx, cudaMemcpyAsync(h, totals, 8 * world, cudaMemcpyDeviceToHost, ctx->stream));
+    BESST_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    for (int d = 0; d < world; ++d) counts_host[d] = (int64_t)h[d];
+    return BESST_OK;
+}
+
 }  // namespace
+
+int besst_launch_partition(besst_ctx* ctx, int world, besst_link_tuple* out_tuples, uint64_t* out_fishy,
+                           int64_t* tuple_counts, int64_t* fishy_counts) {
+    if (world < 1 || world > PT_MAX_WORLD) { ctx->err = "partition: world size must be 1..16"; return BESST_E_INVALID; }
+    if (ctx->n_tuples >= (1ll << 30) || ctx->n_fishy_keys >= (1ll << 30)) { ctx->err = "partition: more than 2^30 items"; return BESST_E_INVALID; }
+    int rc = partition_impl<true>(ctx, ctx->tuples.p, ctx->n_tuples, world, out_tuples, tuple_counts);
+    if (rc) return rc;
+    return partition_impl<false>(ctx, ctx->fishy_keys.p, ctx->n_fishy_keys, world, out_fishy, fishy_counts);
+}
 
 int besst_launch_extract(besst_ctx* ctx, const besst_lib_params& p, const DeviceRecords& rec) {
     const int64_t n = rec.n;
-    const int64_t n_tiles64 = (n + K1_TILE - 1) / K1_TILE;
-    if (n_tiles64 > 0x7fffffff) { ctx->err = "too many records for one call"; return BESST_E_INVALID; }
-    const int n_tiles = (int)n_tiles64;
+    const int64_t n_tiles = (n + WT - 1) / WT;
+    const int64_t n_chunks = (n_tiles + SC_THREADS - 1) / SC_THREADS;
+    if (n_chunks > 0x7fffffff) { ctx->err = "too many records for one call"; return BESST_E_INVALID; }
     BESST_CUDA_TRY(ctx, ctx->aligned.ensure(sizeof(u64) * (size_t)(ctx->n_contigs + 1)));
     BESST_CUDA_TRY(ctx, ctx->counters.ensure(sizeof(u64) * (BESST_N_COUNTERS + 8)));
-    BESST_CUDA_TRY(ctx, ctx->tile_state.ensure(sizeof(u64) * 5 * (size_t)(n_tiles + 1)));
-    if (ctx->tuples_cap == 0) ctx->tuples_cap = n / 2 + 4096;
+    BESST_CUDA_TRY(ctx, ctx->tile_aggs.ensure(sizeof(Agg) * (size_t)(n_tiles + n_chunks + 2)));
+    BESST_CUDA_TRY(ctx, ctx->tile_state.ensure(sizeof(u64) * (size_t)(n_tiles + 2) + sizeof(ChunkIn) * (size_t)(n_chunks + 1)));
+    BESST_CUDA_TRY(ctx, ctx->scratch_tuples.ensure(sizeof(besst_link_tuple) * (size_t)(n_tiles > 0 ? n_tiles : 1) * WT));
     if (ctx->fishy_cap == 0) ctx->fishy_cap = n / 8 + 4096;
 
     bool vec = true;
@@ -436,53 +760,67 @@ int besst_launch_extract(besst_ctx* ctx, const besst_lib_params& p, const Device
     if (vec) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_extract_links<true>, K1_THREADS, 0);
     else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_extract_links<false>, K1_THREADS, 0);
     if (per_sm < 1) per_sm = 1;
-    int grid = ctx->sm_count * per_sm;
-    if (grid > n_tiles) grid = n_tiles > 0 ? n_tiles : 1;
+    long long grid = (long long)ctx->sm_count * per_sm;
+    const long long max_grid = (n_tiles + (K1_THREADS / 32) - 1) / (K1_THREADS / 32);
+    if (grid > max_grid) grid = max_grid > 0 ? max_grid : 1;
+
+    Agg* aggs = ctx->tile_aggs.as<Agg>();
+    Agg* chunk_aggs = aggs + n_tiles + 1;
+    u64* tile_off = ctx->tile_state.as<u64>();
+    ChunkIn* chunk_in = reinterpret_cast<ChunkIn*>(tile_off + n_tiles + 2);
+    u64* counters = ctx->counters.as<u64>();
+    u64* globals = counters + BESST_N_COUNTERS;
 
     for (int attempt = 0; attempt < 3; ++attempt) {
-        BESST_CUDA_TRY(ctx, ctx->tuples.ensure(sizeof(besst_link_tuple) * (size_t)ctx->tuples_cap));
         BESST_CUDA_TRY(ctx, ctx->fishy_keys.ensure(sizeof(u64) * (size_t)ctx->fishy_cap));
         BESST_CUDA_TRY(ctx, cudaMemsetAsync(ctx->aligned.p, 0, sizeof(u64) * (size_t)(ctx->n_contigs + 1), ctx->stream));
-        BESST_CUDA_TRY(ctx, cudaMemsetAsync(ctx->counters.p, 0, sizeof(u64) * (BESST_N_COUNTERS + 8), ctx->stream));
-        BESST_CUDA_TRY(ctx, cudaMemsetAsync(ctx->tile_state.p, 0, sizeof(u64) * 5 * (size_t)(n_tiles + 1), ctx->stream));
+        BESST_CUDA_TRY(ctx, cudaMemsetAsync(counters, 0, sizeof(u64) * (BESST_N_COUNTERS + 8), ctx->stream));
         K1Params P;
         P.rec = rec;
-        P.rows = ctx->rows.as<Row>();
+        P.rows = ctx->rows_packed.as<int4>();
         P.n_contigs = (int)ctx->n_contigs;
         P.orientation = p.orientation; P.min_mapq = p.min_mapq; P.detect_dup = p.detect_duplicate;
         P.extend = p.extend_paths; P.scoring = !p.no_score;
         P.read_len = p.read_len; P.threshold = p.ins_size_threshold;
-        P.halo1 = p.halo_prev_obs1; P.halo2 = p.halo_prev_obs2;
-        P.out = ctx->tuples.as<besst_link_tuple>(); P.out_cap = ctx->tuples_cap;
+        P.scratch = ctx->scratch_tuples.as<besst_link_tuple>();
+        P.aggs = aggs;
         P.fishy = ctx->fishy_keys.as<u64>(); P.fishy_cap = ctx->fishy_cap;
         P.aligned = ctx->aligned.as<u64>();
-        P.counters = ctx->counters.as<u64>();
-        P.globals = ctx->counters.as<u64>() + BESST_N_COUNTERS;
-        u64* ts = ctx->tile_state.as<u64>();
-        const size_t stride = (size_t)(n_tiles + 1);
-        P.eligA0 = ts; P.eligA1 = ts + stride; P.eligP0 = ts + 2 * stride; P.eligP1 = ts + 3 * stride; P.acc = ts + 4 * stride;
+        P.counters = counters;
+        P.globals = globals;
         P.n_tiles = n_tiles;
         if (n_tiles > 0) {
-            KTimer kt(ctx, BESST_K_EXTRACT);
-            if (vec) k_extract_links<true><<<grid, K1_THREADS, 0, ctx->stream>>>(P);
-            else k_extract_links<false><<<grid, K1_THREADS, 0, ctx->stream>>>(P);
+            {
+                KTimer kt(ctx, BESST_K_EXTRACT);
+                if (vec) k_extract_links<true><<<(unsigned)grid, K1_THREADS, 0, ctx->stream>>>(P);
+                else k_extract_links<false><<<(unsigned)grid, K1_THREADS, 0, ctx->stream>>>(P);
+            }
+            { KTimer kt(ctx, BESST_K_TILE_SCAN); k_tile_reduce<<<(unsigned)n_chunks, SC_THREADS, 0, ctx->stream>>>(aggs, n_tiles, chunk_aggs, p.detect_duplicate); }
+            { KTimer kt(ctx, BESST_K_TILE_SCAN); k_chunk_resolve<<<1, SC_THREADS, 0, ctx->stream>>>(chunk_aggs, n_chunks, chunk_in, tile_off + n_tiles, p.halo_prev_obs1, p.halo_prev_obs2, p.detect_duplicate, counters, globals); }
+            { KTimer kt(ctx, BESST_K_TILE_SCAN); k_tile_offsets<<<(unsigned)n_chunks, SC_THREADS, 0, ctx->stream>>>(aggs, n_tiles, chunk_in, tile_off, p.detect_duplicate); }
+            BESST_CUDA_TRY(ctx, cudaGetLastError());
+        } else {
+            const int64_t halo[2] = {p.halo_prev_obs1, p.halo_prev_obs2};
+            BESST_CUDA_TRY(ctx, cudaMemcpyAsync(counters + BESST_CNT_LAST_OBS1, halo, sizeof(halo), cudaMemcpyHostToDevice, ctx->stream));
+        }
+        u64 g[2] = {0, 0};
+        BESST_CUDA_TRY(ctx, cudaMemcpyAsync(g, globals, sizeof(g), cudaMemcpyDeviceToHost, ctx->stream));
+        BESST_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+        ctx->n_tuples = (int64_t)g[0];
+        ctx->n_fishy_keys = (int64_t)g[1];
+        if (ctx->n_fishy_keys > ctx->fishy_cap) { ctx->fishy_cap = ctx->n_fishy_keys + 4096; continue; }
+        BESST_CUDA_TRY(ctx, ctx->tuples.ensure(sizeof(besst_link_tuple) * (size_t)(ctx->n_tuples > 0 ? ctx->n_tuples : 1)));
+        if (ctx->n_tuples > 0) {
+            long long cgrid = (long long)ctx->sm_count * 8;
+            const long long cmax = (n_tiles + 7) / 8;
+            if (cgrid > cmax) cgrid = cmax;
+            KTimer kt(ctx, BESST_K_COMPACT);
+            k_compact_tuples<<<(unsigned)cgrid, 256, 0, ctx->stream>>>(P.scratch, tile_off, n_tiles, ctx->tuples.as<besst_link_tuple>());
             BESST_CUDA_TRY(ctx, cudaGetLastError());
         }
-        u64 g[3] = {0, 0, 0};
-        BESST_CUDA_TRY(ctx, cudaMemcpyAsync(g, P.globals, sizeof(g), cudaMemcpyDeviceToHost, ctx->stream));
-        BESST_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-        if (n_tiles == 0) {
-            int64_t halo[2] = {p.halo_prev_obs1, p.halo_prev_obs2};
-            BESST_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->counters.as<u64>() + BESST_CNT_LAST_OBS1, halo, sizeof(halo),
-                                                cudaMemcpyHostToDevice, ctx->stream));
-        }
-        ctx->n_tuples = (int64_t)g[1];
-        ctx->n_fishy_keys = (int64_t)g[2];
-        bool again = false;
-        if (ctx->n_tuples > ctx->tuples_cap) { ctx->tuples_cap = ctx->n_tuples + 4096; again = true; }
-        if (ctx->n_fishy_keys > ctx->fishy_cap) { ctx->fishy_cap = ctx->n_fishy_keys + 4096; again = true; }
-        if (!again) { ctx->have_links = true; return BESST_OK; }
+        ctx->have_links = true;
+        return BESST_OK;
     }
-    ctx->err = "link extraction: capacity retry failed";
+    ctx->err = "link extraction: fishy-key capacity retry failed";
     return BESST_E_STATE;
 }

@@ -91,6 +91,37 @@ class CudaEngine(object):
                     "besst_links_partials")
         return aligned, counters
 
+    def links_partials_device(self):
+        """(device pointer of aligned_len[C] int64, device pointer of counters[16] int64)"""
+        a, c = C.c_void_p(), C.c_void_p()
+        self._check(self._L.besst_links_partials_device(self._ctx, C.byref(a), C.byref(c)), "besst_links_partials_device")
+        return a.value, c.value
+
+    def links_tuples_host(self):
+        (_, n), _ = self.links_device()
+        out = np.zeros(n, dtype=abi.LINK_TUPLE_DTYPE)
+        self._check(self._L.besst_links_fetch(self._ctx, out.ctypes.data, None), "besst_links_fetch")
+        return out
+
+    def links_fishy_host(self):
+        _, (_, n) = self.links_device()
+        out = np.zeros(n, dtype=np.uint64)
+        self._check(self._L.besst_links_fetch(self._ctx, None, out.ctypes.data), "besst_links_fetch")
+        return out
+
+    def links_partition(self, world, out_tuples_ptr, out_fishy_ptr):
+        """Stable bucketing of the extracted tuples / fishy keys by destination rank into
+        caller-provided device buffers.  -> (tuple_counts[world], fishy_counts[world])"""
+        tc = np.zeros(world, dtype=np.int64)
+        fc = np.zeros(world, dtype=np.int64)
+        self._check(self._L.besst_links_partition(self._ctx, int(world), out_tuples_ptr, out_fishy_ptr, tc.ctypes.data,
+                                                  fc.ctypes.data), "besst_links_partition")
+        return tc, fc
+
+    def set_stream(self, cuda_stream_ptr):
+        """Run the engine on a caller-owned CUDA stream (e.g. torch.cuda.current_stream().cuda_stream); 0/None restores its own."""
+        self._check(self._L.besst_set_stream(self._ctx, cuda_stream_ptr or None), "besst_set_stream")
+
     def links_to_graph(self, params, tuples_ptr, n_tuples, fishy_ptr, n_fishy):
         sizes = abi.GraphSizes()
         self._check(self._L.besst_links_to_graph(self._ctx, C.byref(params), tuples_ptr, int(n_tuples), fishy_ptr,
@@ -124,6 +155,15 @@ class CudaEngine(object):
                     "besst_gapest_batch")
         return gap, sd
 
+    def trsk_sd_batch(self, params, gap, len1, len2):
+        gap = np.ascontiguousarray(gap, dtype=np.float64)
+        len1 = np.ascontiguousarray(len1, dtype=np.int32)
+        len2 = np.ascontiguousarray(len2, dtype=np.int32)
+        sd = np.zeros(gap.shape[0], dtype=np.float64)
+        self._check(self._L.besst_trsk_sd_batch(self._ctx, C.byref(params), gap.ctypes.data, len1.ctypes.data,
+                                                len2.ctypes.data, gap.shape[0], sd.ctypes.data), "besst_trsk_sd_batch")
+        return sd
+
     # -- timing / accounting -------------------------------------------------------------
     def timing(self):
         total = C.c_float()
@@ -148,7 +188,8 @@ class CudaEngine(object):
 
 
 KERNEL_NAMES = ["k_extract_links", "k_radix_hist", "k_radix_scan_hist", "k_radix_sweep", "k_heads", "k_edge_reduce",
-                "k_edge_score", "k_fishy_rekey", "k_metrics", "k_gapest_batch"]
+                "k_edge_score", "k_fishy_rekey", "k_metrics", "k_gapest_batch", "k_tile_scan", "k_compact_tuples",
+                "k_partition"]
 
 _default = None
 

@@ -24,8 +24,13 @@
  *                            order_contigs.py:300,308; pathgaps.py:108,204
  *   besst_libmetrics returns 1 (not an error) when fewer than 1001 insert-size
  *   samples exist (libmetrics.py:311-314).
+ *   besst_trsk_sd_batch      param_est.tr_sk_std_dev at a caller-given gap
+ *                            (CreateGraph.py:555 signature)
  *   besst_links_extract /    the two halves of besst_graph_build on either side
- *   besst_links_to_graph     of the multi-GPU all-to-all
+ *   besst_links_to_graph     of the multi-GPU all-to-all;
+ *   besst_links_partition    stable bucketing of the extracted tuples by
+ *                            destination rank = hash(edge) mod world, the send
+ *                            buffer of that all-to-all
  *
  * Conventions: plain C; all pointers are caller-owned for the duration of the
  * call; nothing is retained after return except inside the ctx; return 0 on
@@ -42,7 +47,7 @@
 extern "C" {
 #endif
 
-#define BESST_ABI_VERSION 1
+#define BESST_ABI_VERSION 2
 
 #define BESST_OK 0
 #define BESST_E_INVALID -1  /* bad argument */
@@ -210,6 +215,17 @@ int besst_links_extract(besst_ctx* ctx, const besst_lib_params* params,
 int besst_links_tuples_device(besst_ctx* ctx, const besst_link_tuple** tuples, int64_t* n_tuples);
 int besst_links_fishy_device(besst_ctx* ctx, const uint64_t** keys, int64_t* n_keys);
 int besst_links_partials(besst_ctx* ctx, int64_t* aligned_len_host /*[C]*/, int64_t* counters_host /*[16]*/);
+/* device views of the same partial sums (aligned_len[C], counters[16], int64) for an in-place
+ * NCCL all-reduce; valid until the next extract */
+int besst_links_partials_device(besst_ctx* ctx, int64_t** aligned_len_device, int64_t** counters_device);
+/* host copies of the extracted tuple stream / fishy keys (tests, debugging); either may be NULL */
+int besst_links_fetch(besst_ctx* ctx, besst_link_tuple* tuples_host, uint64_t* fishy_keys_host);
+/* stable partition of the extracted tuples and fishy keys into `world` destination buckets
+ * (bucket d = hash(u,v) mod world, BAM order kept inside a bucket), written to caller-provided
+ * DEVICE buffers of n_tuples / n_fishy_keys elements; *_counts[world] (host) receive the bucket
+ * sizes.  world <= 16. */
+int besst_links_partition(besst_ctx* ctx, int32_t world, besst_link_tuple* out_tuples_device,
+                          uint64_t* out_fishy_device, int64_t* tuple_counts, int64_t* fishy_counts);
 int besst_links_to_graph(besst_ctx* ctx, const besst_lib_params* params,
                          const besst_link_tuple* tuples_device, int64_t n_tuples,
                          const uint64_t* fishy_keys_device, int64_t n_fishy_keys,
@@ -226,6 +242,15 @@ int besst_libmetrics(besst_ctx* ctx, const besst_lib_params* params, const besst
 int besst_gapest_batch(besst_ctx* ctx, const besst_lib_params* params, const double* mean_obs,
                        const int32_t* len1, const int32_t* len2, int64_t n,
                        int32_t* gap_out, double* sd_out);
+
+/* tr_sk_std_dev(mean, sigma, read_len, len1[i], len2[i], gap[i]) (host arrays in/out) */
+int besst_trsk_sd_batch(besst_ctx* ctx, const besst_lib_params* params, const double* gap, const int32_t* len1,
+                        const int32_t* len2, int64_t n, double* sd_out);
+
+/* run all work of this ctx on a caller-owned CUDA stream (a cudaStream_t passed as void*; NULL
+ * restores the ctx's own stream).  Lets a host framework order the library's kernels with its own
+ * work (NCCL collectives, CUDA-event timing) without device-wide synchronisation. */
+int besst_set_stream(besst_ctx* ctx, void* cuda_stream);
 
 /* device-side timing of the last besst_graph_build, CUDA events on the
  * library's stream: total and per-stage milliseconds */
@@ -247,7 +272,10 @@ int besst_kernel_launches(besst_ctx* ctx, int64_t* n_launches);
 #define BESST_K_FISHY 7        /* k_fishy_rekey */
 #define BESST_K_METRICS 8      /* k_metrics_*              (K7) */
 #define BESST_K_GAPEST 9       /* k_gapest_batch           (K6) */
-#define BESST_N_KERNEL_IDS 10
+#define BESST_K_TILE_SCAN 10   /* k_tile_reduce/k_chunk_resolve/k_tile_offsets (K2) */
+#define BESST_K_COMPACT 11     /* k_compact_tuples         (K1) */
+#define BESST_K_PARTITION 12   /* k_partition_count/scan/scatter (multi-GPU) */
+#define BESST_N_KERNEL_IDS 13
 int besst_set_profiling(besst_ctx* ctx, int enabled);
 int besst_kernel_profile(besst_ctx* ctx, int32_t* kernel_ids, float* ms, int32_t cap);
 

@@ -47,3 +47,266 @@ def test_graph_build_matches_oracle(cuda_engine, config, objects, over):
     got = cuda_engine.graph_build(table, params, batch)
     helpers.assert_graph_equal(got, want, label="%s/%s/%s" % (config, objects, over))
     assert want.n_edges > 0 and want.n_links > 0
+
+
+def _setup(config, over=None, objects="first"):
+    lib = synth.make_config(config)
+    batch = lib.to_batch()
+    params, contig_threshold = _params(lib, over or {})
+    if objects == "first":
+        objs = helpers.first_library_objects(batch.references, batch.lengths, contig_threshold)
+    else:
+        objs = helpers.later_library_objects(batch.references, batch.lengths, contig_threshold, seed=7)
+    return lib, batch, params, helpers.table_for(batch, objs)
+
+
+@pytest.mark.parametrize("n", [0, 1, 2, 31, 1023, 1024, 1025, 4097])
+def test_ragged_and_empty_inputs(cuda_engine, n):
+    lib, batch, params, table = _setup("small_mp")
+    sub = batch.slice(50000, 50000 + n)
+    want, _, _, _ = oracle_lib.graph_build(table.rows, table.n_scaffolds, params, sub)
+    got = cuda_engine.graph_build(table, params, sub)
+    helpers.assert_graph_equal(got, want, label="n=%d" % n)
+
+
+def test_records_with_absent_or_negative_contigs(cuda_engine):
+    lib, batch, params, table = _setup("small_pe", objects="later")   # later: some contigs removed
+    rng = np.random.default_rng(1)
+    tid = batch.tid.copy()
+    mtid = batch.mtid.copy()
+    tid[rng.random(len(batch)) < 0.01] = -1
+    mtid[rng.random(len(batch)) < 0.01] = -1
+    mtid[rng.random(len(batch)) < 0.001] = len(batch.references) + 5    # out of range: dropped like tid < 0
+    from besst_b200.records import RecordBatch
+    bad = RecordBatch(tid=tid, mtid=mtid, pos=batch.pos, mpos=batch.mpos, tlen=batch.tlen, qlen=batch.qlen,
+                      flag=batch.flag, mapq=batch.mapq, references=batch.references, lengths=batch.lengths)
+    want, _, _, _ = oracle_lib.graph_build(table.rows, table.n_scaffolds, params, bad)
+    got = cuda_engine.graph_build(table, params, bad)
+    helpers.assert_graph_equal(got, want, label="absent")
+
+
+def test_edges_with_more_links_than_one_warp_sorts(cuda_engine):
+    """Few long contigs -> edges with thousands of links (the CTA-per-edge path of K5)."""
+    lib = synth.make_library(12, 400000, "rf", 3000.0, 500.0, seed=99)
+    batch = lib.to_batch()
+    params = abi.make_params("rf", 11, 100.0, 3000.0, 500.0, 6000.0)
+    objs = helpers.first_library_objects(batch.references, batch.lengths, 1000.0)
+    table = helpers.table_for(batch, objs)
+    want, _, _, _ = oracle_lib.graph_build(table.rows, table.n_scaffolds, params, batch)
+    assert want.nr_links.max() > 4096
+    got = cuda_engine.graph_build(table, params, batch)
+    helpers.assert_graph_equal(got, want, label="big edges")
+
+
+def test_device_resident_records_equal_host_records(cuda_engine):
+    import torch
+    lib, batch, params, table = _setup("small_mp_cont")
+    host = cuda_engine.graph_build(table, params, batch)
+    cols = {k: torch.from_numpy(np.ascontiguousarray(v).view(np.int16) if k == "flag" else np.ascontiguousarray(v)).cuda()
+            for k, v in batch.device_arrays().items()}
+    ptrs = {k: v.data_ptr() for k, v in cols.items()}
+    ptrs["n"] = len(batch)
+    cuda_engine.set_table(table)
+    dev = cuda_engine.fetch(cuda_engine.build(params, abi.make_records(ptrs, on_device=True)))
+    helpers.assert_graph_equal(dev, host, label="device-resident")
+
+
+def test_two_slices_with_halo_equal_one_pass(cuda_engine):
+    """The multi-GPU decomposition on one GPU: records cut into BAM-order slices, each
+    extracted with the previous slice's last CreateEdge observation as halo, tuples
+    concatenated in slice order == the single-pass tuple stream."""
+    lib, batch, params, table = _setup("small_mp")
+    cuda_engine.set_table(table)
+    keep = []
+    n = len(batch)
+    whole = oracle_lib.graph_build(table.rows, table.n_scaffolds, params, batch)
+    tuples_all, counters_all, aligned_all = [], np.zeros(abi.N_COUNTERS, np.int64), np.zeros(len(batch.references), np.int64)
+    halo = (-1, -1)
+    for lo, hi in ((0, n // 3), (n // 3, n // 3 + 7), (n // 3 + 7, n)):
+        p = abi.make_params(lib.orientation, 11, 100.0, lib.mu, lib.sigma, lib.mu + 6 * lib.sigma, halo=halo)
+        nt = cuda_engine.links_extract(p, abi.make_records(batch.slice(lo, hi), keepalive=keep))
+        tuples_all.append(cuda_engine.links_tuples_host())
+        assert tuples_all[-1].shape[0] == nt
+        aligned, counters = cuda_engine.links_partials()
+        halo = (int(counters[abi.CNT_LAST_OBS1]), int(counters[abi.CNT_LAST_OBS2]))
+        counters_all[:8] += counters[:8]
+        aligned_all += aligned
+    got = np.concatenate(tuples_all)
+    assert np.array_equal(got, whole[1])
+    assert np.array_equal(counters_all[:8], whole[0].counters[:8])
+    assert np.array_equal(aligned_all, whole[0].aligned_len)
+    assert halo == (int(whole[0].counters[abi.CNT_LAST_OBS1]), int(whole[0].counters[abi.CNT_LAST_OBS2]))
+
+
+@pytest.mark.parametrize("erf_variant", [abi.ERF_AS7126, abi.ERF_LIBM])
+def test_gapest_batch_matches_oracle(cuda_engine, erf_variant):
+    rng = np.random.default_rng(11)
+    n = 20000
+    for mean, sd, r in ((3000.0, 500.0, 100.0), (550.0, 50.0, 99.37), (8000.0, 1200.0, 150.0)):
+        p = abi.make_params("fr", 11, r, mean, sd, mean + 6 * sd, erf_variant=erf_variant)
+        mo = rng.uniform(2 * r, mean + 3 * sd, n)
+        l1 = rng.integers(int(2 * sd) + 1, 60000, n).astype(np.int32)
+        l2 = rng.integers(int(2 * sd) + 1, 60000, n).astype(np.int32)
+        gap, sd_out = cuda_engine.gapest_batch(p, mo, l1, l2)
+        gap_o, sd_o = oracle_lib.gapest_batch(p, mo, l1, l2)
+        if erf_variant == abi.ERF_AS7126:
+            assert np.array_equal(gap, gap_o)
+        else:   # device erf() and glibc erf() may differ by an ulp: a bisection step can flip by 1 bp
+            assert np.abs(gap - gap_o).max() <= 1 and (gap != gap_o).mean() < 1e-3
+        same = gap == gap_o
+        np.testing.assert_allclose(sd_out[same], sd_o[same], rtol=helpers.FLOAT_RTOL, atol=0)
+
+
+def test_libmetrics_matches_oracle_and_hits_the_sample_cap(cuda_engine):
+    """> 1e6 qualifying read2 records on the 1000 longest contigs: both capped scans
+    (libmetrics.py:283-304 and :49-84) must cut at the same BAM-order prefix."""
+    from besst_b200 import libmetrics
+    lib = synth.make_library(50, 1400000, "fr", 550.0, 50.0, seed=321)
+    batch = lib.to_batch()
+    params = abi.make_params("fr", 11, 100.0, 0.0, 0.0, 0.0)
+    rows = libmetrics.metric_rows(batch.lengths)
+    rc_o, m_o, adj_o = oracle_lib.libmetrics(rows, params, batch, batch.lengths, True)
+    rc, m, adj = cuda_engine.libmetrics(rows, params, batch, batch.lengths, True)
+    assert rc == rc_o == 0
+    assert m_o.n_samples == 1000000
+    for f in ("n_samples", "n_trimmed", "median_adj", "mode_adj", "n_bins", "cont_mapped", "cont_n", "records_scanned"):
+        assert getattr(m, f) == getattr(m_o, f), f
+    for f in ("mean_before", "sd_before", "mean_converged", "sd_converged", "skewness", "mu_adj", "sigma_adj",
+              "skew_adj", "cont_mean", "cont_sd"):
+        a, b = getattr(m, f), getattr(m_o, f)
+        assert abs(a - b) <= 1e-9 * max(abs(b), 1e-12), (f, a, b)
+    np.testing.assert_allclose(adj, adj_o, rtol=1e-12, atol=0)
+
+
+def test_too_few_insert_size_samples_is_reported_not_fatal(cuda_engine):
+    from besst_b200 import libmetrics
+    lib, batch, _, _ = _setup("tiny")
+    sub = batch.slice(0, 3000)
+    params = abi.make_params("fr", 11, 100.0, 0.0, 0.0, 0.0)
+    rows = libmetrics.metric_rows(sub.lengths)
+    rc, m, _ = cuda_engine.libmetrics(rows, params, sub, sub.lengths, True)
+    rc_o, m_o, _ = oracle_lib.libmetrics(rows, params, sub, sub.lengths, True)
+    assert rc == rc_o == 1 and m.n_samples == m_o.n_samples <= 1000
+
+
+def test_full_size_config2_matches_oracle(cuda_engine):
+    """BASELINE.json configs[1] at full size (10k contigs / 20 M PE pairs): the whole CSR
+    against the sequential C oracle."""
+    import torch
+    from besst_b200.contig_table import first_library_rows
+    lib = synth.make_config("config2", device="cuda", with_names=False)
+    batch = lib.to_batch()
+    rows, n_scaf, n_large = first_library_rows(lib.lengths.numpy(), lib.mu + 4 * lib.sigma)
+    params = abi.make_params("fr", 11, 100.0, lib.mu, lib.sigma, lib.mu + 6 * lib.sigma)
+    want, _, _, consistent = oracle_lib.graph_build(rows, n_scaf, params, batch)
+    assert consistent
+    cuda_engine.set_contigs(rows, n_scaf, n_large)
+    ptrs = {k: v.data_ptr() for k, v in lib.cols.items()}
+    ptrs["n"] = lib.n_records
+    got = cuda_engine.fetch(cuda_engine.build(params, abi.make_records(ptrs, on_device=True)))
+    helpers.assert_graph_equal(got, want, label="config2 full")
+    del lib
+    torch.cuda.empty_cache()
+
+
+def test_full_size_config3_invariants(cuda_engine):
+    """BASELINE.json configs[2] (100k contigs / 200 M MP pairs) at half scale: size-independent
+    properties of the CSR -- sorted unique edge keys, row_ptr consistent with nr_links,
+    per-edge sums equal to the payload, counters balance, and idempotence."""
+    import torch
+    from besst_b200.contig_table import first_library_rows
+    lib = synth.make_config("config3", device="cuda", with_names=False, scale=0.5)
+    rows, n_scaf, n_large = first_library_rows(lib.lengths.numpy(), lib.mu + 4 * lib.sigma)
+    params = abi.make_params("rf", 11, 100.0, lib.mu, lib.sigma, lib.mu + 6 * lib.sigma)
+    cuda_engine.set_contigs(rows, n_scaf, n_large)
+    ptrs = {k: v.data_ptr() for k, v in lib.cols.items()}
+    ptrs["n"] = lib.n_records
+    rec = abi.make_records(ptrs, on_device=True)
+    a = cuda_engine.fetch(cuda_engine.build(params, rec))
+    b = cuda_engine.fetch(cuda_engine.build(params, rec))
+    for f in helpers.INT_FIELDS + ["gap"]:
+        assert np.array_equal(getattr(a, f), getattr(b, f)), "not idempotent: %s" % f
+    assert np.array_equal(a.score, b.score, equal_nan=True)
+    key = (a.edge_u.astype(np.int64) << 32) | a.edge_v
+    assert (np.diff(key) > 0).all() and (a.edge_u < a.edge_v).all()
+    assert a.row_ptr[0] == 0 and a.row_ptr[-1] == a.n_links and np.array_equal(np.diff(a.row_ptr), a.nr_links)
+    tot = a.obs_u.astype(np.int64) + a.obs_v
+    assert np.array_equal(np.add.reduceat(tot, a.row_ptr[:-1]), a.obs_sum)
+    assert np.array_equal(np.add.reduceat(tot * tot, a.row_ptr[:-1]), a.obs_sq)
+    assert (a.obs_u > 25).all() and (a.obs_v > 25).all() and (tot < lib.mu + 6 * lib.sigma).all()
+    c = a.counters
+    ll_links = int(a.nr_links[(a.flags & abi.EDGE_LL) != 0].sum())
+    assert c[abi.CNT_COUNT] == a.n_links + ll_links          # LL links are counted twice (CreateGraph.py:176,183)
+    assert len(set(a.first_idx.tolist())) == a.n_edges and a.first_idx.max() < a.n_links
+    scored = (a.flags & abi.EDGE_SCORED) != 0
+    assert np.array_equal(scored, (a.flags & abi.EDGE_LL) != 0)
+    s = a.score[scored]
+    assert ((s == 0) | ((s > 1.0) & (s <= 2.0))).all()
+    # true gaps of the generator are in [0, 1500]: ML estimates on well-supported edges stay near that range
+    well = scored & (a.nr_links >= 50) & ((a.flags & abi.EDGE_NEGGAP) == 0)
+    assert well.sum() > 1000 and np.percentile(a.gap[well], 1) > -600 and np.percentile(a.gap[well], 99) < 2600
+    del lib
+    torch.cuda.empty_cache()
+
+
+def edge_dest_numpy(u, v, world):
+    """besst_links.cu edge_dest: murmur3 finaliser of (u << 32 | v) mod world."""
+    with np.errstate(over="ignore"):
+        x = (u.astype(np.uint64) << np.uint64(32)) | v.astype(np.uint64)
+        x ^= x >> np.uint64(33)
+        x *= np.uint64(0xff51afd7ed558ccd)
+        x ^= x >> np.uint64(33)
+        x *= np.uint64(0xc4ceb9fe1a85ec53)
+        x ^= x >> np.uint64(33)
+    return (x % np.uint64(world)).astype(np.int64)
+
+
+@pytest.mark.parametrize("world", [1, 2, 3, 8])
+def test_partition_by_edge_hash_is_stable(cuda_engine, world):
+    import torch
+    lib, batch, params, table = _setup("small_mp_cont")
+    cuda_engine.set_table(table)
+    keep = []
+    n = cuda_engine.links_extract(params, abi.make_records(batch, keepalive=keep))
+    tuples = cuda_engine.links_tuples_host()
+    fishy = cuda_engine.links_fishy_host()
+    out_t = torch.zeros(max(n, 1) * 4, dtype=torch.int32, device="cuda")
+    out_f = torch.zeros(max(len(fishy), 1), dtype=torch.int64, device="cuda")
+    tc, fc = cuda_engine.links_partition(world, out_t.data_ptr(), out_f.data_ptr())
+    assert tc.sum() == n and fc.sum() == len(fishy)
+    got = out_t.cpu().numpy().view(abi.LINK_TUPLE_DTYPE)[:n]
+    dest = edge_dest_numpy(tuples["u"], tuples["v"], world)
+    order = np.argsort(dest, kind="stable")
+    assert np.array_equal(np.bincount(dest, minlength=world), tc)
+    assert np.array_equal(got, tuples[order])
+    got_f = out_f.cpu().numpy().view(np.uint64)[:len(fishy)]
+    fdest = edge_dest_numpy((fishy >> np.uint64(32)).astype(np.uint32), (fishy & np.uint64(0xffffffff)).astype(np.uint32), world)
+    assert np.array_equal(np.bincount(fdest, minlength=world), fc)
+    # fishy keys are appended with atomics (order-free): compare bucket contents as multisets
+    start = 0
+    for d in range(world):
+        assert np.array_equal(np.sort(got_f[start:start + fc[d]]), np.sort(fishy[fdest == d]))
+        start += fc[d]
+
+
+def test_trsk_sd_batch_matches_oracle(cuda_engine):
+    rng = np.random.default_rng(2)
+    n = 5000
+    p = abi.make_params("rf", 11, 100.0, 3000.0, 500.0, 6000.0)
+    gap = rng.integers(-800, 3500, n).astype(np.float64)
+    l1 = rng.integers(1001, 50000, n).astype(np.int32)
+    l2 = rng.integers(1001, 50000, n).astype(np.int32)
+    got = cuda_engine.trsk_sd_batch(p, gap, l1, l2)
+    L = oracle_lib.lib()
+    want = np.array([L.besst_oracle_tr_sk_std_dev(3000.0, 500.0, 100.0, float(a), float(b), float(g), abi.ERF_AS7126)
+                     for a, b, g in zip(l1, l2, gap)])
+    np.testing.assert_allclose(got, want, rtol=helpers.FLOAT_RTOL, atol=0)
+
+
+def test_scalar_dropins(cuda_engine):
+    from besst_b200 import param_est
+    L = oracle_lib.lib()
+    assert param_est.GapEstimator(3000.0, 500.0, 100.0, 2500.0, 6000, 7000, engine=cuda_engine) == \
+        L.besst_oracle_gap_estimator(3000.0, 500.0, 100.0, 2500.0, 6000.0, 7000.0, abi.ERF_AS7126)
+    sd = param_est.tr_sk_std_dev(3000.0, 500.0, 100.0, 6000, 7000, 420, engine=cuda_engine)
+    assert sd == pytest.approx(L.besst_oracle_tr_sk_std_dev(3000.0, 500.0, 100.0, 6000.0, 7000.0, 420.0, abi.ERF_AS7126), rel=1e-6)
