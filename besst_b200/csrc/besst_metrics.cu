@@ -145,7 +145,9 @@ __global__ void __launch_bounds__(1024) k_metrics_scan(u32* a, u32* b, int n_til
 }
 
 // out[0] = counter_total (mapped records in scope), out[1] = 1 + index of the
-// record holding the last isize sample, out[2] = same for the scope cut
+// record holding the last isize sample, out[2] = same for the scope cut,
+// out[3] = largest |tlen| among the counted samples (a value >= n_bins means
+// the histogram was too short: the host re-runs with more bins)
 __global__ void __launch_bounds__(MT_THREADS)
     k_metrics_hist(const MParams P, const u32* __restrict__ pre_isize, const u32* __restrict__ pre_scope, long long base_isize,
                    long long base_scope, u32* hist_isize, u32* hist_cont, int n_bins, u64* out) {
@@ -173,9 +175,11 @@ __global__ void __launch_bounds__(MT_THREADS)
     long long ra = base_isize + pre_isize[blockIdx.x] + wa + ia - a;
     long long rb = base_scope + pre_scope[blockIdx.x] + wb + ib - b;
     u32 mapped = 0;
+    int vmax = 0;
 #pragma unroll
     for (int i = 0; i < MT_ITEMS; ++i) {
         const int bin = c[i].v < n_bins ? c[i].v : n_bins - 1;
+        if ((c[i].isize && ra < MT_CAP) || (c[i].scope && rb < MT_CAP && c[i].cont)) vmax = c[i].v > vmax ? c[i].v : vmax;
         if (c[i].isize) {
             if (ra < MT_CAP) {
                 atomicAdd(&hist_isize[bin], 1u);
@@ -193,8 +197,13 @@ __global__ void __launch_bounds__(MT_THREADS)
         }
     }
 #pragma unroll
-    for (int off = 16; off > 0; off >>= 1) mapped += __shfl_xor_sync(0xffffffffu, mapped, off);
+    for (int off = 16; off > 0; off >>= 1) {
+        mapped += __shfl_xor_sync(0xffffffffu, mapped, off);
+        const int o = __shfl_xor_sync(0xffffffffu, vmax, off);
+        vmax = o > vmax ? o : vmax;
+    }
     if (lane == 0 && mapped) atomicAdd(&out[0], (u64)mapped);
+    if (lane == 0 && vmax >= n_bins) atomicMax(&out[3], (u64)vmax);
 }
 
 // ---- host side: statistics over the histogram ---------------------------------------------
@@ -338,48 +347,58 @@ int besst_launch_libmetrics(besst_ctx* ctx, const besst_lib_params& p, const Dev
     if (ctx->n_contigs <= 0) { ctx->err = "libmetrics: besst_set_contigs first"; return BESST_E_STATE; }
     int64_t max_len = 0;
     for (int64_t i = 0; i < n_refs; ++i) max_len = std::max(max_len, ref_lengths[i]);
-    const int n_bins = (int)std::min<int64_t>(max_len + 2, (1ll << 28));
+    // |tlen| of a same-contig pair is bounded by the contig length up to aligner slack (soft clips,
+    // alignments hanging over the contig end): start with some head-room and re-run with the exact
+    // maximum if a sample still falls outside (never clamp: the statistics need exact values)
+    int n_bins = (int)std::min<int64_t>(max_len + 1024, (1ll << 28));
     const long long chunk_tiles = (MT_CHUNK + MT_TILE - 1) / MT_TILE;
-    // misc: hist_isize[n_bins] hist_cont[n_bins] cnt_a[tiles+1] cnt_b[tiles+1] out[4]
-    const size_t bytes = 4 * (size_t)n_bins * 2 + 4 * (size_t)(chunk_tiles + 1) * 2 + 64;
-    BESST_CUDA_TRY(ctx, ctx->misc.ensure(bytes));
-    unsigned char* base = ctx->misc.as<unsigned char>();
-    u64* d_out = reinterpret_cast<u64*>(base);
-    u32* hist_isize = reinterpret_cast<u32*>(base + 64);
-    u32* hist_cont = hist_isize + n_bins;
-    u32* cnt_a = hist_cont + n_bins;
-    u32* cnt_b = cnt_a + chunk_tiles + 1;
-    BESST_CUDA_TRY(ctx, cudaMemsetAsync(base, 0, 64 + 4 * (size_t)n_bins * 2, ctx->stream));
-
-    MParams P;
-    P.rec = rec;
-    P.rows = ctx->rows.as<int4>();
-    P.n_contigs = (int)ctx->n_contigs;
-    P.orientation = p.orientation; P.min_mapq = p.min_mapq; P.want_isize = want_isize; P.read_len = p.read_len;
-    long long base_isize = 0, base_scope = 0;
-    for (long long lo = 0; lo < rec.n; lo += MT_CHUNK) {
-        P.lo = lo;
-        P.hi = std::min<long long>(rec.n, lo + MT_CHUNK);
-        const int n_tiles = (int)((P.hi - P.lo + MT_TILE - 1) / MT_TILE);
-        { KTimer kt(ctx, BESST_K_METRICS); k_metrics_count<<<n_tiles, MT_THREADS, 0, ctx->stream>>>(P, cnt_a, cnt_b); }
-        { KTimer kt(ctx, BESST_K_METRICS); k_metrics_scan<<<1, 1024, 0, ctx->stream>>>(cnt_a, cnt_b, n_tiles); }
-        { KTimer kt(ctx, BESST_K_METRICS); k_metrics_hist<<<n_tiles, MT_THREADS, 0, ctx->stream>>>(P, cnt_a, cnt_b, base_isize, base_scope, hist_isize, hist_cont, n_bins, d_out); }
-        BESST_CUDA_TRY(ctx, cudaGetLastError());
-        u32 tot[2];
-        BESST_CUDA_TRY(ctx, cudaMemcpyAsync(&tot[0], cnt_a + n_tiles, 4, cudaMemcpyDeviceToHost, ctx->stream));
-        BESST_CUDA_TRY(ctx, cudaMemcpyAsync(&tot[1], cnt_b + n_tiles, 4, cudaMemcpyDeviceToHost, ctx->stream));
-        BESST_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-        base_isize += tot[0];
-        base_scope += tot[1];
-        out->records_scanned = P.hi;
-        if ((!want_isize || base_isize >= MT_CAP) && base_scope >= MT_CAP) break;
-    }
-    std::vector<u32> h_isize((size_t)n_bins), h_cont((size_t)n_bins);
+    std::vector<u32> h_isize, h_cont;
     u64 h_out[4] = {0, 0, 0, 0};
-    BESST_CUDA_TRY(ctx, cudaMemcpyAsync(h_isize.data(), hist_isize, 4 * (size_t)n_bins, cudaMemcpyDeviceToHost, ctx->stream));
-    BESST_CUDA_TRY(ctx, cudaMemcpyAsync(h_cont.data(), hist_cont, 4 * (size_t)n_bins, cudaMemcpyDeviceToHost, ctx->stream));
-    BESST_CUDA_TRY(ctx, cudaMemcpyAsync(h_out, d_out, sizeof(h_out), cudaMemcpyDeviceToHost, ctx->stream));
-    BESST_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    long long base_isize = 0, base_scope = 0;
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        // misc: out[8] hist_isize[n_bins] hist_cont[n_bins] cnt_a[tiles+1] cnt_b[tiles+1]
+        const size_t bytes = 4 * (size_t)n_bins * 2 + 4 * (size_t)(chunk_tiles + 1) * 2 + 64;
+        BESST_CUDA_TRY(ctx, ctx->misc.ensure(bytes));
+        unsigned char* base = ctx->misc.as<unsigned char>();
+        u64* d_out = reinterpret_cast<u64*>(base);
+        u32* hist_isize = reinterpret_cast<u32*>(base + 64);
+        u32* hist_cont = hist_isize + n_bins;
+        u32* cnt_a = hist_cont + n_bins;
+        u32* cnt_b = cnt_a + chunk_tiles + 1;
+        BESST_CUDA_TRY(ctx, cudaMemsetAsync(base, 0, 64 + 4 * (size_t)n_bins * 2, ctx->stream));
+
+        MParams P;
+        P.rec = rec;
+        P.rows = ctx->rows.as<int4>();
+        P.n_contigs = (int)ctx->n_contigs;
+        P.orientation = p.orientation; P.min_mapq = p.min_mapq; P.want_isize = want_isize; P.read_len = p.read_len;
+        base_isize = 0; base_scope = 0;
+        for (long long lo = 0; lo < rec.n; lo += MT_CHUNK) {
+            P.lo = lo;
+            P.hi = std::min<long long>(rec.n, lo + MT_CHUNK);
+            const int n_tiles = (int)((P.hi - P.lo + MT_TILE - 1) / MT_TILE);
+            { KTimer kt(ctx, BESST_K_METRICS); k_metrics_count<<<n_tiles, MT_THREADS, 0, ctx->stream>>>(P, cnt_a, cnt_b); }
+            { KTimer kt(ctx, BESST_K_METRICS); k_metrics_scan<<<1, 1024, 0, ctx->stream>>>(cnt_a, cnt_b, n_tiles); }
+            { KTimer kt(ctx, BESST_K_METRICS); k_metrics_hist<<<n_tiles, MT_THREADS, 0, ctx->stream>>>(P, cnt_a, cnt_b, base_isize, base_scope, hist_isize, hist_cont, n_bins, d_out); }
+            BESST_CUDA_TRY(ctx, cudaGetLastError());
+            u32 tot[2];
+            BESST_CUDA_TRY(ctx, cudaMemcpyAsync(&tot[0], cnt_a + n_tiles, 4, cudaMemcpyDeviceToHost, ctx->stream));
+            BESST_CUDA_TRY(ctx, cudaMemcpyAsync(&tot[1], cnt_b + n_tiles, 4, cudaMemcpyDeviceToHost, ctx->stream));
+            BESST_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+            base_isize += tot[0];
+            base_scope += tot[1];
+            if ((!want_isize || base_isize >= MT_CAP) && base_scope >= MT_CAP) break;
+        }
+        h_isize.assign((size_t)n_bins, 0);
+        h_cont.assign((size_t)n_bins, 0);
+        BESST_CUDA_TRY(ctx, cudaMemcpyAsync(h_isize.data(), hist_isize, 4 * (size_t)n_bins, cudaMemcpyDeviceToHost, ctx->stream));
+        BESST_CUDA_TRY(ctx, cudaMemcpyAsync(h_cont.data(), hist_cont, 4 * (size_t)n_bins, cudaMemcpyDeviceToHost, ctx->stream));
+        BESST_CUDA_TRY(ctx, cudaMemcpyAsync(h_out, d_out, sizeof(h_out), cudaMemcpyDeviceToHost, ctx->stream));
+        BESST_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+        if ((long long)h_out[3] < n_bins) break;
+        if (attempt == 1 || h_out[3] >= (1ull << 31) - 2) { ctx->err = "libmetrics: |tlen| histogram overflow"; return BESST_E_INVALID; }
+        n_bins = (int)h_out[3] + 1;
+    }
     {   // records visited by the two capped scans
         long long scanned = 0;
         const long long a = want_isize ? (base_isize >= MT_CAP ? (long long)h_out[1] : rec.n) : 0;
