@@ -213,14 +213,17 @@ def run_ours(args):
     # ---- roofline of the dominant kernel (per-launch CUDA events, timed region) ---------
     per_step = {k: float(np.sum(v)) / args.steps for k, v in prof.items()}
     n_launch = {k: len(v) / args.steps for k, v in prof.items()}
-    n_links, n_edges = int(sizes.n_links), int(sizes.n_edges)
+    n_links, n_edges, n_ll = int(sizes.n_links), int(sizes.n_edges), int(sizes.n_ll_links)
     alg_bytes = {   # algorithmic bytes per launch of each kernel (DESIGN.md "Kernels")
         "k_extract_links": RECORD_BYTES * n_rec + TUPLE_BYTES * n_links + 48 * ((n_rec + 127) // 128),
         "k_compact_tuples": 2 * TUPLE_BYTES * n_links + 8 * ((n_rec + 127) // 128),
         "k_radix_sweep": (12 + 12) * n_links,
         "k_radix_hist": 8 * n_links,
         "k_edge_reduce": (4 + 16 + 8) * n_links + 64 * n_edges,
-        "k_edge_score": 8 * n_links + 48 * n_edges,
+        "k_score_keys": (8 + 8) * n_ll / 3.0 + 13 * n_edges,   # 3 launches: LL scan (2, over edges) + key build
+        "k_ks_sort": (4 + 4) * n_ll,
+        "k_ks_eval": (4 + 4) * n_ll + 8 * n_edges,
+        "k_gapest": 64 * n_edges,
         "k_heads": 8 * n_links,
     }
     dominant = max(per_step, key=per_step.get) if per_step else None
@@ -304,7 +307,7 @@ def run_ours(args):
             "data": "synthetic",
             "config": {"workload": desc + (" x%d ranks" % world if world > 1 else ""), "contigs_per_rank": n_contigs,
                        "pairs_per_rank": pairs_per_rank, "records_per_rank": n_rec, "orientation": orientation,
-                       "mean_ins_size": mu, "std_dev_ins_size": sigma, "accepted_links": n_links, "edges": n_edges,
+                       "mean_ins_size": mu, "std_dev_ins_size": sigma, "accepted_links": n_links, "edges": n_edges, "scored_links": n_ll,
                        "l2_policy": "inputs (%.1f GB) larger than the 126 MB L2" % (RECORD_BYTES * n_rec / 1e9),
                        "parallelism": "1 process per GPU; tuples all-to-all by edge hash" if world > 1 else "single GPU"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches_timed),

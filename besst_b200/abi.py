@@ -43,7 +43,8 @@ class LibParams(C.Structure):
 
 
 class GraphSizes(C.Structure):
-    _fields_ = [("n_edges", C.c_int64), ("n_links", C.c_int64), ("n_contigs", C.c_int64), ("n_fishy", C.c_int64)]
+    _fields_ = [("n_edges", C.c_int64), ("n_links", C.c_int64), ("n_contigs", C.c_int64), ("n_fishy", C.c_int64),
+                ("n_ll_links", C.c_int64)]
 
 
 _GRAPH_FIELDS = [("edge_u", np.uint32, "E"), ("edge_v", np.uint32, "E"), ("nr_links", np.int32, "E"),

@@ -45,7 +45,7 @@ extern "C" void besst_destroy(besst_ctx* ctx) {
                     &ctx->sort_state, &ctx->fishy_sorted, &ctx->fishy_tmp, &ctx->heads, &ctx->block_sums, &ctx->e_u, &ctx->e_v,
                     &ctx->e_nr, &ctx->e_obs, &ctx->e_obs_sq, &ctx->e_first, &ctx->e_row_ptr, &ctx->e_gap, &ctx->e_score,
                     &ctx->e_ks, &ctx->e_sd_obs, &ctx->e_sd_model, &ctx->e_fishy, &ctx->e_flags, &ctx->l_obs_u, &ctx->l_obs_v,
-                    &ctx->big_list, &ctx->big_scratch};
+                    &ctx->e_sum_u, &ctx->e_max_v, &ctx->ll_off, &ctx->ks_key[0], &ctx->ks_key[1], &ctx->ks_key[2], &ctx->ks_key[3]};
     for (DBuf* b : bufs) b->release();
     for (DBuf& b : ctx->rec_i32) b.release();
     for (int i = 0; i <= BESST_N_STAGES; ++i) cudaEventDestroy(ctx->ev[i]);
@@ -256,6 +256,7 @@ extern "C" int besst_links_to_graph(besst_ctx* ctx, const besst_lib_params* para
     if (sizes) {
         sizes->n_edges = ctx->n_edges; sizes->n_links = ctx->n_links; sizes->n_contigs = ctx->n_contigs;
         sizes->n_fishy = n_fishy_keys;
+        sizes->n_ll_links = ctx->n_ll_links;
     }
     return BESST_OK;
 }

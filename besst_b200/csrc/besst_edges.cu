@@ -6,19 +6,23 @@
 //      nr_links, obs = sum(o1+o2), obs_sq = sum((o1+o2)^2), first-appearance
 //      index, per-scaffold observation lists in BAM order
 //      (CreateEdge, CreateGraph.py:842-862), fishy count (:141-163).
-//  K5  per large-large edge: sort the two observation lists in shared memory
-//      (bitonic), two-sample KS statistic = scipy.stats.ks_2samp(...).statistic
-//      as used at CreateGraph.py:582-606.
+//  K5  two-sample KS statistic = scipy.stats.ks_2samp(...).statistic as used at
+//      CreateGraph.py:582-606: the two observation lists of every large-large
+//      edge are sorted by two device-wide radix sorts of (edge, value) keys and
+//      compared by a co-ranking walk, load-balanced over links.
 //  K6  GapEstimator bisection + tr_sk_std_dev (mathstats param_est, call sites
 //      CreateGraph.py:537,555) with the four erf/exp arguments of g(d) spread
 //      over the 4 lanes of a quad and combined with __shfl_sync; then the score
 //      (CreateGraph.py:603-614).  No tensor cores: there is no contraction here.
 #include <math.h>
 
+#include <algorithm>
+
 #include "besst_internal.cuh"
 
 int besst_radix_sort_tuples(besst_ctx* ctx, const besst_link_tuple* tuples, int bv, uint64_t* keys_a, uint64_t* keys_b,
                             uint32_t* val_a, uint32_t* val_b, int64_t n, int* result_in_b);
+int besst_radix_sort_keys32(besst_ctx* ctx, uint32_t* keys_a, uint32_t* keys_b, int64_t n, int key_bits, int* result_in_b);
 
 namespace {
 
@@ -147,18 +151,21 @@ struct EdgeArrays {
     int* fishy;
     unsigned char* flags;
     int *obs_u, *obs_v;
+    long long* sum_u;   // internal: sum of obs_u per edge
+    int* max_v;         // internal: max of obs_v per edge
 };
 
 __global__ void __launch_bounds__(256)
     k_edge_reduce(EdgeArrays E, long long n_edges, const besst_link_tuple* __restrict__ tuples,
                   const u32* __restrict__ sorted_idx, const u64* __restrict__ sorted_keys, int bv,
-                  const u64* __restrict__ fishy_sorted, long long n_fishy, u32 n_large2) {
+                  const u64* __restrict__ fishy_sorted, long long n_fishy, u32 n_large2, int scoring) {
     const int lane = threadIdx.x & 31;
     const long long warp_global = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const long long n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
     for (long long e = warp_global; e < n_edges; e += n_warps) {
         const long long b = E.row_ptr[e], t = E.row_ptr[e + 1];
-        long long s = 0, sq = 0;
+        long long s = 0, sq = 0, su = 0;
+        int mv = -2147483647 - 1;
         for (long long j = b + lane; j < t; j += 32) {
             const u32 idx = __ldg(sorted_idx + j);
             const int4 tp = __ldg(reinterpret_cast<const int4*>(tuples + idx));
@@ -167,11 +174,16 @@ __global__ void __launch_bounds__(256)
             const long long o = (long long)tp.z + (long long)tp.w;
             s += o;
             sq += o * o;
+            su += tp.z;
+            mv = tp.w > mv ? tp.w : mv;
         }
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) {
             s += __shfl_xor_sync(0xffffffffu, s, off);
             sq += __shfl_xor_sync(0xffffffffu, sq, off);
+            su += __shfl_xor_sync(0xffffffffu, su, off);
+            const int o = __shfl_xor_sync(0xffffffffu, mv, off);
+            mv = o > mv ? o : mv;
         }
         if (lane == 0) {
             const u64 key = sorted_keys[b];
@@ -189,10 +201,14 @@ __global__ void __launch_bounds__(256)
                 f = hi - lo;
             }
             E.fishy[e] = (int)f;
-            E.flags[e] = (u < n_large2 && v < n_large2) ? BESST_EDGE_LL : 0;
+            const bool ll = u < n_large2 && v < n_large2;
+            E.flags[e] = ll ? BESST_EDGE_LL : 0;
             E.gap[e] = 0;
+            E.sum_u[e] = su;
+            E.max_v[e] = mv;
             const double nan = __longlong_as_double(0x7ff8000000000000ll);
-            E.score[e] = nan; E.ks[e] = nan; E.sd_obs[e] = nan; E.sd_model[e] = nan;
+            E.score[e] = nan; E.sd_obs[e] = nan; E.sd_model[e] = nan;
+            E.ks[e] = (ll && scoring) ? 0.0 : nan;   // k_ks_eval accumulates the maximum into it
         }
     }
 }
@@ -275,44 +291,108 @@ __device__ __forceinline__ double tr_sk_std_dev_quad(const ScoreConsts& c, doubl
     return sqrt(var);
 }
 
-// ---- group helpers: G = 32 (warp per edge) or G = blockDim (CTA per edge) ---------------
-template <int G>
-__device__ __forceinline__ void group_sync() {
-    if (G == 32) __syncwarp(); else __syncthreads();
+// ---- K5: KS statistic from two device-wide radix sorts --------------------------------------------
+// Links of large-large edges are compacted into "LL link space" (edge order, ll_off[e] = first slot of
+// edge e).  Two 32/64-bit keys per link, (e << B) | value, are radix sorted (keys only): list 1 holds
+// the observations on edge_u's scaffold, list 2 holds max(obs_v) - obs_v (CreateGraph.py:582-593).
+// The sort leaves every edge's two lists ascending in place; the KS statistic
+// (scipy.stats.ks_2samp(...).statistic, :595) is then a co-ranking walk over fixed-size chunks of the
+// sorted arrays -- load-balanced by links, not by edges -- with a per-edge atomicMax on the bit
+// pattern of the (non-negative) double.
+
+struct KsArgs {
+    const long long* row_ptr;    // [E+1] CSR
+    const u32* ll_off;           // [E+1] exclusive sum of nr_links over LL edges
+    const unsigned char* flags;  // [E]
+    const long long* sum_u;      // [E] sum of obs_u
+    const long long* obs_sum;    // [E] sum of obs_u + obs_v
+    const int* max_v;            // [E]
+    long long n_edges;
+    long long n_ll;              // LL links
+    int value_bits;
+};
+
+// edge owning LL slot j: last e with ll_off[e] <= j (zero-length non-LL entries never win a slot)
+__device__ __forceinline__ long long ll_edge_of(const u32* __restrict__ ll_off, long long n_edges, u32 j) {
+    long long lo = 0, hi = n_edges;   // invariant: ll_off[lo] <= j < ll_off[hi]
+    while (hi - lo > 1) {
+        const long long mid = (lo + hi) >> 1;
+        if (__ldg(ll_off + mid) <= j) lo = mid; else hi = mid;
+    }
+    return lo;
 }
 
-template <int G>
-__device__ __forceinline__ void bitonic_sort(int* a, int npad, int t) {
-    for (int k = 2; k <= npad; k <<= 1)
-        for (int j = k >> 1; j > 0; j >>= 1) {
-            for (int i = t; i < npad; i += G) {
-                const int ixj = i ^ j;
-                if (ixj > i) {
-                    const int x = a[i], y = a[ixj];
-                    const bool asc = (i & k) == 0;
-                    if ((x > y) == asc) { a[i] = y; a[ixj] = x; }
-                }
-            }
-            group_sync<G>();
+template <typename KeyT>
+__global__ void __launch_bounds__(256)
+    k_score_keys(const KsArgs A, const int* __restrict__ obs_u, const int* __restrict__ obs_v, KeyT* __restrict__ key1,
+                 KeyT* __restrict__ key2) {
+    const int lane = threadIdx.x & 31;
+    const long long warp_global = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
+    for (long long e = warp_global; e < A.n_edges; e += n_warps) {
+        if (!(A.flags[e] & BESST_EDGE_LL)) continue;
+        const long long b = A.row_ptr[e], t = A.row_ptr[e + 1];
+        const long long dst = (long long)A.ll_off[e] - b;
+        const int mv = A.max_v[e];
+        const KeyT hi = (KeyT)((unsigned long long)e << A.value_bits);
+        for (long long j = b + lane; j < t; j += 32) {
+            key1[dst + j] = hi | (KeyT)(u32)__ldg(obs_u + j);
+            key2[dst + j] = hi | (KeyT)(u32)(mv - __ldg(obs_v + j));   // abs(x - max_obs2), :588-590
         }
+    }
 }
 
-__device__ __forceinline__ int upper_bound_int(const int* a, int n, int key) {
-    int lo = 0, hi = n;
-    while (lo < hi) {
-        const int mid = (lo + hi) >> 1;
-        if (a[mid] <= key) lo = mid + 1; else hi = mid;
+constexpr int KS_CHUNK = 16;
+
+// SIDE 0: evaluate at the points of list 1 (own = key1, other = key2); SIDE 1: the reverse.
+template <typename KeyT, int SIDE>
+__global__ void __launch_bounds__(256)
+    k_ks_eval(const KsArgs A, const KeyT* __restrict__ own, const KeyT* __restrict__ other, double* ks) {
+    const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    long long j = c * KS_CHUNK;
+    if (j >= A.n_ll) return;
+    const long long j_end = (j + KS_CHUNK < A.n_ll) ? j + KS_CHUNK : A.n_ll;
+    const KeyT vmask = (KeyT)((1ull << A.value_bits) - 1ull);
+    long long e = ll_edge_of(A.ll_off, A.n_edges, (u32)j);
+    while (j < j_end) {
+        // segment of edge e in LL space
+        while (!(A.flags[e] & BESST_EDGE_LL) || (long long)A.ll_off[e + 1] <= j) ++e;
+        const long long s0 = A.ll_off[e], s1 = A.ll_off[e + 1];
+        const int n = (int)(s1 - s0);
+        const long long su = A.sum_u[e];
+        const long long sy = (long long)n * A.max_v[e] - (A.obs_sum[e] - su);
+        const double m1 = (double)su / (double)n;   // l1_mean (:584)
+        const double m2 = (double)sy / (double)n;   // l2_mean (:591)
+        const double m_own = SIDE == 0 ? m1 : m2, m_other = SIDE == 0 ? m2 : m1;
+        const long long stop = j_end < s1 ? j_end : s1;
+        // co-rank of the first point in the other list: #{y : y - m_other <= x - m_own}
+        long long q;
+        {
+            const double z = (double)(long long)(__ldg(own + j) & vmask) - m_own;
+            long long lo = s0, hi = s1;
+            while (lo < hi) {
+                const long long mid = (lo + hi) >> 1;
+                if ((double)(long long)(__ldg(other + mid) & vmask) - m_other <= z) lo = mid + 1; else hi = mid;
+            }
+            q = lo;
+        }
+        double dmax = 0.0;
+        KeyT cur = __ldg(own + j);
+        for (; j < stop; ++j) {
+            const bool at_end = j + 1 >= s1;
+            const KeyT nxt = at_end ? cur : __ldg(own + j + 1);
+            const double z = (double)(long long)(cur & vmask) - m_own;
+            while (q < s1 && (double)(long long)(__ldg(other + q) & vmask) - m_other <= z) ++q;
+            if (at_end || nxt != cur) {   // last of a run of equal values: ECDF of the own list = (j + 1 - s0) / n
+                const double f_own = (double)(j + 1 - s0) / (double)n;
+                const double f_other = (double)(q - s0) / (double)n;
+                const double diff = SIDE == 0 ? fabs(f_own - f_other) : fabs(f_other - f_own);
+                if (diff > dmax) dmax = diff;
+            }
+            cur = nxt;
+        }
+        if (dmax > 0.0) atomicMax(reinterpret_cast<unsigned long long*>(ks + e), (unsigned long long)__double_as_longlong(dmax));
     }
-    return lo;
-}
-// number of elements with ((double)a[i] - m) <= z  (a ascending)
-__device__ __forceinline__ int count_le_shifted(const int* a, int n, double m, double z) {
-    int lo = 0, hi = n;
-    while (lo < hi) {
-        const int mid = (lo + hi) >> 1;
-        if ((double)a[mid] - m <= z) lo = mid + 1; else hi = mid;
-    }
-    return lo;
 }
 
 struct ScoreArgs {
@@ -320,78 +400,29 @@ struct ScoreArgs {
     long long n_edges;
     const int* scaf_len;
     ScoreConsts c;
-    int scoring;
-    // big-edge spill list
-    int* big_list;        // [0] = count, then edge ids
-    long long* big_off;   // scratch offset per big edge
-    u64* scratch_used;
-    int* scratch;
-    long long scratch_cap;
 };
 
-constexpr int SC_WARPS = 4;
-constexpr int SC_NS = 1024;  // longest list sorted by one warp in shared memory
-
-// KS statistic + score of one edge whose two lists are already loaded into
-// sa (obs on edge_u's scaffold) and sb (max - obs on edge_v's scaffold), padded
-// to npad with INT_MAX.  Called by the whole group; the result is written by
-// thread 0.  red = group reduction scratch (only used when G > 32).
-template <int G>
-__device__ __forceinline__ void score_edge(const ScoreArgs& A, long long e, int* sa, int* sb, int n, int npad,
-                                           long long sum_u, long long sum_y, int t, double* red) {
-    bitonic_sort<G>(sa, npad, t);
-    bitonic_sort<G>(sb, npad, t);
-    const double m1 = (double)sum_u / (double)n;   // l1_mean (:584)
-    const double m2 = (double)sum_y / (double)n;   // l2_mean (:591)
-    double dmax = 0.0;
-    for (int i = t; i < n; i += G) {
-        {
-            const double z = (double)sa[i] - m1;
-            const int k1 = upper_bound_int(sa, n, sa[i]);
-            const int k2 = count_le_shifted(sb, n, m2, z);
-            const double diff = fabs((double)k1 / (double)n - (double)k2 / (double)n);
-            if (diff > dmax) dmax = diff;
-        }
-        {
-            const double z = (double)sb[i] - m2;
-            const int k2 = upper_bound_int(sb, n, sb[i]);
-            const int k1 = count_le_shifted(sa, n, m1, z);
-            const double diff = fabs((double)k1 / (double)n - (double)k2 / (double)n);
-            if (diff > dmax) dmax = diff;
-        }
-    }
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) {
-        const double o = __shfl_xor_sync(0xffffffffu, dmax, off);
-        if (o > dmax) dmax = o;
-    }
-    if (G > 32) {
-        if ((t & 31) == 0) red[t >> 5] = dmax;
-        __syncthreads();
-        if (t < 32) {
-            dmax = t < G / 32 ? red[t] : 0.0;
-#pragma unroll
-            for (int off = 16; off > 0; off >>= 1) {
-                const double o = __shfl_xor_sync(0xffffffffu, dmax, off);
-                if (o > dmax) dmax = o;
-            }
-        }
-    }
-    if (t >= 32) return;  // warp 0 of the group finishes (quad shuffles need a full warp)
-
+// ---- K6: GapEstimator + tr_sk_std_dev + score, one quad of lanes per edge (CreateGraph.py:501-614) ----
+__global__ void __launch_bounds__(128) k_edge_finalize(const ScoreArgs A) {
+    const long long e = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 2;
+    const bool in_range = e < A.n_edges;
+    const bool ll = in_range && (A.E.flags[e] & BESST_EDGE_LL);
     const ScoreConsts& c = A.c;
-    const double len1 = (double)A.scaf_len[A.E.u[e] >> 1], len2 = (double)A.scaf_len[A.E.v[e] >> 1];
-    const long long obs = A.E.obs[e], obs_sq = A.E.obs_sq[e];
-    unsigned char flags = A.E.flags[e] | BESST_EDGE_SCORED;
+    const int n = ll ? A.E.nr[e] : 1;
+    const double len1 = ll ? (double)A.scaf_len[A.E.u[e] >> 1] : 1.0, len2 = ll ? (double)A.scaf_len[A.E.v[e] >> 1] : 1.0;
+    const long long obs = ll ? A.E.obs[e] : 0, obs_sq = ll ? A.E.obs_sq[e] : 0;
+    const double dmax = ll ? A.E.ks[e] : 0.0;   // accumulated by k_ks_eval (initialised to +0.0)
+    unsigned char flags = ll ? (A.E.flags[e] | BESST_EDGE_SCORED) : 0;
     const double mean_ = (double)obs / (double)n;                                     // :505
     const double data_observation = ((double)n * c.mean - (double)obs) / (double)n;   // :511
-    const bool big = (2 * c.sd < len1) && (2 * c.sd < len2);                          // :536
+    const bool big = ll && (2 * c.sd < len1) && (2 * c.sd < len2);                    // :536
     const int gap_ml = gap_estimator_quad(c, mean_, len1, len2, big);
     double gap = data_observation;
     if (big) { gap = (double)gap_ml; flags |= BESST_EDGE_BIG; }
     const int gap_int = (int)gap;                                                     // :541
     const bool neg = (-gap > len1) || (-gap > len2);                                  // :542
     const double sd_ml = tr_sk_std_dev_quad(c, len1, len2, gap);
+    if (!ll || (threadIdx.x & 3) != 0) return;
     const double nan = __longlong_as_double(0x7ff8000000000000ll);
     double score = 0.0, ks_out = nan, sd_obs_out = nan, sd_model_out = nan;
     if (neg) {
@@ -415,126 +446,68 @@ __device__ __forceinline__ void score_edge(const ScoreArgs& A, long long e, int*
         score = (std_dev_score > 0.5 && span_score > 0.5) ? std_dev_score + span_score : 0.0;  // :614
         ks_out = dmax; sd_obs_out = std_dev; sd_model_out = std_dev_d_eq_0;
     }
-    if (t == 0) {
-        A.E.gap[e] = gap_int;
-        A.E.score[e] = score;
-        A.E.ks[e] = ks_out;
-        A.E.sd_obs[e] = sd_obs_out;
-        A.E.sd_model[e] = sd_model_out;
-        A.E.flags[e] = flags;
+    A.E.gap[e] = gap_int;
+    A.E.score[e] = score;
+    A.E.ks[e] = ks_out;
+    A.E.sd_obs[e] = sd_obs_out;
+    A.E.sd_model[e] = sd_model_out;
+    A.E.flags[e] = flags;
+}
+
+// ---- exclusive scan of (LL ? nr_links : 0) over the edges -> ll_off[E+1] -------------------------------
+constexpr int LS_THREADS = 256;
+constexpr int LS_ITEMS = 8;
+constexpr int LS_TILE = LS_THREADS * LS_ITEMS;
+
+__global__ void __launch_bounds__(LS_THREADS) k_ll_count(const unsigned char* __restrict__ flags, const int* __restrict__ nr,
+                                                         long long n_edges, u32* block_sums) {
+    __shared__ u32 s_w[LS_THREADS / 32];
+    const long long base = (long long)blockIdx.x * LS_TILE;
+    u32 c = 0;
+#pragma unroll
+    for (int i = 0; i < LS_ITEMS; ++i) {
+        const long long e = base + i * LS_THREADS + threadIdx.x;
+        if (e < n_edges && (flags[e] & BESST_EDGE_LL)) c += (u32)nr[e];
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) c += __shfl_xor_sync(0xffffffffu, c, off);
+    if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = c;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        u32 t = 0;
+        for (int w = 0; w < LS_THREADS / 32; ++w) t += s_w[w];
+        block_sums[blockIdx.x] = t;
     }
 }
 
-__global__ void __launch_bounds__(SC_WARPS * 32) k_edge_score(const ScoreArgs A) {
-    __shared__ int s_a[SC_WARPS][SC_NS];
-    __shared__ int s_b[SC_WARPS][SC_NS];
+__global__ void __launch_bounds__(LS_THREADS) k_ll_write(const unsigned char* __restrict__ flags, const int* __restrict__ nr,
+                                                         long long n_edges, const u32* __restrict__ block_sums, u32* ll_off) {
+    __shared__ u32 s_w[LS_THREADS / 32];
+    const long long base = (long long)blockIdx.x * LS_TILE + (long long)threadIdx.x * LS_ITEMS;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const long long warp_global = (long long)blockIdx.x * SC_WARPS + warp;
-    const long long n_warps = (long long)gridDim.x * SC_WARPS;
-    for (long long e = warp_global; e < A.n_edges; e += n_warps) {
-        if (!(A.E.flags[e] & BESST_EDGE_LL)) continue;
-        const int n = A.E.nr[e];
-        if (n > SC_NS) {
-            if (lane == 0) {
-                int npad = 1;
-                while (npad < n) npad <<= 1;
-                const int slot = atomicAdd(&A.big_list[0], 1);
-                A.big_list[1 + slot] = (int)e;
-                A.big_off[slot] = (long long)atomicAdd(A.scratch_used, (u64)(2ll * npad));
-            }
-            continue;
-        }
-        const long long b = A.E.row_ptr[e];
-        int npad = 1;
-        while (npad < n) npad <<= 1;
-        long long sum_u = 0;
-        int max_v = -2147483647 - 1;
-        for (int i = lane; i < npad; i += 32) {
-            int x = 2147483647, y = -2147483647 - 1;
-            if (i < n) { x = A.E.obs_u[b + i]; y = A.E.obs_v[b + i]; sum_u += x; }
-            s_a[warp][i] = x;
-            s_b[warp][i] = y;
-            if (y > max_v) max_v = y;
-        }
+    u32 v[LS_ITEMS], c = 0;
 #pragma unroll
-        for (int off = 16; off > 0; off >>= 1) {
-            sum_u += __shfl_xor_sync(0xffffffffu, sum_u, off);
-            const int o = __shfl_xor_sync(0xffffffffu, max_v, off);
-            if (o > max_v) max_v = o;
-        }
-        __syncwarp();
-        long long sum_y = 0;
-        for (int i = lane; i < npad; i += 32) {
-            if (i < n) {
-                const int y = max_v - s_b[warp][i];   // abs(x - max_obs2), :588-590
-                s_b[warp][i] = y;
-                sum_y += y;
-            } else {
-                s_b[warp][i] = 2147483647;
-            }
-        }
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) sum_y += __shfl_xor_sync(0xffffffffu, sum_y, off);
-        __syncwarp();
-        score_edge<32>(A, e, s_a[warp], s_b[warp], n, npad, sum_u, sum_y, lane, nullptr);
-        __syncwarp();
+    for (int i = 0; i < LS_ITEMS; ++i) {
+        const long long e = base + i;
+        v[i] = (e < n_edges && (flags[e] & BESST_EDGE_LL)) ? (u32)nr[e] : 0u;
+        c += v[i];
     }
-}
-
-constexpr int SB_THREADS = 256;
-
-// edges with more than SC_NS links: one CTA per edge, lists sorted in global scratch
-__global__ void __launch_bounds__(SB_THREADS) k_edge_score_big(const ScoreArgs A) {
-    __shared__ double s_red[SB_THREADS / 32];
-    __shared__ long long s_sum[SB_THREADS / 32];
-    __shared__ int s_max[SB_THREADS / 32];
-    const int n_big = A.big_list[0];
-    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
-    for (int k = blockIdx.x; k < n_big; k += gridDim.x) {
-        const long long e = A.big_list[1 + k];
-        const int n = A.E.nr[e];
-        int npad = 1;
-        while (npad < n) npad <<= 1;
-        const long long off = A.big_off[k];
-        if (off + 2ll * npad > A.scratch_cap) continue;  // cannot happen: cap >= 4*n_links
-        int* sa = A.scratch + off;
-        int* sb = sa + npad;
-        const long long b = A.E.row_ptr[e];
-        long long sum_u = 0;
-        int max_v = -2147483647 - 1;
-        for (int i = t; i < npad; i += SB_THREADS) {
-            int x = 2147483647, y = -2147483647 - 1;
-            if (i < n) { x = A.E.obs_u[b + i]; y = A.E.obs_v[b + i]; sum_u += x; }
-            sa[i] = x;
-            sb[i] = y;
-            if (y > max_v) max_v = y;
-        }
+    u32 incl = c;
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            sum_u += __shfl_xor_sync(0xffffffffu, sum_u, o);
-            const int m = __shfl_xor_sync(0xffffffffu, max_v, o);
-            if (m > max_v) max_v = m;
-        }
-        if (lane == 0) { s_sum[warp] = sum_u; s_max[warp] = max_v; }
-        __syncthreads();
-        sum_u = 0;
-        for (int w = 0; w < SB_THREADS / 32; ++w) { sum_u += s_sum[w]; if (s_max[w] > max_v) max_v = s_max[w]; }
-        __syncthreads();
-        long long sum_y = 0;
-        for (int i = t; i < npad; i += SB_THREADS) {
-            if (i < n) { const int y = max_v - sb[i]; sb[i] = y; sum_y += y; }
-            else sb[i] = 2147483647;
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) sum_y += __shfl_xor_sync(0xffffffffu, sum_y, o);
-        if (lane == 0) s_sum[warp] = sum_y;
-        __syncthreads();
-        sum_y = 0;
-        for (int w = 0; w < SB_THREADS / 32; ++w) sum_y += s_sum[w];
-        __syncthreads();
-        score_edge<SB_THREADS>(A, e, sa, sb, n, npad, sum_u, sum_y, t, s_red);
-        __syncthreads();
+    for (int off = 1; off < 32; off <<= 1) {
+        const u32 t = __shfl_up_sync(0xffffffffu, incl, off);
+        if (lane >= off) incl += t;
     }
+    if (lane == 31) s_w[warp] = incl;
+    __syncthreads();
+    u32 pos = block_sums[blockIdx.x] + incl - c;
+    for (int w = 0; w < warp; ++w) pos += s_w[w];
+#pragma unroll
+    for (int i = 0; i < LS_ITEMS; ++i) {
+        if (base + i < n_edges) ll_off[base + i] = pos;
+        pos += v[i];
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) ll_off[n_edges] = block_sums[gridDim.x];
 }
 
 // ---- batched GapEstimator + tr_sk_std_dev: one quad per item -------------------------------
@@ -613,6 +586,8 @@ int besst_launch_graph(besst_ctx* ctx, const besst_lib_params& p, const besst_li
     ctx->have_graph = false;
     ctx->n_links = n;
     ctx->n_edges = 0;
+    ctx->n_ll_links = 0;
+    ctx->sweep_kernel_id = BESST_K_RADIX_SWEEP;
     ctx->last_params = p;
     const int bv = bits_for((uint64_t)(2 * ctx->n_scaffolds > 0 ? 2 * ctx->n_scaffolds - 1 : 1));
     const size_t nz = (size_t)(n > 0 ? n : 1);
@@ -670,6 +645,8 @@ int besst_launch_graph(besst_ctx* ctx, const besst_lib_params& p, const besst_li
     EA.ks = ctx->e_ks.as<double>(); EA.sd_obs = ctx->e_sd_obs.as<double>(); EA.sd_model = ctx->e_sd_model.as<double>();
     EA.fishy = ctx->e_fishy.as<int>(); EA.flags = ctx->e_flags.as<unsigned char>();
     EA.obs_u = ctx->l_obs_u.as<int>(); EA.obs_v = ctx->l_obs_v.as<int>();
+    BESST_CUDA_TRY(ctx, ctx->e_sum_u.ensure(8 * Ez)); BESST_CUDA_TRY(ctx, ctx->e_max_v.ensure(4 * Ez));
+    EA.sum_u = ctx->e_sum_u.as<long long>(); EA.max_v = ctx->e_max_v.as<int>();
     if (E == 0) {
         const long long zero = 0;
         BESST_CUDA_TRY(ctx, cudaMemcpyAsync(EA.row_ptr, &zero, 8, cudaMemcpyHostToDevice, ctx->stream));
@@ -688,30 +665,71 @@ int besst_launch_graph(besst_ctx* ctx, const besst_lib_params& p, const besst_li
         if (grid > max_grid) grid = max_grid;
         KTimer kt(ctx, BESST_K_EDGE_REDUCE);
         k_edge_reduce<<<grid, 256, 0, ctx->stream>>>(EA, E, d_tuples, idx, keys, bv, fishy_sorted, n_fishy,
-                                                     (u32)(2 * ctx->n_large));
+                                                     (u32)(2 * ctx->n_large), p.no_score ? 0 : 1);
         BESST_CUDA_TRY(ctx, cudaGetLastError());
     }
     besst_mark(ctx);
 
     // ---- K5/K6: KS + GapEst + score on large-large edges --------------------------------
     if (!p.no_score) {
-        BESST_CUDA_TRY(ctx, ctx->big_list.ensure(4 * (Ez + 1) + 8 * Ez + 16));
-        BESST_CUDA_TRY(ctx, ctx->big_scratch.ensure(4 * (4 * nz + 16)));
+        // LL link space
+        const int ls_blocks = (int)((E + LS_TILE - 1) / LS_TILE);
+        BESST_CUDA_TRY(ctx, ctx->ll_off.ensure(4 * (Ez + 2)));
+        BESST_CUDA_TRY(ctx, ctx->block_sums.ensure(4 * (size_t)(std::max(ls_blocks, n_blocks) + 2)));
+        u32* ll_off = ctx->ll_off.as<u32>();
+        u32 n_ll32 = 0;
+        { KTimer kt(ctx, BESST_K_EDGE_SCORE); k_ll_count<<<ls_blocks, LS_THREADS, 0, ctx->stream>>>(EA.flags, EA.nr, E, ctx->block_sums.as<u32>()); }
+        { KTimer kt(ctx, BESST_K_EDGE_SCORE); k_scan_blocks<<<1, 1024, 0, ctx->stream>>>(ctx->block_sums.as<u32>(), ls_blocks); }
+        { KTimer kt(ctx, BESST_K_EDGE_SCORE); k_ll_write<<<ls_blocks, LS_THREADS, 0, ctx->stream>>>(EA.flags, EA.nr, E, ctx->block_sums.as<u32>(), ll_off); }
+        BESST_CUDA_TRY(ctx, cudaMemcpyAsync(&n_ll32, ctx->block_sums.as<u32>() + ls_blocks, 4, cudaMemcpyDeviceToHost, ctx->stream));
+        BESST_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+        const int64_t n_ll = n_ll32;
+        ctx->n_ll_links = n_ll;
+        if (n_ll > 0) {
+            // observations are < ins_size_threshold (CreateGraph.py:840), and so is max(obs_v) - obs_v
+            double thr = p.ins_size_threshold;
+            if (!(thr > 1)) thr = 1;
+            if (thr > 2147483647.0) thr = 2147483647.0;
+            const int value_bits = bits_for((uint64_t)thr);
+            const int edge_bits = bits_for((uint64_t)(E > 1 ? E - 1 : 1));
+            const int key_bits = value_bits + edge_bits;
+            KsArgs K;
+            K.row_ptr = EA.row_ptr; K.ll_off = ll_off; K.flags = EA.flags; K.sum_u = EA.sum_u; K.obs_sum = EA.obs;
+            K.max_v = EA.max_v; K.n_edges = E; K.n_ll = n_ll; K.value_bits = value_bits;
+            const bool narrow = key_bits <= 32;
+            const size_t kb = narrow ? 4 : 8;
+            BESST_CUDA_TRY(ctx, ctx->ks_key[0].ensure(kb * (size_t)n_ll)); BESST_CUDA_TRY(ctx, ctx->ks_key[1].ensure(kb * (size_t)n_ll));
+            BESST_CUDA_TRY(ctx, ctx->ks_key[2].ensure(kb * (size_t)n_ll)); BESST_CUDA_TRY(ctx, ctx->ks_key[3].ensure(kb * (size_t)n_ll));
+            long long kgrid = (E * 32 + 255) / 256;
+            if (kgrid > (long long)ctx->sm_count * 32) kgrid = (long long)ctx->sm_count * 32;
+            const long long chunks = (n_ll + KS_CHUNK - 1) / KS_CHUNK;
+            const unsigned egrid = (unsigned)((chunks + 255) / 256);
+            int b1 = 0, b2 = 0;
+            ctx->sweep_kernel_id = BESST_K_KS_SORT;
+            if (narrow) {
+                u32 *k1 = ctx->ks_key[0].as<u32>(), *k1t = ctx->ks_key[1].as<u32>(), *k2 = ctx->ks_key[2].as<u32>(), *k2t = ctx->ks_key[3].as<u32>();
+                { KTimer kt(ctx, BESST_K_EDGE_SCORE); k_score_keys<u32><<<(unsigned)kgrid, 256, 0, ctx->stream>>>(K, EA.obs_u, EA.obs_v, k1, k2); }
+                rc = besst_radix_sort_keys32(ctx, k1, k1t, n_ll, key_bits, &b1); if (rc) return rc;
+                rc = besst_radix_sort_keys32(ctx, k2, k2t, n_ll, key_bits, &b2); if (rc) return rc;
+                const u32 *s1 = b1 ? k1t : k1, *s2 = b2 ? k2t : k2;
+                { KTimer kt(ctx, BESST_K_KS_EVAL); k_ks_eval<u32, 0><<<egrid, 256, 0, ctx->stream>>>(K, s1, s2, EA.ks); }
+                { KTimer kt(ctx, BESST_K_KS_EVAL); k_ks_eval<u32, 1><<<egrid, 256, 0, ctx->stream>>>(K, s2, s1, EA.ks); }
+            } else {
+                u64 *k1 = ctx->ks_key[0].as<u64>(), *k1t = ctx->ks_key[1].as<u64>(), *k2 = ctx->ks_key[2].as<u64>(), *k2t = ctx->ks_key[3].as<u64>();
+                { KTimer kt(ctx, BESST_K_EDGE_SCORE); k_score_keys<u64><<<(unsigned)kgrid, 256, 0, ctx->stream>>>(K, EA.obs_u, EA.obs_v, k1, k2); }
+                rc = besst_radix_sort_keys(ctx, reinterpret_cast<uint64_t*>(k1), reinterpret_cast<uint64_t*>(k1t), n_ll, key_bits, &b1); if (rc) return rc;
+                rc = besst_radix_sort_keys(ctx, reinterpret_cast<uint64_t*>(k2), reinterpret_cast<uint64_t*>(k2t), n_ll, key_bits, &b2); if (rc) return rc;
+                const u64 *s1 = b1 ? k1t : k1, *s2 = b2 ? k2t : k2;
+                { KTimer kt(ctx, BESST_K_KS_EVAL); k_ks_eval<u64, 0><<<egrid, 256, 0, ctx->stream>>>(K, s1, s2, EA.ks); }
+                { KTimer kt(ctx, BESST_K_KS_EVAL); k_ks_eval<u64, 1><<<egrid, 256, 0, ctx->stream>>>(K, s2, s1, EA.ks); }
+            }
+            ctx->sweep_kernel_id = BESST_K_RADIX_SWEEP;
+            BESST_CUDA_TRY(ctx, cudaGetLastError());
+        }
         ScoreArgs A;
-        A.E = EA; A.n_edges = E; A.scaf_len = ctx->scaf_len.as<int>(); A.c = besst_score_consts(p); A.scoring = 1;
-        unsigned char* bl = ctx->big_list.as<unsigned char>();
-        A.scratch_used = reinterpret_cast<u64*>(bl);
-        A.big_off = reinterpret_cast<long long*>(bl + 8);
-        A.big_list = reinterpret_cast<int*>(bl + 8 + 8 * Ez);
-        A.scratch = ctx->big_scratch.as<int>();
-        A.scratch_cap = (long long)(4 * nz + 16);
-        BESST_CUDA_TRY(ctx, cudaMemsetAsync(A.scratch_used, 0, 8, ctx->stream));
-        BESST_CUDA_TRY(ctx, cudaMemsetAsync(A.big_list, 0, 4, ctx->stream));
-        int grid = (int)((E + SC_WARPS - 1) / SC_WARPS);
-        const int max_grid = ctx->sm_count * 16;
-        if (grid > max_grid) grid = max_grid;
-        { KTimer kt(ctx, BESST_K_EDGE_SCORE); k_edge_score<<<grid, SC_WARPS * 32, 0, ctx->stream>>>(A); }
-        { KTimer kt(ctx, BESST_K_EDGE_SCORE); k_edge_score_big<<<ctx->sm_count, SB_THREADS, 0, ctx->stream>>>(A); }
+        A.E = EA; A.n_edges = E; A.scaf_len = ctx->scaf_len.as<int>(); A.c = besst_score_consts(p);
+        const unsigned fgrid = (unsigned)((E * 4 + 127) / 128);
+        { KTimer kt(ctx, BESST_K_GAPEST); k_edge_finalize<<<fgrid, 128, 0, ctx->stream>>>(A); }
         BESST_CUDA_TRY(ctx, cudaGetLastError());
     }
     besst_mark(ctx);

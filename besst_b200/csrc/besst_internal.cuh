@@ -90,8 +90,8 @@ struct besst_ctx {
     // CSR / per-edge results
     DBuf fishy_sorted, fishy_tmp, heads, block_sums;
     DBuf e_u, e_v, e_nr, e_obs, e_obs_sq, e_first, e_row_ptr, e_gap, e_score, e_ks, e_sd_obs, e_sd_model, e_fishy,
-        e_flags, l_obs_u, l_obs_v, big_list, big_scratch;
-    int64_t n_edges = 0, n_links = 0, n_fishy_pairs = 0;
+        e_flags, l_obs_u, l_obs_v, e_sum_u, e_max_v, ll_off, ks_key[4];
+    int64_t n_edges = 0, n_links = 0, n_fishy_pairs = 0, n_ll_links = 0;
     bool have_graph = false;
     besst_lib_params last_params;
 
@@ -106,6 +106,7 @@ struct besst_ctx {
     bool ev_valid = false;
     int n_stage_marks = 0;
     int64_t launches = 0;
+    int sweep_kernel_id = BESST_K_RADIX_SWEEP;  // profiling id of the next radix sort's digit passes
 };
 
 // ---- launchers (one per translation unit) ----------------------------------

@@ -35,8 +35,8 @@ __device__ __forceinline__ u32 ld_vol32(const u32* p) { return *reinterpret_cast
 __device__ __forceinline__ void st_vol32(u32* p, u32 v) { *reinterpret_cast<volatile u32*>(p) = v; }
 
 // ---- histograms of all passes in one read --------------------------------------
-template <bool FROM_TUPLES>
-__global__ void __launch_bounds__(RS_THREADS) k_radix_hist(const u64* __restrict__ keys,
+template <typename KeyT, bool FROM_TUPLES>
+__global__ void __launch_bounds__(RS_THREADS) k_radix_hist(const KeyT* __restrict__ keys,
                                                             const besst_link_tuple* __restrict__ tuples, int bv,
                                                             long long n, int passes, u32* __restrict__ ghist) {
     __shared__ u32 sh[RS_MAX_PASSES * RS_RADIX];
@@ -53,7 +53,7 @@ __global__ void __launch_bounds__(RS_THREADS) k_radix_hist(const u64* __restrict
                 const uint2 uv = __ldg(reinterpret_cast<const uint2*>(tuples + i));
                 key = ((u64)uv.x << bv) | uv.y;
             } else {
-                key = __ldg(keys + i);
+                key = (u64)__ldg(keys + i);
             }
         }
         const unsigned vmask = __ballot_sync(0xffffffffu, valid);
@@ -86,8 +86,9 @@ __global__ void __launch_bounds__(RS_RADIX) k_radix_scan_hist(u32* ghist) {
     h[threadIdx.x] = s[threadIdx.x] - v;
 }
 
+template <typename KeyT>
 struct SweepSmem {
-    u64 keys[RS_TILE];
+    KeyT keys[RS_TILE];
     u32 vals[RS_TILE];
     u32 warp_hist[RS_WARPS][RS_RADIX];
     u32 digit_start[RS_RADIX];
@@ -96,14 +97,14 @@ struct SweepSmem {
     int tile;
 };
 
-template <bool FROM_TUPLES, bool HAS_VAL>
+template <typename KeyT, bool FROM_TUPLES, bool HAS_VAL>
 __global__ void __launch_bounds__(RS_THREADS)
-    k_radix_sweep(const u64* __restrict__ in_keys, const u32* __restrict__ in_vals,
-                  const besst_link_tuple* __restrict__ tuples, int bv, u64* __restrict__ out_keys,
+    k_radix_sweep(const KeyT* __restrict__ in_keys, const u32* __restrict__ in_vals,
+                  const besst_link_tuple* __restrict__ tuples, int bv, KeyT* __restrict__ out_keys,
                   u32* __restrict__ out_vals, long long n, int shift, const u32* __restrict__ gbase,
                   u32* status, u32* ticket, int n_tiles) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    SweepSmem& S = *reinterpret_cast<SweepSmem*>(smem_raw);
+    SweepSmem<KeyT>& S = *reinterpret_cast<SweepSmem<KeyT>*>(smem_raw);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned lt_mask = (1u << lane) - 1u;
 
@@ -118,18 +119,18 @@ __global__ void __launch_bounds__(RS_THREADS)
         const long long rem = n - tile_base;
         const int tile_count = rem < RS_TILE ? (int)rem : RS_TILE;
 
-        u64 key[RS_ITEMS];
+        KeyT key[RS_ITEMS];
         u32 val[RS_ITEMS];
         unsigned short rank[RS_ITEMS];
 #pragma unroll
         for (int i = 0; i < RS_ITEMS; ++i) {
             const int off = warp * (32 * RS_ITEMS) + i * 32 + lane;
-            key[i] = ~0ull;
+            key[i] = (KeyT)~0ull;
             val[i] = 0;
             if (off < tile_count) {
                 if (FROM_TUPLES) {
                     const uint2 uv = __ldg(reinterpret_cast<const uint2*>(tuples + tile_base + off));
-                    key[i] = ((u64)uv.x << bv) | uv.y;
+                    key[i] = (KeyT)(((u64)uv.x << bv) | uv.y);
                     val[i] = (u32)(tile_base + off);
                 } else {
                     key[i] = __ldg(in_keys + tile_base + off);
@@ -214,7 +215,7 @@ __global__ void __launch_bounds__(RS_THREADS)
         }
         __syncthreads();
         for (int j = threadIdx.x; j < tile_count; j += RS_THREADS) {
-            const u64 k = S.keys[j];
+            const KeyT k = S.keys[j];
             const u32 d = (u32)(k >> shift) & 255u;
             const long long dest = S.gbase[d] + j;
             out_keys[dest] = k;
@@ -223,8 +224,8 @@ __global__ void __launch_bounds__(RS_THREADS)
     }
 }
 
-template <bool FROM_TUPLES, bool HAS_VAL>
-int sort_impl(besst_ctx* ctx, const besst_link_tuple* tuples, int bv, u64* keys_a, u64* keys_b, u32* val_a,
+template <typename KeyT, bool FROM_TUPLES, bool HAS_VAL>
+int sort_impl(besst_ctx* ctx, const besst_link_tuple* tuples, int bv, KeyT* keys_a, KeyT* keys_b, u32* val_a,
               u32* val_b, int64_t n, int key_bits, int* result_in_b) {
     *result_in_b = 0;
     int passes = (key_bits + 7) / 8;
@@ -241,43 +242,42 @@ int sort_impl(besst_ctx* ctx, const besst_link_tuple* tuples, int bv, u64* keys_
     int hgrid = ctx->sm_count * 8;
     const long long max_blocks = (n + RS_THREADS - 1) / RS_THREADS;
     if (hgrid > max_blocks) hgrid = (int)max_blocks;
-    { KTimer kt(ctx, BESST_K_RADIX_HIST); k_radix_hist<FROM_TUPLES><<<hgrid, RS_THREADS, 0, ctx->stream>>>(keys_a, tuples, bv, n, passes, ghist); }
+    { KTimer kt(ctx, BESST_K_RADIX_HIST); k_radix_hist<KeyT, FROM_TUPLES><<<hgrid, RS_THREADS, 0, ctx->stream>>>(keys_a, tuples, bv, n, passes, ghist); }
     { KTimer kt(ctx, BESST_K_RADIX_SCAN); k_radix_scan_hist<<<passes, RS_RADIX, 0, ctx->stream>>>(ghist); }
     BESST_CUDA_TRY(ctx, cudaGetLastError());
 
-    const size_t smem = sizeof(SweepSmem);
+    const size_t smem = sizeof(SweepSmem<KeyT>);
     static bool attr_done = false;
     if (!attr_done) {
-        cudaFuncSetAttribute(k_radix_sweep<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        cudaFuncSetAttribute(k_radix_sweep<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        cudaFuncSetAttribute(k_radix_sweep<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (FROM_TUPLES) cudaFuncSetAttribute(k_radix_sweep<KeyT, FROM_TUPLES, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(k_radix_sweep<KeyT, false, HAS_VAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         attr_done = true;
     }
     int per_sm = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_radix_sweep<false, HAS_VAL>, RS_THREADS, smem);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_radix_sweep<KeyT, false, HAS_VAL>, RS_THREADS, smem);
     if (per_sm < 1) per_sm = 1;
     int grid = ctx->sm_count * per_sm;
     if (grid > n_tiles) grid = n_tiles;
 
-    const u64* in_k = keys_a;
+    const KeyT* in_k = keys_a;
     const u32* in_v = val_a;
-    u64* out_k = keys_b;
+    KeyT* out_k = keys_b;
     u32* out_v = val_b;
     for (int p = 0; p < passes; ++p) {
         BESST_CUDA_TRY(ctx, cudaMemsetAsync(ctx->sort_state.p, 0, sizeof(u32) * (size_t)n_tiles * RS_RADIX, ctx->stream));
         {
-        KTimer kt(ctx, BESST_K_RADIX_SWEEP);
+        KTimer kt(ctx, ctx->sweep_kernel_id);
         if (p == 0 && FROM_TUPLES)
-            k_radix_sweep<true, true><<<grid, RS_THREADS, smem, ctx->stream>>>(
+            k_radix_sweep<KeyT, FROM_TUPLES, true><<<grid, RS_THREADS, smem, ctx->stream>>>(
                 nullptr, nullptr, tuples, bv, out_k, out_v, n, 0, ghist, ctx->sort_state.as<u32>(), tickets + p, n_tiles);
         else
-            k_radix_sweep<false, HAS_VAL><<<grid, RS_THREADS, smem, ctx->stream>>>(
+            k_radix_sweep<KeyT, false, HAS_VAL><<<grid, RS_THREADS, smem, ctx->stream>>>(
                 in_k, in_v, nullptr, bv, out_k, out_v, n, 8 * p, ghist + p * RS_RADIX, ctx->sort_state.as<u32>(),
                 tickets + p, n_tiles);
         }
         BESST_CUDA_TRY(ctx, cudaGetLastError());
         // ping-pong: after the first pass from tuples the data lives in (keys_b, val_b)
-        const u64* nk = out_k;
+        const KeyT* nk = out_k;
         const u32* nv = out_v;
         out_k = (out_k == keys_b) ? keys_a : keys_b;
         out_v = (out_v == val_b) ? val_a : val_b;
@@ -292,19 +292,23 @@ int sort_impl(besst_ctx* ctx, const besst_link_tuple* tuples, int bv, u64* keys_
 
 int besst_radix_sort_pairs(besst_ctx* ctx, uint64_t* keys_a, uint64_t* keys_b, uint32_t* val_a, uint32_t* val_b,
                            int64_t n, int key_bits, int* result_in_b) {
-    return sort_impl<false, true>(ctx, nullptr, 0, reinterpret_cast<u64*>(keys_a), reinterpret_cast<u64*>(keys_b), val_a,
-                                  val_b, n, key_bits, result_in_b);
+    return sort_impl<u64, false, true>(ctx, nullptr, 0, reinterpret_cast<u64*>(keys_a), reinterpret_cast<u64*>(keys_b), val_a,
+                                       val_b, n, key_bits, result_in_b);
 }
 
 int besst_radix_sort_keys(besst_ctx* ctx, uint64_t* keys_a, uint64_t* keys_b, int64_t n, int key_bits,
                           int* result_in_b) {
-    return sort_impl<false, false>(ctx, nullptr, 0, reinterpret_cast<u64*>(keys_a), reinterpret_cast<u64*>(keys_b),
-                                   nullptr, nullptr, n, key_bits, result_in_b);
+    return sort_impl<u64, false, false>(ctx, nullptr, 0, reinterpret_cast<u64*>(keys_a), reinterpret_cast<u64*>(keys_b),
+                                        nullptr, nullptr, n, key_bits, result_in_b);
+}
+
+int besst_radix_sort_keys32(besst_ctx* ctx, uint32_t* keys_a, uint32_t* keys_b, int64_t n, int key_bits, int* result_in_b) {
+    return sort_impl<u32, false, false>(ctx, nullptr, 0, keys_a, keys_b, nullptr, nullptr, n, key_bits, result_in_b);
 }
 
 // tuples (BAM order) -> sorted (key, original index); key = (u << bv) | v
 int besst_radix_sort_tuples(besst_ctx* ctx, const besst_link_tuple* tuples, int bv, uint64_t* keys_a, uint64_t* keys_b,
                             uint32_t* val_a, uint32_t* val_b, int64_t n, int* result_in_b) {
-    return sort_impl<true, true>(ctx, tuples, bv, reinterpret_cast<u64*>(keys_a), reinterpret_cast<u64*>(keys_b), val_a,
-                                 val_b, n, 2 * bv, result_in_b);
+    return sort_impl<u64, true, true>(ctx, tuples, bv, reinterpret_cast<u64*>(keys_a), reinterpret_cast<u64*>(keys_b), val_a,
+                                      val_b, n, 2 * bv, result_in_b);
 }

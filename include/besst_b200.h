@@ -136,7 +136,8 @@ typedef struct besst_graph_sizes {
     int64_t n_edges;   /* E: distinct link edges */
     int64_t n_links;   /* Lk: accepted links = sum of nr_links */
     int64_t n_contigs; /* C */
-    int64_t n_fishy;   /* distinct fishy node pairs */
+    int64_t n_fishy;   /* fishy keys (unmapped-read1 records, :141-163) seen by this build */
+    int64_t n_ll_links; /* links on large-large edges (the ones that are scored) */
 } besst_graph_sizes;
 
 /* Caller-allocated result arrays (host).  Edges are sorted by (edge_u, edge_v),
@@ -268,14 +269,16 @@ int besst_kernel_launches(besst_ctx* ctx, int64_t* n_launches);
 #define BESST_K_RADIX_SWEEP 3  /* k_radix_sweep, one per digit pass (K3) */
 #define BESST_K_HEADS 4        /* k_head_count/k_scan_blocks/k_head_write (K4) */
 #define BESST_K_EDGE_REDUCE 5  /* k_edge_reduce            (K4) */
-#define BESST_K_EDGE_SCORE 6   /* k_edge_score(+_big)      (K5/K6) */
+#define BESST_K_EDGE_SCORE 6   /* k_ll_count/k_ll_write/k_score_keys: LL link space + sort keys (K5) */
 #define BESST_K_FISHY 7        /* k_fishy_rekey */
 #define BESST_K_METRICS 8      /* k_metrics_*              (K7) */
-#define BESST_K_GAPEST 9       /* k_gapest_batch           (K6) */
+#define BESST_K_GAPEST 9       /* k_gapest_batch / k_edge_finalize (K6) */
 #define BESST_K_TILE_SCAN 10   /* k_tile_reduce/k_chunk_resolve/k_tile_offsets (K2) */
 #define BESST_K_COMPACT 11     /* k_compact_tuples         (K1) */
 #define BESST_K_PARTITION 12   /* k_partition_count/scan/scatter (multi-GPU) */
-#define BESST_N_KERNEL_IDS 13
+#define BESST_K_KS_EVAL 13     /* k_ks_eval                (K5) */
+#define BESST_K_KS_SORT 14     /* k_radix_sweep on the (edge, value) keys of K5, one per digit pass */
+#define BESST_N_KERNEL_IDS 15
 int besst_set_profiling(besst_ctx* ctx, int enabled);
 int besst_kernel_profile(besst_ctx* ctx, int32_t* kernel_ids, float* ms, int32_t cap);
 

@@ -552,6 +552,7 @@ besst_oracle_result* besst_oracle_graph_build(const besst_contig_row* rows, int6
     o->counters[BESST_CNT_CALLS] = calls; o->counters[BESST_CNT_VALID] = valid;
     o->counters[BESST_CNT_LAST_OBS1] = st.prev1; o->counters[BESST_CNT_LAST_OBS2] = st.prev2;
     R->sizes.n_edges = E; R->sizes.n_links = U->n_links; R->sizes.n_contigs = n_contigs; R->sizes.n_fishy = fishy_n;
+    { int64_t nll = 0; for (int64_t k = 0; k < E; ++k) if (o->flags[k] & BESST_EDGE_LL) nll += o->nr_links[k]; R->sizes.n_ll_links = nll; }
     R->fishy_keys = fishy_key; R->fishy_counts = fishy_cnt;
     free(order); free(rank); free(cursor); free(slen);
     map_free(&fishy); gs_free(&G); gs_free(&GP);
