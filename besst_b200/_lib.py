@@ -62,7 +62,7 @@ def load():
     L.besst_kernel_profile.argtypes = [vp, vp, vp, i32]
     L.besst_links_partials_device.argtypes = [vp, C.POINTER(vp), C.POINTER(vp)]
     L.besst_links_fetch.argtypes = [vp, vp, vp]
-    L.besst_links_partition.argtypes = [vp, i32, vp, vp, vp, vp]
+    L.besst_links_partition.argtypes = [vp, i32, vp, vp, vp, vp, vp]
     L.besst_trsk_sd_batch.argtypes = [vp, C.POINTER(abi.LibParams), vp, vp, vp, i64, vp]
     L.besst_set_stream.argtypes = [vp, vp]
     if L.besst_abi_version() != abi.ABI_VERSION:

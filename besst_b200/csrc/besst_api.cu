@@ -196,14 +196,15 @@ extern "C" int besst_links_fetch(besst_ctx* ctx, besst_link_tuple* tuples_host, 
 }
 
 extern "C" int besst_links_partition(besst_ctx* ctx, int32_t world, besst_link_tuple* out_tuples_device,
-                                     uint64_t* out_fishy_device, int64_t* tuple_counts, int64_t* fishy_counts) {
+                                     uint32_t* out_ordinals_device, uint64_t* out_fishy_device, int64_t* tuple_counts,
+                                     int64_t* fishy_counts) {
     if (!ctx || !ctx->have_links) { if (ctx) ctx->err = "no extracted links"; return BESST_E_STATE; }
     if (!tuple_counts || !fishy_counts || (ctx->n_tuples > 0 && !out_tuples_device) || (ctx->n_fishy_keys > 0 && !out_fishy_device)) {
         ctx->err = "links_partition: bad arguments";
         return BESST_E_INVALID;
     }
     cudaSetDevice(ctx->device);
-    return besst_launch_partition(ctx, world, out_tuples_device, out_fishy_device, tuple_counts, fishy_counts);
+    return besst_launch_partition(ctx, world, out_tuples_device, out_ordinals_device, out_fishy_device, tuple_counts, fishy_counts);
 }
 
 extern "C" int besst_set_stream(besst_ctx* ctx, void* cuda_stream) {

@@ -660,7 +660,8 @@ __global__ void __launch_bounds__(1024) k_partition_scan(u32* counts, int n_tile
 template <bool TUPLES>
 __global__ void __launch_bounds__(PT_THREADS) k_partition_scatter(const void* __restrict__ in, long long n, int world,
                                                                   const u32* __restrict__ offs, int n_tiles,
-                                                                  const u64* __restrict__ starts, void* __restrict__ out) {
+                                                                  const u64* __restrict__ starts, void* __restrict__ out,
+                                                                  u32* __restrict__ ord_out) {
     __shared__ u32 s_wcnt[PT_THREADS / 32][PT_MAX_WORLD];
     __shared__ u64 s_base[PT_MAX_WORLD];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -704,13 +705,17 @@ __global__ void __launch_bounds__(PT_THREADS) k_partition_scatter(const void* __
         for (int q = 0; q < PT_MAX_WORLD; ++q)
             if (q == (int)dest[k]) { r = excl[q]; excl[q] += 1; }
         const u64 o = s_base[dest[k]] + r;
-        if (TUPLES) reinterpret_cast<int4*>(out)[o] = __ldg(reinterpret_cast<const int4*>(in) + base + k);
-        else reinterpret_cast<u64*>(out)[o] = __ldg(reinterpret_cast<const u64*>(in) + base + k);
+        if (TUPLES) {
+            reinterpret_cast<int4*>(out)[o] = __ldg(reinterpret_cast<const int4*>(in) + base + k);
+            if (ord_out) ord_out[o] = (u32)(base + k);   // ordinal in this rank's BAM-ordered tuple stream
+        } else {
+            reinterpret_cast<u64*>(out)[o] = __ldg(reinterpret_cast<const u64*>(in) + base + k);
+        }
     }
 }
 
 template <bool TUPLES>
-int partition_impl(besst_ctx* ctx, const void* in, int64_t n, int world, void* out, int64_t* counts_host) {
+int partition_impl(besst_ctx* ctx, const void* in, int64_t n, int world, void* out, u32* ord_out, int64_t* counts_host) {
     for (int d = 0; d < world; ++d) counts_host[d] = 0;
     if (n == 0) return BESST_OK;
     const int n_tiles = (int)((n + PT_TILE - 1) / PT_TILE);
@@ -720,7 +725,7 @@ int partition_impl(besst_ctx* ctx, const void* in, int64_t n, int world, void* o
     u32* counts = reinterpret_cast<u32*>(totals + PT_MAX_WORLD);
     { KTimer kt(ctx, BESST_K_PARTITION); k_partition_count<TUPLES><<<n_tiles, PT_THREADS, 0, ctx->stream>>>(in, n, world, counts, n_tiles); }
     { KTimer kt(ctx, BESST_K_PARTITION); k_partition_scan<<<1, 1024, 0, ctx->stream>>>(counts, n_tiles, world, starts, totals); }
-    { KTimer kt(ctx, BESST_K_PARTITION); k_partition_scatter<TUPLES><<<n_tiles, PT_THREADS, 0, ctx->stream>>>(in, n, world, counts, n_tiles, starts, out); }
+    { KTimer kt(ctx, BESST_K_PARTITION); k_partition_scatter<TUPLES><<<n_tiles, PT_THREADS, 0, ctx->stream>>>(in, n, world, counts, n_tiles, starts, out, ord_out); }
     BESST_CUDA_TRY(ctx, cudaGetLastError());
     u64 h[PT_MAX_WORLD];
     BESST_CUDA_TRY(ctx, cudaMemcpyAsync(h, totals, 8 * world, cudaMemcpyDeviceToHost, ctx->stream));
@@ -731,13 +736,13 @@ int partition_impl(besst_ctx* ctx, const void* in, int64_t n, int world, void* o
 
 }  // namespace
 
-int besst_launch_partition(besst_ctx* ctx, int world, besst_link_tuple* out_tuples, uint64_t* out_fishy,
-                           int64_t* tuple_counts, int64_t* fishy_counts) {
+int besst_launch_partition(besst_ctx* ctx, int world, besst_link_tuple* out_tuples, uint32_t* out_ordinals,
+                           uint64_t* out_fishy, int64_t* tuple_counts, int64_t* fishy_counts) {
     if (world < 1 || world > PT_MAX_WORLD) { ctx->err = "partition: world size must be 1..16"; return BESST_E_INVALID; }
     if (ctx->n_tuples >= (1ll << 30) || ctx->n_fishy_keys >= (1ll << 30)) { ctx->err = "partition: more than 2^30 items"; return BESST_E_INVALID; }
-    int rc = partition_impl<true>(ctx, ctx->tuples.p, ctx->n_tuples, world, out_tuples, tuple_counts);
+    int rc = partition_impl<true>(ctx, ctx->tuples.p, ctx->n_tuples, world, out_tuples, out_ordinals, tuple_counts);
     if (rc) return rc;
-    return partition_impl<false>(ctx, ctx->fishy_keys.p, ctx->n_fishy_keys, world, out_fishy, fishy_counts);
+    return partition_impl<false>(ctx, ctx->fishy_keys.p, ctx->n_fishy_keys, world, out_fishy, nullptr, fishy_counts);
 }
 
 int besst_launch_extract(besst_ctx* ctx, const besst_lib_params& p, const DeviceRecords& rec) {

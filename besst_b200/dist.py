@@ -1,0 +1,241 @@
+"""Multi-GPU graph build: one process per GPU, records range-partitioned in BAM
+order, ONE exchange step.
+
+The reference is a single sequential scan (CreateGraph.py:111-211); the only
+state that crosses a record boundary is "(obs1,obs2) of the previous CreateEdge
+call" (:835-838,869-870).  The decomposition therefore is:
+
+  1. halo    every rank finds the last CreateEdge observation of its own slice
+             (extract over the slice tail), an all_gather of 3 integers gives
+             each rank the last call of all preceding ranks;
+  2. extract records -> accepted link tuples of the slice (besst_links_extract,
+             with the halo) -- identical to what the sequential scan would do;
+  3. exchange tuples are bucketed by hash(edge) mod world (besst_links_partition,
+             stable) and sent with ONE all_to_all over NVLink; buckets arrive in
+             source-rank order = global BAM order;
+  4. build   every rank owns a disjoint edge set: bucket -> CSR -> KS -> GapEst
+             (besst_links_to_graph), no further communication;
+  5. reduce  per-contig aligned length and the counters: one all_reduce(sum).
+
+`torch.distributed` is plumbing (NCCL on GPUs, gloo in the CPU tests); all data
+movement on the device side goes through the C ABI.  The backend object hides
+the engine so that the host logic can be exercised on CPU with gloo.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import abi
+
+NO_MATCH = -(2 ** 31) + 1   # halo value no observation pair can equal
+
+
+def _copy_params(params, halo):
+    p = abi.LibParams()
+    C.memmove(C.byref(p), C.byref(params), C.sizeof(abi.LibParams))
+    p.halo_prev_obs1, p.halo_prev_obs2 = int(halo[0]), int(halo[1])
+    return p
+
+
+def records_tail(rec, count):
+    """View of the last `count` records of a device-resident Records struct
+    (start rounded down to a multiple of 16 records so that every column stays
+    16-byte aligned for the 128-bit loads)."""
+    n = int(rec.n)
+    lo = max(0, n - count)
+    lo -= lo % 16
+    r = abi.Records()
+    r.n = n - lo
+    for name, width in (("tid", 4), ("mtid", 4), ("pos", 4), ("mpos", 4), ("tlen", 4), ("qlen", 4), ("flag", 2), ("mapq", 1)):
+        base = getattr(rec, name)
+        setattr(r, name, (base + lo * width) if base else None)
+    r.on_device = rec.on_device
+    return r
+
+
+class CudaBackend(object):
+    """The engine + torch device buffers behind DistributedGraphBuild."""
+
+    def __init__(self, engine, device):
+        import torch
+        self.torch = torch
+        self.engine = engine
+        self.device = device
+        self._bufs = {}
+
+    def _buf(self, name, n, dtype):
+        t = self._bufs.get(name)
+        if t is None or t.numel() < n or t.dtype != dtype:
+            t = self.torch.empty(max(int(n * 1.1) + 1024, 1024), dtype=dtype, device=self.device)
+            self._bufs[name] = t
+        return t
+
+    def tail_last_call(self, params, rec):
+        """(has, obs1, obs2) of the last CreateEdge call in the slice."""
+        n = int(rec.n)
+        count = 1 << 16
+        p = _copy_params(params, (NO_MATCH, NO_MATCH))
+        while True:
+            self.engine.links_extract(p, records_tail(rec, count))
+            c = self.engine.links_counters()
+            if c[abi.CNT_CALLS] > 0:
+                return 1, int(c[abi.CNT_LAST_OBS1]), int(c[abi.CNT_LAST_OBS2])
+            if count >= n:
+                return 0, 0, 0
+            count *= 16
+
+    def extract(self, params, rec):
+        return self.engine.links_extract(params, rec)
+
+    def partition(self, world):
+        torch = self.torch
+        (_, n), (_, nf) = self.engine.links_device()
+        send_t = self._buf("send_t", 4 * n, torch.int32)
+        send_o = self._buf("send_o", n, torch.int32)
+        send_f = self._buf("send_f", nf, torch.int64)
+        tc, fc = self.engine.links_partition(world, send_t.data_ptr(), send_f.data_ptr(), send_o.data_ptr())
+        return send_t[:4 * n].view(-1, 4), send_o[:n], send_f[:nf], tc, fc
+
+    def recv_buffers(self, n_tuples, n_fishy):
+        torch = self.torch
+        return (self._buf("recv_t", 4 * n_tuples, torch.int32)[:4 * n_tuples].view(-1, 4),
+                self._buf("recv_o", n_tuples, torch.int32)[:n_tuples],
+                self._buf("recv_f", n_fishy, torch.int64)[:n_fishy])
+
+    def to_graph(self, params, recv_t, recv_f):
+        return self.engine.links_to_graph(params, recv_t.data_ptr() if recv_t.numel() else None, recv_t.shape[0],
+                                          recv_f.data_ptr() if recv_f.numel() else None, recv_f.shape[0])
+
+    def partial_tensors(self):
+        """(aligned_len[C], counters[16]) as in-place reducible device tensors."""
+        a_ptr, c_ptr = self.engine.links_partials_device()
+        return (_wrap_device_i64(self.torch, a_ptr, self.engine._n_contigs, self.device),
+                _wrap_device_i64(self.torch, c_ptr, abi.N_COUNTERS, self.device))
+
+    def counts_tensor(self, values):
+        return self.torch.tensor(values, dtype=self.torch.int64, device=self.device)
+
+    def fetch(self, sizes):
+        return self.engine.fetch(sizes)
+
+
+class _CudaArray(object):
+    def __init__(self, ptr, n):
+        self.__cuda_array_interface__ = {"shape": (int(n),), "typestr": "<i8", "data": (int(ptr), False), "version": 3,
+                                         "strides": None}
+
+
+def _wrap_device_i64(torch, ptr, n, device):
+    if n == 0 or not ptr:
+        return torch.zeros(0, dtype=torch.int64, device=device)
+    return torch.as_tensor(_CudaArray(ptr, n), device=device)
+
+
+class DistributedGraphBuild(object):
+    def __init__(self, backend, rank, world, group=None):
+        import torch.distributed as dist
+        self.dist = dist
+        self.b = backend
+        self.rank, self.world, self.group = rank, world, group
+        self.last = None
+
+    # -- step 1: the last CreateEdge call of all preceding ranks --------------------------------
+    def halo(self, params, rec):
+        has, o1, o2 = self.b.tail_last_call(params, rec)
+        mine = self.b.counts_tensor([has, o1, o2])
+        gathered = [self.b.counts_tensor([0, 0, 0]) for _ in range(self.world)]
+        self.dist.all_gather(gathered, mine, group=self.group)
+        halo = (params.halo_prev_obs1, params.halo_prev_obs2)
+        for r in range(self.rank):
+            h, a, b = (int(x) for x in gathered[r].tolist())
+            if h:
+                halo = (a, b)
+        return halo
+
+    def step(self, params, rec):
+        """One distributed graph build.  Leaves this rank's share of the CSR in its HBM;
+        returns the local sizes.  `self.last` keeps what fetch_local needs."""
+        dist, world = self.dist, self.world
+        halo = self.halo(params, rec) if world > 1 else (params.halo_prev_obs1, params.halo_prev_obs2)
+        p = _copy_params(params, halo)
+        n_local = self.b.extract(p, rec)
+        send_t, send_o, send_f, tc, fc = self.b.partition(world)
+        # bucket sizes: one small all_to_all, then the payload all_to_all
+        counts_out = self.b.counts_tensor(np.stack([tc, fc], axis=1).reshape(-1).tolist())
+        counts_in = self.b.counts_tensor([0] * (2 * world))
+        dist.all_to_all_single(counts_in, counts_out, group=self.group)
+        ci = np.asarray(counts_in.tolist(), dtype=np.int64).reshape(world, 2)
+        rt, rf = ci[:, 0], ci[:, 1]
+        recv_t, recv_o, recv_f = self.b.recv_buffers(int(rt.sum()), int(rf.sum()))
+        dist.all_to_all_single(recv_t, send_t, output_split_sizes=rt.tolist(), input_split_sizes=tc.tolist(), group=self.group)
+        dist.all_to_all_single(recv_o, send_o, output_split_sizes=rt.tolist(), input_split_sizes=tc.tolist(), group=self.group)
+        dist.all_to_all_single(recv_f, send_f, output_split_sizes=rf.tolist(), input_split_sizes=fc.tolist(), group=self.group)
+        sizes = self.b.to_graph(p, recv_t, recv_f)
+        # exact, order-free partial sums: coverage + counters; the halo slots
+        # (last call) are taken from the last rank that made one
+        aligned, counters = self.b.partial_tensors()
+        n_all = [self.b.counts_tensor([0]) for _ in range(world)]
+        dist.all_gather(n_all, self.b.counts_tensor([n_local]), group=self.group)
+        last = counters[abi.CNT_LAST_OBS1:abi.CNT_LAST_OBS2 + 1].clone()
+        counters[abi.CNT_LAST_OBS1:] = 0
+        dist.all_reduce(aligned, op=dist.ReduceOp.SUM, group=self.group)
+        dist.all_reduce(counters, op=dist.ReduceOp.SUM, group=self.group)
+        lasts = [last.clone() for _ in range(world)]
+        dist.all_gather(lasts, last, group=self.group)
+        self.last = dict(sizes=sizes, recv_o=recv_o, recv_splits=rt, n_tuples_by_rank=[int(t.item()) for t in n_all],
+                         aligned=aligned, counters=counters, last_call=[tuple(int(x) for x in t.tolist()) for t in lasts],
+                         halo=halo)
+        return sizes
+
+    # -- results ------------------------------------------------------------------------------------
+    def fetch_local(self):
+        """This rank's edges (GraphResult) with first_idx rewritten to the GLOBAL ordinal of the
+        edge's first link (source-rank prefix + ordinal in the source's stream), and the reduced
+        aligned_len / counters."""
+        L = self.last
+        res = self.b.fetch(L["sizes"])
+        if res.n_edges:
+            starts = np.concatenate([[0], np.cumsum(L["recv_splits"])])
+            src = np.searchsorted(starts, res.first_idx, side="right") - 1
+            prefix = np.concatenate([[0], np.cumsum(L["n_tuples_by_rank"])])
+            ordinals = np.asarray(L["recv_o"].cpu().numpy()).view(np.uint32).astype(np.int64)
+            res.first_idx = prefix[src] + ordinals[res.first_idx]
+        res.aligned_len = np.asarray(L["aligned"].cpu().numpy(), dtype=np.int64)
+        counters = np.asarray(L["counters"].cpu().numpy(), dtype=np.int64).copy()
+        # the globally last CreateEdge call: every rank starts from its halo, so rank world-1's
+        # pair already folds in all earlier ranks
+        last = L["last_call"][self.world - 1]
+        counters[abi.CNT_LAST_OBS1], counters[abi.CNT_LAST_OBS2] = last
+        res.counters = counters
+        return res
+
+    def fetch_global(self):
+        """All ranks' edges merged into one GraphResult (every rank gets it).  Host-side, outside
+        the timed path: feeds the order-dependent post-filters of CreateGraph.PE."""
+        local = self.fetch_local()
+        parts = [None] * self.world
+        self.dist.all_gather_object(parts, local, group=self.group)
+        return merge_graph_results(parts)
+
+
+def merge_graph_results(parts):
+    """Disjoint edge sets (each sorted by (edge_u, edge_v)) -> one CSR sorted the same way."""
+    parts = [p for p in parts if p is not None]
+    first = parts[0]
+    key = np.concatenate([(p.edge_u.astype(np.int64) << 32) | p.edge_v for p in parts])
+    order = np.argsort(key, kind="stable")
+    nr = np.concatenate([p.nr_links for p in parts])[order]
+    row_ptr = np.concatenate([[0], np.cumsum(nr, dtype=np.int64)])
+    # payload: gather each edge's segment
+    seg_start = np.concatenate([p.row_ptr[:-1] + off for p, off in zip(parts, np.cumsum([0] + [p.n_links for p in parts[:-1]]))])[order]
+    obs_u_all = np.concatenate([p.obs_u for p in parts])
+    obs_v_all = np.concatenate([p.obs_v for p in parts])
+    idx = np.repeat(seg_start - row_ptr[:-1], nr) + np.arange(int(row_ptr[-1]), dtype=np.int64)
+    fields = {}
+    for f in ("edge_u", "edge_v", "nr_links", "obs_sum", "obs_sq", "first_idx", "gap", "score", "ks", "sd_obs", "sd_model",
+              "fishy", "flags"):
+        fields[f] = np.concatenate([getattr(p, f) for p in parts])[order]
+    return abi.GraphResult(row_ptr=row_ptr, obs_u=obs_u_all[idx], obs_v=obs_v_all[idx], aligned_len=first.aligned_len,
+                           counters=first.counters, **fields)

@@ -109,14 +109,19 @@ class CudaEngine(object):
         self._check(self._L.besst_links_fetch(self._ctx, None, out.ctypes.data), "besst_links_fetch")
         return out
 
-    def links_partition(self, world, out_tuples_ptr, out_fishy_ptr):
+    def links_partition(self, world, out_tuples_ptr, out_fishy_ptr, out_ordinals_ptr=None):
         """Stable bucketing of the extracted tuples / fishy keys by destination rank into
         caller-provided device buffers.  -> (tuple_counts[world], fishy_counts[world])"""
         tc = np.zeros(world, dtype=np.int64)
         fc = np.zeros(world, dtype=np.int64)
-        self._check(self._L.besst_links_partition(self._ctx, int(world), out_tuples_ptr, out_fishy_ptr, tc.ctypes.data,
-                                                  fc.ctypes.data), "besst_links_partition")
+        self._check(self._L.besst_links_partition(self._ctx, int(world), out_tuples_ptr, out_ordinals_ptr, out_fishy_ptr,
+                                                  tc.ctypes.data, fc.ctypes.data), "besst_links_partition")
         return tc, fc
+
+    def links_counters(self):
+        counters = np.zeros(abi.N_COUNTERS, dtype=np.int64)
+        self._check(self._L.besst_links_partials(self._ctx, None, counters.ctypes.data), "besst_links_partials")
+        return counters
 
     def set_stream(self, cuda_stream_ptr):
         """Run the engine on a caller-owned CUDA stream (e.g. torch.cuda.current_stream().cuda_stream); 0/None restores its own."""

@@ -223,10 +223,13 @@ int besst_links_partials_device(besst_ctx* ctx, int64_t** aligned_len_device, in
 int besst_links_fetch(besst_ctx* ctx, besst_link_tuple* tuples_host, uint64_t* fishy_keys_host);
 /* stable partition of the extracted tuples and fishy keys into `world` destination buckets
  * (bucket d = hash(u,v) mod world, BAM order kept inside a bucket), written to caller-provided
- * DEVICE buffers of n_tuples / n_fishy_keys elements; *_counts[world] (host) receive the bucket
- * sizes.  world <= 16. */
+ * DEVICE buffers of n_tuples / n_fishy_keys elements; out_ordinals_device (optional, n_tuples
+ * uint32) receives each bucketed tuple's ordinal in this rank's BAM-ordered stream, from which the
+ * receiver rebuilds the global first-appearance order of its edges; *_counts[world] (host) receive
+ * the bucket sizes.  world <= 16. */
 int besst_links_partition(besst_ctx* ctx, int32_t world, besst_link_tuple* out_tuples_device,
-                          uint64_t* out_fishy_device, int64_t* tuple_counts, int64_t* fishy_counts);
+                          uint32_t* out_ordinals_device, uint64_t* out_fishy_device, int64_t* tuple_counts,
+                          int64_t* fishy_counts);
 int besst_links_to_graph(besst_ctx* ctx, const besst_lib_params* params,
                          const besst_link_tuple* tuples_device, int64_t n_tuples,
                          const uint64_t* fishy_keys_device, int64_t n_fishy_keys,
@@ -249,7 +252,7 @@ int besst_trsk_sd_batch(besst_ctx* ctx, const besst_lib_params* params, const do
                         const int32_t* len2, int64_t n, double* sd_out);
 
 /* run all work of this ctx on a caller-owned CUDA stream (a cudaStream_t passed as void*; NULL
- * restores the ctx's own stream).  Lets a host framework order the library's kernels with its own
+ * restores the ctx's own non-blocking stream; pass cudaStreamLegacy (0x1) for the legacy default stream).  Lets a host framework order the library's kernels with its own
  * work (NCCL collectives, CUDA-event timing) without device-wide synchronisation. */
 int besst_set_stream(besst_ctx* ctx, void* cuda_stream);
 

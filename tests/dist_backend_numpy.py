@@ -1,0 +1,96 @@
+"""TEST INFRASTRUCTURE: a CPU stand-in for besst_b200.dist.CudaBackend so that the host logic of
+DistributedGraphBuild (halo, bucket exchange, ordinals, reductions, merge) runs under gloo with
+world_size > 1 on a machine without GPUs.  Extraction is the C oracle; bucketing and the
+tuples -> CSR step are plain numpy (integers only: scores are covered by the GPU tests)."""
+import numpy as np
+import torch
+
+import oracle_lib
+from besst_b200 import abi
+from besst_b200.dist import NO_MATCH, _copy_params
+
+
+def edge_dest_numpy(u, v, world):
+    with np.errstate(over="ignore"):
+        x = (u.astype(np.uint64) << np.uint64(32)) | v.astype(np.uint64)
+        x ^= x >> np.uint64(33)
+        x *= np.uint64(0xff51afd7ed558ccd)
+        x ^= x >> np.uint64(33)
+        x *= np.uint64(0xc4ceb9fe1a85ec53)
+        x ^= x >> np.uint64(33)
+    return (x % np.uint64(world)).astype(np.int64)
+
+
+class NumpyBackend(object):
+    def __init__(self, table):
+        self.table = table
+
+    def _run(self, params, batch):
+        res, tuples, fishy, _ = oracle_lib.graph_build(self.table.rows, self.table.n_scaffolds, params, batch)
+        self.tuples = tuples
+        self.fishy = np.repeat(np.array(list(fishy.keys()), dtype=np.uint64), list(fishy.values())) if fishy else np.zeros(0, np.uint64)
+        self.aligned = torch.from_numpy(res.aligned_len.copy())
+        self.counters = torch.from_numpy(res.counters.copy())
+        return res
+
+    def tail_last_call(self, params, batch):
+        res = self._run(_copy_params(params, (NO_MATCH, NO_MATCH)), batch)
+        c = res.counters
+        return (1, int(c[abi.CNT_LAST_OBS1]), int(c[abi.CNT_LAST_OBS2])) if c[abi.CNT_CALLS] > 0 else (0, 0, 0)
+
+    def extract(self, params, batch):
+        self._run(params, batch)
+        return int(self.tuples.shape[0])
+
+    def partition(self, world):
+        dest = edge_dest_numpy(self.tuples["u"], self.tuples["v"], world)
+        order = np.argsort(dest, kind="stable")
+        t = self.tuples[order]
+        send_t = torch.from_numpy(np.ascontiguousarray(t).view(np.int32).reshape(-1, 4).copy())
+        send_o = torch.from_numpy(order.astype(np.int32))
+        fd = edge_dest_numpy((self.fishy >> np.uint64(32)).astype(np.uint32), (self.fishy & np.uint64(0xffffffff)).astype(np.uint32), world)
+        forder = np.argsort(fd, kind="stable")
+        send_f = torch.from_numpy(self.fishy[forder].view(np.int64).copy())
+        return send_t, send_o, send_f, np.bincount(dest, minlength=world).astype(np.int64), np.bincount(fd, minlength=world).astype(np.int64)
+
+    def recv_buffers(self, n_tuples, n_fishy):
+        return (torch.zeros((n_tuples, 4), dtype=torch.int32), torch.zeros(n_tuples, dtype=torch.int32),
+                torch.zeros(n_fishy, dtype=torch.int64))
+
+    def to_graph(self, params, recv_t, recv_f):
+        """tuples -> CSR (integers only), the numpy statement of CreateEdge's upsert (CreateGraph.py:842-862)."""
+        t = recv_t.numpy().view(abi.LINK_TUPLE_DTYPE).reshape(-1)
+        key = (t["u"].astype(np.int64) << 32) | t["v"]
+        order = np.argsort(key, kind="stable")
+        ks = key[order]
+        heads = np.nonzero(np.concatenate([[True], ks[1:] != ks[:-1]]))[0] if len(ks) else np.zeros(0, np.int64)
+        row_ptr = np.concatenate([heads, [len(ks)]]).astype(np.int64)
+        E = len(heads)
+        ou, ov = t["obs_u"][order], t["obs_v"][order]
+        tot = ou.astype(np.int64) + ov
+        fk = recv_f.numpy().view(np.uint64)
+        fkey = ((fk >> np.uint64(32)).astype(np.int64) << 32) | (fk & np.uint64(0xffffffff)).astype(np.int64)
+        ukeys = ks[heads] if E else np.zeros(0, np.int64)
+        fs = np.sort(fkey)
+        n_large2 = 2 * self.table.n_large_scaffolds
+        eu, ev = (ukeys >> 32).astype(np.uint32), (ukeys & 0xffffffff).astype(np.uint32)
+        self.result = abi.GraphResult(
+            edge_u=eu, edge_v=ev, nr_links=np.diff(row_ptr).astype(np.int32),
+            obs_sum=np.add.reduceat(tot, heads) if E else np.zeros(0, np.int64),
+            obs_sq=np.add.reduceat(tot * tot, heads) if E else np.zeros(0, np.int64),
+            first_idx=order[heads].astype(np.int64) if E else np.zeros(0, np.int64), row_ptr=row_ptr,
+            gap=np.zeros(E, np.int32), score=np.full(E, np.nan), ks=np.full(E, np.nan), sd_obs=np.full(E, np.nan),
+            sd_model=np.full(E, np.nan),
+            fishy=(np.searchsorted(fs, ukeys, side="right") - np.searchsorted(fs, ukeys, side="left")).astype(np.int32),
+            flags=((eu < n_large2) & (ev < n_large2)).astype(np.uint8) * abi.EDGE_LL,
+            obs_u=ou, obs_v=ov, aligned_len=np.zeros(0, np.int64), counters=np.zeros(abi.N_COUNTERS, np.int64))
+        return "sizes"
+
+    def partial_tensors(self):
+        return self.aligned, self.counters
+
+    def counts_tensor(self, values):
+        return torch.tensor(values, dtype=torch.int64)
+
+    def fetch(self, sizes):
+        return self.result

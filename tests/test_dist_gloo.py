@@ -1,0 +1,71 @@
+"""world_size 2 and 3 on CPU (gloo): the host logic of the multi-GPU decomposition
+(besst_b200/dist.py) -- halo from preceding ranks, stable bucket exchange, global
+first-appearance ordinals, all-reduced coverage/counters, merge -- must reproduce the
+single-pass oracle bit for bit (integers)."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch.multiprocessing as mp
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _worker(rank, world, port, config, cuts, out_dir):
+    for p in (ROOT, os.path.join(ROOT, "oracle"), HERE):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    import torch.distributed as dist
+    import helpers
+    import oracle_lib
+    from besst_b200 import abi, synth
+    from besst_b200.dist import DistributedGraphBuild
+    from dist_backend_numpy import NumpyBackend
+    dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%d" % port, rank=rank, world_size=world)
+    try:
+        lib = synth.make_config(config)
+        batch = lib.to_batch()
+        params = abi.make_params(lib.orientation, 11, 100.0, lib.mu, lib.sigma, lib.mu + 6 * lib.sigma)
+        objs = helpers.later_library_objects(batch.references, batch.lengths, lib.mu + 4 * lib.sigma, seed=3)
+        table = helpers.table_for(batch, objs)
+        n = len(batch)
+        bounds = [0] + [int(n * c) for c in cuts] + [n]
+        runner = DistributedGraphBuild(NumpyBackend(table), rank, world)
+        runner.step(params, batch.slice(bounds[rank], bounds[rank + 1]))
+        merged = runner.fetch_global()
+        if rank == 0:
+            want, _, _, _ = oracle_lib.graph_build(table.rows, table.n_scaffolds, params, batch)
+            for f in ("edge_u", "edge_v", "nr_links", "obs_sum", "obs_sq", "row_ptr", "fishy", "obs_u", "obs_v", "aligned_len"):
+                assert np.array_equal(getattr(merged, f), getattr(want, f)), f
+            assert np.array_equal(merged.flags & abi.EDGE_LL, want.flags & abi.EDGE_LL)
+            assert np.array_equal(merged.counters[:10], want.counters[:10]), (merged.counters[:10], want.counters[:10])
+            # first-appearance order of the edges (networkx insertion order) is the global one
+            assert np.array_equal(np.argsort(merged.first_idx, kind="stable"), np.argsort(want.first_idx, kind="stable"))
+            assert np.array_equal(merged.first_idx, want.first_idx)
+            open(os.path.join(out_dir, "ok"), "w").write("ok")
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,config,cuts", [
+    (2, "small_mp", [0.5]),
+    (3, "small_pe", [0.2, 0.21]),       # a tiny middle slice
+    (3, "tiny", [0.0, 0.6]),            # an empty first slice: the halo must pass through
+])
+def test_distributed_build_equals_single_pass(tmp_path, world, config, cuts):
+    import oracle_lib
+    oracle_lib.build()   # before the workers race to do it
+    port = _free_port()
+    mp.spawn(_worker, args=(world, port, config, cuts, str(tmp_path)), nprocs=world, join=True)
+    assert os.path.exists(os.path.join(str(tmp_path), "ok"))

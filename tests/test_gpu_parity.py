@@ -276,13 +276,15 @@ def test_partition_by_edge_hash_is_stable(cuda_engine, world):
     fishy = cuda_engine.links_fishy_host()
     out_t = torch.zeros(max(n, 1) * 4, dtype=torch.int32, device="cuda")
     out_f = torch.zeros(max(len(fishy), 1), dtype=torch.int64, device="cuda")
-    tc, fc = cuda_engine.links_partition(world, out_t.data_ptr(), out_f.data_ptr())
+    out_o = torch.zeros(max(n, 1), dtype=torch.int32, device="cuda")
+    tc, fc = cuda_engine.links_partition(world, out_t.data_ptr(), out_f.data_ptr(), out_o.data_ptr())
     assert tc.sum() == n and fc.sum() == len(fishy)
     got = out_t.cpu().numpy().view(abi.LINK_TUPLE_DTYPE)[:n]
     dest = edge_dest_numpy(tuples["u"], tuples["v"], world)
     order = np.argsort(dest, kind="stable")
     assert np.array_equal(np.bincount(dest, minlength=world), tc)
     assert np.array_equal(got, tuples[order])
+    assert np.array_equal(out_o.cpu().numpy()[:n], order)
     got_f = out_f.cpu().numpy().view(np.uint64)[:len(fishy)]
     fdest = edge_dest_numpy((fishy >> np.uint64(32)).astype(np.uint32), (fishy & np.uint64(0xffffffff)).astype(np.uint32), world)
     assert np.array_equal(np.bincount(fdest, minlength=world), fc)
@@ -314,3 +316,19 @@ def test_scalar_dropins(cuda_engine):
         L.besst_oracle_gap_estimator(3000.0, 500.0, 100.0, 2500.0, 6000.0, 7000.0, abi.ERF_AS7126)
     sd = param_est.tr_sk_std_dev(3000.0, 500.0, 100.0, 6000, 7000, 420, engine=cuda_engine)
     assert sd == pytest.approx(L.besst_oracle_tr_sk_std_dev(3000.0, 500.0, 100.0, 6000.0, 7000.0, 420.0, abi.ERF_AS7126), rel=1e-6)
+
+
+def test_distributed_nccl_equals_oracle():
+    """Needs >= 2 GPUs on the box (gpurun --gpus 2): the real NCCL all-to-all path."""
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("one GPU on this box: the N>1 host logic is covered by tests/test_dist_gloo.py")
+    import os
+    here = os.path.dirname(os.path.abspath(__file__))
+    world = min(torch.cuda.device_count(), 4)
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world),
+                          "--master-addr", "127.0.0.1", "--master-port", "29517", os.path.join(here, "dist_check.py")],
+                         capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and "DIST_CHECK_OK" in out.stdout, out.stdout[-2000:] + out.stderr[-4000:]
