@@ -22,6 +22,8 @@
 
 int besst_radix_sort_tuples(besst_ctx* ctx, const besst_link_tuple* tuples, int bv, uint64_t* keys_a, uint64_t* keys_b,
                             uint32_t* val_a, uint32_t* val_b, int64_t n, int* result_in_b);
+int besst_radix_sort_tuples_packed(besst_ctx* ctx, const besst_link_tuple* tuples, int bv, int idx_bits, uint64_t* keys_a,
+                                   uint64_t* keys_b, int64_t n, int* result_in_b);
 int besst_radix_sort_keys32(besst_ctx* ctx, uint32_t* keys_a, uint32_t* keys_b, int64_t n, int key_bits, int* result_in_b);
 
 namespace {
@@ -34,14 +36,15 @@ constexpr int HB_ITEMS = 8;
 constexpr int HB_TILE = HB_THREADS * HB_ITEMS;
 
 // ---- segment heads ---------------------------------------------------------------
-__global__ void __launch_bounds__(HB_THREADS) k_head_count(const u64* __restrict__ keys, long long n, u32* block_sums) {
+// sorted words are (edge key << idx_bits) | index when the index travels packed in the key (idx_bits > 0)
+__global__ void __launch_bounds__(HB_THREADS) k_head_count(const u64* __restrict__ keys, long long n, int idx_bits, u32* block_sums) {
     __shared__ u32 s_w[HB_THREADS / 32];
     const long long base = (long long)blockIdx.x * HB_TILE;
     u32 c = 0;
 #pragma unroll
     for (int i = 0; i < HB_ITEMS; ++i) {
         const long long j = base + i * HB_THREADS + threadIdx.x;
-        if (j < n) c += (j == 0 || keys[j] != keys[j - 1]) ? 1u : 0u;
+        if (j < n) c += (j == 0 || (keys[j] >> idx_bits) != (keys[j - 1] >> idx_bits)) ? 1u : 0u;
     }
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) c += __shfl_xor_sync(0xffffffffu, c, off);
@@ -93,7 +96,7 @@ __global__ void __launch_bounds__(1024) k_scan_blocks(u32* block_sums, int n_blo
 }
 
 __global__ void __launch_bounds__(HB_THREADS)
-    k_head_write(const u64* __restrict__ keys, long long n, const u32* __restrict__ block_sums, long long* row_ptr) {
+    k_head_write(const u64* __restrict__ keys, long long n, int idx_bits, const u32* __restrict__ block_sums, long long* row_ptr) {
     __shared__ u32 s_w[HB_THREADS / 32];
     const long long base = (long long)blockIdx.x * HB_TILE;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -103,7 +106,7 @@ __global__ void __launch_bounds__(HB_THREADS)
 #pragma unroll
     for (int i = 0; i < HB_ITEMS; ++i) {
         const long long j = base + (long long)threadIdx.x * HB_ITEMS + i;
-        head[i] = j < n && (j == 0 || keys[j] != keys[j - 1]);
+        head[i] = j < n && (j == 0 || (keys[j] >> idx_bits) != (keys[j - 1] >> idx_bits));
         c += head[i] ? 1u : 0u;
     }
     u32 incl = c;
@@ -157,7 +160,7 @@ struct EdgeArrays {
 
 __global__ void __launch_bounds__(256)
     k_edge_reduce(EdgeArrays E, long long n_edges, const besst_link_tuple* __restrict__ tuples,
-                  const u32* __restrict__ sorted_idx, const u64* __restrict__ sorted_keys, int bv,
+                  const u32* __restrict__ sorted_idx, const u64* __restrict__ sorted_keys, int bv, int idx_bits,
                   const u64* __restrict__ fishy_sorted, long long n_fishy, u32 n_large2, int scoring) {
     const int lane = threadIdx.x & 31;
     const long long warp_global = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -167,7 +170,7 @@ __global__ void __launch_bounds__(256)
         long long s = 0, sq = 0, su = 0;
         int mv = -2147483647 - 1;
         for (long long j = b + lane; j < t; j += 32) {
-            const u32 idx = __ldg(sorted_idx + j);
+            const u32 idx = idx_bits ? (u32)(__ldg(sorted_keys + j) & ((1ull << idx_bits) - 1ull)) : __ldg(sorted_idx + j);
             const int4 tp = __ldg(reinterpret_cast<const int4*>(tuples + idx));
             E.obs_u[j] = tp.z;
             E.obs_v[j] = tp.w;
@@ -186,14 +189,15 @@ __global__ void __launch_bounds__(256)
             mv = o > mv ? o : mv;
         }
         if (lane == 0) {
-            const u64 key = sorted_keys[b];
+            const u64 word = sorted_keys[b];
+            const u64 key = word >> idx_bits;
             const u32 u = (u32)(key >> bv), v = (u32)(key & ((1ull << bv) - 1ull));
             E.u[e] = u;
             E.v[e] = v;
             E.nr[e] = (int)(t - b);
             E.obs[e] = s;
             E.obs_sq[e] = sq;
-            E.first[e] = (long long)sorted_idx[b];
+            E.first[e] = idx_bits ? (long long)(word & ((1ull << idx_bits) - 1ull)) : (long long)sorted_idx[b];
             long long f = 0;
             if (n_fishy > 0) {
                 const long long lo = lower_bound_u64(fishy_sorted, n_fishy, key);
@@ -595,14 +599,24 @@ int besst_launch_graph(besst_ctx* ctx, const besst_lib_params& p, const besst_li
     // ---- K3: radix bucket -------------------------------------------------------------
     BESST_CUDA_TRY(ctx, ctx->key_a.ensure(8 * nz));
     BESST_CUDA_TRY(ctx, ctx->key_b.ensure(8 * nz));
-    BESST_CUDA_TRY(ctx, ctx->idx_a.ensure(4 * nz));
-    BESST_CUDA_TRY(ctx, ctx->idx_b.ensure(4 * nz));
+    // the BAM-order index rides in the low bits of the sort word when it fits: 8 B per link per pass
+    int idx_bits = bits_for((uint64_t)(n > 1 ? n - 1 : 1));
+    if (2 * bv + idx_bits > 64) idx_bits = 0;
     int in_b = 0;
-    int rc = besst_radix_sort_tuples(ctx, d_tuples, bv, ctx->key_a.as<uint64_t>(), ctx->key_b.as<uint64_t>(),
+    int rc;
+    const u32* idx = nullptr;
+    if (idx_bits) {
+        rc = besst_radix_sort_tuples_packed(ctx, d_tuples, bv, idx_bits, ctx->key_a.as<uint64_t>(), ctx->key_b.as<uint64_t>(), n, &in_b);
+        if (rc) return rc;
+    } else {
+        BESST_CUDA_TRY(ctx, ctx->idx_a.ensure(4 * nz));
+        BESST_CUDA_TRY(ctx, ctx->idx_b.ensure(4 * nz));
+        rc = besst_radix_sort_tuples(ctx, d_tuples, bv, ctx->key_a.as<uint64_t>(), ctx->key_b.as<uint64_t>(),
                                      ctx->idx_a.as<uint32_t>(), ctx->idx_b.as<uint32_t>(), n, &in_b);
-    if (rc) return rc;
+        if (rc) return rc;
+        idx = in_b ? ctx->idx_b.as<u32>() : ctx->idx_a.as<u32>();
+    }
     const u64* keys = in_b ? ctx->key_b.as<u64>() : ctx->key_a.as<u64>();
-    const u32* idx = in_b ? ctx->idx_b.as<u32>() : ctx->idx_a.as<u32>();
     besst_mark(ctx);
 
     // fishy pairs: rekey, sort (keys only)
@@ -622,7 +636,7 @@ int besst_launch_graph(besst_ctx* ctx, const besst_lib_params& p, const besst_li
     BESST_CUDA_TRY(ctx, ctx->block_sums.ensure(4 * (size_t)(n_blocks + 2)));
     u32 n_edges32 = 0;
     if (n > 0) {
-        { KTimer kt(ctx, BESST_K_HEADS); k_head_count<<<n_blocks, HB_THREADS, 0, ctx->stream>>>(keys, n, ctx->block_sums.as<u32>()); }
+        { KTimer kt(ctx, BESST_K_HEADS); k_head_count<<<n_blocks, HB_THREADS, 0, ctx->stream>>>(keys, n, idx_bits, ctx->block_sums.as<u32>()); }
         { KTimer kt(ctx, BESST_K_HEADS); k_scan_blocks<<<1, 1024, 0, ctx->stream>>>(ctx->block_sums.as<u32>(), n_blocks); }
         BESST_CUDA_TRY(ctx, cudaMemcpyAsync(&n_edges32, ctx->block_sums.as<u32>() + n_blocks, 4, cudaMemcpyDeviceToHost, ctx->stream));
         BESST_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
@@ -655,7 +669,7 @@ int besst_launch_graph(besst_ctx* ctx, const besst_lib_params& p, const besst_li
         ctx->have_graph = true;
         return BESST_OK;
     }
-    { KTimer kt(ctx, BESST_K_HEADS); k_head_write<<<n_blocks, HB_THREADS, 0, ctx->stream>>>(keys, n, ctx->block_sums.as<u32>(), EA.row_ptr); }
+    { KTimer kt(ctx, BESST_K_HEADS); k_head_write<<<n_blocks, HB_THREADS, 0, ctx->stream>>>(keys, n, idx_bits, ctx->block_sums.as<u32>(), EA.row_ptr); }
     besst_mark(ctx);
 
     {
@@ -664,7 +678,7 @@ int besst_launch_graph(besst_ctx* ctx, const besst_lib_params& p, const besst_li
         const int max_grid = ctx->sm_count * 32;
         if (grid > max_grid) grid = max_grid;
         KTimer kt(ctx, BESST_K_EDGE_REDUCE);
-        k_edge_reduce<<<grid, 256, 0, ctx->stream>>>(EA, E, d_tuples, idx, keys, bv, fishy_sorted, n_fishy,
+        k_edge_reduce<<<grid, 256, 0, ctx->stream>>>(EA, E, d_tuples, idx, keys, bv, idx_bits, fishy_sorted, n_fishy,
                                                      (u32)(2 * ctx->n_large), p.no_score ? 0 : 1);
         BESST_CUDA_TRY(ctx, cudaGetLastError());
     }

@@ -86,10 +86,10 @@ __global__ void __launch_bounds__(RS_RADIX) k_radix_scan_hist(u32* ghist) {
     h[threadIdx.x] = s[threadIdx.x] - v;
 }
 
-template <typename KeyT>
+template <typename KeyT, bool HAS_VAL>
 struct SweepSmem {
     KeyT keys[RS_TILE];
-    u32 vals[RS_TILE];
+    u32 vals[HAS_VAL ? RS_TILE : 1];
     u32 warp_hist[RS_WARPS][RS_RADIX];
     u32 digit_start[RS_RADIX];
     long long gbase[RS_RADIX];
@@ -97,14 +97,17 @@ struct SweepSmem {
     int tile;
 };
 
+// FROM_TUPLES: the first pass reads (u, v) straight from the link tuples.  With idx_bits > 0 the
+// BAM-order index is packed into the low bits of the key, (((u << bv) | v) << idx_bits) | index, and
+// there is no separate payload array: one 8-byte word per link per pass instead of 12.
 template <typename KeyT, bool FROM_TUPLES, bool HAS_VAL>
-__global__ void __launch_bounds__(RS_THREADS)
+__global__ void __launch_bounds__(RS_THREADS, 3)
     k_radix_sweep(const KeyT* __restrict__ in_keys, const u32* __restrict__ in_vals,
-                  const besst_link_tuple* __restrict__ tuples, int bv, KeyT* __restrict__ out_keys,
+                  const besst_link_tuple* __restrict__ tuples, int bv, int idx_bits, KeyT* __restrict__ out_keys,
                   u32* __restrict__ out_vals, long long n, int shift, const u32* __restrict__ gbase,
                   u32* status, u32* ticket, int n_tiles) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    SweepSmem<KeyT>& S = *reinterpret_cast<SweepSmem<KeyT>*>(smem_raw);
+    SweepSmem<KeyT, HAS_VAL>& S = *reinterpret_cast<SweepSmem<KeyT, HAS_VAL>*>(smem_raw);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned lt_mask = (1u << lane) - 1u;
 
@@ -120,18 +123,19 @@ __global__ void __launch_bounds__(RS_THREADS)
         const int tile_count = rem < RS_TILE ? (int)rem : RS_TILE;
 
         KeyT key[RS_ITEMS];
-        u32 val[RS_ITEMS];
+        u32 val[HAS_VAL ? RS_ITEMS : 1];
         unsigned short rank[RS_ITEMS];
 #pragma unroll
         for (int i = 0; i < RS_ITEMS; ++i) {
             const int off = warp * (32 * RS_ITEMS) + i * 32 + lane;
             key[i] = (KeyT)~0ull;
-            val[i] = 0;
+            if (HAS_VAL) val[i] = 0;
             if (off < tile_count) {
                 if (FROM_TUPLES) {
                     const uint2 uv = __ldg(reinterpret_cast<const uint2*>(tuples + tile_base + off));
-                    key[i] = (KeyT)(((u64)uv.x << bv) | uv.y);
-                    val[i] = (u32)(tile_base + off);
+                    const u64 k = ((u64)uv.x << bv) | uv.y;
+                    if (HAS_VAL) { key[i] = (KeyT)k; val[i] = (u32)(tile_base + off); }
+                    else key[i] = (KeyT)((k << idx_bits) | (u64)(tile_base + off));
                 } else {
                     key[i] = __ldg(in_keys + tile_base + off);
                     if (HAS_VAL) val[i] = __ldg(in_vals + tile_base + off);
@@ -159,8 +163,10 @@ __global__ void __launch_bounds__(RS_THREADS)
             __syncwarp();
         }
         __syncthreads();
-        // digit totals of the tile and per-warp offsets (thread d owns digit d)
-        u32 tile_hist;
+        // digit totals of the tile and per-warp offsets (thread d owns digit d); publish the tile's
+        // digit counts as early as possible
+        u32 tile_hist, dstart;
+        u32* st = status + (size_t)tile * RS_RADIX + threadIdx.x;
         {
             const int d = threadIdx.x;
             u32 run = 0;
@@ -171,6 +177,7 @@ __global__ void __launch_bounds__(RS_THREADS)
                 run += t;
             }
             tile_hist = run;
+            st_vol32(st, (tile == 0 ? RS_INC : RS_AGG) | tile_hist);
             // exclusive scan over digits
             u32 incl = run;
 #pragma unroll
@@ -184,25 +191,11 @@ __global__ void __launch_bounds__(RS_THREADS)
 #pragma unroll
             for (int w = 0; w < RS_WARPS; ++w)
                 if (w < warp) wbase += S.warp_sum[w];
-            const u32 dstart = wbase + incl - run;
+            dstart = wbase + incl - run;
             S.digit_start[d] = dstart;
-            // decoupled look-back for this digit
-            u32* st = status + (size_t)tile * RS_RADIX + d;
-            st_vol32(st, (tile == 0 ? RS_INC : RS_AGG) | tile_hist);
-            u32 excl = 0;
-            int p = tile - 1;
-            while (p >= 0) {
-                const u32 w = ld_vol32(status + (size_t)p * RS_RADIX + d);
-                const u32 flag = w & ~RS_VAL;
-                if (flag == 0) continue;
-                excl += w & RS_VAL;
-                if (flag == RS_INC) break;
-                --p;
-            }
-            if (tile > 0) st_vol32(st, RS_INC | (excl + tile_hist));
-            S.gbase[d] = (long long)gbase[d] + (long long)excl - (long long)dstart;
         }
         __syncthreads();
+        // local reorder through shared memory (gives the predecessors time to publish)
 #pragma unroll
         for (int i = 0; i < RS_ITEMS; ++i) {
             const int off = warp * (32 * RS_ITEMS) + i * 32 + lane;
@@ -212,6 +205,32 @@ __global__ void __launch_bounds__(RS_THREADS)
                 S.keys[lp] = key[i];
                 if (HAS_VAL) S.vals[lp] = val[i];
             }
+        }
+        // decoupled look-back for digit d = threadIdx.x, four predecessors per round trip
+        {
+            const int d = threadIdx.x;
+            u32 excl = 0;
+            int p = tile - 1;
+            while (p >= 0) {
+                u32 w[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) w[k] = (p - k >= 0) ? ld_vol32(status + (size_t)(p - k) * RS_RADIX + d) : RS_INC;
+                int used = 0;
+                bool done = false;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    if (done || used != k) continue;
+                    const u32 flag = w[k] & ~RS_VAL;
+                    if (flag == 0) continue;          // not published yet: re-poll from here
+                    excl += w[k] & RS_VAL;
+                    used = k + 1;
+                    if (flag == RS_INC) done = true;
+                }
+                if (done) break;
+                p -= used;
+            }
+            if (tile > 0) st_vol32(st, RS_INC | (excl + tile_hist));
+            S.gbase[d] = (long long)gbase[d] + (long long)excl - (long long)dstart;
         }
         __syncthreads();
         for (int j = threadIdx.x; j < tile_count; j += RS_THREADS) {
@@ -225,7 +244,7 @@ __global__ void __launch_bounds__(RS_THREADS)
 }
 
 template <typename KeyT, bool FROM_TUPLES, bool HAS_VAL>
-int sort_impl(besst_ctx* ctx, const besst_link_tuple* tuples, int bv, KeyT* keys_a, KeyT* keys_b, u32* val_a,
+int sort_impl(besst_ctx* ctx, const besst_link_tuple* tuples, int bv, int idx_bits, KeyT* keys_a, KeyT* keys_b, u32* val_a,
               u32* val_b, int64_t n, int key_bits, int* result_in_b) {
     *result_in_b = 0;
     int passes = (key_bits + 7) / 8;
@@ -246,10 +265,10 @@ int sort_impl(besst_ctx* ctx, const besst_link_tuple* tuples, int bv, KeyT* keys
     { KTimer kt(ctx, BESST_K_RADIX_SCAN); k_radix_scan_hist<<<passes, RS_RADIX, 0, ctx->stream>>>(ghist); }
     BESST_CUDA_TRY(ctx, cudaGetLastError());
 
-    const size_t smem = sizeof(SweepSmem<KeyT>);
+    const size_t smem = sizeof(SweepSmem<KeyT, HAS_VAL>);
     static bool attr_done = false;
     if (!attr_done) {
-        if (FROM_TUPLES) cudaFuncSetAttribute(k_radix_sweep<KeyT, FROM_TUPLES, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (FROM_TUPLES) cudaFuncSetAttribute(k_radix_sweep<KeyT, FROM_TUPLES, HAS_VAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         cudaFuncSetAttribute(k_radix_sweep<KeyT, false, HAS_VAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         attr_done = true;
     }
@@ -268,11 +287,11 @@ int sort_impl(besst_ctx* ctx, const besst_link_tuple* tuples, int bv, KeyT* keys
         {
         KTimer kt(ctx, ctx->sweep_kernel_id);
         if (p == 0 && FROM_TUPLES)
-            k_radix_sweep<KeyT, FROM_TUPLES, true><<<grid, RS_THREADS, smem, ctx->stream>>>(
-                nullptr, nullptr, tuples, bv, out_k, out_v, n, 0, ghist, ctx->sort_state.as<u32>(), tickets + p, n_tiles);
+            k_radix_sweep<KeyT, FROM_TUPLES, HAS_VAL><<<grid, RS_THREADS, smem, ctx->stream>>>(
+                nullptr, nullptr, tuples, bv, idx_bits, out_k, out_v, n, idx_bits, ghist, ctx->sort_state.as<u32>(), tickets + p, n_tiles);
         else
             k_radix_sweep<KeyT, false, HAS_VAL><<<grid, RS_THREADS, smem, ctx->stream>>>(
-                in_k, in_v, nullptr, bv, out_k, out_v, n, 8 * p, ghist + p * RS_RADIX, ctx->sort_state.as<u32>(),
+                in_k, in_v, nullptr, bv, idx_bits, out_k, out_v, n, idx_bits + 8 * p, ghist + p * RS_RADIX, ctx->sort_state.as<u32>(),
                 tickets + p, n_tiles);
         }
         BESST_CUDA_TRY(ctx, cudaGetLastError());
@@ -292,23 +311,31 @@ int sort_impl(besst_ctx* ctx, const besst_link_tuple* tuples, int bv, KeyT* keys
 
 int besst_radix_sort_pairs(besst_ctx* ctx, uint64_t* keys_a, uint64_t* keys_b, uint32_t* val_a, uint32_t* val_b,
                            int64_t n, int key_bits, int* result_in_b) {
-    return sort_impl<u64, false, true>(ctx, nullptr, 0, reinterpret_cast<u64*>(keys_a), reinterpret_cast<u64*>(keys_b), val_a,
+    return sort_impl<u64, false, true>(ctx, nullptr, 0, 0, reinterpret_cast<u64*>(keys_a), reinterpret_cast<u64*>(keys_b), val_a,
                                        val_b, n, key_bits, result_in_b);
 }
 
 int besst_radix_sort_keys(besst_ctx* ctx, uint64_t* keys_a, uint64_t* keys_b, int64_t n, int key_bits,
                           int* result_in_b) {
-    return sort_impl<u64, false, false>(ctx, nullptr, 0, reinterpret_cast<u64*>(keys_a), reinterpret_cast<u64*>(keys_b),
+    return sort_impl<u64, false, false>(ctx, nullptr, 0, 0, reinterpret_cast<u64*>(keys_a), reinterpret_cast<u64*>(keys_b),
                                         nullptr, nullptr, n, key_bits, result_in_b);
 }
 
 int besst_radix_sort_keys32(besst_ctx* ctx, uint32_t* keys_a, uint32_t* keys_b, int64_t n, int key_bits, int* result_in_b) {
-    return sort_impl<u32, false, false>(ctx, nullptr, 0, keys_a, keys_b, nullptr, nullptr, n, key_bits, result_in_b);
+    return sort_impl<u32, false, false>(ctx, nullptr, 0, 0, keys_a, keys_b, nullptr, nullptr, n, key_bits, result_in_b);
 }
 
 // tuples (BAM order) -> sorted (key, original index); key = (u << bv) | v
 int besst_radix_sort_tuples(besst_ctx* ctx, const besst_link_tuple* tuples, int bv, uint64_t* keys_a, uint64_t* keys_b,
                             uint32_t* val_a, uint32_t* val_b, int64_t n, int* result_in_b) {
-    return sort_impl<u64, true, true>(ctx, tuples, bv, reinterpret_cast<u64*>(keys_a), reinterpret_cast<u64*>(keys_b), val_a,
+    return sort_impl<u64, true, true>(ctx, tuples, bv, 0, reinterpret_cast<u64*>(keys_a), reinterpret_cast<u64*>(keys_b), val_a,
                                       val_b, n, 2 * bv, result_in_b);
+}
+
+// tuples (BAM order) -> sorted packed words (((u << bv) | v) << idx_bits) | original index; needs
+// 2 * bv + idx_bits <= 64 and n <= 2^idx_bits
+int besst_radix_sort_tuples_packed(besst_ctx* ctx, const besst_link_tuple* tuples, int bv, int idx_bits, uint64_t* keys_a,
+                                   uint64_t* keys_b, int64_t n, int* result_in_b) {
+    return sort_impl<u64, true, false>(ctx, tuples, bv, idx_bits, reinterpret_cast<u64*>(keys_a), reinterpret_cast<u64*>(keys_b),
+                                       nullptr, nullptr, n, 2 * bv, result_in_b);
 }
