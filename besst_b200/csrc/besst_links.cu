@@ -28,6 +28,8 @@
 //
 // Coverage uses __match_any_sync warp-aggregated 64-bit atomics; counters stay
 // in registers for the life of a warp and are flushed once.
+#include <math.h>
+
 #include "besst_internal.cuh"
 
 namespace {
@@ -69,7 +71,9 @@ struct K1Params {
     const int4* rows;   // packed contig rows
     int n_contigs;
     int orientation, min_mapq, detect_dup, extend, scoring;
-    double read_len, threshold;
+    double read_len;
+    int read_len_i;          // read_len when it is integral
+    long long threshold_i;   // ceil(ins_size_threshold): obs1 + obs2 < threshold  <=>  obs1 + obs2 < threshold_i
     besst_link_tuple* scratch;   // [n_tiles * WT]
     Agg* aggs;                   // [n_tiles]
     u64* fishy;
@@ -100,25 +104,28 @@ __device__ __forceinline__ Last warp_scan_last(Last v, int lane) {
     return v;
 }
 
-// PosDirCalculatorPE / PosDirCalculatorMP (CreateGraph.py:1024-1076) for one end
-__device__ __forceinline__ void pos_dir(int cdir, int read_fwd, int orientation, long long cpos, long long rpos,
-                                        long long slen, long long clen, double read_len, int& obs, int& side_r) {
-    int fwd = orientation == BESST_ORIENT_FR ? read_fwd : !read_fwd;
-    double o;
+// PosDirCalculatorPE / PosDirCalculatorMP (CreateGraph.py:1024-1076) for one end.  The reference
+// adds a possibly fractional read_len in fp64 and truncates with int(); when read_len is integral
+// (INT_RL) every intermediate is an exact integer and the fp64 round trip is skipped.
+template <bool INT_RL>
+__device__ __forceinline__ void pos_dir(int cdir, int read_fwd, int orientation, int cpos, int rpos, int slen, int clen,
+                                        double read_len, int read_len_i, int& obs, int& side_r) {
+    const int fwd = orientation == BESST_ORIENT_FR ? read_fwd : !read_fwd;
     if (cdir && fwd) {
-        o = (double)(slen - cpos - rpos);
+        obs = slen - cpos - rpos;
         side_r = 1;
     } else if (!cdir && fwd) {
-        o = (double)(cpos + (clen - rpos));
+        obs = cpos + (clen - rpos);
         side_r = 0;
     } else if (cdir && !fwd) {
-        o = __dadd_rn((double)(cpos + rpos), read_len);
+        if (INT_RL) obs = cpos + rpos + read_len_i;
+        else obs = __double2int_rz(__dadd_rn((double)(cpos + rpos), read_len));
         side_r = 0;
     } else {
-        o = __dsub_rn((double)(slen - cpos), __dsub_rn((double)(clen - rpos), read_len));
+        if (INT_RL) obs = (slen - cpos) - ((clen - rpos) - read_len_i);
+        else obs = __double2int_rz(__dsub_rn((double)(slen - cpos), __dsub_rn((double)(clen - rpos), read_len)));
         side_r = 1;
     }
-    obs = __double2int_rz(o);
 }
 
 // sides only (CheckDir, CreateGraph.py:678-688)
@@ -138,14 +145,23 @@ __device__ __forceinline__ void load_i32x4(const int32_t* p, long long idx, long
     }
 }
 
-__device__ __forceinline__ int row_state(const int4& r) { return r.x & 3; }
-__device__ __forceinline__ int row_dir(const int4& r) { return (r.x >> 2) & 1; }
-__device__ __forceinline__ int row_scaf(const int4& r) { return (int)((u32)r.x >> 3); }
+__device__ __forceinline__ int row_state(int x) { return x & 3; }
+__device__ __forceinline__ int row_dir(int x) { return (x >> 2) & 1; }
+__device__ __forceinline__ int row_scaf(int x) { return (int)((u32)x >> 3); }
 
-template <bool VEC>
+// candidates of one tile, compacted in BAM order (one slot per CreateEdge call)
+struct CandSmem {
+    int tid[WT], mtid[WT], pos[WT], mpos[WT];
+    u32 fm[WT];   // flag | mapq << 16 | large-large << 24
+};
+
+template <bool VEC, bool INT_RL>
 __global__ void __launch_bounds__(K1_THREADS) k_extract_links(const K1Params P) {
     __shared__ u64 s_cnt[8];
+    __shared__ CandSmem s_cand[K1_THREADS / 32];
     const int lane = threadIdx.x & 31;
+    const u32 lt_mask = (1u << lane) - 1u;
+    CandSmem& C = s_cand[threadIdx.x >> 5];
     int c_count = 0, c_nonuniq = 0, c_nonuniq_scaf = 0, c_dups = 0, c_toolong = 0, c_fishy = 0, c_calls = 0, c_valid = 0;
     if (threadIdx.x < 8) s_cnt[threadIdx.x] = 0;
     const long long n = P.rec.n;
@@ -177,16 +193,16 @@ __global__ void __launch_bounds__(K1_THREADS) k_extract_links(const K1Params P) 
             }
         }
 
-        // ---- per-record classification (CreateGraph.py:118-206) ---------------------------
+        // ---- per-record classification (CreateGraph.py:118-206); only word 0 of a row is needed ----
         u32 elig = 0, ll = 0, cov = 0;   // one bit per item
 #pragma unroll
         for (int i = 0; i < WT_ITEMS; ++i) {
             bool ok = tid[i] >= 0 && mtid[i] >= 0 && tid[i] < P.n_contigs && mtid[i] < P.n_contigs;       // :118-124
-            int4 r1 = make_int4(0, 0, 0, 0), r2 = r1;
+            int x1 = 0, x2 = 0;
             if (ok) {
-                r1 = __ldg(P.rows + tid[i]);
-                r2 = (mtid[i] == tid[i]) ? r1 : __ldg(P.rows + mtid[i]);
-                ok = row_state(r1) != BESST_CTG_ABSENT && row_state(r2) != BESST_CTG_ABSENT;              // :127-130
+                x1 = __ldg(reinterpret_cast<const int*>(P.rows + tid[i]));
+                x2 = (mtid[i] == tid[i]) ? x1 : __ldg(reinterpret_cast<const int*>(P.rows + mtid[i]));
+                ok = row_state(x1) != BESST_CTG_ABSENT && row_state(x2) != BESST_CTG_ABSENT;              // :127-130
             }
             if (!ok) continue;
             c_valid++;
@@ -194,52 +210,24 @@ __global__ void __launch_bounds__(K1_THREADS) k_extract_links(const K1Params P) 
             const bool unmapped = f & 0x4u, read1 = f & 0x40u, read2 = f & 0x80u;
             const int mq = (int)mapq[i];
             if ((mq >= P.min_mapq) || mq == 0) cov |= 1u << i;                                            // :138
-            const bool diff_scaf = row_scaf(r1) != row_scaf(r2);
+            if (tid[i] == mtid[i]) continue;   // same contig: same scaffold, no link, no fishy pair
+            const bool diff_scaf = row_scaf(x1) != row_scaf(x2);
             if (unmapped && read1 && diff_scaf) {                                                         // :141-163
-                const u32 n1 = 2u * (u32)row_scaf(r1) + (u32)side_only(row_dir(r1), !(f & 0x10u), P.orientation);
-                const u32 n2 = 2u * (u32)row_scaf(r2) + (u32)side_only(row_dir(r2), !(f & 0x20u), P.orientation);
+                const u32 n1 = 2u * (u32)row_scaf(x1) + (u32)side_only(row_dir(x1), !(f & 0x10u), P.orientation);
+                const u32 n2 = 2u * (u32)row_scaf(x2) + (u32)side_only(row_dir(x2), !(f & 0x20u), P.orientation);
                 const u64 key = n1 < n2 ? (((u64)n1 << 32) | n2) : (((u64)n2 << 32) | n1);
                 const u64 slot = atomicAdd(&P.globals[1], 1ull);
                 if ((long long)slot < P.fishy_cap) P.fishy[slot] = key;
                 c_fishy++;
             }
-            const bool inter = tid[i] != mtid[i];
-            if (inter && mq == 0) c_nonuniq++;                                                            // :166-167
-            if (inter && read2 && !unmapped && mq >= P.min_mapq) {                                        // :169
-                const bool l1 = row_state(r1) == BESST_CTG_LARGE, l2 = row_state(r2) == BESST_CTG_LARGE;
+            if (mq == 0) c_nonuniq++;                                                                     // :166-167
+            if (read2 && !unmapped && mq >= P.min_mapq) {                                                 // :169
+                const bool l1 = row_state(x1) == BESST_CTG_LARGE, l2 = row_state(x2) == BESST_CTG_LARGE;
                 if (l1 && l2) {
                     if (diff_scaf) { elig |= 1u << i; ll |= 1u << i; }                                    // :170
                 } else if (P.extend) {                                                                    // :184-206
                     if (!(l1 || l2) ? diff_scaf : true) elig |= 1u << i;
                 }
-            }
-        }
-
-        // ---- observations of the CreateEdge candidates (:816-833) --------------------------
-        int o1[WT_ITEMS], o2[WT_ITEMS];
-        u32 nu[WT_ITEMS], nv[WT_ITEMS];
-#pragma unroll
-        for (int i = 0; i < WT_ITEMS; ++i) { o1[i] = o2[i] = 0; nu[i] = nv[i] = 0; }
-        if (__any_sync(0xffffffffu, elig != 0)) {
-            int pos[WT_ITEMS], mpos[WT_ITEMS];
-            if (full) {
-                load_i32x4<true>(P.rec.pos, idx0, n, pos);
-                load_i32x4<true>(P.rec.mpos, idx0, n, mpos);
-            } else {
-                load_i32x4<false>(P.rec.pos, idx0, n, pos);
-                load_i32x4<false>(P.rec.mpos, idx0, n, mpos);
-            }
-#pragma unroll
-            for (int i = 0; i < WT_ITEMS; ++i) {
-                if (!(elig >> i & 1u)) continue;
-                const int4 r1 = __ldg(P.rows + tid[i]);    // L1 hits: gathered a moment ago
-                const int4 r2 = __ldg(P.rows + mtid[i]);
-                const u32 f = flag[i];
-                int s1, s2;
-                pos_dir(row_dir(r1), !(f & 0x10u), P.orientation, r1.y, pos[i], r1.w, r1.z, P.read_len, o1[i], s1);
-                pos_dir(row_dir(r2), !(f & 0x20u), P.orientation, r2.y, mpos[i], r2.w, r2.z, P.read_len, o2[i], s2);
-                nu[i] = 2u * (u32)row_scaf(r1) + (u32)s1;
-                nv[i] = 2u * (u32)row_scaf(r2) + (u32)s2;
             }
         }
 
@@ -265,78 +253,105 @@ __global__ void __launch_bounds__(K1_THREADS) k_extract_links(const K1Params P) 
             }
         }
 
-        // ---- previous CreateEdge call inside the tile: rightmost-non-empty scan ---------------
-        Last mine = {0, 0, 0};
-#pragma unroll
-        for (int i = 0; i < WT_ITEMS; ++i)
-            if (elig >> i & 1u) { mine.has = 1; mine.o1 = o1[i]; mine.o2 = o2[i]; }
-        const Last incl = warp_scan_last(mine, lane);
-        Last prev;
-        prev.has = __shfl_up_sync(0xffffffffu, incl.has, 1);
-        prev.o1 = __shfl_up_sync(0xffffffffu, incl.o1, 1);
-        prev.o2 = __shfl_up_sync(0xffffffffu, incl.o2, 1);
-        if (lane == 0) prev.has = 0;
-
-        // ---- CreateEdge: duplicate test, acceptance test, counters (:835-870) -------------------
-        // The tile's first call has no in-tile predecessor: assumed "not a duplicate" here and
-        // settled by the aggregate scan.
-        u32 acc = 0, first_flags = 0;
-        int first_o1 = 0, first_o2 = 0, n_acc = 0;
-#pragma unroll
-        for (int i = 0; i < WT_ITEMS; ++i) {
-            if (!(elig >> i & 1u)) continue;
-            c_calls++;
-            const bool mq0 = mapq[i] == 0;
-            if (mq0) c_nonuniq_scaf++;
-            const bool dup = prev.has && o1[i] == prev.o1 && o2[i] == prev.o2;
-            bool is_dupl = false;
-            if (dup) { c_dups++; is_dupl = P.detect_dup; }
-            const bool pass = (double)((long long)o1[i] + o2[i]) < P.threshold && o1[i] > 25 && o2[i] > 25;
-            const bool second = (ll >> i & 1u) && P.extend && P.scoring;
-            if (!prev.has) {   // only possible for the tile's first call
-                first_flags = AGG_HAS | (pass ? AGG_PASS : 0u) | (second ? AGG_SECOND : 0u) | (mq0 ? AGG_MQ0 : 0u);
-                first_o1 = o1[i]; first_o2 = o2[i];
-            }
-            prev.has = 1; prev.o1 = o1[i]; prev.o2 = o2[i];
-            if (!is_dupl) {
-                if (pass) { c_count++; acc |= 1u << i; n_acc++; } else c_toolong++;
-                if (second) {   // second call into G_prime (:180-183); prev_obs was reset to -1
-                    if (mq0) c_nonuniq_scaf++;
-                    const bool dup2 = (o1[i] == -1 && o2[i] == -1);
-                    if (dup2) c_dups++;
-                    if (!(dup2 && P.detect_dup)) { if (pass) c_count++; else c_toolong++; }
-                }
-            }
-        }
-
-        // ---- ordered compaction into the tile's scratch slot ------------------------------------
-        int incl_cnt = n_acc;
+        // ---- compact the CreateEdge candidates of the tile, BAM order, one per lane ------------
+        const int my_c = __popc(elig);
+        int incl_c = my_c;
 #pragma unroll
         for (int off = 1; off < 32; off <<= 1) {
-            const int t = __shfl_up_sync(0xffffffffu, incl_cnt, off);
-            if (lane >= off) incl_cnt += t;
+            const int t = __shfl_up_sync(0xffffffffu, incl_c, off);
+            if (lane >= off) incl_c += t;
         }
-        long long dst = wt * WT + (incl_cnt - n_acc);
-#pragma unroll
-        for (int i = 0; i < WT_ITEMS; ++i)
-            if (acc >> i & 1u) {
-                int4 t;
-                if (nu[i] < nv[i]) { t.x = (int)nu[i]; t.y = (int)nv[i]; t.z = o1[i]; t.w = o2[i]; }
-                else { t.x = (int)nv[i]; t.y = (int)nu[i]; t.z = o2[i]; t.w = o1[i]; }
-                reinterpret_cast<int4*>(P.scratch)[dst++] = t;
+        const int total_c = __shfl_sync(0xffffffffu, incl_c, 31);
+        int n_out = 0;
+        u32 first_flags = 0;
+        int first_o1 = 0, first_o2 = 0, carry_o1 = 0, carry_o2 = 0;
+        if (total_c > 0) {
+            int pos[WT_ITEMS], mpos[WT_ITEMS];
+            if (full) {
+                load_i32x4<true>(P.rec.pos, idx0, n, pos);
+                load_i32x4<true>(P.rec.mpos, idx0, n, mpos);
+            } else {
+                load_i32x4<false>(P.rec.pos, idx0, n, pos);
+                load_i32x4<false>(P.rec.mpos, idx0, n, mpos);
             }
+            int slot = incl_c - my_c;
+#pragma unroll
+            for (int i = 0; i < WT_ITEMS; ++i)
+                if (elig >> i & 1u) {
+                    C.tid[slot] = tid[i]; C.mtid[slot] = mtid[i]; C.pos[slot] = pos[i]; C.mpos[slot] = mpos[i];
+                    C.fm[slot] = flag[i] | (mapq[i] << 16) | ((ll >> i & 1u) << 24);
+                    ++slot;
+                }
+            __syncwarp();
 
-        // ---- aggregate ---------------------------------------------------------------------------
-        const u32 has_mask = __ballot_sync(0xffffffffu, first_flags != 0);
-        const int fl = has_mask ? __ffs(has_mask) - 1 : 0;
-        const u32 ff = __shfl_sync(0xffffffffu, first_flags, fl);
-        const int f1 = __shfl_sync(0xffffffffu, first_o1, fl), f2 = __shfl_sync(0xffffffffu, first_o2, fl);
-        const int l1v = __shfl_sync(0xffffffffu, incl.o1, 31), l2v = __shfl_sync(0xffffffffu, incl.o2, 31);
-        const int total = __shfl_sync(0xffffffffu, incl_cnt, 31);
+            // ---- CreateEdge, one call per lane: observations (:816-833), duplicate test against the
+            // previous call (:835-838), acceptance test (:840), counters.  The tile's first call has no
+            // in-tile predecessor: assumed "not a duplicate" here and settled by the aggregate scan.
+            bool have_carry = false;
+            for (int r = 0; r < total_c; r += 32) {
+                const int k = r + lane;
+                const bool active = k < total_c;
+                int o1 = 0, o2 = 0;
+                u32 nu = 0, nv = 0, fm = 0;
+                if (active) {
+                    const int t1 = C.tid[k], t2 = C.mtid[k];
+                    fm = C.fm[k];
+                    const int4 r1 = __ldg(P.rows + t1);   // L1 hits: word 0 was gathered a moment ago
+                    const int4 r2 = __ldg(P.rows + t2);
+                    int s1, s2;
+                    pos_dir<INT_RL>(row_dir(r1.x), !(fm & 0x10u), P.orientation, r1.y, C.pos[k], r1.w, r1.z, P.read_len, P.read_len_i, o1, s1);
+                    pos_dir<INT_RL>(row_dir(r2.x), !(fm & 0x20u), P.orientation, r2.y, C.mpos[k], r2.w, r2.z, P.read_len, P.read_len_i, o2, s2);
+                    nu = 2u * (u32)row_scaf(r1.x) + (u32)s1;
+                    nv = 2u * (u32)row_scaf(r2.x) + (u32)s2;
+                }
+                int p1 = __shfl_up_sync(0xffffffffu, o1, 1), p2 = __shfl_up_sync(0xffffffffu, o2, 1);
+                bool has_prev = true;
+                if (lane == 0) { p1 = carry_o1; p2 = carry_o2; has_prev = have_carry; }
+                bool accepted = false;
+                if (active) {
+                    c_calls++;
+                    const bool mq0 = ((fm >> 16) & 0xffu) == 0;
+                    if (mq0) c_nonuniq_scaf++;
+                    const bool dup = has_prev && o1 == p1 && o2 == p2;
+                    bool is_dupl = false;
+                    if (dup) { c_dups++; is_dupl = P.detect_dup; }
+                    const bool pass = ((long long)o1 + o2) < P.threshold_i && o1 > 25 && o2 > 25;
+                    const bool second = ((fm >> 24) & 1u) && P.extend && P.scoring;
+                    if (!has_prev) {   // the tile's first call
+                        first_flags = AGG_HAS | (pass ? AGG_PASS : 0u) | (second ? AGG_SECOND : 0u) | (mq0 ? AGG_MQ0 : 0u);
+                        first_o1 = o1; first_o2 = o2;
+                    }
+                    if (!is_dupl) {
+                        if (pass) { c_count++; accepted = true; } else c_toolong++;
+                        if (second) {   // second call into G_prime (:180-183); prev_obs was reset to -1
+                            if (mq0) c_nonuniq_scaf++;
+                            const bool dup2 = (o1 == -1 && o2 == -1);
+                            if (dup2) c_dups++;
+                            if (!(dup2 && P.detect_dup)) { if (pass) c_count++; else c_toolong++; }
+                        }
+                    }
+                }
+                const u32 bal = __ballot_sync(0xffffffffu, accepted);
+                if (accepted) {
+                    int4 t;
+                    if (nu < nv) { t.x = (int)nu; t.y = (int)nv; t.z = o1; t.w = o2; }
+                    else { t.x = (int)nv; t.y = (int)nu; t.z = o2; t.w = o1; }
+                    reinterpret_cast<int4*>(P.scratch)[wt * WT + n_out + __popc(bal & lt_mask)] = t;
+                }
+                n_out += __popc(bal);
+                const int last_lane = (total_c - r > 32) ? 31 : (total_c - r - 1);
+                carry_o1 = __shfl_sync(0xffffffffu, o1, last_lane);
+                carry_o2 = __shfl_sync(0xffffffffu, o2, last_lane);
+                have_carry = true;
+            }
+            __syncwarp();   // the candidate slots are reused by the next tile
+        }
+
+        // ---- aggregate (the first call of the tile sits in lane 0 of the first round) -----------------
         if (lane == 0) {
             int4* a = reinterpret_cast<int4*>(P.aggs + wt);
-            a[0] = make_int4((int)(has_mask ? ff : 0u), f1, f2, l1v);
-            a[1] = make_int4(l2v, total, 0, 0);
+            a[0] = make_int4((int)first_flags, first_o1, first_o2, carry_o1);
+            a[1] = make_int4(carry_o2, n_out, 0, 0);
             a[2] = make_int4(0, 0, 0, 0);
         }
     }
@@ -761,9 +776,12 @@ int besst_launch_extract(besst_ctx* ctx, const besst_lib_params& p, const Device
     const void* ptrs[] = {rec.tid, rec.mtid, rec.pos, rec.mpos, rec.qlen, rec.flag, rec.mapq};
     for (const void* q : ptrs) vec = vec && ((reinterpret_cast<uintptr_t>(q) & 15u) == 0);
 
+    const bool int_rl = p.read_len >= 0 && p.read_len < 1e9 && p.read_len == (double)(long long)p.read_len;
+    typedef void (*K1Fn)(const K1Params);
+    const K1Fn k1 = vec ? (int_rl ? k_extract_links<true, true> : k_extract_links<true, false>)
+                        : (int_rl ? k_extract_links<false, true> : k_extract_links<false, false>);
     int per_sm = 0;
-    if (vec) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_extract_links<true>, K1_THREADS, 0);
-    else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_extract_links<false>, K1_THREADS, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k1, K1_THREADS, 0);
     if (per_sm < 1) per_sm = 1;
     long long grid = (long long)ctx->sm_count * per_sm;
     const long long max_grid = (n_tiles + (K1_THREADS / 32) - 1) / (K1_THREADS / 32);
@@ -786,7 +804,15 @@ int besst_launch_extract(besst_ctx* ctx, const besst_lib_params& p, const Device
         P.n_contigs = (int)ctx->n_contigs;
         P.orientation = p.orientation; P.min_mapq = p.min_mapq; P.detect_dup = p.detect_duplicate;
         P.extend = p.extend_paths; P.scoring = !p.no_score;
-        P.read_len = p.read_len; P.threshold = p.ins_size_threshold;
+        P.read_len = p.read_len;
+        P.read_len_i = int_rl ? (int)p.read_len : 0;
+        {   // integer form of the acceptance threshold (exact for integer sums; NaN never accepts)
+            const double t = p.ins_size_threshold;
+            if (t != t) P.threshold_i = -(1ll << 62);
+            else if (t >= 4e18) P.threshold_i = (1ll << 62);
+            else if (t <= -4e18) P.threshold_i = -(1ll << 62);
+            else P.threshold_i = (long long)ceil(t);
+        }
         P.scratch = ctx->scratch_tuples.as<besst_link_tuple>();
         P.aggs = aggs;
         P.fishy = ctx->fishy_keys.as<u64>(); P.fishy_cap = ctx->fishy_cap;
@@ -797,8 +823,7 @@ int besst_launch_extract(besst_ctx* ctx, const besst_lib_params& p, const Device
         if (n_tiles > 0) {
             {
                 KTimer kt(ctx, BESST_K_EXTRACT);
-                if (vec) k_extract_links<true><<<(unsigned)grid, K1_THREADS, 0, ctx->stream>>>(P);
-                else k_extract_links<false><<<(unsigned)grid, K1_THREADS, 0, ctx->stream>>>(P);
+                k1<<<(unsigned)grid, K1_THREADS, 0, ctx->stream>>>(P);
             }
             { KTimer kt(ctx, BESST_K_TILE_SCAN); k_tile_reduce<<<(unsigned)n_chunks, SC_THREADS, 0, ctx->stream>>>(aggs, n_tiles, chunk_aggs, p.detect_duplicate); }
             { KTimer kt(ctx, BESST_K_TILE_SCAN); k_chunk_resolve<<<1, SC_THREADS, 0, ctx->stream>>>(chunk_aggs, n_chunks, chunk_in, tile_off + n_tiles, p.halo_prev_obs1, p.halo_prev_obs2, p.detect_duplicate, counters, globals); }
