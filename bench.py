@@ -266,7 +266,7 @@ def run_ours(args):
         rec_host = abi.make_records(hp, on_device=True)
         rec_host.on_device = 0
         e2e_steps = max(1, min(args.steps, 3))
-        if world == 1:
+        if world == 1 and not args.no_e2e:
             res = None
             eng.fetch(eng.build(params, rec_host))   # warm-up: staging buffers
             barrier()
@@ -410,6 +410,7 @@ def main():
     ap.add_argument("--workload", default="config3", choices=sorted(WORKLOADS))
     ap.add_argument("--scale", type=float, default=1.0, help="debug: shrink the workload")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (profiler runs only)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -5,14 +5,18 @@ import csv
 import sys
 
 
-def main(path):
+def main(path, ours_only=True):
+    """ours_only: keep this library's kernels (k_*); the torch kernels of the synthetic generator and of
+    bench.py's bookkeeping run outside the timed region."""
     lines = [l for l in open(path) if l.startswith('"')]
     rows = list(csv.DictReader(lines))
     agg = collections.OrderedDict()
     for r in rows:
         if r.get("Metric Name") != "gpu__time_duration.sum":
             continue
-        k = r["Kernel Name"].replace("void <unnamed>::", "").split("(")[0]
+        k = r["Kernel Name"].replace("void <unnamed>::", "").replace("<unnamed>::", "").split("(")[0]
+        if ours_only and not k.startswith("k_"):
+            continue
         v = float(r["Metric Value"])
         if r.get("Metric Unit") in ("ns", "nsecond"):
             v /= 1e3
@@ -25,4 +29,4 @@ def main(path):
 
 
 if __name__ == "__main__":
-    main(sys.argv[1])
+    main(sys.argv[1], ours_only="--all" not in sys.argv)
