@@ -29,6 +29,7 @@
 // Coverage uses __match_any_sync warp-aggregated 64-bit atomics; counters stay
 // in registers for the life of a warp and are flushed once.
 #include <math.h>
+#include <stdlib.h>
 
 #include "besst_internal.cuh"
 
@@ -354,6 +355,365 @@ __global__ void __launch_bounds__(K1_THREADS) k_extract_links(const K1Params P) 
             a[1] = make_int4(carry_o2, n_out, 0, 0);
             a[2] = make_int4(0, 0, 0, 0);
         }
+    }
+
+    // ---- flush the per-thread counters ------------------------------------------------------------
+    __syncthreads();
+    const int local_cnt[8] = {c_count, c_nonuniq, c_nonuniq_scaf, c_dups, c_toolong, c_fishy, c_calls, c_valid};
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        int v = local_cnt[k];
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+        if (lane == 0 && v) atomicAdd(&s_cnt[k], (u64)(long long)v);
+    }
+    __syncthreads();
+    if (threadIdx.x < 8 && s_cnt[threadIdx.x]) atomicAdd(&P.counters[threadIdx.x], s_cnt[threadIdx.x]);
+}
+
+// ---- K1, TMA-staged variant ---------------------------------------------------------------------
+// Same algorithm as k_extract_links; what changes is how the record columns reach the SM and how the
+// per-record work is laid out:
+//  * every warp owns two shared-memory stages of one 128-record tile (7 columns, 2944 B).  Lane 0
+//    issues the tile after next with cp.async.bulk (TMA, 1-D) completing on a per-stage mbarrier,
+//    so a warp always has a whole tile in flight while it works on the current one and no register
+//    is tied up by outstanding loads.  pos/mpos are only fetched ahead when the previous tile had a
+//    CreateEdge candidate (libraries with long contigs keep reading 15 instead of 23 B/record); a
+//    tile that needs them unexpectedly fetches them on a third mbarrier.
+//  * candidates are compacted as one-byte record indices into the staged tile instead of copying
+//    five words each.
+//  * the contig-table word of a lane's first record is reused for its other three records (the BAM
+//    is tid-sorted); out-of-range contigs read as row word 0 == BESST_CTG_ABSENT.
+constexpr int K1T_WARPS = 6;
+constexpr int K1T_THREADS = 32 * K1T_WARPS;
+constexpr int K1T_MIN_CTAS = 6;
+constexpr int K1T_BATCH = 8;   // consecutive tiles per ticket
+
+struct __align__(16) TileBuf {
+    int tid[WT], mtid[WT], qlen[WT], pos[WT], mpos[WT];
+    unsigned short flag[WT];
+    unsigned char mapq[WT];
+};
+static_assert(sizeof(TileBuf) == 2944, "TileBuf layout");
+constexpr u32 TILE_BYTES_NOPOS = 3 * 4 * WT + 2 * WT + WT;   // tid, mtid, qlen, flag, mapq
+constexpr u32 TILE_BYTES_POS = 2 * 4 * WT;
+
+struct __align__(16) WarpSmem {
+    TileBuf buf[2];
+    u64 bar[4];                 // [0],[1]: stage barriers, [2]: on-demand pos/mpos
+    unsigned char cand[WT];     // record index (within the tile) of every CreateEdge candidate, BAM order
+};
+static_assert(sizeof(WarpSmem) % 16 == 0, "WarpSmem alignment");
+
+__device__ __forceinline__ u32 smem_u32(const void* p) { return (u32)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(u32 bar, u32 count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(u32 bar, u32 bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(u32 dst, const void* src, u32 bytes, u32 bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(__cvta_generic_to_global(src)), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ bool elect_one() {
+    u32 pred;
+    asm volatile("{\n .reg .pred p;\n elect.sync _|p, 0xffffffff;\n selp.u32 %0, 1, 0, p;\n}" : "=r"(pred));
+    return pred != 0;
+}
+__device__ __forceinline__ void mbar_wait(u32 bar, u32 parity) {
+    u32 done;
+    do {
+        asm volatile(
+            "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+
+template <bool INT_RL>
+__global__ void __launch_bounds__(K1T_THREADS, K1T_MIN_CTAS) k_extract_links_tma(const K1Params P, const int vec_ok) {
+    extern __shared__ __align__(128) unsigned char k1_smem[];
+    __shared__ u64 s_cnt[8];
+    const int lane = threadIdx.x & 31;
+    // broadcast from lane 0 so that the compiler knows the warp index (and everything derived from it:
+    // tile numbers, stage addresses) is warp-uniform and keeps the TMA operands in uniform registers
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+    const u32 lt_mask = (1u << lane) - 1u;
+    WarpSmem& W = reinterpret_cast<WarpSmem*>(k1_smem)[warp];
+    const u32 bar0 = smem_u32(&W.bar[0]);
+    int c_count = 0, c_nonuniq = 0, c_nonuniq_scaf = 0, c_dups = 0, c_toolong = 0, c_fishy = 0, c_calls = 0, c_valid = 0;
+    if (threadIdx.x < 8) s_cnt[threadIdx.x] = 0;
+    if (lane == 0) {
+        mbar_init(bar0, 1); mbar_init(bar0 + 8, 1); mbar_init(bar0 + 16, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const long long n = P.rec.n;
+    const long long warp_global = (long long)blockIdx.x * K1T_WARPS + warp;
+    const long long n_warps = (long long)gridDim.x * K1T_WARPS;
+    const u32 n_contigs = (u32)P.n_contigs;
+
+    // stage state, warp-uniform: bit s of `st_async` = stage s was filled by TMA (wait on its barrier),
+    // of `st_pos` = its pos/mpos columns are (being) loaded, of `st_par` = the parity to wait for next
+    u32 st_async = 0, st_pos = 0, st_par = 0, demand_par = 0;
+    auto issue = [&](long long tile, int s, bool want_pos) {
+        const bool full = vec_ok && ((tile + 1) * WT <= n);
+        st_async = (st_async & ~(1u << s)) | ((full ? 1u : 0u) << s);
+        st_pos = (st_pos & ~(1u << s)) | (((want_pos || !full) ? 1u : 0u) << s);
+        if (full && elect_one()) {
+            const long long r0 = tile * WT;
+            const u32 bar = bar0 + 8u * s;
+            const u32 dst = smem_u32(&W.buf[s]);
+            mbar_expect_tx(bar, TILE_BYTES_NOPOS + (want_pos ? TILE_BYTES_POS : 0u));
+            bulk_g2s(dst + 0 * 4 * WT, P.rec.tid + r0, 4 * WT, bar);
+            bulk_g2s(dst + 1 * 4 * WT, P.rec.mtid + r0, 4 * WT, bar);
+            bulk_g2s(dst + 2 * 4 * WT, P.rec.qlen + r0, 4 * WT, bar);
+            if (want_pos) {
+                bulk_g2s(dst + 3 * 4 * WT, P.rec.pos + r0, 4 * WT, bar);
+                bulk_g2s(dst + 4 * 4 * WT, P.rec.mpos + r0, 4 * WT, bar);
+            }
+            bulk_g2s(dst + 5 * 4 * WT, P.rec.flag + r0, 2 * WT, bar);
+            bulk_g2s(dst + 5 * 4 * WT + 2 * WT, P.rec.mapq + r0, WT, bar);
+        }
+    };
+
+    u32 cand_hist = 7u;   // bit t: the t-th last tile had a CreateEdge candidate
+    // tiles are handed out dynamically in batches of K1T_BATCH consecutive tiles (one ticket per warp
+    // and batch; a ticket per tile would serialise 3 M same-address atomics) after a static first
+    // batch: warps progress at different speeds and a static split leaves a quarter of the warp slots
+    // idle towards the end.  The ticket of the next batch is requested a whole batch ahead.
+    u32* const ticket = reinterpret_cast<u32*>(P.globals + 2);
+    long long b_cur = warp_global * K1T_BATCH;
+    int b_j = 0;
+    u32 t_raw = 0;
+    if (lane == 0) t_raw = atomicAdd(ticket, 1u);
+    auto next_tile = [&]() -> long long {
+        if (b_j == K1T_BATCH) {
+            b_cur = (n_warps + (long long)__shfl_sync(0xffffffffu, t_raw, 0)) * K1T_BATCH;
+            b_j = 0;
+            if (lane == 0) t_raw = atomicAdd(ticket, 1u);
+        }
+        return b_cur + (b_j++);
+    };
+    long long wt = next_tile();
+    if (wt < P.n_tiles) issue(wt, 0, true);
+    long long nx = next_tile();
+    for (u32 it = 0; wt < P.n_tiles; ++it) {
+        const int s = (int)(it & 1u);
+        if (nx < P.n_tiles) issue(nx, s ^ 1, (cand_hist & 7u) != 0);
+        TileBuf& B = W.buf[s];
+        if (st_async >> s & 1u) {
+            mbar_wait(bar0 + 8u * s, (st_par >> s) & 1u);
+            st_par ^= 1u << s;
+        } else {   // ragged last tile or unaligned columns: plain bounds-checked loads into the stage
+            const long long idx0 = wt * WT + (long long)lane * WT_ITEMS;
+#pragma unroll
+            for (int i = 0; i < WT_ITEMS; ++i) {
+                const long long r = idx0 + i;
+                const bool in = r < n;
+                const int q = lane * WT_ITEMS + i;
+                B.tid[q] = in ? __ldg(P.rec.tid + r) : -1;
+                B.mtid[q] = in ? __ldg(P.rec.mtid + r) : -1;
+                B.qlen[q] = in ? __ldg(P.rec.qlen + r) : 0;
+                B.pos[q] = in ? __ldg(P.rec.pos + r) : 0;
+                B.mpos[q] = in ? __ldg(P.rec.mpos + r) : 0;
+                B.flag[q] = in ? __ldg(P.rec.flag + r) : (unsigned short)0;
+                B.mapq[q] = in ? __ldg(P.rec.mapq + r) : (unsigned char)0;
+            }
+            __syncwarp();
+        }
+
+        int tid[WT_ITEMS], mtid[WT_ITEMS], qlen[WT_ITEMS];
+        u32 flag[WT_ITEMS], mapq[WT_ITEMS];
+        {
+            const int4 a = *reinterpret_cast<const int4*>(&B.tid[lane * WT_ITEMS]);
+            const int4 b = *reinterpret_cast<const int4*>(&B.mtid[lane * WT_ITEMS]);
+            const int4 c = *reinterpret_cast<const int4*>(&B.qlen[lane * WT_ITEMS]);
+            const uint2 f = *reinterpret_cast<const uint2*>(&B.flag[lane * WT_ITEMS]);
+            const u32 m = *reinterpret_cast<const u32*>(&B.mapq[lane * WT_ITEMS]);
+            tid[0] = a.x; tid[1] = a.y; tid[2] = a.z; tid[3] = a.w;
+            mtid[0] = b.x; mtid[1] = b.y; mtid[2] = b.z; mtid[3] = b.w;
+            qlen[0] = c.x; qlen[1] = c.y; qlen[2] = c.z; qlen[3] = c.w;
+            flag[0] = f.x & 0xffffu; flag[1] = f.x >> 16; flag[2] = f.y & 0xffffu; flag[3] = f.y >> 16;
+            mapq[0] = m & 0xffu; mapq[1] = (m >> 8) & 0xffu; mapq[2] = (m >> 16) & 0xffu; mapq[3] = m >> 24;
+        }
+
+        // ---- per-record classification (CreateGraph.py:118-206); only word 0 of a row is needed ----
+        // word 0 == 0 <=> the contig is absent (state ABSENT == 0) or out of range (:118-130)
+        const int xa = ((u32)tid[0] < n_contigs) ? __ldg(reinterpret_cast<const int*>(P.rows + tid[0])) : 0;
+        u32 elig = 0, cov = 0;   // one bit per item
+#pragma unroll
+        for (int i = 0; i < WT_ITEMS; ++i) {
+            int x1 = xa;
+            if (i > 0 && tid[i] != tid[0]) x1 = ((u32)tid[i] < n_contigs) ? __ldg(reinterpret_cast<const int*>(P.rows + tid[i])) : 0;
+            const int mq = (int)mapq[i];
+            const bool covered = (mq >= P.min_mapq) || mq == 0;                                           // :138
+            if (tid[i] == mtid[i]) {   // same contig: same scaffold, no link, no fishy pair
+                if (row_state(x1) != BESST_CTG_ABSENT) { c_valid++; if (covered) cov |= 1u << i; }
+                continue;
+            }
+            const int x2 = ((u32)mtid[i] < n_contigs) ? __ldg(reinterpret_cast<const int*>(P.rows + mtid[i])) : 0;
+            if (row_state(x1) == BESST_CTG_ABSENT || row_state(x2) == BESST_CTG_ABSENT) continue;          // :127-130
+            c_valid++;
+            if (covered) cov |= 1u << i;
+            const u32 f = flag[i];
+            const bool unmapped = f & 0x4u;
+            const bool diff_scaf = ((u32)(x1 ^ x2) >> 3) != 0;
+            if (unmapped && (f & 0x40u) && diff_scaf) {                                                   // :141-163
+                const u32 n1 = 2u * (u32)row_scaf(x1) + (u32)side_only(row_dir(x1), !(f & 0x10u), P.orientation);
+                const u32 n2 = 2u * (u32)row_scaf(x2) + (u32)side_only(row_dir(x2), !(f & 0x20u), P.orientation);
+                const u64 key = n1 < n2 ? (((u64)n1 << 32) | n2) : (((u64)n2 << 32) | n1);
+                const u64 slot = atomicAdd(&P.globals[1], 1ull);
+                if ((long long)slot < P.fishy_cap) P.fishy[slot] = key;
+                c_fishy++;
+            }
+            if (mq == 0) c_nonuniq++;                                                                     // :166-167
+            if ((f & 0x80u) && !unmapped && mq >= P.min_mapq) {                                           // :169
+                const bool both_large = row_state(x1) == BESST_CTG_LARGE && row_state(x2) == BESST_CTG_LARGE;
+                const bool both_small = row_state(x1) == BESST_CTG_SMALL && row_state(x2) == BESST_CTG_SMALL;
+                // :170 large-large needs different scaffolds; :184-206 (extend_paths) small-small needs
+                // different scaffolds, exactly one small always qualifies
+                const bool e = both_large ? diff_scaf : (P.extend && (both_small ? diff_scaf : true));
+                if (e) elig |= 1u << i;
+            }
+        }
+
+        // ---- coverage: warp-aggregated 64-bit atomics (:138-139) ----------------------------
+        {
+            int t0 = -1, s0 = 0;
+#pragma unroll
+            for (int i = 0; i < WT_ITEMS; ++i)
+                if (cov >> i & 1u) {
+                    if (t0 < 0) t0 = tid[i];
+                    if (tid[i] == t0) { s0 += qlen[i]; cov &= ~(1u << i); }
+                }
+            // common case: the whole tile lies on one contig -> one reduction, one atomic
+            const int tw = __shfl_sync(0xffffffffu, tid[0], 0);
+            if (__all_sync(0xffffffffu, t0 < 0 || t0 == tw)) {
+                const int sum = __reduce_add_sync(0xffffffffu, s0);
+                if (lane == 0 && sum != 0) atomicAdd(&P.aligned[tw], (u64)(long long)sum);
+            } else {
+                const u32 act = __ballot_sync(0xffffffffu, t0 >= 0);
+                if (t0 >= 0) {
+                    const u32 peers = __match_any_sync(act, t0);
+                    const int sum = __reduce_add_sync(peers, s0);
+                    if (lane == __ffs(peers) - 1) atomicAdd(&P.aligned[t0], (u64)(long long)sum);
+                }
+            }
+            if (__any_sync(0xffffffffu, cov != 0)) {   // a lane's 4 records straddle contigs: rare
+#pragma unroll
+                for (int i = 1; i < WT_ITEMS; ++i)
+                    if (cov >> i & 1u) atomicAdd(&P.aligned[tid[i]], (u64)(long long)qlen[i]);
+            }
+        }
+
+        // ---- compact the CreateEdge candidates of the tile, BAM order, one per lane ------------
+        const int my_c = __popc(elig);
+        int incl_c = my_c;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl_c, off);
+            if (lane >= off) incl_c += t;
+        }
+        const int total_c = __shfl_sync(0xffffffffu, incl_c, 31);
+        int n_out = 0;
+        u32 first_flags = 0;
+        int first_o1 = 0, first_o2 = 0, carry_o1 = 0, carry_o2 = 0;
+        cand_hist = (cand_hist << 1) | (total_c > 0 ? 1u : 0u);
+        if (total_c > 0) {
+            int slot = incl_c - my_c;
+#pragma unroll
+            for (int i = 0; i < WT_ITEMS; ++i)
+                if (elig >> i & 1u) W.cand[slot++] = (unsigned char)(lane * WT_ITEMS + i);
+            if (!(st_pos >> s & 1u)) {   // pos/mpos were not fetched ahead for this tile
+                if (elect_one()) {
+                    const long long r0 = wt * WT;
+                    mbar_expect_tx(bar0 + 16u, TILE_BYTES_POS);
+                    bulk_g2s(smem_u32(&B.pos[0]), P.rec.pos + r0, 4 * WT, bar0 + 16u);
+                    bulk_g2s(smem_u32(&B.mpos[0]), P.rec.mpos + r0, 4 * WT, bar0 + 16u);
+                }
+                mbar_wait(bar0 + 16u, demand_par);
+                demand_par ^= 1u;
+            }
+            __syncwarp();
+
+            // ---- CreateEdge, one call per lane: observations (:816-833), duplicate test against the
+            // previous call (:835-838), acceptance test (:840), counters.  The tile's first call has no
+            // in-tile predecessor: assumed "not a duplicate" here and settled by the aggregate scan.
+            bool have_carry = false;
+            for (int r = 0; r < total_c; r += 32) {
+                const int k = r + lane;
+                const bool active = k < total_c;
+                int o1 = 0, o2 = 0;
+                u32 nu = 0, nv = 0, fl = 0;
+                bool mq0 = false, both_large = false;
+                if (active) {
+                    const int j = W.cand[k];
+                    fl = B.flag[j];
+                    mq0 = B.mapq[j] == 0;
+                    const int4 r1 = __ldg(P.rows + B.tid[j]);   // L1 hits: word 0 was gathered a moment ago
+                    const int4 r2 = __ldg(P.rows + B.mtid[j]);
+                    both_large = row_state(r1.x) == BESST_CTG_LARGE && row_state(r2.x) == BESST_CTG_LARGE;
+                    int s1, s2;
+                    pos_dir<INT_RL>(row_dir(r1.x), !(fl & 0x10u), P.orientation, r1.y, B.pos[j], r1.w, r1.z, P.read_len, P.read_len_i, o1, s1);
+                    pos_dir<INT_RL>(row_dir(r2.x), !(fl & 0x20u), P.orientation, r2.y, B.mpos[j], r2.w, r2.z, P.read_len, P.read_len_i, o2, s2);
+                    nu = 2u * (u32)row_scaf(r1.x) + (u32)s1;
+                    nv = 2u * (u32)row_scaf(r2.x) + (u32)s2;
+                }
+                int p1 = __shfl_up_sync(0xffffffffu, o1, 1), p2 = __shfl_up_sync(0xffffffffu, o2, 1);
+                bool has_prev = true;
+                if (lane == 0) { p1 = carry_o1; p2 = carry_o2; has_prev = have_carry; }
+                bool accepted = false;
+                if (active) {
+                    c_calls++;
+                    if (mq0) c_nonuniq_scaf++;
+                    const bool dup = has_prev && o1 == p1 && o2 == p2;
+                    bool is_dupl = false;
+                    if (dup) { c_dups++; is_dupl = P.detect_dup; }
+                    const bool pass = ((long long)o1 + o2) < P.threshold_i && o1 > 25 && o2 > 25;
+                    const bool second = both_large && P.extend && P.scoring;
+                    if (!has_prev) {   // the tile's first call
+                        first_flags = AGG_HAS | (pass ? AGG_PASS : 0u) | (second ? AGG_SECOND : 0u) | (mq0 ? AGG_MQ0 : 0u);
+                        first_o1 = o1; first_o2 = o2;
+                    }
+                    if (!is_dupl) {
+                        if (pass) { c_count++; accepted = true; } else c_toolong++;
+                        if (second) {   // second call into G_prime (:180-183); prev_obs was reset to -1
+                            if (mq0) c_nonuniq_scaf++;
+                            const bool dup2 = (o1 == -1 && o2 == -1);
+                            if (dup2) c_dups++;
+                            if (!(dup2 && P.detect_dup)) { if (pass) c_count++; else c_toolong++; }
+                        }
+                    }
+                }
+                const u32 bal = __ballot_sync(0xffffffffu, accepted);
+                if (accepted) {
+                    int4 t;
+                    if (nu < nv) { t.x = (int)nu; t.y = (int)nv; t.z = o1; t.w = o2; }
+                    else { t.x = (int)nv; t.y = (int)nu; t.z = o2; t.w = o1; }
+                    reinterpret_cast<int4*>(P.scratch)[wt * WT + n_out + __popc(bal & lt_mask)] = t;
+                }
+                n_out += __popc(bal);
+                const int last_lane = (total_c - r > 32) ? 31 : (total_c - r - 1);
+                carry_o1 = __shfl_sync(0xffffffffu, o1, last_lane);
+                carry_o2 = __shfl_sync(0xffffffffu, o2, last_lane);
+                have_carry = true;
+            }
+        }
+        __syncwarp();   // the stage and the candidate list are reused two / one tiles from now
+
+        // ---- aggregate (the first call of the tile sits in lane 0 of the first round) -----------------
+        if (lane == 0) {
+            int4* a = reinterpret_cast<int4*>(P.aggs + wt);
+            a[0] = make_int4((int)first_flags, first_o1, first_o2, carry_o1);
+            a[1] = make_int4(carry_o2, n_out, 0, 0);
+            a[2] = make_int4(0, 0, 0, 0);
+        }
+        wt = nx;
+        nx = next_tile();
     }
 
     // ---- flush the per-thread counters ------------------------------------------------------------
@@ -780,11 +1140,18 @@ int besst_launch_extract(besst_ctx* ctx, const besst_lib_params& p, const Device
     typedef void (*K1Fn)(const K1Params);
     const K1Fn k1 = vec ? (int_rl ? k_extract_links<true, true> : k_extract_links<true, false>)
                         : (int_rl ? k_extract_links<false, true> : k_extract_links<false, false>);
+    // BESST_K1_LEGACY=1 selects the register-staged kernel (A/B measurements); default is the TMA-staged one
+    static const bool legacy = [] { const char* e = getenv("BESST_K1_LEGACY"); return e && e[0] == '1'; }();
+    typedef void (*K1TFn)(const K1Params, const int);
+    const K1TFn k1t = int_rl ? k_extract_links_tma<true> : k_extract_links_tma<false>;
+    const size_t k1t_smem = sizeof(WarpSmem) * K1T_WARPS;
+    const int k1_threads = legacy ? K1_THREADS : K1T_THREADS;
     int per_sm = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k1, K1_THREADS, 0);
+    if (legacy) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k1, K1_THREADS, 0);
+    else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k1t, K1T_THREADS, k1t_smem);
     if (per_sm < 1) per_sm = 1;
     long long grid = (long long)ctx->sm_count * per_sm;
-    const long long max_grid = (n_tiles + (K1_THREADS / 32) - 1) / (K1_THREADS / 32);
+    const long long max_grid = (n_tiles + (k1_threads / 32) - 1) / (k1_threads / 32);
     if (grid > max_grid) grid = max_grid > 0 ? max_grid : 1;
 
     Agg* aggs = ctx->tile_aggs.as<Agg>();
@@ -823,7 +1190,8 @@ int besst_launch_extract(besst_ctx* ctx, const besst_lib_params& p, const Device
         if (n_tiles > 0) {
             {
                 KTimer kt(ctx, BESST_K_EXTRACT);
-                k1<<<(unsigned)grid, K1_THREADS, 0, ctx->stream>>>(P);
+                if (legacy) k1<<<(unsigned)grid, K1_THREADS, 0, ctx->stream>>>(P);
+                else k1t<<<(unsigned)grid, K1T_THREADS, k1t_smem, ctx->stream>>>(P, vec ? 1 : 0);
             }
             { KTimer kt(ctx, BESST_K_TILE_SCAN); k_tile_reduce<<<(unsigned)n_chunks, SC_THREADS, 0, ctx->stream>>>(aggs, n_tiles, chunk_aggs, p.detect_duplicate); }
             { KTimer kt(ctx, BESST_K_TILE_SCAN); k_chunk_resolve<<<1, SC_THREADS, 0, ctx->stream>>>(chunk_aggs, n_chunks, chunk_in, tile_off + n_tiles, p.halo_prev_obs1, p.halo_prev_obs2, p.detect_duplicate, counters, globals); }
