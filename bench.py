@@ -227,7 +227,7 @@ def run_ours(args):
     alg_bytes = {   # algorithmic bytes per launch of each kernel (DESIGN.md "Kernels")
         "k_extract_links": RECORD_BYTES * n_rec + TUPLE_BYTES * n_links + 48 * ((n_rec + 127) // 128),
         "k_compact_tuples": 2 * TUPLE_BYTES * n_links + 8 * ((n_rec + 127) // 128),
-        "k_radix_sweep": (12 + 12) * n_links,
+        "k_radix_sweep": (8 + 8) * n_links,       # packed sort word (key | BAM index): 8 B in, 8 B out per pass
         "k_radix_hist": 8 * n_links,
         "k_edge_reduce": (4 + 16 + 8) * n_links + 64 * n_edges,
         "k_score_keys": (8 + 8) * n_ll / 3.0 + 13 * n_edges,   # 3 launches: LL scan (2, over edges) + key build
@@ -268,12 +268,12 @@ def run_ours(args):
         e2e_steps = max(1, min(args.steps, 3))
         if world == 1 and not args.no_e2e:
             res = None
-            eng.fetch(eng.build(params, rec_host))   # warm-up: staging buffers
+            eng.fetch_view(eng.build(params, rec_host))   # warm-up: staging buffers, pinned result buffers
             barrier()
             t0 = time.perf_counter()
             for _ in range(e2e_steps):
                 s = eng.build(params, rec_host)
-                res = eng.fetch(s)
+                res = eng.fetch_view(s)
             barrier()
             t1 = time.perf_counter()
             d2h = sum(int(getattr(res, f).nbytes) for f in ("edge_u", "edge_v", "nr_links", "obs_sum", "obs_sq",

@@ -8,7 +8,7 @@ from dataclasses import dataclass
 
 import numpy as np
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 CTG_ABSENT, CTG_LARGE, CTG_SMALL = 0, 1, 2
 ORIENT_FR, ORIENT_RF = 0, 1
@@ -107,6 +107,22 @@ def alloc_graph_out(sizes):
     for name, _, _ in _GRAPH_FIELDS:
         setattr(out, name, arrays[name].ctypes.data)
     return out, arrays
+
+
+def view_graph_out(out, sizes):
+    """numpy views over the library-owned pinned buffers a besst_graph_view call left in `out`
+    (no copy; valid until the next view / destroy on that ctx)."""
+    dims = {"E": int(sizes.n_edges), "E1": int(sizes.n_edges) + 1, "L": int(sizes.n_links), "C": int(sizes.n_contigs)}
+    arrays = {}
+    for name, dt, d in _GRAPH_FIELDS:
+        n = dims[d]
+        ptr = getattr(out, name)
+        if n == 0 or not ptr:
+            arrays[name] = np.empty(0, dtype=dt)
+            continue
+        buf = (C.c_char * (n * np.dtype(dt).itemsize)).from_address(ptr)
+        arrays[name] = np.frombuffer(buf, dtype=dt, count=n)
+    return arrays
 
 
 def graph_result(out, arrays):

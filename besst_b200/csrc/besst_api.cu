@@ -2,6 +2,7 @@
 // buffers, H2D/D2H marshalling, stage ordering on one CUDA stream, CUDA-event
 // timing.  There is no CPU implementation behind these entry points: without a
 // CUDA device besst_create fails.
+#include <stdlib.h>
 #include <string.h>
 
 #include <vector>
@@ -32,6 +33,12 @@ extern "C" besst_ctx* besst_create(int device) {
     e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) { g_create_error = std::string("cudaStreamCreate: ") + cudaGetErrorString(e); delete ctx; return nullptr; }
     ctx->stream = ctx->own_stream;
+    cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking);
+    cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming);
+    if (const char* e = getenv("BESST_SLICE_RECORDS")) {   // tuning knob: records per H2D slice
+        const long long v = atoll(e);
+        if (v >= 128) ctx->slice_records = (v / 128) * 128;
+    }
     for (int i = 0; i <= BESST_N_STAGES; ++i) cudaEventCreate(&ctx->ev[i]);
     return ctx;
 }
@@ -48,6 +55,10 @@ extern "C" void besst_destroy(besst_ctx* ctx) {
                     &ctx->e_sum_u, &ctx->e_max_v, &ctx->ll_off, &ctx->ks_key[0], &ctx->ks_key[1], &ctx->ks_key[2], &ctx->ks_key[3]};
     for (DBuf* b : bufs) b->release();
     for (DBuf& b : ctx->rec_i32) b.release();
+    for (HBuf& b : ctx->h_out) b.release();
+    for (cudaEvent_t e : ctx->slice_events) cudaEventDestroy(e);
+    if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     for (int i = 0; i <= BESST_N_STAGES; ++i) cudaEventDestroy(ctx->ev[i]);
     for (auto& e : ctx->prof_pool) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
     cudaStreamDestroy(ctx->own_stream);
@@ -127,6 +138,59 @@ static int stage_records(besst_ctx* ctx, const besst_records* r, DeviceRecords* 
     return BESST_OK;
 }
 
+// Host-buffer graph build: the seven record columns are copied slice by slice on copy_stream while
+// the record kernel works on the slices that have arrived (an event per slice orders the two
+// streams), so the call costs max(PCIe, K1) instead of their sum.
+static int extract_host_pipelined(besst_ctx* ctx, const besst_lib_params* params, const besst_records* r, DeviceRecords* d) {
+    if (r->n < 0 || !r->tid || !r->mtid || !r->flag || !r->mapq || !r->pos || !r->mpos || !r->qlen) {
+        ctx->err = "records: missing column";
+        return BESST_E_INVALID;
+    }
+    const size_t n = (size_t)r->n;
+    const int32_t* src[6] = {r->tid, r->mtid, r->pos, r->mpos, nullptr, r->qlen};
+    const int32_t** dst[6] = {&d->tid, &d->mtid, &d->pos, &d->mpos, &d->tlen, &d->qlen};
+    for (int k = 0; k < 6; ++k) {
+        *dst[k] = nullptr;
+        if (!src[k]) continue;
+        BESST_CUDA_TRY(ctx, ctx->rec_i32[k].ensure(4 * n));
+        *dst[k] = ctx->rec_i32[k].as<int32_t>();
+    }
+    BESST_CUDA_TRY(ctx, ctx->rec_flag.ensure(2 * n));
+    BESST_CUDA_TRY(ctx, ctx->rec_mapq.ensure(n));
+    d->flag = ctx->rec_flag.as<uint16_t>();
+    d->mapq = ctx->rec_mapq.as<uint8_t>();
+    d->n = r->n;
+    const int64_t S = ctx->slice_records;
+    const int64_t n_slices = (r->n + S - 1) / S;
+    while ((int64_t)ctx->slice_events.size() < n_slices) {
+        cudaEvent_t e;
+        BESST_CUDA_TRY(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        ctx->slice_events.push_back(e);
+    }
+    int rc = besst_extract_begin(ctx, *params, r->n);
+    if (rc) return rc;
+    // the staging buffers may still be read by earlier work on `stream`
+    BESST_CUDA_TRY(ctx, cudaEventRecord(ctx->ev_fork, ctx->stream));
+    BESST_CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_fork, 0));
+    for (int64_t s = 0; s < n_slices; ++s) {
+        const size_t r0 = (size_t)(s * S), r1 = (size_t)((s + 1) * S < r->n ? (s + 1) * S : r->n), m = r1 - r0;
+        for (int k = 0; k < 6; ++k)
+            if (src[k])
+                BESST_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->rec_i32[k].as<int32_t>() + r0, src[k] + r0, 4 * m, cudaMemcpyHostToDevice, ctx->copy_stream));
+        BESST_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->rec_flag.as<uint16_t>() + r0, r->flag + r0, 2 * m, cudaMemcpyHostToDevice, ctx->copy_stream));
+        BESST_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->rec_mapq.as<uint8_t>() + r0, r->mapq + r0, m, cudaMemcpyHostToDevice, ctx->copy_stream));
+        BESST_CUDA_TRY(ctx, cudaEventRecord(ctx->slice_events[(size_t)s], ctx->copy_stream));
+        BESST_CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream, ctx->slice_events[(size_t)s], 0));
+        rc = besst_extract_slice(ctx, *params, *d, (int64_t)r0, (int64_t)r1);
+        if (rc) return rc;
+    }
+    bool overflow = false;
+    rc = besst_extract_finish(ctx, *params, r->n, &overflow);
+    if (rc) return rc;
+    if (overflow) return besst_launch_extract(ctx, *params, *d);   // the records are resident now
+    return BESST_OK;
+}
+
 static int check_params(besst_ctx* ctx, const besst_lib_params* p) {
     if (!p) { ctx->err = "params: null"; return BESST_E_INVALID; }
     if (p->orientation != BESST_ORIENT_FR && p->orientation != BESST_ORIENT_RF) { ctx->err = "params: orientation must be fr or rf"; return BESST_E_INVALID; }
@@ -143,9 +207,13 @@ extern "C" int besst_links_extract(besst_ctx* ctx, const besst_lib_params* param
     ctx->prof_used = 0;
     besst_mark(ctx);
     DeviceRecords d;
-    rc = stage_records(ctx, records, &d, false, true);
-    if (rc) return rc;
-    rc = besst_launch_extract(ctx, *params, d);
+    if (records && !records->on_device && records->n > ctx->slice_records) {
+        rc = extract_host_pipelined(ctx, params, records, &d);
+    } else {
+        rc = stage_records(ctx, records, &d, false, true);
+        if (rc) return rc;
+        rc = besst_launch_extract(ctx, *params, d);
+    }
     if (rc) return rc;
     besst_mark(ctx);
     if (n_tuples) *n_tuples = ctx->n_tuples;
@@ -290,6 +358,44 @@ extern "C" int besst_graph_fetch(besst_ctx* ctx, besst_graph_out* out) {
 #undef FETCH
     if (out->aligned_len && C > 0 && ctx->have_links)
         BESST_CUDA_TRY(ctx, cudaMemcpyAsync(out->aligned_len, ctx->aligned.p, 8 * C, cudaMemcpyDeviceToHost, ctx->stream));
+    memset(out->counters, 0, sizeof(out->counters));
+    if (ctx->have_links)
+        BESST_CUDA_TRY(ctx, cudaMemcpyAsync(out->counters, ctx->counters.p, 8 * BESST_N_COUNTERS, cudaMemcpyDeviceToHost, ctx->stream));
+    BESST_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return BESST_OK;
+}
+
+extern "C" int besst_graph_view(besst_ctx* ctx, besst_graph_out* out) {
+    if (!ctx || !out) return BESST_E_INVALID;
+    if (!ctx->have_graph) { ctx->err = "besst_graph_view before a successful build"; return BESST_E_STATE; }
+    cudaSetDevice(ctx->device);
+    const size_t E = (size_t)ctx->n_edges, L = (size_t)ctx->n_links, C = (size_t)ctx->n_contigs;
+    int slot = 0;
+#define VIEW(field, type, buf, bytes)                                                                               \
+    do {                                                                                                            \
+        HBuf& h = ctx->h_out[slot++];                                                                               \
+        BESST_CUDA_TRY(ctx, h.ensure((bytes) > 0 ? (bytes) : 1));                                                   \
+        if ((bytes) > 0)                                                                                            \
+            BESST_CUDA_TRY(ctx, cudaMemcpyAsync(h.p, ctx->buf.p, (bytes), cudaMemcpyDeviceToHost, ctx->stream));    \
+        out->field = reinterpret_cast<type*>(h.p);                                                                  \
+    } while (0)
+    // the two big per-link arrays first: the rest follows while they are on the wire
+    VIEW(obs_u, int32_t, l_obs_u, 4 * L); VIEW(obs_v, int32_t, l_obs_v, 4 * L);
+    VIEW(edge_u, uint32_t, e_u, 4 * E); VIEW(edge_v, uint32_t, e_v, 4 * E); VIEW(nr_links, int32_t, e_nr, 4 * E);
+    VIEW(obs_sum, int64_t, e_obs, 8 * E); VIEW(obs_sq, int64_t, e_obs_sq, 8 * E); VIEW(first_idx, int64_t, e_first, 8 * E);
+    VIEW(row_ptr, int64_t, e_row_ptr, 8 * (E + 1)); VIEW(gap, int32_t, e_gap, 4 * E); VIEW(score, double, e_score, 8 * E);
+    VIEW(ks, double, e_ks, 8 * E); VIEW(sd_obs, double, e_sd_obs, 8 * E); VIEW(sd_model, double, e_sd_model, 8 * E);
+    VIEW(fishy, int32_t, e_fishy, 4 * E); VIEW(flags, uint8_t, e_flags, E);
+#undef VIEW
+    {
+        HBuf& h = ctx->h_out[slot++];
+        BESST_CUDA_TRY(ctx, h.ensure(C > 0 ? 8 * C : 1));
+        out->aligned_len = reinterpret_cast<int64_t*>(h.p);
+        if (C > 0) {
+            if (ctx->have_links) BESST_CUDA_TRY(ctx, cudaMemcpyAsync(h.p, ctx->aligned.p, 8 * C, cudaMemcpyDeviceToHost, ctx->stream));
+            else memset(h.p, 0, 8 * C);
+        }
+    }
     memset(out->counters, 0, sizeof(out->counters));
     if (ctx->have_links)
         BESST_CUDA_TRY(ctx, cudaMemcpyAsync(out->counters, ctx->counters.p, 8 * BESST_N_COUNTERS, cudaMemcpyDeviceToHost, ctx->stream));

@@ -626,7 +626,9 @@ int besst_launch_graph(besst_ctx* ctx, const besst_lib_params& p, const besst_li
         BESST_CUDA_TRY(ctx, ctx->fishy_tmp.ensure(8 * (size_t)n_fishy));
         { KTimer kt(ctx, BESST_K_FISHY); k_fishy_rekey<<<(int)((n_fishy + 255) / 256), 256, 0, ctx->stream>>>(reinterpret_cast<const u64*>(d_fishy), ctx->fishy_sorted.as<u64>(), n_fishy, bv); }
         int fb = 0;
+        ctx->sweep_kernel_id = BESST_K_FISHY;   // profiling: keep the small fishy-key sort out of k_radix_sweep
         rc = besst_radix_sort_keys(ctx, ctx->fishy_sorted.as<uint64_t>(), ctx->fishy_tmp.as<uint64_t>(), n_fishy, 2 * bv, &fb);
+        ctx->sweep_kernel_id = BESST_K_RADIX_SWEEP;
         if (rc) return rc;
         fishy_sorted = fb ? ctx->fishy_tmp.as<u64>() : ctx->fishy_sorted.as<u64>();
     }

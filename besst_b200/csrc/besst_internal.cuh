@@ -42,6 +42,27 @@ struct DBuf {
     T* as() const { return reinterpret_cast<T*>(p); }
 };
 
+// grow-only pinned host buffer (results handed out as views, see besst_graph_view)
+struct HBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaHostAlloc(&p, want, cudaHostAllocDefault);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() {
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
 struct DeviceRecords {
     int64_t n;
     const int32_t *tid, *mtid, *pos, *mpos, *tlen, *qlen;
@@ -75,8 +96,16 @@ struct besst_ctx {
     DBuf rows, rows_packed, scaf_len;
     int64_t n_contigs = 0, n_scaffolds = 0, n_large = 0;
 
-    // staged records (host-pointer calls)
+    // staged records (host-pointer calls); the copies run on copy_stream, slice by slice, overlapped
+    // with the record kernel on `stream`
     DBuf rec_i32[6], rec_flag, rec_mapq;
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_fork = nullptr;
+    std::vector<cudaEvent_t> slice_events;
+    int64_t slice_records = 16ll << 20;   // records per H2D slice (multiple of 128)
+
+    // pinned host copies of the result (besst_graph_view)
+    HBuf h_out[17];
 
     // link extraction
     DBuf tuples, scratch_tuples, tile_aggs, fishy_keys, aligned, counters, tile_state, part_state, misc;
@@ -112,6 +141,10 @@ struct besst_ctx {
 // ---- launchers (one per translation unit) ----------------------------------
 // links: records -> accepted link tuples (BAM order), coverage, fishy keys, counters
 int besst_launch_extract(besst_ctx* ctx, const besst_lib_params& p, const DeviceRecords& rec);
+// the same in phases, for callers that feed the record range in slices (H2D overlap)
+int besst_extract_begin(besst_ctx* ctx, const besst_lib_params& p, int64_t n);
+int besst_extract_slice(besst_ctx* ctx, const besst_lib_params& p, const DeviceRecords& rec, int64_t r0, int64_t r1);
+int besst_extract_finish(besst_ctx* ctx, const besst_lib_params& p, int64_t n, bool* overflow);
 
 // sort + CSR: tuples -> sorted (key, idx) -> edges
 int besst_launch_graph(besst_ctx* ctx, const besst_lib_params& p, const besst_link_tuple* d_tuples, int64_t n_tuples,

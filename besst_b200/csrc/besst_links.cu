@@ -8,11 +8,10 @@
 //
 // Design (HBM-bound streaming, no tensor cores, no inter-CTA waiting):
 //
-//  k_extract_links   one WARP owns a tile of 128 consecutive records (4 per
-//      lane, 128-bit coalesced loads of the SoA columns; the contig table is a
-//      packed 16-byte row, one 128-bit gather per read end, L1/L2 resident
-//      because the BAM is tid-sorted).  No shared memory and no block barrier:
-//      latency is hidden purely by resident warps.  The only order-dependent
+//  k_extract_links_tma   one WARP owns a tile of 128 consecutive records, staged in shared
+//      memory by TMA bulk copies (cp.async.bulk + mbarrier), double buffered per warp; the contig
+//      table is a packed 16-byte row, one 128-bit gather per read end, L1/L2 resident because the
+//      BAM is tid-sorted.  No block barrier in the main loop.  The only order-dependent
 //      state of the reference -- "(obs1,obs2) of the previous CreateEdge call"
 //      -- is a rightmost-non-empty scan: inside the tile it is done with warp
 //      shuffles; across tiles only the FIRST eligible record of a tile depends
@@ -26,7 +25,7 @@
 //  k_compact_tuples  copies each tile's run to its final position (16-byte
 //      loads/stores), dropping a boundary duplicate.
 //
-// Coverage uses __match_any_sync warp-aggregated 64-bit atomics; counters stay
+// Coverage uses warp-aggregated 64-bit atomics; counters stay
 // in registers for the life of a warp and are flushed once.
 #include <math.h>
 #include <stdlib.h>
@@ -38,7 +37,6 @@ namespace {
 typedef unsigned long long u64;
 typedef unsigned int u32;
 
-constexpr int K1_THREADS = 256;
 constexpr int WT_ITEMS = 4;
 constexpr int WT = 32 * WT_ITEMS;   // records per warp tile
 constexpr int SC_THREADS = 1024;    // aggregates per scan chunk
@@ -135,245 +133,12 @@ __device__ __forceinline__ int side_only(int cdir, int read_fwd, int orientation
     return (cdir && fwd) || (!cdir && !fwd);
 }
 
-template <bool VEC>
-__device__ __forceinline__ void load_i32x4(const int32_t* p, long long idx, long long n, int (&v)[WT_ITEMS]) {
-    if (VEC) {
-        int4 t = __ldg(reinterpret_cast<const int4*>(p + idx));
-        v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
-    } else {
-#pragma unroll
-        for (int i = 0; i < WT_ITEMS; ++i) v[i] = (idx + i < n) ? __ldg(p + idx + i) : -1;
-    }
-}
-
 __device__ __forceinline__ int row_state(int x) { return x & 3; }
 __device__ __forceinline__ int row_dir(int x) { return (x >> 2) & 1; }
 __device__ __forceinline__ int row_scaf(int x) { return (int)((u32)x >> 3); }
 
-// candidates of one tile, compacted in BAM order (one slot per CreateEdge call)
-struct CandSmem {
-    int tid[WT], mtid[WT], pos[WT], mpos[WT];
-    u32 fm[WT];   // flag | mapq << 16 | large-large << 24
-};
-
-template <bool VEC, bool INT_RL>
-__global__ void __launch_bounds__(K1_THREADS) k_extract_links(const K1Params P) {
-    __shared__ u64 s_cnt[8];
-    __shared__ CandSmem s_cand[K1_THREADS / 32];
-    const int lane = threadIdx.x & 31;
-    const u32 lt_mask = (1u << lane) - 1u;
-    CandSmem& C = s_cand[threadIdx.x >> 5];
-    int c_count = 0, c_nonuniq = 0, c_nonuniq_scaf = 0, c_dups = 0, c_toolong = 0, c_fishy = 0, c_calls = 0, c_valid = 0;
-    if (threadIdx.x < 8) s_cnt[threadIdx.x] = 0;
-    const long long n = P.rec.n;
-    const long long warp_global = ((long long)blockIdx.x * K1_THREADS + threadIdx.x) >> 5;
-    const long long n_warps = ((long long)gridDim.x * K1_THREADS) >> 5;
-
-    for (long long wt = warp_global; wt < P.n_tiles; wt += n_warps) {
-        const long long idx0 = wt * WT + (long long)lane * WT_ITEMS;
-        const bool full = VEC && ((wt + 1) * WT <= n);
-
-        int tid[WT_ITEMS], mtid[WT_ITEMS], qlen[WT_ITEMS];
-        u32 flag[WT_ITEMS], mapq[WT_ITEMS];
-        if (full) {
-            load_i32x4<true>(P.rec.tid, idx0, n, tid);
-            load_i32x4<true>(P.rec.mtid, idx0, n, mtid);
-            load_i32x4<true>(P.rec.qlen, idx0, n, qlen);
-            const uint2 f = __ldg(reinterpret_cast<const uint2*>(P.rec.flag + idx0));
-            flag[0] = f.x & 0xffffu; flag[1] = f.x >> 16; flag[2] = f.y & 0xffffu; flag[3] = f.y >> 16;
-            const u32 m = __ldg(reinterpret_cast<const u32*>(P.rec.mapq + idx0));
-            mapq[0] = m & 0xffu; mapq[1] = (m >> 8) & 0xffu; mapq[2] = (m >> 16) & 0xffu; mapq[3] = m >> 24;
-        } else {
-            load_i32x4<false>(P.rec.tid, idx0, n, tid);
-            load_i32x4<false>(P.rec.mtid, idx0, n, mtid);
-            load_i32x4<false>(P.rec.qlen, idx0, n, qlen);
-#pragma unroll
-            for (int i = 0; i < WT_ITEMS; ++i) {
-                flag[i] = (idx0 + i < n) ? __ldg(P.rec.flag + idx0 + i) : 0u;
-                mapq[i] = (idx0 + i < n) ? __ldg(P.rec.mapq + idx0 + i) : 0u;
-            }
-        }
-
-        // ---- per-record classification (CreateGraph.py:118-206); only word 0 of a row is needed ----
-        u32 elig = 0, ll = 0, cov = 0;   // one bit per item
-#pragma unroll
-        for (int i = 0; i < WT_ITEMS; ++i) {
-            bool ok = tid[i] >= 0 && mtid[i] >= 0 && tid[i] < P.n_contigs && mtid[i] < P.n_contigs;       // :118-124
-            int x1 = 0, x2 = 0;
-            if (ok) {
-                x1 = __ldg(reinterpret_cast<const int*>(P.rows + tid[i]));
-                x2 = (mtid[i] == tid[i]) ? x1 : __ldg(reinterpret_cast<const int*>(P.rows + mtid[i]));
-                ok = row_state(x1) != BESST_CTG_ABSENT && row_state(x2) != BESST_CTG_ABSENT;              // :127-130
-            }
-            if (!ok) continue;
-            c_valid++;
-            const u32 f = flag[i];
-            const bool unmapped = f & 0x4u, read1 = f & 0x40u, read2 = f & 0x80u;
-            const int mq = (int)mapq[i];
-            if ((mq >= P.min_mapq) || mq == 0) cov |= 1u << i;                                            // :138
-            if (tid[i] == mtid[i]) continue;   // same contig: same scaffold, no link, no fishy pair
-            const bool diff_scaf = row_scaf(x1) != row_scaf(x2);
-            if (unmapped && read1 && diff_scaf) {                                                         // :141-163
-                const u32 n1 = 2u * (u32)row_scaf(x1) + (u32)side_only(row_dir(x1), !(f & 0x10u), P.orientation);
-                const u32 n2 = 2u * (u32)row_scaf(x2) + (u32)side_only(row_dir(x2), !(f & 0x20u), P.orientation);
-                const u64 key = n1 < n2 ? (((u64)n1 << 32) | n2) : (((u64)n2 << 32) | n1);
-                const u64 slot = atomicAdd(&P.globals[1], 1ull);
-                if ((long long)slot < P.fishy_cap) P.fishy[slot] = key;
-                c_fishy++;
-            }
-            if (mq == 0) c_nonuniq++;                                                                     // :166-167
-            if (read2 && !unmapped && mq >= P.min_mapq) {                                                 // :169
-                const bool l1 = row_state(x1) == BESST_CTG_LARGE, l2 = row_state(x2) == BESST_CTG_LARGE;
-                if (l1 && l2) {
-                    if (diff_scaf) { elig |= 1u << i; ll |= 1u << i; }                                    // :170
-                } else if (P.extend) {                                                                    // :184-206
-                    if (!(l1 || l2) ? diff_scaf : true) elig |= 1u << i;
-                }
-            }
-        }
-
-        // ---- coverage: warp-aggregated 64-bit atomics (:138-139) ----------------------------
-        {
-            int t0 = -1, s0 = 0;
-#pragma unroll
-            for (int i = 0; i < WT_ITEMS; ++i)
-                if (cov >> i & 1u) {
-                    if (t0 < 0) t0 = tid[i];
-                    if (tid[i] == t0) { s0 += qlen[i]; cov &= ~(1u << i); }
-                }
-            const u32 act = __ballot_sync(0xffffffffu, t0 >= 0);
-            if (t0 >= 0) {
-                const u32 peers = __match_any_sync(act, t0);
-                const int sum = __reduce_add_sync(peers, s0);
-                if (lane == __ffs(peers) - 1) atomicAdd(&P.aligned[t0], (u64)(long long)sum);
-            }
-            if (__any_sync(0xffffffffu, cov != 0)) {   // a lane's 4 records straddle contigs: rare
-#pragma unroll
-                for (int i = 1; i < WT_ITEMS; ++i)
-                    if (cov >> i & 1u) atomicAdd(&P.aligned[tid[i]], (u64)(long long)qlen[i]);
-            }
-        }
-
-        // ---- compact the CreateEdge candidates of the tile, BAM order, one per lane ------------
-        const int my_c = __popc(elig);
-        int incl_c = my_c;
-#pragma unroll
-        for (int off = 1; off < 32; off <<= 1) {
-            const int t = __shfl_up_sync(0xffffffffu, incl_c, off);
-            if (lane >= off) incl_c += t;
-        }
-        const int total_c = __shfl_sync(0xffffffffu, incl_c, 31);
-        int n_out = 0;
-        u32 first_flags = 0;
-        int first_o1 = 0, first_o2 = 0, carry_o1 = 0, carry_o2 = 0;
-        if (total_c > 0) {
-            int pos[WT_ITEMS], mpos[WT_ITEMS];
-            if (full) {
-                load_i32x4<true>(P.rec.pos, idx0, n, pos);
-                load_i32x4<true>(P.rec.mpos, idx0, n, mpos);
-            } else {
-                load_i32x4<false>(P.rec.pos, idx0, n, pos);
-                load_i32x4<false>(P.rec.mpos, idx0, n, mpos);
-            }
-            int slot = incl_c - my_c;
-#pragma unroll
-            for (int i = 0; i < WT_ITEMS; ++i)
-                if (elig >> i & 1u) {
-                    C.tid[slot] = tid[i]; C.mtid[slot] = mtid[i]; C.pos[slot] = pos[i]; C.mpos[slot] = mpos[i];
-                    C.fm[slot] = flag[i] | (mapq[i] << 16) | ((ll >> i & 1u) << 24);
-                    ++slot;
-                }
-            __syncwarp();
-
-            // ---- CreateEdge, one call per lane: observations (:816-833), duplicate test against the
-            // previous call (:835-838), acceptance test (:840), counters.  The tile's first call has no
-            // in-tile predecessor: assumed "not a duplicate" here and settled by the aggregate scan.
-            bool have_carry = false;
-            for (int r = 0; r < total_c; r += 32) {
-                const int k = r + lane;
-                const bool active = k < total_c;
-                int o1 = 0, o2 = 0;
-                u32 nu = 0, nv = 0, fm = 0;
-                if (active) {
-                    const int t1 = C.tid[k], t2 = C.mtid[k];
-                    fm = C.fm[k];
-                    const int4 r1 = __ldg(P.rows + t1);   // L1 hits: word 0 was gathered a moment ago
-                    const int4 r2 = __ldg(P.rows + t2);
-                    int s1, s2;
-                    pos_dir<INT_RL>(row_dir(r1.x), !(fm & 0x10u), P.orientation, r1.y, C.pos[k], r1.w, r1.z, P.read_len, P.read_len_i, o1, s1);
-                    pos_dir<INT_RL>(row_dir(r2.x), !(fm & 0x20u), P.orientation, r2.y, C.mpos[k], r2.w, r2.z, P.read_len, P.read_len_i, o2, s2);
-                    nu = 2u * (u32)row_scaf(r1.x) + (u32)s1;
-                    nv = 2u * (u32)row_scaf(r2.x) + (u32)s2;
-                }
-                int p1 = __shfl_up_sync(0xffffffffu, o1, 1), p2 = __shfl_up_sync(0xffffffffu, o2, 1);
-                bool has_prev = true;
-                if (lane == 0) { p1 = carry_o1; p2 = carry_o2; has_prev = have_carry; }
-                bool accepted = false;
-                if (active) {
-                    c_calls++;
-                    const bool mq0 = ((fm >> 16) & 0xffu) == 0;
-                    if (mq0) c_nonuniq_scaf++;
-                    const bool dup = has_prev && o1 == p1 && o2 == p2;
-                    bool is_dupl = false;
-                    if (dup) { c_dups++; is_dupl = P.detect_dup; }
-                    const bool pass = ((long long)o1 + o2) < P.threshold_i && o1 > 25 && o2 > 25;
-                    const bool second = ((fm >> 24) & 1u) && P.extend && P.scoring;
-                    if (!has_prev) {   // the tile's first call
-                        first_flags = AGG_HAS | (pass ? AGG_PASS : 0u) | (second ? AGG_SECOND : 0u) | (mq0 ? AGG_MQ0 : 0u);
-                        first_o1 = o1; first_o2 = o2;
-                    }
-                    if (!is_dupl) {
-                        if (pass) { c_count++; accepted = true; } else c_toolong++;
-                        if (second) {   // second call into G_prime (:180-183); prev_obs was reset to -1
-                            if (mq0) c_nonuniq_scaf++;
-                            const bool dup2 = (o1 == -1 && o2 == -1);
-                            if (dup2) c_dups++;
-                            if (!(dup2 && P.detect_dup)) { if (pass) c_count++; else c_toolong++; }
-                        }
-                    }
-                }
-                const u32 bal = __ballot_sync(0xffffffffu, accepted);
-                if (accepted) {
-                    int4 t;
-                    if (nu < nv) { t.x = (int)nu; t.y = (int)nv; t.z = o1; t.w = o2; }
-                    else { t.x = (int)nv; t.y = (int)nu; t.z = o2; t.w = o1; }
-                    reinterpret_cast<int4*>(P.scratch)[wt * WT + n_out + __popc(bal & lt_mask)] = t;
-                }
-                n_out += __popc(bal);
-                const int last_lane = (total_c - r > 32) ? 31 : (total_c - r - 1);
-                carry_o1 = __shfl_sync(0xffffffffu, o1, last_lane);
-                carry_o2 = __shfl_sync(0xffffffffu, o2, last_lane);
-                have_carry = true;
-            }
-            __syncwarp();   // the candidate slots are reused by the next tile
-        }
-
-        // ---- aggregate (the first call of the tile sits in lane 0 of the first round) -----------------
-        if (lane == 0) {
-            int4* a = reinterpret_cast<int4*>(P.aggs + wt);
-            a[0] = make_int4((int)first_flags, first_o1, first_o2, carry_o1);
-            a[1] = make_int4(carry_o2, n_out, 0, 0);
-            a[2] = make_int4(0, 0, 0, 0);
-        }
-    }
-
-    // ---- flush the per-thread counters ------------------------------------------------------------
-    __syncthreads();
-    const int local_cnt[8] = {c_count, c_nonuniq, c_nonuniq_scaf, c_dups, c_toolong, c_fishy, c_calls, c_valid};
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-        int v = local_cnt[k];
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
-        if (lane == 0 && v) atomicAdd(&s_cnt[k], (u64)(long long)v);
-    }
-    __syncthreads();
-    if (threadIdx.x < 8 && s_cnt[threadIdx.x]) atomicAdd(&P.counters[threadIdx.x], s_cnt[threadIdx.x]);
-}
-
-// ---- K1, TMA-staged variant ---------------------------------------------------------------------
-// Same algorithm as k_extract_links; what changes is how the record columns reach the SM and how the
-// per-record work is laid out:
+// ---- K1 -------------------------------------------------------------------------------------------
+// How the record columns reach the SM and how the per-record work is laid out:
 //  * every warp owns two shared-memory stages of one 128-record tile (7 columns, 2944 B).  Lane 0
 //    issues the tile after next with cp.async.bulk (TMA, 1-D) completing on a per-stage mbarrier,
 //    so a warp always has a whole tile in flight while it works on the current one and no register
@@ -1120,9 +885,14 @@ int besst_launch_partition(besst_ctx* ctx, int world, besst_link_tuple* out_tupl
     return partition_impl<false>(ctx, ctx->fishy_keys.p, ctx->n_fishy_keys, world, out_fishy, nullptr, fishy_counts);
 }
 
-int besst_launch_extract(besst_ctx* ctx, const besst_lib_params& p, const DeviceRecords& rec) {
-    const int64_t n = rec.n;
-    const int64_t n_tiles = (n + WT - 1) / WT;
+// ---- launcher: begin / slice* / finish --------------------------------------------------------------
+// The record range can be fed in slices (besst_extract_slice, r0 a multiple of the tile size) so
+// that a host-buffer call overlaps the H2D copy of slice k+1 with K1 on slice k.
+static int64_t tiles_of(int64_t n) { return (n + WT - 1) / WT; }
+
+int besst_extract_begin(besst_ctx* ctx, const besst_lib_params& p, int64_t n) {
+    (void)p;
+    const int64_t n_tiles = tiles_of(n);
     const int64_t n_chunks = (n_tiles + SC_THREADS - 1) / SC_THREADS;
     if (n_chunks > 0x7fffffff) { ctx->err = "too many records for one call"; return BESST_E_INVALID; }
     BESST_CUDA_TRY(ctx, ctx->aligned.ensure(sizeof(u64) * (size_t)(ctx->n_contigs + 1)));
@@ -1131,93 +901,120 @@ int besst_launch_extract(besst_ctx* ctx, const besst_lib_params& p, const Device
     BESST_CUDA_TRY(ctx, ctx->tile_state.ensure(sizeof(u64) * (size_t)(n_tiles + 2) + sizeof(ChunkIn) * (size_t)(n_chunks + 1)));
     BESST_CUDA_TRY(ctx, ctx->scratch_tuples.ensure(sizeof(besst_link_tuple) * (size_t)(n_tiles > 0 ? n_tiles : 1) * WT));
     if (ctx->fishy_cap == 0) ctx->fishy_cap = n / 8 + 4096;
+    BESST_CUDA_TRY(ctx, ctx->fishy_keys.ensure(sizeof(u64) * (size_t)ctx->fishy_cap));
+    BESST_CUDA_TRY(ctx, cudaMemsetAsync(ctx->aligned.p, 0, sizeof(u64) * (size_t)(ctx->n_contigs + 1), ctx->stream));
+    BESST_CUDA_TRY(ctx, cudaMemsetAsync(ctx->counters.p, 0, sizeof(u64) * (BESST_N_COUNTERS + 8), ctx->stream));
+    return BESST_OK;
+}
 
+// K1 over records [r0, r1) of `rec` (device pointers to the WHOLE batch); r0 must be a multiple of 128
+int besst_extract_slice(besst_ctx* ctx, const besst_lib_params& p, const DeviceRecords& rec, int64_t r0, int64_t r1) {
+    if (r1 <= r0) return BESST_OK;
+    if (r0 % WT) { ctx->err = "extract slice: unaligned start"; return BESST_E_INVALID; }
+    const int64_t tile0 = r0 / WT, n_tiles = tiles_of(r1 - r0);
+    u64* counters = ctx->counters.as<u64>();
+    u64* globals = counters + BESST_N_COUNTERS;
+    K1Params P;
+    P.rec.n = r1 - r0;
+    P.rec.tid = rec.tid + r0; P.rec.mtid = rec.mtid + r0; P.rec.pos = rec.pos + r0; P.rec.mpos = rec.mpos + r0;
+    P.rec.qlen = rec.qlen + r0; P.rec.flag = rec.flag + r0; P.rec.mapq = rec.mapq + r0; P.rec.tlen = nullptr;
     bool vec = true;
-    const void* ptrs[] = {rec.tid, rec.mtid, rec.pos, rec.mpos, rec.qlen, rec.flag, rec.mapq};
+    const void* ptrs[] = {P.rec.tid, P.rec.mtid, P.rec.pos, P.rec.mpos, P.rec.qlen, P.rec.flag, P.rec.mapq};
     for (const void* q : ptrs) vec = vec && ((reinterpret_cast<uintptr_t>(q) & 15u) == 0);
-
     const bool int_rl = p.read_len >= 0 && p.read_len < 1e9 && p.read_len == (double)(long long)p.read_len;
-    typedef void (*K1Fn)(const K1Params);
-    const K1Fn k1 = vec ? (int_rl ? k_extract_links<true, true> : k_extract_links<true, false>)
-                        : (int_rl ? k_extract_links<false, true> : k_extract_links<false, false>);
-    // BESST_K1_LEGACY=1 selects the register-staged kernel (A/B measurements); default is the TMA-staged one
-    static const bool legacy = [] { const char* e = getenv("BESST_K1_LEGACY"); return e && e[0] == '1'; }();
-    typedef void (*K1TFn)(const K1Params, const int);
-    const K1TFn k1t = int_rl ? k_extract_links_tma<true> : k_extract_links_tma<false>;
-    const size_t k1t_smem = sizeof(WarpSmem) * K1T_WARPS;
-    const int k1_threads = legacy ? K1_THREADS : K1T_THREADS;
+    P.rows = ctx->rows_packed.as<int4>();
+    P.n_contigs = (int)ctx->n_contigs;
+    P.orientation = p.orientation; P.min_mapq = p.min_mapq; P.detect_dup = p.detect_duplicate;
+    P.extend = p.extend_paths; P.scoring = !p.no_score;
+    P.read_len = p.read_len;
+    P.read_len_i = int_rl ? (int)p.read_len : 0;
+    {   // integer form of the acceptance threshold (exact for integer sums; NaN never accepts)
+        const double t = p.ins_size_threshold;
+        if (t != t) P.threshold_i = -(1ll << 62);
+        else if (t >= 4e18) P.threshold_i = (1ll << 62);
+        else if (t <= -4e18) P.threshold_i = -(1ll << 62);
+        else P.threshold_i = (long long)ceil(t);
+    }
+    P.scratch = ctx->scratch_tuples.as<besst_link_tuple>() + tile0 * WT;
+    P.aggs = ctx->tile_aggs.as<Agg>() + tile0;
+    P.fishy = ctx->fishy_keys.as<u64>(); P.fishy_cap = ctx->fishy_cap;
+    P.aligned = ctx->aligned.as<u64>();
+    P.counters = counters;
+    P.globals = globals;
+    P.n_tiles = n_tiles;
+
+    typedef void (*K1Fn)(const K1Params, const int);
+    const K1Fn k1 = int_rl ? k_extract_links_tma<true> : k_extract_links_tma<false>;
+    const size_t smem = sizeof(WarpSmem) * K1T_WARPS;
     int per_sm = 0;
-    if (legacy) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k1, K1_THREADS, 0);
-    else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k1t, K1T_THREADS, k1t_smem);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k1, K1T_THREADS, smem);
     if (per_sm < 1) per_sm = 1;
     long long grid = (long long)ctx->sm_count * per_sm;
-    const long long max_grid = (n_tiles + (k1_threads / 32) - 1) / (k1_threads / 32);
+    const long long max_grid = (n_tiles + (long long)K1T_WARPS * K1T_BATCH - 1) / ((long long)K1T_WARPS * K1T_BATCH);
     if (grid > max_grid) grid = max_grid > 0 ? max_grid : 1;
+    BESST_CUDA_TRY(ctx, cudaMemsetAsync(globals + 2, 0, sizeof(u64), ctx->stream));   // the tile ticket
+    {
+        KTimer kt(ctx, BESST_K_EXTRACT);
+        k1<<<(unsigned)grid, K1T_THREADS, smem, ctx->stream>>>(P, vec ? 1 : 0);
+    }
+    BESST_CUDA_TRY(ctx, cudaGetLastError());
+    return BESST_OK;
+}
 
+// scan of the tile aggregates, sizes to the host, compaction.  *overflow: the fishy-key buffer was
+// too small (it has been grown; run begin/slice/finish again)
+int besst_extract_finish(besst_ctx* ctx, const besst_lib_params& p, int64_t n, bool* overflow) {
+    *overflow = false;
+    const int64_t n_tiles = tiles_of(n);
+    const int64_t n_chunks = (n_tiles + SC_THREADS - 1) / SC_THREADS;
     Agg* aggs = ctx->tile_aggs.as<Agg>();
     Agg* chunk_aggs = aggs + n_tiles + 1;
     u64* tile_off = ctx->tile_state.as<u64>();
     ChunkIn* chunk_in = reinterpret_cast<ChunkIn*>(tile_off + n_tiles + 2);
     u64* counters = ctx->counters.as<u64>();
     u64* globals = counters + BESST_N_COUNTERS;
-
-    for (int attempt = 0; attempt < 3; ++attempt) {
-        BESST_CUDA_TRY(ctx, ctx->fishy_keys.ensure(sizeof(u64) * (size_t)ctx->fishy_cap));
-        BESST_CUDA_TRY(ctx, cudaMemsetAsync(ctx->aligned.p, 0, sizeof(u64) * (size_t)(ctx->n_contigs + 1), ctx->stream));
-        BESST_CUDA_TRY(ctx, cudaMemsetAsync(counters, 0, sizeof(u64) * (BESST_N_COUNTERS + 8), ctx->stream));
-        K1Params P;
-        P.rec = rec;
-        P.rows = ctx->rows_packed.as<int4>();
-        P.n_contigs = (int)ctx->n_contigs;
-        P.orientation = p.orientation; P.min_mapq = p.min_mapq; P.detect_dup = p.detect_duplicate;
-        P.extend = p.extend_paths; P.scoring = !p.no_score;
-        P.read_len = p.read_len;
-        P.read_len_i = int_rl ? (int)p.read_len : 0;
-        {   // integer form of the acceptance threshold (exact for integer sums; NaN never accepts)
-            const double t = p.ins_size_threshold;
-            if (t != t) P.threshold_i = -(1ll << 62);
-            else if (t >= 4e18) P.threshold_i = (1ll << 62);
-            else if (t <= -4e18) P.threshold_i = -(1ll << 62);
-            else P.threshold_i = (long long)ceil(t);
-        }
-        P.scratch = ctx->scratch_tuples.as<besst_link_tuple>();
-        P.aggs = aggs;
-        P.fishy = ctx->fishy_keys.as<u64>(); P.fishy_cap = ctx->fishy_cap;
-        P.aligned = ctx->aligned.as<u64>();
-        P.counters = counters;
-        P.globals = globals;
-        P.n_tiles = n_tiles;
-        if (n_tiles > 0) {
-            {
-                KTimer kt(ctx, BESST_K_EXTRACT);
-                if (legacy) k1<<<(unsigned)grid, K1_THREADS, 0, ctx->stream>>>(P);
-                else k1t<<<(unsigned)grid, K1T_THREADS, k1t_smem, ctx->stream>>>(P, vec ? 1 : 0);
-            }
-            { KTimer kt(ctx, BESST_K_TILE_SCAN); k_tile_reduce<<<(unsigned)n_chunks, SC_THREADS, 0, ctx->stream>>>(aggs, n_tiles, chunk_aggs, p.detect_duplicate); }
-            { KTimer kt(ctx, BESST_K_TILE_SCAN); k_chunk_resolve<<<1, SC_THREADS, 0, ctx->stream>>>(chunk_aggs, n_chunks, chunk_in, tile_off + n_tiles, p.halo_prev_obs1, p.halo_prev_obs2, p.detect_duplicate, counters, globals); }
-            { KTimer kt(ctx, BESST_K_TILE_SCAN); k_tile_offsets<<<(unsigned)n_chunks, SC_THREADS, 0, ctx->stream>>>(aggs, n_tiles, chunk_in, tile_off, p.detect_duplicate); }
-            BESST_CUDA_TRY(ctx, cudaGetLastError());
-        } else {
-            const int64_t halo[2] = {p.halo_prev_obs1, p.halo_prev_obs2};
-            BESST_CUDA_TRY(ctx, cudaMemcpyAsync(counters + BESST_CNT_LAST_OBS1, halo, sizeof(halo), cudaMemcpyHostToDevice, ctx->stream));
-        }
-        u64 g[2] = {0, 0};
-        BESST_CUDA_TRY(ctx, cudaMemcpyAsync(g, globals, sizeof(g), cudaMemcpyDeviceToHost, ctx->stream));
-        BESST_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-        ctx->n_tuples = (int64_t)g[0];
-        ctx->n_fishy_keys = (int64_t)g[1];
-        if (ctx->n_fishy_keys > ctx->fishy_cap) { ctx->fishy_cap = ctx->n_fishy_keys + 4096; continue; }
-        BESST_CUDA_TRY(ctx, ctx->tuples.ensure(sizeof(besst_link_tuple) * (size_t)(ctx->n_tuples > 0 ? ctx->n_tuples : 1)));
-        if (ctx->n_tuples > 0) {
-            long long cgrid = (long long)ctx->sm_count * 8;
-            const long long cmax = (n_tiles + 7) / 8;
-            if (cgrid > cmax) cgrid = cmax;
-            KTimer kt(ctx, BESST_K_COMPACT);
-            k_compact_tuples<<<(unsigned)cgrid, 256, 0, ctx->stream>>>(P.scratch, tile_off, n_tiles, ctx->tuples.as<besst_link_tuple>());
-            BESST_CUDA_TRY(ctx, cudaGetLastError());
-        }
-        ctx->have_links = true;
+    if (n_tiles > 0) {
+        { KTimer kt(ctx, BESST_K_TILE_SCAN); k_tile_reduce<<<(unsigned)n_chunks, SC_THREADS, 0, ctx->stream>>>(aggs, n_tiles, chunk_aggs, p.detect_duplicate); }
+        { KTimer kt(ctx, BESST_K_TILE_SCAN); k_chunk_resolve<<<1, SC_THREADS, 0, ctx->stream>>>(chunk_aggs, n_chunks, chunk_in, tile_off + n_tiles, p.halo_prev_obs1, p.halo_prev_obs2, p.detect_duplicate, counters, globals); }
+        { KTimer kt(ctx, BESST_K_TILE_SCAN); k_tile_offsets<<<(unsigned)n_chunks, SC_THREADS, 0, ctx->stream>>>(aggs, n_tiles, chunk_in, tile_off, p.detect_duplicate); }
+        BESST_CUDA_TRY(ctx, cudaGetLastError());
+    } else {
+        const int64_t halo[2] = {p.halo_prev_obs1, p.halo_prev_obs2};
+        BESST_CUDA_TRY(ctx, cudaMemcpyAsync(counters + BESST_CNT_LAST_OBS1, halo, sizeof(halo), cudaMemcpyHostToDevice, ctx->stream));
+    }
+    u64 g[2] = {0, 0};
+    BESST_CUDA_TRY(ctx, cudaMemcpyAsync(g, globals, sizeof(g), cudaMemcpyDeviceToHost, ctx->stream));
+    BESST_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->n_tuples = (int64_t)g[0];
+    ctx->n_fishy_keys = (int64_t)g[1];
+    if (ctx->n_fishy_keys > ctx->fishy_cap) {
+        ctx->fishy_cap = ctx->n_fishy_keys + 4096;
+        *overflow = true;
         return BESST_OK;
+    }
+    BESST_CUDA_TRY(ctx, ctx->tuples.ensure(sizeof(besst_link_tuple) * (size_t)(ctx->n_tuples > 0 ? ctx->n_tuples : 1)));
+    if (ctx->n_tuples > 0) {
+        long long cgrid = (long long)ctx->sm_count * 8;
+        const long long cmax = (n_tiles + 7) / 8;
+        if (cgrid > cmax) cgrid = cmax;
+        KTimer kt(ctx, BESST_K_COMPACT);
+        k_compact_tuples<<<(unsigned)cgrid, 256, 0, ctx->stream>>>(ctx->scratch_tuples.as<besst_link_tuple>(), tile_off, n_tiles, ctx->tuples.as<besst_link_tuple>());
+        BESST_CUDA_TRY(ctx, cudaGetLastError());
+    }
+    ctx->have_links = true;
+    return BESST_OK;
+}
+
+int besst_launch_extract(besst_ctx* ctx, const besst_lib_params& p, const DeviceRecords& rec) {
+    for (int attempt = 0; attempt < 3; ++attempt) {
+        int rc = besst_extract_begin(ctx, p, rec.n);
+        if (rc) return rc;
+        rc = besst_extract_slice(ctx, p, rec, 0, rec.n);
+        if (rc) return rc;
+        bool overflow = false;
+        rc = besst_extract_finish(ctx, p, rec.n, &overflow);
+        if (rc) return rc;
+        if (!overflow) return BESST_OK;
     }
     ctx->err = "link extraction: fishy-key capacity retry failed";
     return BESST_E_STATE;

@@ -62,6 +62,14 @@ class CudaEngine(object):
         self._check(self._L.besst_graph_fetch(self._ctx, C.byref(out)), "besst_graph_fetch")
         return abi.graph_result(out, arrays)
 
+    def fetch_view(self, sizes):
+        """Like fetch, but the arrays are zero-copy views of pinned buffers owned by the engine:
+        valid until the next fetch_view / close.  The fast path for a caller that consumes the
+        result right away (CreateGraph.PE materialising networkx graphs, bench.py)."""
+        out = abi.GraphOut()
+        self._check(self._L.besst_graph_view(self._ctx, C.byref(out)), "besst_graph_view")
+        return abi.graph_result(out, abi.view_graph_out(out, sizes))
+
     def graph_build(self, table, params, batch):
         """Host-buffer call used by CreateGraph.PE: table + RecordBatch in, GraphResult out."""
         self.set_table(table)

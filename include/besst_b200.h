@@ -47,7 +47,7 @@
 extern "C" {
 #endif
 
-#define BESST_ABI_VERSION 2
+#define BESST_ABI_VERSION 3
 
 #define BESST_OK 0
 #define BESST_E_INVALID -1  /* bad argument */
@@ -207,6 +207,12 @@ int besst_graph_build(besst_ctx* ctx, const besst_lib_params* params,
                       const besst_records* records, besst_graph_sizes* sizes);
 /* copy the last build's result into caller-allocated host arrays */
 int besst_graph_fetch(besst_ctx* ctx, besst_graph_out* out);
+
+/* the same result as zero-copy views: the arrays of `out` are set to PINNED host buffers owned by
+ * the ctx (filled by this call); they stay valid until the next besst_graph_view / besst_destroy on
+ * this ctx.  Avoids the page faults and the bounce buffer of a pageable destination (0.6 GB at
+ * config 3). */
+int besst_graph_view(besst_ctx* ctx, besst_graph_out* out);
 
 /* multi-GPU halves: extract leaves the accepted link tuples (BAM order) in HBM
  * and reports how many; tuples_device returns the device pointer for the NCCL

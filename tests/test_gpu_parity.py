@@ -111,6 +111,42 @@ def test_device_resident_records_equal_host_records(cuda_engine):
     helpers.assert_graph_equal(dev, host, label="device-resident")
 
 
+@pytest.mark.parametrize("slice_records", [128, 1024, 128 * 77])
+def test_sliced_host_copy_equals_one_pass(cuda_engine, slice_records, monkeypatch):
+    """Host-buffer calls copy the record columns slice by slice and run the record kernel on each slice
+    as it lands (H2D overlap): the result must not depend on the slice size."""
+    from besst_b200.engine import CudaEngine
+    lib, batch, params, table = _setup("small_mp_cont")
+    want = cuda_engine.graph_build(table, params, batch)
+    monkeypatch.setenv("BESST_SLICE_RECORDS", str(slice_records))
+    eng = CudaEngine()
+    try:
+        for n in (len(batch), 5 * slice_records + 1, slice_records + 127):
+            sub = batch.slice(0, min(n, len(batch)))
+            ref = cuda_engine.graph_build(table, params, sub) if n < len(batch) else want
+            got = eng.graph_build(table, params, sub)
+            helpers.assert_graph_equal(got, ref, label="slice=%d n=%d" % (slice_records, n))
+    finally:
+        eng.close()
+
+
+def test_fetch_view_equals_fetch(cuda_engine):
+    lib, batch, params, table = _setup("small_pe")
+    cuda_engine.set_table(table)
+    keep = []
+    sizes = cuda_engine.build(params, abi.make_records(batch, keepalive=keep))
+    a = cuda_engine.fetch(sizes)
+    b = cuda_engine.fetch_view(sizes)
+    helpers.assert_graph_equal(b, a, label="view")
+    # views are reused by the next view call, copies are not
+    sub = batch.slice(0, 2000)
+    keep2 = []
+    s2 = cuda_engine.build(params, abi.make_records(sub, keepalive=keep2))
+    c = cuda_engine.fetch_view(s2)
+    assert c.n_edges <= a.n_edges and c.counters[abi.CNT_VALID] <= a.counters[abi.CNT_VALID]
+    helpers.assert_graph_equal(cuda_engine.fetch(s2), c, label="view after rebuild")
+
+
 def test_two_slices_with_halo_equal_one_pass(cuda_engine):
     """The multi-GPU decomposition on one GPU: records cut into BAM-order slices, each
     extracted with the previous slice's last CreateEdge observation as halo, tuples
