@@ -229,7 +229,8 @@ def run_ours(args):
         "k_compact_tuples": 2 * TUPLE_BYTES * n_links + 8 * ((n_rec + 127) // 128),
         "k_radix_sweep": (8 + 8) * n_links,       # packed sort word (key | BAM index): 8 B in, 8 B out per pass
         "k_radix_hist": 8 * n_links,
-        "k_edge_reduce": (4 + 16 + 8) * n_links + 64 * n_edges,
+        "k_edge_reduce": (8 + 8) * n_links + 64 * n_edges,    # k_edge_gather: grouped (o1,o2) in, obs_u/obs_v out
+        "k_group_blocks": (16 + 8) * n_links,                 # tuples in, grouped observations out (+ run descriptors)
         "k_score_keys": (8 + 8) * n_ll / 3.0 + 13 * n_edges,   # 3 launches: LL scan (2, over edges) + key build
         "k_ks_sort": (4 + 4) * n_ll,
         "k_ks_eval": (4 + 4) * n_ll + 8 * n_edges,

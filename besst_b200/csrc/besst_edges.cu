@@ -15,6 +15,7 @@
 //      over the 4 lanes of a quad and combined with __shfl_sync; then the score
 //      (CreateGraph.py:603-614).  No tensor cores: there is no contraction here.
 #include <math.h>
+#include <stdlib.h>
 
 #include <algorithm>
 
@@ -198,6 +199,401 @@ __global__ void __launch_bounds__(256)
             E.obs[e] = s;
             E.obs_sq[e] = sq;
             E.first[e] = idx_bits ? (long long)(word & ((1ull << idx_bits) - 1ull)) : (long long)sorted_idx[b];
+            long long f = 0;
+            if (n_fishy > 0) {
+                const long long lo = lower_bound_u64(fishy_sorted, n_fishy, key);
+                const long long hi = lower_bound_u64(fishy_sorted, n_fishy, key + 1);
+                f = hi - lo;
+            }
+            E.fishy[e] = (int)f;
+            const bool ll = u < n_large2 && v < n_large2;
+            E.flags[e] = ll ? BESST_EDGE_LL : 0;
+            E.gap[e] = 0;
+            E.sum_u[e] = su;
+            E.max_v[e] = mv;
+            const double nan = __longlong_as_double(0x7ff8000000000000ll);
+            E.score[e] = nan; E.sd_obs[e] = nan; E.sd_model[e] = nan;
+            E.ks[e] = (ll && scoring) ? 0.0 : nan;   // k_ks_eval accumulates the maximum into it
+        }
+    }
+}
+
+// ---- K3': run-merge bucket ---------------------------------------------------------------------------
+// The tuple stream is in BAM order, i.e. sorted by the record's contig: the links of one edge sit in
+// a few dense stretches of the stream (the stretch of either contig).  A device-wide radix sort
+// ignores that and moves every link five times.  Instead:
+//   k_group_blocks  every CTA takes 2048 consecutive tuples, gives each distinct (u,v) a dense local
+//                   id through a shared-memory hash table, ranks the tuples stably by id (per-warp
+//                   __match_any_sync multisplit + prefix over warps) and writes the block's
+//                   observations grouped by edge, BAM order kept, plus one RUN descriptor per
+//                   (block, edge): key, where the run starts, its length, its first BAM ordinal;
+//   sort            the run descriptors (a few per contig, ~0.6 % of the links at config 3) are radix
+//                   sorted by (u, v, block): runs of one edge become adjacent, in BAM order;
+//   k_run_*         heads / prefix sums over the sorted runs -> edges, row_ptr, where each run goes;
+//   k_edge_gather   one warp per edge copies its runs to their CSR position with coalesced 8-byte
+//                   accesses and reduces nr_links / obs / obs_sq (CreateEdge, CreateGraph.py:842-862).
+// Each link is read twice and written twice.  Input that is not locally ordered makes many runs: the
+// caller falls back to the radix bucket when a block holds more than GB_DMAX edges or the runs
+// exceed a fraction of the links.
+constexpr int GB_THREADS = 256;
+constexpr int GB_WARPS = GB_THREADS / 32;
+constexpr int GB_ITEMS = 8;
+constexpr int GB_TILE = GB_THREADS * GB_ITEMS;   // 2048 tuples per block
+constexpr int GB_HT = 2 * GB_TILE;               // hash slots
+constexpr int GB_DMAX = 512;                     // distinct edges per block
+constexpr u64 GB_EMPTY = ~0ull;
+
+struct GroupSmem {
+    union {
+        u64 ht[GB_HT];          // hash table of (u << 32 | v) ...
+        int2 stage[GB_TILE];    // ... later the observations in grouped order
+    };
+    unsigned short id_of_slot[GB_HT];
+    unsigned short warp_hist[GB_WARPS][GB_DMAX];
+    u64 key_of_id[GB_DMAX];
+    unsigned short start[GB_DMAX + 2];
+    u32 scan_w[GB_WARPS];
+    u32 n_ids, run_base, overflow;
+};
+
+__device__ __forceinline__ u32 gb_insert(u64* ht, u64 key) {
+    u32 h = ((u32)(key >> 32) * 0x9E3779B1u) ^ ((u32)key * 0x85EBCA77u);
+    h = (h >> 11) & (GB_HT - 1);
+    for (;;) {
+        const u64 cur = ht[h];
+        if (cur == key) return h;
+        if (cur == GB_EMPTY) {
+            const u64 old = atomicCAS(reinterpret_cast<unsigned long long*>(ht + h), GB_EMPTY, key);
+            if (old == GB_EMPTY || old == key) return h;
+        }
+        h = (h + 1) & (GB_HT - 1);
+    }
+}
+
+// gstate: [0] = runs so far, [1] = overflow flags (1: a block with too many edges, 2: run capacity)
+__global__ void __launch_bounds__(GB_THREADS, 4)
+    k_group_blocks(const besst_link_tuple* __restrict__ tuples, long long n, int bv, int block_bits, int2* __restrict__ grouped,
+                   u64* __restrict__ run_key, u32* __restrict__ run_val, u32* __restrict__ run_start, u32* __restrict__ run_cnt,
+                   u32* __restrict__ run_first, u32* gstate, u32 run_cap) {
+    extern __shared__ __align__(16) unsigned char gb_smem[];
+    GroupSmem& S = *reinterpret_cast<GroupSmem*>(gb_smem);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const u32 lt_mask = (1u << lane) - 1u;
+    const long long base = (long long)blockIdx.x * GB_TILE;
+    const int count = (n - base < GB_TILE) ? (int)(n - base) : GB_TILE;
+
+    for (int i = threadIdx.x; i < GB_HT; i += GB_THREADS) S.ht[i] = GB_EMPTY;
+    for (int i = threadIdx.x; i < GB_WARPS * GB_DMAX / 2; i += GB_THREADS) reinterpret_cast<u32*>(&S.warp_hist[0][0])[i] = 0;
+    if (threadIdx.x == 0) { S.n_ids = 0; S.overflow = 0; }
+    __syncthreads();
+
+    // ---- phase 1: load, warp-level dedup of the keys, hash insert by one lane per distinct key ----
+    int2 obs[GB_ITEMS];
+    u32 meta[GB_ITEMS];   // slot (12) | lanes of the same key before me (5) << 12 | same-key lanes - 1 (5) << 17 | leader (5) << 22
+#pragma unroll
+    for (int i = 0; i < GB_ITEMS; ++i) {
+        const int p = warp * (32 * GB_ITEMS) + i * 32 + lane;
+        const bool valid = p < count;
+        const u32 vmask = __ballot_sync(0xffffffffu, valid);
+        meta[i] = 0;
+        obs[i] = make_int2(0, 0);
+        if (valid) {
+            const int4 t = __ldg(reinterpret_cast<const int4*>(tuples + base + p));
+            obs[i] = make_int2(t.z, t.w);
+            const u64 key = ((u64)(u32)t.x << 32) | (u32)t.y;
+            const u32 peers = __match_any_sync(vmask, key);
+            const int leader = __ffs(peers) - 1;
+            u32 slot = 0;
+            if (lane == leader) slot = gb_insert(S.ht, key);
+            slot = __shfl_sync(vmask, slot, leader);
+            meta[i] = slot | ((u32)__popc(peers & lt_mask) << 12) | ((u32)(__popc(peers) - 1) << 17) | ((u32)leader << 22);
+        }
+    }
+    __syncthreads();
+
+    // ---- phase 2: dense local ids in slot order --------------------------------------------------
+    {
+        constexpr int PER = GB_HT / GB_THREADS;   // 16 slots per thread
+        u32 used = 0;
+#pragma unroll
+        for (int k = 0; k < PER; ++k) used |= (S.ht[threadIdx.x * PER + k] != GB_EMPTY ? 1u : 0u) << k;
+        const u32 c = (u32)__popc(used);
+        u32 incl = c;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const u32 t = __shfl_up_sync(0xffffffffu, incl, off);
+            if (lane >= off) incl += t;
+        }
+        if (lane == 31) S.scan_w[warp] = incl;
+        __syncthreads();
+        u32 id = incl - c;
+        u32 total = 0;
+#pragma unroll
+        for (int w = 0; w < GB_WARPS; ++w) {
+            if (w < warp) id += S.scan_w[w];
+            total += S.scan_w[w];
+        }
+#pragma unroll
+        for (int k = 0; k < PER; ++k)
+            if (used >> k & 1u) {
+                const int s = threadIdx.x * PER + k;
+                S.id_of_slot[s] = (unsigned short)id;
+                if (id < GB_DMAX) S.key_of_id[id] = S.ht[s];
+                ++id;
+            }
+        if (threadIdx.x == 0) {
+            S.n_ids = total;
+            if (total > GB_DMAX) { S.overflow = 1; atomicOr(gstate + 1, 1u); }
+            else S.run_base = atomicAdd(gstate, total);
+        }
+    }
+    __syncthreads();
+    if (S.overflow) return;   // the caller falls back to the radix bucket
+    const int D = (int)S.n_ids;
+
+    // ---- phase 3: stable rank inside the warp, items in BAM order ------------------------------------
+#pragma unroll
+    for (int i = 0; i < GB_ITEMS; ++i) {
+        const int p = warp * (32 * GB_ITEMS) + i * 32 + lane;
+        const bool valid = p < count;
+        const u32 vmask = __ballot_sync(0xffffffffu, valid);
+        if (valid) {
+            const u32 m = meta[i];
+            const u32 id = S.id_of_slot[m & 0xfffu];
+            const int leader = (int)(m >> 22);
+            u32 pre = 0;
+            if (lane == leader) {
+                pre = S.warp_hist[warp][id];
+                S.warp_hist[warp][id] = (unsigned short)(pre + ((m >> 17) & 31u) + 1u);
+            }
+            pre = __shfl_sync(vmask, pre, leader);
+            meta[i] = id | ((pre + ((m >> 12) & 31u)) << 9);   // id (9) | rank within the warp (<= 255)
+        }
+        __syncwarp();
+    }
+    __syncthreads();
+
+    // ---- phase 4: prefix over warps, starts of the ids, run descriptors ----------------------------------
+    {
+        const int id0 = 2 * threadIdx.x, id1 = id0 + 1;   // GB_DMAX == 2 * GB_THREADS
+        u32 tot0 = 0, tot1 = 0;
+        if (id0 < D) {
+#pragma unroll
+            for (int w = 0; w < GB_WARPS; ++w) { const u32 t = S.warp_hist[w][id0]; S.warp_hist[w][id0] = (unsigned short)tot0; tot0 += t; }
+        }
+        if (id1 < D) {
+#pragma unroll
+            for (int w = 0; w < GB_WARPS; ++w) { const u32 t = S.warp_hist[w][id1]; S.warp_hist[w][id1] = (unsigned short)tot1; tot1 += t; }
+        }
+        const u32 c = tot0 + tot1;
+        u32 incl = c;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const u32 t = __shfl_up_sync(0xffffffffu, incl, off);
+            if (lane >= off) incl += t;
+        }
+        if (lane == 31) S.scan_w[warp] = incl;
+        __syncthreads();
+        u32 st = incl - c;
+#pragma unroll
+        for (int w = 0; w < GB_WARPS; ++w)
+            if (w < warp) st += S.scan_w[w];
+        const u32 rb = S.run_base;
+        if (id0 < D) {
+            S.start[id0] = (unsigned short)st;
+            const u32 r = rb + (u32)id0;
+            if (r < run_cap) {
+                const u64 k = S.key_of_id[id0];
+                run_key[r] = (((k >> 32) << bv | (k & 0xffffffffull)) << block_bits) | (u64)blockIdx.x;
+                run_val[r] = r; run_start[r] = (u32)(base + st); run_cnt[r] = tot0;
+            } else atomicOr(gstate + 1, 2u);
+        }
+        if (id1 < D) {
+            S.start[id1] = (unsigned short)(st + tot0);
+            const u32 r = rb + (u32)id1;
+            if (r < run_cap) {
+                const u64 k = S.key_of_id[id1];
+                run_key[r] = (((k >> 32) << bv | (k & 0xffffffffull)) << block_bits) | (u64)blockIdx.x;
+                run_val[r] = r; run_start[r] = (u32)(base + st + tot0); run_cnt[r] = tot1;
+            } else atomicOr(gstate + 1, 2u);
+        }
+    }
+    __syncthreads();
+
+    // ---- phase 5: final position inside the block; the observations go through shared memory ----------
+    {
+        const u32 rb = S.run_base;
+#pragma unroll
+        for (int i = 0; i < GB_ITEMS; ++i) {
+            const int p = warp * (32 * GB_ITEMS) + i * 32 + lane;
+            if (p < count) {
+                const u32 id = meta[i] & 511u;
+                const u32 in_run = (u32)S.warp_hist[warp][id] + (meta[i] >> 9);
+                S.stage[S.start[id] + in_run] = obs[i];
+                if (in_run == 0 && rb + id < run_cap) run_first[rb + id] = (u32)(base + p);   // the run's first link, BAM order
+            }
+        }
+    }
+    __syncthreads();
+    for (int j = threadIdx.x; j < count; j += GB_THREADS) grouped[base + j] = S.stage[j];
+}
+
+// ---- heads and prefix sums over the sorted runs: packed (heads << 32 | links) ----------------------------
+constexpr int RS_T = 256, RS_I = 8, RS_TILE = RS_T * RS_I;
+
+__global__ void __launch_bounds__(RS_T)
+    k_run_count(const u64* __restrict__ keys, const u32* __restrict__ vals, const u32* __restrict__ run_cnt, long long R,
+                int block_bits, u64* block_sums) {
+    __shared__ u64 s_w[RS_T / 32];
+    const long long base = (long long)blockIdx.x * RS_TILE;
+    u64 c = 0;
+#pragma unroll
+    for (int i = 0; i < RS_I; ++i) {
+        const long long r = base + i * RS_T + threadIdx.x;
+        if (r < R) {
+            const bool head = r == 0 || (keys[r] >> block_bits) != (keys[r - 1] >> block_bits);
+            c += ((u64)(head ? 1u : 0u) << 32) | (u64)__ldg(run_cnt + __ldg(vals + r));
+        }
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) c += __shfl_xor_sync(0xffffffffu, c, off);
+    if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = c;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        u64 t = 0;
+        for (int w = 0; w < RS_T / 32; ++w) t += s_w[w];
+        block_sums[blockIdx.x] = t;
+    }
+}
+
+// single-CTA exclusive scan of packed sums; total -> block_sums[n_blocks]
+__global__ void __launch_bounds__(1024) k_scan_blocks64(u64* block_sums, int n_blocks) {
+    __shared__ u64 s_w[32];
+    __shared__ u64 s_carry;
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int base = 0; base < n_blocks; base += 1024) {
+        const int i = base + threadIdx.x;
+        const u64 v = i < n_blocks ? block_sums[i] : 0;
+        u64 incl = v;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const u64 t = __shfl_up_sync(0xffffffffu, incl, off);
+            if (lane >= off) incl += t;
+        }
+        if (lane == 31) s_w[warp] = incl;
+        __syncthreads();
+        u64 pre = 0, tot = 0;
+        for (int w = 0; w < 32; ++w) { if (w < warp) pre += s_w[w]; tot += s_w[w]; }
+        const u64 carry = s_carry;
+        if (i < n_blocks) block_sums[i] = carry + pre + incl - v;
+        __syncthreads();
+        if (threadIdx.x == 0) s_carry = carry + tot;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) block_sums[n_blocks] = s_carry;
+}
+
+// per sorted run: where its links go (run_off), where they come from (run_src), how many (run_len);
+// per edge (at its first run): row_ptr, first run, u, v, first BAM ordinal
+__global__ void __launch_bounds__(RS_T)
+    k_run_write(const u64* __restrict__ keys, const u32* __restrict__ vals, const u32* __restrict__ run_cnt,
+                const u32* __restrict__ run_start, const u32* __restrict__ run_first, long long R, int block_bits, int bv,
+                const u64* __restrict__ block_sums, u32* run_off, u32* run_src, u32* run_len, long long* row_ptr,
+                u32* edge_run_ptr, u32* edge_u, u32* edge_v, long long* edge_first, long long n_links) {
+    __shared__ u64 s_w[RS_T / 32];
+    const long long base = (long long)blockIdx.x * RS_TILE + (long long)threadIdx.x * RS_I;   // blocked: order kept
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    u64 item[RS_I];
+    u32 val[RS_I];
+    u64 c = 0;
+#pragma unroll
+    for (int i = 0; i < RS_I; ++i) {
+        const long long r = base + i;
+        item[i] = 0; val[i] = 0;
+        if (r < R) {
+            const bool head = r == 0 || (keys[r] >> block_bits) != (keys[r - 1] >> block_bits);
+            val[i] = __ldg(vals + r);
+            item[i] = ((u64)(head ? 1u : 0u) << 32) | (u64)__ldg(run_cnt + val[i]);
+        }
+        c += item[i];
+    }
+    u64 incl = c;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        const u64 t = __shfl_up_sync(0xffffffffu, incl, off);
+        if (lane >= off) incl += t;
+    }
+    if (lane == 31) s_w[warp] = incl;
+    __syncthreads();
+    u64 pos = block_sums[blockIdx.x] + incl - c;
+    for (int w = 0; w < warp; ++w) pos += s_w[w];
+#pragma unroll
+    for (int i = 0; i < RS_I; ++i) {
+        const long long r = base + i;
+        if (r < R) {
+            const u32 link_off = (u32)pos, e = (u32)(pos >> 32);   // exclusive: links before this run, heads before it
+            run_off[r] = link_off;
+            run_src[r] = __ldg(run_start + val[i]);
+            run_len[r] = (u32)item[i];
+            if (item[i] >> 32) {
+                const u64 key = keys[r] >> block_bits;
+                row_ptr[e] = (long long)link_off;
+                edge_run_ptr[e] = (u32)r;
+                edge_u[e] = (u32)(key >> bv);
+                edge_v[e] = (u32)(key & ((1ull << bv) - 1ull));
+                edge_first[e] = (long long)__ldg(run_first + val[i]);
+            }
+        }
+        pos += item[i];
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        const u32 E = (u32)(block_sums[gridDim.x] >> 32);
+        row_ptr[E] = n_links;
+        edge_run_ptr[E] = (u32)R;
+    }
+}
+
+// K4': one warp per edge: copy its runs to CSR order and reduce
+__global__ void __launch_bounds__(256)
+    k_edge_gather(EdgeArrays E, long long n_edges, const int2* __restrict__ grouped, const u32* __restrict__ edge_run_ptr,
+                  const u32* __restrict__ run_off, const u32* __restrict__ run_src, const u32* __restrict__ run_len, int bv,
+                  const u64* __restrict__ fishy_sorted, long long n_fishy, u32 n_large2, int scoring) {
+    const int lane = threadIdx.x & 31;
+    const long long warp_global = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
+    for (long long e = warp_global; e < n_edges; e += n_warps) {
+        const u32 r0 = __ldg(edge_run_ptr + e), r1 = __ldg(edge_run_ptr + e + 1);
+        long long s = 0, sq = 0, su = 0;
+        int mv = -2147483647 - 1;
+        for (u32 r = r0; r < r1; ++r) {
+            const u32 src = __ldg(run_src + r), dst = __ldg(run_off + r), len = __ldg(run_len + r);
+            for (u32 k = lane; k < len; k += 32) {
+                const int2 o = __ldg(grouped + src + k);
+                E.obs_u[dst + k] = o.x;
+                E.obs_v[dst + k] = o.y;
+                const long long t = (long long)o.x + (long long)o.y;
+                s += t;
+                sq += t * t;
+                su += o.x;
+                mv = o.y > mv ? o.y : mv;
+            }
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            s += __shfl_xor_sync(0xffffffffu, s, off);
+            sq += __shfl_xor_sync(0xffffffffu, sq, off);
+            su += __shfl_xor_sync(0xffffffffu, su, off);
+            const int o = __shfl_xor_sync(0xffffffffu, mv, off);
+            mv = o > mv ? o : mv;
+        }
+        if (lane == 0) {
+            const u32 u = E.u[e], v = E.v[e];
+            const u64 key = ((u64)u << bv) | v;
+            E.nr[e] = (int)(E.row_ptr[e + 1] - E.row_ptr[e]);
+            E.obs[e] = s;
+            E.obs_sq[e] = sq;
             long long f = 0;
             if (n_fishy > 0) {
                 const long long lo = lower_bound_u64(fishy_sorted, n_fishy, key);
@@ -596,14 +992,140 @@ int besst_launch_graph(besst_ctx* ctx, const besst_lib_params& p, const besst_li
     const int bv = bits_for((uint64_t)(2 * ctx->n_scaffolds > 0 ? 2 * ctx->n_scaffolds - 1 : 1));
     const size_t nz = (size_t)(n > 0 ? n : 1);
 
-    // ---- K3: radix bucket -------------------------------------------------------------
+    // fishy pairs: rekey, sort (keys only)
+    int rc;
+    const u64* fishy_sorted = nullptr;
+    if (n_fishy > 0) {
+        BESST_CUDA_TRY(ctx, ctx->fishy_sorted.ensure(8 * (size_t)n_fishy));
+        BESST_CUDA_TRY(ctx, ctx->fishy_tmp.ensure(8 * (size_t)n_fishy));
+        { KTimer kt(ctx, BESST_K_FISHY); k_fishy_rekey<<<(int)((n_fishy + 255) / 256), 256, 0, ctx->stream>>>(reinterpret_cast<const u64*>(d_fishy), ctx->fishy_sorted.as<u64>(), n_fishy, bv); }
+        int fb = 0;
+        ctx->sweep_kernel_id = BESST_K_FISHY;   // profiling: keep the small fishy-key sort out of k_radix_sweep
+        rc = besst_radix_sort_keys(ctx, ctx->fishy_sorted.as<uint64_t>(), ctx->fishy_tmp.as<uint64_t>(), n_fishy, 2 * bv, &fb);
+        ctx->sweep_kernel_id = BESST_K_RADIX_SWEEP;
+        if (rc) return rc;
+        fishy_sorted = fb ? ctx->fishy_tmp.as<u64>() : ctx->fishy_sorted.as<u64>();
+    }
+
+    EdgeArrays EA;
+    int64_t E = 0;
+    auto alloc_edges = [&](int64_t n_edges) -> int {
+        E = n_edges;
+        ctx->n_edges = E;
+        const size_t Ez = (size_t)(E > 0 ? E : 1);
+        BESST_CUDA_TRY(ctx, ctx->e_u.ensure(4 * Ez)); BESST_CUDA_TRY(ctx, ctx->e_v.ensure(4 * Ez));
+        BESST_CUDA_TRY(ctx, ctx->e_nr.ensure(4 * Ez)); BESST_CUDA_TRY(ctx, ctx->e_obs.ensure(8 * Ez));
+        BESST_CUDA_TRY(ctx, ctx->e_obs_sq.ensure(8 * Ez)); BESST_CUDA_TRY(ctx, ctx->e_first.ensure(8 * Ez));
+        BESST_CUDA_TRY(ctx, ctx->e_row_ptr.ensure(8 * (Ez + 1))); BESST_CUDA_TRY(ctx, ctx->e_gap.ensure(4 * Ez));
+        BESST_CUDA_TRY(ctx, ctx->e_score.ensure(8 * Ez)); BESST_CUDA_TRY(ctx, ctx->e_ks.ensure(8 * Ez));
+        BESST_CUDA_TRY(ctx, ctx->e_sd_obs.ensure(8 * Ez)); BESST_CUDA_TRY(ctx, ctx->e_sd_model.ensure(8 * Ez));
+        BESST_CUDA_TRY(ctx, ctx->e_fishy.ensure(4 * Ez)); BESST_CUDA_TRY(ctx, ctx->e_flags.ensure(Ez));
+        BESST_CUDA_TRY(ctx, ctx->l_obs_u.ensure(4 * nz)); BESST_CUDA_TRY(ctx, ctx->l_obs_v.ensure(4 * nz));
+        BESST_CUDA_TRY(ctx, ctx->e_sum_u.ensure(8 * Ez)); BESST_CUDA_TRY(ctx, ctx->e_max_v.ensure(4 * Ez));
+        EA.u = ctx->e_u.as<u32>(); EA.v = ctx->e_v.as<u32>(); EA.nr = ctx->e_nr.as<int>();
+        EA.obs = ctx->e_obs.as<long long>(); EA.obs_sq = ctx->e_obs_sq.as<long long>(); EA.first = ctx->e_first.as<long long>();
+        EA.row_ptr = ctx->e_row_ptr.as<long long>(); EA.gap = ctx->e_gap.as<int>(); EA.score = ctx->e_score.as<double>();
+        EA.ks = ctx->e_ks.as<double>(); EA.sd_obs = ctx->e_sd_obs.as<double>(); EA.sd_model = ctx->e_sd_model.as<double>();
+        EA.fishy = ctx->e_fishy.as<int>(); EA.flags = ctx->e_flags.as<unsigned char>();
+        EA.obs_u = ctx->l_obs_u.as<int>(); EA.obs_v = ctx->l_obs_v.as<int>();
+        EA.sum_u = ctx->e_sum_u.as<long long>(); EA.max_v = ctx->e_max_v.as<int>();
+        return BESST_OK;
+    };
+    auto finish_empty = [&]() -> int {
+        const long long zero = 0;
+        BESST_CUDA_TRY(ctx, cudaMemcpyAsync(EA.row_ptr, &zero, 8, cudaMemcpyHostToDevice, ctx->stream));
+        BESST_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+        besst_mark(ctx); besst_mark(ctx); besst_mark(ctx);
+        ctx->have_graph = true;
+        return BESST_OK;
+    };
+    int edge_grid_max = ctx->sm_count * 32;
+
+    // ---- K3'/K4': run-merge bucket (default) ------------------------------------------------------
+    // BESST_BUCKET=radix forces the device-wide radix sort below (A/B measurements, tests of the fallback)
+    const char* bucket_env = getenv("BESST_BUCKET");
+    const bool force_radix = bucket_env && bucket_env[0] == 'r';
+    bool done = false;
+    const int64_t n_gblocks = (n + GB_TILE - 1) / GB_TILE;
+    const int block_bits = bits_for((uint64_t)(n_gblocks > 1 ? n_gblocks - 1 : 1));
+    if (!force_radix && n > 0 && 2 * bv + block_bits <= 64) {
+        const int64_t run_cap64 = std::max<int64_t>(n / 8, 1 << 16);
+        const u32 run_cap = (u32)std::min<int64_t>(run_cap64, 0x7fffffff);
+        BESST_CUDA_TRY(ctx, ctx->grouped.ensure(8 * nz));
+        for (int k = 0; k < 2; ++k) {
+            BESST_CUDA_TRY(ctx, ctx->run_key[k].ensure(8 * (size_t)run_cap));
+            BESST_CUDA_TRY(ctx, ctx->run_val[k].ensure(4 * (size_t)run_cap));
+        }
+        BESST_CUDA_TRY(ctx, ctx->run_start.ensure(4 * (size_t)run_cap)); BESST_CUDA_TRY(ctx, ctx->run_cnt.ensure(4 * (size_t)run_cap));
+        BESST_CUDA_TRY(ctx, ctx->run_first.ensure(4 * (size_t)run_cap)); BESST_CUDA_TRY(ctx, ctx->run_off.ensure(4 * (size_t)run_cap));
+        BESST_CUDA_TRY(ctx, ctx->run_src.ensure(4 * (size_t)run_cap)); BESST_CUDA_TRY(ctx, ctx->run_len.ensure(4 * (size_t)run_cap));
+        BESST_CUDA_TRY(ctx, ctx->run_state.ensure(64));
+        u32* gstate = ctx->run_state.as<u32>();
+        BESST_CUDA_TRY(ctx, cudaMemsetAsync(gstate, 0, 64, ctx->stream));
+        static bool attr_done = false;
+        if (!attr_done) {
+            cudaFuncSetAttribute(k_group_blocks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(GroupSmem));
+            attr_done = true;
+        }
+        {
+            KTimer kt(ctx, BESST_K_GROUP);
+            k_group_blocks<<<(unsigned)n_gblocks, GB_THREADS, sizeof(GroupSmem), ctx->stream>>>(
+                d_tuples, n, bv, block_bits, ctx->grouped.as<int2>(), ctx->run_key[0].as<u64>(), ctx->run_val[0].as<u32>(),
+                ctx->run_start.as<u32>(), ctx->run_cnt.as<u32>(), ctx->run_first.as<u32>(), gstate, run_cap);
+        }
+        BESST_CUDA_TRY(ctx, cudaGetLastError());
+        u32 hs[2] = {0, 0};
+        BESST_CUDA_TRY(ctx, cudaMemcpyAsync(hs, gstate, 8, cudaMemcpyDeviceToHost, ctx->stream));
+        BESST_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+        const int64_t R = hs[0];
+        if (hs[1] == 0 && R <= (int64_t)run_cap) {
+            int in_b = 0;
+            rc = besst_radix_sort_pairs(ctx, ctx->run_key[0].as<uint64_t>(), ctx->run_key[1].as<uint64_t>(), ctx->run_val[0].as<uint32_t>(),
+                                        ctx->run_val[1].as<uint32_t>(), R, 2 * bv + block_bits, &in_b);
+            if (rc) return rc;
+            const u64* rkeys = ctx->run_key[in_b].as<u64>();
+            const u32* rvals = ctx->run_val[in_b].as<u32>();
+            besst_mark(ctx);
+            const int rblocks = (int)((R + RS_TILE - 1) / RS_TILE);
+            BESST_CUDA_TRY(ctx, ctx->heads.ensure(8 * (size_t)(rblocks + 2)));
+            u64* bsums = ctx->heads.as<u64>();
+            { KTimer kt(ctx, BESST_K_RUNS); k_run_count<<<rblocks, RS_T, 0, ctx->stream>>>(rkeys, rvals, ctx->run_cnt.as<u32>(), R, block_bits, bsums); }
+            { KTimer kt(ctx, BESST_K_RUNS); k_scan_blocks64<<<1, 1024, 0, ctx->stream>>>(bsums, rblocks); }
+            u64 tot = 0;
+            BESST_CUDA_TRY(ctx, cudaMemcpyAsync(&tot, bsums + rblocks, 8, cudaMemcpyDeviceToHost, ctx->stream));
+            BESST_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+            rc = alloc_edges((int64_t)(tot >> 32));
+            if (rc) return rc;
+            if ((int64_t)(tot & 0xffffffffull) != n) { ctx->err = "run-merge bucket: link count mismatch"; return BESST_E_STATE; }
+            BESST_CUDA_TRY(ctx, ctx->edge_run_ptr.ensure(4 * (size_t)(E + 2)));
+            { KTimer kt(ctx, BESST_K_RUNS);
+              k_run_write<<<rblocks, RS_T, 0, ctx->stream>>>(rkeys, rvals, ctx->run_cnt.as<u32>(), ctx->run_start.as<u32>(), ctx->run_first.as<u32>(), R,
+                                                            block_bits, bv, bsums, ctx->run_off.as<u32>(), ctx->run_src.as<u32>(), ctx->run_len.as<u32>(),
+                                                            EA.row_ptr, ctx->edge_run_ptr.as<u32>(), EA.u, EA.v, EA.first, n); }
+            besst_mark(ctx);
+            {
+                int grid = (int)((E * 32 + 255) / 256);
+                if (grid > edge_grid_max) grid = edge_grid_max;
+                KTimer kt(ctx, BESST_K_EDGE_REDUCE);
+                k_edge_gather<<<grid, 256, 0, ctx->stream>>>(EA, E, ctx->grouped.as<int2>(), ctx->edge_run_ptr.as<u32>(), ctx->run_off.as<u32>(),
+                                                             ctx->run_src.as<u32>(), ctx->run_len.as<u32>(), bv, fishy_sorted, n_fishy,
+                                                             (u32)(2 * ctx->n_large), p.no_score ? 0 : 1);
+                BESST_CUDA_TRY(ctx, cudaGetLastError());
+            }
+            besst_mark(ctx);
+            done = true;
+        }   // else: fall through to the radix bucket
+    }
+
+    int n_blocks = (int)((n + HB_TILE - 1) / HB_TILE);
+    if (!done) {
+    // ---- K3: radix bucket (fallback for input without local order) ----------------------------------
     BESST_CUDA_TRY(ctx, ctx->key_a.ensure(8 * nz));
     BESST_CUDA_TRY(ctx, ctx->key_b.ensure(8 * nz));
     // the BAM-order index rides in the low bits of the sort word when it fits: 8 B per link per pass
     int idx_bits = bits_for((uint64_t)(n > 1 ? n - 1 : 1));
     if (2 * bv + idx_bits > 64) idx_bits = 0;
     int in_b = 0;
-    int rc;
     const u32* idx = nullptr;
     if (idx_bits) {
         rc = besst_radix_sort_tuples_packed(ctx, d_tuples, bv, idx_bits, ctx->key_a.as<uint64_t>(), ctx->key_b.as<uint64_t>(), n, &in_b);
@@ -619,22 +1141,7 @@ int besst_launch_graph(besst_ctx* ctx, const besst_lib_params& p, const besst_li
     const u64* keys = in_b ? ctx->key_b.as<u64>() : ctx->key_a.as<u64>();
     besst_mark(ctx);
 
-    // fishy pairs: rekey, sort (keys only)
-    const u64* fishy_sorted = nullptr;
-    if (n_fishy > 0) {
-        BESST_CUDA_TRY(ctx, ctx->fishy_sorted.ensure(8 * (size_t)n_fishy));
-        BESST_CUDA_TRY(ctx, ctx->fishy_tmp.ensure(8 * (size_t)n_fishy));
-        { KTimer kt(ctx, BESST_K_FISHY); k_fishy_rekey<<<(int)((n_fishy + 255) / 256), 256, 0, ctx->stream>>>(reinterpret_cast<const u64*>(d_fishy), ctx->fishy_sorted.as<u64>(), n_fishy, bv); }
-        int fb = 0;
-        ctx->sweep_kernel_id = BESST_K_FISHY;   // profiling: keep the small fishy-key sort out of k_radix_sweep
-        rc = besst_radix_sort_keys(ctx, ctx->fishy_sorted.as<uint64_t>(), ctx->fishy_tmp.as<uint64_t>(), n_fishy, 2 * bv, &fb);
-        ctx->sweep_kernel_id = BESST_K_RADIX_SWEEP;
-        if (rc) return rc;
-        fishy_sorted = fb ? ctx->fishy_tmp.as<u64>() : ctx->fishy_sorted.as<u64>();
-    }
-
     // ---- K4: heads -> row_ptr ------------------------------------------------------------
-    const int n_blocks = (int)((n + HB_TILE - 1) / HB_TILE);
     BESST_CUDA_TRY(ctx, ctx->block_sums.ensure(4 * (size_t)(n_blocks + 2)));
     u32 n_edges32 = 0;
     if (n > 0) {
@@ -643,48 +1150,24 @@ int besst_launch_graph(besst_ctx* ctx, const besst_lib_params& p, const besst_li
         BESST_CUDA_TRY(ctx, cudaMemcpyAsync(&n_edges32, ctx->block_sums.as<u32>() + n_blocks, 4, cudaMemcpyDeviceToHost, ctx->stream));
         BESST_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     }
-    const int64_t E = n_edges32;
-    ctx->n_edges = E;
-    const size_t Ez = (size_t)(E > 0 ? E : 1);
-    BESST_CUDA_TRY(ctx, ctx->e_u.ensure(4 * Ez)); BESST_CUDA_TRY(ctx, ctx->e_v.ensure(4 * Ez));
-    BESST_CUDA_TRY(ctx, ctx->e_nr.ensure(4 * Ez)); BESST_CUDA_TRY(ctx, ctx->e_obs.ensure(8 * Ez));
-    BESST_CUDA_TRY(ctx, ctx->e_obs_sq.ensure(8 * Ez)); BESST_CUDA_TRY(ctx, ctx->e_first.ensure(8 * Ez));
-    BESST_CUDA_TRY(ctx, ctx->e_row_ptr.ensure(8 * (Ez + 1))); BESST_CUDA_TRY(ctx, ctx->e_gap.ensure(4 * Ez));
-    BESST_CUDA_TRY(ctx, ctx->e_score.ensure(8 * Ez)); BESST_CUDA_TRY(ctx, ctx->e_ks.ensure(8 * Ez));
-    BESST_CUDA_TRY(ctx, ctx->e_sd_obs.ensure(8 * Ez)); BESST_CUDA_TRY(ctx, ctx->e_sd_model.ensure(8 * Ez));
-    BESST_CUDA_TRY(ctx, ctx->e_fishy.ensure(4 * Ez)); BESST_CUDA_TRY(ctx, ctx->e_flags.ensure(Ez));
-    BESST_CUDA_TRY(ctx, ctx->l_obs_u.ensure(4 * nz)); BESST_CUDA_TRY(ctx, ctx->l_obs_v.ensure(4 * nz));
-    EdgeArrays EA;
-    EA.u = ctx->e_u.as<u32>(); EA.v = ctx->e_v.as<u32>(); EA.nr = ctx->e_nr.as<int>();
-    EA.obs = ctx->e_obs.as<long long>(); EA.obs_sq = ctx->e_obs_sq.as<long long>(); EA.first = ctx->e_first.as<long long>();
-    EA.row_ptr = ctx->e_row_ptr.as<long long>(); EA.gap = ctx->e_gap.as<int>(); EA.score = ctx->e_score.as<double>();
-    EA.ks = ctx->e_ks.as<double>(); EA.sd_obs = ctx->e_sd_obs.as<double>(); EA.sd_model = ctx->e_sd_model.as<double>();
-    EA.fishy = ctx->e_fishy.as<int>(); EA.flags = ctx->e_flags.as<unsigned char>();
-    EA.obs_u = ctx->l_obs_u.as<int>(); EA.obs_v = ctx->l_obs_v.as<int>();
-    BESST_CUDA_TRY(ctx, ctx->e_sum_u.ensure(8 * Ez)); BESST_CUDA_TRY(ctx, ctx->e_max_v.ensure(4 * Ez));
-    EA.sum_u = ctx->e_sum_u.as<long long>(); EA.max_v = ctx->e_max_v.as<int>();
-    if (E == 0) {
-        const long long zero = 0;
-        BESST_CUDA_TRY(ctx, cudaMemcpyAsync(EA.row_ptr, &zero, 8, cudaMemcpyHostToDevice, ctx->stream));
-        BESST_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-        besst_mark(ctx); besst_mark(ctx); besst_mark(ctx);
-        ctx->have_graph = true;
-        return BESST_OK;
-    }
+    rc = alloc_edges((int64_t)n_edges32);
+    if (rc) return rc;
+    if (E == 0) return finish_empty();
     { KTimer kt(ctx, BESST_K_HEADS); k_head_write<<<n_blocks, HB_THREADS, 0, ctx->stream>>>(keys, n, idx_bits, ctx->block_sums.as<u32>(), EA.row_ptr); }
     besst_mark(ctx);
 
     {
         long long warps = E;
         int grid = (int)((warps * 32 + 255) / 256);
-        const int max_grid = ctx->sm_count * 32;
-        if (grid > max_grid) grid = max_grid;
+        if (grid > edge_grid_max) grid = edge_grid_max;
         KTimer kt(ctx, BESST_K_EDGE_REDUCE);
         k_edge_reduce<<<grid, 256, 0, ctx->stream>>>(EA, E, d_tuples, idx, keys, bv, idx_bits, fishy_sorted, n_fishy,
                                                      (u32)(2 * ctx->n_large), p.no_score ? 0 : 1);
         BESST_CUDA_TRY(ctx, cudaGetLastError());
     }
     besst_mark(ctx);
+    }
+    const size_t Ez = (size_t)(E > 0 ? E : 1);
 
     // ---- K5/K6: KS + GapEst + score on large-large edges --------------------------------
     if (!p.no_score) {

@@ -147,6 +147,57 @@ def test_fetch_view_equals_fetch(cuda_engine):
     helpers.assert_graph_equal(cuda_engine.fetch(s2), c, label="view after rebuild")
 
 
+@pytest.mark.parametrize("config,objects", [("small_mp", "first"), ("small_pe", "later"), ("small_mp_cont", "first")])
+def test_radix_bucket_fallback_equals_run_merge_bucket(cuda_engine, config, objects, monkeypatch):
+    """The edge bucket has two implementations: block-local grouping + merge of the run descriptors
+    (default) and a device-wide radix sort (fallback for input without local order)."""
+    lib, batch, params, table = _setup(config, objects=objects)
+    want, _, _, _ = oracle_lib.graph_build(table.rows, table.n_scaffolds, params, batch)
+    monkeypatch.setenv("BESST_BUCKET", "radix")
+    got = cuda_engine.graph_build(table, params, batch)
+    helpers.assert_graph_equal(got, want, label="radix bucket %s" % config)
+    monkeypatch.delenv("BESST_BUCKET")
+    got = cuda_engine.graph_build(table, params, batch)
+    helpers.assert_graph_equal(got, want, label="run-merge bucket %s" % config)
+
+
+@pytest.mark.parametrize("order", ["reversed", "window", "shuffled"])
+def test_bucket_on_tuple_streams_without_bam_order(cuda_engine, order, monkeypatch):
+    """links_to_graph accepts any tuple order (multi-GPU exchange).  A fully shuffled stream has more
+    than 512 edges per block: the run-merge bucket must notice and hand over to the radix bucket."""
+    import torch
+    lib, batch, params, table = _setup("small_mp")
+    cuda_engine.set_table(table)
+    keep = []
+    cuda_engine.links_extract(params, abi.make_records(batch, keepalive=keep))
+    tuples = cuda_engine.links_tuples_host()
+    rng = np.random.default_rng(5)
+    n = tuples.shape[0]
+    if order == "reversed":
+        perm = np.arange(n)[::-1].copy()
+    elif order == "window":
+        perm = np.arange(n)
+        for a in range(0, n, 300):
+            rng.shuffle(perm[a:a + 300])
+    else:
+        perm = rng.permutation(n)
+    t = torch.from_numpy(np.ascontiguousarray(tuples[perm]).view(np.int32).reshape(-1, 4)).cuda()
+    res = {}
+    for mode in ("radix", "runs"):
+        if mode == "radix":
+            monkeypatch.setenv("BESST_BUCKET", "radix")
+        else:
+            monkeypatch.delenv("BESST_BUCKET", raising=False)
+        sizes = cuda_engine.links_to_graph(params, t.data_ptr(), n, None, 0)
+        res[mode] = cuda_engine.fetch(sizes)
+    helpers.assert_graph_equal(res["runs"], res["radix"], label="tuple order %s" % order)
+    # same edges and link multisets as the BAM-ordered build
+    sizes = cuda_engine.links_to_graph(params, torch.from_numpy(tuples.view(np.int32).reshape(-1, 4)).cuda().data_ptr(), n, None, 0)
+    ref = cuda_engine.fetch(sizes)
+    assert np.array_equal(ref.edge_u, res["runs"].edge_u) and np.array_equal(ref.nr_links, res["runs"].nr_links)
+    assert np.array_equal(ref.obs_sum, res["runs"].obs_sum) and np.array_equal(ref.obs_sq, res["runs"].obs_sq)
+
+
 def test_two_slices_with_halo_equal_one_pass(cuda_engine):
     """The multi-GPU decomposition on one GPU: records cut into BAM-order slices, each
     extracted with the previous slice's last CreateEdge observation as halo, tuples
