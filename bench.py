@@ -232,6 +232,7 @@ def run_ours(args):
         "k_edge_reduce": (8 + 8) * n_links + 64 * n_edges,    # k_edge_gather: grouped (o1,o2) in, obs_u/obs_v out
         "k_group_blocks": (16 + 8) * n_links,                 # tuples in, grouped observations out (+ run descriptors)
         "k_score_keys": (8 + 8) * n_ll / 3.0 + 13 * n_edges,   # 3 launches: LL scan (2, over edges) + key build
+        "k_ks_block": (4 + 4) * n_ll + 8 * n_edges,           # obs_u, obs_v of the scored links in, one double per edge out
         "k_ks_sort": (4 + 4) * n_ll,
         "k_ks_eval": (4 + 4) * n_ll + 8 * n_edges,
         "k_gapest": 64 * n_edges,

@@ -52,7 +52,7 @@ extern "C" void besst_destroy(besst_ctx* ctx) {
                     &ctx->sort_state, &ctx->fishy_sorted, &ctx->fishy_tmp, &ctx->heads, &ctx->block_sums, &ctx->e_u, &ctx->e_v,
                     &ctx->e_nr, &ctx->e_obs, &ctx->e_obs_sq, &ctx->e_first, &ctx->e_row_ptr, &ctx->e_gap, &ctx->e_score,
                     &ctx->e_ks, &ctx->e_sd_obs, &ctx->e_sd_model, &ctx->e_fishy, &ctx->e_flags, &ctx->l_obs_u, &ctx->l_obs_v,
-                    &ctx->e_sum_u, &ctx->e_max_v, &ctx->ll_off, &ctx->ks_key[0], &ctx->ks_key[1], &ctx->ks_key[2], &ctx->ks_key[3],
+                    &ctx->e_sum_u, &ctx->e_max_v, &ctx->ll_off, &ctx->ks_key[0], &ctx->ks_key[1], &ctx->ks_key[2], &ctx->ks_key[3], &ctx->ks_key[4], &ctx->ks_key[5],
                     &ctx->grouped, &ctx->run_key[0], &ctx->run_key[1], &ctx->run_val[0], &ctx->run_val[1], &ctx->run_start, &ctx->run_cnt,
                     &ctx->run_first, &ctx->run_off, &ctx->run_src, &ctx->run_len, &ctx->edge_run_ptr, &ctx->run_state};
     for (DBuf* b : bufs) b->release();

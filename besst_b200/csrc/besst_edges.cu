@@ -730,7 +730,7 @@ __global__ void __launch_bounds__(256)
     const long long warp_global = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const long long n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
     for (long long e = warp_global; e < A.n_edges; e += n_warps) {
-        if (!(A.flags[e] & BESST_EDGE_LL)) continue;
+        if (A.ll_off[e + 1] == A.ll_off[e]) continue;   // not in this LL link space
         const long long b = A.row_ptr[e], t = A.row_ptr[e + 1];
         const long long dst = (long long)A.ll_off[e] - b;
         const int mv = A.max_v[e];
@@ -859,15 +859,16 @@ constexpr int LS_THREADS = 256;
 constexpr int LS_ITEMS = 8;
 constexpr int LS_TILE = LS_THREADS * LS_ITEMS;
 
+// LL link space of the edges with more than `thr` links (thr = 0: every LL edge)
 __global__ void __launch_bounds__(LS_THREADS) k_ll_count(const unsigned char* __restrict__ flags, const int* __restrict__ nr,
-                                                         long long n_edges, u32* block_sums) {
+                                                         long long n_edges, int thr, u32* block_sums) {
     __shared__ u32 s_w[LS_THREADS / 32];
     const long long base = (long long)blockIdx.x * LS_TILE;
     u32 c = 0;
 #pragma unroll
     for (int i = 0; i < LS_ITEMS; ++i) {
         const long long e = base + i * LS_THREADS + threadIdx.x;
-        if (e < n_edges && (flags[e] & BESST_EDGE_LL)) c += (u32)nr[e];
+        if (e < n_edges && (flags[e] & BESST_EDGE_LL) && nr[e] > thr) c += (u32)nr[e];
     }
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) c += __shfl_xor_sync(0xffffffffu, c, off);
@@ -881,7 +882,7 @@ __global__ void __launch_bounds__(LS_THREADS) k_ll_count(const unsigned char* __
 }
 
 __global__ void __launch_bounds__(LS_THREADS) k_ll_write(const unsigned char* __restrict__ flags, const int* __restrict__ nr,
-                                                         long long n_edges, const u32* __restrict__ block_sums, u32* ll_off) {
+                                                         long long n_edges, int thr, const u32* __restrict__ block_sums, u32* ll_off) {
     __shared__ u32 s_w[LS_THREADS / 32];
     const long long base = (long long)blockIdx.x * LS_TILE + (long long)threadIdx.x * LS_ITEMS;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -889,7 +890,7 @@ __global__ void __launch_bounds__(LS_THREADS) k_ll_write(const unsigned char* __
 #pragma unroll
     for (int i = 0; i < LS_ITEMS; ++i) {
         const long long e = base + i;
-        v[i] = (e < n_edges && (flags[e] & BESST_EDGE_LL)) ? (u32)nr[e] : 0u;
+        v[i] = (e < n_edges && (flags[e] & BESST_EDGE_LL) && nr[e] > thr) ? (u32)nr[e] : 0u;
         c += v[i];
     }
     u32 incl = c;
@@ -908,6 +909,267 @@ __global__ void __launch_bounds__(LS_THREADS) k_ll_write(const unsigned char* __
         pos += v[i];
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) ll_off[n_edges] = block_sums[gridDim.x];
+}
+
+// ---- K5': KS statistic of the edges with at most KB_G links, one CTA per ~KB_G links ---------------------
+// The per-edge observation lists are contiguous (CSR order).  A CTA takes the LL edges whose first
+// link falls into its window of the compact "small LL link space", builds (local edge << B | value)
+// keys for both lists in shared memory, sorts each with an in-block LSD radix sort (stable warp
+// multisplit, 8-bit digits, only as many passes as the key has bits) and evaluates the two-sided
+// ECDF difference with the same co-ranking walk as k_ks_eval -- all in one launch, one read of the
+// observations, no global sort passes.  Edges with more links take the device-wide path above.
+constexpr int KB_THREADS = 256;
+constexpr int KB_WARPS = KB_THREADS / 32;
+constexpr int KB_G = 2048;            // window of the small LL link space per CTA; also the largest edge handled here
+constexpr int KB_CAP = 2 * KB_G;      // links per CTA: < KB_G (window) + KB_G (the edge straddling its end)
+constexpr int KB_ITEMS = KB_CAP / KB_THREADS;   // 16
+
+struct KsBlockSmem {
+    u32 buf[3][KB_CAP];
+    unsigned short warp_hist[KB_WARPS][256];
+    u32 digit_start[256];
+    u32 warp_sum[KB_WARPS];
+    u32 seg_start[KB_G + 1];   // first position of every local edge
+};
+
+// stable LSD pass over `count` keys: src -> dst by digit (key >> shift) & 255
+__device__ __forceinline__ void kb_radix_pass(KsBlockSmem& S, const u32* src, u32* dst, int count, int shift) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const u32 lt_mask = (1u << lane) - 1u;
+    for (int i = threadIdx.x; i < KB_WARPS * 256 / 2; i += KB_THREADS) reinterpret_cast<u32*>(&S.warp_hist[0][0])[i] = 0;
+    __syncthreads();
+    u32 key[KB_ITEMS];
+    unsigned short rank[KB_ITEMS];
+#pragma unroll
+    for (int i = 0; i < KB_ITEMS; ++i) {
+        const int p = warp * (32 * KB_ITEMS) + i * 32 + lane;
+        const bool valid = p < count;
+        const u32 vmask = __ballot_sync(0xffffffffu, valid);
+        key[i] = 0; rank[i] = 0;
+        if (valid) {
+            key[i] = src[p];
+            const u32 d = (key[i] >> shift) & 255u;
+            const u32 peers = __match_any_sync(vmask, d);
+            const int leader = __ffs(peers) - 1;
+            u32 pre = 0;
+            if (lane == leader) {
+                pre = S.warp_hist[warp][d];
+                S.warp_hist[warp][d] = (unsigned short)(pre + __popc(peers));
+            }
+            pre = __shfl_sync(vmask, pre, leader);
+            rank[i] = (unsigned short)(pre + __popc(peers & lt_mask));
+        }
+        __syncwarp();
+    }
+    __syncthreads();
+    {   // thread d owns digit d: prefix over warps, then exclusive scan over digits
+        const int d = threadIdx.x;
+        u32 run = 0;
+#pragma unroll
+        for (int w = 0; w < KB_WARPS; ++w) { const u32 t = S.warp_hist[w][d]; S.warp_hist[w][d] = (unsigned short)run; run += t; }
+        u32 incl = run;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const u32 t = __shfl_up_sync(0xffffffffu, incl, off);
+            if (lane >= off) incl += t;
+        }
+        if (lane == 31) S.warp_sum[warp] = incl;
+        __syncthreads();
+        u32 wbase = 0;
+#pragma unroll
+        for (int w = 0; w < KB_WARPS; ++w)
+            if (w < warp) wbase += S.warp_sum[w];
+        S.digit_start[d] = wbase + incl - run;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < KB_ITEMS; ++i) {
+        const int p = warp * (32 * KB_ITEMS) + i * 32 + lane;
+        if (p < count) {
+            const u32 d = (key[i] >> shift) & 255u;
+            dst[S.digit_start[d] + S.warp_hist[warp][d] + rank[i]] = key[i];
+        }
+    }
+    __syncthreads();
+}
+
+struct KsBlockArgs {
+    const long long* row_ptr;
+    const int* nr;
+    const long long* sum_u;
+    const long long* obs_sum;
+    const int* max_v;
+    const int* obs_u;
+    const int* obs_v;
+    const u32* ll_edges;   // [n_small] global edge id of every small LL edge, edge order
+    const u32* ll_start;   // [n_small + 1] exclusive prefix of their link counts
+    long long n_small;
+    long long n_links;     // ll_start[n_small]
+    int value_bits;
+    double* ks;
+};
+
+// one side of the KS evaluation over the CTA's sorted lists (see k_ks_eval)
+template <int SIDE>
+__device__ __forceinline__ void kb_eval(const KsBlockSmem& S, const KsBlockArgs& A, const u32* own, const u32* other, int count,
+                                        long long k_lo, int n_local) {
+    const u32 vmask = (1u << A.value_bits) - 1u;
+    for (int c = threadIdx.x; c * KS_CHUNK < count; c += KB_THREADS) {
+        int j = c * KS_CHUNK;
+        const int j_end = (j + KS_CHUNK < count) ? j + KS_CHUNK : count;
+        while (j < j_end) {
+            const int lid = (int)(own[j] >> A.value_bits);
+            const long long e = A.ll_edges[k_lo + lid];
+            const int s0 = (int)S.seg_start[lid], s1 = (lid + 1 < n_local) ? (int)S.seg_start[lid + 1] : count;
+            const int n = s1 - s0;
+            const long long su = A.sum_u[e];
+            const long long sy = (long long)n * A.max_v[e] - (A.obs_sum[e] - su);
+            const double m1 = (double)su / (double)n;   // l1_mean (:584)
+            const double m2 = (double)sy / (double)n;   // l2_mean (:591)
+            const double m_own = SIDE == 0 ? m1 : m2, m_other = SIDE == 0 ? m2 : m1;
+            const int stop = j_end < s1 ? j_end : s1;
+            int q;
+            {
+                const double z = (double)(long long)(own[j] & vmask) - m_own;
+                int lo = s0, hi = s1;
+                while (lo < hi) {
+                    const int mid = (lo + hi) >> 1;
+                    if ((double)(long long)(other[mid] & vmask) - m_other <= z) lo = mid + 1; else hi = mid;
+                }
+                q = lo;
+            }
+            double dmax = 0.0;
+            u32 cur = own[j];
+            for (; j < stop; ++j) {
+                const bool at_end = j + 1 >= s1;
+                const u32 nxt = at_end ? cur : own[j + 1];
+                const double z = (double)(long long)(cur & vmask) - m_own;
+                while (q < s1 && (double)(long long)(other[q] & vmask) - m_other <= z) ++q;
+                if (at_end || nxt != cur) {
+                    const double f_own = (double)(j + 1 - s0) / (double)n;
+                    const double f_other = (double)(q - s0) / (double)n;
+                    const double diff = SIDE == 0 ? fabs(f_own - f_other) : fabs(f_other - f_own);
+                    if (diff > dmax) dmax = diff;
+                }
+                cur = nxt;
+            }
+            if (dmax > 0.0) atomicMax(reinterpret_cast<unsigned long long*>(A.ks + e), (unsigned long long)__double_as_longlong(dmax));
+        }
+    }
+}
+
+__global__ void __launch_bounds__(KB_THREADS, 3) k_ks_block(const KsBlockArgs A) {
+    extern __shared__ __align__(16) unsigned char kb_smem[];
+    KsBlockSmem& S = *reinterpret_cast<KsBlockSmem*>(kb_smem);
+    __shared__ long long s_k[2];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x < 2) {   // first small LL edge starting at or after the window's start / end
+        const u32 target = (u32)(((long long)blockIdx.x + threadIdx.x) * KB_G);
+        long long lo = 0, hi = A.n_small;
+        while (lo < hi) {
+            const long long mid = (lo + hi) >> 1;
+            if (__ldg(A.ll_start + mid) < target) lo = mid + 1; else hi = mid;
+        }
+        s_k[threadIdx.x] = lo;
+    }
+    __syncthreads();
+    const long long k_lo = s_k[0], k_hi = s_k[1];
+    const int n_local = (int)(k_hi - k_lo);
+    if (n_local <= 0) return;
+    const u32 base = __ldg(A.ll_start + k_lo);
+    const int count = (int)(__ldg(A.ll_start + k_hi) - base);
+    for (int i = threadIdx.x; i <= n_local; i += KB_THREADS) S.seg_start[i] = __ldg(A.ll_start + k_lo + i) - base;
+    __syncthreads();
+    // keys of both lists, edge by edge (one warp per edge)
+    u32* l1 = S.buf[0];
+    u32* l2 = S.buf[1];
+    u32* tmp = S.buf[2];
+    for (int lid = warp; lid < n_local; lid += KB_WARPS) {
+        const long long e = __ldg(A.ll_edges + k_lo + lid);
+        const long long b = A.row_ptr[e];
+        const int n = (int)(S.seg_start[lid + 1] - S.seg_start[lid]);
+        const int mv = A.max_v[e];
+        const u32 hi = (u32)lid << A.value_bits;
+        const int s0 = (int)S.seg_start[lid];
+        for (int k = lane; k < n; k += 32) {
+            l1[s0 + k] = hi | (u32)__ldg(A.obs_u + b + k);
+            l2[s0 + k] = hi | (u32)(mv - __ldg(A.obs_v + b + k));   // abs(x - max_obs2), :588-590
+        }
+    }
+    __syncthreads();
+    int key_bits = A.value_bits;
+    for (int t = n_local - 1; t > 0; t >>= 1) ++key_bits;
+    // list 1: l1 <-> tmp; list 2: l2 <-> whichever of the two is free afterwards
+    for (int shift = 0; shift < key_bits; shift += 8) {
+        kb_radix_pass(S, l1, tmp, count, shift);
+        u32* x = l1; l1 = tmp; tmp = x;
+    }
+    for (int shift = 0; shift < key_bits; shift += 8) {
+        kb_radix_pass(S, l2, tmp, count, shift);
+        u32* x = l2; l2 = tmp; tmp = x;
+    }
+    kb_eval<0>(S, A, l1, l2, count, k_lo, n_local);
+    kb_eval<1>(S, A, l2, l1, count, k_lo, n_local);
+}
+
+// compact list of the LL edges with at most `thr` links: packed sums (edges << 32 | links)
+__global__ void __launch_bounds__(LS_THREADS) k_llc_count(const unsigned char* __restrict__ flags, const int* __restrict__ nr,
+                                                          long long n_edges, int thr, u64* block_sums) {
+    __shared__ u64 s_w[LS_THREADS / 32];
+    const long long base = (long long)blockIdx.x * LS_TILE;
+    u64 c = 0;
+#pragma unroll
+    for (int i = 0; i < LS_ITEMS; ++i) {
+        const long long e = base + i * LS_THREADS + threadIdx.x;
+        if (e < n_edges && (flags[e] & BESST_EDGE_LL) && nr[e] <= thr) c += (1ull << 32) | (u64)(u32)nr[e];
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) c += __shfl_xor_sync(0xffffffffu, c, off);
+    if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = c;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        u64 t = 0;
+        for (int w = 0; w < LS_THREADS / 32; ++w) t += s_w[w];
+        block_sums[blockIdx.x] = t;
+    }
+}
+
+__global__ void __launch_bounds__(LS_THREADS) k_llc_write(const unsigned char* __restrict__ flags, const int* __restrict__ nr,
+                                                          long long n_edges, int thr, const u64* __restrict__ block_sums,
+                                                          u32* ll_edges, u32* ll_start) {
+    __shared__ u64 s_w[LS_THREADS / 32];
+    const long long base = (long long)blockIdx.x * LS_TILE + (long long)threadIdx.x * LS_ITEMS;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    u64 v[LS_ITEMS], c = 0;
+#pragma unroll
+    for (int i = 0; i < LS_ITEMS; ++i) {
+        const long long e = base + i;
+        v[i] = (e < n_edges && (flags[e] & BESST_EDGE_LL) && nr[e] <= thr) ? ((1ull << 32) | (u64)(u32)nr[e]) : 0ull;
+        c += v[i];
+    }
+    u64 incl = c;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        const u64 t = __shfl_up_sync(0xffffffffu, incl, off);
+        if (lane >= off) incl += t;
+    }
+    if (lane == 31) s_w[warp] = incl;
+    __syncthreads();
+    u64 pos = block_sums[blockIdx.x] + incl - c;
+    for (int w = 0; w < warp; ++w) pos += s_w[w];
+#pragma unroll
+    for (int i = 0; i < LS_ITEMS; ++i) {
+        if (v[i]) {
+            const u32 k = (u32)(pos >> 32);
+            ll_edges[k] = (u32)(base + i);
+            ll_start[k] = (u32)pos;
+        }
+        pos += v[i];
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        const u64 tot = block_sums[gridDim.x];
+        ll_start[(u32)(tot >> 32)] = (u32)tot;
+    }
 }
 
 // ---- batched GapEstimator + tr_sk_std_dev: one quad per item -------------------------------
@@ -1171,34 +1433,75 @@ int besst_launch_graph(besst_ctx* ctx, const besst_lib_params& p, const besst_li
 
     // ---- K5/K6: KS + GapEst + score on large-large edges --------------------------------
     if (!p.no_score) {
-        // LL link space
+        // observations are < ins_size_threshold (CreateGraph.py:840), and so is max(obs_v) - obs_v
+        double thr = p.ins_size_threshold;
+        if (!(thr > 1)) thr = 1;
+        if (thr > 2147483647.0) thr = 2147483647.0;
+        const int value_bits = bits_for((uint64_t)thr);
+        const int edge_bits = bits_for((uint64_t)(E > 1 ? E - 1 : 1));
         const int ls_blocks = (int)((E + LS_TILE - 1) / LS_TILE);
+        int64_t n_ll_total = 0;
+
+        // ---- edges with at most KB_G links: in-block sort + evaluation (k_ks_block) ------------------
+        // BESST_KS=global sends every edge through the device-wide sorts below (A/B, tests)
+        const char* ks_env = getenv("BESST_KS");
+        const bool block_ks = !(ks_env && ks_env[0] == 'g') && value_bits + 11 <= 32;
+        const int big_thr = block_ks ? KB_G : 0;
+        if (block_ks) {
+            BESST_CUDA_TRY(ctx, ctx->heads.ensure(8 * (size_t)(ls_blocks + 2)));
+            u64* bs = ctx->heads.as<u64>();
+            { KTimer kt(ctx, BESST_K_EDGE_SCORE); k_llc_count<<<ls_blocks, LS_THREADS, 0, ctx->stream>>>(EA.flags, EA.nr, E, KB_G, bs); }
+            { KTimer kt(ctx, BESST_K_EDGE_SCORE); k_scan_blocks64<<<1, 1024, 0, ctx->stream>>>(bs, ls_blocks); }
+            u64 tot = 0;
+            BESST_CUDA_TRY(ctx, cudaMemcpyAsync(&tot, bs + ls_blocks, 8, cudaMemcpyDeviceToHost, ctx->stream));
+            BESST_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+            const int64_t n_small = (int64_t)(tot >> 32), n_small_links = (int64_t)(tot & 0xffffffffull);
+            n_ll_total += n_small_links;
+            if (n_small > 0) {
+                BESST_CUDA_TRY(ctx, ctx->ks_key[0].ensure(4 * (size_t)(n_small + 1)));
+                BESST_CUDA_TRY(ctx, ctx->ks_key[1].ensure(4 * (size_t)(n_small + 1)));
+                u32* ll_edges = ctx->ks_key[0].as<u32>();
+                u32* ll_start = ctx->ks_key[1].as<u32>();
+                { KTimer kt(ctx, BESST_K_EDGE_SCORE); k_llc_write<<<ls_blocks, LS_THREADS, 0, ctx->stream>>>(EA.flags, EA.nr, E, KB_G, bs, ll_edges, ll_start); }
+                static bool attr_done = false;
+                if (!attr_done) {
+                    cudaFuncSetAttribute(k_ks_block, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(KsBlockSmem));
+                    attr_done = true;
+                }
+                KsBlockArgs B;
+                B.row_ptr = EA.row_ptr; B.nr = EA.nr; B.sum_u = EA.sum_u; B.obs_sum = EA.obs; B.max_v = EA.max_v;
+                B.obs_u = EA.obs_u; B.obs_v = EA.obs_v; B.ll_edges = ll_edges; B.ll_start = ll_start;
+                B.n_small = n_small; B.n_links = n_small_links; B.value_bits = value_bits; B.ks = EA.ks;
+                const unsigned windows = (unsigned)((n_small_links + KB_G - 1) / KB_G);
+                { KTimer kt(ctx, BESST_K_KS_BLOCK); k_ks_block<<<windows, KB_THREADS, sizeof(KsBlockSmem), ctx->stream>>>(B); }
+                BESST_CUDA_TRY(ctx, cudaGetLastError());
+            }
+        }
+
+        // ---- the rest (edges with more links; every LL edge when the block path is off): LL link space,
+        // two device-wide key sorts, co-ranking evaluation ------------------------------------------------
         BESST_CUDA_TRY(ctx, ctx->ll_off.ensure(4 * (Ez + 2)));
         BESST_CUDA_TRY(ctx, ctx->block_sums.ensure(4 * (size_t)(std::max(ls_blocks, n_blocks) + 2)));
         u32* ll_off = ctx->ll_off.as<u32>();
         u32 n_ll32 = 0;
-        { KTimer kt(ctx, BESST_K_EDGE_SCORE); k_ll_count<<<ls_blocks, LS_THREADS, 0, ctx->stream>>>(EA.flags, EA.nr, E, ctx->block_sums.as<u32>()); }
+        { KTimer kt(ctx, BESST_K_EDGE_SCORE); k_ll_count<<<ls_blocks, LS_THREADS, 0, ctx->stream>>>(EA.flags, EA.nr, E, big_thr, ctx->block_sums.as<u32>()); }
         { KTimer kt(ctx, BESST_K_EDGE_SCORE); k_scan_blocks<<<1, 1024, 0, ctx->stream>>>(ctx->block_sums.as<u32>(), ls_blocks); }
-        { KTimer kt(ctx, BESST_K_EDGE_SCORE); k_ll_write<<<ls_blocks, LS_THREADS, 0, ctx->stream>>>(EA.flags, EA.nr, E, ctx->block_sums.as<u32>(), ll_off); }
         BESST_CUDA_TRY(ctx, cudaMemcpyAsync(&n_ll32, ctx->block_sums.as<u32>() + ls_blocks, 4, cudaMemcpyDeviceToHost, ctx->stream));
         BESST_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
         const int64_t n_ll = n_ll32;
-        ctx->n_ll_links = n_ll;
+        n_ll_total += n_ll;
+        ctx->n_ll_links = n_ll_total;
         if (n_ll > 0) {
-            // observations are < ins_size_threshold (CreateGraph.py:840), and so is max(obs_v) - obs_v
-            double thr = p.ins_size_threshold;
-            if (!(thr > 1)) thr = 1;
-            if (thr > 2147483647.0) thr = 2147483647.0;
-            const int value_bits = bits_for((uint64_t)thr);
-            const int edge_bits = bits_for((uint64_t)(E > 1 ? E - 1 : 1));
+            { KTimer kt(ctx, BESST_K_EDGE_SCORE); k_ll_write<<<ls_blocks, LS_THREADS, 0, ctx->stream>>>(EA.flags, EA.nr, E, big_thr, ctx->block_sums.as<u32>(), ll_off); }
             const int key_bits = value_bits + edge_bits;
             KsArgs K;
             K.row_ptr = EA.row_ptr; K.ll_off = ll_off; K.flags = EA.flags; K.sum_u = EA.sum_u; K.obs_sum = EA.obs;
             K.max_v = EA.max_v; K.n_edges = E; K.n_ll = n_ll; K.value_bits = value_bits;
             const bool narrow = key_bits <= 32;
             const size_t kb = narrow ? 4 : 8;
-            BESST_CUDA_TRY(ctx, ctx->ks_key[0].ensure(kb * (size_t)n_ll)); BESST_CUDA_TRY(ctx, ctx->ks_key[1].ensure(kb * (size_t)n_ll));
+            // ks_key[0..1] may hold the compact small-edge lists still being read by k_ks_block: stream order protects them
             BESST_CUDA_TRY(ctx, ctx->ks_key[2].ensure(kb * (size_t)n_ll)); BESST_CUDA_TRY(ctx, ctx->ks_key[3].ensure(kb * (size_t)n_ll));
+            BESST_CUDA_TRY(ctx, ctx->ks_key[4].ensure(kb * (size_t)n_ll)); BESST_CUDA_TRY(ctx, ctx->ks_key[5].ensure(kb * (size_t)n_ll));
             long long kgrid = (E * 32 + 255) / 256;
             if (kgrid > (long long)ctx->sm_count * 32) kgrid = (long long)ctx->sm_count * 32;
             const long long chunks = (n_ll + KS_CHUNK - 1) / KS_CHUNK;
@@ -1206,7 +1509,7 @@ int besst_launch_graph(besst_ctx* ctx, const besst_lib_params& p, const besst_li
             int b1 = 0, b2 = 0;
             ctx->sweep_kernel_id = BESST_K_KS_SORT;
             if (narrow) {
-                u32 *k1 = ctx->ks_key[0].as<u32>(), *k1t = ctx->ks_key[1].as<u32>(), *k2 = ctx->ks_key[2].as<u32>(), *k2t = ctx->ks_key[3].as<u32>();
+                u32 *k1 = ctx->ks_key[2].as<u32>(), *k1t = ctx->ks_key[3].as<u32>(), *k2 = ctx->ks_key[4].as<u32>(), *k2t = ctx->ks_key[5].as<u32>();
                 { KTimer kt(ctx, BESST_K_EDGE_SCORE); k_score_keys<u32><<<(unsigned)kgrid, 256, 0, ctx->stream>>>(K, EA.obs_u, EA.obs_v, k1, k2); }
                 rc = besst_radix_sort_keys32(ctx, k1, k1t, n_ll, key_bits, &b1); if (rc) return rc;
                 rc = besst_radix_sort_keys32(ctx, k2, k2t, n_ll, key_bits, &b2); if (rc) return rc;
@@ -1214,7 +1517,7 @@ int besst_launch_graph(besst_ctx* ctx, const besst_lib_params& p, const besst_li
                 { KTimer kt(ctx, BESST_K_KS_EVAL); k_ks_eval<u32, 0><<<egrid, 256, 0, ctx->stream>>>(K, s1, s2, EA.ks); }
                 { KTimer kt(ctx, BESST_K_KS_EVAL); k_ks_eval<u32, 1><<<egrid, 256, 0, ctx->stream>>>(K, s2, s1, EA.ks); }
             } else {
-                u64 *k1 = ctx->ks_key[0].as<u64>(), *k1t = ctx->ks_key[1].as<u64>(), *k2 = ctx->ks_key[2].as<u64>(), *k2t = ctx->ks_key[3].as<u64>();
+                u64 *k1 = ctx->ks_key[2].as<u64>(), *k1t = ctx->ks_key[3].as<u64>(), *k2 = ctx->ks_key[4].as<u64>(), *k2t = ctx->ks_key[5].as<u64>();
                 { KTimer kt(ctx, BESST_K_EDGE_SCORE); k_score_keys<u64><<<(unsigned)kgrid, 256, 0, ctx->stream>>>(K, EA.obs_u, EA.obs_v, k1, k2); }
                 rc = besst_radix_sort_keys(ctx, reinterpret_cast<uint64_t*>(k1), reinterpret_cast<uint64_t*>(k1t), n_ll, key_bits, &b1); if (rc) return rc;
                 rc = besst_radix_sort_keys(ctx, reinterpret_cast<uint64_t*>(k2), reinterpret_cast<uint64_t*>(k2t), n_ll, key_bits, &b2); if (rc) return rc;

@@ -119,7 +119,7 @@ struct besst_ctx {
     // CSR / per-edge results
     DBuf fishy_sorted, fishy_tmp, heads, block_sums;
     DBuf e_u, e_v, e_nr, e_obs, e_obs_sq, e_first, e_row_ptr, e_gap, e_score, e_ks, e_sd_obs, e_sd_model, e_fishy,
-        e_flags, l_obs_u, l_obs_v, e_sum_u, e_max_v, ll_off, ks_key[4];
+        e_flags, l_obs_u, l_obs_v, e_sum_u, e_max_v, ll_off, ks_key[6];
     // run-merge bucket: block-grouped observations and the run descriptors
     DBuf grouped, run_key[2], run_val[2], run_start, run_cnt, run_first, run_off, run_src, run_len, edge_run_ptr, run_state;
     int64_t n_edges = 0, n_links = 0, n_fishy_pairs = 0, n_ll_links = 0;

@@ -202,7 +202,7 @@ class CudaEngine(object):
 
 KERNEL_NAMES = ["k_extract_links", "k_radix_hist", "k_radix_scan_hist", "k_radix_sweep", "k_heads", "k_edge_reduce",
                 "k_score_keys", "k_fishy_rekey", "k_metrics", "k_gapest", "k_tile_scan", "k_compact_tuples",
-                "k_partition", "k_ks_eval", "k_ks_sort", "k_group_blocks", "k_runs"]
+                "k_partition", "k_ks_eval", "k_ks_sort", "k_group_blocks", "k_runs", "k_ks_block"]
 
 _default = None
 

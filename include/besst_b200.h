@@ -289,7 +289,8 @@ int besst_kernel_launches(besst_ctx* ctx, int64_t* n_launches);
 #define BESST_K_KS_SORT 14     /* k_radix_sweep on the (edge, value) keys of K5, one per digit pass */
 #define BESST_K_GROUP 15       /* k_group_blocks: block-local grouping of the tuple stream (K3') */
 #define BESST_K_RUNS 16        /* k_run_count/k_scan_blocks64/k_run_write: heads and offsets over the sorted runs (K3') */
-#define BESST_N_KERNEL_IDS 17
+#define BESST_K_KS_BLOCK 17    /* k_ks_block: in-block sort + KS evaluation of the edges with <= 2048 links (K5') */
+#define BESST_N_KERNEL_IDS 18
 int besst_set_profiling(besst_ctx* ctx, int enabled);
 int besst_kernel_profile(besst_ctx* ctx, int32_t* kernel_ids, float* ms, int32_t cap);
 

@@ -98,6 +98,30 @@ def test_edges_with_more_links_than_one_warp_sorts(cuda_engine):
     helpers.assert_graph_equal(got, want, label="big edges")
 
 
+@pytest.mark.parametrize("config", ["small_mp", "small_mp_cont", "mixed_edge_sizes"])
+def test_ks_block_path_equals_global_sort_path(cuda_engine, config, monkeypatch):
+    """KS statistic: edges with <= 2048 links are sorted and evaluated inside one CTA, larger ones by
+    two device-wide key sorts; BESST_KS=global sends everything through the latter."""
+    if config == "mixed_edge_sizes":   # few contigs of very different lengths: edges from a handful to > 2048 links
+        lib = synth.make_library(40, 300000, "rf", 3000.0, 500.0, seed=123)
+        batch = lib.to_batch()
+        params = abi.make_params("rf", 11, 100.0, 3000.0, 500.0, 6000.0)
+        objs = helpers.first_library_objects(batch.references, batch.lengths, 1000.0)
+        table = helpers.table_for(batch, objs)
+    else:
+        lib, batch, params, table = _setup(config)
+    want, _, _, _ = oracle_lib.graph_build(table.rows, table.n_scaffolds, params, batch)
+    monkeypatch.setenv("BESST_KS", "global")
+    got = cuda_engine.graph_build(table, params, batch)
+    helpers.assert_graph_equal(got, want, label="global KS %s" % config)
+    monkeypatch.delenv("BESST_KS")
+    got = cuda_engine.graph_build(table, params, batch)
+    helpers.assert_graph_equal(got, want, label="block KS %s" % config)
+    if config == "mixed_edge_sizes":
+        ll = (want.flags & abi.EDGE_LL) != 0
+        assert (want.nr_links[ll] > 2048).any() and (want.nr_links[ll] <= 2048).any()
+
+
 def test_device_resident_records_equal_host_records(cuda_engine):
     import torch
     lib, batch, params, table = _setup("small_mp_cont")
