@@ -239,8 +239,9 @@ constexpr int GB_THREADS = 256;
 constexpr int GB_WARPS = GB_THREADS / 32;
 constexpr int GB_ITEMS = 8;
 constexpr int GB_TILE = GB_THREADS * GB_ITEMS;   // 2048 tuples per block
-constexpr int GB_HT = 2 * GB_TILE;               // hash slots
 constexpr int GB_DMAX = 512;                     // distinct edges per block
+constexpr int GB_HT = 2 * GB_DMAX;               // hash slots (load <= 0.5 for the blocks this kernel accepts)
+constexpr int GB_PROBES = 96;                    // longer probe sequences mean more than GB_DMAX edges (or bad luck): fall back
 constexpr u64 GB_EMPTY = ~0ull;
 
 struct GroupSmem {
@@ -248,6 +249,7 @@ struct GroupSmem {
         u64 ht[GB_HT];          // hash table of (u << 32 | v) ...
         int2 stage[GB_TILE];    // ... later the observations in grouped order
     };
+    static_assert(sizeof(u64) * GB_HT <= sizeof(int2) * GB_TILE, "union sizes");
     unsigned short id_of_slot[GB_HT];
     unsigned short warp_hist[GB_WARPS][GB_DMAX];
     u64 key_of_id[GB_DMAX];
@@ -256,10 +258,10 @@ struct GroupSmem {
     u32 n_ids, run_base, overflow;
 };
 
-__device__ __forceinline__ u32 gb_insert(u64* ht, u64 key) {
+__device__ __forceinline__ u32 gb_insert(u64* ht, u64 key, u32* overflow) {
     u32 h = ((u32)(key >> 32) * 0x9E3779B1u) ^ ((u32)key * 0x85EBCA77u);
-    h = (h >> 11) & (GB_HT - 1);
-    for (;;) {
+    h = (h >> 12) & (GB_HT - 1);
+    for (int probe = 0; probe < GB_PROBES; ++probe) {
         const u64 cur = ht[h];
         if (cur == key) return h;
         if (cur == GB_EMPTY) {
@@ -268,6 +270,8 @@ __device__ __forceinline__ u32 gb_insert(u64* ht, u64 key) {
         }
         h = (h + 1) & (GB_HT - 1);
     }
+    *overflow = 1;
+    return 0;
 }
 
 // gstate: [0] = runs so far, [1] = overflow flags (1: a block with too many edges, 2: run capacity)
@@ -282,8 +286,8 @@ __global__ void __launch_bounds__(GB_THREADS, 4)
     const long long base = (long long)blockIdx.x * GB_TILE;
     const int count = (n - base < GB_TILE) ? (int)(n - base) : GB_TILE;
 
-    for (int i = threadIdx.x; i < GB_HT; i += GB_THREADS) S.ht[i] = GB_EMPTY;
-    for (int i = threadIdx.x; i < GB_WARPS * GB_DMAX / 2; i += GB_THREADS) reinterpret_cast<u32*>(&S.warp_hist[0][0])[i] = 0;
+    for (int i = threadIdx.x; i < GB_HT / 2; i += GB_THREADS) reinterpret_cast<ulonglong2*>(S.ht)[i] = make_ulonglong2(GB_EMPTY, GB_EMPTY);
+    for (int i = threadIdx.x; i < GB_WARPS * GB_DMAX / 8; i += GB_THREADS) reinterpret_cast<uint4*>(&S.warp_hist[0][0])[i] = make_uint4(0, 0, 0, 0);
     if (threadIdx.x == 0) { S.n_ids = 0; S.overflow = 0; }
     __syncthreads();
 
@@ -304,7 +308,7 @@ __global__ void __launch_bounds__(GB_THREADS, 4)
             const u32 peers = __match_any_sync(vmask, key);
             const int leader = __ffs(peers) - 1;
             u32 slot = 0;
-            if (lane == leader) slot = gb_insert(S.ht, key);
+            if (lane == leader) slot = gb_insert(S.ht, key, &S.overflow);
             slot = __shfl_sync(vmask, slot, leader);
             meta[i] = slot | ((u32)__popc(peers & lt_mask) << 12) | ((u32)(__popc(peers) - 1) << 17) | ((u32)leader << 22);
         }
@@ -313,10 +317,10 @@ __global__ void __launch_bounds__(GB_THREADS, 4)
 
     // ---- phase 2: dense local ids in slot order --------------------------------------------------
     {
-        constexpr int PER = GB_HT / GB_THREADS;   // 16 slots per thread
+        constexpr int PER = GB_HT / GB_THREADS;   // slots k * GB_THREADS + thread: conflict-free
         u32 used = 0;
 #pragma unroll
-        for (int k = 0; k < PER; ++k) used |= (S.ht[threadIdx.x * PER + k] != GB_EMPTY ? 1u : 0u) << k;
+        for (int k = 0; k < PER; ++k) used |= (S.ht[k * GB_THREADS + threadIdx.x] != GB_EMPTY ? 1u : 0u) << k;
         const u32 c = (u32)__popc(used);
         u32 incl = c;
 #pragma unroll
@@ -336,14 +340,14 @@ __global__ void __launch_bounds__(GB_THREADS, 4)
 #pragma unroll
         for (int k = 0; k < PER; ++k)
             if (used >> k & 1u) {
-                const int s = threadIdx.x * PER + k;
+                const int s = k * GB_THREADS + threadIdx.x;
                 S.id_of_slot[s] = (unsigned short)id;
                 if (id < GB_DMAX) S.key_of_id[id] = S.ht[s];
                 ++id;
             }
         if (threadIdx.x == 0) {
             S.n_ids = total;
-            if (total > GB_DMAX) { S.overflow = 1; atomicOr(gstate + 1, 1u); }
+            if (total > GB_DMAX || S.overflow) { S.overflow = 1; atomicOr(gstate + 1, 1u); }
             else S.run_base = atomicAdd(gstate, total);
         }
     }
@@ -911,38 +915,47 @@ __global__ void __launch_bounds__(LS_THREADS) k_ll_write(const unsigned char* __
     if (blockIdx.x == 0 && threadIdx.x == 0) ll_off[n_edges] = block_sums[gridDim.x];
 }
 
-// ---- K5': KS statistic of the edges with at most KB_G links, one CTA per ~KB_G links ---------------------
+// ---- K5': KS statistic of the edges with at most KB_G links, one CTA per ~KB_W links ---------------------
 // The per-edge observation lists are contiguous (CSR order).  A CTA takes the LL edges whose first
 // link falls into its window of the compact "small LL link space", builds (local edge << B | value)
 // keys for both lists in shared memory, sorts each with an in-block LSD radix sort (stable warp
 // multisplit, 8-bit digits, only as many passes as the key has bits) and evaluates the two-sided
-// ECDF difference with the same co-ranking walk as k_ks_eval -- all in one launch, one read of the
-// observations, no global sort passes.  Edges with more links take the device-wide path above.
+// ECDF difference -- all in one launch, one read of the observations, no global sort passes.
+// Evaluation: every element finds its rank in the other list by binary search (shared memory); the
+// statistic of an edge is max |i/n - k/n| over (own rank i, other rank k).  For one edge the fp64
+// value is strictly increasing in |i - k| (steps of 1/n >= 2^-11 against rounding errors of 2^-52),
+// so the per-edge maximum of the INTEGER |i - k| is taken first (shared-memory atomics) and only
+// its maximisers evaluate scipy's expression fabs(i/n - k/n) in fp64: bit-identical, two fp64
+// divisions per edge instead of per link.  Edges with more links take the device-wide path above.
 constexpr int KB_THREADS = 256;
 constexpr int KB_WARPS = KB_THREADS / 32;
-constexpr int KB_G = 2048;            // window of the small LL link space per CTA; also the largest edge handled here
-constexpr int KB_CAP = 2 * KB_G;      // links per CTA: < KB_G (window) + KB_G (the edge straddling its end)
-constexpr int KB_ITEMS = KB_CAP / KB_THREADS;   // 16
+constexpr int KB_G = 2048;            // largest edge handled here
+constexpr int KB_W = 768;             // window of the small LL link space per CTA (>= the number of its edges)
+constexpr int KB_CAP = 3072;          // links per CTA: < KB_W (window) + KB_G (the edge straddling its end)
+static_assert(KB_W + KB_G <= KB_CAP + 1, "CTA capacity");
 
 struct KsBlockSmem {
-    u32 buf[3][KB_CAP];
-    unsigned short warp_hist[KB_WARPS][256];
+    u32 buf[3][KB_CAP];                      // two key lists + ping-pong; the free one holds the per-edge means afterwards
+    unsigned short warp_hist[KB_WARPS][256]; // later: u32 max |i - k| per local edge
     u32 digit_start[256];
     u32 warp_sum[KB_WARPS];
-    u32 seg_start[KB_G + 1];   // first position of every local edge
+    u32 seg_start[KB_W + 1];                 // first position of every local edge
 };
+static_assert(sizeof(double2) * KB_W <= sizeof(u32) * KB_CAP, "means fit the free key buffer");
+static_assert(sizeof(u32) * KB_W <= sizeof(unsigned short) * KB_WARPS * 256, "integer maxima fit the histogram area");
 
-// stable LSD pass over `count` keys: src -> dst by digit (key >> shift) & 255
+// stable LSD pass over `count` <= ITEMS * 256 keys: src -> dst by digit (key >> shift) & 255
+template <int ITEMS>
 __device__ __forceinline__ void kb_radix_pass(KsBlockSmem& S, const u32* src, u32* dst, int count, int shift) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const u32 lt_mask = (1u << lane) - 1u;
     for (int i = threadIdx.x; i < KB_WARPS * 256 / 2; i += KB_THREADS) reinterpret_cast<u32*>(&S.warp_hist[0][0])[i] = 0;
     __syncthreads();
-    u32 key[KB_ITEMS];
-    unsigned short rank[KB_ITEMS];
+    u32 key[ITEMS];
+    unsigned short rank[ITEMS];
 #pragma unroll
-    for (int i = 0; i < KB_ITEMS; ++i) {
-        const int p = warp * (32 * KB_ITEMS) + i * 32 + lane;
+    for (int i = 0; i < ITEMS; ++i) {
+        const int p = warp * (32 * ITEMS) + i * 32 + lane;
         const bool valid = p < count;
         const u32 vmask = __ballot_sync(0xffffffffu, valid);
         key[i] = 0; rank[i] = 0;
@@ -983,8 +996,8 @@ __device__ __forceinline__ void kb_radix_pass(KsBlockSmem& S, const u32* src, u3
     }
     __syncthreads();
 #pragma unroll
-    for (int i = 0; i < KB_ITEMS; ++i) {
-        const int p = warp * (32 * KB_ITEMS) + i * 32 + lane;
+    for (int i = 0; i < ITEMS; ++i) {
+        const int p = warp * (32 * ITEMS) + i * 32 + lane;
         if (p < count) {
             const u32 d = (key[i] >> shift) & 255u;
             dst[S.digit_start[d] + S.warp_hist[warp][d] + rank[i]] = key[i];
@@ -1009,62 +1022,110 @@ struct KsBlockArgs {
     double* ks;
 };
 
-// one side of the KS evaluation over the CTA's sorted lists (see k_ks_eval)
-template <int SIDE>
-__device__ __forceinline__ void kb_eval(const KsBlockSmem& S, const KsBlockArgs& A, const u32* own, const u32* other, int count,
-                                        long long k_lo, int n_local) {
-    const u32 vmask = (1u << A.value_bits) - 1u;
-    for (int c = threadIdx.x; c * KS_CHUNK < count; c += KB_THREADS) {
-        int j = c * KS_CHUNK;
-        const int j_end = (j + KS_CHUNK < count) ? j + KS_CHUNK : count;
-        while (j < j_end) {
+// rank of own[j] in the other list of its edge: #{y : y - m_other <= x - m_own}, and whether own[j] is
+// the last of a run of equal values (ks_2samp evaluates the ECDFs at distinct points)
+struct KbRank {
+    int lid, i, k;   // local edge, own rank (1-based, ties counted), other rank; lid < 0: not an evaluation point
+};
+
+__device__ __forceinline__ KbRank kb_rank(const KsBlockSmem& S, const double2* means, const u32* own, const u32* other, int j,
+                                          int count, int value_bits, int side) {
+    KbRank r;
+    r.lid = -1; r.i = 0; r.k = 0;
+    if (j >= count) return r;
+    const u32 vmask = (1u << value_bits) - 1u;
+    const u32 key = own[j];
+    const int lid = (int)(key >> value_bits);
+    const int s0 = (int)S.seg_start[lid], s1 = (int)S.seg_start[lid + 1];
+    if (j + 1 < s1 && own[j + 1] == key) return r;   // not the last of its run of ties
+    const double2 m = means[lid];
+    const double m_own = side == 0 ? m.x : m.y, m_other = side == 0 ? m.y : m.x;
+    const double z = (double)(long long)(key & vmask) - m_own;
+    int lo = s0, hi = s1;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if ((double)(long long)(other[mid] & vmask) - m_other <= z) lo = mid + 1; else hi = mid;
+    }
+    r.lid = lid; r.i = j + 1 - s0; r.k = lo - s0;
+    return r;
+}
+
+template <int ITEMS>
+__device__ __forceinline__ void kb_sort_and_eval(KsBlockSmem& S, const KsBlockArgs& A, int count, long long k_lo, int n_local) {
+    const int lane = threadIdx.x & 31;
+    u32* l1 = S.buf[0];
+    u32* l2 = S.buf[1];
+    u32* tmp = S.buf[2];
+    int key_bits = A.value_bits;
+    for (int t = n_local - 1; t > 0; t >>= 1) ++key_bits;
+    // list 1: l1 <-> tmp; list 2: l2 <-> whichever of the two is free afterwards
+    for (int shift = 0; shift < key_bits; shift += 8) {
+        kb_radix_pass<ITEMS>(S, l1, tmp, count, shift);
+        u32* x = l1; l1 = tmp; tmp = x;
+    }
+    for (int shift = 0; shift < key_bits; shift += 8) {
+        kb_radix_pass<ITEMS>(S, l2, tmp, count, shift);
+        u32* x = l2; l2 = tmp; tmp = x;
+    }
+    // per-edge means of the two lists (CreateGraph.py:584,591) and integer maxima
+    double2* means = reinterpret_cast<double2*>(tmp);
+    u32* gap_max = reinterpret_cast<u32*>(&S.warp_hist[0][0]);
+    for (int lid = threadIdx.x; lid < n_local; lid += KB_THREADS) {
+        const long long e = __ldg(A.ll_edges + k_lo + lid);
+        const int n = (int)(S.seg_start[lid + 1] - S.seg_start[lid]);
+        const long long su = A.sum_u[e];
+        const long long sy = (long long)n * A.max_v[e] - (A.obs_sum[e] - su);
+        means[lid] = make_double2((double)su / (double)n, (double)sy / (double)n);
+        gap_max[lid] = 0;
+    }
+    __syncthreads();
+    // pass A: integer |i - k| of every evaluation point of both sides, per-edge maximum
+    unsigned short gi[2][ITEMS], gk[2][ITEMS];
+#pragma unroll
+    for (int side = 0; side < 2; ++side) {
+        const u32* own = side == 0 ? l1 : l2;
+        const u32* other = side == 0 ? l2 : l1;
+#pragma unroll
+        for (int t = 0; t < ITEMS; ++t) {
+            const int j = t * KB_THREADS + threadIdx.x;
+            const KbRank r = kb_rank(S, means, own, other, j, count, A.value_bits, side);
+            gi[side][t] = (unsigned short)r.i;
+            gk[side][t] = (unsigned short)r.k;
+            const u32 gap = (u32)(r.i > r.k ? r.i - r.k : r.k - r.i);
+            // lanes hold consecutive positions: equal edges are contiguous -> one atomic per (warp, edge)
+            const u32 peers = __match_any_sync(0xffffffffu, r.lid);
+            const u32 best = __reduce_max_sync(peers, gap);
+            if (r.lid >= 0 && lane == __ffs(peers) - 1 && best > 0) atomicMax(gap_max + r.lid, best);
+        }
+    }
+    __syncthreads();
+    // pass B: the maximisers evaluate fabs(F_own - F_other) exactly like scipy and publish the edge's statistic
+#pragma unroll
+    for (int side = 0; side < 2; ++side) {
+        const u32* own = side == 0 ? l1 : l2;
+#pragma unroll
+        for (int t = 0; t < ITEMS; ++t) {
+            const int j = t * KB_THREADS + threadIdx.x;
+            const int i = gi[side][t], k = gk[side][t];
+            if (j >= count || i == 0) continue;   // i >= 1 for every evaluation point
+            const u32 gap = (u32)(i > k ? i - k : k - i);
             const int lid = (int)(own[j] >> A.value_bits);
-            const long long e = A.ll_edges[k_lo + lid];
-            const int s0 = (int)S.seg_start[lid], s1 = (lid + 1 < n_local) ? (int)S.seg_start[lid + 1] : count;
-            const int n = s1 - s0;
-            const long long su = A.sum_u[e];
-            const long long sy = (long long)n * A.max_v[e] - (A.obs_sum[e] - su);
-            const double m1 = (double)su / (double)n;   // l1_mean (:584)
-            const double m2 = (double)sy / (double)n;   // l2_mean (:591)
-            const double m_own = SIDE == 0 ? m1 : m2, m_other = SIDE == 0 ? m2 : m1;
-            const int stop = j_end < s1 ? j_end : s1;
-            int q;
-            {
-                const double z = (double)(long long)(own[j] & vmask) - m_own;
-                int lo = s0, hi = s1;
-                while (lo < hi) {
-                    const int mid = (lo + hi) >> 1;
-                    if ((double)(long long)(other[mid] & vmask) - m_other <= z) lo = mid + 1; else hi = mid;
-                }
-                q = lo;
-            }
-            double dmax = 0.0;
-            u32 cur = own[j];
-            for (; j < stop; ++j) {
-                const bool at_end = j + 1 >= s1;
-                const u32 nxt = at_end ? cur : own[j + 1];
-                const double z = (double)(long long)(cur & vmask) - m_own;
-                while (q < s1 && (double)(long long)(other[q] & vmask) - m_other <= z) ++q;
-                if (at_end || nxt != cur) {
-                    const double f_own = (double)(j + 1 - s0) / (double)n;
-                    const double f_other = (double)(q - s0) / (double)n;
-                    const double diff = SIDE == 0 ? fabs(f_own - f_other) : fabs(f_other - f_own);
-                    if (diff > dmax) dmax = diff;
-                }
-                cur = nxt;
-            }
-            if (dmax > 0.0) atomicMax(reinterpret_cast<unsigned long long*>(A.ks + e), (unsigned long long)__double_as_longlong(dmax));
+            if (gap == 0 || gap != gap_max[lid]) continue;
+            const int n = (int)(S.seg_start[lid + 1] - S.seg_start[lid]);
+            const double f_own = (double)i / (double)n, f_other = (double)k / (double)n;
+            const double diff = side == 0 ? fabs(f_own - f_other) : fabs(f_other - f_own);
+            const long long e = __ldg(A.ll_edges + k_lo + lid);
+            atomicMax(reinterpret_cast<unsigned long long*>(A.ks + e), (unsigned long long)__double_as_longlong(diff));
         }
     }
 }
 
-__global__ void __launch_bounds__(KB_THREADS, 3) k_ks_block(const KsBlockArgs A) {
-    extern __shared__ __align__(16) unsigned char kb_smem[];
-    KsBlockSmem& S = *reinterpret_cast<KsBlockSmem*>(kb_smem);
+__global__ void __launch_bounds__(KB_THREADS, 4) k_ks_block(const KsBlockArgs A) {
+    __shared__ KsBlockSmem S;
     __shared__ long long s_k[2];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (threadIdx.x < 2) {   // first small LL edge starting at or after the window's start / end
-        const u32 target = (u32)(((long long)blockIdx.x + threadIdx.x) * KB_G);
+        const u32 target = (u32)(((long long)blockIdx.x + threadIdx.x) * KB_W);
         long long lo = 0, hi = A.n_small;
         while (lo < hi) {
             const long long mid = (lo + hi) >> 1;
@@ -1081,9 +1142,6 @@ __global__ void __launch_bounds__(KB_THREADS, 3) k_ks_block(const KsBlockArgs A)
     for (int i = threadIdx.x; i <= n_local; i += KB_THREADS) S.seg_start[i] = __ldg(A.ll_start + k_lo + i) - base;
     __syncthreads();
     // keys of both lists, edge by edge (one warp per edge)
-    u32* l1 = S.buf[0];
-    u32* l2 = S.buf[1];
-    u32* tmp = S.buf[2];
     for (int lid = warp; lid < n_local; lid += KB_WARPS) {
         const long long e = __ldg(A.ll_edges + k_lo + lid);
         const long long b = A.row_ptr[e];
@@ -1092,24 +1150,15 @@ __global__ void __launch_bounds__(KB_THREADS, 3) k_ks_block(const KsBlockArgs A)
         const u32 hi = (u32)lid << A.value_bits;
         const int s0 = (int)S.seg_start[lid];
         for (int k = lane; k < n; k += 32) {
-            l1[s0 + k] = hi | (u32)__ldg(A.obs_u + b + k);
-            l2[s0 + k] = hi | (u32)(mv - __ldg(A.obs_v + b + k));   // abs(x - max_obs2), :588-590
+            S.buf[0][s0 + k] = hi | (u32)__ldg(A.obs_u + b + k);
+            S.buf[1][s0 + k] = hi | (u32)(mv - __ldg(A.obs_v + b + k));   // abs(x - max_obs2), :588-590
         }
     }
     __syncthreads();
-    int key_bits = A.value_bits;
-    for (int t = n_local - 1; t > 0; t >>= 1) ++key_bits;
-    // list 1: l1 <-> tmp; list 2: l2 <-> whichever of the two is free afterwards
-    for (int shift = 0; shift < key_bits; shift += 8) {
-        kb_radix_pass(S, l1, tmp, count, shift);
-        u32* x = l1; l1 = tmp; tmp = x;
-    }
-    for (int shift = 0; shift < key_bits; shift += 8) {
-        kb_radix_pass(S, l2, tmp, count, shift);
-        u32* x = l2; l2 = tmp; tmp = x;
-    }
-    kb_eval<0>(S, A, l1, l2, count, k_lo, n_local);
-    kb_eval<1>(S, A, l2, l1, count, k_lo, n_local);
+    if (count <= 4 * KB_THREADS) kb_sort_and_eval<4>(S, A, count, k_lo, n_local);
+    else if (count <= 6 * KB_THREADS) kb_sort_and_eval<6>(S, A, count, k_lo, n_local);
+    else if (count <= 8 * KB_THREADS) kb_sort_and_eval<8>(S, A, count, k_lo, n_local);
+    else kb_sort_and_eval<12>(S, A, count, k_lo, n_local);
 }
 
 // compact list of the LL edges with at most `thr` links: packed sums (edges << 32 | links)
@@ -1324,11 +1373,6 @@ int besst_launch_graph(besst_ctx* ctx, const besst_lib_params& p, const besst_li
         BESST_CUDA_TRY(ctx, ctx->run_state.ensure(64));
         u32* gstate = ctx->run_state.as<u32>();
         BESST_CUDA_TRY(ctx, cudaMemsetAsync(gstate, 0, 64, ctx->stream));
-        static bool attr_done = false;
-        if (!attr_done) {
-            cudaFuncSetAttribute(k_group_blocks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(GroupSmem));
-            attr_done = true;
-        }
         {
             KTimer kt(ctx, BESST_K_GROUP);
             k_group_blocks<<<(unsigned)n_gblocks, GB_THREADS, sizeof(GroupSmem), ctx->stream>>>(
@@ -1445,7 +1489,7 @@ int besst_launch_graph(besst_ctx* ctx, const besst_lib_params& p, const besst_li
         // ---- edges with at most KB_G links: in-block sort + evaluation (k_ks_block) ------------------
         // BESST_KS=global sends every edge through the device-wide sorts below (A/B, tests)
         const char* ks_env = getenv("BESST_KS");
-        const bool block_ks = !(ks_env && ks_env[0] == 'g') && value_bits + 11 <= 32;
+        const bool block_ks = !(ks_env && ks_env[0] == 'g') && value_bits + 10 <= 32;   // local edge ids take <= 10 bits
         const int big_thr = block_ks ? KB_G : 0;
         if (block_ks) {
             BESST_CUDA_TRY(ctx, ctx->heads.ensure(8 * (size_t)(ls_blocks + 2)));
@@ -1463,17 +1507,12 @@ int besst_launch_graph(besst_ctx* ctx, const besst_lib_params& p, const besst_li
                 u32* ll_edges = ctx->ks_key[0].as<u32>();
                 u32* ll_start = ctx->ks_key[1].as<u32>();
                 { KTimer kt(ctx, BESST_K_EDGE_SCORE); k_llc_write<<<ls_blocks, LS_THREADS, 0, ctx->stream>>>(EA.flags, EA.nr, E, KB_G, bs, ll_edges, ll_start); }
-                static bool attr_done = false;
-                if (!attr_done) {
-                    cudaFuncSetAttribute(k_ks_block, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(KsBlockSmem));
-                    attr_done = true;
-                }
                 KsBlockArgs B;
                 B.row_ptr = EA.row_ptr; B.nr = EA.nr; B.sum_u = EA.sum_u; B.obs_sum = EA.obs; B.max_v = EA.max_v;
                 B.obs_u = EA.obs_u; B.obs_v = EA.obs_v; B.ll_edges = ll_edges; B.ll_start = ll_start;
                 B.n_small = n_small; B.n_links = n_small_links; B.value_bits = value_bits; B.ks = EA.ks;
-                const unsigned windows = (unsigned)((n_small_links + KB_G - 1) / KB_G);
-                { KTimer kt(ctx, BESST_K_KS_BLOCK); k_ks_block<<<windows, KB_THREADS, sizeof(KsBlockSmem), ctx->stream>>>(B); }
+                const unsigned windows = (unsigned)((n_small_links + KB_W - 1) / KB_W);
+                { KTimer kt(ctx, BESST_K_KS_BLOCK); k_ks_block<<<windows, KB_THREADS, 0, ctx->stream>>>(B); }
                 BESST_CUDA_TRY(ctx, cudaGetLastError());
             }
         }
