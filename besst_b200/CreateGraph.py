@@ -408,7 +408,7 @@ def PE(Contigs, Scaffolds, Information, C_dict, param, small_contigs, small_scaf
         engine = default_engine()
     batch = as_batch(bam_file)
     table = ContigTable(bam_file.references, bam_file.lengths, Contigs, small_contigs, Scaffolds, small_scaffolds)
-    res = engine.graph_build(table, engine_params(param), batch)
+    res = engine.graph_build(table, engine_params(param), batch, view=True)   # consumed below, before the next build
     _populate(G, G_prime, res, table, param)
     cnt = res.counters
     print('ELAPSED reading file:', time() - start, file=Information)

@@ -117,8 +117,8 @@ class CudaBackend(object):
     def counts_tensor(self, values):
         return self.torch.tensor(values, dtype=self.torch.int64, device=self.device)
 
-    def fetch(self, sizes):
-        return self.engine.fetch(sizes)
+    def fetch(self, sizes, view=False):
+        return self.engine.fetch_view(sizes) if view else self.engine.fetch(sizes)
 
 
 class _CudaArray(object):
@@ -190,12 +190,13 @@ class DistributedGraphBuild(object):
         return sizes
 
     # -- results ------------------------------------------------------------------------------------
-    def fetch_local(self):
+    def fetch_local(self, view=False):
         """This rank's edges (GraphResult) with first_idx rewritten to the GLOBAL ordinal of the
         edge's first link (source-rank prefix + ordinal in the source's stream), and the reduced
-        aligned_len / counters."""
+        aligned_len / counters.  view=True: zero-copy views of the engine's pinned result buffers
+        (valid until the next view)."""
         L = self.last
-        res = self.b.fetch(L["sizes"])
+        res = self.b.fetch(L["sizes"], view) if view else self.b.fetch(L["sizes"])
         if res.n_edges:
             starts = np.concatenate([[0], np.cumsum(L["recv_splits"])])
             src = np.searchsorted(starts, res.first_idx, side="right") - 1

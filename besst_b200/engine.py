@@ -70,13 +70,14 @@ class CudaEngine(object):
         self._check(self._L.besst_graph_view(self._ctx, C.byref(out)), "besst_graph_view")
         return abi.graph_result(out, abi.view_graph_out(out, sizes))
 
-    def graph_build(self, table, params, batch):
-        """Host-buffer call used by CreateGraph.PE: table + RecordBatch in, GraphResult out."""
+    def graph_build(self, table, params, batch, view=False):
+        """Host-buffer call used by CreateGraph.PE: table + RecordBatch in, GraphResult out.
+        view=True: the arrays are views of the engine's pinned buffers (valid until the next view)."""
         self.set_table(table)
         keep = []
         rec = abi.make_records(batch, keepalive=keep)
         sizes = self.build(params, rec)
-        return self.fetch(sizes)
+        return self.fetch_view(sizes) if view else self.fetch(sizes)
 
     # -- the two halves around the multi-GPU exchange --------------------------------------
     def links_extract(self, params, records):

@@ -10,7 +10,7 @@ import oracle_lib
 class OracleEngine(object):
     name = "oracle"
 
-    def graph_build(self, table, params, batch):
+    def graph_build(self, table, params, batch, view=False):
         res, tuples, fishy, consistent = oracle_lib.graph_build(table.rows, table.n_scaffolds, params, batch)
         assert consistent, "oracle: G and G_prime disagree on large-large edges"
         self.last_tuples = tuples
