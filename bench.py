@@ -29,6 +29,7 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+os.environ["NCCL_DEBUG"] = os.environ.get("BESST_NCCL_DEBUG", "WARN")   # NCCL's version banner goes to stdout: keep the one JSON line alone
 
 import numpy as np  # noqa: E402
 

@@ -17,7 +17,8 @@ EXPORTS = ["besst_abi_version", "besst_create", "besst_destroy", "besst_last_err
            "besst_links_fishy_device", "besst_links_partials", "besst_links_to_graph", "besst_libmetrics",
            "besst_gapest_batch", "besst_last_timing", "besst_kernel_launches", "besst_set_profiling",
            "besst_kernel_profile", "besst_links_partials_device", "besst_links_fetch", "besst_links_partition",
-           "besst_trsk_sd_batch", "besst_set_stream", "besst_graph_view"]
+           "besst_trsk_sd_batch", "besst_set_stream", "besst_graph_view", "besst_links_group", "besst_runs_route",
+           "besst_runs_pack", "besst_runs_to_graph"]
 
 _lib = None
 
@@ -66,6 +67,11 @@ def load():
     L.besst_trsk_sd_batch.argtypes = [vp, C.POINTER(abi.LibParams), vp, vp, vp, i64, vp]
     L.besst_set_stream.argtypes = [vp, vp]
     L.besst_graph_view.argtypes = [vp, C.POINTER(abi.GraphOut)]
+    L.besst_links_group.argtypes = [vp, C.POINTER(i64)]
+    L.besst_runs_route.argtypes = [vp, i32, vp, vp]
+    L.besst_runs_pack.argtypes = [vp, i32, vp, vp]
+    L.besst_runs_to_graph.argtypes = [vp, C.POINTER(abi.LibParams), vp, i64, vp, i64, i32, i32, vp, vp, vp, vp, i64,
+                                      C.POINTER(abi.GraphSizes)]
     if L.besst_abi_version() != abi.ABI_VERSION:
         raise BesstLibraryError("ABI version mismatch: library %d, binding %d" % (L.besst_abi_version(), abi.ABI_VERSION))
     _lib = L

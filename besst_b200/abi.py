@@ -26,6 +26,8 @@ ERRORS = {-1: "invalid argument", -2: "CUDA error", -3: "out of memory", -4: "ba
 
 CONTIG_ROW_DTYPE = np.dtype([("state", "<i4"), ("scaffold", "<i4"), ("direction", "<i4"), ("position", "<i4"),
                              ("length", "<i4"), ("scaf_length", "<i4"), ("in_largest", "<i4"), ("reserved", "<i4")])
+RUN_DESC_DTYPE = np.dtype([("u", "<u4"), ("v", "<u4"), ("count", "<u4"), ("first", "<u4"), ("offset", "<u4"), ("block", "<u4")])
+RUN_BLOCK = 2048   # links per grouping block (GB_TILE in besst_edges.cu)
 LINK_TUPLE_DTYPE = np.dtype([("u", "<u4"), ("v", "<u4"), ("obs_u", "<i4"), ("obs_v", "<i4")])
 
 

@@ -204,7 +204,7 @@ extern "C" int besst_links_extract(besst_ctx* ctx, const besst_lib_params* param
     int rc = check_params(ctx, params);
     if (rc) return rc;
     cudaSetDevice(ctx->device);
-    ctx->have_links = ctx->have_graph = false;
+    ctx->have_links = ctx->have_graph = ctx->have_runs = false;
     ctx->n_stage_marks = 0;
     ctx->prof_used = 0;
     besst_mark(ctx);
@@ -269,12 +269,84 @@ extern "C" int besst_links_partition(besst_ctx* ctx, int32_t world, besst_link_t
                                      uint32_t* out_ordinals_device, uint64_t* out_fishy_device, int64_t* tuple_counts,
                                      int64_t* fishy_counts) {
     if (!ctx || !ctx->have_links) { if (ctx) ctx->err = "no extracted links"; return BESST_E_STATE; }
-    if (!tuple_counts || !fishy_counts || (ctx->n_tuples > 0 && !out_tuples_device) || (ctx->n_fishy_keys > 0 && !out_fishy_device)) {
+    if (!tuple_counts || !fishy_counts || (ctx->n_fishy_keys > 0 && !out_fishy_device)) {
         ctx->err = "links_partition: bad arguments";
         return BESST_E_INVALID;
     }
     cudaSetDevice(ctx->device);
     return besst_launch_partition(ctx, world, out_tuples_device, out_ordinals_device, out_fishy_device, tuple_counts, fishy_counts);
+}
+
+extern "C" int besst_links_group(besst_ctx* ctx, int64_t* n_runs) {
+    if (!ctx || !ctx->have_links) { if (ctx) ctx->err = "no extracted links"; return BESST_E_STATE; }
+    cudaSetDevice(ctx->device);
+    ctx->have_runs = false;
+    int bv = 1;
+    {
+        const uint64_t m = (uint64_t)(2 * ctx->n_scaffolds > 0 ? 2 * ctx->n_scaffolds - 1 : 1);
+        while (bv < 32 && (m >> bv)) ++bv;
+    }
+    const int64_t n = ctx->n_tuples;
+    const int64_t blocks = (n + 2047) / 2048;
+    int bb = 1;
+    while (bb < 32 && ((uint64_t)(blocks > 1 ? blocks - 1 : 1) >> bb)) ++bb;
+    if (2 * bv + bb > 64) return 1;
+    int64_t R = 0;
+    int overflow = 0;
+    int rc = besst_group_tuples(ctx, ctx->tuples.as<besst_link_tuple>(), n, bv, bb, &R, &overflow);
+    if (rc) return rc;
+    if (overflow) return 1;
+    ctx->n_runs = R;
+    ctx->run_block_bits = bb;
+    ctx->have_runs = true;
+    if (n_runs) *n_runs = R;
+    return BESST_OK;
+}
+
+extern "C" int besst_runs_route(besst_ctx* ctx, int32_t world, int64_t* link_counts, int64_t* run_counts) {
+    if (!ctx || !ctx->have_runs) { if (ctx) ctx->err = "no grouped runs (besst_links_group)"; return BESST_E_STATE; }
+    if (world < 1 || world > 16 || !link_counts || !run_counts) { ctx->err = "runs_route: bad arguments"; return BESST_E_INVALID; }
+    cudaSetDevice(ctx->device);
+    return besst_launch_runs_route(ctx, world, link_counts, run_counts);
+}
+
+extern "C" int besst_runs_pack(besst_ctx* ctx, int32_t world, int32_t* out_obs_device, besst_run_desc* out_desc_device) {
+    if (!ctx || !ctx->have_runs) { if (ctx) ctx->err = "no grouped runs (besst_links_group)"; return BESST_E_STATE; }
+    if (world < 1 || world > 16 || (ctx->n_runs > 0 && (!out_obs_device || !out_desc_device))) { ctx->err = "runs_pack: bad arguments"; return BESST_E_INVALID; }
+    cudaSetDevice(ctx->device);
+    return besst_launch_runs_pack(ctx, world, out_obs_device, out_desc_device);
+}
+
+extern "C" int besst_runs_to_graph(besst_ctx* ctx, const besst_lib_params* params, const int32_t* obs_device, int64_t n_links,
+                                   const besst_run_desc* desc_device, int64_t n_runs, int32_t world, int32_t block_bits,
+                                   const int64_t* src_run_counts, const int64_t* src_link_counts, const int64_t* src_first_base,
+                                   const uint64_t* fishy_keys_device, int64_t n_fishy_keys, besst_graph_sizes* sizes) {
+    if (!ctx) return BESST_E_INVALID;
+    int rc = check_params(ctx, params);
+    if (rc) return rc;
+    if (n_links < 0 || n_runs < 0 || n_fishy_keys < 0 || world < 1 || world > 16 || block_bits < 1 || block_bits > 31 ||
+        (n_runs > 0 && (!obs_device || !desc_device)) || (n_links > 0 && n_runs == 0) || n_links >= (1ll << 30) ||
+        !src_run_counts || !src_link_counts || !src_first_base || (n_fishy_keys > 0 && !fishy_keys_device)) {
+        ctx->err = "runs_to_graph: bad arguments";
+        return BESST_E_INVALID;
+    }
+    cudaSetDevice(ctx->device);
+    int low_bits = 0;
+    rc = besst_launch_runs_import(ctx, desc_device, n_runs, world, block_bits, src_run_counts, src_link_counts, src_first_base, &low_bits);
+    if (rc) return rc;
+    BesstRunInput in;
+    in.grouped = reinterpret_cast<const int2*>(obs_device);
+    in.n_runs = n_runs;
+    in.low_bits = low_bits;
+    rc = besst_launch_graph_from_runs(ctx, *params, n_links, in, fishy_keys_device, n_fishy_keys);
+    if (rc) return rc;
+    ctx->have_runs = false;   // the run buffers now describe the received runs
+    if (sizes) {
+        sizes->n_edges = ctx->n_edges; sizes->n_links = ctx->n_links; sizes->n_contigs = ctx->n_contigs;
+        sizes->n_fishy = n_fishy_keys;
+        sizes->n_ll_links = ctx->n_ll_links;
+    }
+    return BESST_OK;
 }
 
 extern "C" int besst_set_stream(besst_ctx* ctx, void* cuda_stream) {

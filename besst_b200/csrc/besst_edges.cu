@@ -1292,8 +1292,192 @@ int besst_launch_trsk_sd(besst_ctx* ctx, const besst_lib_params& p, const double
     return BESST_OK;
 }
 
-int besst_launch_graph(besst_ctx* ctx, const besst_lib_params& p, const besst_link_tuple* d_tuples, int64_t n,
-                       const uint64_t* d_fishy, int64_t n_fishy) {
+// k_group_blocks over a device tuple array: grouped observations in ctx->grouped, run descriptors in
+// ctx->run_key[0] / run_val[0] / run_start / run_cnt / run_first.  *overflow: the stream has no local order
+// (a block with more than GB_DMAX edges, or more runs than n/8) -- use the radix bucket
+int besst_group_tuples(besst_ctx* ctx, const besst_link_tuple* d_tuples, int64_t n, int bv, int block_bits, int64_t* n_runs,
+                       int* overflow) {
+    *n_runs = 0;
+    *overflow = 0;
+    const size_t nz = (size_t)(n > 0 ? n : 1);
+    const int64_t n_gblocks = (n + GB_TILE - 1) / GB_TILE;
+    const int64_t run_cap64 = std::max<int64_t>(n / 8, 1 << 16);
+    const u32 run_cap = (u32)std::min<int64_t>(run_cap64, 0x7fffffff);
+    BESST_CUDA_TRY(ctx, ctx->grouped.ensure(8 * nz));
+    for (int k = 0; k < 2; ++k) {
+        BESST_CUDA_TRY(ctx, ctx->run_key[k].ensure(8 * (size_t)run_cap));
+        BESST_CUDA_TRY(ctx, ctx->run_val[k].ensure(4 * (size_t)run_cap));
+    }
+    BESST_CUDA_TRY(ctx, ctx->run_start.ensure(4 * (size_t)run_cap)); BESST_CUDA_TRY(ctx, ctx->run_cnt.ensure(4 * (size_t)run_cap));
+    BESST_CUDA_TRY(ctx, ctx->run_first.ensure(4 * (size_t)run_cap)); BESST_CUDA_TRY(ctx, ctx->run_off.ensure(4 * (size_t)run_cap));
+    BESST_CUDA_TRY(ctx, ctx->run_src.ensure(4 * (size_t)run_cap)); BESST_CUDA_TRY(ctx, ctx->run_len.ensure(4 * (size_t)run_cap));
+    BESST_CUDA_TRY(ctx, ctx->run_state.ensure(512));
+    if (n == 0) return BESST_OK;
+    u32* gstate = ctx->run_state.as<u32>();
+    BESST_CUDA_TRY(ctx, cudaMemsetAsync(gstate, 0, 64, ctx->stream));
+    {
+        KTimer kt(ctx, BESST_K_GROUP);
+        k_group_blocks<<<(unsigned)n_gblocks, GB_THREADS, sizeof(GroupSmem), ctx->stream>>>(
+            d_tuples, n, bv, block_bits, ctx->grouped.as<int2>(), ctx->run_key[0].as<u64>(), ctx->run_val[0].as<u32>(),
+            ctx->run_start.as<u32>(), ctx->run_cnt.as<u32>(), ctx->run_first.as<u32>(), gstate, run_cap);
+    }
+    BESST_CUDA_TRY(ctx, cudaGetLastError());
+    u32 hs[2] = {0, 0};
+    BESST_CUDA_TRY(ctx, cudaMemcpyAsync(hs, gstate, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    BESST_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    *n_runs = hs[0];
+    *overflow = (hs[1] != 0 || (int64_t)hs[0] > (int64_t)run_cap) ? 1 : 0;
+    return BESST_OK;
+}
+
+// ---- run-level multi-GPU exchange: route / pack on the sender, import on the receiver ------------------
+constexpr int RX_MAX_WORLD = 16;
+struct RouteBases { u32 link_base[RX_MAX_WORLD]; u32 run_base[RX_MAX_WORLD]; };
+
+// state: [0..15] links per destination, [16..31] runs per destination
+__global__ void __launch_bounds__(256) k_runs_route_count(const u64* __restrict__ run_key, const u32* __restrict__ run_cnt, long long R,
+                                                          int block_bits, int bv, int world, u32* state) {
+    __shared__ u32 s_l[RX_MAX_WORLD], s_r[RX_MAX_WORLD];
+    if (threadIdx.x < RX_MAX_WORLD) { s_l[threadIdx.x] = 0; s_r[threadIdx.x] = 0; }
+    __syncthreads();
+    const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r < R) {
+        const u64 key = run_key[r] >> block_bits;
+        const u32 d = besst_edge_dest((u32)(key >> bv), (u32)(key & ((1ull << bv) - 1ull)), world);
+        atomicAdd(&s_l[d], run_cnt[r]);
+        atomicAdd(&s_r[d], 1u);
+    }
+    __syncthreads();
+    if (threadIdx.x < world) {
+        if (s_l[threadIdx.x]) atomicAdd(state + threadIdx.x, s_l[threadIdx.x]);
+        if (s_r[threadIdx.x]) atomicAdd(state + RX_MAX_WORLD + threadIdx.x, s_r[threadIdx.x]);
+    }
+}
+
+// one warp per run: reserve space in its destination segment, copy the observations, write the descriptor
+__global__ void __launch_bounds__(256) k_runs_pack(const u64* __restrict__ run_key, const u32* __restrict__ run_start,
+                                                   const u32* __restrict__ run_cnt, const u32* __restrict__ run_first, long long R,
+                                                   int block_bits, int bv, int world, const int2* __restrict__ grouped,
+                                                   const RouteBases B, u32* cursors, int2* __restrict__ out_obs,
+                                                   besst_run_desc* __restrict__ out_desc) {
+    const int lane = threadIdx.x & 31;
+    const long long warp_global = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
+    for (long long r = warp_global; r < R; r += n_warps) {
+        const u64 word = __ldg(run_key + r);
+        const u64 key = word >> block_bits;
+        const u32 u = (u32)(key >> bv), v = (u32)(key & ((1ull << bv) - 1ull));
+        const u32 d = besst_edge_dest(u, v, world);
+        const u32 cnt = __ldg(run_cnt + r), src = __ldg(run_start + r);
+        u32 a = 0, slot = 0;
+        if (lane == 0) { a = atomicAdd(cursors + d, cnt); slot = atomicAdd(cursors + RX_MAX_WORLD + d, 1u); }
+        a = __shfl_sync(0xffffffffu, a, 0);
+        int2* dst = out_obs + B.link_base[d] + a;
+        for (u32 k = lane; k < cnt; k += 32) dst[k] = __ldg(grouped + src + k);
+        if (lane == 0) {
+            besst_run_desc ds;
+            ds.u = u; ds.v = v; ds.count = cnt; ds.first = __ldg(run_first + r); ds.offset = a;
+            ds.block = (u32)(word & ((1ull << block_bits) - 1ull));
+            out_desc[B.run_base[d] + slot] = ds;
+        }
+    }
+}
+
+struct ImportBases { u32 run_end[RX_MAX_WORLD]; u32 link_base[RX_MAX_WORLD]; u32 first_base[RX_MAX_WORLD]; };
+
+// received descriptors (source-major) -> the sort key (u, v, source, block) and absolute positions
+__global__ void __launch_bounds__(256) k_runs_import(const besst_run_desc* __restrict__ desc, long long R, int world, int bv,
+                                                     int block_bits, int low_bits, const ImportBases B, u64* run_key, u32* run_val,
+                                                     u32* run_start, u32* run_cnt, u32* run_first) {
+    const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= R) return;
+    int src = 0;
+    while (src + 1 < world && (u32)r >= B.run_end[src]) ++src;
+    const besst_run_desc ds = desc[r];
+    run_key[r] = (((((u64)ds.u << bv) | ds.v)) << low_bits) | ((u64)src << block_bits) | (u64)ds.block;
+    run_val[r] = (u32)r;
+    run_start[r] = B.link_base[src] + ds.offset;
+    run_cnt[r] = ds.count;
+    run_first[r] = B.first_base[src] + ds.first;
+}
+
+int besst_launch_runs_route(besst_ctx* ctx, int world, int64_t* link_counts, int64_t* run_counts) {
+    for (int d = 0; d < world; ++d) link_counts[d] = run_counts[d] = 0;
+    const int64_t R = ctx->n_runs;
+    if (R == 0) return BESST_OK;
+    const int bv = bits_for((uint64_t)(2 * ctx->n_scaffolds > 0 ? 2 * ctx->n_scaffolds - 1 : 1));
+    u32* state = ctx->run_state.as<u32>() + 16;   // [16..47]: route counts, [48..79]: pack cursors
+    BESST_CUDA_TRY(ctx, cudaMemsetAsync(state, 0, 4 * 4 * RX_MAX_WORLD, ctx->stream));
+    { KTimer kt(ctx, BESST_K_PARTITION);
+      k_runs_route_count<<<(unsigned)((R + 255) / 256), 256, 0, ctx->stream>>>(ctx->run_key[0].as<u64>(), ctx->run_cnt.as<u32>(), R,
+                                                                               ctx->run_block_bits, bv, world, state); }
+    BESST_CUDA_TRY(ctx, cudaGetLastError());
+    u32 h[2 * RX_MAX_WORLD];
+    BESST_CUDA_TRY(ctx, cudaMemcpyAsync(h, state, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+    BESST_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    for (int d = 0; d < world; ++d) { link_counts[d] = h[d]; run_counts[d] = h[RX_MAX_WORLD + d]; }
+    return BESST_OK;
+}
+
+int besst_launch_runs_pack(besst_ctx* ctx, int world, int32_t* out_obs, besst_run_desc* out_desc) {
+    const int64_t R = ctx->n_runs;
+    if (R == 0) return BESST_OK;
+    const int bv = bits_for((uint64_t)(2 * ctx->n_scaffolds > 0 ? 2 * ctx->n_scaffolds - 1 : 1));
+    u32* state = ctx->run_state.as<u32>() + 16;
+    u32 h[2 * RX_MAX_WORLD];
+    BESST_CUDA_TRY(ctx, cudaMemcpyAsync(h, state, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+    BESST_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    RouteBases B;
+    u32 lb = 0, rb = 0;
+    for (int d = 0; d < RX_MAX_WORLD; ++d) {
+        B.link_base[d] = lb; B.run_base[d] = rb;
+        if (d < world) { lb += h[d]; rb += h[RX_MAX_WORLD + d]; }
+    }
+    u32* cursors = state + 2 * RX_MAX_WORLD;
+    long long grid = (R * 32 + 255) / 256;
+    if (grid > (long long)ctx->sm_count * 16) grid = (long long)ctx->sm_count * 16;
+    { KTimer kt(ctx, BESST_K_PARTITION);
+      k_runs_pack<<<(unsigned)grid, 256, 0, ctx->stream>>>(ctx->run_key[0].as<u64>(), ctx->run_start.as<u32>(), ctx->run_cnt.as<u32>(),
+                                                           ctx->run_first.as<u32>(), R, ctx->run_block_bits, bv, world, ctx->grouped.as<int2>(), B,
+                                                           cursors, reinterpret_cast<int2*>(out_obs), out_desc); }
+    BESST_CUDA_TRY(ctx, cudaGetLastError());
+    return BESST_OK;
+}
+
+int besst_launch_runs_import(besst_ctx* ctx, const besst_run_desc* desc, int64_t n_runs, int world, int block_bits,
+                             const int64_t* src_run_counts, const int64_t* src_link_counts, const int64_t* src_first_base,
+                             int* low_bits) {
+    const int bv = bits_for((uint64_t)(2 * ctx->n_scaffolds > 0 ? 2 * ctx->n_scaffolds - 1 : 1));
+    const int src_bits = bits_for((uint64_t)(world > 1 ? world - 1 : 1));
+    *low_bits = src_bits + block_bits;
+    if (2 * bv + *low_bits > 64) { ctx->err = "runs_to_graph: sort key wider than 64 bits"; return BESST_E_INVALID; }
+    const size_t cap = (size_t)(n_runs > 0 ? n_runs : 1);
+    for (int k = 0; k < 2; ++k) {
+        BESST_CUDA_TRY(ctx, ctx->run_key[k].ensure(8 * cap));
+        BESST_CUDA_TRY(ctx, ctx->run_val[k].ensure(4 * cap));
+    }
+    BESST_CUDA_TRY(ctx, ctx->run_start.ensure(4 * cap)); BESST_CUDA_TRY(ctx, ctx->run_cnt.ensure(4 * cap));
+    BESST_CUDA_TRY(ctx, ctx->run_first.ensure(4 * cap));
+    if (n_runs == 0) return BESST_OK;
+    ImportBases B;
+    int64_t re = 0, lb = 0;
+    for (int s = 0; s < RX_MAX_WORLD; ++s) {
+        B.link_base[s] = (u32)lb; B.first_base[s] = s < world ? (u32)src_first_base[s] : 0u;
+        if (s < world) { re += src_run_counts[s]; lb += src_link_counts[s]; }
+        B.run_end[s] = (u32)re;
+    }
+    { KTimer kt(ctx, BESST_K_PARTITION);
+      k_runs_import<<<(unsigned)((n_runs + 255) / 256), 256, 0, ctx->stream>>>(desc, n_runs, world, bv, block_bits, *low_bits, B,
+                                                                               ctx->run_key[0].as<u64>(), ctx->run_val[0].as<u32>(),
+                                                                               ctx->run_start.as<u32>(), ctx->run_cnt.as<u32>(), ctx->run_first.as<u32>()); }
+    BESST_CUDA_TRY(ctx, cudaGetLastError());
+    return BESST_OK;
+}
+
+// runs != nullptr: the run descriptors (ctx->run_key[0] / run_val[0] / run_start / run_cnt / run_first) and the
+// grouped observations were prepared by the caller (multi-GPU import) instead of k_group_blocks
+static int launch_graph_impl(besst_ctx* ctx, const besst_lib_params& p, const besst_link_tuple* d_tuples, int64_t n,
+                             const uint64_t* d_fishy, int64_t n_fishy, const BesstRunInput* runs) {
     ctx->have_graph = false;
     ctx->n_links = n;
     ctx->n_edges = 0;
@@ -1357,37 +1541,28 @@ int besst_launch_graph(besst_ctx* ctx, const besst_lib_params& p, const besst_li
     const char* bucket_env = getenv("BESST_BUCKET");
     const bool force_radix = bucket_env && bucket_env[0] == 'r';
     bool done = false;
+    bool have_runs = false;
+    const int2* grouped_ptr = nullptr;
+    int64_t R = 0;
+    int low_bits = 0, run_key_bits = 0;
     const int64_t n_gblocks = (n + GB_TILE - 1) / GB_TILE;
     const int block_bits = bits_for((uint64_t)(n_gblocks > 1 ? n_gblocks - 1 : 1));
-    if (!force_radix && n > 0 && 2 * bv + block_bits <= 64) {
-        const int64_t run_cap64 = std::max<int64_t>(n / 8, 1 << 16);
-        const u32 run_cap = (u32)std::min<int64_t>(run_cap64, 0x7fffffff);
-        BESST_CUDA_TRY(ctx, ctx->grouped.ensure(8 * nz));
-        for (int k = 0; k < 2; ++k) {
-            BESST_CUDA_TRY(ctx, ctx->run_key[k].ensure(8 * (size_t)run_cap));
-            BESST_CUDA_TRY(ctx, ctx->run_val[k].ensure(4 * (size_t)run_cap));
-        }
-        BESST_CUDA_TRY(ctx, ctx->run_start.ensure(4 * (size_t)run_cap)); BESST_CUDA_TRY(ctx, ctx->run_cnt.ensure(4 * (size_t)run_cap));
-        BESST_CUDA_TRY(ctx, ctx->run_first.ensure(4 * (size_t)run_cap)); BESST_CUDA_TRY(ctx, ctx->run_off.ensure(4 * (size_t)run_cap));
-        BESST_CUDA_TRY(ctx, ctx->run_src.ensure(4 * (size_t)run_cap)); BESST_CUDA_TRY(ctx, ctx->run_len.ensure(4 * (size_t)run_cap));
-        BESST_CUDA_TRY(ctx, ctx->run_state.ensure(64));
-        u32* gstate = ctx->run_state.as<u32>();
-        BESST_CUDA_TRY(ctx, cudaMemsetAsync(gstate, 0, 64, ctx->stream));
+    if (runs) {
+        have_runs = true;
+        grouped_ptr = runs->grouped; R = runs->n_runs; low_bits = runs->low_bits; run_key_bits = 2 * bv + runs->low_bits;
+        BESST_CUDA_TRY(ctx, ctx->run_off.ensure(4 * (size_t)(R + 1))); BESST_CUDA_TRY(ctx, ctx->run_src.ensure(4 * (size_t)(R + 1)));
+        BESST_CUDA_TRY(ctx, ctx->run_len.ensure(4 * (size_t)(R + 1)));
+    } else if (!force_radix && n > 0 && 2 * bv + block_bits <= 64) {
+        int overflow = 0;
+        rc = besst_group_tuples(ctx, d_tuples, n, bv, block_bits, &R, &overflow);
+        if (rc) return rc;
+        if (!overflow) { have_runs = true; grouped_ptr = ctx->grouped.as<int2>(); low_bits = block_bits; run_key_bits = 2 * bv + block_bits; }
+    }
+    if (have_runs && n > 0) {
         {
-            KTimer kt(ctx, BESST_K_GROUP);
-            k_group_blocks<<<(unsigned)n_gblocks, GB_THREADS, sizeof(GroupSmem), ctx->stream>>>(
-                d_tuples, n, bv, block_bits, ctx->grouped.as<int2>(), ctx->run_key[0].as<u64>(), ctx->run_val[0].as<u32>(),
-                ctx->run_start.as<u32>(), ctx->run_cnt.as<u32>(), ctx->run_first.as<u32>(), gstate, run_cap);
-        }
-        BESST_CUDA_TRY(ctx, cudaGetLastError());
-        u32 hs[2] = {0, 0};
-        BESST_CUDA_TRY(ctx, cudaMemcpyAsync(hs, gstate, 8, cudaMemcpyDeviceToHost, ctx->stream));
-        BESST_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-        const int64_t R = hs[0];
-        if (hs[1] == 0 && R <= (int64_t)run_cap) {
             int in_b = 0;
             rc = besst_radix_sort_pairs(ctx, ctx->run_key[0].as<uint64_t>(), ctx->run_key[1].as<uint64_t>(), ctx->run_val[0].as<uint32_t>(),
-                                        ctx->run_val[1].as<uint32_t>(), R, 2 * bv + block_bits, &in_b);
+                                        ctx->run_val[1].as<uint32_t>(), R, run_key_bits, &in_b);
             if (rc) return rc;
             const u64* rkeys = ctx->run_key[in_b].as<u64>();
             const u32* rvals = ctx->run_val[in_b].as<u32>();
@@ -1395,7 +1570,7 @@ int besst_launch_graph(besst_ctx* ctx, const besst_lib_params& p, const besst_li
             const int rblocks = (int)((R + RS_TILE - 1) / RS_TILE);
             BESST_CUDA_TRY(ctx, ctx->heads.ensure(8 * (size_t)(rblocks + 2)));
             u64* bsums = ctx->heads.as<u64>();
-            { KTimer kt(ctx, BESST_K_RUNS); k_run_count<<<rblocks, RS_T, 0, ctx->stream>>>(rkeys, rvals, ctx->run_cnt.as<u32>(), R, block_bits, bsums); }
+            { KTimer kt(ctx, BESST_K_RUNS); k_run_count<<<rblocks, RS_T, 0, ctx->stream>>>(rkeys, rvals, ctx->run_cnt.as<u32>(), R, low_bits, bsums); }
             { KTimer kt(ctx, BESST_K_RUNS); k_scan_blocks64<<<1, 1024, 0, ctx->stream>>>(bsums, rblocks); }
             u64 tot = 0;
             BESST_CUDA_TRY(ctx, cudaMemcpyAsync(&tot, bsums + rblocks, 8, cudaMemcpyDeviceToHost, ctx->stream));
@@ -1406,22 +1581,22 @@ int besst_launch_graph(besst_ctx* ctx, const besst_lib_params& p, const besst_li
             BESST_CUDA_TRY(ctx, ctx->edge_run_ptr.ensure(4 * (size_t)(E + 2)));
             { KTimer kt(ctx, BESST_K_RUNS);
               k_run_write<<<rblocks, RS_T, 0, ctx->stream>>>(rkeys, rvals, ctx->run_cnt.as<u32>(), ctx->run_start.as<u32>(), ctx->run_first.as<u32>(), R,
-                                                            block_bits, bv, bsums, ctx->run_off.as<u32>(), ctx->run_src.as<u32>(), ctx->run_len.as<u32>(),
+                                                            low_bits, bv, bsums, ctx->run_off.as<u32>(), ctx->run_src.as<u32>(), ctx->run_len.as<u32>(),
                                                             EA.row_ptr, ctx->edge_run_ptr.as<u32>(), EA.u, EA.v, EA.first, n); }
             besst_mark(ctx);
             {
                 int grid = (int)((E * 32 + 255) / 256);
                 if (grid > edge_grid_max) grid = edge_grid_max;
                 KTimer kt(ctx, BESST_K_EDGE_REDUCE);
-                k_edge_gather<<<grid, 256, 0, ctx->stream>>>(EA, E, ctx->grouped.as<int2>(), ctx->edge_run_ptr.as<u32>(), ctx->run_off.as<u32>(),
+                k_edge_gather<<<grid, 256, 0, ctx->stream>>>(EA, E, grouped_ptr, ctx->edge_run_ptr.as<u32>(), ctx->run_off.as<u32>(),
                                                              ctx->run_src.as<u32>(), ctx->run_len.as<u32>(), bv, fishy_sorted, n_fishy,
                                                              (u32)(2 * ctx->n_large), p.no_score ? 0 : 1);
                 BESST_CUDA_TRY(ctx, cudaGetLastError());
             }
             besst_mark(ctx);
             done = true;
-        }   // else: fall through to the radix bucket
-    }
+        }
+    }   // no runs: fall through to the radix bucket
 
     int n_blocks = (int)((n + HB_TILE - 1) / HB_TILE);
     if (!done) {
@@ -1576,4 +1751,14 @@ int besst_launch_graph(besst_ctx* ctx, const besst_lib_params& p, const besst_li
     besst_mark(ctx);
     ctx->have_graph = true;
     return BESST_OK;
+}
+
+int besst_launch_graph(besst_ctx* ctx, const besst_lib_params& p, const besst_link_tuple* d_tuples, int64_t n,
+                       const uint64_t* d_fishy, int64_t n_fishy) {
+    return launch_graph_impl(ctx, p, d_tuples, n, d_fishy, n_fishy, nullptr);
+}
+
+int besst_launch_graph_from_runs(besst_ctx* ctx, const besst_lib_params& p, int64_t n_links, const BesstRunInput& runs,
+                                 const uint64_t* d_fishy, int64_t n_fishy) {
+    return launch_graph_impl(ctx, p, nullptr, n_links, d_fishy, n_fishy, &runs);
 }

@@ -123,6 +123,9 @@ struct besst_ctx {
     // run-merge bucket: block-grouped observations and the run descriptors
     DBuf grouped, run_key[2], run_val[2], run_start, run_cnt, run_first, run_off, run_src, run_len, edge_run_ptr, run_state;
     int64_t n_edges = 0, n_links = 0, n_fishy_pairs = 0, n_ll_links = 0;
+    int64_t n_runs = 0;        // run descriptors of the last besst_links_group
+    int run_block_bits = 0;
+    bool have_runs = false;
     bool have_graph = false;
     besst_lib_params last_params;
 
@@ -140,6 +143,15 @@ struct besst_ctx {
     int sweep_kernel_id = BESST_K_RADIX_SWEEP;  // profiling id of the next radix sort's digit passes
 };
 
+// destination rank of an edge in the multi-GPU exchange: hash(u, v) mod world (tuple-level and run-level paths)
+#ifdef __CUDACC__
+__device__ __forceinline__ unsigned int besst_edge_dest(unsigned int u, unsigned int v, int world) {
+    unsigned long long x = ((unsigned long long)u << 32) | v;
+    x ^= x >> 33; x *= 0xff51afd7ed558ccdull; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ull; x ^= x >> 33;
+    return (unsigned int)(x % (unsigned long long)world);
+}
+#endif
+
 // ---- launchers (one per translation unit) ----------------------------------
 // links: records -> accepted link tuples (BAM order), coverage, fishy keys, counters
 int besst_launch_extract(besst_ctx* ctx, const besst_lib_params& p, const DeviceRecords& rec);
@@ -151,6 +163,22 @@ int besst_extract_finish(besst_ctx* ctx, const besst_lib_params& p, int64_t n, b
 // sort + CSR: tuples -> sorted (key, idx) -> edges
 int besst_launch_graph(besst_ctx* ctx, const besst_lib_params& p, const besst_link_tuple* d_tuples, int64_t n_tuples,
                        const uint64_t* d_fishy, int64_t n_fishy);
+
+// the graph build from run descriptors prepared by the caller (multi-GPU import of exchanged runs)
+struct BesstRunInput {
+    const int2* grouped;   // (obs_u, obs_v) per link; run r covers [run_start[r], run_start[r] + run_cnt[r])
+    int64_t n_runs;        // descriptors in ctx->run_key[0] / run_val[0] / run_start / run_cnt / run_first
+    int low_bits;          // bits of the sort key below the edge key (source rank, block)
+};
+int besst_launch_graph_from_runs(besst_ctx* ctx, const besst_lib_params& p, int64_t n_links, const BesstRunInput& runs,
+                                 const uint64_t* d_fishy, int64_t n_fishy);
+int besst_launch_runs_route(besst_ctx* ctx, int world, int64_t* link_counts, int64_t* run_counts);
+int besst_launch_runs_pack(besst_ctx* ctx, int world, int32_t* out_obs, besst_run_desc* out_desc);
+int besst_launch_runs_import(besst_ctx* ctx, const besst_run_desc* desc, int64_t n_runs, int world, int block_bits,
+                             const int64_t* src_run_counts, const int64_t* src_link_counts, const int64_t* src_first_base,
+                             int* low_bits);
+int besst_group_tuples(besst_ctx* ctx, const besst_link_tuple* d_tuples, int64_t n, int bv, int block_bits, int64_t* n_runs,
+                       int* overflow);
 
 // radix sort of 64-bit keys with 32-bit payload (onesweep); returns which buffer holds the result
 int besst_radix_sort_pairs(besst_ctx* ctx, uint64_t* keys_a, uint64_t* keys_b, uint32_t* val_a, uint32_t* val_b,

@@ -715,11 +715,7 @@ constexpr int PT_ITEMS = 8;
 constexpr int PT_TILE = PT_THREADS * PT_ITEMS;
 constexpr int PT_MAX_WORLD = 16;
 
-__device__ __forceinline__ u32 edge_dest(u32 u, u32 v, int world) {
-    u64 x = ((u64)u << 32) | v;
-    x ^= x >> 33; x *= 0xff51afd7ed558ccdull; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ull; x ^= x >> 33;
-    return (u32)(x % (u64)world);
-}
+__device__ __forceinline__ u32 edge_dest(u32 u, u32 v, int world) { return besst_edge_dest(u, v, world); }
 
 template <bool TUPLES>
 __device__ __forceinline__ u32 item_dest(const void* in, long long i, int world) {
@@ -880,7 +876,9 @@ int besst_launch_partition(besst_ctx* ctx, int world, besst_link_tuple* out_tupl
                            uint64_t* out_fishy, int64_t* tuple_counts, int64_t* fishy_counts) {
     if (world < 1 || world > PT_MAX_WORLD) { ctx->err = "partition: world size must be 1..16"; return BESST_E_INVALID; }
     if (ctx->n_tuples >= (1ll << 30) || ctx->n_fishy_keys >= (1ll << 30)) { ctx->err = "partition: more than 2^30 items"; return BESST_E_INVALID; }
-    int rc = partition_impl<true>(ctx, ctx->tuples.p, ctx->n_tuples, world, out_tuples, out_ordinals, tuple_counts);
+    int rc = BESST_OK;
+    if (out_tuples) rc = partition_impl<true>(ctx, ctx->tuples.p, ctx->n_tuples, world, out_tuples, out_ordinals, tuple_counts);
+    else for (int d = 0; d < world; ++d) tuple_counts[d] = 0;   // run-level exchange: only the fishy keys travel as keys
     if (rc) return rc;
     return partition_impl<false>(ctx, ctx->fishy_keys.p, ctx->n_fishy_keys, world, out_fishy, nullptr, fishy_counts);
 }

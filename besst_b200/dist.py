@@ -98,6 +98,39 @@ class CudaBackend(object):
         tc, fc = self.engine.links_partition(world, send_t.data_ptr(), send_f.data_ptr(), send_o.data_ptr())
         return send_t[:4 * n].view(-1, 4), send_o[:n], send_f[:nf], tc, fc
 
+    # run-level exchange
+    def group(self):
+        return self.engine.links_group()
+
+    def route(self, world):
+        return self.engine.runs_route(world)
+
+    def partition_fishy(self, world):
+        torch = self.torch
+        _, (_, nf) = self.engine.links_device()
+        send_f = self._buf("send_f", nf, torch.int64)
+        _, fc = self.engine.links_partition(world, None, send_f.data_ptr(), None)
+        return send_f[:nf], fc
+
+    def pack(self, world, n_links, n_runs):
+        torch = self.torch
+        send_obs = self._buf("send_obs", 2 * n_links, torch.int32)
+        send_desc = self._buf("send_desc", 6 * n_runs, torch.int32)
+        self.engine.runs_pack(world, send_obs.data_ptr(), send_desc.data_ptr())
+        return send_obs[:2 * n_links].view(-1, 2), send_desc[:6 * n_runs].view(-1, 6)
+
+    def recv_run_buffers(self, n_links, n_runs, n_fishy):
+        torch = self.torch
+        return (self._buf("recv_obs", 2 * n_links, torch.int32)[:2 * n_links].view(-1, 2),
+                self._buf("recv_desc", 6 * n_runs, torch.int32)[:6 * n_runs].view(-1, 6),
+                self._buf("recv_f", n_fishy, torch.int64)[:n_fishy])
+
+    def runs_to_graph(self, params, recv_obs, recv_desc, world, block_bits, src_runs, src_links, src_first, recv_f):
+        return self.engine.runs_to_graph(params, recv_obs.data_ptr() if recv_obs.numel() else None, recv_obs.shape[0],
+                                         recv_desc.data_ptr() if recv_desc.numel() else None, recv_desc.shape[0], world,
+                                         block_bits, src_runs, src_links, src_first,
+                                         recv_f.data_ptr() if recv_f.numel() else None, recv_f.shape[0])
+
     def recv_buffers(self, n_tuples, n_fishy):
         torch = self.torch
         return (self._buf("recv_t", 4 * n_tuples, torch.int32)[:4 * n_tuples].view(-1, 4),
@@ -140,6 +173,9 @@ class DistributedGraphBuild(object):
         self.b = backend
         self.rank, self.world, self.group = rank, world, group
         self.last = None
+        # BESST_DIST_EXCHANGE=tuples forces the tuple-level exchange (A/B, tests); default: runs
+        import os
+        self.exchange_runs = os.environ.get("BESST_DIST_EXCHANGE", "runs") != "tuples"
 
     # -- step 1: the last CreateEdge call of all preceding ranks --------------------------------
     def halo(self, params, rec):
@@ -161,6 +197,10 @@ class DistributedGraphBuild(object):
         halo = self.halo(params, rec) if world > 1 else (params.halo_prev_obs1, params.halo_prev_obs2)
         p = _copy_params(params, halo)
         n_local = self.b.extract(p, rec)
+        if self.exchange_runs and hasattr(self.b, "group"):
+            sizes = self._step_runs(p, n_local)
+            if sizes is not None:
+                return sizes
         send_t, send_o, send_f, tc, fc = self.b.partition(world)
         # bucket sizes: one small all_to_all, then the payload all_to_all
         counts_out = self.b.counts_tensor(np.stack([tc, fc], axis=1).reshape(-1).tolist())
@@ -189,6 +229,46 @@ class DistributedGraphBuild(object):
                          halo=halo)
         return sizes
 
+    def _step_runs(self, p, n_local):
+        """Run-level exchange: whole runs (block-grouped links of one edge) are routed by edge hash; 8 bytes
+        per link + 24 per run cross NVLink and the receiver starts at the run merge.  None: some rank's
+        stream has no local order -- every rank takes the tuple-level path."""
+        dist, world = self.dist, self.world
+        n_runs = self.b.group()
+        ok = self.b.counts_tensor([1 if n_runs is not None else 0])
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=self.group)
+        if int(ok.item()) == 0:
+            return None
+        lc, rc = self.b.route(world)
+        send_f, fc = self.b.partition_fishy(world)
+        # one small all_to_all: what every destination gets from me (links, runs, fishy keys) + my link count
+        meta_out = self.b.counts_tensor(np.stack([lc, rc, fc, np.full(world, n_local)], axis=1).reshape(-1).tolist())
+        meta_in = self.b.counts_tensor([0] * (4 * world))
+        dist.all_to_all_single(meta_in, meta_out, group=self.group)
+        mi = np.asarray(meta_in.tolist(), dtype=np.int64).reshape(world, 4)
+        rl, rr, rf, n_by_rank = mi[:, 0], mi[:, 1], mi[:, 2], mi[:, 3]
+        if int(n_by_rank.sum()) >= 2 ** 32 or int(rl.sum()) >= 2 ** 30:
+            raise ValueError("run-level exchange: more than 2^32 links in the library or 2^30 on one rank")
+        send_obs, send_desc = self.b.pack(world, int(lc.sum()), int(rc.sum()))
+        recv_obs, recv_desc, recv_f = self.b.recv_run_buffers(int(rl.sum()), int(rr.sum()), int(rf.sum()))
+        dist.all_to_all_single(recv_obs, send_obs, output_split_sizes=rl.tolist(), input_split_sizes=lc.tolist(), group=self.group)
+        dist.all_to_all_single(recv_desc, send_desc, output_split_sizes=rr.tolist(), input_split_sizes=rc.tolist(), group=self.group)
+        dist.all_to_all_single(recv_f, send_f, output_split_sizes=rf.tolist(), input_split_sizes=fc.tolist(), group=self.group)
+        max_blocks = int(((n_by_rank + abi.RUN_BLOCK - 1) // abi.RUN_BLOCK).max())
+        block_bits = max(1, int(max(max_blocks - 1, 1)).bit_length())
+        first_base = np.concatenate([[0], np.cumsum(n_by_rank)[:-1]])
+        sizes = self.b.runs_to_graph(p, recv_obs, recv_desc, world, block_bits, rr, rl, first_base, recv_f)
+        aligned, counters = self.b.partial_tensors()
+        last = counters[abi.CNT_LAST_OBS1:abi.CNT_LAST_OBS2 + 1].clone()
+        counters[abi.CNT_LAST_OBS1:] = 0
+        dist.all_reduce(aligned, op=dist.ReduceOp.SUM, group=self.group)
+        dist.all_reduce(counters, op=dist.ReduceOp.SUM, group=self.group)
+        lasts = [last.clone() for _ in range(world)]
+        dist.all_gather(lasts, last, group=self.group)
+        self.last = dict(sizes=sizes, global_first=True, n_tuples_by_rank=n_by_rank.tolist(), aligned=aligned, counters=counters,
+                         last_call=[tuple(int(x) for x in t.tolist()) for t in lasts], halo=(p.halo_prev_obs1, p.halo_prev_obs2))
+        return sizes
+
     # -- results ------------------------------------------------------------------------------------
     def fetch_local(self, view=False):
         """This rank's edges (GraphResult) with first_idx rewritten to the GLOBAL ordinal of the
@@ -197,7 +277,7 @@ class DistributedGraphBuild(object):
         (valid until the next view)."""
         L = self.last
         res = self.b.fetch(L["sizes"], view) if view else self.b.fetch(L["sizes"])
-        if res.n_edges:
+        if res.n_edges and not L.get("global_first"):
             starts = np.concatenate([[0], np.cumsum(L["recv_splits"])])
             src = np.searchsorted(starts, res.first_idx, side="right") - 1
             prefix = np.concatenate([[0], np.cumsum(L["n_tuples_by_rank"])])

@@ -127,6 +127,34 @@ class CudaEngine(object):
                                                   tc.ctypes.data, fc.ctypes.data), "besst_links_partition")
         return tc, fc
 
+    # -- run-level exchange (preferred multi-GPU path) ----------------------------------------------
+    def links_group(self):
+        """Group the extracted links into runs.  -> number of runs, or None when the stream has no
+        local order (use the tuple-level exchange)."""
+        n = C.c_int64()
+        rc = self._check(self._L.besst_links_group(self._ctx, C.byref(n)), "besst_links_group")
+        return None if rc == 1 else n.value
+
+    def runs_route(self, world):
+        lc = np.zeros(world, dtype=np.int64)
+        rc = np.zeros(world, dtype=np.int64)
+        self._check(self._L.besst_runs_route(self._ctx, int(world), lc.ctypes.data, rc.ctypes.data), "besst_runs_route")
+        return lc, rc
+
+    def runs_pack(self, world, out_obs_ptr, out_desc_ptr):
+        self._check(self._L.besst_runs_pack(self._ctx, int(world), out_obs_ptr, out_desc_ptr), "besst_runs_pack")
+
+    def runs_to_graph(self, params, obs_ptr, n_links, desc_ptr, n_runs, world, block_bits, src_run_counts, src_link_counts,
+                      src_first_base, fishy_ptr, n_fishy):
+        sizes = abi.GraphSizes()
+        a = np.ascontiguousarray(src_run_counts, dtype=np.int64)
+        b = np.ascontiguousarray(src_link_counts, dtype=np.int64)
+        c = np.ascontiguousarray(src_first_base, dtype=np.int64)
+        self._check(self._L.besst_runs_to_graph(self._ctx, C.byref(params), obs_ptr, int(n_links), desc_ptr, int(n_runs), int(world),
+                                                int(block_bits), a.ctypes.data, b.ctypes.data, c.ctypes.data, fishy_ptr, int(n_fishy),
+                                                C.byref(sizes)), "besst_runs_to_graph")
+        return sizes
+
     def links_counters(self):
         counters = np.zeros(abi.N_COUNTERS, dtype=np.int64)
         self._check(self._L.besst_links_partials(self._ctx, None, counters.ctypes.data), "besst_links_partials")

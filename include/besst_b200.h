@@ -232,7 +232,8 @@ int besst_links_fetch(besst_ctx* ctx, besst_link_tuple* tuples_host, uint64_t* f
  * DEVICE buffers of n_tuples / n_fishy_keys elements; out_ordinals_device (optional, n_tuples
  * uint32) receives each bucketed tuple's ordinal in this rank's BAM-ordered stream, from which the
  * receiver rebuilds the global first-appearance order of its edges; *_counts[world] (host) receive
- * the bucket sizes.  world <= 16. */
+ * the bucket sizes.  world <= 16.  out_tuples_device == NULL: only the fishy keys are partitioned (the
+ * links travel as runs, see besst_links_group). */
 int besst_links_partition(besst_ctx* ctx, int32_t world, besst_link_tuple* out_tuples_device,
                           uint32_t* out_ordinals_device, uint64_t* out_fishy_device, int64_t* tuple_counts,
                           int64_t* fishy_counts);
@@ -240,6 +241,34 @@ int besst_links_to_graph(besst_ctx* ctx, const besst_lib_params* params,
                          const besst_link_tuple* tuples_device, int64_t n_tuples,
                          const uint64_t* fishy_keys_device, int64_t n_fishy_keys,
                          besst_graph_sizes* sizes);
+
+/* ---- run-level multi-GPU exchange (preferred over the tuple-level one) -------------------------------
+ * After besst_links_extract, besst_links_group groups the rank's accepted links by edge inside blocks
+ * of 2048 consecutive links (BAM order kept) and leaves one RUN per (block, edge).  Whole runs are
+ * routed by hash(u,v) mod world: 8 bytes per link (obs_u, obs_v) plus one 24-byte descriptor per run
+ * cross NVLink instead of 20 bytes per link, and the receiver starts at the run merge -- it never
+ * regroups links.  returns 1 (not an error) when the stream has no local order: use the tuple path. */
+typedef struct besst_run_desc {
+    uint32_t u, v;    /* edge, u < v */
+    uint32_t count;   /* links of the run */
+    uint32_t first;   /* ordinal of its first link in the SOURCE rank's accepted-link stream (BAM order) */
+    uint32_t offset;  /* its first observation inside the (source -> destination) observation segment */
+    uint32_t block;   /* block of the source's stream it comes from: BAM order among the runs of one edge */
+} besst_run_desc;
+int besst_links_group(besst_ctx* ctx, int64_t* n_runs);
+/* per destination: links and runs this rank will send (host arrays of `world` entries) */
+int besst_runs_route(besst_ctx* ctx, int32_t world, int64_t* link_counts, int64_t* run_counts);
+/* fill caller-provided DEVICE buffers, destination-major: out_obs = (obs_u, obs_v) int32 pairs of
+ * sum(link_counts) links, out_desc = sum(run_counts) descriptors */
+int besst_runs_pack(besst_ctx* ctx, int32_t world, int32_t* out_obs_device, besst_run_desc* out_desc_device);
+/* build this rank's share of the graph from the runs received from all sources (source-major device
+ * buffers).  src_*_counts[world]: what each source sent here; src_first_base[world]: number of accepted
+ * links on all ranks before the source (first_idx becomes a GLOBAL ordinal); block_bits: bits of the
+ * largest block index on any rank. */
+int besst_runs_to_graph(besst_ctx* ctx, const besst_lib_params* params, const int32_t* obs_device, int64_t n_links,
+                        const besst_run_desc* desc_device, int64_t n_runs, int32_t world, int32_t block_bits,
+                        const int64_t* src_run_counts, const int64_t* src_link_counts, const int64_t* src_first_base,
+                        const uint64_t* fishy_keys_device, int64_t n_fishy_keys, besst_graph_sizes* sizes);
 
 /* library metrics: capped BAM-order sampling + histogram on the GPU, O(bins)
  * statistics on the host side of the shim.  lengths = BAM header lengths.

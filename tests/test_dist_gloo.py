@@ -22,7 +22,8 @@ def _free_port():
     return port
 
 
-def _worker(rank, world, port, config, cuts, out_dir):
+def _worker(rank, world, port, config, cuts, out_dir, exchange):
+    os.environ["BESST_DIST_EXCHANGE"] = exchange
     for p in (ROOT, os.path.join(ROOT, "oracle"), HERE):
         if p not in sys.path:
             sys.path.insert(0, p)
@@ -63,9 +64,10 @@ def _worker(rank, world, port, config, cuts, out_dir):
     (3, "small_pe", [0.2, 0.21]),       # a tiny middle slice
     (3, "tiny", [0.0, 0.6]),            # an empty first slice: the halo must pass through
 ])
-def test_distributed_build_equals_single_pass(tmp_path, world, config, cuts):
+@pytest.mark.parametrize("exchange", ["runs", "tuples"])
+def test_distributed_build_equals_single_pass(tmp_path, world, config, cuts, exchange):
     import oracle_lib
     oracle_lib.build()   # before the workers race to do it
     port = _free_port()
-    mp.spawn(_worker, args=(world, port, config, cuts, str(tmp_path)), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, port, config, cuts, str(tmp_path), exchange), nprocs=world, join=True)
     assert os.path.exists(os.path.join(str(tmp_path), "ok"))
