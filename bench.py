@@ -29,7 +29,10 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-os.environ["NCCL_DEBUG"] = os.environ.get("BESST_NCCL_DEBUG", "WARN")   # NCCL's version banner goes to stdout: keep the one JSON line alone
+# NCCL's version banner (NCCL_DEBUG=VERSION/WARN/INFO) goes to stdout: keep the one JSON line alone
+os.environ.pop("NCCL_DEBUG", None)
+if os.environ.get("BESST_NCCL_DEBUG"):
+    os.environ["NCCL_DEBUG"] = os.environ["BESST_NCCL_DEBUG"]
 
 import numpy as np  # noqa: E402
 
@@ -231,7 +234,7 @@ def run_ours(args):
         "k_radix_sweep": (8 + 8) * n_links,       # packed sort word (key | BAM index): 8 B in, 8 B out per pass
         "k_radix_hist": 8 * n_links,
         "k_edge_reduce": (8 + 8) * n_links + 64 * n_edges,    # k_edge_gather: grouped (o1,o2) in, obs_u/obs_v out
-        "k_group_blocks": (16 + 8) * n_links,                 # tuples in, grouped observations out (+ run descriptors)
+        "k_group_blocks": (16 + 8) * n_links + 8 * ((n_rec + 127) // 128),   # scratch tuples + tile offsets in, grouped observations out
         "k_score_keys": (8 + 8) * n_ll / 3.0 + 13 * n_edges,   # 3 launches: LL scan (2, over edges) + key build
         "k_ks_block": (4 + 4) * n_ll + 8 * n_edges,           # obs_u, obs_v of the scored links in, one double per edge out
         "k_ks_sort": (4 + 4) * n_ll,

@@ -47,7 +47,7 @@ extern "C" void besst_destroy(besst_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    DBuf* bufs[] = {&ctx->rows, &ctx->rows_packed, &ctx->scratch_tuples, &ctx->tile_aggs, &ctx->part_state, &ctx->scaf_len, &ctx->rec_flag, &ctx->rec_mapq, &ctx->tuples, &ctx->fishy_keys, &ctx->aligned,
+    DBuf* bufs[] = {&ctx->rows, &ctx->rows_packed, &ctx->scratch_tuples, &ctx->block_tile0, &ctx->tile_aggs, &ctx->part_state, &ctx->scaf_len, &ctx->rec_flag, &ctx->rec_mapq, &ctx->tuples, &ctx->fishy_keys, &ctx->aligned,
                     &ctx->counters, &ctx->tile_state, &ctx->misc, &ctx->key_a, &ctx->key_b, &ctx->idx_a, &ctx->idx_b, &ctx->hist,
                     &ctx->sort_state, &ctx->fishy_sorted, &ctx->fishy_tmp, &ctx->heads, &ctx->block_sums, &ctx->e_u, &ctx->e_v,
                     &ctx->e_nr, &ctx->e_obs, &ctx->e_obs_sq, &ctx->e_first, &ctx->e_row_ptr, &ctx->e_gap, &ctx->e_score,
@@ -224,6 +224,8 @@ extern "C" int besst_links_extract(besst_ctx* ctx, const besst_lib_params* param
 
 extern "C" int besst_links_tuples_device(besst_ctx* ctx, const besst_link_tuple** tuples, int64_t* n_tuples) {
     if (!ctx || !ctx->have_links) { if (ctx) ctx->err = "no extracted links"; return BESST_E_STATE; }
+    cudaSetDevice(ctx->device);
+    { const int rc = besst_ensure_tuples(ctx); if (rc) return rc; }
     *tuples = ctx->tuples.as<besst_link_tuple>();
     *n_tuples = ctx->n_tuples;
     return BESST_OK;
@@ -257,6 +259,7 @@ extern "C" int besst_links_partials_device(besst_ctx* ctx, int64_t** aligned_len
 extern "C" int besst_links_fetch(besst_ctx* ctx, besst_link_tuple* tuples_host, uint64_t* fishy_keys_host) {
     if (!ctx || !ctx->have_links) { if (ctx) ctx->err = "no extracted links"; return BESST_E_STATE; }
     cudaSetDevice(ctx->device);
+    if (tuples_host) { const int rc = besst_ensure_tuples(ctx); if (rc) return rc; }
     if (tuples_host && ctx->n_tuples > 0)
         BESST_CUDA_TRY(ctx, cudaMemcpyAsync(tuples_host, ctx->tuples.p, sizeof(besst_link_tuple) * (size_t)ctx->n_tuples, cudaMemcpyDeviceToHost, ctx->stream));
     if (fishy_keys_host && ctx->n_fishy_keys > 0)
@@ -293,7 +296,7 @@ extern "C" int besst_links_group(besst_ctx* ctx, int64_t* n_runs) {
     if (2 * bv + bb > 64) return 1;
     int64_t R = 0;
     int overflow = 0;
-    int rc = besst_group_tuples(ctx, ctx->tuples.as<besst_link_tuple>(), n, bv, bb, &R, &overflow);
+    int rc = besst_group_tuples(ctx, nullptr, n, bv, bb, &R, &overflow);
     if (rc) return rc;
     if (overflow) return 1;
     ctx->n_runs = R;
@@ -409,9 +412,15 @@ extern "C" int besst_graph_build(besst_ctx* ctx, const besst_lib_params* params,
     int64_t n = 0;
     int rc = besst_links_extract(ctx, params, records, &n);
     if (rc) return rc;
-    rc = besst_links_to_graph(ctx, params, ctx->tuples.as<besst_link_tuple>(), ctx->n_tuples, ctx->fishy_keys.as<uint64_t>(),
-                              ctx->n_fishy_keys, sizes);
+    // tuples_device == NULL: the links of this ctx's last extraction, read from their scratch runs
+    cudaSetDevice(ctx->device);
+    rc = besst_launch_graph(ctx, *params, nullptr, ctx->n_tuples, ctx->fishy_keys.as<uint64_t>(), ctx->n_fishy_keys);
     if (rc) return rc;
+    if (sizes) {
+        sizes->n_edges = ctx->n_edges; sizes->n_links = ctx->n_links; sizes->n_contigs = ctx->n_contigs;
+        sizes->n_fishy = ctx->n_fishy_keys;
+        sizes->n_ll_links = ctx->n_ll_links;
+    }
     ctx->ev_valid = true;
     return BESST_OK;
 }

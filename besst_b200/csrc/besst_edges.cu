@@ -256,7 +256,12 @@ struct GroupSmem {
     unsigned short start[GB_DMAX + 2];
     u32 scan_w[GB_WARPS];
     u32 n_ids, run_base, overflow;
+    // FROM_SCRATCH: the non-empty record tiles overlapping this block
+    u32 tile_id[GB_TILE + 2];      // tile number | drop-first flag << 31
+    u32 tile_start[GB_TILE + 2];   // ordinal of the tile's first kept tuple, relative to the block
+    u32 n_list, scan_tile0;
 };
+constexpr u64 GB_OFF_DROP = 1ull << 63;   // tile_off flag (besst_links.cu): skip the tile's first scratch tuple
 
 __device__ __forceinline__ u32 gb_insert(u64* ht, u64 key, u32* overflow) {
     u32 h = ((u32)(key >> 32) * 0x9E3779B1u) ^ ((u32)key * 0x85EBCA77u);
@@ -275,10 +280,15 @@ __device__ __forceinline__ u32 gb_insert(u64* ht, u64 key, u32* overflow) {
 }
 
 // gstate: [0] = runs so far, [1] = overflow flags (1: a block with too many edges, 2: run capacity)
+// FROM_SCRATCH: `tuples` is K1's scratch (128 slots per record tile, the kept tuples of tile t at
+// t * 128 + drop .. ) and tile_off[t] the ordinal of tile t's first kept tuple: the block finds the tiles
+// that overlap its 2048 ordinals and reads them in place -- no compacted copy of the tuple stream.
+template <bool FROM_SCRATCH>
 __global__ void __launch_bounds__(GB_THREADS, 4)
     k_group_blocks(const besst_link_tuple* __restrict__ tuples, long long n, int bv, int block_bits, int2* __restrict__ grouped,
                    u64* __restrict__ run_key, u32* __restrict__ run_val, u32* __restrict__ run_start, u32* __restrict__ run_cnt,
-                   u32* __restrict__ run_first, u32* gstate, u32 run_cap) {
+                   u32* __restrict__ run_first, u32* gstate, u32 run_cap, const u64* __restrict__ tile_off, long long n_tiles,
+                   const u32* __restrict__ block_tile0) {
     extern __shared__ __align__(16) unsigned char gb_smem[];
     GroupSmem& S = *reinterpret_cast<GroupSmem*>(gb_smem);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -288,11 +298,45 @@ __global__ void __launch_bounds__(GB_THREADS, 4)
 
     for (int i = threadIdx.x; i < GB_HT / 2; i += GB_THREADS) reinterpret_cast<ulonglong2*>(S.ht)[i] = make_ulonglong2(GB_EMPTY, GB_EMPTY);
     for (int i = threadIdx.x; i < GB_WARPS * GB_DMAX / 8; i += GB_THREADS) reinterpret_cast<uint4*>(&S.warp_hist[0][0])[i] = make_uint4(0, 0, 0, 0);
-    if (threadIdx.x == 0) { S.n_ids = 0; S.overflow = 0; }
+    if (threadIdx.x == 0) { S.n_ids = 0; S.overflow = 0; S.n_list = 0; }
+    if (FROM_SCRATCH && threadIdx.x == 0) S.scan_tile0 = __ldg(block_tile0 + blockIdx.x);   // the tile holding ordinal `base` (k_tile_offsets)
     __syncthreads();
+    if (FROM_SCRATCH) {   // list of the non-empty tiles overlapping [base, base + count)
+        const long long end = base + count;
+        for (long long t0 = S.scan_tile0;; t0 += GB_THREADS) {
+            const long long t = t0 + threadIdx.x;
+            long long a = end, b = end;
+            u64 raw = 0;
+            if (t < n_tiles) {
+                raw = __ldg(tile_off + t);
+                a = (long long)(raw & ~GB_OFF_DROP);
+                b = (long long)(__ldg(tile_off + t + 1) & ~GB_OFF_DROP);
+            }
+            const bool keep = b > a && a < end && b > base;
+            const u32 bal = __ballot_sync(0xffffffffu, keep);
+            if (lane == 0) S.scan_w[warp] = (u32)__popc(bal);
+            __syncthreads();
+            u32 pos = S.n_list;
+            for (int w = 0; w < warp; ++w) pos += S.scan_w[w];
+            if (keep) {
+                const u32 k = pos + (u32)__popc(bal & lt_mask);
+                S.tile_id[k] = (u32)t | ((raw & GB_OFF_DROP) ? 0x80000000u : 0u);
+                S.tile_start[k] = (u32)(a - base + 0x40000000ll);   // biased: the first tile may start before the block
+            }
+            const bool more = __syncthreads_or(t == t0 + GB_THREADS - 1 && a < end && t + 1 < n_tiles);
+            if (threadIdx.x == 0) {
+                u32 tot = 0;
+                for (int w = 0; w < GB_WARPS; ++w) tot += S.scan_w[w];
+                S.n_list += tot;
+            }
+            __syncthreads();
+            if (!more) break;
+        }
+    }
 
     // ---- phase 1: load, warp-level dedup of the keys, hash insert by one lane per distinct key ----
     int2 obs[GB_ITEMS];
+    int list_pos = 0;
     u32 meta[GB_ITEMS];   // slot (12) | lanes of the same key before me (5) << 12 | same-key lanes - 1 (5) << 17 | leader (5) << 22
 #pragma unroll
     for (int i = 0; i < GB_ITEMS; ++i) {
@@ -302,7 +346,25 @@ __global__ void __launch_bounds__(GB_THREADS, 4)
         meta[i] = 0;
         obs[i] = make_int2(0, 0);
         if (valid) {
-            const int4 t = __ldg(reinterpret_cast<const int4*>(tuples + base + p));
+            long long src = base + p;
+            if (FROM_SCRATCH) {   // last listed tile starting at or before ordinal p
+                const u32 want = (u32)p + 0x40000000u;
+                int lo = list_pos;
+                if (i == 0) {   // binary search once; the following items continue from the previous tile
+                    int hi = (int)S.n_list;   // tile_start[lo] <= want < tile_start[hi]
+                    while (hi - lo > 1) {
+                        const int mid = (lo + hi) >> 1;
+                        if (S.tile_start[mid] <= want) lo = mid; else hi = mid;
+                    }
+                } else {
+                    const int last = (int)S.n_list - 1;
+                    while (lo < last && S.tile_start[lo + 1] <= want) ++lo;
+                }
+                list_pos = lo;
+                const u32 id = S.tile_id[lo];
+                src = (long long)(id & 0x7fffffffu) * 128 + (long long)(want - S.tile_start[lo]) + (id >> 31);
+            }
+            const int4 t = __ldg(reinterpret_cast<const int4*>(tuples + src));
             obs[i] = make_int2(t.z, t.w);
             const u64 key = ((u64)(u32)t.x << 32) | (u32)t.y;
             const u32 peers = __match_any_sync(vmask, key);
@@ -1315,11 +1377,23 @@ int besst_group_tuples(besst_ctx* ctx, const besst_link_tuple* d_tuples, int64_t
     if (n == 0) return BESST_OK;
     u32* gstate = ctx->run_state.as<u32>();
     BESST_CUDA_TRY(ctx, cudaMemsetAsync(gstate, 0, 64, ctx->stream));
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaFuncSetAttribute(k_group_blocks<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(GroupSmem));
+        cudaFuncSetAttribute(k_group_blocks<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(GroupSmem));
+        attr_done = true;
+    }
     {
         KTimer kt(ctx, BESST_K_GROUP);
-        k_group_blocks<<<(unsigned)n_gblocks, GB_THREADS, sizeof(GroupSmem), ctx->stream>>>(
-            d_tuples, n, bv, block_bits, ctx->grouped.as<int2>(), ctx->run_key[0].as<u64>(), ctx->run_val[0].as<u32>(),
-            ctx->run_start.as<u32>(), ctx->run_cnt.as<u32>(), ctx->run_first.as<u32>(), gstate, run_cap);
+        if (d_tuples)
+            k_group_blocks<false><<<(unsigned)n_gblocks, GB_THREADS, sizeof(GroupSmem), ctx->stream>>>(
+                d_tuples, n, bv, block_bits, ctx->grouped.as<int2>(), ctx->run_key[0].as<u64>(), ctx->run_val[0].as<u32>(),
+                ctx->run_start.as<u32>(), ctx->run_cnt.as<u32>(), ctx->run_first.as<u32>(), gstate, run_cap, nullptr, 0, nullptr);
+        else   // the last extraction, in place
+            k_group_blocks<true><<<(unsigned)n_gblocks, GB_THREADS, sizeof(GroupSmem), ctx->stream>>>(
+                ctx->scratch_tuples.as<besst_link_tuple>(), n, bv, block_bits, ctx->grouped.as<int2>(), ctx->run_key[0].as<u64>(),
+                ctx->run_val[0].as<u32>(), ctx->run_start.as<u32>(), ctx->run_cnt.as<u32>(), ctx->run_first.as<u32>(), gstate, run_cap,
+                ctx->tile_state.as<u64>(), ctx->n_rec_tiles, ctx->block_tile0.as<u32>());
     }
     BESST_CUDA_TRY(ctx, cudaGetLastError());
     u32 hs[2] = {0, 0};
@@ -1599,6 +1673,11 @@ static int launch_graph_impl(besst_ctx* ctx, const besst_lib_params& p, const be
     }   // no runs: fall through to the radix bucket
 
     int n_blocks = (int)((n + HB_TILE - 1) / HB_TILE);
+    if (!done && !d_tuples && !runs && n > 0) {   // the links of the last extraction: the radix bucket wants the BAM-ordered array
+        rc = besst_ensure_tuples(ctx);
+        if (rc) return rc;
+        d_tuples = ctx->tuples.as<besst_link_tuple>();
+    }
     if (!done) {
     // ---- K3: radix bucket (fallback for input without local order) ----------------------------------
     BESST_CUDA_TRY(ctx, ctx->key_a.ensure(8 * nz));

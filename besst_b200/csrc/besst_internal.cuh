@@ -108,10 +108,12 @@ struct besst_ctx {
     HBuf h_out[17];
 
     // link extraction
-    DBuf tuples, scratch_tuples, tile_aggs, fishy_keys, aligned, counters, tile_state, part_state, misc;
+    DBuf tuples, scratch_tuples, block_tile0, tile_aggs, fishy_keys, aligned, counters, tile_state, part_state, misc;
     int64_t fishy_cap = 0;
     int64_t n_tuples = 0, n_fishy_keys = 0;
+    int64_t n_rec_tiles = 0;     // 128-record tiles of the last extraction (scratch_tuples / tile_state layout)
     bool have_links = false;
+    bool tuples_valid = false;   // `tuples` holds the BAM-ordered array (else the links still sit in scratch_tuples)
 
     // sort
     DBuf key_a, key_b, idx_a, idx_b, hist, sort_state;
@@ -159,6 +161,7 @@ int besst_launch_extract(besst_ctx* ctx, const besst_lib_params& p, const Device
 int besst_extract_begin(besst_ctx* ctx, const besst_lib_params& p, int64_t n);
 int besst_extract_slice(besst_ctx* ctx, const besst_lib_params& p, const DeviceRecords& rec, int64_t r0, int64_t r1);
 int besst_extract_finish(besst_ctx* ctx, const besst_lib_params& p, int64_t n, bool* overflow);
+int besst_ensure_tuples(besst_ctx* ctx);
 
 // sort + CSR: tuples -> sorted (key, idx) -> edges
 int besst_launch_graph(besst_ctx* ctx, const besst_lib_params& p, const besst_link_tuple* d_tuples, int64_t n_tuples,
@@ -177,6 +180,7 @@ int besst_launch_runs_pack(besst_ctx* ctx, int world, int32_t* out_obs, besst_ru
 int besst_launch_runs_import(besst_ctx* ctx, const besst_run_desc* desc, int64_t n_runs, int world, int block_bits,
                              const int64_t* src_run_counts, const int64_t* src_link_counts, const int64_t* src_first_base,
                              int* low_bits);
+// d_tuples == nullptr: group the last extraction straight from its tile-local scratch runs
 int besst_group_tuples(besst_ctx* ctx, const besst_link_tuple* d_tuples, int64_t n, int bv, int block_bits, int64_t* n_runs,
                        int* overflow);
 

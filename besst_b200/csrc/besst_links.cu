@@ -677,16 +677,23 @@ __global__ void __launch_bounds__(SC_THREADS) k_chunk_resolve(const Agg* __restr
 }
 
 // level 0 again, now with what each chunk receives: exact output offset of every tile
+// also: block_tile0[g] = the tile holding the tuple with ordinal 2048 * g (where the grouping block g of the
+// run-merge bucket starts reading the scratch runs)
 __global__ void __launch_bounds__(SC_THREADS) k_tile_offsets(const Agg* __restrict__ aggs, long long n_tiles,
                                                              const ChunkIn* __restrict__ chunk_in, u64* tile_off,
-                                                             int detect_dup) {
+                                                             int detect_dup, u32* block_tile0) {
     __shared__ ScanSmem S;
     const long long i = (long long)blockIdx.x * SC_THREADS + threadIdx.x;
     const Agg a = load_agg(aggs, i, n_tiles);
     const ChunkIn in = chunk_in[blockIdx.x];
     const Last carry = {1, in.carry_o1, in.carry_o2};
     const ScanResult R = block_scan_aggs(a, carry, detect_dup, S);
-    if (i < n_tiles) tile_off[i] = (in.offset + R.excl) | (R.drop_first ? OFF_DROP : 0ull);
+    if (i < n_tiles) {
+        const u64 a = in.offset + R.excl;
+        tile_off[i] = a | (R.drop_first ? OFF_DROP : 0ull);
+        const u64 g = (a + 2047) >> 11;   // a tile keeps at most 128 tuples: it can hold at most one block start
+        if ((g << 11) < a + R.cnt_adj) block_tile0[g] = (u32)i;
+    }
 }
 
 // tile-local scratch runs -> the final BAM-ordered tuple array
@@ -877,6 +884,8 @@ int besst_launch_partition(besst_ctx* ctx, int world, besst_link_tuple* out_tupl
     if (world < 1 || world > PT_MAX_WORLD) { ctx->err = "partition: world size must be 1..16"; return BESST_E_INVALID; }
     if (ctx->n_tuples >= (1ll << 30) || ctx->n_fishy_keys >= (1ll << 30)) { ctx->err = "partition: more than 2^30 items"; return BESST_E_INVALID; }
     int rc = BESST_OK;
+    if (out_tuples) rc = besst_ensure_tuples(ctx);
+    if (rc) return rc;
     if (out_tuples) rc = partition_impl<true>(ctx, ctx->tuples.p, ctx->n_tuples, world, out_tuples, out_ordinals, tuple_counts);
     else for (int d = 0; d < world; ++d) tuple_counts[d] = 0;   // run-level exchange: only the fishy keys travel as keys
     if (rc) return rc;
@@ -898,6 +907,7 @@ int besst_extract_begin(besst_ctx* ctx, const besst_lib_params& p, int64_t n) {
     BESST_CUDA_TRY(ctx, ctx->tile_aggs.ensure(sizeof(Agg) * (size_t)(n_tiles + n_chunks + 2)));
     BESST_CUDA_TRY(ctx, ctx->tile_state.ensure(sizeof(u64) * (size_t)(n_tiles + 2) + sizeof(ChunkIn) * (size_t)(n_chunks + 1)));
     BESST_CUDA_TRY(ctx, ctx->scratch_tuples.ensure(sizeof(besst_link_tuple) * (size_t)(n_tiles > 0 ? n_tiles : 1) * WT));
+    BESST_CUDA_TRY(ctx, ctx->block_tile0.ensure(sizeof(u32) * (size_t)(n_tiles / 16 + 4)));   // one entry per 2048 accepted tuples
     if (ctx->fishy_cap == 0) ctx->fishy_cap = n / 8 + 4096;
     BESST_CUDA_TRY(ctx, ctx->fishy_keys.ensure(sizeof(u64) * (size_t)ctx->fishy_cap));
     BESST_CUDA_TRY(ctx, cudaMemsetAsync(ctx->aligned.p, 0, sizeof(u64) * (size_t)(ctx->n_contigs + 1), ctx->stream));
@@ -974,7 +984,7 @@ int besst_extract_finish(besst_ctx* ctx, const besst_lib_params& p, int64_t n, b
     if (n_tiles > 0) {
         { KTimer kt(ctx, BESST_K_TILE_SCAN); k_tile_reduce<<<(unsigned)n_chunks, SC_THREADS, 0, ctx->stream>>>(aggs, n_tiles, chunk_aggs, p.detect_duplicate); }
         { KTimer kt(ctx, BESST_K_TILE_SCAN); k_chunk_resolve<<<1, SC_THREADS, 0, ctx->stream>>>(chunk_aggs, n_chunks, chunk_in, tile_off + n_tiles, p.halo_prev_obs1, p.halo_prev_obs2, p.detect_duplicate, counters, globals); }
-        { KTimer kt(ctx, BESST_K_TILE_SCAN); k_tile_offsets<<<(unsigned)n_chunks, SC_THREADS, 0, ctx->stream>>>(aggs, n_tiles, chunk_in, tile_off, p.detect_duplicate); }
+        { KTimer kt(ctx, BESST_K_TILE_SCAN); k_tile_offsets<<<(unsigned)n_chunks, SC_THREADS, 0, ctx->stream>>>(aggs, n_tiles, chunk_in, tile_off, p.detect_duplicate, ctx->block_tile0.as<u32>()); }
         BESST_CUDA_TRY(ctx, cudaGetLastError());
     } else {
         const int64_t halo[2] = {p.halo_prev_obs1, p.halo_prev_obs2};
@@ -990,16 +1000,30 @@ int besst_extract_finish(besst_ctx* ctx, const besst_lib_params& p, int64_t n, b
         *overflow = true;
         return BESST_OK;
     }
+    // the accepted tuples stay in their tile-local scratch runs: the run-merge bucket reads them from
+    // there (tile_off says where); the BAM-ordered array is only materialised on demand (besst_ensure_tuples)
+    ctx->n_rec_tiles = n_tiles;
+    ctx->tuples_valid = false;
+    ctx->have_links = true;
+    return BESST_OK;
+}
+
+// materialise the BAM-ordered tuple array (tuple-level multi-GPU exchange, radix fallback, ABI accessors)
+int besst_ensure_tuples(besst_ctx* ctx) {
+    if (!ctx->have_links) { ctx->err = "no extracted links"; return BESST_E_STATE; }
+    if (ctx->tuples_valid) return BESST_OK;
     BESST_CUDA_TRY(ctx, ctx->tuples.ensure(sizeof(besst_link_tuple) * (size_t)(ctx->n_tuples > 0 ? ctx->n_tuples : 1)));
     if (ctx->n_tuples > 0) {
+        const long long n_tiles = ctx->n_rec_tiles;
         long long cgrid = (long long)ctx->sm_count * 8;
         const long long cmax = (n_tiles + 7) / 8;
         if (cgrid > cmax) cgrid = cmax;
         KTimer kt(ctx, BESST_K_COMPACT);
-        k_compact_tuples<<<(unsigned)cgrid, 256, 0, ctx->stream>>>(ctx->scratch_tuples.as<besst_link_tuple>(), tile_off, n_tiles, ctx->tuples.as<besst_link_tuple>());
+        k_compact_tuples<<<(unsigned)cgrid, 256, 0, ctx->stream>>>(ctx->scratch_tuples.as<besst_link_tuple>(), ctx->tile_state.as<u64>(), n_tiles,
+                                                                   ctx->tuples.as<besst_link_tuple>());
         BESST_CUDA_TRY(ctx, cudaGetLastError());
     }
-    ctx->have_links = true;
+    ctx->tuples_valid = true;
     return BESST_OK;
 }
 

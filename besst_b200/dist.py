@@ -107,7 +107,7 @@ class CudaBackend(object):
 
     def partition_fishy(self, world):
         torch = self.torch
-        _, (_, nf) = self.engine.links_device()
+        _, nf = self.engine.fishy_device()
         send_f = self._buf("send_f", nf, torch.int64)
         _, fc = self.engine.links_partition(world, None, send_f.data_ptr(), None)
         return send_f[:nf], fc
@@ -263,10 +263,8 @@ class DistributedGraphBuild(object):
         counters[abi.CNT_LAST_OBS1:] = 0
         dist.all_reduce(aligned, op=dist.ReduceOp.SUM, group=self.group)
         dist.all_reduce(counters, op=dist.ReduceOp.SUM, group=self.group)
-        lasts = [last.clone() for _ in range(world)]
-        dist.all_gather(lasts, last, group=self.group)
         self.last = dict(sizes=sizes, global_first=True, n_tuples_by_rank=n_by_rank.tolist(), aligned=aligned, counters=counters,
-                         last_call=[tuple(int(x) for x in t.tolist()) for t in lasts], halo=(p.halo_prev_obs1, p.halo_prev_obs2))
+                         last_local=last, halo=(p.halo_prev_obs1, p.halo_prev_obs2))
         return sizes
 
     # -- results ------------------------------------------------------------------------------------
@@ -287,6 +285,10 @@ class DistributedGraphBuild(object):
         counters = np.asarray(L["counters"].cpu().numpy(), dtype=np.int64).copy()
         # the globally last CreateEdge call: every rank starts from its halo, so rank world-1's
         # pair already folds in all earlier ranks
+        if "last_call" not in L:   # run-level path: gathered here, outside the step (collective: every rank calls fetch_local)
+            lasts = [L["last_local"].clone() for _ in range(self.world)]
+            self.dist.all_gather(lasts, L["last_local"], group=self.group)
+            L["last_call"] = [tuple(int(x) for x in t.tolist()) for t in lasts]
         last = L["last_call"][self.world - 1]
         counters[abi.CNT_LAST_OBS1], counters[abi.CNT_LAST_OBS2] = last
         res.counters = counters

@@ -93,6 +93,12 @@ class CudaEngine(object):
         self._check(self._L.besst_links_fishy_device(self._ctx, C.byref(fp), C.byref(fn)), "besst_links_fishy_device")
         return (p.value or 0, n.value), (fp.value or 0, fn.value)
 
+    def fishy_device(self):
+        """(device pointer, count) of the fishy keys of the last extraction (does not materialise the tuple array)."""
+        fp, fn = C.c_void_p(), C.c_int64()
+        self._check(self._L.besst_links_fishy_device(self._ctx, C.byref(fp), C.byref(fn)), "besst_links_fishy_device")
+        return fp.value or 0, fn.value
+
     def links_partials(self):
         aligned = np.zeros(self._n_contigs, dtype=np.int64)
         counters = np.zeros(abi.N_COUNTERS, dtype=np.int64)
