@@ -217,80 +217,17 @@ __global__ void __launch_bounds__(K1T_THREADS, K1T_MIN_CTAS) k_extract_links_tma
     }
     __syncthreads();
     const long long n = P.rec.n;
-    const long long warp_global = (long long)blockIdx.x * K1T_WARPS + warp;
-    const long long n_warps = (long long)gridDim.x * K1T_WARPS;
+    const int warp_global = (int)blockIdx.x * K1T_WARPS + warp;
+    const int n_warps = (int)gridDim.x * K1T_WARPS;
     const u32 n_contigs = (u32)P.n_contigs;
+    // acceptance test obs1 + obs2 < ins_size_threshold (:840) in 32 bits: both terms are > 25 when it matters
+    const bool thr_all = P.threshold_i > 0xffffffffll;
+    const u32 thr_u = P.threshold_i <= 0 ? 0u : (thr_all ? 0xffffffffu : (u32)P.threshold_i);
+    const bool second_on = P.extend && P.scoring;
+    u32 demand_par = 0;
 
-    // stage state, warp-uniform: bit s of `st_async` = stage s was filled by TMA (wait on its barrier),
-    // of `st_pos` = its pos/mpos columns are (being) loaded, of `st_par` = the parity to wait for next
-    u32 st_async = 0, st_pos = 0, st_par = 0, demand_par = 0;
-    auto issue = [&](long long tile, int s, bool want_pos) {
-        const bool full = vec_ok && ((tile + 1) * WT <= n);
-        st_async = (st_async & ~(1u << s)) | ((full ? 1u : 0u) << s);
-        st_pos = (st_pos & ~(1u << s)) | (((want_pos || !full) ? 1u : 0u) << s);
-        if (full && elect_one()) {
-            const long long r0 = tile * WT;
-            const u32 bar = bar0 + 8u * s;
-            const u32 dst = smem_u32(&W.buf[s]);
-            mbar_expect_tx(bar, TILE_BYTES_NOPOS + (want_pos ? TILE_BYTES_POS : 0u));
-            bulk_g2s(dst + 0 * 4 * WT, P.rec.tid + r0, 4 * WT, bar);
-            bulk_g2s(dst + 1 * 4 * WT, P.rec.mtid + r0, 4 * WT, bar);
-            bulk_g2s(dst + 2 * 4 * WT, P.rec.qlen + r0, 4 * WT, bar);
-            if (want_pos) {
-                bulk_g2s(dst + 3 * 4 * WT, P.rec.pos + r0, 4 * WT, bar);
-                bulk_g2s(dst + 4 * 4 * WT, P.rec.mpos + r0, 4 * WT, bar);
-            }
-            bulk_g2s(dst + 5 * 4 * WT, P.rec.flag + r0, 2 * WT, bar);
-            bulk_g2s(dst + 5 * 4 * WT + 2 * WT, P.rec.mapq + r0, WT, bar);
-        }
-    };
-
-    u32 cand_hist = 7u;   // bit t: the t-th last tile had a CreateEdge candidate
-    // tiles are handed out dynamically in batches of K1T_BATCH consecutive tiles (one ticket per warp
-    // and batch; a ticket per tile would serialise 3 M same-address atomics) after a static first
-    // batch: warps progress at different speeds and a static split leaves a quarter of the warp slots
-    // idle towards the end.  The ticket of the next batch is requested a whole batch ahead.
-    u32* const ticket = reinterpret_cast<u32*>(P.globals + 2);
-    long long b_cur = warp_global * K1T_BATCH;
-    int b_j = 0;
-    u32 t_raw = 0;
-    if (lane == 0) t_raw = atomicAdd(ticket, 1u);
-    auto next_tile = [&]() -> long long {
-        if (b_j == K1T_BATCH) {
-            b_cur = (n_warps + (long long)__shfl_sync(0xffffffffu, t_raw, 0)) * K1T_BATCH;
-            b_j = 0;
-            if (lane == 0) t_raw = atomicAdd(ticket, 1u);
-        }
-        return b_cur + (b_j++);
-    };
-    long long wt = next_tile();
-    if (wt < P.n_tiles) issue(wt, 0, true);
-    long long nx = next_tile();
-    for (u32 it = 0; wt < P.n_tiles; ++it) {
-        const int s = (int)(it & 1u);
-        if (nx < P.n_tiles) issue(nx, s ^ 1, (cand_hist & 7u) != 0);
-        TileBuf& B = W.buf[s];
-        if (st_async >> s & 1u) {
-            mbar_wait(bar0 + 8u * s, (st_par >> s) & 1u);
-            st_par ^= 1u << s;
-        } else {   // ragged last tile or unaligned columns: plain bounds-checked loads into the stage
-            const long long idx0 = wt * WT + (long long)lane * WT_ITEMS;
-#pragma unroll
-            for (int i = 0; i < WT_ITEMS; ++i) {
-                const long long r = idx0 + i;
-                const bool in = r < n;
-                const int q = lane * WT_ITEMS + i;
-                B.tid[q] = in ? __ldg(P.rec.tid + r) : -1;
-                B.mtid[q] = in ? __ldg(P.rec.mtid + r) : -1;
-                B.qlen[q] = in ? __ldg(P.rec.qlen + r) : 0;
-                B.pos[q] = in ? __ldg(P.rec.pos + r) : 0;
-                B.mpos[q] = in ? __ldg(P.rec.mpos + r) : 0;
-                B.flag[q] = in ? __ldg(P.rec.flag + r) : (unsigned short)0;
-                B.mapq[q] = in ? __ldg(P.rec.mapq + r) : (unsigned char)0;
-            }
-            __syncwarp();
-        }
-
+    // ---- one tile, staged in B.  pos_ready: its pos/mpos columns are (being) loaded.  -> it had a candidate
+    auto process = [&](const long long wt, TileBuf& B, const bool pos_ready, const bool can_demand) -> bool {
         int tid[WT_ITEMS], mtid[WT_ITEMS], qlen[WT_ITEMS];
         u32 flag[WT_ITEMS], mapq[WT_ITEMS];
         {
@@ -306,14 +243,16 @@ __global__ void __launch_bounds__(K1T_THREADS, K1T_MIN_CTAS) k_extract_links_tma
             mapq[0] = m & 0xffu; mapq[1] = (m >> 8) & 0xffu; mapq[2] = (m >> 16) & 0xffu; mapq[3] = m >> 24;
         }
 
-        // ---- per-record classification (CreateGraph.py:118-206); only word 0 of a row is needed ----
-        // word 0 == 0 <=> the contig is absent (state ABSENT == 0) or out of range (:118-130)
-        const int xa = ((u32)tid[0] < n_contigs) ? __ldg(reinterpret_cast<const int*>(P.rows + tid[0])) : 0;
+        // ---- per-record classification (CreateGraph.py:118-206); only word 0 of a contig row is needed:
+        // 0 <=> absent (state ABSENT == 0) or out of range (:118-130).  Kept branchy on purpose: the
+        // same-contig half of the records leaves early (a predicated version issued 24 % more instructions)
+        const int t0 = tid[0];
+        const int xa = ((u32)t0 < n_contigs) ? __ldg(reinterpret_cast<const int*>(P.rows + t0)) : 0;
         u32 elig = 0, cov = 0;   // one bit per item
 #pragma unroll
         for (int i = 0; i < WT_ITEMS; ++i) {
             int x1 = xa;
-            if (i > 0 && tid[i] != tid[0]) x1 = ((u32)tid[i] < n_contigs) ? __ldg(reinterpret_cast<const int*>(P.rows + tid[i])) : 0;
+            if (i > 0 && tid[i] != t0) x1 = ((u32)tid[i] < n_contigs) ? __ldg(reinterpret_cast<const int*>(P.rows + tid[i])) : 0;
             const int mq = (int)mapq[i];
             const bool covered = (mq >= P.min_mapq) || mq == 0;                                           // :138
             if (tid[i] == mtid[i]) {   // same contig: same scaffold, no link, no fishy pair
@@ -337,41 +276,41 @@ __global__ void __launch_bounds__(K1T_THREADS, K1T_MIN_CTAS) k_extract_links_tma
             }
             if (mq == 0) c_nonuniq++;                                                                     // :166-167
             if ((f & 0x80u) && !unmapped && mq >= P.min_mapq) {                                           // :169
-                const bool both_large = row_state(x1) == BESST_CTG_LARGE && row_state(x2) == BESST_CTG_LARGE;
-                const bool both_small = row_state(x1) == BESST_CTG_SMALL && row_state(x2) == BESST_CTG_SMALL;
-                // :170 large-large needs different scaffolds; :184-206 (extend_paths) small-small needs
-                // different scaffolds, exactly one small always qualifies
-                const bool e = both_large ? diff_scaf : (P.extend && (both_small ? diff_scaf : true));
+                // :170 large-large needs different scaffolds; :184-206 (extend_paths) small-small needs different
+                // scaffolds, exactly one small always qualifies.  s1|s2: 1 both large, 2 both small, 3 one of each
+                const u32 so = ((u32)x1 | (u32)x2) & 3u;
+                const bool e = so == 3u ? P.extend != 0 : (diff_scaf && (so == 1u || P.extend != 0));
                 if (e) elig |= 1u << i;
             }
         }
 
         // ---- coverage: warp-aggregated 64-bit atomics (:138-139) ----------------------------
         {
-            int t0 = -1, s0 = 0;
+            int s0 = 0;
+            u32 rest = 0;
 #pragma unroll
-            for (int i = 0; i < WT_ITEMS; ++i)
-                if (cov >> i & 1u) {
-                    if (t0 < 0) t0 = tid[i];
-                    if (tid[i] == t0) { s0 += qlen[i]; cov &= ~(1u << i); }
-                }
+            for (int i = 0; i < WT_ITEMS; ++i) {
+                const bool c = cov >> i & 1u, own = tid[i] == t0;
+                s0 += (c && own) ? qlen[i] : 0;
+                rest |= ((c && !own) ? 1u : 0u) << i;
+            }
             // common case: the whole tile lies on one contig -> one reduction, one atomic
-            const int tw = __shfl_sync(0xffffffffu, tid[0], 0);
-            if (__all_sync(0xffffffffu, t0 < 0 || t0 == tw)) {
+            const int tw = __shfl_sync(0xffffffffu, t0, 0);
+            if (__all_sync(0xffffffffu, s0 == 0 || t0 == tw)) {
                 const int sum = __reduce_add_sync(0xffffffffu, s0);
                 if (lane == 0 && sum != 0) atomicAdd(&P.aligned[tw], (u64)(long long)sum);
             } else {
-                const u32 act = __ballot_sync(0xffffffffu, t0 >= 0);
-                if (t0 >= 0) {
+                const u32 act = __ballot_sync(0xffffffffu, s0 != 0);
+                if (s0 != 0) {
                     const u32 peers = __match_any_sync(act, t0);
                     const int sum = __reduce_add_sync(peers, s0);
                     if (lane == __ffs(peers) - 1) atomicAdd(&P.aligned[t0], (u64)(long long)sum);
                 }
             }
-            if (__any_sync(0xffffffffu, cov != 0)) {   // a lane's 4 records straddle contigs: rare
+            if (__any_sync(0xffffffffu, rest != 0)) {   // a lane's 4 records straddle contigs: rare
 #pragma unroll
                 for (int i = 1; i < WT_ITEMS; ++i)
-                    if (cov >> i & 1u) atomicAdd(&P.aligned[tid[i]], (u64)(long long)qlen[i]);
+                    if (rest >> i & 1u) atomicAdd(&P.aligned[tid[i]], (u64)(long long)qlen[i]);
             }
         }
 
@@ -387,13 +326,12 @@ __global__ void __launch_bounds__(K1T_THREADS, K1T_MIN_CTAS) k_extract_links_tma
         int n_out = 0;
         u32 first_flags = 0;
         int first_o1 = 0, first_o2 = 0, carry_o1 = 0, carry_o2 = 0;
-        cand_hist = (cand_hist << 1) | (total_c > 0 ? 1u : 0u);
         if (total_c > 0) {
             int slot = incl_c - my_c;
 #pragma unroll
             for (int i = 0; i < WT_ITEMS; ++i)
                 if (elig >> i & 1u) W.cand[slot++] = (unsigned char)(lane * WT_ITEMS + i);
-            if (!(st_pos >> s & 1u)) {   // pos/mpos were not fetched ahead for this tile
+            if (can_demand && !pos_ready) {   // pos/mpos were not fetched ahead for this tile
                 if (elect_one()) {
                     const long long r0 = wt * WT;
                     mbar_expect_tx(bar0 + 16u, TILE_BYTES_POS);
@@ -409,19 +347,20 @@ __global__ void __launch_bounds__(K1T_THREADS, K1T_MIN_CTAS) k_extract_links_tma
             // previous call (:835-838), acceptance test (:840), counters.  The tile's first call has no
             // in-tile predecessor: assumed "not a duplicate" here and settled by the aggregate scan.
             bool have_carry = false;
+            int4* const out = reinterpret_cast<int4*>(P.scratch) + wt * WT;
             for (int r = 0; r < total_c; r += 32) {
                 const int k = r + lane;
                 const bool active = k < total_c;
                 int o1 = 0, o2 = 0;
-                u32 nu = 0, nv = 0, fl = 0;
+                u32 nu = 0, nv = 0;
                 bool mq0 = false, both_large = false;
                 if (active) {
                     const int j = W.cand[k];
-                    fl = B.flag[j];
+                    const u32 fl = B.flag[j];
                     mq0 = B.mapq[j] == 0;
                     const int4 r1 = __ldg(P.rows + B.tid[j]);   // L1 hits: word 0 was gathered a moment ago
                     const int4 r2 = __ldg(P.rows + B.mtid[j]);
-                    both_large = row_state(r1.x) == BESST_CTG_LARGE && row_state(r2.x) == BESST_CTG_LARGE;
+                    both_large = (((u32)r1.x | (u32)r2.x) & 3u) == (u32)BESST_CTG_LARGE;   // neither is absent here
                     int s1, s2;
                     pos_dir<INT_RL>(row_dir(r1.x), !(fl & 0x10u), P.orientation, r1.y, B.pos[j], r1.w, r1.z, P.read_len, P.read_len_i, o1, s1);
                     pos_dir<INT_RL>(row_dir(r2.x), !(fl & 0x20u), P.orientation, r2.y, B.mpos[j], r2.w, r2.z, P.read_len, P.read_len_i, o2, s2);
@@ -434,32 +373,33 @@ __global__ void __launch_bounds__(K1T_THREADS, K1T_MIN_CTAS) k_extract_links_tma
                 bool accepted = false;
                 if (active) {
                     c_calls++;
-                    if (mq0) c_nonuniq_scaf++;
+                    c_nonuniq_scaf += mq0 ? 1 : 0;
                     const bool dup = has_prev && o1 == p1 && o2 == p2;
-                    bool is_dupl = false;
-                    if (dup) { c_dups++; is_dupl = P.detect_dup; }
-                    const bool pass = ((long long)o1 + o2) < P.threshold_i && o1 > 25 && o2 > 25;
-                    const bool second = both_large && P.extend && P.scoring;
+                    c_dups += dup ? 1 : 0;
+                    const bool is_dupl = dup && P.detect_dup;
+                    const bool pass = o1 > 25 && o2 > 25 && (thr_all || (u32)o1 + (u32)o2 < thr_u);
+                    const bool second = both_large && second_on;
                     if (!has_prev) {   // the tile's first call
                         first_flags = AGG_HAS | (pass ? AGG_PASS : 0u) | (second ? AGG_SECOND : 0u) | (mq0 ? AGG_MQ0 : 0u);
                         first_o1 = o1; first_o2 = o2;
                     }
                     if (!is_dupl) {
-                        if (pass) { c_count++; accepted = true; } else c_toolong++;
-                        if (second) {   // second call into G_prime (:180-183); prev_obs was reset to -1
-                            if (mq0) c_nonuniq_scaf++;
-                            const bool dup2 = (o1 == -1 && o2 == -1);
-                            if (dup2) c_dups++;
-                            if (!(dup2 && P.detect_dup)) { if (pass) c_count++; else c_toolong++; }
-                        }
+                        // the second call into G_prime (:180-183) sees prev_obs reset to -1: a duplicate only of (-1,-1)
+                        const bool dup2 = second && o1 == -1 && o2 == -1;
+                        const int calls = 1 + ((second && !(dup2 && P.detect_dup)) ? 1 : 0);
+                        c_nonuniq_scaf += (second && mq0) ? 1 : 0;
+                        c_dups += dup2 ? 1 : 0;
+                        c_count += pass ? calls : 0;
+                        c_toolong += pass ? 0 : calls;
+                        accepted = pass;
                     }
                 }
                 const u32 bal = __ballot_sync(0xffffffffu, accepted);
                 if (accepted) {
                     int4 t;
-                    if (nu < nv) { t.x = (int)nu; t.y = (int)nv; t.z = o1; t.w = o2; }
-                    else { t.x = (int)nv; t.y = (int)nu; t.z = o2; t.w = o1; }
-                    reinterpret_cast<int4*>(P.scratch)[wt * WT + n_out + __popc(bal & lt_mask)] = t;
+                    const bool fw = nu < nv;
+                    t.x = (int)(fw ? nu : nv); t.y = (int)(fw ? nv : nu); t.z = fw ? o1 : o2; t.w = fw ? o2 : o1;
+                    out[n_out + __popc(bal & lt_mask)] = t;
                 }
                 n_out += __popc(bal);
                 const int last_lane = (total_c - r > 32) ? 31 : (total_c - r - 1);
@@ -477,8 +417,78 @@ __global__ void __launch_bounds__(K1T_THREADS, K1T_MIN_CTAS) k_extract_links_tma
             a[1] = make_int4(carry_o2, n_out, 0, 0);
             a[2] = make_int4(0, 0, 0, 0);
         }
+        return total_c > 0;
+    };
+
+    // ---- full tiles: TMA-staged, double buffered, handed out dynamically in batches of K1T_BATCH
+    // consecutive tiles (one ticket per warp and batch; a ticket per tile would serialise 3 M same-address
+    // atomics) after a static first batch: warps progress at different speeds and a static split leaves
+    // a quarter of the warp slots idle towards the end.  The next batch's ticket is requested a batch ahead.
+    const long long n_full = vec_ok ? n / WT : 0;
+    auto issue = [&](const long long tile, const int s, const bool want_pos) {
+        if (elect_one()) {
+            const long long r0 = tile * WT;
+            const u32 bar = bar0 + 8u * s;
+            const u32 dst = smem_u32(&W.buf[s]);
+            mbar_expect_tx(bar, TILE_BYTES_NOPOS + (want_pos ? TILE_BYTES_POS : 0u));
+            bulk_g2s(dst + 0 * 4 * WT, P.rec.tid + r0, 4 * WT, bar);
+            bulk_g2s(dst + 1 * 4 * WT, P.rec.mtid + r0, 4 * WT, bar);
+            bulk_g2s(dst + 2 * 4 * WT, P.rec.qlen + r0, 4 * WT, bar);
+            if (want_pos) {
+                bulk_g2s(dst + 3 * 4 * WT, P.rec.pos + r0, 4 * WT, bar);
+                bulk_g2s(dst + 4 * 4 * WT, P.rec.mpos + r0, 4 * WT, bar);
+            }
+            bulk_g2s(dst + 5 * 4 * WT, P.rec.flag + r0, 2 * WT, bar);
+            bulk_g2s(dst + 5 * 4 * WT + 2 * WT, P.rec.mapq + r0, WT, bar);
+        }
+    };
+    u32* const ticket = reinterpret_cast<u32*>(P.globals + 2);
+    u32 cand_hist = 7u;   // bit t: the t-th last tile had a CreateEdge candidate
+    u32 st_pos = 1u;      // bit s: stage s has (or is getting) its pos/mpos columns
+    long long wt = (long long)warp_global * K1T_BATCH;
+    int b_left = K1T_BATCH - 1;   // tiles left in the current batch after wt
+    u32 t_raw = 0;
+    if (lane == 0) t_raw = atomicAdd(ticket, 1u);
+    if (wt < n_full) issue(wt, 0, true);
+    for (u32 it = 0; wt < n_full; ++it) {
+        const int s = (int)(it & 1u);
+        long long nx = wt + 1;
+        if (b_left == 0) {   // next batch: (ticket + number of static batches) * batch size
+            nx = ((long long)n_warps + (long long)__shfl_sync(0xffffffffu, t_raw, 0)) * K1T_BATCH;
+            b_left = K1T_BATCH;
+            if (lane == 0) t_raw = atomicAdd(ticket, 1u);
+        }
+        --b_left;
+        if (nx < n_full) {
+            const bool want = (cand_hist & 7u) != 0;
+            issue(nx, s ^ 1, want);
+            st_pos = (st_pos & ~(2u >> s)) | ((want ? 2u : 0u) >> s);   // bit s ^ 1
+        }
+        mbar_wait(bar0 + 8u * s, (it >> 1) & 1u);
+        const bool had = process(wt, W.buf[s], (st_pos >> s) & 1u, true);
+        cand_hist = (cand_hist << 1) | (had ? 1u : 0u);
         wt = nx;
-        nx = next_tile();
+    }
+    // ---- leftovers: the ragged last tile, or every tile when a column is not 16-byte aligned: plain
+    // bounds-checked loads into stage 0 (no bulk copy is outstanding any more)
+    for (long long t = n_full + warp_global; t < P.n_tiles; t += n_warps) {
+        TileBuf& B = W.buf[0];
+        const long long idx0 = t * WT + (long long)lane * WT_ITEMS;
+#pragma unroll
+        for (int i = 0; i < WT_ITEMS; ++i) {
+            const long long r = idx0 + i;
+            const bool in = r < n;
+            const int q = lane * WT_ITEMS + i;
+            B.tid[q] = in ? __ldg(P.rec.tid + r) : -1;
+            B.mtid[q] = in ? __ldg(P.rec.mtid + r) : -1;
+            B.qlen[q] = in ? __ldg(P.rec.qlen + r) : 0;
+            B.pos[q] = in ? __ldg(P.rec.pos + r) : 0;
+            B.mpos[q] = in ? __ldg(P.rec.mpos + r) : 0;
+            B.flag[q] = in ? __ldg(P.rec.flag + r) : (unsigned short)0;
+            B.mapq[q] = in ? __ldg(P.rec.mapq + r) : (unsigned char)0;
+        }
+        __syncwarp();
+        process(t, B, true, false);
     }
 
     // ---- flush the per-thread counters ------------------------------------------------------------
