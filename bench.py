@@ -210,8 +210,12 @@ def run_ours(args):
     # nvidia-smi samples every 100 ms and the timed region lasts a few tens of ms: keep the same load running
     # (untimed) until there are enough clock samples under load
     t_load = time.perf_counter()
-    while len(sampler.rows) < 6 and time.perf_counter() - t_load < 3.0:
-        step()
+    if world > 1:   # collectives inside: every rank must run the same number of steps
+        for _ in range(80):
+            step()
+    else:
+        while len(sampler.rows) < 6 and time.perf_counter() - t_load < 3.0:
+            step()
     torch.cuda.synchronize()
     clocks = sampler.finish()
     launches_timed = eng.kernel_launches() - launches_warm
