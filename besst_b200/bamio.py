@@ -1,11 +1,15 @@
-"""Pure-Python BGZF/BAM reader -> RecordBatch (host tooling, not the hot path).
+"""BAM file -> RecordBatch.
 
-In production the records come from pysam (`records.from_alignments`); pysam is
-not installed in this image, so tests and fixtures decode the reference's
-`testdata/*/mapped.bam` with this reader.  It follows the SAM/BAM spec's 32-byte
-fixed core; `qlen`/`alen` follow pysam 0.8.4's `query_alignment_length` /
-`reference_length`.  BAM decode stays outside the C ABI
-(SURVEY.md 8b, row "BAM decode"); a GPU inflate is a "next" row (8f rank 1).
+`read_bam_native` is the product path: libbesst_bamio.so inflates the BGZF
+blocks on a pool of host threads and decodes the fixed-core fields straight into the column layout
+the engine consumes (include/besst_bamio.h) -- one pass over the file instead of the reference's
+three to four pysam iterations per library (runBESST:162, libmetrics.py:63,257,293,
+CreateGraph.py:111).  It raises if the library is not built.
+
+`read_bam` is a pure-Python reader of the same format, kept as test tooling: the native reader is
+checked against it (tests/test_bamio.py) and fixtures can be decoded without the native library.
+Both follow the SAM/BAM spec's 32-byte fixed core; `qlen`/`alen` follow pysam 0.8.4's
+`query_alignment_length` / `reference_length`.
 """
 from __future__ import annotations
 
@@ -14,7 +18,103 @@ import struct
 
 import numpy as np
 
+import ctypes as C
+import os
+
 from .records import RecordBatch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+BAMIO_SO = os.path.join(_HERE, "libbesst_bamio.so")
+_bamio = None
+
+
+class _Columns(C.Structure):
+    _fields_ = [("n", C.c_int64)] + [(k, C.c_void_p) for k in ("tid", "mtid", "pos", "mpos", "tlen", "qlen", "flag", "mapq",
+                                                               "rlen", "alen")] + [("n_head", C.c_int64)]
+
+
+class BamStats(C.Structure):
+    _fields_ = [("compressed_bytes", C.c_int64), ("uncompressed_bytes", C.c_int64), ("blocks", C.c_int64),
+                ("records", C.c_int64), ("seconds_inflate", C.c_double), ("seconds_decode", C.c_double),
+                ("seconds_total", C.c_double), ("threads", C.c_int32)]
+
+
+BAMIO_EXPORTS = ["besst_bamio_abi_version", "besst_bam_read", "besst_bam_n_refs", "besst_bam_ref_name", "besst_bam_ref_length",
+                 "besst_bam_get_columns", "besst_bam_get_stats", "besst_bam_close"]
+
+
+def load_bamio():
+    global _bamio
+    if _bamio is not None:
+        return _bamio
+    if not os.path.exists(BAMIO_SO):
+        raise IOError("libbesst_bamio.so is not built (%s): run `python -m besst_b200.build`" % BAMIO_SO)
+    L = C.CDLL(BAMIO_SO)
+    L.besst_bam_read.restype = C.c_void_p
+    L.besst_bam_read.argtypes = [C.c_char_p, C.c_int32, C.c_int64, C.c_int64, C.c_char_p, C.c_int32]
+    L.besst_bam_n_refs.restype = C.c_int64
+    L.besst_bam_n_refs.argtypes = [C.c_void_p]
+    L.besst_bam_ref_name.restype = C.c_char_p
+    L.besst_bam_ref_name.argtypes = [C.c_void_p, C.c_int64]
+    L.besst_bam_ref_length.restype = C.c_int64
+    L.besst_bam_ref_length.argtypes = [C.c_void_p, C.c_int64]
+    L.besst_bam_get_columns.argtypes = [C.c_void_p, C.POINTER(_Columns)]
+    L.besst_bam_get_stats.argtypes = [C.c_void_p, C.POINTER(BamStats)]
+    L.besst_bam_close.argtypes = [C.c_void_p]
+    _bamio = L
+    return L
+
+
+class _BamHandle(object):
+    """Owns the native column buffers; the numpy views of a RecordBatch keep it alive."""
+
+    def __init__(self, lib, ptr):
+        self.lib, self.ptr = lib, ptr
+
+    def __del__(self):
+        if getattr(self, "ptr", None):
+            self.lib.besst_bam_close(self.ptr)
+            self.ptr = None
+
+
+def read_bam_native(path, threads=0, max_records=None, head_records=1000):
+    """-> RecordBatch whose columns are zero-copy views of the native buffers (`batch.stats` has the
+    inflate/decode timings).  rlen/alen are kept for the first `head_records` records only (the
+    reference reads 1000, libmetrics.py:246-266)."""
+    L = load_bamio()
+    err = C.create_string_buffer(512)
+    ptr = L.besst_bam_read(os.fsencode(path), int(threads), -1 if max_records is None else int(max_records), int(head_records),
+                           err, len(err))
+    if not ptr:
+        raise IOError("besst_bam_read: %s" % err.value.decode(errors="replace"))
+    h = _BamHandle(L, ptr)
+    cols = _Columns()
+    L.besst_bam_get_columns(ptr, C.byref(cols))
+    n, nh = int(cols.n), int(cols.n_head)
+
+    def view(p, count, dt):
+        if count == 0 or not p:
+            return np.zeros(0, dtype=dt)
+        buf = (C.c_char * (count * np.dtype(dt).itemsize)).from_address(p)
+        a = np.frombuffer(buf, dtype=dt, count=count)
+        return a
+
+    n_ref = int(L.besst_bam_n_refs(ptr))
+    references = [L.besst_bam_ref_name(ptr, i).decode("ascii") for i in range(n_ref)]
+    lengths = [int(L.besst_bam_ref_length(ptr, i)) for i in range(n_ref)]
+    rlen = np.zeros(n, np.int32)
+    alen = np.zeros(n, np.int32)
+    rlen[:nh] = view(cols.rlen, nh, np.int32)
+    alen[:nh] = view(cols.alen, nh, np.int32)
+    batch = RecordBatch(tid=view(cols.tid, n, np.int32), mtid=view(cols.mtid, n, np.int32), pos=view(cols.pos, n, np.int32),
+                        mpos=view(cols.mpos, n, np.int32), tlen=view(cols.tlen, n, np.int32), qlen=view(cols.qlen, n, np.int32),
+                        flag=view(cols.flag, n, np.uint16), mapq=view(cols.mapq, n, np.uint8), references=references,
+                        lengths=lengths, rlen=rlen, alen=alen)
+    st = BamStats()
+    L.besst_bam_get_stats(ptr, C.byref(st))
+    batch.stats = {k: getattr(st, k) for k, _ in BamStats._fields_}
+    batch._owner = h
+    return batch
 
 _CORE = struct.Struct("<iiBBHHHiiii")   # refID pos l_read_name mapq bin n_cigar flag l_seq next_refID next_pos tlen
 

@@ -16,6 +16,23 @@ SOURCES = [("besst_api.cu", []), ("besst_links.cu", []), ("besst_sort.cu", []),
            ("besst_edges.cu", ["-fmad=false"]), ("besst_metrics.cu", [])]
 
 
+BAMIO_SO = os.path.join(HERE, "libbesst_bamio.so")
+
+
+def build_bamio(force=False):
+    """Host-only ingest library (g++, zlib, threads): BAM file -> record columns."""
+    src = os.path.join(CSRC, "besst_bamio.cpp")
+    hdr = os.path.join(HERE, "..", "include", "besst_bamio.h")
+    if force or _stale(BAMIO_SO, [src, hdr]):
+        cxx = os.environ.get("CXX", "g++")
+        cmd = [cxx, "-O3", "-std=c++17", "-shared", "-fPIC", "-pthread", "-Wall", "-Wextra", "-o", BAMIO_SO, src, "-lz"]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            sys.stderr.write(r.stdout + r.stderr)
+            raise RuntimeError("g++ failed on besst_bamio.cpp")
+    return BAMIO_SO
+
+
 def _stale(target, deps):
     if not os.path.exists(target):
         return True
@@ -50,6 +67,7 @@ def build(force=False, verbose=False):
             raise RuntimeError("link failed")
     with open(os.path.join(objdir, "ptxas.log"), "a") as fh:
         fh.write("".join(log))
+    build_bamio(force)
     return SO
 
 

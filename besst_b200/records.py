@@ -144,10 +144,13 @@ class BatchFile(object):
 
 
 def as_batch(bam_file):
-    """RecordBatch behind a `bam_file` argument: a RecordBatch, anything
-    carrying `.record_batch`, or a pysam-like iterable of AlignedRead."""
+    """RecordBatch behind a `bam_file` argument: a RecordBatch, a path to a BAM file (decoded by
+    libbesst_bamio.so), anything carrying `.record_batch`, or a pysam-like iterable of AlignedRead."""
     if isinstance(bam_file, RecordBatch):
         return bam_file
+    if isinstance(bam_file, (str, bytes)) or hasattr(bam_file, "__fspath__"):   # a path: native threaded ingest
+        from .bamio import read_bam_native
+        return read_bam_native(bam_file)
     batch = getattr(bam_file, "record_batch", None)
     if batch is not None:
         return batch

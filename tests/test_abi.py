@@ -35,6 +35,20 @@ def test_library_exports_every_declared_symbol():
     assert L.besst_abi_version() == abi.ABI_VERSION
 
 
+def test_bamio_library_exports_every_declared_symbol():
+    from besst_b200 import bamio, build
+    if not os.path.exists(bamio.BAMIO_SO):
+        build.build_bamio()
+    text = re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", "besst_bamio.h")).read(), flags=re.S)
+    names = sorted(set(re.findall(r"\b(besst_[a-z0-9_]+)\s*\(", text)))
+    L = C.CDLL(bamio.BAMIO_SO)
+    for name in names:
+        assert hasattr(L, name), "libbesst_bamio.so does not export %s" % name
+    assert sorted(bamio.BAMIO_EXPORTS) == names
+    L.besst_bamio_abi_version.restype = C.c_int
+    assert L.besst_bamio_abi_version() == 1
+
+
 def test_ctypes_structs_match_c_layout():
     src = r'''
 #include <stdio.h>

@@ -1,0 +1,108 @@
+"""CPU: the native BAM ingest (libbesst_bamio.so: threaded BGZF inflate + fixed-core decode) against the
+pure-Python reader, on BAM files written here (ragged CIGARs, soft/hard clips, SEQ '*', unmapped
+records, many small BGZF blocks, records straddling blocks and inflate windows) and, where the
+reference tree is present, on its own testdata."""
+import os
+import struct
+import zlib
+
+import numpy as np
+import pytest
+
+from besst_b200 import bamio
+
+REF_BAM = "/root/reference/testdata/testset1/mapped.bam"
+
+
+def _bgzf_block(data):
+    comp = zlib.compressobj(6, zlib.DEFLATED, -15)
+    c = comp.compress(data) + comp.flush()
+    bsize = 12 + 6 + len(c) + 8
+    hdr = b"\x1f\x8b\x08\x04" + b"\0\0\0\0" + b"\0\xff" + struct.pack("<H", 6) + b"BC" + struct.pack("<HH", 2, bsize - 1)
+    return hdr + c + struct.pack("<II", zlib.crc32(data) & 0xffffffff, len(data))
+
+
+def write_bam(path, refs, records, block_bytes=3000):
+    """records: dicts with tid, pos, mapq, flag, l_seq, mtid, mpos, tlen, cigar [(op, len)], name"""
+    text = b"@HD\tVN:1.0\tSO:coordinate\n"
+    raw = b"BAM\x01" + struct.pack("<i", len(text)) + text + struct.pack("<i", len(refs))
+    for name, ln in refs:
+        nm = name.encode() + b"\0"
+        raw += struct.pack("<i", len(nm)) + nm + struct.pack("<i", ln)
+    for r in records:
+        name = r.get("name", "q").encode() + b"\0"
+        cig = b"".join(struct.pack("<I", (ln << 4) | op) for op, ln in r["cigar"])
+        l_seq = r["l_seq"]
+        body = struct.pack("<iiBBHHHiiii", r["tid"], r["pos"], len(name), r["mapq"], 4680, len(r["cigar"]), r["flag"], l_seq,
+                           r["mtid"], r["mpos"], r["tlen"]) + name + cig + b"\x11" * ((l_seq + 1) // 2) + b"\x20" * l_seq
+        raw += struct.pack("<i", len(body)) + body
+    with open(path, "wb") as fh:
+        for o in range(0, len(raw), block_bytes):
+            fh.write(_bgzf_block(raw[o:o + block_bytes]))
+        fh.write(_bgzf_block(b""))   # EOF marker
+
+
+def _random_records(rng, n, n_refs):
+    ops_pool = [[(0, 100)], [(4, 7), (0, 93)], [(0, 60), (1, 3), (0, 37)], [(5, 4), (4, 5), (0, 80), (2, 6), (0, 10), (4, 1)],
+                [(0, 50), (3, 200), (0, 50)], [(4, 100)], [(7, 40), (8, 1), (7, 59)], []]
+    recs = []
+    for i in range(n):
+        cig = ops_pool[int(rng.integers(len(ops_pool)))]
+        l_seq = sum(ln for op, ln in cig if op in (0, 1, 4, 7, 8)) if cig else 100
+        if rng.random() < 0.05:
+            l_seq = 0   # SEQ '*'
+        recs.append(dict(tid=int(rng.integers(-1, n_refs)), pos=int(rng.integers(0, 50000)), mapq=int(rng.integers(0, 61)),
+                         flag=int(rng.integers(0, 4096)), l_seq=l_seq, mtid=int(rng.integers(-1, n_refs)),
+                         mpos=int(rng.integers(0, 50000)), tlen=int(rng.integers(-9000, 9000)), cigar=cig,
+                         name="read%d" % i if i % 7 else "r" * 200))
+    return recs
+
+
+def _assert_same(a, b, head=1000):
+    assert a.references == b.references and list(a.lengths) == list(b.lengths)
+    for f in ("tid", "mtid", "pos", "mpos", "tlen", "qlen", "flag", "mapq"):
+        assert np.array_equal(getattr(a, f), getattr(b, f)), f
+    assert np.array_equal(a.rlen[:head], b.rlen[:head]) and np.array_equal(a.alen[:head], b.alen[:head])
+
+
+@pytest.mark.parametrize("n,block_bytes,threads", [(0, 3000, 2), (1, 3000, 1), (5000, 700, 4), (5000, 65000, 3), (20000, 3000, 8)])
+def test_native_reader_equals_python_reader(tmp_path, n, block_bytes, threads):
+    rng = np.random.default_rng(n + block_bytes)
+    refs = [("c%d,pos:%d-%d,rc:0" % (i, i * 1000, i * 1000 + 900), 900 + i) for i in range(37)]
+    path = str(tmp_path / "t.bam")
+    write_bam(path, refs, _random_records(rng, n, len(refs)), block_bytes)
+    py = bamio.read_bam(path)
+    nat = bamio.read_bam_native(path, threads=threads)
+    assert len(nat) == n
+    _assert_same(nat, py)
+    assert nat.stats["records"] == n and nat.stats["blocks"] >= 1
+    if n > 100:
+        part = bamio.read_bam_native(path, threads=threads, max_records=100)
+        assert len(part) == 100 and np.array_equal(part.pos, py.pos[:100])
+
+
+def test_native_reader_rejects_garbage(tmp_path):
+    p = tmp_path / "x.bam"
+    p.write_bytes(b"this is not a BAM file, not even gzip" * 10)
+    with pytest.raises(IOError):
+        bamio.read_bam_native(str(p))
+    with pytest.raises(IOError):
+        bamio.read_bam_native(str(tmp_path / "missing.bam"))
+    # truncated in the middle of a block
+    refs = [("c0", 1000)]
+    good = tmp_path / "g.bam"
+    write_bam(str(good), refs, _random_records(np.random.default_rng(1), 500, 1), 3000)
+    data = good.read_bytes()
+    (tmp_path / "t.bam").write_bytes(data[:len(data) // 2])
+    with pytest.raises(IOError):
+        bamio.read_bam_native(str(tmp_path / "t.bam"))
+
+
+@pytest.mark.skipif(not os.path.exists(REF_BAM), reason="reference testdata not on this machine")
+def test_native_reader_on_reference_testset1():
+    py = bamio.read_bam(REF_BAM, max_records=300000)
+    nat = bamio.read_bam_native(REF_BAM, max_records=300000)
+    _assert_same(nat, py)
+    full = bamio.read_bam_native(REF_BAM)
+    assert len(full) == 1999958 and len(full.references) == 1836
+    assert int((full.tid != full.mtid).sum()) == 1356734

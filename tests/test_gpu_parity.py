@@ -222,6 +222,26 @@ def test_bucket_on_tuple_streams_without_bam_order(cuda_engine, order, monkeypat
     assert np.array_equal(ref.obs_sum, res["runs"].obs_sum) and np.array_equal(ref.obs_sq, res["runs"].obs_sq)
 
 
+def test_bam_file_to_graph_through_native_ingest(cuda_engine, tmp_path):
+    """BAM file -> libbesst_bamio.so (threaded inflate + decode) -> host columns -> graph build: equals the
+    oracle on the in-memory records the file was written from."""
+    from besst_b200 import bamio
+    from test_bamio import write_bam
+    lib, batch, params, table = _setup("tiny")
+    recs = []
+    for i in range(len(batch)):
+        q = int(batch.qlen[i])
+        recs.append(dict(tid=int(batch.tid[i]), pos=int(batch.pos[i]), mapq=int(batch.mapq[i]), flag=int(batch.flag[i]), l_seq=q,
+                         mtid=int(batch.mtid[i]), mpos=int(batch.mpos[i]), tlen=int(batch.tlen[i]), cigar=[(0, q)] if q else []))
+    path = str(tmp_path / "lib.bam")
+    write_bam(path, list(zip(batch.references, [int(x) for x in batch.lengths])), recs, block_bytes=20000)
+    nat = bamio.read_bam_native(path, threads=4)
+    assert len(nat) == len(batch) and nat.references == list(batch.references)
+    want, _, _, _ = oracle_lib.graph_build(table.rows, table.n_scaffolds, params, batch)
+    got = cuda_engine.graph_build(table, params, nat)
+    helpers.assert_graph_equal(got, want, label="bam ingest")
+
+
 def test_two_slices_with_halo_equal_one_pass(cuda_engine):
     """The multi-GPU decomposition on one GPU: records cut into BAM-order slices, each
     extracted with the previous slice's last CreateEdge observation as halo, tuples
