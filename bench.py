@@ -363,6 +363,7 @@ def run_ours(args):
             "device_ms_per_step": round(float(np.mean(dev_ms)), 4) if world == 1 else None,
             "wall_ms_per_step": round(1e3 * wall / args.steps, 4),
             "timing": "CUDA events on the launching stream (the library runs on torch's current stream), max over ranks",
+            "dist_phases_ms": ({k: round(v, 3) for k, v in runner.phase_ms.items()} if (runner is not None and runner.timing) else None),
             "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu_baseline, "parity": parity,
             "generate_s": round(t_gen, 2), "impl": "ours",
         }

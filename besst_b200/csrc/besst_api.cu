@@ -317,7 +317,14 @@ extern "C" int besst_runs_pack(besst_ctx* ctx, int32_t world, int32_t* out_obs_d
     if (!ctx || !ctx->have_runs) { if (ctx) ctx->err = "no grouped runs (besst_links_group)"; return BESST_E_STATE; }
     if (world < 1 || world > 16 || (ctx->n_runs > 0 && (!out_obs_device || !out_desc_device))) { ctx->err = "runs_pack: bad arguments"; return BESST_E_INVALID; }
     cudaSetDevice(ctx->device);
-    return besst_launch_runs_pack(ctx, world, out_obs_device, out_desc_device);
+    return besst_launch_runs_pack(ctx, world, out_obs_device, out_desc_device, nullptr, nullptr);
+}
+
+extern "C" int besst_runs_pack_peer(besst_ctx* ctx, int32_t world, int32_t* const* obs_ptrs, besst_run_desc* const* desc_ptrs) {
+    if (!ctx || !ctx->have_runs) { if (ctx) ctx->err = "no grouped runs (besst_links_group)"; return BESST_E_STATE; }
+    if (world < 1 || world > 16 || !obs_ptrs || !desc_ptrs) { ctx->err = "runs_pack_peer: bad arguments"; return BESST_E_INVALID; }
+    cudaSetDevice(ctx->device);
+    return besst_launch_runs_pack(ctx, world, nullptr, nullptr, obs_ptrs, desc_ptrs);
 }
 
 extern "C" int besst_runs_to_graph(besst_ctx* ctx, const besst_lib_params* params, const int32_t* obs_device, int64_t n_links,

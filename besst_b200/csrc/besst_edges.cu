@@ -1406,7 +1406,9 @@ int besst_group_tuples(besst_ctx* ctx, const besst_link_tuple* d_tuples, int64_t
 
 // ---- run-level multi-GPU exchange: route / pack on the sender, import on the receiver ------------------
 constexpr int RX_MAX_WORLD = 16;
-struct RouteBases { u32 link_base[RX_MAX_WORLD]; u32 run_base[RX_MAX_WORLD]; };
+// where this rank's segment starts inside every destination's observation / descriptor buffer: local
+// addresses (NCCL all-to-all afterwards) or peer-mapped addresses of the destination GPU (NVLink stores)
+struct PackDst { int2* obs[RX_MAX_WORLD]; besst_run_desc* desc[RX_MAX_WORLD]; };
 
 // state: [0..15] links per destination, [16..31] runs per destination
 __global__ void __launch_bounds__(256) k_runs_route_count(const u64* __restrict__ run_key, const u32* __restrict__ run_cnt, long long R,
@@ -1432,8 +1434,7 @@ __global__ void __launch_bounds__(256) k_runs_route_count(const u64* __restrict_
 __global__ void __launch_bounds__(256) k_runs_pack(const u64* __restrict__ run_key, const u32* __restrict__ run_start,
                                                    const u32* __restrict__ run_cnt, const u32* __restrict__ run_first, long long R,
                                                    int block_bits, int bv, int world, const int2* __restrict__ grouped,
-                                                   const RouteBases B, u32* cursors, int2* __restrict__ out_obs,
-                                                   besst_run_desc* __restrict__ out_desc) {
+                                                   const PackDst D, u32* cursors) {
     const int lane = threadIdx.x & 31;
     const long long warp_global = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const long long n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
@@ -1446,13 +1447,13 @@ __global__ void __launch_bounds__(256) k_runs_pack(const u64* __restrict__ run_k
         u32 a = 0, slot = 0;
         if (lane == 0) { a = atomicAdd(cursors + d, cnt); slot = atomicAdd(cursors + RX_MAX_WORLD + d, 1u); }
         a = __shfl_sync(0xffffffffu, a, 0);
-        int2* dst = out_obs + B.link_base[d] + a;
+        int2* dst = D.obs[d] + a;
         for (u32 k = lane; k < cnt; k += 32) dst[k] = __ldg(grouped + src + k);
         if (lane == 0) {
             besst_run_desc ds;
             ds.u = u; ds.v = v; ds.count = cnt; ds.first = __ldg(run_first + r); ds.offset = a;
             ds.block = (u32)(word & ((1ull << block_bits) - 1ull));
-            out_desc[B.run_base[d] + slot] = ds;
+            D.desc[d][slot] = ds;
         }
     }
 }
@@ -1493,27 +1494,36 @@ int besst_launch_runs_route(besst_ctx* ctx, int world, int64_t* link_counts, int
     return BESST_OK;
 }
 
-int besst_launch_runs_pack(besst_ctx* ctx, int world, int32_t* out_obs, besst_run_desc* out_desc) {
+// obs_ptrs / desc_ptrs == nullptr: one local destination-major buffer pair (out_obs, out_desc)
+int besst_launch_runs_pack(besst_ctx* ctx, int world, int32_t* out_obs, besst_run_desc* out_desc, int32_t* const* obs_ptrs,
+                           besst_run_desc* const* desc_ptrs) {
     const int64_t R = ctx->n_runs;
     if (R == 0) return BESST_OK;
     const int bv = bits_for((uint64_t)(2 * ctx->n_scaffolds > 0 ? 2 * ctx->n_scaffolds - 1 : 1));
     u32* state = ctx->run_state.as<u32>() + 16;
-    u32 h[2 * RX_MAX_WORLD];
-    BESST_CUDA_TRY(ctx, cudaMemcpyAsync(h, state, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
-    BESST_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-    RouteBases B;
-    u32 lb = 0, rb = 0;
-    for (int d = 0; d < RX_MAX_WORLD; ++d) {
-        B.link_base[d] = lb; B.run_base[d] = rb;
-        if (d < world) { lb += h[d]; rb += h[RX_MAX_WORLD + d]; }
+    PackDst D;
+    if (obs_ptrs) {
+        for (int d = 0; d < RX_MAX_WORLD; ++d) {
+            D.obs[d] = d < world ? reinterpret_cast<int2*>(obs_ptrs[d]) : nullptr;
+            D.desc[d] = d < world ? desc_ptrs[d] : nullptr;
+        }
+    } else {
+        u32 h[2 * RX_MAX_WORLD];
+        BESST_CUDA_TRY(ctx, cudaMemcpyAsync(h, state, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+        BESST_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+        u32 lb = 0, rb = 0;
+        for (int d = 0; d < RX_MAX_WORLD; ++d) {
+            D.obs[d] = reinterpret_cast<int2*>(out_obs) + lb; D.desc[d] = out_desc + rb;
+            if (d < world) { lb += h[d]; rb += h[RX_MAX_WORLD + d]; }
+        }
     }
     u32* cursors = state + 2 * RX_MAX_WORLD;
     long long grid = (R * 32 + 255) / 256;
     if (grid > (long long)ctx->sm_count * 16) grid = (long long)ctx->sm_count * 16;
     { KTimer kt(ctx, BESST_K_PARTITION);
       k_runs_pack<<<(unsigned)grid, 256, 0, ctx->stream>>>(ctx->run_key[0].as<u64>(), ctx->run_start.as<u32>(), ctx->run_cnt.as<u32>(),
-                                                           ctx->run_first.as<u32>(), R, ctx->run_block_bits, bv, world, ctx->grouped.as<int2>(), B,
-                                                           cursors, reinterpret_cast<int2*>(out_obs), out_desc); }
+                                                           ctx->run_first.as<u32>(), R, ctx->run_block_bits, bv, world, ctx->grouped.as<int2>(), D,
+                                                           cursors); }
     BESST_CUDA_TRY(ctx, cudaGetLastError());
     return BESST_OK;
 }

@@ -32,6 +32,10 @@ from . import abi
 NO_MATCH = -(2 ** 31) + 1   # halo value no observation pair can equal
 
 
+class _SymmUnavailable(RuntimeError):
+    pass
+
+
 def _copy_params(params, halo):
     p = abi.LibParams()
     C.memmove(C.byref(p), C.byref(params), C.sizeof(abi.LibParams))
@@ -64,6 +68,7 @@ class CudaBackend(object):
         self.engine = engine
         self.device = device
         self._bufs = {}
+        self._symm = {}
 
     def _buf(self, name, n, dtype):
         t = self._bufs.get(name)
@@ -131,6 +136,23 @@ class CudaBackend(object):
                                          block_bits, src_runs, src_links, src_first,
                                          recv_f.data_ptr() if recv_f.numel() else None, recv_f.shape[0])
 
+    # peer-mapped receive buffers (torch symmetric memory over NVLink) for the fused pack + exchange
+    def symm_buffer(self, name, n_elems, dtype, group):
+        """A symmetric buffer of at least n_elems (every rank passes the same n_elems: the allocation and
+        the rendezvous are collective).  -> (local tensor, handle with .buffer_ptrs / .barrier / .get_buffer)"""
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as sm
+        cur = self._symm.get(name)
+        if cur is None or cur[0].numel() < n_elems or cur[0].dtype != dtype:
+            cap = int(n_elems * 1.25) + 4096
+            t = sm.empty(cap, dtype=dtype, device=self.device)
+            h = sm.rendezvous(t, group=group if group is not None else dist.group.WORLD)
+            self._symm[name] = (t, h)
+        return self._symm[name]
+
+    def pack_peer(self, world, obs_ptrs, desc_ptrs):
+        self.engine.runs_pack_peer(world, obs_ptrs, desc_ptrs)
+
     def recv_buffers(self, n_tuples, n_fishy):
         torch = self.torch
         return (self._buf("recv_t", 4 * n_tuples, torch.int32)[:4 * n_tuples].view(-1, 4),
@@ -149,6 +171,9 @@ class CudaBackend(object):
 
     def counts_tensor(self, values):
         return self.torch.tensor(values, dtype=self.torch.int64, device=self.device)
+
+    def synchronize(self):
+        self.torch.cuda.synchronize(self.device)
 
     def fetch(self, sizes, view=False):
         return self.engine.fetch_view(sizes) if view else self.engine.fetch(sizes)
@@ -175,7 +200,25 @@ class DistributedGraphBuild(object):
         self.last = None
         # BESST_DIST_EXCHANGE=tuples forces the tuple-level exchange (A/B, tests); default: runs
         import os
-        self.exchange_runs = os.environ.get("BESST_DIST_EXCHANGE", "runs") != "tuples"
+        mode = os.environ.get("BESST_DIST_EXCHANGE", "peer")   # peer | runs | tuples
+        self.exchange_runs = mode != "tuples"
+        self.exchange_peer = mode == "peer" and hasattr(backend, "symm_buffer") and world > 1
+        # BESST_DIST_TIMING=1: device-synchronised wall time per phase of the last step in self.phase_ms (diagnostics)
+        self.timing = os.environ.get("BESST_DIST_TIMING", "0") == "1"
+        self.phase_ms = {}
+        self._t_last = None
+
+    def _mark(self, name):
+        if not self.timing:
+            return
+        import time
+        sync = getattr(self.b, "synchronize", None)
+        if sync:
+            sync()
+        t = time.perf_counter()
+        if self._t_last is not None and name:
+            self.phase_ms[name] = self.phase_ms.get(name, 0.0) + 1e3 * (t - self._t_last)
+        self._t_last = t
 
     # -- step 1: the last CreateEdge call of all preceding ranks --------------------------------
     def halo(self, params, rec):
@@ -194,11 +237,26 @@ class DistributedGraphBuild(object):
         """One distributed graph build.  Leaves this rank's share of the CSR in its HBM;
         returns the local sizes.  `self.last` keeps what fetch_local needs."""
         dist, world = self.dist, self.world
+        self.phase_ms = {}
+        self._t_last = None
+        self._mark(None)
         halo = self.halo(params, rec) if world > 1 else (params.halo_prev_obs1, params.halo_prev_obs2)
+        self._mark("halo")
         p = _copy_params(params, halo)
         n_local = self.b.extract(p, rec)
+        self._mark("extract")
         if self.exchange_runs and hasattr(self.b, "group"):
-            sizes = self._step_runs(p, n_local)
+            sizes = None
+            if self.exchange_peer:
+                try:
+                    sizes = self._step_runs_peer(p, n_local)
+                except _SymmUnavailable as exc:   # no peer mapping on this box: every rank raises alike (collective setup)
+                    import warnings
+                    warnings.warn("symmetric memory unavailable (%s): NCCL all-to-all instead" % exc)
+                    self.exchange_peer = False
+                    sizes = self._step_runs(p, n_local, regroup=False)
+            else:
+                sizes = self._step_runs(p, n_local)
             if sizes is not None:
                 return sizes
         send_t, send_o, send_f, tc, fc = self.b.partition(world)
@@ -229,18 +287,86 @@ class DistributedGraphBuild(object):
                          halo=halo)
         return sizes
 
-    def _step_runs(self, p, n_local):
+    def _step_runs_peer(self, p, n_local):
+        """Run-level exchange with the all-to-all FUSED into the pack kernel: every rank owns peer-mapped
+        receive buffers (symmetric memory); k_runs_pack stores each run straight into its destination GPU
+        over NVLink, bracketed by two cross-GPU barriers.  One all_gather of the segment sizes is the only
+        host-visible collective.  None: some rank's stream has no local order (tuple-level path)."""
+        dist, world, rank = self.dist, self.world, self.rank
+        torch = self.b.torch
+        n_runs = self.b.group()
+        self._mark("group")
+        ok = n_runs is not None
+        if ok:
+            lc, rc = self.b.route(world)
+        else:
+            lc, rc = np.zeros(world, np.int64), np.zeros(world, np.int64)
+        send_f, fc = self.b.partition_fishy(world)
+        self._mark("route+fishy")
+        mine = self.b.counts_tensor([1 if ok else 0, n_local] + lc.tolist() + rc.tolist() + fc.tolist())
+        gathered = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(gathered, mine, group=self.group)
+        M = np.asarray(torch.stack(gathered).tolist(), dtype=np.int64)
+        self._mark("meta")
+        if int(M[:, 0].min()) == 0:
+            return None
+        n_by_rank = M[:, 1]
+        LC, RC, FC = M[:, 2:2 + world], M[:, 2 + world:2 + 2 * world], M[:, 2 + 2 * world:2 + 3 * world]
+        if int(n_by_rank.sum()) >= 2 ** 32 or int(LC.sum(axis=0).max()) >= 2 ** 30:
+            raise ValueError("run-level exchange: more than 2^32 links in the library or 2^30 on one rank")
+        try:
+            obs_t, obs_h = self.b.symm_buffer("obs", 2 * int(LC.sum(axis=0).max()) + 2, torch.int32, self.group)
+            desc_t, desc_h = self.b.symm_buffer("desc", 6 * int(RC.sum(axis=0).max()) + 6, torch.int32, self.group)
+            f_t, f_h = self.b.symm_buffer("fishy", int(FC.sum(axis=0).max()) + 1, torch.int64, self.group)
+        except Exception as exc:
+            raise _SymmUnavailable(repr(exc))
+        link_off = LC[:rank].sum(axis=0)   # my segment's start inside every destination's buffers
+        run_off = RC[:rank].sum(axis=0)
+        f_off = FC[:rank].sum(axis=0)
+        obs_ptrs = [int(obs_h.buffer_ptrs[d]) + 8 * int(link_off[d]) for d in range(world)]
+        desc_ptrs = [int(desc_h.buffer_ptrs[d]) + 24 * int(run_off[d]) for d in range(world)]
+        obs_h.barrier(channel=0)   # every rank is done reading the buffers of the previous step
+        self.b.pack_peer(world, obs_ptrs, desc_ptrs)
+        fstart = np.concatenate([[0], np.cumsum(fc)])
+        for d in range(world):
+            if fc[d]:
+                f_h.get_buffer(d, (int(fc[d]),), torch.int64, int(f_off[d])).copy_(send_f[int(fstart[d]):int(fstart[d + 1])])
+        obs_h.barrier(channel=0)   # all stores have landed
+        self._mark("pack+exchange")
+        rl, rr, rf = LC[:, rank], RC[:, rank], FC[:, rank]
+        recv_obs = obs_t[:2 * int(rl.sum())].view(-1, 2)
+        recv_desc = desc_t[:6 * int(rr.sum())].view(-1, 6)
+        recv_f = f_t[:int(rf.sum())]
+        max_blocks = int(((n_by_rank + abi.RUN_BLOCK - 1) // abi.RUN_BLOCK).max())
+        block_bits = max(1, int(max(max_blocks - 1, 1)).bit_length())
+        first_base = np.concatenate([[0], np.cumsum(n_by_rank)[:-1]])
+        sizes = self.b.runs_to_graph(p, recv_obs, recv_desc, world, block_bits, rr, rl, first_base, recv_f)
+        self._mark("runs_to_graph")
+        aligned, counters = self.b.partial_tensors()
+        last = counters[abi.CNT_LAST_OBS1:abi.CNT_LAST_OBS2 + 1].clone()
+        counters[abi.CNT_LAST_OBS1:] = 0
+        dist.all_reduce(aligned, op=dist.ReduceOp.SUM, group=self.group)
+        dist.all_reduce(counters, op=dist.ReduceOp.SUM, group=self.group)
+        self._mark("all_reduce")
+        self.last = dict(sizes=sizes, global_first=True, n_tuples_by_rank=n_by_rank.tolist(), aligned=aligned, counters=counters,
+                         last_local=last, halo=(p.halo_prev_obs1, p.halo_prev_obs2))
+        return sizes
+
+    def _step_runs(self, p, n_local, regroup=True):
         """Run-level exchange: whole runs (block-grouped links of one edge) are routed by edge hash; 8 bytes
         per link + 24 per run cross NVLink and the receiver starts at the run merge.  None: some rank's
         stream has no local order -- every rank takes the tuple-level path."""
         dist, world = self.dist, self.world
-        n_runs = self.b.group()
+        n_runs = self.b.group() if regroup else 0
+        self._mark("group")
         ok = self.b.counts_tensor([1 if n_runs is not None else 0])
         dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=self.group)
         if int(ok.item()) == 0:
             return None
+        self._mark("agree")
         lc, rc = self.b.route(world)
         send_f, fc = self.b.partition_fishy(world)
+        self._mark("route+fishy")
         # one small all_to_all: what every destination gets from me (links, runs, fishy keys) + my link count
         meta_out = self.b.counts_tensor(np.stack([lc, rc, fc, np.full(world, n_local)], axis=1).reshape(-1).tolist())
         meta_in = self.b.counts_tensor([0] * (4 * world))
@@ -249,20 +375,25 @@ class DistributedGraphBuild(object):
         rl, rr, rf, n_by_rank = mi[:, 0], mi[:, 1], mi[:, 2], mi[:, 3]
         if int(n_by_rank.sum()) >= 2 ** 32 or int(rl.sum()) >= 2 ** 30:
             raise ValueError("run-level exchange: more than 2^32 links in the library or 2^30 on one rank")
+        self._mark("meta")
         send_obs, send_desc = self.b.pack(world, int(lc.sum()), int(rc.sum()))
         recv_obs, recv_desc, recv_f = self.b.recv_run_buffers(int(rl.sum()), int(rr.sum()), int(rf.sum()))
+        self._mark("pack")
         dist.all_to_all_single(recv_obs, send_obs, output_split_sizes=rl.tolist(), input_split_sizes=lc.tolist(), group=self.group)
         dist.all_to_all_single(recv_desc, send_desc, output_split_sizes=rr.tolist(), input_split_sizes=rc.tolist(), group=self.group)
         dist.all_to_all_single(recv_f, send_f, output_split_sizes=rf.tolist(), input_split_sizes=fc.tolist(), group=self.group)
+        self._mark("all_to_all")
         max_blocks = int(((n_by_rank + abi.RUN_BLOCK - 1) // abi.RUN_BLOCK).max())
         block_bits = max(1, int(max(max_blocks - 1, 1)).bit_length())
         first_base = np.concatenate([[0], np.cumsum(n_by_rank)[:-1]])
         sizes = self.b.runs_to_graph(p, recv_obs, recv_desc, world, block_bits, rr, rl, first_base, recv_f)
+        self._mark("runs_to_graph")
         aligned, counters = self.b.partial_tensors()
         last = counters[abi.CNT_LAST_OBS1:abi.CNT_LAST_OBS2 + 1].clone()
         counters[abi.CNT_LAST_OBS1:] = 0
         dist.all_reduce(aligned, op=dist.ReduceOp.SUM, group=self.group)
         dist.all_reduce(counters, op=dist.ReduceOp.SUM, group=self.group)
+        self._mark("all_reduce")
         self.last = dict(sizes=sizes, global_first=True, n_tuples_by_rank=n_by_rank.tolist(), aligned=aligned, counters=counters,
                          last_local=last, halo=(p.halo_prev_obs1, p.halo_prev_obs2))
         return sizes

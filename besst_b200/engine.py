@@ -150,6 +150,12 @@ class CudaEngine(object):
     def runs_pack(self, world, out_obs_ptr, out_desc_ptr):
         self._check(self._L.besst_runs_pack(self._ctx, int(world), out_obs_ptr, out_desc_ptr), "besst_runs_pack")
 
+    def runs_pack_peer(self, world, obs_ptrs, desc_ptrs):
+        """obs_ptrs[d] / desc_ptrs[d]: device addresses (ints) of this rank's segment in destination d's buffers."""
+        a = (C.c_void_p * world)(*[int(p) for p in obs_ptrs])
+        b = (C.c_void_p * world)(*[int(p) for p in desc_ptrs])
+        self._check(self._L.besst_runs_pack_peer(self._ctx, int(world), a, b), "besst_runs_pack_peer")
+
     def runs_to_graph(self, params, obs_ptr, n_links, desc_ptr, n_runs, world, block_bits, src_run_counts, src_link_counts,
                       src_first_base, fishy_ptr, n_fishy):
         sizes = abi.GraphSizes()

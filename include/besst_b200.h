@@ -261,6 +261,11 @@ int besst_runs_route(besst_ctx* ctx, int32_t world, int64_t* link_counts, int64_
 /* fill caller-provided DEVICE buffers, destination-major: out_obs = (obs_u, obs_v) int32 pairs of
  * sum(link_counts) links, out_desc = sum(run_counts) descriptors */
 int besst_runs_pack(besst_ctx* ctx, int32_t world, int32_t* out_obs_device, besst_run_desc* out_desc_device);
+/* the same, fused with the exchange: obs_ptrs[d] / desc_ptrs[d] (host arrays of `world` DEVICE pointers) address
+ * the start of this rank's segment inside destination d's receive buffers -- peer-mapped memory of GPU d
+ * (CUDA IPC / symmetric memory over NVLink).  The kernel's stores ARE the all-to-all; the caller brackets
+ * it with a cross-GPU barrier on each side. */
+int besst_runs_pack_peer(besst_ctx* ctx, int32_t world, int32_t* const* obs_ptrs, besst_run_desc* const* desc_ptrs);
 /* build this rank's share of the graph from the runs received from all sources (source-major device
  * buffers).  src_*_counts[world]: what each source sent here; src_first_base[world]: number of accepted
  * links on all ranks before the source (first_idx becomes a GLOBAL ordinal); block_bits: bits of the

@@ -1,25 +1,29 @@
 #!/bin/bash
-# N-GPU check: NCCL paths (run-level and tuple-level exchange) against the oracle, then the bench at N ranks
+# N-GPU check: the three exchange modes (peer stores fused into the pack kernel / NCCL all-to-all of runs /
+# NCCL all-to-all of tuples) against the oracle, then the bench at N ranks.  usage: gpu_multi.sh N tag [compare]
 N=${1:-2}; TAG=${2:-multi$N}
 OUT=gpurun_out/$TAG
 mkdir -p $OUT
 nvidia-smi -L > $OUT/smi.txt
 run() { timeout -s KILL 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port $1 "${@:2}"; }
-run 29511 tests/dist_check.py > $OUT/dist_check_runs.log 2>&1; grep -E "DIST_CHECK_OK|Error|error" $OUT/dist_check_runs.log | tail -3
-run 29512 tests/dist_check.py small_mp > $OUT/dist_check_runs2.log 2>&1; grep -E "DIST_CHECK_OK|Error|error" $OUT/dist_check_runs2.log | tail -3
-BESST_DIST_EXCHANGE=tuples run 29513 tests/dist_check.py > $OUT/dist_check_tuples.log 2>&1; grep -E "DIST_CHECK_OK|Error|error" $OUT/dist_check_tuples.log | tail -3
-run 29514 bench.py --gpus $N --steps 5 --warmup 3 > $OUT/bench_n$N.json 2> $OUT/bench_n$N.err
-python - <<PY
+PORT=29540
+for mode in peer runs tuples; do
+  for cfg in small_mp_cont small_mp; do
+    PORT=$((PORT+1))
+    BESST_DIST_EXCHANGE=$mode run $PORT tests/dist_check.py $cfg > $OUT/dist_check_${mode}_$cfg.log 2>&1
+    echo "$mode $cfg: $(grep -E 'DIST_CHECK_OK|Error|error|unavailable' $OUT/dist_check_${mode}_$cfg.log | tail -2)"
+  done
+done
+show() { python - <<PY
 import json
 try:
-    d=json.load(open("$OUT/bench_n$N.json"))
-    print("N=%d ms/step"%d["n_gpus"], d["ms_per_step"], "value %.4g"%d["value"], "wall", d["wall_ms_per_step"], "e2e", d["e2e"])
-    for k,v in d["kernels"].items(): print("   %-20s %8.4f ms  x%-4g"%(k, v["ms_per_step"], v["launches_per_step"]))
+    d=json.loads([l for l in open("$1") if l.startswith("{")][-1])
+    print("$2 N=%d ms/step"%d["n_gpus"], d["ms_per_step"], "value %.4g"%d["value"], "e2e", d["e2e"], "phases", d.get("dist_phases_ms"))
 except Exception as e:
-    print("bench failed", e); print(open("$OUT/bench_n$N.err").read()[-3000:])
+    print("bench failed", e); print(open("$1".replace(".json",".err")).read()[-3000:])
 PY
-if [ "$3" == "tuples" ]; then
-BESST_DIST_EXCHANGE=tuples run 29515 bench.py --gpus $N --steps 5 --warmup 3 --no-e2e > $OUT/bench_tuples_n$N.json 2> $OUT/bench_tuples_n$N.err
-python -c "
-import json; d=json.load(open('$OUT/bench_tuples_n$N.json')); print('tuple exchange: ms/step', d['ms_per_step'], 'value %.4g'%d['value'])"
+}
+run 29560 bench.py --gpus $N --steps 5 --warmup 3 > $OUT/bench_n$N.json 2> $OUT/bench_n$N.err; show $OUT/bench_n$N.json peer
+if [ "$3" == "compare" ]; then
+BESST_DIST_EXCHANGE=runs run 29561 bench.py --gpus $N --steps 5 --warmup 3 > $OUT/bench_runs_n$N.json 2> $OUT/bench_runs_n$N.err; show $OUT/bench_runs_n$N.json runs
 fi
