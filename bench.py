@@ -207,6 +207,7 @@ def run_ours(args):
     ev1.record()
     barrier()
     t1 = time.perf_counter()
+    launches_timed = eng.kernel_launches() - launches_warm   # kernels of this library inside the timed region
     # nvidia-smi samples every 100 ms and the timed region lasts a few tens of ms: keep the same load running
     # (untimed) until there are enough clock samples under load
     t_load = time.perf_counter()
@@ -218,7 +219,6 @@ def run_ours(args):
             step()
     torch.cuda.synchronize()
     clocks = sampler.finish()
-    launches_timed = eng.kernel_launches() - launches_warm
     wall = t1 - t0
     elapsed = ev0.elapsed_time(ev1) * 1e-3    # device time on the launching stream
     if world > 1:
@@ -252,6 +252,14 @@ def run_ours(args):
         "k_gapest": 64 * n_edges,
         "k_heads": 8 * n_links,
     }
+    traffic = {}
+    try:   # DRAM bytes per launch from the committed ncu capture of this workload (profiles/ncu_traffic.json)
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as fh:
+            tj = json.load(fh)
+        if tj.get("workload") == args.workload and args.scale == 1.0:
+            traffic = tj
+    except Exception:
+        pass
     dominant = max(per_step, key=per_step.get) if per_step else None
     peak, peak_src = measured_peak_gbs()
     roofline = None
@@ -259,7 +267,7 @@ def run_ours(args):
         avg_ms = per_step[dominant] / max(n_launch[dominant], 1)
         ach = alg_bytes.get(dominant, 0) / (avg_ms * 1e-3) / 1e9 if avg_ms > 0 else 0.0
         roofline = {"bound": "hbm", "kernel": dominant, "achieved": round(ach, 1), "peak": peak, "unit": "GB/s",
-                    "frac": round(ach / peak, 4), "traffic": None, "peak_source": peak_src,
+                    "frac": round(ach / peak, 4), "traffic": traffic.get(dominant), "peak_source": peak_src,
                     "avg_launch_ms": round(avg_ms, 4), "launches_per_step": n_launch[dominant],
                     "algorithmic_bytes_per_launch": int(alg_bytes.get(dominant, 0)),
                     "share_of_step": round(per_step[dominant] / max(sum(per_step.values()), 1e-9), 3)}

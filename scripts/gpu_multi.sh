@@ -7,7 +7,7 @@ mkdir -p $OUT
 nvidia-smi -L > $OUT/smi.txt
 run() { timeout -s KILL 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port $1 "${@:2}"; }
 PORT=29540
-for mode in peer runs tuples; do
+for mode in ${MODES:-peer runs tuples}; do
   for cfg in small_mp_cont small_mp; do
     PORT=$((PORT+1))
     BESST_DIST_EXCHANGE=$mode run $PORT tests/dist_check.py $cfg > $OUT/dist_check_${mode}_$cfg.log 2>&1

@@ -17,6 +17,6 @@ tail -c 3000 $OUT/bench.json
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv \
     --log-file $OUT/launches.csv python bench.py --steps 2 --warmup 1 --no-cpu > $OUT/ncu_launches.log 2>&1
 timeout 900 ncu --set full --clock-control none --import-source on \
-    -k regex:'k_extract_links|k_radix_sweep|k_edge_reduce|k_ks_eval' -c 12 -f -o $OUT/prof \
+    -k regex:'k_extract_links|k_group_blocks|k_ks_block|k_edge_gather|k_run_write|k_tile_offsets|k_tile_reduce' -c 8 -f -o $OUT/prof \
     python bench.py --steps 1 --warmup 0 --no-cpu --no-e2e > $OUT/ncu_full.log 2>&1
 ls -la $OUT
