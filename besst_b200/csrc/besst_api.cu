@@ -393,6 +393,31 @@ extern "C" int besst_trsk_sd_batch(besst_ctx* ctx, const besst_lib_params* param
     return BESST_OK;
 }
 
+extern "C" int besst_gapest_func_batch(besst_ctx* ctx, const besst_lib_params* params, const double* d, const int32_t* len1,
+                                       const int32_t* len2, int64_t n, double* func_out) {
+    if (!ctx) return BESST_E_INVALID;
+    int rc = check_params(ctx, params);
+    if (rc) return rc;
+    if (n < 0 || (n > 0 && (!d || !len1 || !len2 || !func_out))) { ctx->err = "gapest_func_batch: bad arguments"; return BESST_E_INVALID; }
+    if (n == 0) return BESST_OK;
+    cudaSetDevice(ctx->device);
+    const size_t nn = (size_t)n;
+    BESST_CUDA_TRY(ctx, ctx->misc.ensure(nn * (8 + 8 + 4 + 4) + 64));
+    unsigned char* base = ctx->misc.as<unsigned char>();
+    double* d_d = reinterpret_cast<double*>(base);
+    double* d_out = reinterpret_cast<double*>(base + 8 * nn);
+    int32_t* d_l1 = reinterpret_cast<int32_t*>(base + 16 * nn);
+    int32_t* d_l2 = d_l1 + nn;
+    BESST_CUDA_TRY(ctx, cudaMemcpyAsync(d_d, d, 8 * nn, cudaMemcpyHostToDevice, ctx->stream));
+    BESST_CUDA_TRY(ctx, cudaMemcpyAsync(d_l1, len1, 4 * nn, cudaMemcpyHostToDevice, ctx->stream));
+    BESST_CUDA_TRY(ctx, cudaMemcpyAsync(d_l2, len2, 4 * nn, cudaMemcpyHostToDevice, ctx->stream));
+    rc = besst_launch_func_of_d(ctx, *params, d_d, d_l1, d_l2, n, d_out);
+    if (rc) return rc;
+    BESST_CUDA_TRY(ctx, cudaMemcpyAsync(func_out, d_out, 8 * nn, cudaMemcpyDeviceToHost, ctx->stream));
+    BESST_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return BESST_OK;
+}
+
 extern "C" int besst_links_to_graph(besst_ctx* ctx, const besst_lib_params* params, const besst_link_tuple* tuples_device,
                                     int64_t n_tuples, const uint64_t* fishy_keys_device, int64_t n_fishy_keys,
                                     besst_graph_sizes* sizes) {

@@ -1310,6 +1310,21 @@ __global__ void __launch_bounds__(128)
     if (active && (threadIdx.x & 3) == 0) sd_out[quad] = sd;
 }
 
+// d + sigma^2 g'(d)/g(d) -- the left-hand side of the ML equation (funcDGeneral) -- for a batch of d:
+// what mathstats' PreCalcMLvaluesOfdLongContigs tabulates (MakeScaffolds.py:68)
+__global__ void __launch_bounds__(128)
+    k_func_of_d_batch(const ScoreConsts c, const double* __restrict__ d_in, const int* __restrict__ len1,
+                      const int* __restrict__ len2, long long n, double* out) {
+    const long long quad = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 2;
+    const bool active = quad < n;
+    const double d = active ? d_in[quad] : 0.0;
+    const double l1 = active ? (double)len1[quad] : 1.0, l2 = active ? (double)len2[quad] : 1.0;
+    const double c_min = l1 < l2 ? l1 : l2, c_max = l1 < l2 ? l2 : l1;
+    const GTerms t = g_terms_quad(d, c, c_min, c_max);
+    const double aofd = t.gp / t.g;
+    if (active && (threadIdx.x & 3) == 0) out[quad] = d + aofd * c.sd2;
+}
+
 int bits_for(uint64_t max_value) {
     int b = 1;
     while (b < 32 && (max_value >> b)) ++b;
@@ -1339,6 +1354,16 @@ int besst_launch_gapest(besst_ctx* ctx, const besst_lib_params& p, const double*
     const long long threads = n * 4;
     const int grid = (int)((threads + 127) / 128);
     { KTimer kt(ctx, BESST_K_GAPEST); k_gapest_batch<<<grid, 128, 0, ctx->stream>>>(c, d_mean_obs, d_len1, d_len2, n, d_gap, d_sd); }
+    BESST_CUDA_TRY(ctx, cudaGetLastError());
+    return BESST_OK;
+}
+
+int besst_launch_func_of_d(besst_ctx* ctx, const besst_lib_params& p, const double* d_d, const int32_t* d_len1,
+                           const int32_t* d_len2, int64_t n, double* d_out) {
+    if (n == 0) return BESST_OK;
+    const ScoreConsts c = besst_score_consts(p);
+    const int grid = (int)((n * 4 + 127) / 128);
+    { KTimer kt(ctx, BESST_K_GAPEST); k_func_of_d_batch<<<grid, 128, 0, ctx->stream>>>(c, d_d, d_len1, d_len2, n, d_out); }
     BESST_CUDA_TRY(ctx, cudaGetLastError());
     return BESST_OK;
 }

@@ -209,6 +209,15 @@ class CudaEngine(object):
                     "besst_gapest_batch")
         return gap, sd
 
+    def func_of_d_batch(self, params, d, len1, len2):
+        d = np.ascontiguousarray(d, dtype=np.float64)
+        len1 = np.ascontiguousarray(len1, dtype=np.int32)
+        len2 = np.ascontiguousarray(len2, dtype=np.int32)
+        out = np.zeros(d.shape[0], dtype=np.float64)
+        self._check(self._L.besst_gapest_func_batch(self._ctx, C.byref(params), d.ctypes.data, len1.ctypes.data,
+                                                    len2.ctypes.data, d.shape[0], out.ctypes.data), "besst_gapest_func_batch")
+        return out
+
     def trsk_sd_batch(self, params, gap, len1, len2):
         gap = np.ascontiguousarray(gap, dtype=np.float64)
         len1 = np.ascontiguousarray(len1, dtype=np.int32)

@@ -55,3 +55,38 @@ def tr_sk_std_dev_batch(mean, sigma, read_len, c1_len, c2_len, gap, engine=None,
 
 def tr_sk_std_dev(mean, stdDev, readLen, c1Len, c2Len, d, engine=None):
     return float(tr_sk_std_dev_batch(mean, stdDev, readLen, [c1Len], [c2Len], [d], engine=engine)[0])
+
+
+def func_of_d_batch(mean, sigma, read_len, d, c1_len, c2_len, engine=None, erf_variant=abi.ERF_AS7126):
+    """d + sigma^2 g'(d)/g(d) (mathstats funcDGeneral) for arrays of d and contig lengths."""
+    d = np.atleast_1d(np.asarray(d, dtype=np.float64))
+    c1 = np.broadcast_to(np.asarray(c1_len), d.shape)
+    c2 = np.broadcast_to(np.asarray(c2_len), d.shape)
+    return _engine(engine).func_of_d_batch(_params(mean, sigma, read_len, erf_variant), d, c1, c2)
+
+
+def PreCalcMLvaluesOfdLongContigs(mean, stdDev, readLen, engine=None):
+    """Drop-in for mathstats' table {rounded left-hand side of the ML equation: gap d} for two long contigs
+    (c1 = c2 = mean + 4 stdDev), built once per library by MakeScaffolds.py:68 and looked up in UpdateInfo.
+    All d in [int(-4 sd), int(mean + 2 sd - 2 r)] are evaluated in one kernel launch; the dictionary is
+    filled in the reference's order (holes between consecutive rounded values take the larger d)."""
+    d_upper = int(mean + 2 * stdDev - 2 * readLen)
+    d_lower = int(-4 * stdDev)
+    table = {}
+    if d_upper < d_lower:
+        return table
+    ds = np.arange(d_lower, d_upper + 1, dtype=np.float64)
+    # contig lengths travel as int32 across the ABI: mean + 4 stdDev must be integral for the batched form
+    c = mean + 4 * stdDev
+    if float(c) != float(int(c)):
+        raise ValueError("PreCalcMLvaluesOfdLongContigs: mean + 4*stdDev must be an integer (got %r)" % (c,))
+    f = func_of_d_batch(mean, stdDev, readLen, ds, int(c), int(c), engine=engine)
+    prev_obs = d_lower
+    for d, func_of_d in zip(range(d_lower, d_upper + 1), f.tolist()):
+        obs = int(round(func_of_d, 0))
+        table[obs] = d
+        if abs(obs - prev_obs) > 1:
+            for i in range(abs(obs - prev_obs)):
+                table[prev_obs + i + 1] = d
+        prev_obs = obs
+    return table

@@ -287,6 +287,11 @@ int besst_gapest_batch(besst_ctx* ctx, const besst_lib_params* params, const dou
                        const int32_t* len1, const int32_t* len2, int64_t n,
                        int32_t* gap_out, double* sd_out);
 
+/* d[i] + sigma^2 g'(d[i])/g(d[i]) for contig lengths len1[i], len2[i]: the left-hand side of the ML equation
+ * (mathstats funcDGeneral), what PreCalcMLvaluesOfdLongContigs tabulates (MakeScaffolds.py:68) */
+int besst_gapest_func_batch(besst_ctx* ctx, const besst_lib_params* params, const double* d, const int32_t* len1,
+                            const int32_t* len2, int64_t n, double* func_out);
+
 /* tr_sk_std_dev(mean, sigma, read_len, len1[i], len2[i], gap[i]) (host arrays in/out) */
 int besst_trsk_sd_batch(besst_ctx* ctx, const besst_lib_params* params, const double* gap, const int32_t* len1,
                         const int32_t* len2, int64_t n, double* sd_out);

@@ -449,6 +449,24 @@ def test_scalar_dropins(cuda_engine):
     assert sd == pytest.approx(L.besst_oracle_tr_sk_std_dev(3000.0, 500.0, 100.0, 6000.0, 7000.0, 420.0, abi.ERF_AS7126), rel=1e-6)
 
 
+@pytest.mark.parametrize("mean,sd,r", [(3000.0, 500.0, 100.0), (550.0, 50.0, 100.0), (8000.0, 1200.0, 150.0), (350.0, 100.0, 75.0)])
+def test_precalc_table_of_long_contig_gaps_equals_restated_mathstats(cuda_engine, mean, sd, r):
+    """GC.PreCalcMLvaluesOfdLongContigs (MakeScaffolds.py:68): every d of the table in one kernel launch."""
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "mathstats_restated"))
+    from mathstats.normaldist.truncatedskewed import param_est as ref
+    from besst_b200 import param_est
+    want = ref.PreCalcMLvaluesOfdLongContigs(mean, sd, r)
+    got = param_est.PreCalcMLvaluesOfdLongContigs(mean, sd, r, engine=cuda_engine)
+    assert got == want and len(want) > 100
+    assert list(got.keys()) == list(want.keys())   # same insertion order
+    ds = np.array([-200.0, 0.0, 17.5, 900.0])
+    f = param_est.func_of_d_batch(mean, sd, r, ds, 6000, 4100, engine=cuda_engine)
+    for d, v in zip(ds, f):
+        assert v == pytest.approx(ref.funcDGeneral(float(d), mean, sd, 6000, 4100, r)[0], rel=1e-12)
+
+
 def test_distributed_nccl_equals_oracle():
     """Needs >= 2 GPUs on the box (gpurun --gpus 2): the real NCCL all-to-all path."""
     import subprocess
