@@ -393,7 +393,7 @@ def run_reference(args):
     from besst_b200.contig_table import first_library_rows
     cfg_name, desc = WORKLOADS[args.workload]
     n_contigs, n_pairs, orientation, mu, sigma, cont = synth.CONFIGS[cfg_name]
-    frac = min(1.0, (CPU_SAMPLE_RECORDS / 8) / (2.0 * n_pairs)) * args.scale
+    frac = min(1.0, (CPU_SAMPLE_RECORDS / 2) / (2.0 * n_pairs)) * args.scale   # 10 M pairs: ~0.5 s per step on one core
     lib = synth.make_library(max(2, int(n_contigs * frac)), max(1000, int(n_pairs * frac)), orientation, mu, sigma, cont,
                              seed=synth.SEED0 + 2, device="cpu", with_names=False)
     batch = lib.to_batch()

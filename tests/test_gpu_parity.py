@@ -49,6 +49,36 @@ def test_graph_build_matches_oracle(cuda_engine, config, objects, over):
     assert want.n_edges > 0 and want.n_links > 0
 
 
+@pytest.mark.parametrize("over", [
+    {"ins_size_threshold": 5.0e6},     # 23 value bits: KS keys do not fit the in-block path, 64-bit device-wide sorts
+    {"ins_size_threshold": 70000.0},   # 17 value bits
+    {"ins_size_threshold": 26.0},      # nothing passes obs1 > 25 and obs2 > 25 and obs1 + obs2 < 26: no links at all
+    {"ins_size_threshold": float("nan")},
+    {"min_mapq": 61},                  # no record passes the link filter
+])
+def test_threshold_extremes(cuda_engine, over):
+    lib = synth.make_config("small_mp")
+    batch = lib.to_batch()
+    params, contig_threshold = _params(lib, over)
+    objs = helpers.first_library_objects(batch.references, batch.lengths, contig_threshold)
+    table = helpers.table_for(batch, objs)
+    want, _, _, consistent = oracle_lib.graph_build(table.rows, table.n_scaffolds, params, batch)
+    assert consistent
+    got = cuda_engine.graph_build(table, params, batch)
+    helpers.assert_graph_equal(got, want, label=str(over))
+
+
+def test_library_without_inter_contig_pairs(cuda_engine):
+    lib, batch, params, table = _setup("small_pe")
+    from besst_b200.records import RecordBatch
+    same = RecordBatch(tid=batch.tid, mtid=batch.tid.copy(), pos=batch.pos, mpos=batch.mpos, tlen=batch.tlen, qlen=batch.qlen,
+                       flag=batch.flag, mapq=batch.mapq, references=batch.references, lengths=batch.lengths)
+    want, _, _, _ = oracle_lib.graph_build(table.rows, table.n_scaffolds, params, same)
+    got = cuda_engine.graph_build(table, params, same)
+    helpers.assert_graph_equal(got, want, label="no inter-contig pairs")
+    assert got.n_edges == 0 and got.counters[abi.CNT_VALID] == len(batch)
+
+
 def _setup(config, over=None, objects="first"):
     lib = synth.make_config(config)
     batch = lib.to_batch()
