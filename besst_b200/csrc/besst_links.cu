@@ -648,7 +648,9 @@ __global__ void __launch_bounds__(SC_THREADS) k_chunk_resolve(const Agg* __restr
     __shared__ Last s_carry;
     __shared__ u64 s_off;
     __shared__ long long s_corr[4];
+    __shared__ unsigned long long s_first_chunk;   // first chunk holding a CreateEdge call
     if (threadIdx.x == 0) {
+        s_first_chunk = ~0ull;
         s_carry.has = 1; s_carry.o1 = halo1; s_carry.o2 = halo2;   // counters(..., prev_obs1=-1, prev_obs2=-1) :98
         s_off = 0;
         s_corr[0] = s_corr[1] = s_corr[2] = s_corr[3] = 0;
@@ -657,6 +659,7 @@ __global__ void __launch_bounds__(SC_THREADS) k_chunk_resolve(const Agg* __restr
     for (long long base = 0; base < n_chunks; base += SC_THREADS) {
         const long long i = base + threadIdx.x;
         const Agg a = load_agg(chunk_aggs, i, n_chunks);
+        if (a.flags & AGG_HAS) atomicMin(&s_first_chunk, (unsigned long long)i);
         const Last carry = s_carry;
         const u64 off0 = s_off;
         const ScanResult R = block_scan_aggs(a, carry, detect_dup, S);
@@ -683,6 +686,10 @@ __global__ void __launch_bounds__(SC_THREADS) k_chunk_resolve(const Agg* __restr
         counters[BESST_CNT_NON_UNIQUE_SCAF] += (u64)s_corr[3];
         counters[BESST_CNT_LAST_OBS1] = (u64)(long long)s_carry.o1;
         counters[BESST_CNT_LAST_OBS2] = (u64)(long long)s_carry.o2;
+        long long f1 = 0, f2 = 0;
+        if (s_first_chunk != ~0ull) { f1 = chunk_aggs[s_first_chunk].first_o1; f2 = chunk_aggs[s_first_chunk].first_o2; }
+        counters[BESST_CNT_FIRST_OBS1] = (u64)f1;
+        counters[BESST_CNT_FIRST_OBS2] = (u64)f2;
     }
 }
 

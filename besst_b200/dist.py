@@ -104,6 +104,12 @@ class CudaBackend(object):
         return send_t[:4 * n].view(-1, 4), send_o[:n], send_f[:nf], tc, fc
 
     # run-level exchange
+    def call_summary(self):
+        """(number of CreateEdge calls, (obs1, obs2) of the last one, of the first one) of the last extraction"""
+        c = self.engine.links_counters()
+        return (int(c[abi.CNT_CALLS]), (int(c[abi.CNT_LAST_OBS1]), int(c[abi.CNT_LAST_OBS2])),
+                (int(c[abi.CNT_FIRST_OBS1]), int(c[abi.CNT_FIRST_OBS2])))
+
     def group(self):
         return self.engine.links_group()
 
@@ -236,29 +242,23 @@ class DistributedGraphBuild(object):
     def step(self, params, rec):
         """One distributed graph build.  Leaves this rank's share of the CSR in its HBM;
         returns the local sizes.  `self.last` keeps what fetch_local needs."""
-        dist, world = self.dist, self.world
         self.phase_ms = {}
         self._t_last = None
         self._mark(None)
+        if self.exchange_runs and hasattr(self.b, "group"):
+            sizes = self._step_runs(params, rec)
+            if sizes is not None:
+                return sizes
+        return self._step_tuples(params, rec)
+
+    # -- exchange by tuples (fallback: a rank's link stream has no local order) ---------------------------
+    def _step_tuples(self, params, rec):
+        dist, world = self.dist, self.world
         halo = self.halo(params, rec) if world > 1 else (params.halo_prev_obs1, params.halo_prev_obs2)
         self._mark("halo")
         p = _copy_params(params, halo)
         n_local = self.b.extract(p, rec)
         self._mark("extract")
-        if self.exchange_runs and hasattr(self.b, "group"):
-            sizes = None
-            if self.exchange_peer:
-                try:
-                    sizes = self._step_runs_peer(p, n_local)
-                except _SymmUnavailable as exc:   # no peer mapping on this box: every rank raises alike (collective setup)
-                    import warnings
-                    warnings.warn("symmetric memory unavailable (%s): NCCL all-to-all instead" % exc)
-                    self.exchange_peer = False
-                    sizes = self._step_runs(p, n_local, regroup=False)
-            else:
-                sizes = self._step_runs(p, n_local)
-            if sizes is not None:
-                return sizes
         send_t, send_o, send_f, tc, fc = self.b.partition(world)
         # bucket sizes: one small all_to_all, then the payload all_to_all
         counts_out = self.b.counts_tensor(np.stack([tc, fc], axis=1).reshape(-1).tolist())
@@ -283,37 +283,101 @@ class DistributedGraphBuild(object):
         lasts = [last.clone() for _ in range(world)]
         dist.all_gather(lasts, last, group=self.group)
         self.last = dict(sizes=sizes, recv_o=recv_o, recv_splits=rt, n_tuples_by_rank=[int(t.item()) for t in n_all],
-                         aligned=aligned, counters=counters, last_call=[tuple(int(x) for x in t.tolist()) for t in lasts],
+                         aligned=aligned, counters=counters, last_call=[tuple(int(x) for x in t.tolist()) for t in lasts][world - 1],
                          halo=halo)
         return sizes
 
-    def _step_runs_peer(self, p, n_local):
-        """Run-level exchange with the all-to-all FUSED into the pack kernel: every rank owns peer-mapped
-        receive buffers (symmetric memory); k_runs_pack stores each run straight into its destination GPU
-        over NVLink, bracketed by two cross-GPU barriers.  One all_gather of the segment sizes is the only
-        host-visible collective.  None: some rank's stream has no local order (tuple-level path)."""
+    # -- exchange by runs (default) -------------------------------------------------------------------------
+    def _step_runs(self, params, rec):
+        """Whole runs (block-grouped links of one edge) are routed by edge hash: 8 bytes per link + 24 per
+        run cross NVLink and the receiver starts at the run merge.
+
+        No halo pass: every rank extracts with a PROVISIONAL halo that matches nothing; the one
+        all_gather that carries the segment sizes also carries each slice's first and last CreateEdge
+        call, so every rank can tell afterwards whether some slice's first call duplicates the call
+        before it (CreateGraph.py:835-838).  Only then (rare) the affected ranks extract again with
+        their true halo and the sizes are gathered once more.
+
+        Transport: `peer` -- k_runs_pack stores straight into the destination GPU's symmetric-memory
+        buffers, two cross-GPU barriers; else three NCCL all_to_all_single calls.
+        None: some rank's stream has no local order (tuple-level path)."""
         dist, world, rank = self.dist, self.world, self.rank
-        torch = self.b.torch
-        n_runs = self.b.group()
-        self._mark("group")
-        ok = n_runs is not None
-        if ok:
-            lc, rc = self.b.route(world)
-        else:
-            lc, rc = np.zeros(world, np.int64), np.zeros(world, np.int64)
-        send_f, fc = self.b.partition_fishy(world)
-        self._mark("route+fishy")
-        mine = self.b.counts_tensor([1 if ok else 0, n_local] + lc.tolist() + rc.tolist() + fc.tolist())
-        gathered = [torch.empty_like(mine) for _ in range(world)]
-        dist.all_gather(gathered, mine, group=self.group)
-        M = np.asarray(torch.stack(gathered).tolist(), dtype=np.int64)
-        self._mark("meta")
-        if int(M[:, 0].min()) == 0:
-            return None
+        init_halo = (int(params.halo_prev_obs1), int(params.halo_prev_obs2))
+        p = _copy_params(params, (NO_MATCH, NO_MATCH))
+        need_extract = True
+        self.redo_count = 0
+        for attempt in range(2):
+            if need_extract:
+                n_local = self.b.extract(p, rec)
+                self._mark("extract")
+                calls, last, first = self.b.call_summary()
+                n_runs = self.b.group()
+                self._mark("group")
+                ok = n_runs is not None
+                lc, rc = self.b.route(world) if ok else (np.zeros(world, np.int64), np.zeros(world, np.int64))
+                send_f, fc = self.b.partition_fishy(world)
+                self._mark("route+fishy")
+            mine = self.b.counts_tensor([1 if ok else 0, n_local, 1 if calls > 0 else 0, last[0], last[1], first[0], first[1]]
+                                        + lc.tolist() + rc.tolist() + fc.tolist())
+            gathered = [self.b.counts_tensor([0] * (7 + 3 * world)) for _ in range(world)]
+            dist.all_gather(gathered, mine, group=self.group)
+            M = np.asarray([g.tolist() for g in gathered], dtype=np.int64)
+            self._mark("meta")
+            if int(M[:, 0].min()) == 0:
+                return None
+            halos, cur = [], init_halo
+            for r in range(world):
+                halos.append(cur)
+                if M[r, 2]:
+                    cur = (int(M[r, 3]), int(M[r, 4]))
+            global_last = cur
+            redo = [bool(M[r, 2]) and (int(M[r, 5]), int(M[r, 6])) == halos[r] for r in range(world)]
+            if attempt == 0 and any(redo):   # a slice starts with a duplicate of the call before it
+                self.redo_count = sum(redo)
+                need_extract = redo[rank]
+                if need_extract:
+                    p = _copy_params(params, halos[rank])
+                continue
+            break
         n_by_rank = M[:, 1]
-        LC, RC, FC = M[:, 2:2 + world], M[:, 2 + world:2 + 2 * world], M[:, 2 + 2 * world:2 + 3 * world]
+        LC, RC, FC = M[:, 7:7 + world], M[:, 7 + world:7 + 2 * world], M[:, 7 + 2 * world:7 + 3 * world]
+        rl, rr, rf = LC[:, rank], RC[:, rank], FC[:, rank]
         if int(n_by_rank.sum()) >= 2 ** 32 or int(LC.sum(axis=0).max()) >= 2 ** 30:
             raise ValueError("run-level exchange: more than 2^32 links in the library or 2^30 on one rank")
+        if self.exchange_peer:
+            try:
+                recv_obs, recv_desc, recv_f = self._transport_peer(LC, RC, FC, send_f, fc)
+            except _SymmUnavailable as exc:   # no peer mapping on this box: every rank raises alike (collective setup)
+                import warnings
+                warnings.warn("symmetric memory unavailable (%s): NCCL all-to-all instead" % exc)
+                self.exchange_peer = False
+        if not self.exchange_peer:
+            send_obs, send_desc = self.b.pack(world, int(lc.sum()), int(rc.sum()))
+            recv_obs, recv_desc, recv_f = self.b.recv_run_buffers(int(rl.sum()), int(rr.sum()), int(rf.sum()))
+            self._mark("pack")
+            dist.all_to_all_single(recv_obs, send_obs, output_split_sizes=rl.tolist(), input_split_sizes=lc.tolist(), group=self.group)
+            dist.all_to_all_single(recv_desc, send_desc, output_split_sizes=rr.tolist(), input_split_sizes=rc.tolist(), group=self.group)
+            dist.all_to_all_single(recv_f, send_f, output_split_sizes=rf.tolist(), input_split_sizes=fc.tolist(), group=self.group)
+            self._mark("all_to_all")
+        max_blocks = int(((n_by_rank + abi.RUN_BLOCK - 1) // abi.RUN_BLOCK).max())
+        block_bits = max(1, int(max(max_blocks - 1, 1)).bit_length())
+        first_base = np.concatenate([[0], np.cumsum(n_by_rank)[:-1]])
+        sizes = self.b.runs_to_graph(p, recv_obs, recv_desc, world, block_bits, rr, rl, first_base, recv_f)
+        self._mark("runs_to_graph")
+        aligned, counters = self.b.partial_tensors()
+        counters[abi.CNT_LAST_OBS1:] = 0   # per-rank slots (last / first call): not sums
+        dist.all_reduce(aligned, op=dist.ReduceOp.SUM, group=self.group)
+        dist.all_reduce(counters, op=dist.ReduceOp.SUM, group=self.group)
+        self._mark("all_reduce")
+        self.last = dict(sizes=sizes, global_first=True, n_tuples_by_rank=n_by_rank.tolist(), aligned=aligned, counters=counters,
+                         last_call=global_last, halo=halos[rank])
+        return sizes
+
+    def _transport_peer(self, LC, RC, FC, send_f, fc):
+        """The exchange fused into the pack kernel: every rank owns peer-mapped receive buffers (symmetric
+        memory); the W x W count matrix gives every sender its offset inside every receiver."""
+        world, rank = self.world, self.rank
+        torch = self.b.torch
         try:
             obs_t, obs_h = self.b.symm_buffer("obs", 2 * int(LC.sum(axis=0).max()) + 2, torch.int32, self.group)
             desc_t, desc_h = self.b.symm_buffer("desc", 6 * int(RC.sum(axis=0).max()) + 6, torch.int32, self.group)
@@ -334,69 +398,7 @@ class DistributedGraphBuild(object):
         obs_h.barrier(channel=0)   # all stores have landed
         self._mark("pack+exchange")
         rl, rr, rf = LC[:, rank], RC[:, rank], FC[:, rank]
-        recv_obs = obs_t[:2 * int(rl.sum())].view(-1, 2)
-        recv_desc = desc_t[:6 * int(rr.sum())].view(-1, 6)
-        recv_f = f_t[:int(rf.sum())]
-        max_blocks = int(((n_by_rank + abi.RUN_BLOCK - 1) // abi.RUN_BLOCK).max())
-        block_bits = max(1, int(max(max_blocks - 1, 1)).bit_length())
-        first_base = np.concatenate([[0], np.cumsum(n_by_rank)[:-1]])
-        sizes = self.b.runs_to_graph(p, recv_obs, recv_desc, world, block_bits, rr, rl, first_base, recv_f)
-        self._mark("runs_to_graph")
-        aligned, counters = self.b.partial_tensors()
-        last = counters[abi.CNT_LAST_OBS1:abi.CNT_LAST_OBS2 + 1].clone()
-        counters[abi.CNT_LAST_OBS1:] = 0
-        dist.all_reduce(aligned, op=dist.ReduceOp.SUM, group=self.group)
-        dist.all_reduce(counters, op=dist.ReduceOp.SUM, group=self.group)
-        self._mark("all_reduce")
-        self.last = dict(sizes=sizes, global_first=True, n_tuples_by_rank=n_by_rank.tolist(), aligned=aligned, counters=counters,
-                         last_local=last, halo=(p.halo_prev_obs1, p.halo_prev_obs2))
-        return sizes
-
-    def _step_runs(self, p, n_local, regroup=True):
-        """Run-level exchange: whole runs (block-grouped links of one edge) are routed by edge hash; 8 bytes
-        per link + 24 per run cross NVLink and the receiver starts at the run merge.  None: some rank's
-        stream has no local order -- every rank takes the tuple-level path."""
-        dist, world = self.dist, self.world
-        n_runs = self.b.group() if regroup else 0
-        self._mark("group")
-        ok = self.b.counts_tensor([1 if n_runs is not None else 0])
-        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=self.group)
-        if int(ok.item()) == 0:
-            return None
-        self._mark("agree")
-        lc, rc = self.b.route(world)
-        send_f, fc = self.b.partition_fishy(world)
-        self._mark("route+fishy")
-        # one small all_to_all: what every destination gets from me (links, runs, fishy keys) + my link count
-        meta_out = self.b.counts_tensor(np.stack([lc, rc, fc, np.full(world, n_local)], axis=1).reshape(-1).tolist())
-        meta_in = self.b.counts_tensor([0] * (4 * world))
-        dist.all_to_all_single(meta_in, meta_out, group=self.group)
-        mi = np.asarray(meta_in.tolist(), dtype=np.int64).reshape(world, 4)
-        rl, rr, rf, n_by_rank = mi[:, 0], mi[:, 1], mi[:, 2], mi[:, 3]
-        if int(n_by_rank.sum()) >= 2 ** 32 or int(rl.sum()) >= 2 ** 30:
-            raise ValueError("run-level exchange: more than 2^32 links in the library or 2^30 on one rank")
-        self._mark("meta")
-        send_obs, send_desc = self.b.pack(world, int(lc.sum()), int(rc.sum()))
-        recv_obs, recv_desc, recv_f = self.b.recv_run_buffers(int(rl.sum()), int(rr.sum()), int(rf.sum()))
-        self._mark("pack")
-        dist.all_to_all_single(recv_obs, send_obs, output_split_sizes=rl.tolist(), input_split_sizes=lc.tolist(), group=self.group)
-        dist.all_to_all_single(recv_desc, send_desc, output_split_sizes=rr.tolist(), input_split_sizes=rc.tolist(), group=self.group)
-        dist.all_to_all_single(recv_f, send_f, output_split_sizes=rf.tolist(), input_split_sizes=fc.tolist(), group=self.group)
-        self._mark("all_to_all")
-        max_blocks = int(((n_by_rank + abi.RUN_BLOCK - 1) // abi.RUN_BLOCK).max())
-        block_bits = max(1, int(max(max_blocks - 1, 1)).bit_length())
-        first_base = np.concatenate([[0], np.cumsum(n_by_rank)[:-1]])
-        sizes = self.b.runs_to_graph(p, recv_obs, recv_desc, world, block_bits, rr, rl, first_base, recv_f)
-        self._mark("runs_to_graph")
-        aligned, counters = self.b.partial_tensors()
-        last = counters[abi.CNT_LAST_OBS1:abi.CNT_LAST_OBS2 + 1].clone()
-        counters[abi.CNT_LAST_OBS1:] = 0
-        dist.all_reduce(aligned, op=dist.ReduceOp.SUM, group=self.group)
-        dist.all_reduce(counters, op=dist.ReduceOp.SUM, group=self.group)
-        self._mark("all_reduce")
-        self.last = dict(sizes=sizes, global_first=True, n_tuples_by_rank=n_by_rank.tolist(), aligned=aligned, counters=counters,
-                         last_local=last, halo=(p.halo_prev_obs1, p.halo_prev_obs2))
-        return sizes
+        return obs_t[:2 * int(rl.sum())].view(-1, 2), desc_t[:6 * int(rr.sum())].view(-1, 6), f_t[:int(rf.sum())]
 
     # -- results ------------------------------------------------------------------------------------
     def fetch_local(self, view=False):
@@ -414,14 +416,9 @@ class DistributedGraphBuild(object):
             res.first_idx = prefix[src] + ordinals[res.first_idx]
         res.aligned_len = np.asarray(L["aligned"].cpu().numpy(), dtype=np.int64)
         counters = np.asarray(L["counters"].cpu().numpy(), dtype=np.int64).copy()
-        # the globally last CreateEdge call: every rank starts from its halo, so rank world-1's
-        # pair already folds in all earlier ranks
-        if "last_call" not in L:   # run-level path: gathered here, outside the step (collective: every rank calls fetch_local)
-            lasts = [L["last_local"].clone() for _ in range(self.world)]
-            self.dist.all_gather(lasts, L["last_local"], group=self.group)
-            L["last_call"] = [tuple(int(x) for x in t.tolist()) for t in lasts]
-        last = L["last_call"][self.world - 1]
-        counters[abi.CNT_LAST_OBS1], counters[abi.CNT_LAST_OBS2] = last
+        # the globally last CreateEdge call (the next library pass would start from it)
+        counters[abi.CNT_LAST_OBS1], counters[abi.CNT_LAST_OBS2] = L["last_call"]
+        counters[abi.CNT_FIRST_OBS1] = counters[abi.CNT_FIRST_OBS2] = 0
         res.counters = counters
         return res
 

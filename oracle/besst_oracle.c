@@ -321,6 +321,7 @@ typedef struct {
     const besst_lib_params* p;
     int64_t count, non_unique_for_scaf, dups, too_long;
     int32_t prev1, prev2;
+    int32_t first1, first2, has_first;   /* the first CreateEdge call of the batch */
 } ce_state;
 
 /* CreateEdge, CreateGraph.py:812-871; returns is_dupl */
@@ -333,6 +334,7 @@ static int create_edge(ce_state* st, gstore* g, const besst_contig_row* r1, cons
     int32_t obs1, obs2; int s1, s2;
     pos_dir_end(r1->direction, !rev, p->orientation, r1->position, pos, r1->scaf_length, r1->length, p->read_len, &obs1, &s1);
     pos_dir_end(r2->direction, !mate_rev, p->orientation, r2->position, mpos, r2->scaf_length, r2->length, p->read_len, &obs2, &s2);
+    if (!st->has_first) { st->has_first = 1; st->first1 = obs1; st->first2 = obs2; }
     if (obs1 == st->prev1 && obs2 == st->prev2) {
         st->dups += 1;
         if (p->detect_duplicate) return 1;
@@ -551,6 +553,7 @@ besst_oracle_result* besst_oracle_graph_build(const besst_contig_row* rows, int6
     o->counters[BESST_CNT_TOO_LONG] = st.too_long; o->counters[BESST_CNT_FISHY] = ctr;
     o->counters[BESST_CNT_CALLS] = calls; o->counters[BESST_CNT_VALID] = valid;
     o->counters[BESST_CNT_LAST_OBS1] = st.prev1; o->counters[BESST_CNT_LAST_OBS2] = st.prev2;
+    o->counters[BESST_CNT_FIRST_OBS1] = st.has_first ? st.first1 : 0; o->counters[BESST_CNT_FIRST_OBS2] = st.has_first ? st.first2 : 0;
     R->sizes.n_edges = E; R->sizes.n_links = U->n_links; R->sizes.n_contigs = n_contigs; R->sizes.n_fishy = fishy_n;
     { int64_t nll = 0; for (int64_t k = 0; k < E; ++k) if (o->flags[k] & BESST_EDGE_LL) nll += o->nr_links[k]; R->sizes.n_ll_links = nll; }
     R->fishy_keys = fishy_key; R->fishy_counts = fishy_cnt;

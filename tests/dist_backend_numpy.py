@@ -87,6 +87,11 @@ class NumpyBackend(object):
         return "sizes"
 
     # ---- run-level exchange: numpy statement of besst_links_group / runs_route / runs_pack / runs_to_graph ----
+    def call_summary(self):
+        c = self.counters.numpy()
+        return (int(c[abi.CNT_CALLS]), (int(c[abi.CNT_LAST_OBS1]), int(c[abi.CNT_LAST_OBS2])),
+                (int(c[abi.CNT_FIRST_OBS1]), int(c[abi.CNT_FIRST_OBS2])))
+
     def group(self):
         t = self.tuples
         n = t.shape[0]

@@ -74,7 +74,7 @@ def assert_graph_equal(got, want, check_scores=True, label=""):
         if f == "flags" and not check_scores:
             a, b = a & abi.EDGE_LL, b & abi.EDGE_LL
         assert np.array_equal(a, b), "%s: integer field %s differs at %s" % (label, f, np.nonzero(a != b)[0][:5])
-    n_cnt = 10
+    n_cnt = 12
     assert np.array_equal(got.counters[:n_cnt], want.counters[:n_cnt]), "%s: counters %s != %s" % (
         label, got.counters[:n_cnt], want.counters[:n_cnt])
     if check_scores:

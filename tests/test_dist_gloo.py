@@ -24,6 +24,7 @@ def _free_port():
 
 def _worker(rank, world, port, config, cuts, out_dir, exchange):
     os.environ["BESST_DIST_EXCHANGE"] = exchange
+    expect_redo = cuts == "split_duplicate"
     for p in (ROOT, os.path.join(ROOT, "oracle"), HERE):
         if p not in sys.path:
             sys.path.insert(0, p)
@@ -41,9 +42,18 @@ def _worker(rank, world, port, config, cuts, out_dir, exchange):
         objs = helpers.later_library_objects(batch.references, batch.lengths, lib.mu + 4 * lib.sigma, seed=3)
         table = helpers.table_for(batch, objs)
         n = len(batch)
+        if cuts == "split_duplicate":   # cut between two adjacent identical read2 records: the second slice starts with a duplicate
+            same = ((batch.tid[1:] == batch.tid[:-1]) & (batch.pos[1:] == batch.pos[:-1]) & (batch.mtid[1:] == batch.mtid[:-1]) &
+                    (batch.mpos[1:] == batch.mpos[:-1]) & (batch.flag[1:] == batch.flag[:-1]) & (batch.tid[1:] != batch.mtid[1:]) &
+                    ((batch.flag[1:] & 0x80) != 0) & ((batch.flag[1:] & 0x4) == 0) & (batch.mapq[1:] >= 11) & (batch.mapq[:-1] >= 11))
+            cand = np.nonzero(same)[0] + 1
+            assert len(cand) > 0
+            cuts = [cand[len(cand) // 2] / float(n) + 1e-12]
         bounds = [0] + [int(n * c) for c in cuts] + [n]
         runner = DistributedGraphBuild(NumpyBackend(table), rank, world)
         runner.step(params, batch.slice(bounds[rank], bounds[rank + 1]))
+        if expect_redo and exchange == "runs":
+            assert runner.redo_count > 0, "the cut was meant to split a duplicate pair"
         merged = runner.fetch_global()
         if rank == 0:
             want, _, _, _ = oracle_lib.graph_build(table.rows, table.n_scaffolds, params, batch)
@@ -63,6 +73,7 @@ def _worker(rank, world, port, config, cuts, out_dir, exchange):
     (2, "small_mp", [0.5]),
     (3, "small_pe", [0.2, 0.21]),       # a tiny middle slice
     (3, "tiny", [0.0, 0.6]),            # an empty first slice: the halo must pass through
+    (2, "small_mp", "split_duplicate"), # the second slice starts with a duplicate of the first slice's last call
 ])
 @pytest.mark.parametrize("exchange", ["runs", "tuples"])
 def test_distributed_build_equals_single_pass(tmp_path, world, config, cuts, exchange):
