@@ -276,15 +276,18 @@ class DistributedGraphBuild(object):
         aligned, counters = self.b.partial_tensors()
         n_all = [self.b.counts_tensor([0]) for _ in range(world)]
         dist.all_gather(n_all, self.b.counts_tensor([n_local]), group=self.group)
-        last = counters[abi.CNT_LAST_OBS1:abi.CNT_LAST_OBS2 + 1].clone()
+        ends = counters[[abi.CNT_CALLS, abi.CNT_LAST_OBS1, abi.CNT_LAST_OBS2, abi.CNT_FIRST_OBS1, abi.CNT_FIRST_OBS2]].clone()
         counters[abi.CNT_LAST_OBS1:] = 0
         dist.all_reduce(aligned, op=dist.ReduceOp.SUM, group=self.group)
         dist.all_reduce(counters, op=dist.ReduceOp.SUM, group=self.group)
-        lasts = [last.clone() for _ in range(world)]
-        dist.all_gather(lasts, last, group=self.group)
+        all_ends = [ends.clone() for _ in range(world)]
+        dist.all_gather(all_ends, ends, group=self.group)
+        E = [[int(x) for x in t.tolist()] for t in all_ends]
+        with_calls = [e for e in E if e[0] > 0]
+        # every rank starts from its halo, so the last rank's pair already folds in all earlier ranks
         self.last = dict(sizes=sizes, recv_o=recv_o, recv_splits=rt, n_tuples_by_rank=[int(t.item()) for t in n_all],
-                         aligned=aligned, counters=counters, last_call=[tuple(int(x) for x in t.tolist()) for t in lasts][world - 1],
-                         halo=halo)
+                         aligned=aligned, counters=counters, last_call=(E[world - 1][1], E[world - 1][2]),
+                         first_call=(with_calls[0][3], with_calls[0][4]) if with_calls else (0, 0), halo=halo)
         return sizes
 
     # -- exchange by runs (default) -------------------------------------------------------------------------
@@ -331,6 +334,8 @@ class DistributedGraphBuild(object):
                 if M[r, 2]:
                     cur = (int(M[r, 3]), int(M[r, 4]))
             global_last = cur
+            firsts = [(int(M[r, 5]), int(M[r, 6])) for r in range(world) if M[r, 2]]
+            global_first = firsts[0] if firsts else (0, 0)
             redo = [bool(M[r, 2]) and (int(M[r, 5]), int(M[r, 6])) == halos[r] for r in range(world)]
             if attempt == 0 and any(redo):   # a slice starts with a duplicate of the call before it
                 self.redo_count = sum(redo)
@@ -370,7 +375,7 @@ class DistributedGraphBuild(object):
         dist.all_reduce(counters, op=dist.ReduceOp.SUM, group=self.group)
         self._mark("all_reduce")
         self.last = dict(sizes=sizes, global_first=True, n_tuples_by_rank=n_by_rank.tolist(), aligned=aligned, counters=counters,
-                         last_call=global_last, halo=halos[rank])
+                         last_call=global_last, first_call=global_first, halo=halos[rank])
         return sizes
 
     def _transport_peer(self, LC, RC, FC, send_f, fc):
@@ -418,7 +423,7 @@ class DistributedGraphBuild(object):
         counters = np.asarray(L["counters"].cpu().numpy(), dtype=np.int64).copy()
         # the globally last CreateEdge call (the next library pass would start from it)
         counters[abi.CNT_LAST_OBS1], counters[abi.CNT_LAST_OBS2] = L["last_call"]
-        counters[abi.CNT_FIRST_OBS1] = counters[abi.CNT_FIRST_OBS2] = 0
+        counters[abi.CNT_FIRST_OBS1], counters[abi.CNT_FIRST_OBS2] = L["first_call"]
         res.counters = counters
         return res
 
