@@ -18,7 +18,7 @@ EXPORTS = ["besst_abi_version", "besst_create", "besst_destroy", "besst_last_err
            "besst_gapest_batch", "besst_last_timing", "besst_kernel_launches", "besst_set_profiling",
            "besst_kernel_profile", "besst_links_partials_device", "besst_links_fetch", "besst_links_partition",
            "besst_trsk_sd_batch", "besst_set_stream", "besst_graph_view", "besst_links_group", "besst_runs_route",
-           "besst_runs_pack", "besst_runs_to_graph", "besst_runs_pack_peer", "besst_gapest_func_batch"]
+           "besst_runs_pack", "besst_runs_to_graph", "besst_runs_pack_peer", "besst_gapest_func_batch", "besst_runs_obs_bytes"]
 
 _lib = None
 
@@ -71,6 +71,7 @@ def load():
     L.besst_runs_route.argtypes = [vp, i32, vp, vp]
     L.besst_runs_pack.argtypes = [vp, i32, vp, vp]
     L.besst_runs_pack_peer.argtypes = [vp, i32, vp, vp]
+    L.besst_runs_obs_bytes.argtypes = [C.POINTER(abi.LibParams)]
     L.besst_gapest_func_batch.argtypes = [vp, C.POINTER(abi.LibParams), vp, vp, vp, i64, vp]
     L.besst_runs_to_graph.argtypes = [vp, C.POINTER(abi.LibParams), vp, i64, vp, i64, i32, i32, vp, vp, vp, vp, i64,
                                       C.POINTER(abi.GraphSizes)]

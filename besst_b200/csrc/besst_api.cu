@@ -205,6 +205,7 @@ extern "C" int besst_links_extract(besst_ctx* ctx, const besst_lib_params* param
     if (rc) return rc;
     cudaSetDevice(ctx->device);
     ctx->have_links = ctx->have_graph = ctx->have_runs = false;
+    ctx->extract_params = *params;
     ctx->n_stage_marks = 0;
     ctx->prof_used = 0;
     besst_mark(ctx);
@@ -327,6 +328,8 @@ extern "C" int besst_runs_pack_peer(besst_ctx* ctx, int32_t world, int32_t* cons
     return besst_launch_runs_pack(ctx, world, nullptr, nullptr, obs_ptrs, desc_ptrs);
 }
 
+extern "C" int besst_runs_obs_bytes(const besst_lib_params* params) { return params ? besst_obs_bytes(*params) : -1; }
+
 extern "C" int besst_runs_to_graph(besst_ctx* ctx, const besst_lib_params* params, const int32_t* obs_device, int64_t n_links,
                                    const besst_run_desc* desc_device, int64_t n_runs, int32_t world, int32_t block_bits,
                                    const int64_t* src_run_counts, const int64_t* src_link_counts, const int64_t* src_first_base,
@@ -348,6 +351,7 @@ extern "C" int besst_runs_to_graph(besst_ctx* ctx, const besst_lib_params* param
     in.grouped = reinterpret_cast<const int2*>(obs_device);
     in.n_runs = n_runs;
     in.low_bits = low_bits;
+    in.packed16 = besst_obs_bytes(*params) == 4;
     rc = besst_launch_graph_from_runs(ctx, *params, n_links, in, fishy_keys_device, n_fishy_keys);
     if (rc) return rc;
     ctx->have_runs = false;   // the run buffers now describe the received runs

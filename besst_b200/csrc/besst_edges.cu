@@ -622,6 +622,9 @@ __global__ void __launch_bounds__(RS_T)
 }
 
 // K4': one warp per edge: copy its runs to CSR order and reduce
+// PACK16: the observations arrive as one 32-bit word per link, obs_u | obs_v << 16 (multi-GPU exchange when
+// ins_size_threshold <= 65535: every accepted observation is below the threshold, CreateGraph.py:840)
+template <bool PACK16>
 __global__ void __launch_bounds__(256)
     k_edge_gather(EdgeArrays E, long long n_edges, const int2* __restrict__ grouped, const u32* __restrict__ edge_run_ptr,
                   const u32* __restrict__ run_off, const u32* __restrict__ run_src, const u32* __restrict__ run_len, int bv,
@@ -636,7 +639,13 @@ __global__ void __launch_bounds__(256)
         for (u32 r = r0; r < r1; ++r) {
             const u32 src = __ldg(run_src + r), dst = __ldg(run_off + r), len = __ldg(run_len + r);
             for (u32 k = lane; k < len; k += 32) {
-                const int2 o = __ldg(grouped + src + k);
+                int2 o;
+                if (PACK16) {
+                    const u32 w = __ldg(reinterpret_cast<const u32*>(grouped) + src + k);
+                    o = make_int2((int)(w & 0xffffu), (int)(w >> 16));
+                } else {
+                    o = __ldg(grouped + src + k);
+                }
                 E.obs_u[dst + k] = o.x;
                 E.obs_v[dst + k] = o.y;
                 const long long t = (long long)o.x + (long long)o.y;
@@ -1433,7 +1442,7 @@ int besst_group_tuples(besst_ctx* ctx, const besst_link_tuple* d_tuples, int64_t
 constexpr int RX_MAX_WORLD = 16;
 // where this rank's segment starts inside every destination's observation / descriptor buffer: local
 // addresses (NCCL all-to-all afterwards) or peer-mapped addresses of the destination GPU (NVLink stores)
-struct PackDst { int2* obs[RX_MAX_WORLD]; besst_run_desc* desc[RX_MAX_WORLD]; };
+struct PackDst { void* obs[RX_MAX_WORLD]; besst_run_desc* desc[RX_MAX_WORLD]; };   // obs: int2 or (PACK16) u32 per link
 
 // state: [0..15] links per destination, [16..31] runs per destination
 __global__ void __launch_bounds__(256) k_runs_route_count(const u64* __restrict__ run_key, const u32* __restrict__ run_cnt, long long R,
@@ -1456,6 +1465,7 @@ __global__ void __launch_bounds__(256) k_runs_route_count(const u64* __restrict_
 }
 
 // one warp per run: reserve space in its destination segment, copy the observations, write the descriptor
+template <bool PACK16>
 __global__ void __launch_bounds__(256) k_runs_pack(const u64* __restrict__ run_key, const u32* __restrict__ run_start,
                                                    const u32* __restrict__ run_cnt, const u32* __restrict__ run_first, long long R,
                                                    int block_bits, int bv, int world, const int2* __restrict__ grouped,
@@ -1472,8 +1482,16 @@ __global__ void __launch_bounds__(256) k_runs_pack(const u64* __restrict__ run_k
         u32 a = 0, slot = 0;
         if (lane == 0) { a = atomicAdd(cursors + d, cnt); slot = atomicAdd(cursors + RX_MAX_WORLD + d, 1u); }
         a = __shfl_sync(0xffffffffu, a, 0);
-        int2* dst = D.obs[d] + a;
-        for (u32 k = lane; k < cnt; k += 32) dst[k] = __ldg(grouped + src + k);
+        if (PACK16) {
+            u32* dst = reinterpret_cast<u32*>(D.obs[d]) + a;
+            for (u32 k = lane; k < cnt; k += 32) {
+                const int2 o = __ldg(grouped + src + k);
+                dst[k] = (u32)o.x | ((u32)o.y << 16);
+            }
+        } else {
+            int2* dst = reinterpret_cast<int2*>(D.obs[d]) + a;
+            for (u32 k = lane; k < cnt; k += 32) dst[k] = __ldg(grouped + src + k);
+        }
         if (lane == 0) {
             besst_run_desc ds;
             ds.u = u; ds.v = v; ds.count = cnt; ds.first = __ldg(run_first + r); ds.offset = a;
@@ -1526,10 +1544,11 @@ int besst_launch_runs_pack(besst_ctx* ctx, int world, int32_t* out_obs, besst_ru
     if (R == 0) return BESST_OK;
     const int bv = bits_for((uint64_t)(2 * ctx->n_scaffolds > 0 ? 2 * ctx->n_scaffolds - 1 : 1));
     u32* state = ctx->run_state.as<u32>() + 16;
+    const bool pack16 = besst_obs_bytes(ctx->extract_params) == 4;
     PackDst D;
     if (obs_ptrs) {
         for (int d = 0; d < RX_MAX_WORLD; ++d) {
-            D.obs[d] = d < world ? reinterpret_cast<int2*>(obs_ptrs[d]) : nullptr;
+            D.obs[d] = d < world ? static_cast<void*>(obs_ptrs[d]) : nullptr;
             D.desc[d] = d < world ? desc_ptrs[d] : nullptr;
         }
     } else {
@@ -1538,7 +1557,7 @@ int besst_launch_runs_pack(besst_ctx* ctx, int world, int32_t* out_obs, besst_ru
         BESST_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
         u32 lb = 0, rb = 0;
         for (int d = 0; d < RX_MAX_WORLD; ++d) {
-            D.obs[d] = reinterpret_cast<int2*>(out_obs) + lb; D.desc[d] = out_desc + rb;
+            D.obs[d] = reinterpret_cast<char*>(out_obs) + (size_t)lb * (pack16 ? 4 : 8); D.desc[d] = out_desc + rb;
             if (d < world) { lb += h[d]; rb += h[RX_MAX_WORLD + d]; }
         }
     }
@@ -1546,9 +1565,14 @@ int besst_launch_runs_pack(besst_ctx* ctx, int world, int32_t* out_obs, besst_ru
     long long grid = (R * 32 + 255) / 256;
     if (grid > (long long)ctx->sm_count * 16) grid = (long long)ctx->sm_count * 16;
     { KTimer kt(ctx, BESST_K_PARTITION);
-      k_runs_pack<<<(unsigned)grid, 256, 0, ctx->stream>>>(ctx->run_key[0].as<u64>(), ctx->run_start.as<u32>(), ctx->run_cnt.as<u32>(),
-                                                           ctx->run_first.as<u32>(), R, ctx->run_block_bits, bv, world, ctx->grouped.as<int2>(), D,
-                                                           cursors); }
+      if (pack16)
+          k_runs_pack<true><<<(unsigned)grid, 256, 0, ctx->stream>>>(ctx->run_key[0].as<u64>(), ctx->run_start.as<u32>(), ctx->run_cnt.as<u32>(),
+                                                                     ctx->run_first.as<u32>(), R, ctx->run_block_bits, bv, world,
+                                                                     ctx->grouped.as<int2>(), D, cursors);
+      else
+          k_runs_pack<false><<<(unsigned)grid, 256, 0, ctx->stream>>>(ctx->run_key[0].as<u64>(), ctx->run_start.as<u32>(), ctx->run_cnt.as<u32>(),
+                                                                      ctx->run_first.as<u32>(), R, ctx->run_block_bits, bv, world,
+                                                                      ctx->grouped.as<int2>(), D, cursors); }
     BESST_CUDA_TRY(ctx, cudaGetLastError());
     return BESST_OK;
 }
@@ -1697,9 +1721,14 @@ static int launch_graph_impl(besst_ctx* ctx, const besst_lib_params& p, const be
                 int grid = (int)((E * 32 + 255) / 256);
                 if (grid > edge_grid_max) grid = edge_grid_max;
                 KTimer kt(ctx, BESST_K_EDGE_REDUCE);
-                k_edge_gather<<<grid, 256, 0, ctx->stream>>>(EA, E, grouped_ptr, ctx->edge_run_ptr.as<u32>(), ctx->run_off.as<u32>(),
-                                                             ctx->run_src.as<u32>(), ctx->run_len.as<u32>(), bv, fishy_sorted, n_fishy,
-                                                             (u32)(2 * ctx->n_large), p.no_score ? 0 : 1);
+                if (runs && runs->packed16)
+                    k_edge_gather<true><<<grid, 256, 0, ctx->stream>>>(EA, E, grouped_ptr, ctx->edge_run_ptr.as<u32>(), ctx->run_off.as<u32>(),
+                                                                       ctx->run_src.as<u32>(), ctx->run_len.as<u32>(), bv, fishy_sorted, n_fishy,
+                                                                       (u32)(2 * ctx->n_large), p.no_score ? 0 : 1);
+                else
+                    k_edge_gather<false><<<grid, 256, 0, ctx->stream>>>(EA, E, grouped_ptr, ctx->edge_run_ptr.as<u32>(), ctx->run_off.as<u32>(),
+                                                                        ctx->run_src.as<u32>(), ctx->run_len.as<u32>(), bv, fishy_sorted, n_fishy,
+                                                                        (u32)(2 * ctx->n_large), p.no_score ? 0 : 1);
                 BESST_CUDA_TRY(ctx, cudaGetLastError());
             }
             besst_mark(ctx);

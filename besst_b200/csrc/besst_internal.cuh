@@ -130,6 +130,7 @@ struct besst_ctx {
     bool have_runs = false;
     bool have_graph = false;
     besst_lib_params last_params;
+    besst_lib_params extract_params;   // of the last besst_links_extract
 
     // per-kernel profiling (optional)
     bool prof = false;
@@ -172,7 +173,13 @@ struct BesstRunInput {
     const int2* grouped;   // (obs_u, obs_v) per link; run r covers [run_start[r], run_start[r] + run_cnt[r])
     int64_t n_runs;        // descriptors in ctx->run_key[0] / run_val[0] / run_start / run_cnt / run_first
     int low_bits;          // bits of the sort key below the edge key (source rank, block)
+    bool packed16;         // one u32 per link (obs_u | obs_v << 16) instead of an int2
 };
+// bytes per link of the exchanged observations under these library parameters: every accepted observation is
+// below ins_size_threshold (CreateGraph.py:840), so two of them share a 32-bit word when it is <= 65535
+static inline int besst_obs_bytes(const besst_lib_params& p) {
+    return (p.ins_size_threshold > 0 && p.ins_size_threshold <= 65535.0) ? 4 : 8;
+}
 int besst_launch_graph_from_runs(besst_ctx* ctx, const besst_lib_params& p, int64_t n_links, const BesstRunInput& runs,
                                  const uint64_t* d_fishy, int64_t n_fishy);
 int besst_launch_runs_route(besst_ctx* ctx, int world, int64_t* link_counts, int64_t* run_counts);

@@ -123,16 +123,20 @@ class CudaBackend(object):
         _, fc = self.engine.links_partition(world, None, send_f.data_ptr(), None)
         return send_f[:nf], fc
 
-    def pack(self, world, n_links, n_runs):
+    def obs_words(self, params):
+        """int32 words per exchanged link: 1 (two 16-bit observations) or 2"""
+        return self.engine.runs_obs_bytes(params) // 4
+
+    def pack(self, world, n_links, n_runs, w=2):
         torch = self.torch
-        send_obs = self._buf("send_obs", 2 * n_links, torch.int32)
+        send_obs = self._buf("send_obs", w * n_links, torch.int32)
         send_desc = self._buf("send_desc", 6 * n_runs, torch.int32)
         self.engine.runs_pack(world, send_obs.data_ptr(), send_desc.data_ptr())
-        return send_obs[:2 * n_links].view(-1, 2), send_desc[:6 * n_runs].view(-1, 6)
+        return send_obs[:w * n_links].view(-1, w), send_desc[:6 * n_runs].view(-1, 6)
 
-    def recv_run_buffers(self, n_links, n_runs, n_fishy):
+    def recv_run_buffers(self, n_links, n_runs, n_fishy, w=2):
         torch = self.torch
-        return (self._buf("recv_obs", 2 * n_links, torch.int32)[:2 * n_links].view(-1, 2),
+        return (self._buf("recv_obs", w * n_links, torch.int32)[:w * n_links].view(-1, w),
                 self._buf("recv_desc", 6 * n_runs, torch.int32)[:6 * n_runs].view(-1, 6),
                 self._buf("recv_f", n_fishy, torch.int64)[:n_fishy])
 
@@ -349,16 +353,17 @@ class DistributedGraphBuild(object):
         rl, rr, rf = LC[:, rank], RC[:, rank], FC[:, rank]
         if int(n_by_rank.sum()) >= 2 ** 32 or int(LC.sum(axis=0).max()) >= 2 ** 30:
             raise ValueError("run-level exchange: more than 2^32 links in the library or 2^30 on one rank")
+        w = self.b.obs_words(p) if hasattr(self.b, "obs_words") else 2
         if self.exchange_peer:
             try:
-                recv_obs, recv_desc, recv_f = self._transport_peer(LC, RC, FC, send_f, fc)
+                recv_obs, recv_desc, recv_f = self._transport_peer(LC, RC, FC, send_f, fc, w)
             except _SymmUnavailable as exc:   # no peer mapping on this box: every rank raises alike (collective setup)
                 import warnings
                 warnings.warn("symmetric memory unavailable (%s): NCCL all-to-all instead" % exc)
                 self.exchange_peer = False
         if not self.exchange_peer:
-            send_obs, send_desc = self.b.pack(world, int(lc.sum()), int(rc.sum()))
-            recv_obs, recv_desc, recv_f = self.b.recv_run_buffers(int(rl.sum()), int(rr.sum()), int(rf.sum()))
+            send_obs, send_desc = self.b.pack(world, int(lc.sum()), int(rc.sum()), w)
+            recv_obs, recv_desc, recv_f = self.b.recv_run_buffers(int(rl.sum()), int(rr.sum()), int(rf.sum()), w)
             self._mark("pack")
             dist.all_to_all_single(recv_obs, send_obs, output_split_sizes=rl.tolist(), input_split_sizes=lc.tolist(), group=self.group)
             dist.all_to_all_single(recv_desc, send_desc, output_split_sizes=rr.tolist(), input_split_sizes=rc.tolist(), group=self.group)
@@ -378,13 +383,13 @@ class DistributedGraphBuild(object):
                          last_call=global_last, first_call=global_first, halo=halos[rank])
         return sizes
 
-    def _transport_peer(self, LC, RC, FC, send_f, fc):
+    def _transport_peer(self, LC, RC, FC, send_f, fc, w):
         """The exchange fused into the pack kernel: every rank owns peer-mapped receive buffers (symmetric
         memory); the W x W count matrix gives every sender its offset inside every receiver."""
         world, rank = self.world, self.rank
         torch = self.b.torch
         try:
-            obs_t, obs_h = self.b.symm_buffer("obs", 2 * int(LC.sum(axis=0).max()) + 2, torch.int32, self.group)
+            obs_t, obs_h = self.b.symm_buffer("obs", w * int(LC.sum(axis=0).max()) + 2, torch.int32, self.group)
             desc_t, desc_h = self.b.symm_buffer("desc", 6 * int(RC.sum(axis=0).max()) + 6, torch.int32, self.group)
             f_t, f_h = self.b.symm_buffer("fishy", int(FC.sum(axis=0).max()) + 1, torch.int64, self.group)
         except Exception as exc:
@@ -392,7 +397,7 @@ class DistributedGraphBuild(object):
         link_off = LC[:rank].sum(axis=0)   # my segment's start inside every destination's buffers
         run_off = RC[:rank].sum(axis=0)
         f_off = FC[:rank].sum(axis=0)
-        obs_ptrs = [int(obs_h.buffer_ptrs[d]) + 8 * int(link_off[d]) for d in range(world)]
+        obs_ptrs = [int(obs_h.buffer_ptrs[d]) + 4 * w * int(link_off[d]) for d in range(world)]
         desc_ptrs = [int(desc_h.buffer_ptrs[d]) + 24 * int(run_off[d]) for d in range(world)]
         obs_h.barrier(channel=0)   # every rank is done reading the buffers of the previous step
         self.b.pack_peer(world, obs_ptrs, desc_ptrs)
@@ -403,7 +408,7 @@ class DistributedGraphBuild(object):
         obs_h.barrier(channel=0)   # all stores have landed
         self._mark("pack+exchange")
         rl, rr, rf = LC[:, rank], RC[:, rank], FC[:, rank]
-        return obs_t[:2 * int(rl.sum())].view(-1, 2), desc_t[:6 * int(rr.sum())].view(-1, 6), f_t[:int(rf.sum())]
+        return obs_t[:w * int(rl.sum())].view(-1, w), desc_t[:6 * int(rr.sum())].view(-1, 6), f_t[:int(rf.sum())]
 
     # -- results ------------------------------------------------------------------------------------
     def fetch_local(self, view=False):

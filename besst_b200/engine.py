@@ -150,6 +150,9 @@ class CudaEngine(object):
     def runs_pack(self, world, out_obs_ptr, out_desc_ptr):
         self._check(self._L.besst_runs_pack(self._ctx, int(world), out_obs_ptr, out_desc_ptr), "besst_runs_pack")
 
+    def runs_obs_bytes(self, params):
+        return int(self._L.besst_runs_obs_bytes(C.byref(params)))
+
     def runs_pack_peer(self, world, obs_ptrs, desc_ptrs):
         """obs_ptrs[d] / desc_ptrs[d]: device addresses (ints) of this rank's segment in destination d's buffers."""
         a = (C.c_void_p * world)(*[int(p) for p in obs_ptrs])

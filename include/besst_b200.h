@@ -258,10 +258,13 @@ typedef struct besst_run_desc {
     uint32_t block;   /* block of the source's stream it comes from: BAM order among the runs of one edge */
 } besst_run_desc;
 int besst_links_group(besst_ctx* ctx, int64_t* n_runs);
+/* bytes per link of the exchanged observations: 4 (obs_u | obs_v << 16) when 0 < ins_size_threshold <= 65535
+ * -- every accepted observation is below the threshold, CreateGraph.py:840 -- else 8 (two int32) */
+int besst_runs_obs_bytes(const besst_lib_params* params);
 /* per destination: links and runs this rank will send (host arrays of `world` entries) */
 int besst_runs_route(besst_ctx* ctx, int32_t world, int64_t* link_counts, int64_t* run_counts);
-/* fill caller-provided DEVICE buffers, destination-major: out_obs = (obs_u, obs_v) int32 pairs of
- * sum(link_counts) links, out_desc = sum(run_counts) descriptors */
+/* fill caller-provided DEVICE buffers, destination-major: out_obs = the observations of sum(link_counts) links
+ * (besst_runs_obs_bytes each), out_desc = sum(run_counts) descriptors */
 int besst_runs_pack(besst_ctx* ctx, int32_t world, int32_t* out_obs_device, besst_run_desc* out_desc_device);
 /* the same, fused with the exchange: obs_ptrs[d] / desc_ptrs[d] (host arrays of `world` DEVICE pointers) address
  * the start of this rank's segment inside destination d's receive buffers -- peer-mapped memory of GPU d

@@ -5,6 +5,8 @@ N=${1:-2}; TAG=${2:-multi$N}
 OUT=gpurun_out/$TAG
 mkdir -p $OUT
 nvidia-smi -L > $OUT/smi.txt
+# wide observations (ins_size_threshold > 65535): the int32-pair format of the exchange
+WIDE=1
 run() { timeout -s KILL 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port $1 "${@:2}"; }
 PORT=29540
 for mode in ${MODES:-peer runs tuples}; do
@@ -14,6 +16,10 @@ for mode in ${MODES:-peer runs tuples}; do
     echo "$mode $cfg: $(grep -E 'DIST_CHECK_OK|Error|error|unavailable' $OUT/dist_check_${mode}_$cfg.log | tail -2)"
   done
 done
+if [ "$WIDE" == "1" ]; then
+  run 29559 tests/dist_check.py small_mp 70000 > $OUT/dist_check_wide.log 2>&1
+  echo "peer wide: $(grep -E 'DIST_CHECK_OK|Error|error' $OUT/dist_check_wide.log | tail -2)"
+fi
 show() { python - <<PY
 import json
 try:

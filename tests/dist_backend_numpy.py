@@ -123,7 +123,7 @@ class NumpyBackend(object):
         forder = np.argsort(fd, kind="stable")
         return torch.from_numpy(self.fishy[forder].view(np.int64).copy()), np.bincount(fd, minlength=world).astype(np.int64)
 
-    def pack(self, world, n_links, n_runs):
+    def pack(self, world, n_links, n_runs, w=2):
         # any placement inside a destination segment is legal (the device uses atomics): use reverse run order here
         order = np.lexsort((-np.arange(len(self.run_dest)), self.run_dest))
         send_obs = np.zeros((n_links, 2), np.int32)
@@ -139,7 +139,7 @@ class NumpyBackend(object):
             pos += cnt
         return torch.from_numpy(send_obs), torch.from_numpy(send_desc)
 
-    def recv_run_buffers(self, n_links, n_runs, n_fishy):
+    def recv_run_buffers(self, n_links, n_runs, n_fishy, w=2):
         return (torch.zeros((n_links, 2), dtype=torch.int32), torch.zeros((n_runs, 6), dtype=torch.int32),
                 torch.zeros(n_fishy, dtype=torch.int64))
 

@@ -26,6 +26,7 @@ from besst_b200.engine import CudaEngine  # noqa: E402
 
 def main():
     config = sys.argv[1] if len(sys.argv) > 1 else "small_mp_cont"
+    threshold = float(sys.argv[2]) if len(sys.argv) > 2 else None   # e.g. 70000: observations travel as int32 pairs, not 2 x u16
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
@@ -35,7 +36,7 @@ def main():
     dist.barrier()
     lib = synth.make_config(config)
     batch = lib.to_batch()
-    params = abi.make_params(lib.orientation, 11, 100.0, lib.mu, lib.sigma, lib.mu + 6 * lib.sigma)
+    params = abi.make_params(lib.orientation, 11, 100.0, lib.mu, lib.sigma, threshold if threshold else lib.mu + 6 * lib.sigma)
     objs = helpers.later_library_objects(batch.references, batch.lengths, lib.mu + 4 * lib.sigma, seed=3)
     table = helpers.table_for(batch, objs)
     n = len(batch)
