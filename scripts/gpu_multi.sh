@@ -6,7 +6,7 @@ OUT=gpurun_out/$TAG
 mkdir -p $OUT
 nvidia-smi -L > $OUT/smi.txt
 # wide observations (ins_size_threshold > 65535): the int32-pair format of the exchange
-WIDE=1
+WIDE=${WIDE:-1}
 run() { timeout -s KILL 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port $1 "${@:2}"; }
 PORT=29540
 for mode in ${MODES:-peer runs tuples}; do
