@@ -194,7 +194,11 @@ extern "C" besst_bam* besst_bam_read(const char* path, int32_t n_threads, int64_
     if (!scan_blocks(f, fsize, &blocks, &why)) return fail(why);
     B->stats.blocks = (int64_t)blocks.size();
 
-    const uint64_t WINDOW = 64ull << 20;   // inflated bytes per window
+    uint64_t WINDOW = 64ull << 20;   // inflated bytes per window
+    if (const char* e = getenv("BESST_BAMIO_WINDOW")) {   // tests: force many small windows
+        const long long v = atoll(e);
+        if (v > 0) WINDOW = (uint64_t)v;
+    }
     // inflated bytes not consumed yet (header / partial record at the front); a raw buffer: no zero fill on growth
     struct Pend {
         unsigned char* p = nullptr;
@@ -296,10 +300,62 @@ extern "C" besst_bam* besst_bam_read(const char* path, int32_t n_threads, int64_
             header_done = true;
         }
 
-        // ---- record boundaries of this window (sequential hop over block_size) --------------------------
+        // ---- record boundaries of this window ------------------------------------------------------------
+        // The hop over the block_size fields is a dependent chain of cache misses (~80 ns each): sequentially it
+        // costs more than the whole inflate.  htslib flushes a BGZF block rather than split a record across two
+        // (bgzf_flush_try), so in practice every block starts at a record boundary: the threads hop through
+        // disjoint groups of blocks in parallel and the assumption is VERIFIED -- every group's chain must end
+        // exactly where the next group starts -- else this window is scanned sequentially.
         const double t1 = now();
-        offs.clear();
-        {
+        const int64_t n0 = B->n;
+        std::vector<std::vector<uint32_t>> toffs((size_t)n_threads);
+        std::vector<int64_t> tbase((size_t)n_threads + 1, 0);
+        bool parallel_scan = false;
+        if (max_records < 0 && n_threads > 1) {
+            // block starts at or after `cur`, plus the end of the window
+            std::vector<uint64_t> starts;
+            for (size_t k = 0; k < dst_off.size(); ++k)
+                if (dst_off[k] >= cur && blocks[b0 + k].usize > 0) starts.push_back(dst_off[k]);
+            const uint64_t wend = pend.size();
+            if (!starts.empty() && starts[0] == cur) {
+                starts.push_back(wend);
+                const size_t nb = starts.size() - 1;
+                std::vector<size_t> gfirst((size_t)n_threads + 1);
+                for (int t = 0; t <= n_threads; ++t) gfirst[(size_t)t] = nb * (size_t)t / (size_t)n_threads;
+                std::atomic<int> mismatch(0);
+                auto hop_worker = [&](int t) {
+                    const size_t g0 = gfirst[(size_t)t], g1 = gfirst[(size_t)t + 1];
+                    if (g0 == g1) return;
+                    const unsigned char* d = pend.data();
+                    uint64_t o = starts[g0];
+                    const uint64_t end = starts[g1];
+                    std::vector<uint32_t>& out = toffs[(size_t)t];
+                    out.reserve((size_t)((end - o) / 200 + 16));
+                    while (o + 4 <= end) {
+                        const int64_t bs = rdi32(d + o);
+                        if (bs < 32 || o + 4 + (uint64_t)bs > end) break;
+                        out.push_back((uint32_t)o);
+                        o += 4 + (uint64_t)bs;
+                    }
+                    if (o != end) mismatch.store(1);
+                };
+                {
+                    std::vector<std::thread> th;
+                    for (int t = 1; t < n_threads; ++t) th.emplace_back(hop_worker, t);
+                    hop_worker(0);
+                    for (auto& x : th) x.join();
+                }
+                if (!mismatch.load()) {
+                    parallel_scan = true;
+                    for (int t = 0; t < n_threads; ++t) tbase[(size_t)t + 1] = tbase[(size_t)t] + (int64_t)toffs[(size_t)t].size();
+                    cur = wend;
+                } else {
+                    for (auto& v : toffs) v.clear();
+                }
+            }
+        }
+        if (!parallel_scan) {   // sequential hop; the decode below splits the records evenly
+            offs.clear();
             const unsigned char* d = pend.data();
             const size_t have = pend.size();
             while (cur + 4 <= have) {
@@ -310,8 +366,10 @@ extern "C" besst_bam* besst_bam_read(const char* path, int32_t n_threads, int64_
                 cur += 4 + (size_t)bs;
                 if (max_records >= 0 && B->n + (int64_t)offs.size() >= max_records) { stop = true; break; }
             }
+            const int64_t mm = (int64_t)offs.size();
+            for (int t = 0; t <= n_threads; ++t) tbase[(size_t)t] = mm * t / n_threads;
         }
-        const int64_t m = (int64_t)offs.size(), n0 = B->n;
+        const int64_t m = tbase[(size_t)n_threads];
         if (!B->tid.ensure(n0 + m, n0) || !B->mtid.ensure(n0 + m, n0) || !B->pos.ensure(n0 + m, n0) || !B->mpos.ensure(n0 + m, n0) ||
             !B->tlen.ensure(n0 + m, n0) || !B->qlen.ensure(n0 + m, n0) || !B->flag.ensure(n0 + m, n0) || !B->mapq.ensure(n0 + m, n0))
             return fail("out of memory for the record columns");
@@ -319,13 +377,14 @@ extern "C" besst_bam* besst_bam_read(const char* path, int32_t n_threads, int64_
         if (!B->rlen.ensure(head_new > 0 ? head_new : 1, B->n_head) || !B->alen.ensure(head_new > 0 ? head_new : 1, B->n_head))
             return fail("out of memory for the record columns");
 
-        // ---- decode: thread t takes records [m*t/T, m*(t+1)/T) ------------------------------------------
+        // ---- decode: thread t takes the records it found (parallel scan) or an even share -----------------
         std::atomic<int> bad_rec(0);
         auto decode_worker = [&](int t) {
-            const int64_t r0 = m * t / n_threads, r1 = m * (t + 1) / n_threads;
+            const int64_t r0 = tbase[(size_t)t], r1 = tbase[(size_t)t + 1];
+            const uint32_t* my = parallel_scan ? toffs[(size_t)t].data() - r0 : offs.data();
             const unsigned char* d = pend.data();
             for (int64_t r = r0; r < r1; ++r) {
-                const unsigned char* p = d + offs[(size_t)r];
+                const unsigned char* p = d + my[r];
                 const int64_t bs = rdi32(p);
                 const uint32_t l_read_name = p[12], n_cigar = rd16(p + 16);
                 const int32_t l_seq = rdi32(p + 20);

@@ -81,6 +81,18 @@ def test_native_reader_equals_python_reader(tmp_path, n, block_bytes, threads):
         assert len(part) == 100 and np.array_equal(part.pos, py.pos[:100])
 
 
+def test_records_straddling_inflate_windows(tmp_path, monkeypatch):
+    """The reader inflates a window of blocks at a time and carries a partial record into the next one."""
+    rng = np.random.default_rng(11)
+    refs = [("c%d" % i, 5000 + i) for i in range(9)]
+    path = str(tmp_path / "w.bam")
+    write_bam(path, refs, _random_records(rng, 8000, len(refs)), block_bytes=1500)
+    py = bamio.read_bam(path)
+    for window in (1, 4000, 50000):   # 1: every block is its own window
+        monkeypatch.setenv("BESST_BAMIO_WINDOW", str(window))
+        _assert_same(bamio.read_bam_native(path, threads=3), py)
+
+
 def test_native_reader_rejects_garbage(tmp_path):
     p = tmp_path / "x.bam"
     p.write_bytes(b"this is not a BAM file, not even gzip" * 10)
