@@ -26,11 +26,18 @@
  *   samples exist (libmetrics.py:311-314).
  *   besst_trsk_sd_batch      param_est.tr_sk_std_dev at a caller-given gap
  *                            (CreateGraph.py:555 signature)
- *   besst_links_extract /    the two halves of besst_graph_build on either side
- *   besst_links_to_graph     of the multi-GPU all-to-all;
- *   besst_links_partition    stable bucketing of the extracted tuples by
- *                            destination rank = hash(edge) mod world, the send
- *                            buffer of that all-to-all
+ *   besst_graph_view         the same result as views of pinned buffers owned by the ctx
+ *   besst_gapest_func_batch  param_est.funcDGeneral, what PreCalcMLvaluesOfdLongContigs
+ *                            tabulates (MakeScaffolds.py:68)
+ *   besst_links_extract /    the two halves of besst_graph_build on either side of the
+ *   besst_links_group /      multi-GPU exchange (no reference counterpart,
+ *   besst_runs_route /       the reference is one process): the rank's links are grouped
+ *   besst_runs_pack[_peer] / into runs (edge x 2048-link block), whole runs are routed by
+ *   besst_runs_to_graph      hash(edge) mod world -- through NCCL or stored straight into
+ *                            the destination GPU's peer-mapped buffers -- and the receiver
+ *                            merges runs into its share of the CSR
+ *   besst_links_partition /  the tuple-level variant of the same exchange (fallback for
+ *   besst_links_to_graph     link streams without local order; any caller-made tuple array)
  *
  * Conventions: plain C; all pointers are caller-owned for the duration of the
  * call; nothing is retained after return except inside the ctx; return 0 on
