@@ -1411,11 +1411,10 @@ int besst_group_tuples(besst_ctx* ctx, const besst_link_tuple* d_tuples, int64_t
     if (n == 0) return BESST_OK;
     u32* gstate = ctx->run_state.as<u32>();
     BESST_CUDA_TRY(ctx, cudaMemsetAsync(gstate, 0, 64, ctx->stream));
-    static bool attr_done = false;
-    if (!attr_done) {
+    if (!ctx->attr_group_done) {   // per ctx (= per device): function attributes are set on the current device
         cudaFuncSetAttribute(k_group_blocks<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(GroupSmem));
         cudaFuncSetAttribute(k_group_blocks<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(GroupSmem));
-        attr_done = true;
+        ctx->attr_group_done = true;
     }
     {
         KTimer kt(ctx, BESST_K_GROUP);

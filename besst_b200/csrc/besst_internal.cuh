@@ -128,6 +128,7 @@ struct besst_ctx {
     int64_t n_runs = 0;        // run descriptors of the last besst_links_group
     int run_block_bits = 0;
     bool have_runs = false;
+    bool attr_group_done = false;
     bool have_graph = false;
     besst_lib_params last_params;
     besst_lib_params extract_params;   // of the last besst_links_extract

@@ -266,12 +266,9 @@ int sort_impl(besst_ctx* ctx, const besst_link_tuple* tuples, int bv, int idx_bi
     BESST_CUDA_TRY(ctx, cudaGetLastError());
 
     const size_t smem = sizeof(SweepSmem<KeyT, HAS_VAL>);
-    static bool attr_done = false;
-    if (!attr_done) {
-        if (FROM_TUPLES) cudaFuncSetAttribute(k_radix_sweep<KeyT, FROM_TUPLES, HAS_VAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        cudaFuncSetAttribute(k_radix_sweep<KeyT, false, HAS_VAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        attr_done = true;
-    }
+    // every call: cheap, and a process may drive several devices (one ctx each) with the same kernels
+    if (FROM_TUPLES) cudaFuncSetAttribute(k_radix_sweep<KeyT, FROM_TUPLES, HAS_VAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(k_radix_sweep<KeyT, false, HAS_VAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     int per_sm = 0;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_radix_sweep<KeyT, false, HAS_VAL>, RS_THREADS, smem);
     if (per_sm < 1) per_sm = 1;
