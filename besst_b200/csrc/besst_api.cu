@@ -58,6 +58,7 @@ extern "C" void besst_destroy(besst_ctx* ctx) {
     for (DBuf* b : bufs) b->release();
     for (DBuf& b : ctx->rec_i32) b.release();
     for (HBuf& b : ctx->h_out) b.release();
+    if (ctx->h_scalars) cudaFreeHost(ctx->h_scalars);
     for (cudaEvent_t e : ctx->slice_events) cudaEventDestroy(e);
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);

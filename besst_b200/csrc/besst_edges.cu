@@ -1429,7 +1429,8 @@ int besst_group_tuples(besst_ctx* ctx, const besst_link_tuple* d_tuples, int64_t
                 ctx->tile_state.as<u64>(), ctx->n_rec_tiles, ctx->block_tile0.as<u32>());
     }
     BESST_CUDA_TRY(ctx, cudaGetLastError());
-    u32 hs[2] = {0, 0};
+    u32* const hs = reinterpret_cast<u32*>(ctx->host_scalars());
+    if (!hs) { ctx->err = "pinned host scratch allocation failed"; return BESST_E_NOMEM; }
     BESST_CUDA_TRY(ctx, cudaMemcpyAsync(hs, gstate, 8, cudaMemcpyDeviceToHost, ctx->stream));
     BESST_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     *n_runs = hs[0];
@@ -1704,9 +1705,11 @@ static int launch_graph_impl(besst_ctx* ctx, const besst_lib_params& p, const be
             u64* bsums = ctx->heads.as<u64>();
             { KTimer kt(ctx, BESST_K_RUNS); k_run_count<<<rblocks, RS_T, 0, ctx->stream>>>(rkeys, rvals, ctx->run_cnt.as<u32>(), R, low_bits, bsums); }
             { KTimer kt(ctx, BESST_K_RUNS); k_scan_blocks64<<<1, 1024, 0, ctx->stream>>>(bsums, rblocks); }
-            u64 tot = 0;
-            BESST_CUDA_TRY(ctx, cudaMemcpyAsync(&tot, bsums + rblocks, 8, cudaMemcpyDeviceToHost, ctx->stream));
+            u64* const hp = reinterpret_cast<u64*>(ctx->host_scalars());
+            if (!hp) { ctx->err = "pinned host scratch allocation failed"; return BESST_E_NOMEM; }
+            BESST_CUDA_TRY(ctx, cudaMemcpyAsync(hp, bsums + rblocks, 8, cudaMemcpyDeviceToHost, ctx->stream));
             BESST_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+            const u64 tot = hp[0];
             rc = alloc_edges((int64_t)(tot >> 32));
             if (rc) return rc;
             if ((int64_t)(tot & 0xffffffffull) != n) { ctx->err = "run-merge bucket: link count mismatch"; return BESST_E_STATE; }
@@ -1808,14 +1811,26 @@ static int launch_graph_impl(besst_ctx* ctx, const besst_lib_params& p, const be
         const char* ks_env = getenv("BESST_KS");
         const bool block_ks = !(ks_env && ks_env[0] == 'g') && value_bits + 10 <= 32;   // local edge ids take <= 10 bits
         const int big_thr = block_ks ? KB_G : 0;
+        // both link spaces are sized with ONE host round trip: the counts of the small-edge space and of the rest
+        BESST_CUDA_TRY(ctx, ctx->ll_off.ensure(4 * (Ez + 2)));
+        BESST_CUDA_TRY(ctx, ctx->block_sums.ensure(4 * (size_t)(std::max(ls_blocks, n_blocks) + 2)));
+        u64* const hp = reinterpret_cast<u64*>(ctx->host_scalars());
+        if (!hp) { ctx->err = "pinned host scratch allocation failed"; return BESST_E_NOMEM; }
+        hp[0] = hp[1] = 0;
         if (block_ks) {
             BESST_CUDA_TRY(ctx, ctx->heads.ensure(8 * (size_t)(ls_blocks + 2)));
+            u64* bs0 = ctx->heads.as<u64>();
+            { KTimer kt(ctx, BESST_K_EDGE_SCORE); k_llc_count<<<ls_blocks, LS_THREADS, 0, ctx->stream>>>(EA.flags, EA.nr, E, KB_G, bs0); }
+            { KTimer kt(ctx, BESST_K_EDGE_SCORE); k_scan_blocks64<<<1, 1024, 0, ctx->stream>>>(bs0, ls_blocks); }
+            BESST_CUDA_TRY(ctx, cudaMemcpyAsync(&hp[0], bs0 + ls_blocks, 8, cudaMemcpyDeviceToHost, ctx->stream));
+        }
+        { KTimer kt(ctx, BESST_K_EDGE_SCORE); k_ll_count<<<ls_blocks, LS_THREADS, 0, ctx->stream>>>(EA.flags, EA.nr, E, big_thr, ctx->block_sums.as<u32>()); }
+        { KTimer kt(ctx, BESST_K_EDGE_SCORE); k_scan_blocks<<<1, 1024, 0, ctx->stream>>>(ctx->block_sums.as<u32>(), ls_blocks); }
+        BESST_CUDA_TRY(ctx, cudaMemcpyAsync(&hp[1], ctx->block_sums.as<u32>() + ls_blocks, 4, cudaMemcpyDeviceToHost, ctx->stream));
+        BESST_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+        if (block_ks) {
             u64* bs = ctx->heads.as<u64>();
-            { KTimer kt(ctx, BESST_K_EDGE_SCORE); k_llc_count<<<ls_blocks, LS_THREADS, 0, ctx->stream>>>(EA.flags, EA.nr, E, KB_G, bs); }
-            { KTimer kt(ctx, BESST_K_EDGE_SCORE); k_scan_blocks64<<<1, 1024, 0, ctx->stream>>>(bs, ls_blocks); }
-            u64 tot = 0;
-            BESST_CUDA_TRY(ctx, cudaMemcpyAsync(&tot, bs + ls_blocks, 8, cudaMemcpyDeviceToHost, ctx->stream));
-            BESST_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+            const u64 tot = hp[0];
             const int64_t n_small = (int64_t)(tot >> 32), n_small_links = (int64_t)(tot & 0xffffffffull);
             n_ll_total += n_small_links;
             if (n_small > 0) {
@@ -1836,15 +1851,8 @@ static int launch_graph_impl(besst_ctx* ctx, const besst_lib_params& p, const be
 
         // ---- the rest (edges with more links; every LL edge when the block path is off): LL link space,
         // two device-wide key sorts, co-ranking evaluation ------------------------------------------------
-        BESST_CUDA_TRY(ctx, ctx->ll_off.ensure(4 * (Ez + 2)));
-        BESST_CUDA_TRY(ctx, ctx->block_sums.ensure(4 * (size_t)(std::max(ls_blocks, n_blocks) + 2)));
         u32* ll_off = ctx->ll_off.as<u32>();
-        u32 n_ll32 = 0;
-        { KTimer kt(ctx, BESST_K_EDGE_SCORE); k_ll_count<<<ls_blocks, LS_THREADS, 0, ctx->stream>>>(EA.flags, EA.nr, E, big_thr, ctx->block_sums.as<u32>()); }
-        { KTimer kt(ctx, BESST_K_EDGE_SCORE); k_scan_blocks<<<1, 1024, 0, ctx->stream>>>(ctx->block_sums.as<u32>(), ls_blocks); }
-        BESST_CUDA_TRY(ctx, cudaMemcpyAsync(&n_ll32, ctx->block_sums.as<u32>() + ls_blocks, 4, cudaMemcpyDeviceToHost, ctx->stream));
-        BESST_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-        const int64_t n_ll = n_ll32;
+        const int64_t n_ll = (int64_t)(hp[1] & 0xffffffffull);
         n_ll_total += n_ll;
         ctx->n_ll_links = n_ll_total;
         if (n_ll > 0) {

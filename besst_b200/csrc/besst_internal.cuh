@@ -129,6 +129,13 @@ struct besst_ctx {
     int run_block_bits = 0;
     bool have_runs = false;
     bool attr_group_done = false;
+    // pinned host words for the size read-backs between kernels (pageable targets go through a bounce buffer)
+    uint64_t* h_scalars = nullptr;
+    uint64_t* host_scalars() {
+        if (!h_scalars && cudaHostAlloc(reinterpret_cast<void**>(&h_scalars), 64 * sizeof(uint64_t), cudaHostAllocDefault) != cudaSuccess)
+            h_scalars = nullptr;
+        return h_scalars;
+    }
     bool have_graph = false;
     besst_lib_params last_params;
     besst_lib_params extract_params;   // of the last besst_links_extract

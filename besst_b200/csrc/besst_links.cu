@@ -1007,8 +1007,9 @@ int besst_extract_finish(besst_ctx* ctx, const besst_lib_params& p, int64_t n, b
         const int64_t halo[2] = {p.halo_prev_obs1, p.halo_prev_obs2};
         BESST_CUDA_TRY(ctx, cudaMemcpyAsync(counters + BESST_CNT_LAST_OBS1, halo, sizeof(halo), cudaMemcpyHostToDevice, ctx->stream));
     }
-    u64 g[2] = {0, 0};
-    BESST_CUDA_TRY(ctx, cudaMemcpyAsync(g, globals, sizeof(g), cudaMemcpyDeviceToHost, ctx->stream));
+    u64* const g = reinterpret_cast<u64*>(ctx->host_scalars());   // pinned: no bounce buffer on the size read-backs
+    if (!g) { ctx->err = "pinned host scratch allocation failed"; return BESST_E_NOMEM; }
+    BESST_CUDA_TRY(ctx, cudaMemcpyAsync(g, globals, 16, cudaMemcpyDeviceToHost, ctx->stream));
     BESST_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     ctx->n_tuples = (int64_t)g[0];
     ctx->n_fishy_keys = (int64_t)g[1];
