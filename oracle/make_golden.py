@@ -4,9 +4,9 @@ Runs the reference's own, unmodified bytecode (oracle/ref_harness.py:
 /root/reference/BESST/{libmetrics,CreateGraph}.py with pysam / networkx-1.x /
 mathstats stand-ins) on
 
-  * a committed slice of the reference's testdata/testset1/mapped.bam (the first
-    N records, decoded by besst_b200/bamio.py) with the two Travis command
-    lines (.travis.yml:14-15) and once without -m/-s so libmetrics is exercised;
+  * committed slices of the reference's testdata/testset1/mapped.bam and testset2/mapped.bam (the
+    first N records, decoded by besst_b200/bamio.py) with the two Travis command lines
+    (.travis.yml:14-15) and without -m/-s so libmetrics is exercised;
   * seeded synthetic libraries (besst_b200/synth.py) as first and later libraries,
     with the option combinations the record loop branches on,
 
@@ -36,12 +36,15 @@ from besst_b200 import bamio, synth  # noqa: E402
 
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 TESTSET1_RECORDS = 300000
+TESTSET2_RECORDS = 250000
 
 # name -> (input, options, later-library seed or None, run libmetrics)
 CASES = {
     "testset1_travis": ("testset1", dict(orientation="fr", mean=4000, stddev=500, minsize=3000, threshold=6000), None, True),
     "testset1_travis_no_score": ("testset1", dict(orientation="fr", mean=4000, stddev=500, minsize=3000, threshold=6000, no_score=True), None, True),
     "testset1_auto": ("testset1", dict(orientation="fr"), None, True),
+    "testset2_auto": ("testset2", dict(orientation="fr"), None, True),
+    "testset2_given": ("testset2", dict(orientation="fr", mean=2800, stddev=350, minsize=4600, threshold=4500), None, True),
     "small_pe_auto": ("small_pe", dict(orientation="fr"), None, True),
     "small_mp_auto": ("small_mp", dict(orientation="rf"), None, True),
     "small_mp_cont_auto": ("small_mp_cont", dict(orientation="rf"), None, True),
@@ -55,8 +58,8 @@ CASES = {
 
 
 def load_input(name):
-    if name == "testset1":
-        path = os.path.join(GOLDEN, "testset1_head.npz")
+    if name in ("testset1", "testset2"):
+        path = os.path.join(GOLDEN, name + "_head.npz")
         from besst_b200.records import RecordBatch
         return RecordBatch.load(path)
     return synth.make_config(name).to_batch()
@@ -66,6 +69,8 @@ def make_testset1_fixture():
     bam = os.path.join(ref_harness.REFERENCE_ROOT, "testdata", "testset1", "mapped.bam")
     batch = bamio.read_bam(bam, max_records=TESTSET1_RECORDS)
     batch.save(os.path.join(GOLDEN, "testset1_head.npz"))
+    bam2 = os.path.join(ref_harness.REFERENCE_ROOT, "testdata", "testset2", "mapped.bam")
+    bamio.read_bam(bam2, max_records=TESTSET2_RECORDS).save(os.path.join(GOLDEN, "testset2_head.npz"))
     return batch
 
 
