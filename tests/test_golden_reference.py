@@ -40,8 +40,8 @@ _inputs = {}
 
 def load_input(name):
     if name not in _inputs:
-        if name == "testset1":
-            _inputs[name] = RecordBatch.load(os.path.join(GOLDEN, "testset1_head.npz"))
+        if name in ("testset1", "testset2"):
+            _inputs[name] = RecordBatch.load(os.path.join(GOLDEN, name + "_head.npz"))
         else:
             _inputs[name] = synth.make_config(name).to_batch()
     return _inputs[name]
