@@ -27,7 +27,7 @@ from . import e_nr_links
 from .contig_table import ContigTable
 from .normal import MaxObsDistr
 from .objects import classes
-from .records import as_batch
+from .records import as_batch, as_file
 
 
 def _new_graph():
@@ -372,6 +372,7 @@ def engine_params(param, halo=(-1, -1)):
 
 
 def PE(Contigs, Scaffolds, Information, C_dict, param, small_contigs, small_scaffolds, bam_file, engine=None):
+    bam_file = as_file(bam_file)   # a path: decoded once by the native ingest library (shared with get_metrics)
     G = _new_graph()
     G_prime = _new_graph()
     print('Parsing BAM file...', file=Information)

@@ -23,7 +23,7 @@ import numpy as np
 
 from . import abi
 from .contig_table import largest_reference_mask
-from .records import as_batch
+from .records import as_batch, as_file
 
 ISIZE_DICT_CAP = 1 << 22   # bins of param.empirical_distribution fetched from the engine
 
@@ -69,6 +69,7 @@ def metric_rows(lengths):
 
 
 def get_metrics(bam_file, param, Information, engine=None):
+    bam_file = as_file(bam_file)   # a path: decoded once by the native ingest library
     cont_names = bam_file.references
     cont_lengths = [int(x) for x in bam_file.lengths]
     param.lognormal = False

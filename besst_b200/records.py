@@ -143,6 +143,28 @@ class BatchFile(object):
         return iter(())
 
 
+_open_cache = {}
+
+
+def as_file(bam_file):
+    """What the drop-in entry points do with their `bam_file` argument first: a path becomes a
+    BatchFile over the natively decoded records (libbesst_bamio.so) -- cached per path, because
+    runBESST hands the same library to get_metrics and then to PE -- anything else passes through."""
+    if isinstance(bam_file, (str, bytes)) or hasattr(bam_file, "__fspath__"):
+        import os
+        key = os.path.abspath(os.fsdecode(bam_file))
+        st = os.stat(key)
+        stamp = (st.st_size, st.st_mtime_ns)
+        hit = _open_cache.get(key)
+        if hit is None or hit[0] != stamp:
+            from .bamio import read_bam_native
+            _open_cache.clear()   # one library at a time, like the reference's loop (runBESST:143-231)
+            hit = (stamp, BatchFile(read_bam_native(key)))
+            _open_cache[key] = hit
+        return hit[1]
+    return bam_file
+
+
 def as_batch(bam_file):
     """RecordBatch behind a `bam_file` argument: a RecordBatch, a path to a BAM file (decoded by
     libbesst_bamio.so), anything carrying `.record_batch`, or a pysam-like iterable of AlignedRead."""

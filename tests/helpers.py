@@ -233,7 +233,7 @@ class FakeSeq(object):
         return "N"
 
 
-def run_dropin(batch, opts, engine, state=None, run_libmetrics=True, fasta_lengths=None):
+def run_dropin(batch, opts, engine, state=None, run_libmetrics=True, fasta_lengths=None, bam_path=None):
     """One library pass through the drop-in entry points (besst_b200.libmetrics.get_metrics
     + besst_b200.CreateGraph.PE) with `engine` behind them.  Mirrors
     oracle/ref_harness.run_reference so that the two outputs compare field by field."""
@@ -255,7 +255,7 @@ def run_dropin(batch, opts, engine, state=None, run_libmetrics=True, fasta_lengt
         small_contigs, small_scaffolds = state["small_contigs"], state["small_scaffolds"]
         param.scaffold_indexer = state["scaffold_indexer"]
         param.tot_assembly_length = state["tot_assembly_length"]
-    bam_file = BatchFile(batch)
+    bam_file = BatchFile(batch) if bam_path is None else bam_path   # a path goes through the native ingest library
     import contextlib
     with contextlib.redirect_stdout(io.StringIO()):
         if run_libmetrics:

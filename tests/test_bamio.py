@@ -118,3 +118,28 @@ def test_native_reader_on_reference_testset1():
     full = bamio.read_bam_native(REF_BAM)
     assert len(full) == 1999958 and len(full.references) == 1836
     assert int((full.tid != full.mtid).sum()) == 1356734
+
+
+def test_dropin_entry_points_accept_a_bam_path(tmp_path):
+    """get_metrics / PE called with a file name: the native reader decodes the file once (cached for the second
+    call) and the pass equals the one over the in-memory records the file was written from."""
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    sys.path.insert(0, os.path.join(os.path.dirname(here), "oracle"))
+    import helpers
+    from oracle_engine import OracleEngine
+    from besst_b200 import records, synth
+    batch = synth.make_config("tiny").to_batch()
+    recs = []
+    for i in range(len(batch)):
+        q = int(batch.qlen[i])
+        recs.append(dict(tid=int(batch.tid[i]), pos=int(batch.pos[i]), mapq=int(batch.mapq[i]), flag=int(batch.flag[i]), l_seq=q,
+                         mtid=int(batch.mtid[i]), mpos=int(batch.mpos[i]), tlen=int(batch.tlen[i]), cigar=[(0, q)] if q else []))
+    path = str(tmp_path / "lib.bam")
+    write_bam(path, list(zip(batch.references, [int(x) for x in batch.lengths])), recs, block_bytes=30000)
+    opts = dict(orientation="fr")
+    want = helpers.run_dropin(batch, opts, OracleEngine())
+    got = helpers.run_dropin(batch, opts, OracleEngine(), bam_path=path)
+    assert got["G"] == want["G"] and got["G_prime"] == want["G_prime"] and got["param"] == want["param"]
+    assert got["objects"] == want["objects"]
+    assert len(records._open_cache) == 1   # decoded once for get_metrics + PE
