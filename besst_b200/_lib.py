@@ -10,7 +10,7 @@ import os
 from . import abi
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(HERE, "libbesst_b200.so")
+SO_PATH = os.environ.get("BESST_B200_LIB") or os.path.join(HERE, "libbesst_b200.so")   # override: A/B builds of the same ABI
 
 EXPORTS = ["besst_abi_version", "besst_create", "besst_destroy", "besst_last_error", "besst_set_contigs",
            "besst_graph_build", "besst_graph_fetch", "besst_links_extract", "besst_links_tuples_device",

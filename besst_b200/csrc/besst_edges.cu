@@ -283,8 +283,11 @@ __device__ __forceinline__ u32 gb_insert(u64* ht, u64 key, u32* overflow) {
 // FROM_SCRATCH: `tuples` is K1's scratch (128 slots per record tile, the kept tuples of tile t at
 // t * 128 + drop .. ) and tile_off[t] the ordinal of tile t's first kept tuple: the block finds the tiles
 // that overlap its 2048 ordinals and reads them in place -- no compacted copy of the tuple stream.
+#ifndef BESST_GB_MIN_CTAS
+#define BESST_GB_MIN_CTAS 4
+#endif
 template <bool FROM_SCRATCH>
-__global__ void __launch_bounds__(GB_THREADS, 4)
+__global__ void __launch_bounds__(GB_THREADS, BESST_GB_MIN_CTAS)
     k_group_blocks(const besst_link_tuple* __restrict__ tuples, long long n, int bv, int block_bits, int2* __restrict__ grouped,
                    u64* __restrict__ run_key, u32* __restrict__ run_val, u32* __restrict__ run_start, u32* __restrict__ run_cnt,
                    u32* __restrict__ run_first, u32* gstate, u32 run_cap, const u64* __restrict__ tile_off, long long n_tiles,
@@ -1191,7 +1194,10 @@ __device__ __forceinline__ void kb_sort_and_eval(KsBlockSmem& S, const KsBlockAr
     }
 }
 
-__global__ void __launch_bounds__(KB_THREADS, 4) k_ks_block(const KsBlockArgs A) {
+#ifndef BESST_KB_MIN_CTAS
+#define BESST_KB_MIN_CTAS 4
+#endif
+__global__ void __launch_bounds__(KB_THREADS, BESST_KB_MIN_CTAS) k_ks_block(const KsBlockArgs A) {
     __shared__ KsBlockSmem S;
     __shared__ long long s_k[2];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;

@@ -149,10 +149,20 @@ __device__ __forceinline__ int row_scaf(int x) { return (int)((u32)x >> 3); }
 //    five words each.
 //  * the contig-table word of a lane's first record is reused for its other three records (the BAM
 //    is tid-sorted); out-of-range contigs read as row word 0 == BESST_CTG_ABSENT.
-constexpr int K1T_WARPS = 6;
+// tuning knobs (overridable with -D for A/B builds, scripts/variants.sh)
+#ifndef BESST_K1T_WARPS
+#define BESST_K1T_WARPS 8
+#endif
+#ifndef BESST_K1T_MIN_CTAS
+#define BESST_K1T_MIN_CTAS 4
+#endif
+#ifndef BESST_K1T_BATCH
+#define BESST_K1T_BATCH 8
+#endif
+constexpr int K1T_WARPS = BESST_K1T_WARPS;
 constexpr int K1T_THREADS = 32 * K1T_WARPS;
-constexpr int K1T_MIN_CTAS = 6;
-constexpr int K1T_BATCH = 8;   // consecutive tiles per ticket
+constexpr int K1T_MIN_CTAS = BESST_K1T_MIN_CTAS;
+constexpr int K1T_BATCH = BESST_K1T_BATCH;   // consecutive tiles per ticket
 
 struct __align__(16) TileBuf {
     int tid[WT], mtid[WT], qlen[WT], pos[WT], mpos[WT];
