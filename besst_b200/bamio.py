@@ -39,7 +39,9 @@ class BamStats(C.Structure):
                 ("seconds_total", C.c_double), ("threads", C.c_int32)]
 
 
-BAMIO_EXPORTS = ["besst_bamio_abi_version", "besst_bam_read", "besst_bam_n_refs", "besst_bam_ref_name", "besst_bam_ref_length",
+WINDOW_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.POINTER(_Columns), C.c_int64)
+
+BAMIO_EXPORTS = ["besst_bamio_abi_version", "besst_bam_read", "besst_bam_stream", "besst_bam_n_refs", "besst_bam_ref_name", "besst_bam_ref_length",
                  "besst_bam_get_columns", "besst_bam_get_stats", "besst_bam_close"]
 
 
@@ -52,6 +54,8 @@ def load_bamio():
     L = C.CDLL(BAMIO_SO)
     L.besst_bam_read.restype = C.c_void_p
     L.besst_bam_read.argtypes = [C.c_char_p, C.c_int32, C.c_int64, C.c_int64, C.c_char_p, C.c_int32]
+    L.besst_bam_stream.restype = C.c_void_p
+    L.besst_bam_stream.argtypes = [C.c_char_p, C.c_int32, C.c_int64, C.c_int64, WINDOW_FN, C.c_void_p, C.c_char_p, C.c_int32]
     L.besst_bam_n_refs.restype = C.c_int64
     L.besst_bam_n_refs.argtypes = [C.c_void_p]
     L.besst_bam_ref_name.restype = C.c_char_p
@@ -199,3 +203,53 @@ def read_fasta_lengths(path):
     if name is not None:
         out[name] = n
     return out
+
+
+def stream_bam_native(path, on_window, threads=0, max_records=None, head_records=1000):
+    """Decode the file window by window: on_window(columns, first_record, references, lengths) is called for each
+    window with a dict of numpy views (tid, mtid, pos, mpos, tlen, qlen, flag, mapq) that are valid only during the
+    call -- copy (or upload) what you need.  Returning a true value stops the pass.  -> stats dict.
+    Memory stays bounded for files of any size; this is the hook for overlapping ingest with the sliced upload of
+    besst_graph_build."""
+    L = load_bamio()
+    header = {}
+    failure = []
+
+    def view(p, count, dt):
+        if count == 0 or not p:
+            return np.zeros(0, dtype=dt)
+        return np.frombuffer((C.c_char * (count * np.dtype(dt).itemsize)).from_address(p), dtype=dt, count=count)
+
+    def trampoline(_user, handle, cols_p, first):
+        try:
+            if not header:
+                n_ref = int(L.besst_bam_n_refs(handle))
+                header["references"] = [L.besst_bam_ref_name(handle, i).decode("ascii") for i in range(n_ref)]
+                header["lengths"] = [int(L.besst_bam_ref_length(handle, i)) for i in range(n_ref)]
+            c = cols_p.contents
+            n = int(c.n)
+            cols = {"tid": view(c.tid, n, np.int32), "mtid": view(c.mtid, n, np.int32), "pos": view(c.pos, n, np.int32),
+                    "mpos": view(c.mpos, n, np.int32), "tlen": view(c.tlen, n, np.int32), "qlen": view(c.qlen, n, np.int32),
+                    "flag": view(c.flag, n, np.uint16), "mapq": view(c.mapq, n, np.uint8)}
+            return 1 if on_window(cols, int(first), header["references"], header["lengths"]) else 0
+        except BaseException as exc:   # never unwind through the C frames
+            failure.append(exc)
+            return 1
+
+    cb = WINDOW_FN(trampoline)
+    err = C.create_string_buffer(512)
+    ptr = L.besst_bam_stream(os.fsencode(path), int(threads), -1 if max_records is None else int(max_records), int(head_records),
+                             cb, None, err, len(err))
+    if failure:
+        if ptr:
+            L.besst_bam_close(ptr)
+        raise failure[0]
+    if not ptr:
+        msg = err.value.decode(errors="replace")
+        if "stopped by the window callback" in msg:
+            return None
+        raise IOError("besst_bam_stream: %s" % msg)
+    st = BamStats()
+    L.besst_bam_get_stats(ptr, C.byref(st))
+    L.besst_bam_close(ptr)
+    return {k: getattr(st, k) for k, _ in BamStats._fields_}

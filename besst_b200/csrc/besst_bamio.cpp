@@ -160,9 +160,12 @@ inline void cigar_lengths(const unsigned char* cig, uint32_t n_cigar, int32_t l_
 
 extern "C" int besst_bamio_abi_version(void) { return 1; }
 
-extern "C" besst_bam* besst_bam_read(const char* path, int32_t n_threads, int64_t max_records, int64_t head_records,
-                                     char* err, int32_t err_len) {
+// window_fn == nullptr: all records accumulate in the handle's columns (besst_bam_read); else every decoded window is
+// handed to window_fn and its column space reused (besst_bam_stream)
+static besst_bam* read_impl(const char* path, int32_t n_threads, int64_t max_records, int64_t head_records,
+                            besst_bam_window_fn window_fn, void* user, char* err, int32_t err_len) {
     const double t_start = now();
+    int64_t base_total = 0;   // records delivered to window_fn so far
     if (n_threads <= 0) n_threads = (int32_t)std::thread::hardware_concurrency();
     if (n_threads <= 0) n_threads = 1;
     if (n_threads > 256) n_threads = 256;
@@ -364,7 +367,7 @@ extern "C" besst_bam* besst_bam_read(const char* path, int32_t n_threads, int64_
                 if (cur + 4 + (size_t)bs > have) break;
                 offs.push_back((uint32_t)cur);
                 cur += 4 + (size_t)bs;
-                if (max_records >= 0 && B->n + (int64_t)offs.size() >= max_records) { stop = true; break; }
+                if (max_records >= 0 && base_total + B->n + (int64_t)offs.size() >= max_records) { stop = true; break; }
             }
             const int64_t mm = (int64_t)offs.size();
             for (int t = 0; t <= n_threads; ++t) tbase[(size_t)t] = mm * t / n_threads;
@@ -373,7 +376,7 @@ extern "C" besst_bam* besst_bam_read(const char* path, int32_t n_threads, int64_
         if (!B->tid.ensure(n0 + m, n0) || !B->mtid.ensure(n0 + m, n0) || !B->pos.ensure(n0 + m, n0) || !B->mpos.ensure(n0 + m, n0) ||
             !B->tlen.ensure(n0 + m, n0) || !B->qlen.ensure(n0 + m, n0) || !B->flag.ensure(n0 + m, n0) || !B->mapq.ensure(n0 + m, n0))
             return fail("out of memory for the record columns");
-        const int64_t head_new = std::min<int64_t>(head_records, n0 + m);
+        const int64_t head_new = std::min<int64_t>(head_records, base_total + n0 + m);
         if (!B->rlen.ensure(head_new > 0 ? head_new : 1, B->n_head) || !B->alen.ensure(head_new > 0 ? head_new : 1, B->n_head))
             return fail("out of memory for the record columns");
 
@@ -400,7 +403,7 @@ extern "C" besst_bam* besst_bam_read(const char* path, int32_t n_threads, int64_
                 int32_t ql, al;
                 cigar_lengths(p + 36 + l_read_name, n_cigar, l_seq, &ql, &al);
                 B->qlen.p[g] = ql;
-                if (g < head_records) { B->rlen.p[g] = l_seq; B->alen.p[g] = al; }
+                if (base_total + g < head_records) { B->rlen.p[base_total + g] = l_seq; B->alen.p[base_total + g] = al; }
             }
         };
         {
@@ -413,6 +416,13 @@ extern "C" besst_bam* besst_bam_read(const char* path, int32_t n_threads, int64_
         B->n = n0 + m;
         B->n_head = head_new;
         B->stats.seconds_decode += now() - t1;
+        if (window_fn) {   // streaming: hand the window over, then reuse the column space
+            besst_bam_columns w;
+            besst_bam_get_columns(B, &w);
+            if (window_fn(user, B, &w, base_total) != 0) return fail("stopped by the window callback");
+            base_total += B->n;
+            B->n = 0;
+        }
         // keep the unconsumed tail (a partial record) for the next window
         if (cur < pend.size()) memmove(pend.data(), pend.data() + cur, pend.size() - cur);
         pend.resize(pend.size() - cur);
@@ -420,9 +430,20 @@ extern "C" besst_bam* besst_bam_read(const char* path, int32_t n_threads, int64_
     if (!header_done) return fail("truncated BAM header");
     if (!stop && !pend.empty()) return fail("truncated BAM file (partial record at the end)");
     munmap(map, fsize);
-    B->stats.records = B->n;
+    B->stats.records = base_total + B->n;
     B->stats.seconds_total = now() - t_start;
     return B;
+}
+
+extern "C" besst_bam* besst_bam_read(const char* path, int32_t n_threads, int64_t max_records, int64_t head_records,
+                                     char* err, int32_t err_len) {
+    return read_impl(path, n_threads, max_records, head_records, nullptr, nullptr, err, err_len);
+}
+
+extern "C" besst_bam* besst_bam_stream(const char* path, int32_t n_threads, int64_t max_records, int64_t head_records,
+                                       besst_bam_window_fn window_fn, void* user, char* err, int32_t err_len) {
+    if (!window_fn) { set_err(err, err_len, "besst_bam_stream: no callback"); return nullptr; }
+    return read_impl(path, n_threads, max_records, head_records, window_fn, user, err, err_len);
 }
 
 extern "C" int64_t besst_bam_n_refs(const besst_bam* b) { return b ? (int64_t)b->ref_names.size() : -1; }

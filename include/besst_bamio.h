@@ -56,6 +56,17 @@ int besst_bamio_abi_version(void);
 besst_bam* besst_bam_read(const char* path, int32_t n_threads, int64_t max_records, int64_t head_records,
                           char* err, int32_t err_len);
 
+/* The same pass, streamed: every decoded window of records (a few hundred thousand) is handed to window_fn as
+ * soon as it is ready and its column space is reused: memory stays bounded for a file of any size and a
+ * consumer can move window k on (copy it to pinned staging and start its upload) before window k+1 is inflated.
+ * window->n records starting at ordinal first_record; the pointers are valid only during the call (the call runs
+ * on the caller's thread, between windows); b gives access to the header (besst_bam_n_refs ...) from the first
+ * call on.  A non-zero return stops the pass (NULL is returned).  The returned handle holds the header, the
+ * statistics and rlen/alen of the first head_records records, but no record columns. */
+typedef int (*besst_bam_window_fn)(void* user, const besst_bam* b, const besst_bam_columns* window, int64_t first_record);
+besst_bam* besst_bam_stream(const char* path, int32_t n_threads, int64_t max_records, int64_t head_records,
+                            besst_bam_window_fn window_fn, void* user, char* err, int32_t err_len);
+
 int64_t besst_bam_n_refs(const besst_bam* b);
 const char* besst_bam_ref_name(const besst_bam* b, int64_t i);
 int64_t besst_bam_ref_length(const besst_bam* b, int64_t i);

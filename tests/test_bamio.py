@@ -143,3 +143,29 @@ def test_dropin_entry_points_accept_a_bam_path(tmp_path):
     assert got["G"] == want["G"] and got["G_prime"] == want["G_prime"] and got["param"] == want["param"]
     assert got["objects"] == want["objects"]
     assert len(records._open_cache) == 1   # decoded once for get_metrics + PE
+
+
+def test_streamed_windows_concatenate_to_the_full_read(tmp_path, monkeypatch):
+    rng = np.random.default_rng(3)
+    refs = [("c%d" % i, 4000 + i) for i in range(5)]
+    path = str(tmp_path / "s.bam")
+    write_bam(path, refs, _random_records(rng, 6000, len(refs)), block_bytes=2500)
+    full = bamio.read_bam(path)
+    monkeypatch.setenv("BESST_BAMIO_WINDOW", "30000")
+    parts, firsts, seen_refs = [], [], []
+
+    def on_window(cols, first, references, lengths):
+        parts.append({k: v.copy() for k, v in cols.items()})   # the views die with the call
+        firsts.append(first)
+        seen_refs.append((tuple(references), tuple(lengths)))
+
+    stats = bamio.stream_bam_native(path, on_window, threads=3)
+    assert len(parts) > 5 and stats["records"] == len(full)
+    assert firsts == list(np.cumsum([0] + [len(p["tid"]) for p in parts[:-1]]))
+    assert all(r == (tuple(full.references), tuple(full.lengths)) for r in seen_refs)
+    for f in ("tid", "mtid", "pos", "mpos", "tlen", "qlen", "flag", "mapq"):
+        assert np.array_equal(np.concatenate([p[f] for p in parts]), getattr(full, f)), f
+    # a callback can stop the pass; an exception inside it surfaces in Python
+    assert bamio.stream_bam_native(path, lambda *a: True, threads=2) is None
+    with pytest.raises(ZeroDivisionError):
+        bamio.stream_bam_native(path, lambda *a: 1 // 0, threads=2)
