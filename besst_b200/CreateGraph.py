@@ -31,7 +31,10 @@ from .records import as_batch, as_file
 
 
 def _new_graph():
-    return nx.Graph()
+    # looked up at call time: the graphs are handed to BESST's consumers (MakeScaffolds.Algorithm, runBESST:199),
+    # so they must be of whatever `networkx` the host process runs BESST with (1.x per docs/INSTALL.md:42)
+    import networkx
+    return networkx.Graph()
 
 
 def _remove_nodes(graph, scaf):
@@ -124,9 +127,11 @@ def InitializeGraph(dict_with_scaffolds, graph, Information):
     (CreateGraph.py:710-722)."""
     start = time()
     for cnt, (name, s) in enumerate(dict_with_scaffolds.items(), 1):
+        # add_node(..., length=) works under networkx 1.x (where graph.nodes is a method) and 2.x/3.x alike;
+        # same node and adjacency insertion order as add_edge followed by the two attribute writes (:713-716)
+        graph.add_node((name, 'L'), length=s.s_length)
+        graph.add_node((name, 'R'), length=s.s_length)
         graph.add_edge((name, 'L'), (name, 'R'), nr_links=None)
-        graph.nodes[(name, 'L')]['length'] = s.s_length
-        graph.nodes[(name, 'R')]['length'] = s.s_length
         if cnt % 100000 == 0:
             print('Total nr of keys added: ', cnt, 'Time for adding last 100 000 keys: ', time() - start, file=Information)
             start = time()
@@ -339,12 +344,27 @@ def _populate(G, G_prime, res, table, param, observations_as_list=True):
             G_prime.add_edge(nv, nu, nr_links=nr, obs=obs, obs_sq=obs_sq, observations=conv(total[b:t]))
 
 
-def GiveScoreOnEdges(G, res, table, param, Information):
+def _score_file_names(Scaffolds, node, first):
+    """Contig names / directions column of score_file_pass_N.tsv (CreateGraph.py:622-650); the reference's
+    direction strings are constant by construction ('+' if True else '-')."""
+    forward = (node[1] == 'R') if first else (node[1] == 'L')
+    contigs = Scaffolds[node[0]].contigs if forward else Scaffolds[node[0]].contigs[::-1]
+    return ";".join(c.name for c in contigs), ";".join(('+' if forward else '-') for _ in contigs)
+
+
+def GiveScoreOnEdges(G, res, table, param, Information, Scaffolds=None):
     """Attach the engine's per-edge gap and score to the surviving G edges
-    (the arithmetic of CreateGraph.py:498-614 ran on the GPU)."""
+    (the arithmetic of CreateGraph.py:498-614 ran on the GPU); writes
+    score_file_pass_N.tsv when param.print_scores (:481-483,622-654)."""
     if param.lognormal:
         raise NotImplementedError("lognormal libraries: the reference's scoring branch (CreateGraph.py:485-493) "
                                   "is a 'next' row (SURVEY.md 8f rank 3)")
+    if getattr(param, 'plots', False):
+        print('plots requested: the score histograms of CreateGraph.py:656-662 are not produced by besst_b200', file=Information)
+    score_file = None
+    if getattr(param, 'print_scores', False) and Scaffolds is not None:
+        score_file = open(os.path.join(param.output_directory, "score_file_pass_{0}.tsv".format(param.pass_number)), "w")
+        print("{0}\t{1}\t{2}\t{3}\t{4}\t{5}\t{6}\t{7}".format("scf1/ctg1", "o1", "scf2/ctg2", "o2", "gap", "link_variation_score", "link_dispersity_score", "number_of_links"), file=score_file)
     index = {}
     for e in np.nonzero(res.flags & abi.EDGE_SCORED)[0].tolist():
         index[(int(res.edge_u[e]), int(res.edge_v[e]))] = e
@@ -361,6 +381,18 @@ def GiveScoreOnEdges(G, res, table, param, Information):
         del d[n1[0]]
         s = float(res.score[e])
         d['score'] = s if s != 0.0 else 0
+        if score_file is not None:
+            n = int(res.nr_links[e])
+            sd, sd0 = float(res.sd_obs[e]), float(res.sd_model[e])
+            std_dev_score = 0 if (sd == 0.0 or sd0 == 0.0 or sd != sd) else min(sd / sd0, sd0 / sd)
+            span_score = 0 if n < 5 else 1 - float(res.ks[e])
+            # `gap` of the reference is GapEstimator's int for two long scaffolds, else the float naive estimate (:536-539)
+            gap = int(res.gap[e]) if res.flags[e] & abi.EDGE_BIG else (n * param.mean_ins_size - int(res.obs_sum[e])) / float(n)
+            scf1, dir1 = _score_file_names(Scaffolds, n0, True)
+            scf2, dir2 = _score_file_names(Scaffolds, n1, False)
+            print("{0}\t{1}\t{2}\t{3}\t{4}\t{5}\t{6}\t{7}".format(scf1, dir1, scf2, dir2, gap, std_dev_score, span_score, n), file=score_file)
+    if score_file is not None:
+        score_file.close()
     print('Number of significantly spurious edges:', 0, file=Information)
 
 
@@ -454,7 +486,7 @@ def PE(Contigs, Scaffolds, Information, C_dict, param, small_contigs, small_scaf
     remove_edges_below_threshold(G_prime, param)
 
     if not param.no_score:
-        GiveScoreOnEdges(G, res, table, param, Information)
+        GiveScoreOnEdges(G, res, table, param, Information, Scaffolds)
     print('Number of edges in G_prime  (after removing edges under -e threshold (if not specified, default is -e 3): ', G_prime.number_of_edges(), file=Information)
     print("\n -------------------------------------------------------------\n", file=Information)
     print('Nr of contigs/scaffolds included in this pass: ' + str(len(Scaffolds) + len(small_scaffolds)), file=Information)

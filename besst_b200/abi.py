@@ -8,7 +8,7 @@ from dataclasses import dataclass
 
 import numpy as np
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 CTG_ABSENT, CTG_LARGE, CTG_SMALL = 0, 1, 2
 ORIENT_FR, ORIENT_RF = 0, 1
@@ -68,7 +68,8 @@ class LibMetricsOut(C.Structure):
                 ("skewness", C.c_double), ("mu_adj", C.c_double), ("sigma_adj", C.c_double),
                 ("skew_adj", C.c_double), ("median_adj", C.c_int64), ("mode_adj", C.c_int64),
                 ("n_bins", C.c_int64), ("cont_mapped", C.c_int64), ("cont_n", C.c_int64),
-                ("cont_mean", C.c_double), ("cont_sd", C.c_double), ("records_scanned", C.c_int64)]
+                ("cont_mean", C.c_double), ("cont_sd", C.c_double), ("records_scanned", C.c_int64),
+                ("cont_n_before", C.c_int64), ("cont_mean_before", C.c_double), ("cont_sd_before", C.c_double)]
 
 
 @dataclass

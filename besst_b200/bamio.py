@@ -100,6 +100,7 @@ def read_bam_native(path, threads=0, max_records=None, head_records=1000):
         if count == 0 or not p:
             return np.zeros(0, dtype=dt)
         buf = (C.c_char * (count * np.dtype(dt).itemsize)).from_address(p)
+        buf._owner = h   # the ctypes object becomes ndarray.base of every derived view: slices keep the handle alive
         a = np.frombuffer(buf, dtype=dt, count=count)
         return a
 

@@ -373,54 +373,50 @@ extern "C" int besst_set_stream(besst_ctx* ctx, void* cuda_stream) {
     return BESST_OK;
 }
 
-extern "C" int besst_trsk_sd_batch(besst_ctx* ctx, const besst_lib_params* params, const double* gap, const int32_t* len1,
-                                   const int32_t* len2, int64_t n, double* sd_out) {
+// host arrays of n doubles (values) + two length arrays in, one double array out, through ctx->misc
+static int batch_f64(besst_ctx* ctx, const besst_lib_params* params, const double* x, const double* len1, const double* len2, int64_t n,
+                     double* out, int32_t* gap_out, const char* what,
+                     int (*launch)(besst_ctx*, const besst_lib_params&, const double*, const double*, const double*, int64_t, int32_t*, double*)) {
     if (!ctx) return BESST_E_INVALID;
     int rc = check_params(ctx, params);
     if (rc) return rc;
-    if (n < 0 || (n > 0 && (!gap || !len1 || !len2 || !sd_out))) { ctx->err = "trsk_sd_batch: bad arguments"; return BESST_E_INVALID; }
+    if (n < 0 || (n > 0 && (!x || !len1 || !len2 || (!out && !gap_out)))) { ctx->err = std::string(what) + ": bad arguments"; return BESST_E_INVALID; }
     if (n == 0) return BESST_OK;
     cudaSetDevice(ctx->device);
     const size_t nn = (size_t)n;
-    BESST_CUDA_TRY(ctx, ctx->misc.ensure(nn * (8 + 8 + 4 + 4) + 64));
-    unsigned char* base = ctx->misc.as<unsigned char>();
-    double* d_gap = reinterpret_cast<double*>(base);
-    double* d_sd = reinterpret_cast<double*>(base + 8 * nn);
-    int32_t* d_l1 = reinterpret_cast<int32_t*>(base + 16 * nn);
-    int32_t* d_l2 = d_l1 + nn;
-    BESST_CUDA_TRY(ctx, cudaMemcpyAsync(d_gap, gap, 8 * nn, cudaMemcpyHostToDevice, ctx->stream));
-    BESST_CUDA_TRY(ctx, cudaMemcpyAsync(d_l1, len1, 4 * nn, cudaMemcpyHostToDevice, ctx->stream));
-    BESST_CUDA_TRY(ctx, cudaMemcpyAsync(d_l2, len2, 4 * nn, cudaMemcpyHostToDevice, ctx->stream));
-    rc = besst_launch_trsk_sd(ctx, *params, d_gap, d_l1, d_l2, n, d_sd);
+    BESST_CUDA_TRY(ctx, ctx->misc.ensure(nn * (4 * 8 + 4) + 64));
+    double* d_x = ctx->misc.as<double>();
+    double* d_l1 = d_x + nn;
+    double* d_l2 = d_l1 + nn;
+    double* d_out = d_l2 + nn;
+    int32_t* d_gap = reinterpret_cast<int32_t*>(d_out + nn);
+    BESST_CUDA_TRY(ctx, cudaMemcpyAsync(d_x, x, 8 * nn, cudaMemcpyHostToDevice, ctx->stream));
+    BESST_CUDA_TRY(ctx, cudaMemcpyAsync(d_l1, len1, 8 * nn, cudaMemcpyHostToDevice, ctx->stream));
+    BESST_CUDA_TRY(ctx, cudaMemcpyAsync(d_l2, len2, 8 * nn, cudaMemcpyHostToDevice, ctx->stream));
+    rc = launch(ctx, *params, d_x, d_l1, d_l2, n, d_gap, d_out);
     if (rc) return rc;
-    BESST_CUDA_TRY(ctx, cudaMemcpyAsync(sd_out, d_sd, 8 * nn, cudaMemcpyDeviceToHost, ctx->stream));
+    if (gap_out) BESST_CUDA_TRY(ctx, cudaMemcpyAsync(gap_out, d_gap, 4 * nn, cudaMemcpyDeviceToHost, ctx->stream));
+    if (out) BESST_CUDA_TRY(ctx, cudaMemcpyAsync(out, d_out, 8 * nn, cudaMemcpyDeviceToHost, ctx->stream));
     BESST_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     return BESST_OK;
 }
 
-extern "C" int besst_gapest_func_batch(besst_ctx* ctx, const besst_lib_params* params, const double* d, const int32_t* len1,
-                                       const int32_t* len2, int64_t n, double* func_out) {
-    if (!ctx) return BESST_E_INVALID;
-    int rc = check_params(ctx, params);
-    if (rc) return rc;
-    if (n < 0 || (n > 0 && (!d || !len1 || !len2 || !func_out))) { ctx->err = "gapest_func_batch: bad arguments"; return BESST_E_INVALID; }
-    if (n == 0) return BESST_OK;
-    cudaSetDevice(ctx->device);
-    const size_t nn = (size_t)n;
-    BESST_CUDA_TRY(ctx, ctx->misc.ensure(nn * (8 + 8 + 4 + 4) + 64));
-    unsigned char* base = ctx->misc.as<unsigned char>();
-    double* d_d = reinterpret_cast<double*>(base);
-    double* d_out = reinterpret_cast<double*>(base + 8 * nn);
-    int32_t* d_l1 = reinterpret_cast<int32_t*>(base + 16 * nn);
-    int32_t* d_l2 = d_l1 + nn;
-    BESST_CUDA_TRY(ctx, cudaMemcpyAsync(d_d, d, 8 * nn, cudaMemcpyHostToDevice, ctx->stream));
-    BESST_CUDA_TRY(ctx, cudaMemcpyAsync(d_l1, len1, 4 * nn, cudaMemcpyHostToDevice, ctx->stream));
-    BESST_CUDA_TRY(ctx, cudaMemcpyAsync(d_l2, len2, 4 * nn, cudaMemcpyHostToDevice, ctx->stream));
-    rc = besst_launch_func_of_d(ctx, *params, d_d, d_l1, d_l2, n, d_out);
-    if (rc) return rc;
-    BESST_CUDA_TRY(ctx, cudaMemcpyAsync(func_out, d_out, 8 * nn, cudaMemcpyDeviceToHost, ctx->stream));
-    BESST_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-    return BESST_OK;
+extern "C" int besst_trsk_sd_batch(besst_ctx* ctx, const besst_lib_params* params, const double* gap, const double* len1,
+                                   const double* len2, int64_t n, double* sd_out) {
+    if (ctx && n > 0 && !sd_out) { ctx->err = "trsk_sd_batch: bad arguments"; return BESST_E_INVALID; }
+    return batch_f64(ctx, params, gap, len1, len2, n, sd_out, nullptr, "trsk_sd_batch",
+                     [](besst_ctx* c, const besst_lib_params& p, const double* x, const double* l1, const double* l2, int64_t m, int32_t*, double* o) {
+                         return besst_launch_trsk_sd(c, p, x, l1, l2, m, o);
+                     });
+}
+
+extern "C" int besst_gapest_func_batch(besst_ctx* ctx, const besst_lib_params* params, const double* d, const double* len1,
+                                       const double* len2, int64_t n, double* func_out) {
+    if (ctx && n > 0 && !func_out) { ctx->err = "gapest_func_batch: bad arguments"; return BESST_E_INVALID; }
+    return batch_f64(ctx, params, d, len1, len2, n, func_out, nullptr, "gapest_func_batch",
+                     [](besst_ctx* c, const besst_lib_params& p, const double* x, const double* l1, const double* l2, int64_t m, int32_t*, double* o) {
+                         return besst_launch_func_of_d(c, p, x, l1, l2, m, o);
+                     });
 }
 
 extern "C" int besst_links_to_graph(besst_ctx* ctx, const besst_lib_params* params, const besst_link_tuple* tuples_device,
@@ -523,31 +519,13 @@ extern "C" int besst_graph_view(besst_ctx* ctx, besst_graph_out* out) {
     return BESST_OK;
 }
 
-extern "C" int besst_gapest_batch(besst_ctx* ctx, const besst_lib_params* params, const double* mean_obs, const int32_t* len1,
-                                  const int32_t* len2, int64_t n, int32_t* gap_out, double* sd_out) {
-    if (!ctx) return BESST_E_INVALID;
-    int rc = check_params(ctx, params);
-    if (rc) return rc;
-    if (n < 0 || (n > 0 && (!mean_obs || !len1 || !len2 || !gap_out))) { ctx->err = "gapest_batch: bad arguments"; return BESST_E_INVALID; }
-    if (n == 0) return BESST_OK;
-    cudaSetDevice(ctx->device);
-    const size_t nn = (size_t)n;
-    BESST_CUDA_TRY(ctx, ctx->misc.ensure(nn * (8 + 4 + 4 + 4 + 8) + 64));
-    unsigned char* base = ctx->misc.as<unsigned char>();
-    double* d_mo = reinterpret_cast<double*>(base);
-    double* d_sd = reinterpret_cast<double*>(base + 8 * nn);
-    int32_t* d_l1 = reinterpret_cast<int32_t*>(base + 16 * nn);
-    int32_t* d_l2 = d_l1 + nn;
-    int32_t* d_gap = d_l2 + nn;
-    BESST_CUDA_TRY(ctx, cudaMemcpyAsync(d_mo, mean_obs, 8 * nn, cudaMemcpyHostToDevice, ctx->stream));
-    BESST_CUDA_TRY(ctx, cudaMemcpyAsync(d_l1, len1, 4 * nn, cudaMemcpyHostToDevice, ctx->stream));
-    BESST_CUDA_TRY(ctx, cudaMemcpyAsync(d_l2, len2, 4 * nn, cudaMemcpyHostToDevice, ctx->stream));
-    rc = besst_launch_gapest(ctx, *params, d_mo, d_l1, d_l2, n, d_gap, d_sd);
-    if (rc) return rc;
-    BESST_CUDA_TRY(ctx, cudaMemcpyAsync(gap_out, d_gap, 4 * nn, cudaMemcpyDeviceToHost, ctx->stream));
-    if (sd_out) BESST_CUDA_TRY(ctx, cudaMemcpyAsync(sd_out, d_sd, 8 * nn, cudaMemcpyDeviceToHost, ctx->stream));
-    BESST_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-    return BESST_OK;
+extern "C" int besst_gapest_batch(besst_ctx* ctx, const besst_lib_params* params, const double* mean_obs, const double* len1,
+                                  const double* len2, int64_t n, int32_t* gap_out, double* sd_out) {
+    if (ctx && n > 0 && !gap_out) { ctx->err = "gapest_batch: bad arguments"; return BESST_E_INVALID; }
+    return batch_f64(ctx, params, mean_obs, len1, len2, n, sd_out, gap_out, "gapest_batch",
+                     [](besst_ctx* c, const besst_lib_params& p, const double* x, const double* l1, const double* l2, int64_t m, int32_t* g, double* o) {
+                         return besst_launch_gapest(c, p, x, l1, l2, m, g, o);
+                     });
 }
 
 extern "C" int besst_libmetrics(besst_ctx* ctx, const besst_lib_params* params, const besst_records* records,

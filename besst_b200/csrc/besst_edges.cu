@@ -1300,12 +1300,12 @@ __global__ void __launch_bounds__(LS_THREADS) k_llc_write(const unsigned char* _
 
 // ---- batched GapEstimator + tr_sk_std_dev: one quad per item -------------------------------
 __global__ void __launch_bounds__(128)
-    k_gapest_batch(const ScoreConsts c, const double* __restrict__ mean_obs, const int* __restrict__ len1,
-                   const int* __restrict__ len2, long long n, int* gap_out, double* sd_out) {
+    k_gapest_batch(const ScoreConsts c, const double* __restrict__ mean_obs, const double* __restrict__ len1,
+                   const double* __restrict__ len2, long long n, int* gap_out, double* sd_out) {
     const long long quad = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 2;
     const bool active = quad < n;
     const double mo = active ? mean_obs[quad] : 0.0;
-    const double l1 = active ? (double)len1[quad] : 1.0, l2 = active ? (double)len2[quad] : 1.0;
+    const double l1 = active ? len1[quad] : 1.0, l2 = active ? len2[quad] : 1.0;
     const int gap = gap_estimator_quad(c, mo, l1, l2, active);
     const double sd = tr_sk_std_dev_quad(c, l1, l2, (double)gap);
     if (active && (threadIdx.x & 3) == 0) {
@@ -1315,12 +1315,12 @@ __global__ void __launch_bounds__(128)
 }
 
 __global__ void __launch_bounds__(128)
-    k_trsk_sd_batch(const ScoreConsts c, const double* __restrict__ gap, const int* __restrict__ len1,
-                    const int* __restrict__ len2, long long n, double* sd_out) {
+    k_trsk_sd_batch(const ScoreConsts c, const double* __restrict__ gap, const double* __restrict__ len1,
+                    const double* __restrict__ len2, long long n, double* sd_out) {
     const long long quad = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 2;
     const bool active = quad < n;
     const double d = active ? gap[quad] : 0.0;
-    const double l1 = active ? (double)len1[quad] : 1.0, l2 = active ? (double)len2[quad] : 1.0;
+    const double l1 = active ? len1[quad] : 1.0, l2 = active ? len2[quad] : 1.0;
     const double sd = tr_sk_std_dev_quad(c, l1, l2, d);
     if (active && (threadIdx.x & 3) == 0) sd_out[quad] = sd;
 }
@@ -1328,12 +1328,12 @@ __global__ void __launch_bounds__(128)
 // d + sigma^2 g'(d)/g(d) -- the left-hand side of the ML equation (funcDGeneral) -- for a batch of d:
 // what mathstats' PreCalcMLvaluesOfdLongContigs tabulates (MakeScaffolds.py:68)
 __global__ void __launch_bounds__(128)
-    k_func_of_d_batch(const ScoreConsts c, const double* __restrict__ d_in, const int* __restrict__ len1,
-                      const int* __restrict__ len2, long long n, double* out) {
+    k_func_of_d_batch(const ScoreConsts c, const double* __restrict__ d_in, const double* __restrict__ len1,
+                      const double* __restrict__ len2, long long n, double* out) {
     const long long quad = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 2;
     const bool active = quad < n;
     const double d = active ? d_in[quad] : 0.0;
-    const double l1 = active ? (double)len1[quad] : 1.0, l2 = active ? (double)len2[quad] : 1.0;
+    const double l1 = active ? len1[quad] : 1.0, l2 = active ? len2[quad] : 1.0;
     const double c_min = l1 < l2 ? l1 : l2, c_max = l1 < l2 ? l2 : l1;
     const GTerms t = g_terms_quad(d, c, c_min, c_max);
     const double aofd = t.gp / t.g;
@@ -1362,8 +1362,8 @@ ScoreConsts besst_score_consts(const besst_lib_params& p) {
     return c;
 }
 
-int besst_launch_gapest(besst_ctx* ctx, const besst_lib_params& p, const double* d_mean_obs, const int32_t* d_len1,
-                        const int32_t* d_len2, int64_t n, int32_t* d_gap, double* d_sd) {
+int besst_launch_gapest(besst_ctx* ctx, const besst_lib_params& p, const double* d_mean_obs, const double* d_len1,
+                        const double* d_len2, int64_t n, int32_t* d_gap, double* d_sd) {
     if (n == 0) return BESST_OK;
     const ScoreConsts c = besst_score_consts(p);
     const long long threads = n * 4;
@@ -1373,8 +1373,8 @@ int besst_launch_gapest(besst_ctx* ctx, const besst_lib_params& p, const double*
     return BESST_OK;
 }
 
-int besst_launch_func_of_d(besst_ctx* ctx, const besst_lib_params& p, const double* d_d, const int32_t* d_len1,
-                           const int32_t* d_len2, int64_t n, double* d_out) {
+int besst_launch_func_of_d(besst_ctx* ctx, const besst_lib_params& p, const double* d_d, const double* d_len1,
+                           const double* d_len2, int64_t n, double* d_out) {
     if (n == 0) return BESST_OK;
     const ScoreConsts c = besst_score_consts(p);
     const int grid = (int)((n * 4 + 127) / 128);
@@ -1383,8 +1383,8 @@ int besst_launch_func_of_d(besst_ctx* ctx, const besst_lib_params& p, const doub
     return BESST_OK;
 }
 
-int besst_launch_trsk_sd(besst_ctx* ctx, const besst_lib_params& p, const double* d_gap, const int32_t* d_len1,
-                         const int32_t* d_len2, int64_t n, double* d_sd) {
+int besst_launch_trsk_sd(besst_ctx* ctx, const besst_lib_params& p, const double* d_gap, const double* d_len1,
+                         const double* d_len2, int64_t n, double* d_sd) {
     if (n == 0) return BESST_OK;
     const ScoreConsts c = besst_score_consts(p);
     const long long threads = n * 4;

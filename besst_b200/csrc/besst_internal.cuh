@@ -209,12 +209,12 @@ int besst_radix_sort_keys(besst_ctx* ctx, uint64_t* keys_a, uint64_t* keys_b, in
 // per-edge statistics, KS, GapEst, score
 int besst_launch_edge_stats(besst_ctx* ctx, const besst_lib_params& p, const besst_link_tuple* d_tuples,
                             const uint64_t* d_sorted_keys, const uint32_t* d_sorted_idx, int64_t n_links, int key_shift);
-int besst_launch_gapest(besst_ctx* ctx, const besst_lib_params& p, const double* d_mean_obs, const int32_t* d_len1,
-                        const int32_t* d_len2, int64_t n, int32_t* d_gap, double* d_sd);
-int besst_launch_trsk_sd(besst_ctx* ctx, const besst_lib_params& p, const double* d_gap, const int32_t* d_len1,
-                         const int32_t* d_len2, int64_t n, double* d_sd);
-int besst_launch_func_of_d(besst_ctx* ctx, const besst_lib_params& p, const double* d_d, const int32_t* d_len1,
-                           const int32_t* d_len2, int64_t n, double* d_out);
+int besst_launch_gapest(besst_ctx* ctx, const besst_lib_params& p, const double* d_mean_obs, const double* d_len1,
+                        const double* d_len2, int64_t n, int32_t* d_gap, double* d_sd);
+int besst_launch_trsk_sd(besst_ctx* ctx, const besst_lib_params& p, const double* d_gap, const double* d_len1,
+                         const double* d_len2, int64_t n, double* d_sd);
+int besst_launch_func_of_d(besst_ctx* ctx, const besst_lib_params& p, const double* d_d, const double* d_len1,
+                           const double* d_len2, int64_t n, double* d_out);
 int besst_launch_partition(besst_ctx* ctx, int world, besst_link_tuple* out_tuples, uint32_t* out_ordinals,
                            uint64_t* out_fishy, int64_t* tuple_counts, int64_t* fishy_counts);
 

@@ -453,8 +453,10 @@ int besst_launch_libmetrics(besst_ctx* ctx, const besst_lib_params& p, const Dev
         H.shift = fr ? 2 * p.read_len : 0.0;
         long long n = H.n();
         double mean = 0, sd = 0;
+        out->cont_n_before = n; out->cont_mean_before = 0; out->cont_sd_before = 0;
         if (n > 2) {
             H.mean_sd(&mean, &sd);
+            out->cont_mean_before = mean; out->cont_sd_before = sd;
             for (;;) {
                 const double k = 1.5 * max_obs_distr((double)n, 0.95);
                 const long long m = H.trimmed_count(mean, sd, k);

@@ -69,6 +69,19 @@ class CudaBackend(object):
         self.device = device
         self._bufs = {}
         self._symm = {}
+        self._stream = None
+        self.bind_stream()
+
+    def bind_stream(self):
+        """Run the engine on torch's CURRENT stream of this device: the NCCL collectives, the symmetric-memory
+        barriers and torch's own ops in DistributedGraphBuild are enqueued there, and the engine's kernels read
+        and write the same buffers (receive buffers, partial sums).  Called at construction and at the start
+        of every step (a no-op unless the caller switched streams in between)."""
+        s = int(self.torch.cuda.current_stream(self.device).cuda_stream)
+        if s != self._stream:
+            # stream 0 is the legacy default stream: the ABI spells it cudaStreamLegacy (0x1), NULL means "ctx-owned"
+            self.engine.set_stream(s if s else 1)
+            self._stream = s
 
     def _buf(self, name, n, dtype):
         t = self._bufs.get(name)
@@ -248,6 +261,8 @@ class DistributedGraphBuild(object):
         returns the local sizes.  `self.last` keeps what fetch_local needs."""
         self.phase_ms = {}
         self._t_last = None
+        if hasattr(self.b, "bind_stream"):
+            self.b.bind_stream()
         self._mark(None)
         if self.exchange_runs and hasattr(self.b, "group"):
             sizes = self._step_runs(params, rec)

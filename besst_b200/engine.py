@@ -203,8 +203,8 @@ class CudaEngine(object):
     # -- batched GapEstimator --------------------------------------------------------------
     def gapest_batch(self, params, mean_obs, len1, len2):
         mean_obs = np.ascontiguousarray(mean_obs, dtype=np.float64)
-        len1 = np.ascontiguousarray(len1, dtype=np.int32)
-        len2 = np.ascontiguousarray(len2, dtype=np.int32)
+        len1 = np.ascontiguousarray(len1, dtype=np.float64)
+        len2 = np.ascontiguousarray(len2, dtype=np.float64)
         gap = np.zeros(mean_obs.shape[0], dtype=np.int32)
         sd = np.zeros(mean_obs.shape[0], dtype=np.float64)
         self._check(self._L.besst_gapest_batch(self._ctx, C.byref(params), mean_obs.ctypes.data, len1.ctypes.data,
@@ -214,8 +214,8 @@ class CudaEngine(object):
 
     def func_of_d_batch(self, params, d, len1, len2):
         d = np.ascontiguousarray(d, dtype=np.float64)
-        len1 = np.ascontiguousarray(len1, dtype=np.int32)
-        len2 = np.ascontiguousarray(len2, dtype=np.int32)
+        len1 = np.ascontiguousarray(len1, dtype=np.float64)
+        len2 = np.ascontiguousarray(len2, dtype=np.float64)
         out = np.zeros(d.shape[0], dtype=np.float64)
         self._check(self._L.besst_gapest_func_batch(self._ctx, C.byref(params), d.ctypes.data, len1.ctypes.data,
                                                     len2.ctypes.data, d.shape[0], out.ctypes.data), "besst_gapest_func_batch")
@@ -223,8 +223,8 @@ class CudaEngine(object):
 
     def trsk_sd_batch(self, params, gap, len1, len2):
         gap = np.ascontiguousarray(gap, dtype=np.float64)
-        len1 = np.ascontiguousarray(len1, dtype=np.int32)
-        len2 = np.ascontiguousarray(len2, dtype=np.int32)
+        len1 = np.ascontiguousarray(len1, dtype=np.float64)
+        len2 = np.ascontiguousarray(len2, dtype=np.float64)
         sd = np.zeros(gap.shape[0], dtype=np.float64)
         self._check(self._L.besst_trsk_sd_batch(self._ctx, C.byref(params), gap.ctypes.data, len1.ctypes.data,
                                                 len2.ctypes.data, gap.shape[0], sd.ctypes.data), "besst_trsk_sd_batch")

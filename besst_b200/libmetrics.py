@@ -150,7 +150,9 @@ def get_metrics(bam_file, param, Information, engine=None):
 
     # contamination verdict (libmetrics.py:86-128)
     n_contamine = float(m.cont_n)
-    if m.cont_n > 2 or m.cont_mean or m.cont_sd:
+    if m.cont_n_before > 2:   # :91-110
+        print('Contamine mean before filtering :', m.cont_mean_before, file=Information)
+        print('Contamine stddev before filtering: ', m.cont_sd_before, file=Information)
         print('Contamine mean converged:', m.cont_mean, file=Information)
         print('Contamine std_est converged: ', m.cont_sd, file=Information)
     ratio = 2 * n_contamine / float(m.cont_mapped) if m.cont_mapped > 0 else 0

@@ -76,11 +76,10 @@ def PreCalcMLvaluesOfdLongContigs(mean, stdDev, readLen, engine=None):
     if d_upper < d_lower:
         return table
     ds = np.arange(d_lower, d_upper + 1, dtype=np.float64)
-    # contig lengths travel as int32 across the ABI: mean + 4 stdDev must be integral for the batched form
-    c = mean + 4 * stdDev
-    if float(c) != float(int(c)):
-        raise ValueError("PreCalcMLvaluesOfdLongContigs: mean + 4*stdDev must be an integer (got %r)" % (c,))
-    f = func_of_d_batch(mean, stdDev, readLen, ds, int(c), int(c), engine=engine)
+    # c1 = c2 = mean + 4 stdDev as a float: the call site passes ESTIMATED library parameters
+    # (mu_adj, sigma_adj of get_metrics), so the length is never integral; lengths are fp64 across the ABI
+    c = float(mean + 4 * stdDev)
+    f = func_of_d_batch(mean, stdDev, readLen, ds, c, c, engine=engine)
     prev_obs = d_lower
     for d, func_of_d in zip(range(d_lower, d_upper + 1), f.tolist()):
         obs = int(round(func_of_d, 0))

@@ -54,7 +54,7 @@
 extern "C" {
 #endif
 
-#define BESST_ABI_VERSION 3
+#define BESST_ABI_VERSION 4
 
 #define BESST_OK 0
 #define BESST_E_INVALID -1  /* bad argument */
@@ -198,6 +198,8 @@ typedef struct besst_libmetrics_out {
     int64_t cont_n;           /* n_contamine after trim */
     double cont_mean, cont_sd;
     int64_t records_scanned;  /* records visited by the capped scans */
+    int64_t cont_n_before;    /* len(contamination_reads) before the trim loop (:89) */
+    double cont_mean_before, cont_sd_before;   /* :92-95, printed to Information; 0 unless cont_n_before > 2 */
 } besst_libmetrics_out;
 
 typedef struct besst_ctx besst_ctx;
@@ -294,19 +296,21 @@ int besst_libmetrics(besst_ctx* ctx, const besst_lib_params* params, const besst
                      const int64_t* ref_lengths, int64_t n_refs, int32_t want_isize,
                      besst_libmetrics_out* out, double* adjusted_distribution, int64_t cap);
 
-/* batched GapEstimator + tr_sk_std_dev (host arrays in, host arrays out) */
+/* batched GapEstimator + tr_sk_std_dev (host arrays in, host arrays out).  Contig lengths are fp64
+ * like every other argument of the mathstats functions: MakeScaffolds.py:68 passes c1 = c2 =
+ * mean + 4*stdDev of the ESTIMATED library parameters, which is never integral. */
 int besst_gapest_batch(besst_ctx* ctx, const besst_lib_params* params, const double* mean_obs,
-                       const int32_t* len1, const int32_t* len2, int64_t n,
+                       const double* len1, const double* len2, int64_t n,
                        int32_t* gap_out, double* sd_out);
 
 /* d[i] + sigma^2 g'(d[i])/g(d[i]) for contig lengths len1[i], len2[i]: the left-hand side of the ML equation
  * (mathstats funcDGeneral), what PreCalcMLvaluesOfdLongContigs tabulates (MakeScaffolds.py:68) */
-int besst_gapest_func_batch(besst_ctx* ctx, const besst_lib_params* params, const double* d, const int32_t* len1,
-                            const int32_t* len2, int64_t n, double* func_out);
+int besst_gapest_func_batch(besst_ctx* ctx, const besst_lib_params* params, const double* d, const double* len1,
+                            const double* len2, int64_t n, double* func_out);
 
 /* tr_sk_std_dev(mean, sigma, read_len, len1[i], len2[i], gap[i]) (host arrays in/out) */
-int besst_trsk_sd_batch(besst_ctx* ctx, const besst_lib_params* params, const double* gap, const int32_t* len1,
-                        const int32_t* len2, int64_t n, double* sd_out);
+int besst_trsk_sd_batch(besst_ctx* ctx, const besst_lib_params* params, const double* gap, const double* len1,
+                        const double* len2, int64_t n, double* sd_out);
 
 /* run all work of this ctx on a caller-owned CUDA stream (a cudaStream_t passed as void*; NULL
  * restores the ctx's own non-blocking stream; pass cudaStreamLegacy (0x1) for the legacy default stream).  Lets a host framework order the library's kernels with its own

@@ -118,8 +118,8 @@ double besst_oracle_tr_sk_std_dev(double mean, double sd, double r, double c1, d
     return pow(var, 0.5);
 }
 
-int besst_oracle_gapest_batch(const besst_lib_params* p, const double* mean_obs, const int32_t* len1,
-                              const int32_t* len2, int64_t n, int32_t* gap_out, double* sd_out) {
+int besst_oracle_gapest_batch(const besst_lib_params* p, const double* mean_obs, const double* len1,
+                              const double* len2, int64_t n, int32_t* gap_out, double* sd_out) {
     for (int64_t i = 0; i < n; ++i) {
         int32_t g = besst_oracle_gap_estimator(p->mean_ins_size, p->std_dev_ins_size, p->read_len, mean_obs[i],
                                                len1[i], len2[i], p->erf_variant);
@@ -759,8 +759,10 @@ int besst_oracle_libmetrics(const besst_contig_row* rows, int64_t n_contigs, con
         }
         if (i > scanned) scanned = i;
         double mean = 0, sd = 0;
+        out->cont_n_before = n; out->cont_mean_before = 0; out->cont_sd_before = 0;
         if (n > 2) {                                                  /* :91-110 */
             mean_sd(x, n, &mean, &sd);
+            out->cont_mean_before = mean; out->cont_sd_before = sd;  /* :94-95 */
             n = trim_loop(x, n, &mean, &sd, 2);
         }
         out->cont_mapped = counter_total; out->cont_n = n; out->cont_mean = mean; out->cont_sd = sd;

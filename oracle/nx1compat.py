@@ -20,14 +20,16 @@ class Graph(_nx.Graph):
     def node(self):
         return self._node
 
+    # networkx 3 implements edges/nodes/degree as cached properties that store the view object in the
+    # INSTANCE dict, where it would shadow these methods after the first call: build the views directly
     def edges(self, nbunch=None, data=False, default=None):
-        return list(_nx.Graph.edges.__get__(self)(nbunch=nbunch, data=data, default=default))
+        return list(_nx.classes.reportviews.EdgeView(self)(nbunch=nbunch, data=data, default=default))
 
     def edges_iter(self, nbunch=None, data=False, default=None):
         return iter(self.edges(nbunch, data, default))
 
     def nodes(self, data=False):
-        return list(_nx.Graph.nodes.__get__(self)(data=data))
+        return list(_nx.classes.reportviews.NodeView(self)(data=data))
 
     def nodes_iter(self, data=False):
         return iter(self.nodes(data))

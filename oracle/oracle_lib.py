@@ -93,8 +93,8 @@ def libmetrics(rows, params, batch, ref_lengths, want_isize, cap=1 << 20):
 def gapest_batch(params, mean_obs, len1, len2):
     L = lib()
     mean_obs = np.ascontiguousarray(mean_obs, dtype=np.float64)
-    len1 = np.ascontiguousarray(len1, dtype=np.int32)
-    len2 = np.ascontiguousarray(len2, dtype=np.int32)
+    len1 = np.ascontiguousarray(len1, dtype=np.float64)
+    len2 = np.ascontiguousarray(len2, dtype=np.float64)
     gap = np.zeros(mean_obs.shape[0], dtype=np.int32)
     sd = np.zeros(mean_obs.shape[0], dtype=np.float64)
     L.besst_oracle_gapest_batch(C.byref(params), mean_obs.ctypes.data, len1.ctypes.data, len2.ctypes.data,

@@ -93,6 +93,31 @@ def test_records_straddling_inflate_windows(tmp_path, monkeypatch):
         _assert_same(bamio.read_bam_native(path, threads=3), py)
 
 
+def test_slices_keep_the_native_buffers_alive(tmp_path):
+    """The zero-copy column views own a reference to the native handle through ndarray.base, so a slice
+    (or a single column) outlives the parent batch."""
+    import gc
+    rng = np.random.default_rng(3)
+    refs = [("c%d" % i, 5000 + i) for i in range(9)]
+    path = str(tmp_path / "o.bam")
+    write_bam(path, refs, _random_records(rng, 6000, len(refs)), block_bytes=3000)
+    want = bamio.read_bam(path)
+    import weakref
+    batch = bamio.read_bam_native(path, threads=2)
+    alive = weakref.ref(batch._owner)
+    part = batch.slice(1000, 3000)
+    col = batch.pos
+    del batch
+    gc.collect()
+    assert alive() is not None and alive().ptr is not None   # held by the views, not by the batch
+    junk = [np.full(6000, -7, np.int32) for _ in range(64)]   # would overwrite the freed heap
+    assert np.array_equal(part.pos, want.pos[1000:3000]) and np.array_equal(part.flag, want.flag[1000:3000])
+    assert np.array_equal(col, want.pos)
+    del part, col, junk
+    gc.collect()
+    assert alive() is None   # and released with the last view
+
+
 def test_native_reader_rejects_garbage(tmp_path):
     p = tmp_path / "x.bam"
     p.write_bytes(b"this is not a BAM file, not even gzip" * 10)

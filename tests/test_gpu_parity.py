@@ -334,10 +334,10 @@ def test_libmetrics_matches_oracle_and_hits_the_sample_cap(cuda_engine):
     rc, m, adj = cuda_engine.libmetrics(rows, params, batch, batch.lengths, True)
     assert rc == rc_o == 0
     assert m_o.n_samples == 1000000
-    for f in ("n_samples", "n_trimmed", "median_adj", "mode_adj", "n_bins", "cont_mapped", "cont_n", "records_scanned"):
+    for f in ("n_samples", "n_trimmed", "median_adj", "mode_adj", "n_bins", "cont_mapped", "cont_n", "records_scanned", "cont_n_before"):
         assert getattr(m, f) == getattr(m_o, f), f
     for f in ("mean_before", "sd_before", "mean_converged", "sd_converged", "skewness", "mu_adj", "sigma_adj",
-              "skew_adj", "cont_mean", "cont_sd"):
+              "skew_adj", "cont_mean", "cont_sd", "cont_mean_before", "cont_sd_before"):
         a, b = getattr(m, f), getattr(m_o, f)
         assert abs(a - b) <= 1e-9 * max(abs(b), 1e-12), (f, a, b)
     np.testing.assert_allclose(adj, adj_o, rtol=1e-12, atol=0)
@@ -470,6 +470,24 @@ def test_trsk_sd_batch_matches_oracle(cuda_engine):
     np.testing.assert_allclose(got, want, rtol=helpers.FLOAT_RTOL, atol=0)
 
 
+def test_gapest_batch_with_fractional_contig_lengths(cuda_engine):
+    """mathstats takes float lengths (c1 = c2 = mean + 4*stdDev at MakeScaffolds.py:68): fp64 across the ABI."""
+    rng = np.random.default_rng(5)
+    n = 2000
+    p = abi.make_params("rf", 11, 99.37, 2987.4142135, 512.7182818, 6000.0)
+    mo = rng.uniform(200.0, 3400.0, n)
+    l1 = rng.uniform(1100.0, 40000.0, n)
+    l2 = rng.uniform(1100.0, 40000.0, n)
+    gap, sd = cuda_engine.gapest_batch(p, mo, l1, l2)
+    gap_o, sd_o = oracle_lib.gapest_batch(p, mo, l1, l2)
+    assert np.array_equal(gap, gap_o)
+    np.testing.assert_allclose(sd, sd_o, rtol=helpers.FLOAT_RTOL, atol=0)
+    L = oracle_lib.lib()
+    want = np.array([L.besst_oracle_gap_estimator(2987.4142135, 512.7182818, 99.37, float(m), float(a), float(b), abi.ERF_AS7126)
+                     for m, a, b in zip(mo[:200], l1[:200], l2[:200])])
+    assert np.array_equal(gap[:200], want)   # the lengths were not truncated on the way
+
+
 def test_scalar_dropins(cuda_engine):
     from besst_b200 import param_est
     L = oracle_lib.lib()
@@ -479,7 +497,9 @@ def test_scalar_dropins(cuda_engine):
     assert sd == pytest.approx(L.besst_oracle_tr_sk_std_dev(3000.0, 500.0, 100.0, 6000.0, 7000.0, 420.0, abi.ERF_AS7126), rel=1e-6)
 
 
-@pytest.mark.parametrize("mean,sd,r", [(3000.0, 500.0, 100.0), (550.0, 50.0, 100.0), (8000.0, 1200.0, 150.0), (350.0, 100.0, 75.0)])
+@pytest.mark.parametrize("mean,sd,r", [(3000.0, 500.0, 100.0), (550.0, 50.0, 100.0), (8000.0, 1200.0, 150.0), (350.0, 100.0, 75.0),
+                                       # what MakeScaffolds.py:68 really passes: get_metrics' estimates (mu_adj, sigma_adj, mean read length)
+                                       (2987.4142135, 512.7182818, 99.37), (561.0307, 47.93, 100.0)])
 def test_precalc_table_of_long_contig_gaps_equals_restated_mathstats(cuda_engine, mean, sd, r):
     """GC.PreCalcMLvaluesOfdLongContigs (MakeScaffolds.py:68): every d of the table in one kernel launch."""
     import os
