@@ -1,21 +1,28 @@
 #!/usr/bin/env python
 """Benchmark of the hot path: read-pairs/s through graph build + GapEst.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME]
 
-One "step" = one pass of the hot path (records -> CSR edges + link statistics +
-KS/GapEst score) over one synthetic library (SURVEY.md 8d generator).  At N=1
-the workload is BASELINE.json's config 3 (100k contigs / 200 M MP pairs, rf):
-the configuration the north-star target (>= 100 M read-pairs/s) is quoted on.
-At N>1 every rank owns one such library slice (weak scaling), link tuples are
-exchanged once with an NCCL all-to-all keyed by the edge hash.
+One "step" = one pass of the hot path (records -> CSR edges + link statistics + KS/GapEst score) over
+every library of the workload, in sequence (SURVEY.md 8d generator).  Workloads follow BASELINE.json's
+`configs`:
 
-Prints ONE JSON line (rank 0).  `value` = whole-job read-pairs/s with the
-records resident in HBM; `e2e` = the same through the C-ABI call with pinned
-HOST buffers (H2D of the record columns and D2H of the result inside the timed
-region); `roofline` = the dominant kernel against the measured HBM peak;
-`cpu_baseline` = the C oracle (a port of the reference's Python path) on one
-host core over a bounded sample.  `--impl reference` times that CPU port alone.
+  N=1  config3  100 k contigs / 200 M MP pairs (rf), 1 library  -- the configuration the north-star
+                target (>= 100 M read-pairs/s) is quoted on
+  N=2  config3  scaled x2 (weak): ONE global library of 200 k contigs / 400 M pairs
+  N=4  config4  100 k contigs / 400 M pairs: a PE library, then a PE-contaminated MP library that sees
+                multi-contig scaffolds (the state a previous pass leaves behind)
+  N=8  config5  1 M contigs / 2 B pairs: three libraries (PE 550/50, MP 3000/500, MP 8000/1200)
+
+At N>1 every library is ONE global BAM-ordered file range-partitioned over the ranks (pairs and
+duplicates span the cuts); whole runs of links are exchanged once by edge hash (stored straight into
+the destination GPU's memory over NVLink), every rank builds its share of the edges.
+
+Prints ONE JSON line (rank 0).  `value` = whole-job read-pairs/s with the records resident in HBM;
+`e2e` = the same through the C-ABI call with pinned HOST buffers (H2D of the record columns and D2H of
+the result inside the timed region); `roofline` = the dominant kernel against the measured HBM peak;
+`cpu_baseline` = the C oracle (a port of the reference's Python path) on host cores; `parity` = the CUDA
+result of the WHOLE workload against that oracle.  `--impl reference` times that CPU port alone.
 """
 from __future__ import annotations
 
@@ -29,22 +36,34 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-# NCCL's version banner (NCCL_DEBUG=VERSION/WARN/INFO) goes to stdout: keep the one JSON line alone
-os.environ.pop("NCCL_DEBUG", None)
-if os.environ.get("BESST_NCCL_DEBUG"):
-    os.environ["NCCL_DEBUG"] = os.environ["BESST_NCCL_DEBUG"]
+# NCCL's banner (NCCL_DEBUG=VERSION/WARN/INFO) would land on stdout next to the one JSON line: send it to stderr
+if os.environ.get("NCCL_DEBUG") and not os.environ.get("NCCL_DEBUG_FILE"):
+    os.environ["NCCL_DEBUG_FILE"] = "/dev/stderr"
 
 import numpy as np  # noqa: E402
 
+# name: contigs, libraries (orientation, mu, sigma, contamination, pairs), weak = scale contigs/pairs with the world size
 WORKLOADS = {
-    # name: (synth config, description)
-    "config3": ("config3", "synthetic 100k contigs / 200 M MP pairs (rf), 1 library"),
-    "config2": ("config2", "synthetic 10k contigs / 20 M PE pairs, 1 library"),
-    "small": ("small_mp", "synthetic 400 contigs / 200 k MP pairs (debug)"),
+    "config3": dict(desc="synthetic 100k contigs / 200 M MP pairs (rf), 1 library", contigs=100_000, weak=True,
+                    libs=[("rf", 3000.0, 500.0, 0.0, 200_000_000)]),
+    "config2": dict(desc="synthetic 10k contigs / 20 M PE pairs, 1 library", contigs=10_000, weak=True,
+                    libs=[("fr", 550.0, 50.0, 0.0, 20_000_000)]),
+    "config4": dict(desc="two libraries PE + MP with PE-contamination, 100k contigs / 400 M pairs", contigs=100_000, weak=False,
+                    libs=[("fr", 550.0, 50.0, 0.0, 200_000_000), ("rf", 3000.0, 500.0, 0.25, 200_000_000)]),
+    "config5": dict(desc="1 M contigs / 2 B read pairs, 3 libraries", contigs=1_000_000, weak=False,
+                    libs=[("fr", 550.0, 50.0, 0.0, 667_000_000), ("rf", 3000.0, 500.0, 0.0, 667_000_000),
+                          ("rf", 8000.0, 1200.0, 0.0, 666_000_000)]),
+    "small": dict(desc="synthetic 400 contigs / 200 k MP pairs (debug)", contigs=400, weak=True,
+                  libs=[("rf", 3000.0, 500.0, 0.0, 200_000)]),
+    "small2": dict(desc="synthetic 3000 contigs, PE then contaminated MP, 2 x 1 M pairs (debug)", contigs=3000, weak=False,
+                   libs=[("fr", 550.0, 50.0, 0.0, 1_000_000), ("rf", 3000.0, 500.0, 0.25, 1_000_000)]),
 }
+DEFAULT_WORKLOAD = {1: "config3", 2: "config3", 4: "config4", 8: "config5"}
 RECORD_BYTES = 4 + 4 + 4 + 4 + 4 + 2 + 1   # tid mtid pos mpos qlen flag mapq (tlen is only read by libmetrics)
 TUPLE_BYTES = 16
-CPU_SAMPLE_RECORDS = 40_000_000
+REFERENCE_SAMPLE_PAIRS = 10_000_000
+RESULT_FIELDS = ("edge_u", "edge_v", "nr_links", "obs_sum", "obs_sq", "first_idx", "row_ptr", "gap", "score", "ks", "sd_obs",
+                 "sd_model", "fishy", "flags", "obs_u", "obs_v", "aligned_len")
 
 
 def measured_peak_gbs():
@@ -122,6 +141,47 @@ def checksum(res):
     return h.hexdigest()[:16]
 
 
+def result_bytes(res, abi):
+    return sum(int(getattr(res, f).nbytes) for f in RESULT_FIELDS) + 8 * abi.N_COUNTERS
+
+
+class Library(object):
+    """One library of the workload on this rank: device-resident record columns + its contig table slot."""
+
+    def __init__(self, index, spec, n_contigs, world, rank, dev, synth, abi, first_library_rows, legacy_single):
+        import torch
+        orientation, mu, sigma, cont, n_pairs = spec
+        self.index, self.orientation, self.mu, self.sigma, self.cont = index, orientation, mu, sigma, cont
+        seed = synth.SEED0 + 2 + 100 * index
+        if legacy_single:   # N=1 single-library workloads: the very library of the round-1 bench lines
+            lib = synth.make_library(n_contigs, n_pairs, orientation, mu, sigma, cont, seed=seed, device=dev, with_names=False)
+        else:
+            lib = synth.make_library_slice(n_contigs, n_pairs, orientation, mu, sigma, cont, synth.SEED0 + 2, rank, world, device=dev,
+                                           read_seed=index)
+        self.cols = {k: v for k, v in lib.cols.items() if k != "tlen"}
+        self.tlen = lib.cols["tlen"] if index == 0 and world == 1 else None   # only the libmetrics leg reads it
+        self.n_rec = lib.n_records
+        self.lengths = lib.lengths.numpy()
+        threshold = mu + 4 * sigma
+        if index == 0:
+            self.rows, self.n_scaf, self.n_large = first_library_rows(self.lengths, threshold)
+            self.state = "first library (one contig per scaffold)"
+        else:
+            self.rows, self.n_scaf, self.n_large = synth.later_library_rows(self.lengths, threshold, seed=synth.SEED0 + 31 * index)
+            self.state = "later library (runs of 1-3 contigs joined into scaffolds, 1/17 removed)"
+        self.params = library_params(abi, orientation, mu, sigma)
+        ptrs = {k: v.data_ptr() for k, v in self.cols.items()}
+        ptrs["tlen"] = self.tlen.data_ptr() if self.tlen is not None else 0
+        ptrs["n"] = self.n_rec
+        self.rec_dev = abi.make_records(ptrs, on_device=True)
+        del lib
+        torch.cuda.synchronize()
+
+    def describe(self):
+        return {"orientation": self.orientation, "mean_ins_size": self.mu, "std_dev_ins_size": self.sigma,
+                "contamination": self.cont, "records_this_rank": self.n_rec, "contig_table": self.state}
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -132,53 +192,46 @@ def run_ours(args):
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if world != args.gpus:
-        args.gpus = world
+    args.gpus = world
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+        host_group = dist.new_group(backend="gloo")   # host-side object gathers of the parity leg
+    name = args.workload or DEFAULT_WORKLOAD.get(world, "config3")
+    W = WORKLOADS[name]
+    mult = world if W["weak"] else 1
+    n_contigs = max(2, int(W["contigs"] * mult * args.scale))
+    specs = [(o, mu, sd, c, max(1000, int(p * mult * args.scale))) for o, mu, sd, c, p in W["libs"]]
+    legacy_single = world == 1 and len(specs) == 1
 
-    cfg_name, desc = WORKLOADS[args.workload]
-    n_contigs, n_pairs, orientation, mu, sigma, cont = synth.CONFIGS[cfg_name]
-    n_contigs = max(2, int(n_contigs * args.scale))
-    n_pairs = max(1000, int(n_pairs * args.scale))
     t_gen = time.time()
-    lib = synth.make_library(n_contigs, n_pairs, orientation, mu, sigma, cont,
-                             seed=synth.SEED0 + 2 + 1000 * rank, device=dev, with_names=False)
-    torch.cuda.synchronize()
+    libs = [Library(i, s, n_contigs, world, rank, dev, synth, abi, first_library_rows, legacy_single) for i, s in enumerate(specs)]
     t_gen = time.time() - t_gen
-    n_rec = lib.n_records
-    pairs_per_rank = lib.n_pairs
-    contig_threshold = mu + 4 * sigma
-    lengths_all = [lib.lengths.numpy()]
-    if world > 1:   # global contig table = concatenation of every rank's contig block
-        lengths_all = [synth.make_contigs(n_contigs, synth.SEED0 + 2 + 1000 * r)[0].numpy() for r in range(world)]
-    rows, n_scaf, n_large = first_library_rows(np.concatenate(lengths_all), contig_threshold)
-    cols = dict(lib.cols)
-    if world > 1:
-        cols["tid"] = cols["tid"] + rank * n_contigs
-        cols["mtid"] = cols["mtid"] + rank * n_contigs
+    n_rec = sum(L.n_rec for L in libs)
+    pairs_this_rank = n_rec / 2.0
 
     eng = CudaEngine(local_rank)
-    eng.set_contigs(rows, n_scaf, n_large)
+    for L in libs:
+        eng.select_table(L.index)
+        eng.set_contigs(L.rows, L.n_scaf, L.n_large)
     # run the library on torch's current stream: CUDA events recorded there bracket its kernels and
     # the NCCL collectives alike
     torch.cuda.synchronize()
     torch.cuda.set_stream(torch.cuda.Stream(device=dev))
     eng.set_stream(torch.cuda.current_stream().cuda_stream)
-    params = library_params(abi, orientation, mu, sigma)
-    ptrs = {k: v.data_ptr() for k, v in cols.items()}
-    ptrs["n"] = n_rec
-    rec_dev = abi.make_records(ptrs, on_device=True)
 
     runner = None
     if world > 1:
         from besst_b200.dist import CudaBackend, DistributedGraphBuild
         runner = DistributedGraphBuild(CudaBackend(eng, dev), rank, world)
-        step = lambda: runner.step(params, rec_dev)      # noqa: E731
-    else:
-        step = lambda: eng.build(params, rec_dev)        # noqa: E731
+
+    def build(L, rec):
+        eng.select_table(L.index)
+        return runner.step(L.params, rec) if runner is not None else eng.build(L.params, rec)
+
+    def step():
+        return [build(L, L.rec_dev) for L in libs]
 
     def barrier():
         if world > 1:
@@ -194,16 +247,15 @@ def run_ours(args):
     sampler.start()
     time.sleep(0.25)
     prof = {}
-    dev_ms = []
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     t0 = time.perf_counter()
     ev0.record()
     for _ in range(args.steps):
-        sizes = step()
-        for name, ms in eng.kernel_profile():
-            prof.setdefault(name, []).append(ms)
-        dev_ms.append(eng.timing()[0] if world == 1 else 0.0)
+        for L in libs:
+            build(L, L.rec_dev)
+            for kname, ms in eng.kernel_profile():
+                prof.setdefault(kname, []).append(ms)
     ev1.record()
     barrier()
     t1 = time.perf_counter()
@@ -212,7 +264,7 @@ def run_ours(args):
     # (untimed) until there are enough clock samples under load
     t_load = time.perf_counter()
     if world > 1:   # collectives inside: every rank must run the same number of steps
-        for _ in range(80):
+        for _ in range(max(4, min(80, int(0.6 / max((t1 - t0) / args.steps, 1e-3))))):
             step()
     else:
         while len(sampler.rows) < 6 and time.perf_counter() - t_load < 3.0:
@@ -221,42 +273,62 @@ def run_ours(args):
     clocks = sampler.finish()
     wall = t1 - t0
     elapsed = ev0.elapsed_time(ev1) * 1e-3    # device time on the launching stream
+    n_links = sum(int(s.n_links) for s in sizes)
+    n_edges = sum(int(s.n_edges) for s in sizes)
+    n_ll = sum(int(s.n_ll_links) for s in sizes)
+    n_rec_total = n_rec
     if world > 1:
         t = torch.tensor([elapsed, wall], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         elapsed, wall = float(t[0].item()), float(t[1].item())
-        tot = torch.tensor([pairs_per_rank, launches_timed, int(sizes.n_links), int(sizes.n_edges), int(sizes.n_ll_links)],
-                           device=dev, dtype=torch.float64)
+        tot = torch.tensor([pairs_this_rank, launches_timed, n_links, n_edges, n_ll, n_rec], device=dev, dtype=torch.float64)
         dist.all_reduce(tot, op=dist.ReduceOp.SUM)
         total_pairs, launches_timed = float(tot[0].item()), int(tot[1].item())
+        g_links, g_edges, g_ll, n_rec_total = int(tot[2].item()), int(tot[3].item()), int(tot[4].item()), int(tot[5].item())
     else:
-        total_pairs = float(pairs_per_rank)
+        total_pairs = float(pairs_this_rank)
+        g_links, g_edges, g_ll = n_links, n_edges, n_ll
     ms_per_step = 1e3 * elapsed / args.steps
     value = total_pairs * args.steps / elapsed
 
-    # ---- roofline of the dominant kernel (per-launch CUDA events, timed region) ---------
+    # one more (untimed) step with device-synchronised phase marks: where the multi-GPU step spends its time
+    dist_phases = None
+    if runner is not None:
+        runner.timing = True
+        acc = {}
+        for L in libs:
+            build(L, L.rec_dev)
+            for k, v in runner.phase_ms.items():
+                acc[k] = acc.get(k, 0.0) + v
+        runner.timing = False
+        dist_phases = {k: round(v, 3) for k, v in acc.items()}
+        barrier()
+
+    # ---- roofline of the dominant kernel (per-launch CUDA events, timed region; this rank's share) ---------
     per_step = {k: float(np.sum(v)) / args.steps for k, v in prof.items()}
     n_launch = {k: len(v) / args.steps for k, v in prof.items()}
-    n_links, n_edges, n_ll = int(sizes.n_links), int(sizes.n_edges), int(sizes.n_ll_links)
-    alg_bytes = {   # algorithmic bytes per launch of each kernel (DESIGN.md "Kernels")
-        "k_extract_links": RECORD_BYTES * n_rec + TUPLE_BYTES * n_links + 48 * ((n_rec + 127) // 128),
-        "k_compact_tuples": 2 * TUPLE_BYTES * n_links + 8 * ((n_rec + 127) // 128),
+    n_tiles = sum((L.n_rec + 127) // 128 for L in libs)
+    alg_bytes_step = {   # algorithmic bytes per STEP of each kernel family on this rank (DESIGN.md "Kernels")
+        "k_extract_links": RECORD_BYTES * n_rec + TUPLE_BYTES * (n_links if world == 1 else 0) + 48 * n_tiles,
+        "k_compact_tuples": 2 * TUPLE_BYTES * n_links + 8 * n_tiles,
         "k_radix_sweep": (8 + 8) * n_links,       # packed sort word (key | BAM index): 8 B in, 8 B out per pass
         "k_radix_hist": 8 * n_links,
         "k_edge_reduce": (8 + 8) * n_links + 64 * n_edges,    # k_edge_gather: grouped (o1,o2) in, obs_u/obs_v out
-        "k_group_blocks": (16 + 8) * n_links + 8 * ((n_rec + 127) // 128),   # scratch tuples + tile offsets in, grouped observations out
-        "k_score_keys": (8 + 8) * n_ll / 3.0 + 13 * n_edges,   # 3 launches: LL scan (2, over edges) + key build
+        "k_group_blocks": (16 + 8) * n_links + 8 * n_tiles,   # scratch tuples + tile offsets in, grouped observations out
+        "k_score_keys": (8 + 8) * n_ll / 3.0 + 13 * n_edges,   # LL scan (over edges) + key build
         "k_ks_block": (4 + 4) * n_ll + 8 * n_edges,           # obs_u, obs_v of the scored links in, one double per edge out
         "k_ks_sort": (4 + 4) * n_ll,
         "k_ks_eval": (4 + 4) * n_ll + 8 * n_edges,
         "k_gapest": 64 * n_edges,
         "k_heads": 8 * n_links,
     }
+    if world > 1:   # this rank's extraction produced the links it SENT, not the ones it owns now: use the global mean
+        alg_bytes_step["k_extract_links"] += TUPLE_BYTES * (g_links // world)
     traffic = {}
     try:   # DRAM bytes per launch from the committed ncu capture of this workload (profiles/ncu_traffic.json)
         with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as fh:
             tj = json.load(fh)
-        if tj.get("workload") == args.workload and args.scale == 1.0:
+        if tj.get("workload") == name and args.scale == 1.0 and world == 1:
             traffic = tj
     except Exception:
         pass
@@ -264,119 +336,175 @@ def run_ours(args):
     peak, peak_src = measured_peak_gbs()
     roofline = None
     if dominant is not None:
-        avg_ms = per_step[dominant] / max(n_launch[dominant], 1)
-        ach = alg_bytes.get(dominant, 0) / (avg_ms * 1e-3) / 1e9 if avg_ms > 0 else 0.0
+        launches = max(n_launch[dominant], 1)
+        avg_ms = per_step[dominant] / launches
+        per_launch = alg_bytes_step.get(dominant, 0) / launches
+        ach = per_launch / (avg_ms * 1e-3) / 1e9 if avg_ms > 0 else 0.0
         roofline = {"bound": "hbm", "kernel": dominant, "achieved": round(ach, 1), "peak": peak, "unit": "GB/s",
                     "frac": round(ach / peak, 4), "traffic": traffic.get(dominant), "peak_source": peak_src,
                     "avg_launch_ms": round(avg_ms, 4), "launches_per_step": n_launch[dominant],
-                    "algorithmic_bytes_per_launch": int(alg_bytes.get(dominant, 0)),
-                    "share_of_step": round(per_step[dominant] / max(sum(per_step.values()), 1e-9), 3)}
+                    "algorithmic_bytes_per_launch": int(per_launch),
+                    "share_of_step": round(per_step[dominant] / max(sum(per_step.values()), 1e-9), 3),
+                    "whole_step": {"bytes_alg": int(48 * pairs_this_rank + 8 * n_links + 64 * n_edges + 32 * n_contigs * len(libs)),
+                                   "note": "SURVEY 8d: 48 B/pair + 8 B/link + 64 B/edge + 32 B/contig over the device-resident step"}}
+        roofline["whole_step"]["frac"] = round(roofline["whole_step"]["bytes_alg"] / (ms_per_step * 1e-3) / 1e9 / peak, 4)
     kernels = {k: {"ms_per_step": round(per_step[k], 4), "launches_per_step": n_launch[k],
-                   "GBps": round(alg_bytes[k] * n_launch[k] / (per_step[k] * 1e-3) / 1e9, 1) if k in alg_bytes and per_step[k] > 0 else None}
+                   "GBps": round(alg_bytes_step[k] / (per_step[k] * 1e-3) / 1e9, 1) if k in alg_bytes_step and per_step[k] > 0 else None}
                for k in sorted(per_step, key=per_step.get, reverse=True)}
 
-    # ---- end to end through the C ABI with pinned host buffers (N=1 path per rank) -------
+    # ---- library metrics (K7) on the first library, records resident: the metric "when mu, sigma are not given" --
+    libmetrics = None
+    if world == 1 and libs[0].tlen is not None and not args.no_libmetrics:
+        try:
+            L0 = libs[0]
+            eng.select_table(7)   # besst_libmetrics uploads its own table (in_largest flags): keep the builds' tables intact
+            eng.libmetrics(L0.rows, L0.params, None, L0.lengths, True, records=L0.rec_dev)   # warm-up
+            torch.cuda.synchronize()
+            reps = 3
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(reps):
+                rc, m, _ = eng.libmetrics(L0.rows, L0.params, None, L0.lengths, True, records=L0.rec_dev)
+            b.record()
+            torch.cuda.synchronize()
+            ms = a.elapsed_time(b) / reps
+            kms = [x for kname, x in eng.kernel_profile() if kname == "k_metrics"]
+            scanned = int(m.records_scanned)
+            libmetrics = {"ms_per_call": round(ms, 4), "records_scanned": scanned, "samples": int(m.n_samples),
+                          "kernel_ms": round(float(np.sum(kms)), 4), "kernel_launches": len(kms),
+                          "algorithmic_bytes": 15 * scanned,
+                          "GBps_kernels": round(15 * scanned / max(float(np.sum(kms)), 1e-6) / 1e6, 1),
+                          "note": "capped BAM-order sampling (libmetrics.py:283-343): the scan stops at the reference's 1e6-sample caps; "
+                                  "host call includes the O(bins) statistics and the read-back"}
+        except Exception as exc:
+            libmetrics = {"error": repr(exc)}
+
+    # ---- end to end through the C ABI with pinned host buffers + CPU baseline + parity, library by library -------
     e2e = None
     cpu_baseline = None
     parity = None
     try:
-        host = {k: torch.empty(v.shape, dtype=v.dtype, pin_memory=True) for k, v in cols.items() if k != "tlen"}
-        for k in host:
-            host[k].copy_(cols[k])
-        torch.cuda.synchronize()
-        hp = {k: v.data_ptr() for k, v in host.items()}
-        hp["tlen"] = 0
-        hp["n"] = n_rec
-        rec_host = abi.make_records(hp, on_device=True)
-        rec_host.on_device = 0
+        max_rec = max(L.n_rec for L in libs)
+        host = {k: torch.empty((max_rec,), dtype=v.dtype, pin_memory=True) for k, v in libs[0].cols.items()}
         e2e_steps = max(1, min(args.steps, 3))
-        if world == 1 and not args.no_e2e:
-            res = None
-            eng.fetch_view(eng.build(params, rec_host))   # warm-up: staging buffers, pinned result buffers
-            barrier()
-            t0 = time.perf_counter()
-            for _ in range(e2e_steps):
-                s = eng.build(params, rec_host)
-                res = eng.fetch_view(s)
-            barrier()
-            t1 = time.perf_counter()
-            d2h = sum(int(getattr(res, f).nbytes) for f in ("edge_u", "edge_v", "nr_links", "obs_sum", "obs_sq",
-                      "first_idx", "row_ptr", "gap", "score", "ks", "sd_obs", "sd_model", "fishy", "flags", "obs_u",
-                      "obs_v", "aligned_len")) + 8 * abi.N_COUNTERS
-            e2e = {"value": pairs_per_rank * e2e_steps / (t1 - t0), "unit": "read-pairs/s",
-                   "h2d_bytes_per_step": RECORD_BYTES * n_rec, "d2h_bytes_per_step": d2h,
-                   "ms_per_step": round(1e3 * (t1 - t0) / e2e_steps, 3), "steps": e2e_steps}
-        # ---- CPU baseline: the C oracle on one host core over a bounded sample -------------
-        if rank == 0 and world == 1 and not args.no_cpu:
+        e2e_time, h2d, d2h = 0.0, 0, 0
+        oracle_s, oracle_pairs = 0.0, 0.0
+        reports = []
+        if (rank == 0 or world > 1) and not args.no_cpu:
             sys.path.insert(0, os.path.join(ROOT, "oracle"))
             import oracle_lib
-            from besst_b200.records import RecordBatch
-            m = min(n_rec, CPU_SAMPLE_RECORDS)
-            arrs = {k: host[k][:m].numpy() for k in host}
-            arrs["flag"] = arrs["flag"].view(np.uint16)
-            sample = RecordBatch(tlen=np.zeros(m, np.int32), **arrs)
-            t0 = time.perf_counter()
-            want, _, _, _ = oracle_lib.graph_build(rows, n_scaf, params, sample)
-            t_cpu = time.perf_counter() - t0
-            cpu_baseline = {"value": (m / 2) / t_cpu, "unit": "read-pairs/s", "cores": 1, "kind": "port",
-                            "sample": "first %d records (%d pairs) of the same library, C oracle "
-                                      "(oracle/besst_oracle.c), %.1f s" % (m, m // 2, t_cpu)}
-            keep = []
-            got = eng.fetch(eng.build(params, abi.make_records(sample, keepalive=keep)))
-            parity = {"sample_records": m, "oracle_digest": checksum(want), "cuda_digest": checksum(got),
-                      "integers_bit_exact": checksum(want) == checksum(got),
-                      "gap_equal": bool(np.array_equal(got.gap, want.gap)),
-                      "score_max_rel_diff": float(np.nanmax(np.abs(got.score - want.score) / np.maximum(np.abs(want.score), 1e-300))) if want.n_edges else 0.0}
-    except Exception as exc:   # pinned allocation can fail on small hosts: say so instead of inventing a number
-        e2e = e2e or {"value": None, "unit": "read-pairs/s", "error": repr(exc)}
-
-    if world > 1:
-        try:
-            e2e_steps = max(1, min(args.steps, 3))
+            if rank == 0:
+                oracle_lib.build()
+            barrier()
+        for L in libs:
+            for k in host:
+                host[k][:L.n_rec].copy_(L.cols[k])
+            torch.cuda.synchronize()
+            hp = {k: v.data_ptr() for k, v in host.items()}
+            hp["tlen"] = 0
+            hp["n"] = L.n_rec
+            rec_host = abi.make_records(hp, on_device=True)
+            rec_host.on_device = 0
 
             def e2e_step():   # host columns in (sliced H2D overlapped with K1 inside the library), this rank's CSR out
-                runner.step(params, rec_host)
-                return runner.fetch_local(view=True)
-            e2e_step()
-            barrier()
-            t0 = time.perf_counter()
-            for _ in range(e2e_steps):
-                res = e2e_step()
-            barrier()
-            dt = time.perf_counter() - t0
-            d2h = sum(int(getattr(res, f).nbytes) for f in ("edge_u", "edge_v", "nr_links", "obs_sum", "obs_sq", "first_idx",
-                      "row_ptr", "gap", "score", "ks", "sd_obs", "sd_model", "fishy", "flags", "obs_u", "obs_v", "aligned_len"))
-            t = torch.tensor([dt], device=dev, dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            b = torch.tensor([RECORD_BYTES * n_rec, d2h], device=dev, dtype=torch.float64)
-            dist.all_reduce(b, op=dist.ReduceOp.SUM)
-            e2e = {"value": total_pairs * e2e_steps / float(t.item()), "unit": "read-pairs/s",
-                   "h2d_bytes_per_step": int(b[0].item()), "d2h_bytes_per_step": int(b[1].item()),
-                   "ms_per_step": round(1e3 * float(t.item()) / e2e_steps, 3), "steps": e2e_steps}
-        except Exception as exc:
-            e2e = {"value": None, "unit": "read-pairs/s", "error": repr(exc)}
+                s = build(L, rec_host)
+                return runner.fetch_local(view=True) if runner is not None else eng.fetch_view(s)
+            if not args.no_e2e:
+                e2e_step()   # warm-up: staging buffers, pinned result buffers
+                barrier()
+                t0 = time.perf_counter()
+                for _ in range(e2e_steps):
+                    res = e2e_step()
+                barrier()
+                e2e_time += time.perf_counter() - t0
+                h2d += RECORD_BYTES * L.n_rec
+                d2h += result_bytes(res, abi)
+            # ---- CPU: the C oracle over the WHOLE library (every rank its own BAM-order slice), then parity ----
+            if not args.no_cpu:
+                from besst_b200.records import RecordBatch
+                arrs = {k: host[k][:L.n_rec].numpy() for k in host}
+                arrs["flag"] = arrs["flag"].view(np.uint16)
+                batch = RecordBatch(tlen=np.zeros(L.n_rec, np.int32), **arrs)
+                if world == 1:
+                    t0 = time.perf_counter()
+                    want, _, _, _ = oracle_lib.graph_build(L.rows, L.n_scaf, L.params, batch)
+                    t_cpu = time.perf_counter() - t0
+                    got = eng.fetch(build(L, L.rec_dev))
+                    scored = (want.flags & abi.EDGE_SCORED) != 0
+                    reports.append({"library": L.index, "records": L.n_rec, "edges": int(want.n_edges), "links": int(want.n_links),
+                                    "oracle_digest": checksum(want), "cuda_digest": checksum(got),
+                                    "integers_bit_exact": checksum(want) == checksum(got),
+                                    "gap_equal": bool(np.array_equal(got.gap[scored], want.gap[scored])),
+                                    "score_max_rel_diff": float(np.nanmax(np.abs(got.score[scored] - want.score[scored]) / np.maximum(np.abs(want.score[scored]), 1e-300))) if scored.any() else 0.0})
+                    oracle_s += t_cpu
+                    oracle_pairs += L.n_rec / 2.0
+                else:
+                    import slice_oracle
+                    build(L, L.rec_dev)
+                    got = slice_oracle.gather_owned(dist, rank, world, runner.fetch_local(), group=host_group)
+                    want = slice_oracle.sliced_oracle(dist, rank, world, L.rows, L.n_scaf, L.params, batch, group=host_group)
+                    if rank == 0:
+                        rep = slice_oracle.compare(got, want)
+                        rep["library"] = L.index
+                        reports.append(rep)
+                        oracle_s += want["seconds"]
+                    oracle_pairs += L.n_rec / 2.0
+                del batch
+        if not args.no_e2e:
+            if world > 1:
+                t = torch.tensor([e2e_time], device=dev, dtype=torch.float64)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                b = torch.tensor([h2d, d2h], device=dev, dtype=torch.float64)
+                dist.all_reduce(b, op=dist.ReduceOp.SUM)
+                e2e_time, h2d, d2h = float(t.item()), int(b[0].item()), int(b[1].item())
+            e2e = {"value": total_pairs * e2e_steps / e2e_time, "unit": "read-pairs/s", "h2d_bytes_per_step": int(h2d),
+                   "d2h_bytes_per_step": int(d2h), "ms_per_step": round(1e3 * e2e_time / e2e_steps, 3), "steps": e2e_steps,
+                   "h2d_GBps_aggregate": round(h2d * e2e_steps / e2e_time / 1e9, 1)}
+        if not args.no_cpu:
+            if world > 1:
+                t = torch.tensor([oracle_pairs], device=dev, dtype=torch.float64)
+                dist.all_reduce(t, op=dist.ReduceOp.SUM)
+                oracle_pairs = float(t.item())
+            if rank == 0:
+                cpu_baseline = {"value": oracle_pairs / max(oracle_s, 1e-9), "unit": "read-pairs/s", "cores": world, "kind": "port",
+                                "sample": "the whole workload (%d pairs), C oracle (oracle/besst_oracle.c), %s, %.1f s"
+                                          % (int(oracle_pairs), "one sequential pass on one core" if world == 1 else
+                                             "every rank scans its BAM-order slice on its own core, slices merged (oracle/slice_oracle.py)", oracle_s)}
+                parity = {"coverage": "whole workload: every library, every record, every link",
+                          "integers_bit_exact": all(r["integers_bit_exact"] for r in reports),
+                          "gap_equal": all(r.get("gap_equal", False) for r in reports),
+                          "score_max_rel_diff": max(r.get("score_max_rel_diff", 0.0) for r in reports), "libraries": reports}
+    except Exception as exc:   # pinned allocation can fail on small hosts: say so instead of inventing a number
+        import traceback
+        traceback.print_exc(file=sys.stderr)
+        e2e = e2e or {"value": None, "unit": "read-pairs/s", "error": repr(exc)}
 
     if rank == 0:
         line = {
             "metric": "read-pairs/s through graph-build+GapEst", "value": value, "unit": "read-pairs/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_per_step, 4),
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32/int64 + f64 (GapEst)",
-            "data": "synthetic",
-            "config": {"workload": desc + (" x%d ranks" % world if world > 1 else ""), "contigs_per_rank": n_contigs,
-                       "pairs_per_rank": pairs_per_rank, "records_per_rank": n_rec, "orientation": orientation,
-                       "mean_ins_size": mu, "std_dev_ins_size": sigma, "accepted_links": n_links, "edges": n_edges, "scored_links": n_ll,
-                       "l2_policy": "inputs (%.1f GB) larger than the 126 MB L2" % (RECORD_BYTES * n_rec / 1e9),
-                       "parallelism": "1 process per GPU; tuples all-to-all by edge hash" if world > 1 else "single GPU"},
+            "higher_is_better": True, "scaling": "weak" if (W["weak"] or world == 1) else "strong", "vs_baseline": None,
+            "dtype": "int32/int64 + f64 (GapEst)", "data": "synthetic",
+            "config": {"workload": "%s: %s%s" % (name, W["desc"], (" -- scaled x%d: ONE global library of %d contigs, range-partitioned in BAM order"
+                                                                  % (world, n_contigs)) if (W["weak"] and world > 1) else ""),
+                       "contigs": n_contigs, "pairs_per_step": int(total_pairs), "records_per_step": n_rec_total,
+                       "libraries": [L.describe() for L in libs],
+                       "accepted_links": g_links, "edges": g_edges, "scored_links": g_ll,
+                       "l2_policy": "inputs (%.1f GB per rank) larger than the 126 MB L2" % (RECORD_BYTES * n_rec / 1e9),
+                       "parallelism": ("1 process per GPU; every library ONE global BAM range-partitioned over the ranks; runs of links "
+                                       "routed by edge hash and stored into the destination GPU's memory by the pack kernel (NVLink peer "
+                                       "stores), one all_gather of sizes, one all_reduce of coverage+counters") if world > 1 else "single GPU"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches_timed),
-            "device_ms_per_step": round(float(np.mean(dev_ms)), 4) if world == 1 else None,
             "wall_ms_per_step": round(1e3 * wall / args.steps, 4),
             "timing": "CUDA events on the launching stream (the library runs on torch's current stream), max over ranks",
-            "dist_phases_ms": ({k: round(v, 3) for k, v in runner.phase_ms.items()} if (runner is not None and runner.timing) else None),
-            "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu_baseline, "parity": parity,
+            "dist_phases_ms": dist_phases,
+            "roofline": roofline, "kernels": kernels, "libmetrics": libmetrics, "cpu_baseline": cpu_baseline, "parity": parity,
             "generate_s": round(t_gen, 2), "impl": "ours",
         }
         print(json.dumps(line))
+        sys.stdout.flush()
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
 
 
@@ -391,29 +519,40 @@ def run_reference(args):
     import oracle_lib
     from besst_b200 import abi, synth
     from besst_b200.contig_table import first_library_rows
-    cfg_name, desc = WORKLOADS[args.workload]
-    n_contigs, n_pairs, orientation, mu, sigma, cont = synth.CONFIGS[cfg_name]
-    frac = min(1.0, (CPU_SAMPLE_RECORDS / 2) / (2.0 * n_pairs)) * args.scale   # 10 M pairs: ~0.5 s per step on one core
-    lib = synth.make_library(max(2, int(n_contigs * frac)), max(1000, int(n_pairs * frac)), orientation, mu, sigma, cont,
-                             seed=synth.SEED0 + 2, device="cpu", with_names=False)
-    batch = lib.to_batch()
-    rows, n_scaf, n_large = first_library_rows(lib.lengths.numpy(), mu + 4 * sigma)
-    params = library_params(abi, orientation, mu, sigma)
+    world = int(os.environ.get("WORLD_SIZE", str(args.gpus)))
+    name = args.workload or DEFAULT_WORKLOAD.get(world, "config3")
+    W = WORKLOADS[name]
+    total = float(sum(s[4] for s in W["libs"]))
+    frac = min(1.0, REFERENCE_SAMPLE_PAIRS / total) * args.scale   # 10 M pairs over all libraries: ~0.5 s per step on one core
+    n_contigs = max(2, int(W["contigs"] * frac))
+    libs = []
+    for i, (orientation, mu, sigma, cont, pairs) in enumerate(W["libs"]):
+        lib = synth.make_library(n_contigs, max(1000, int(pairs * frac)), orientation, mu, sigma, cont,
+                                 seed=synth.SEED0 + 2 + 100 * i, device="cpu", with_names=False)
+        lengths = lib.lengths.numpy()
+        rows, n_scaf, _ = first_library_rows(lengths, mu + 4 * sigma) if i == 0 else synth.later_library_rows(lengths, mu + 4 * sigma, seed=synth.SEED0 + 31 * i)
+        libs.append((lib.to_batch(), rows, n_scaf, library_params(abi, orientation, mu, sigma), lib.n_pairs))
+    n_pairs = sum(l[4] for l in libs)
+
+    def step():
+        for batch, rows, n_scaf, params, _ in libs:
+            oracle_lib.graph_build(rows, n_scaf, params, batch)
     for _ in range(min(args.warmup, 1)):
-        oracle_lib.graph_build(rows, n_scaf, params, batch)
+        step()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        res, _, _, _ = oracle_lib.graph_build(rows, n_scaf, params, batch)
+        step()
     dt = time.perf_counter() - t0
-    value = lib.n_pairs * args.steps / dt
-    sample = "%d contigs / %d pairs (%.2f%% of the workload, same generator), C oracle port, 1 core" % (
-        len(lib.names), lib.n_pairs, 100.0 * frac)
+    value = n_pairs * args.steps / dt
+    sample = "%d contigs / %d pairs in %d libraries (%.2f%% of the workload, same generator), C oracle port, 1 core" % (
+        n_contigs, n_pairs, len(libs), 100.0 * frac)
     print(json.dumps({
         "impl": "reference", "metric": "read-pairs/s through graph-build+GapEst", "value": value,
         "unit": "read-pairs/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": round(1e3 * dt / args.steps, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": round(1e3 * dt / args.steps, 3), "higher_is_better": True,
+        "scaling": "weak" if (W["weak"] or world == 1) else "strong", "vs_baseline": None,
         "dtype": "int32/int64 + f64 (GapEst)", "data": "synthetic",
-        "config": {"workload": desc, "sample": sample},
+        "config": {"workload": "%s: %s" % (name, W["desc"]), "sample": sample},
         "cpu_baseline": {"value": value, "unit": "read-pairs/s", "cores": 1, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "read-pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0}))
@@ -425,10 +564,12 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="config3", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default=None, choices=sorted(WORKLOADS),
+                    help="default: config3 at 1 and 2 GPUs, config4 at 4, config5 at 8 (BASELINE.json configs)")
     ap.add_argument("--scale", type=float, default=1.0, help="debug: shrink the workload")
-    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline / parity leg")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (profiler runs only)")
+    ap.add_argument("--no-libmetrics", action="store_true", help="skip the library-metrics leg")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -403,6 +403,31 @@ def engine_params(param, halo=(-1, -1)):
                            no_score=param.no_score, halo=halo)
 
 
+def _world():
+    """(rank, world size) of the torch.distributed job this process belongs to, (0, 1) outside one."""
+    if int(os.environ.get("WORLD_SIZE", "1")) <= 1 and "torch.distributed" not in sys.modules:
+        return 0, 1
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()):
+        return 0, 1
+    return dist.get_rank(), dist.get_world_size()
+
+
+def graph_build_distributed(engine, table, params, batch, rank, world):
+    """The multi-GPU build behind PE: every process of a torchrun job calls PE with the same
+    arguments; rank r extracts the r-th BAM-order slice of the records on its GPU, runs of links are exchanged
+    once by edge hash, every rank builds its share of the edges, and the shares are merged on every rank
+    (fetch_global), so that all processes continue with the identical CSR -- the order-dependent post-filters
+    below and BESST's consumers run replicated, as the single-process program would."""
+    from .dist import DistributedGraphBuild
+    n = len(batch)
+    bounds = [(n * r // world) - ((n * r // world) % 128) for r in range(world)] + [n]
+    backend = engine.make_dist_backend(table)
+    runner = DistributedGraphBuild(backend, rank, world)
+    runner.step(params, backend.records(batch.slice(bounds[rank], bounds[rank + 1])))
+    return runner.fetch_global()
+
+
 def PE(Contigs, Scaffolds, Information, C_dict, param, small_contigs, small_scaffolds, bam_file, engine=None):
     bam_file = as_file(bam_file)   # a path: decoded once by the native ingest library (shared with get_metrics)
     G = _new_graph()
@@ -441,7 +466,11 @@ def PE(Contigs, Scaffolds, Information, C_dict, param, small_contigs, small_scaf
         engine = default_engine()
     batch = as_batch(bam_file)
     table = ContigTable(bam_file.references, bam_file.lengths, Contigs, small_contigs, Scaffolds, small_scaffolds)
-    res = engine.graph_build(table, engine_params(param), batch, view=True)   # consumed below, before the next build
+    rank, world = _world()
+    if world > 1:
+        res = graph_build_distributed(engine, table, engine_params(param), batch, rank, world)
+    else:
+        res = engine.graph_build(table, engine_params(param), batch, view=True)   # consumed below, before the next build
     _populate(G, G_prime, res, table, param)
     cnt = res.counters
     print('ELAPSED reading file:', time() - start, file=Information)

@@ -56,6 +56,7 @@ extern "C" void besst_destroy(besst_ctx* ctx) {
                     &ctx->grouped, &ctx->run_key[0], &ctx->run_key[1], &ctx->run_val[0], &ctx->run_val[1], &ctx->run_start, &ctx->run_cnt,
                     &ctx->run_first, &ctx->run_off, &ctx->run_src, &ctx->run_len, &ctx->edge_run_ptr, &ctx->run_state};
     for (DBuf* b : bufs) b->release();
+    for (auto& t : ctx->tables) { t.rows.release(); t.rows_packed.release(); t.scaf_len.release(); }
     for (DBuf& b : ctx->rec_i32) b.release();
     for (HBuf& b : ctx->h_out) b.release();
     if (ctx->h_scalars) cudaFreeHost(ctx->h_scalars);
@@ -103,6 +104,21 @@ extern "C" int besst_set_contigs(besst_ctx* ctx, const besst_contig_row* rows, i
     BESST_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     ctx->n_contigs = n_contigs; ctx->n_scaffolds = n_scaffolds; ctx->n_large = n_large_scaffolds;
     ctx->have_links = ctx->have_graph = false;
+    return BESST_OK;
+}
+
+extern "C" int besst_contigs_select(besst_ctx* ctx, int32_t slot) {
+    if (!ctx) return BESST_E_INVALID;
+    if (slot < 0 || slot >= BESST_MAX_TABLES) { ctx->err = "besst_contigs_select: slot out of range"; return BESST_E_INVALID; }
+    if (slot == ctx->cur_table) return BESST_OK;
+    besst_ctx::TableSlot& out = ctx->tables[ctx->cur_table];
+    besst_ctx::TableSlot& in = ctx->tables[slot];
+    std::swap(out.rows, ctx->rows); std::swap(out.rows_packed, ctx->rows_packed); std::swap(out.scaf_len, ctx->scaf_len);
+    out.n_contigs = ctx->n_contigs; out.n_scaffolds = ctx->n_scaffolds; out.n_large = ctx->n_large;
+    std::swap(in.rows, ctx->rows); std::swap(in.rows_packed, ctx->rows_packed); std::swap(in.scaf_len, ctx->scaf_len);
+    ctx->n_contigs = in.n_contigs; ctx->n_scaffolds = in.n_scaffolds; ctx->n_large = in.n_large;
+    ctx->cur_table = slot;
+    ctx->have_links = ctx->have_graph = ctx->have_runs = false;
     return BESST_OK;
 }
 

@@ -92,9 +92,12 @@ struct besst_ctx {
     bool use_caller_stream = false;
     std::string err;
 
-    // contig table
+    // contig table (the current one); besst_contigs_select parks it in `tables` and swaps another one in
     DBuf rows, rows_packed, scaf_len;
     int64_t n_contigs = 0, n_scaffolds = 0, n_large = 0;
+    struct TableSlot { DBuf rows, rows_packed, scaf_len; int64_t n_contigs = 0, n_scaffolds = 0, n_large = 0; };
+    TableSlot tables[BESST_MAX_TABLES];
+    int cur_table = 0;
 
     // staged records (host-pointer calls); the copies run on copy_stream, slice by slice, overlapped
     // with the record kernel on `stream`

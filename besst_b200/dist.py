@@ -90,6 +90,11 @@ class CudaBackend(object):
             self._bufs[name] = t
         return t
 
+    def records(self, batch):
+        """abi.Records over a host RecordBatch (kept alive by the backend until the next call)"""
+        self._keep = []
+        return abi.make_records(batch, keepalive=self._keep)
+
     def tail_last_call(self, params, rec):
         """(has, obs1, obs2) of the last CreateEdge call in the slice."""
         n = int(rec.n)

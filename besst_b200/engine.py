@@ -21,6 +21,8 @@ class CudaEngine(object):
             raise BesstLibraryError("besst_create failed: %s (no CPU fallback)"
                                     % self._L.besst_last_error(None).decode())
         self._table_id = None
+        self._slot = 0
+        self._slot_contigs = {}
 
     def close(self):
         if getattr(self, "_ctx", None):
@@ -45,6 +47,15 @@ class CudaEngine(object):
         self._check(self._L.besst_set_contigs(self._ctx, rows.ctypes.data, rows.shape[0], int(n_scaffolds),
                                               int(n_large_scaffolds)), "besst_set_contigs")
         self._n_contigs = rows.shape[0]
+        self._slot_contigs[self._slot] = rows.shape[0]
+
+    def select_table(self, slot):
+        """Make contig table `slot` (0..7) current: set_contigs writes it, builds read it.  The libraries of a run
+        see different Contigs/Scaffolds states (runBESST:143-231); their tables stay resident side by side."""
+        self._check(self._L.besst_contigs_select(self._ctx, int(slot)), "besst_contigs_select")
+        self._slot = int(slot)
+        self._n_contigs = self._slot_contigs.get(self._slot, 0)
+        self._table_id = None
 
     def set_table(self, table):
         self.set_contigs(table.rows, table.n_scaffolds, table.n_large_scaffolds)
@@ -78,6 +89,14 @@ class CudaEngine(object):
         rec = abi.make_records(batch, keepalive=keep)
         sizes = self.build(params, rec)
         return self.fetch_view(sizes) if view else self.fetch(sizes)
+
+    def make_dist_backend(self, table):
+        """The device side of besst_b200.dist.DistributedGraphBuild for this engine (CreateGraph.PE under torchrun)."""
+        import torch
+        from .dist import CudaBackend
+        self.set_table(table)
+        dev = torch.device("cuda", torch.cuda.current_device())
+        return CudaBackend(self, dev)
 
     # -- the two halves around the multi-GPU exchange --------------------------------------
     def links_extract(self, params, records):

@@ -203,15 +203,16 @@ def slice_bounds(n_contigs, world):
     return [(n_contigs * r) // world for r in range(world)] + [n_contigs]
 
 
-def make_library_slice(n_contigs, n_pairs, orientation, mu, sigma, contamination, seed, rank, world, device="cpu"):
+def make_library_slice(n_contigs, n_pairs, orientation, mu, sigma, contamination, seed, rank, world, device="cpu", read_seed=0):
     """Rank `rank`'s slice of ONE global BAM-ordered library of n_contigs contigs and ~n_pairs pairs, range-
     partitioned by contig: the concatenation of the slices of ranks 0..world-1 is a single sorted BAM whose
     pairs span the cuts (a pair starting left of a cut with its right read on the other side leaves one
     record in either slice; duplicates of such pairs are split too).  The genome is divided into interior
     zones (one per rank, own seed) and boundary zones of ZONE_W bases left of every cut (own seed, generated
     IDENTICALLY by both neighbours, each keeping the records on its own contigs), so no rank ever needs
-    another rank's records.  The library is defined by (seed, world): a different world size is a different
-    (equally distributed) library.
+    another rank's records.  The library is defined by (seed, read_seed, world): `seed` fixes the contigs,
+    `read_seed` tells the libraries of one assembly apart, a different world size is a different (equally
+    distributed) library.
     -> SynthLibrary (lengths = ALL contigs; n_pairs = records of the slice / 2)"""
     lengths, strand, starts, _ = make_contigs(n_contigs, seed)
     dev = torch.device(device)
@@ -244,11 +245,12 @@ def make_library_slice(n_contigs, n_pairs, orientation, mu, sigma, contamination
     hi = cut[rank + 1] - (ZONE_W if rank + 1 < world else 0)   # the last rank's interior runs to the genome end
     if rank + 1 == world:
         hi -= READ
-    parts.append(zone(lo, max(lo, hi), seed + 7919 * (rank + 1)))
+    rs = seed + 15485863 * int(read_seed)
+    parts.append(zone(lo, max(lo, hi), rs + 7919 * (rank + 1)))
     if rank > 0:
-        parts.append(zone(cut[rank] - ZONE_W, cut[rank], seed + 104729 * rank))
+        parts.append(zone(cut[rank] - ZONE_W, cut[rank], rs + 104729 * rank))
     if rank + 1 < world:
-        parts.append(zone(max(cut[rank], cut[rank + 1] - ZONE_W), cut[rank + 1], seed + 104729 * (rank + 1)))
+        parts.append(zone(max(cut[rank], cut[rank + 1] - ZONE_W), cut[rank + 1], rs + 104729 * (rank + 1)))
     parts = [p for p in parts if p is not None]
     keys = ("tid", "mtid", "pos", "mpos", "tlen", "flag", "mapq")
     cols = {k: torch.cat([p[k] for p in parts]) if parts else torch.zeros(0, dtype=torch.int32 if k != "mapq" else torch.uint8, device=dev) for k in keys}

@@ -213,6 +213,13 @@ const char* besst_last_error(besst_ctx* ctx);
 int besst_set_contigs(besst_ctx* ctx, const besst_contig_row* rows, int64_t n_contigs,
                       int64_t n_scaffolds, int64_t n_large_scaffolds);
 
+/* Several contig tables resident in HBM at once: a scaffolding run walks its libraries in sequence
+ * (runBESST:143-231) and every library sees a different Contigs/Scaffolds state.  besst_contigs_select
+ * makes `slot` (0 .. BESST_MAX_TABLES-1) the table besst_set_contigs writes and the builds read; slot 0
+ * is selected at creation.  Switching is O(1): no copy, no synchronisation. */
+#define BESST_MAX_TABLES 8
+int besst_contigs_select(besst_ctx* ctx, int32_t slot);
+
 /* records -> CSR edges + per-edge statistics + gap/score, resident in HBM. */
 int besst_graph_build(besst_ctx* ctx, const besst_lib_params* params,
                       const besst_records* records, besst_graph_sizes* sizes);

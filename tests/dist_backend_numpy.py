@@ -25,6 +25,9 @@ class NumpyBackend(object):
     def __init__(self, table):
         self.table = table
 
+    def records(self, batch):
+        return batch
+
     def _run(self, params, batch):
         res, tuples, fishy, _ = oracle_lib.graph_build(self.table.rows, self.table.n_scaffolds, params, batch)
         self.tuples = tuples

@@ -82,3 +82,45 @@ def test_distributed_build_equals_single_pass(tmp_path, world, config, cuts, exc
     port = _free_port()
     mp.spawn(_worker, args=(world, port, config, cuts, str(tmp_path), exchange), nprocs=world, join=True)
     assert os.path.exists(os.path.join(str(tmp_path), "ok"))
+
+
+# ---- CreateGraph.PE under a torch.distributed job: the entry point itself runs the multi-rank build -------
+class _DistEngine(object):
+    """OracleEngine for the single-process calls (libmetrics) + the numpy dist backend for the build."""
+
+    def __init__(self):
+        from oracle_engine import OracleEngine
+        self._o = OracleEngine()
+        self.libmetrics = self._o.libmetrics
+        self.gapest_batch = self._o.gapest_batch
+
+    def graph_build(self, *a, **k):
+        raise AssertionError("PE must take the distributed build when the process group has more than one rank")
+
+    def make_dist_backend(self, table):
+        from dist_backend_numpy import NumpyBackend
+        return NumpyBackend(table)
+
+
+def _pe_worker(rank, world, port, case, out_dir):
+    for p in (ROOT, os.path.join(ROOT, "oracle"), HERE):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    import torch.distributed as dist
+    dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%d" % port, rank=rank, world_size=world)
+    try:
+        import test_golden_reference as tg
+        tg.check_case(case, _DistEngine())   # every rank ends with the reference's graphs, params, objects, counter lines
+        open(os.path.join(out_dir, "ok%d" % rank), "w").write("ok")
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("case", ["small_pe_no_score_later", "testset1_travis_no_score"])
+def test_entry_point_PE_runs_the_distributed_build_under_a_process_group(tmp_path, case):
+    """north-star: 'called from the existing Python entry points' -- besst_b200.CreateGraph.PE in a world-2 job
+    against the goldens minted from the reference's bytecode (no_score cases: the numpy backend has no scores)."""
+    import oracle_lib
+    oracle_lib.build()
+    mp.spawn(_pe_worker, args=(2, _free_port(), case, str(tmp_path)), nprocs=2, join=True)
+    assert os.path.exists(os.path.join(str(tmp_path), "ok0")) and os.path.exists(os.path.join(str(tmp_path), "ok1"))

@@ -374,6 +374,31 @@ def test_full_size_config2_matches_oracle(cuda_engine):
     torch.cuda.empty_cache()
 
 
+def test_full_size_config3_against_oracle(cuda_engine):
+    """BASELINE.json configs[2] at FULL size (100k contigs / 202 M MP pairs, 404 M records, the bench workload):
+    every integer of the CSR, every observation list, counters and coverages bit-exact against the sequential
+    C oracle (~11 s on one core), gaps equal, scores to 1e-6."""
+    import gc
+    import torch
+    from besst_b200.contig_table import first_library_rows
+    lib = synth.make_config("config3", device="cuda", with_names=False)
+    rows, n_scaf, n_large = first_library_rows(lib.lengths.numpy(), lib.mu + 4 * lib.sigma)
+    params = abi.make_params("rf", 11, 100.0, lib.mu, lib.sigma, lib.mu + 6 * lib.sigma)
+    cuda_engine.set_contigs(rows, n_scaf, n_large)
+    ptrs = {k: v.data_ptr() for k, v in lib.cols.items()}
+    ptrs["n"] = lib.n_records
+    got = cuda_engine.fetch(cuda_engine.build(params, abi.make_records(ptrs, on_device=True)))
+    assert lib.n_records > 400_000_000 and got.n_links > 50_000_000
+    batch = lib.to_batch()
+    del lib
+    torch.cuda.empty_cache()
+    want, _, _, consistent = oracle_lib.graph_build(rows, n_scaf, params, batch)
+    assert consistent
+    helpers.assert_graph_equal(got, want, label="config3 full")
+    del batch, want, got
+    gc.collect()
+
+
 def test_full_size_config3_invariants(cuda_engine):
     """BASELINE.json configs[2] (100k contigs / 200 M MP pairs) at half scale: size-independent
     properties of the CSR -- sorted unique edge keys, row_ptr consistent with nr_links,
