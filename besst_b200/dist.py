@@ -346,9 +346,10 @@ class DistributedGraphBuild(object):
                 self._mark("route+fishy")
             mine = self.b.counts_tensor([1 if ok else 0, n_local, 1 if calls > 0 else 0, last[0], last[1], first[0], first[1]]
                                         + lc.tolist() + rc.tolist() + fc.tolist())
-            gathered = [self.b.counts_tensor([0] * (7 + 3 * world)) for _ in range(world)]
-            dist.all_gather(gathered, mine, group=self.group)
-            M = np.asarray([g.tolist() for g in gathered], dtype=np.int64)
+            # ONE collective and ONE device->host read for the whole W x (7 + 3W) matrix
+            gathered = mine.new_zeros((world, 7 + 3 * world))
+            dist.all_gather_into_tensor(gathered, mine, group=self.group)
+            M = gathered.cpu().numpy().astype(np.int64)
             self._mark("meta")
             if int(M[:, 0].min()) == 0:
                 return None

@@ -93,7 +93,9 @@ typedef struct besst_records {
     const int32_t* qlen;
     const uint16_t* flag;
     const uint8_t* mapq;
-    int32_t on_device;    /* 0: host pointers (copied in), 1: device pointers */
+    int32_t on_device;    /* 0: host pointers (copied in), 1: device pointers -- the data must be complete with
+                             respect to the ctx's stream: synchronise the producing stream first, or make the
+                             ctx run on it (besst_set_stream) */
     int32_t reserved;
 } besst_records;
 

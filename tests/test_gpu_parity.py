@@ -160,6 +160,7 @@ def test_device_resident_records_equal_host_records(cuda_engine):
             for k, v in batch.device_arrays().items()}
     ptrs = {k: v.data_ptr() for k, v in cols.items()}
     ptrs["n"] = len(batch)
+    torch.cuda.synchronize()
     cuda_engine.set_table(table)
     dev = cuda_engine.fetch(cuda_engine.build(params, abi.make_records(ptrs, on_device=True)))
     helpers.assert_graph_equal(dev, host, label="device-resident")
@@ -368,6 +369,7 @@ def test_full_size_config2_matches_oracle(cuda_engine):
     cuda_engine.set_contigs(rows, n_scaf, n_large)
     ptrs = {k: v.data_ptr() for k, v in lib.cols.items()}
     ptrs["n"] = lib.n_records
+    torch.cuda.synchronize()   # the generator ran on torch's stream, the engine has its own: device pointers must be ready
     got = cuda_engine.fetch(cuda_engine.build(params, abi.make_records(ptrs, on_device=True)))
     helpers.assert_graph_equal(got, want, label="config2 full")
     del lib
@@ -387,6 +389,7 @@ def test_full_size_config3_against_oracle(cuda_engine):
     cuda_engine.set_contigs(rows, n_scaf, n_large)
     ptrs = {k: v.data_ptr() for k, v in lib.cols.items()}
     ptrs["n"] = lib.n_records
+    torch.cuda.synchronize()   # the generator ran on torch's stream, the engine has its own: device pointers must be ready
     got = cuda_engine.fetch(cuda_engine.build(params, abi.make_records(ptrs, on_device=True)))
     assert lib.n_records > 400_000_000 and got.n_links > 50_000_000
     batch = lib.to_batch()
@@ -411,6 +414,7 @@ def test_full_size_config3_invariants(cuda_engine):
     cuda_engine.set_contigs(rows, n_scaf, n_large)
     ptrs = {k: v.data_ptr() for k, v in lib.cols.items()}
     ptrs["n"] = lib.n_records
+    torch.cuda.synchronize()   # the generator ran on torch's stream, the engine has its own: device pointers must be ready
     rec = abi.make_records(ptrs, on_device=True)
     a = cuda_engine.fetch(cuda_engine.build(params, rec))
     b = cuda_engine.fetch(cuda_engine.build(params, rec))
