@@ -6,9 +6,10 @@ graphs -- but the per-record loop (:111-211), CreateEdge (:812-871), the
 PosDir calculators (:1024-1076) and the per-edge statistics of
 GiveScoreOnEdges (:498-614) run as sm_100a CUDA kernels behind the C ABI
 (include/besst_b200.h).  This module is the host side above that ABI: it
-flattens the objects into the contig table, calls the engine once, and then
-replays the reference's order-dependent post-filters (:237-321) on the CSR
-edge list it gets back.
+flattens the objects into the contig table, calls the engine once, replays the
+reference's post-filters (:237-321) on the CSR edge list it gets back
+(besst_b200/csr_post.py: masks over the edge list, the order-dependent pruning in C)
+and only then builds the two networkx graphs, for the surviving edges.
 
 There is no CPU fallback: without the CUDA library `PE` raises.
 """
@@ -16,10 +17,8 @@ from __future__ import annotations
 
 import os
 import sys
-from collections import Counter
 from time import time
 
-import networkx as nx
 import numpy as np
 
 from . import abi
@@ -35,10 +34,6 @@ def _new_graph():
     # so they must be of whatever `networkx` the host process runs BESST with (1.x per docs/INSTALL.md:42)
     import networkx
     return networkx.Graph()
-
-
-def _remove_nodes(graph, scaf):
-    graph.remove_nodes_from([(scaf, 'L'), (scaf, 'R')])
 
 
 def _sample_sd(values, mean):
@@ -154,7 +149,7 @@ def _forget(contigs, Contigs, small_contigs):
             del small_contigs[c.name]
 
 
-def filter_low_coverage_contigs(Contigs, Scaffolds, G, param, G_prime, small_contigs, small_scaffolds, Information):
+def filter_low_coverage_contigs(Contigs, Scaffolds, graphs, param, small_contigs, small_scaffolds, Information):
     """-z_min filter (CreateGraph.py:407-433; GenerateOutput.py:68-79)."""
     print('Removing low coverage contigs if -z_min specified..', file=Information)
     low = []
@@ -162,14 +157,12 @@ def filter_low_coverage_contigs(Contigs, Scaffolds, G, param, G_prime, small_con
         if c.coverage < param.lower_cov_cutoff:
             low.append(c)
             del Scaffolds[c.scaffold]
-            _remove_nodes(G, c.scaffold)
-            if param.extend_paths:
-                _remove_nodes(G_prime, c.scaffold)
+            graphs.remove_scaffold(c.scaffold, large=True)
     for c in small_contigs.values():
         if c.coverage < param.lower_cov_cutoff:
             low.append(c)
             del small_scaffolds[c.scaffold]
-            _remove_nodes(G_prime, c.scaffold)
+            graphs.remove_scaffold(c.scaffold, large=False)
     _write_fasta(param.output_directory + '/low_coverage_contigs.fa', low)
     _forget(low, Contigs, small_contigs)
     print('Removed a total of: ', len(low), ' low coverage contigs. With coverage lower than ', param.lower_cov_cutoff, file=Information)
@@ -211,7 +204,7 @@ def CalculateMeanCoverage(Contigs, Information, param):
     return mean_cov, std_dev
 
 
-def RepeatDetector(Contigs, Scaffolds, G, param, G_prime, small_contigs, small_scaffolds, Information):
+def RepeatDetector(Contigs, Scaffolds, graphs, param, small_contigs, small_scaffolds, Information):
     """Coverage-based repeat removal (CreateGraph.py:959-1018;
     GenerateOutput.py:47-66)."""
     mean_cov, std_dev = param.mean_coverage, param.std_dev_coverage
@@ -226,9 +219,7 @@ def RepeatDetector(Contigs, Scaffolds, G, param, G_prime, small_contigs, small_s
         if c.coverage > thresh:
             repeats.append(c)
             del Scaffolds[c.scaffold]
-            _remove_nodes(G, c.scaffold)
-            if param.extend_paths:
-                _remove_nodes(G_prime, c.scaffold)
+            graphs.remove_scaffold(c.scaffold, large=True)
         if hapl_limit is not None and c.coverage < hapl_limit:
             count_hapl += 1
             c.is_haplotype = True
@@ -236,7 +227,7 @@ def RepeatDetector(Contigs, Scaffolds, G, param, G_prime, small_contigs, small_s
         if c.coverage > thresh:
             repeats.append(c)
             del small_scaffolds[c.scaffold]
-            _remove_nodes(G_prime, c.scaffold)
+            graphs.remove_scaffold(c.scaffold, large=False)
         if hapl_limit is not None and c.coverage < hapl_limit:
             count_hapl += 1
             c.is_haplotype = True
@@ -250,98 +241,32 @@ def RepeatDetector(Contigs, Scaffolds, G, param, G_prime, small_contigs, small_s
     print('Removed a total of: ', len(repeats), ' repeats. With coverage larger than ', thresh, file=Information)
     if param.detect_haplotype:
         print('Marked a total of: ', count_hapl, ' potential haplotypes.', file=Information)
-    return Contigs, Scaffolds, G
 
 
-def infer_spurious_link_count_threshold(G_prime, param):
+def infer_spurious_link_count_threshold(graphs, param):
     """Expected link count over a gap of mean+sd-2r between two 100 kb contigs
     -> param.expected_links_over_mean_plus_stddev (CreateGraph.py:323-353)."""
-    nr_nodes = nx.number_of_nodes(G_prime) / 2
+    nr_nodes = graphs.number_of_nodes("G_prime") / 2
     ratio = param.contamination_ratio if param.contamination_ratio else 0
     cov = param.mean_coverage * (1 - ratio)
     link_params = e_nr_links.Param(param.mean_ins_size, param.std_dev_ins_size, cov, param.read_len, 0)
     gap = param.mean_ins_size + param.std_dev_ins_size - 2 * param.read_len
     expected = e_nr_links.ExpectedLinks(100000, 100000, gap, link_params)
-    link_counter = Counter(d['nr_links'] for _, _, d in G_prime.edges(data=True) if d['nr_links'] is not None)
-    total = 0
-    for link_number in sorted(link_counter, reverse=True):
-        total += link_counter[link_number]
+    for link_number, total in graphs.link_count_profile():
         print('Nodes: {0}.\t Total edges with over {1} links:{2}. \tAverage density: {3}'.format(nr_nodes, link_number, total, total / float(nr_nodes)), file=param.information_file)
     param.expected_links_over_mean_plus_stddev = 5 if expected < 5 else int(expected)
     print('Letting filtering threshold in high complexity regions be {0} for this library.'.format(param.expected_links_over_mean_plus_stddev), file=param.information_file)
 
 
-def _drop_low_support(graph, edgesupport):
-    removed = 0
-    for u, v, d in list(graph.edges(data=True)):
-        if d['nr_links'] is not None and d['nr_links'] < edgesupport:
-            graph.remove_edge(u, v)
-            removed += 1
-    return removed
-
-
-def remove_edges_below_threshold(graph, param):
+def remove_edges_below_threshold(graphs, param):
     """Order-dependent pruning of G_prime (CreateGraph.py:355-404): in
     `graph.edges()` order, drop a weak edge only while both endpoints still have
     more than 4 neighbours; then drop everything under -e."""
     print('Remove edges in high complexity areas.', file=param.information_file)
-    limit = param.expected_links_over_mean_plus_stddev
-    weak = [(u, v) for u, v, d in graph.edges(data=True) if d['nr_links'] is not None and d['nr_links'] < limit]
-    removed = 0
-    adj = graph.adj
-    for u, v in weak:
-        if len(adj[u]) > 4 and len(adj[v]) > 4:
-            graph.remove_edge(u, v)
-            removed += 1
+    removed = graphs.prune_dense_regions(param.expected_links_over_mean_plus_stddev)
     print('Removed total of {0} edges in high density areas.'.format(removed), file=param.information_file)
-    low = _drop_low_support(graph, param.edgesupport)
+    low = graphs.drop_low_support("G_prime", param.edgesupport)
     print('Removed an additional of {0} edges with low support from full graph G_prime of all contigs.'.format(low), file=param.information_file)
-
-
-def RemoveBugEdges(G, G_prime, res, table, param, Information):
-    """Drop edges whose fishy count (unmapped read1 with the mate on another
-    scaffold, CreateGraph.py:141-163) reaches their link count (:690-708)."""
-    removed = 0
-    for e in np.nonzero(res.fishy > 0)[0].tolist():
-        n0, n1 = table.node(int(res.edge_u[e])), table.node(int(res.edge_v[e]))
-        count = int(res.fishy[e])
-        if param.extend_paths:
-            if G_prime.has_edge(n0, n1) and count >= G_prime[n0][n1]['nr_links']:
-                G_prime.remove_edge(n0, n1)
-                removed += 1
-            if G.has_edge(n0, n1) and count >= G[n0][n1]['nr_links']:
-                G.remove_edge(n0, n1)
-        elif G.has_edge(n0, n1) and count >= G[n0][n1]['nr_links']:
-            G.remove_edge(n0, n1)
-            removed += 1
-    print('Number of BWA buggy edges removed: ', removed, file=Information)
-
-
-def _populate(G, G_prime, res, table, param, observations_as_list=True):
-    """Insert the CSR link edges into the networkx graphs in first-appearance
-    (BAM) order, with the attribute names/types CreateEdge uses
-    (CreateGraph.py:842-862)."""
-    scoring = not param.no_score
-    into_G = scoring
-    into_GP = param.no_score or param.extend_paths
-    order = np.argsort(res.first_idx, kind='stable')
-    names = table.scaffold_names
-    total = res.obs_u.astype(np.int64) + res.obs_v
-    conv = (lambda a: a.tolist()) if observations_as_list else (lambda a: a)
-    row_ptr = res.row_ptr
-    for e in order.tolist():
-        u, v = int(res.edge_u[e]), int(res.edge_v[e])
-        nu = (names[u >> 1], 'R' if u & 1 else 'L')
-        nv = (names[v >> 1], 'R' if v & 1 else 'L')
-        b, t = int(row_ptr[e]), int(row_ptr[e + 1])
-        nr, obs, obs_sq = int(res.nr_links[e]), int(res.obs_sum[e]), int(res.obs_sq[e])
-        if into_G and (res.flags[e] & abi.EDGE_LL):
-            G.add_edge(nv, nu, nr_links=nr, obs=obs, obs_sq=obs_sq, observations=conv(total[b:t]))
-            d = G[nu][nv]
-            d[nu[0]] = conv(res.obs_u[b:t])   # per-scaffold lists, keyed by scaffold name (:848-849)
-            d[nv[0]] = conv(res.obs_v[b:t])
-        if into_GP:
-            G_prime.add_edge(nv, nu, nr_links=nr, obs=obs, obs_sq=obs_sq, observations=conv(total[b:t]))
 
 
 def _score_file_names(Scaffolds, node, first):
@@ -353,46 +278,33 @@ def _score_file_names(Scaffolds, node, first):
 
 
 def GiveScoreOnEdges(G, res, table, param, Information, Scaffolds=None):
-    """Attach the engine's per-edge gap and score to the surviving G edges
-    (the arithmetic of CreateGraph.py:498-614 ran on the GPU); writes
-    score_file_pass_N.tsv when param.print_scores (:481-483,622-654)."""
-    if param.lognormal:
-        raise NotImplementedError("lognormal libraries: the reference's scoring branch (CreateGraph.py:485-493) "
-                                  "is a 'next' row (SURVEY.md 8f rank 3)")
+    """The per-edge gap and score (the arithmetic of CreateGraph.py:498-614 ran on the GPU) are attached when
+    the graphs are materialised (csr_post.CsrGraphs.materialise); this writes score_file_pass_N.tsv when
+    param.print_scores (:481-483,622-654) and the closing counter line."""
     if getattr(param, 'plots', False):
         print('plots requested: the score histograms of CreateGraph.py:656-662 are not produced by besst_b200', file=Information)
-    score_file = None
     if getattr(param, 'print_scores', False) and Scaffolds is not None:
-        score_file = open(os.path.join(param.output_directory, "score_file_pass_{0}.tsv".format(param.pass_number)), "w")
-        print("{0}\t{1}\t{2}\t{3}\t{4}\t{5}\t{6}\t{7}".format("scf1/ctg1", "o1", "scf2/ctg2", "o2", "gap", "link_variation_score", "link_dispersity_score", "number_of_links"), file=score_file)
-    index = {}
-    for e in np.nonzero(res.flags & abi.EDGE_SCORED)[0].tolist():
-        index[(int(res.edge_u[e]), int(res.edge_v[e]))] = e
-    for n0, n1, d in G.edges(data=True):
-        if d['nr_links'] is None:
-            continue
-        a, b = table.node_id(n0), table.node_id(n1)
-        e = index[(a, b) if a < b else (b, a)]
-        d['gap'] = int(res.gap[e])
-        if res.flags[e] & abi.EDGE_NEGGAP:
-            d['score'] = 0
-            continue
-        del d[n0[0]]
-        del d[n1[0]]
-        s = float(res.score[e])
-        d['score'] = s if s != 0.0 else 0
-        if score_file is not None:
-            n = int(res.nr_links[e])
-            sd, sd0 = float(res.sd_obs[e]), float(res.sd_model[e])
-            std_dev_score = 0 if (sd == 0.0 or sd0 == 0.0 or sd != sd) else min(sd / sd0, sd0 / sd)
-            span_score = 0 if n < 5 else 1 - float(res.ks[e])
-            # `gap` of the reference is GapEstimator's int for two long scaffolds, else the float naive estimate (:536-539)
-            gap = int(res.gap[e]) if res.flags[e] & abi.EDGE_BIG else (n * param.mean_ins_size - int(res.obs_sum[e])) / float(n)
-            scf1, dir1 = _score_file_names(Scaffolds, n0, True)
-            scf2, dir2 = _score_file_names(Scaffolds, n1, False)
-            print("{0}\t{1}\t{2}\t{3}\t{4}\t{5}\t{6}\t{7}".format(scf1, dir1, scf2, dir2, gap, std_dev_score, span_score, n), file=score_file)
-    if score_file is not None:
-        score_file.close()
+        index = {}
+        for e in np.nonzero(res.flags & abi.EDGE_SCORED)[0].tolist():
+            index[(int(res.edge_u[e]), int(res.edge_v[e]))] = e
+        with open(os.path.join(param.output_directory, "score_file_pass_{0}.tsv".format(param.pass_number)), "w") as score_file:
+            print("{0}\t{1}\t{2}\t{3}\t{4}\t{5}\t{6}\t{7}".format("scf1/ctg1", "o1", "scf2/ctg2", "o2", "gap", "link_variation_score", "link_dispersity_score", "number_of_links"), file=score_file)
+            for n0, n1, d in G.edges(data=True):
+                if d['nr_links'] is None:
+                    continue
+                a, b = table.node_id(n0), table.node_id(n1)
+                e = index[(a, b) if a < b else (b, a)]
+                if res.flags[e] & abi.EDGE_NEGGAP:
+                    continue
+                n = int(res.nr_links[e])
+                sd, sd0 = float(res.sd_obs[e]), float(res.sd_model[e])
+                std_dev_score = 0 if (sd == 0.0 or sd0 == 0.0 or sd != sd) else min(sd / sd0, sd0 / sd)
+                span_score = 0 if n < 5 else 1 - float(res.ks[e])
+                # `gap` of the reference is GapEstimator's int for two long scaffolds, else the float naive estimate (:536-539)
+                gap = int(res.gap[e]) if res.flags[e] & abi.EDGE_BIG else (n * param.mean_ins_size - int(res.obs_sum[e])) / float(n)
+                scf1, dir1 = _score_file_names(Scaffolds, n0, True)
+                scf2, dir2 = _score_file_names(Scaffolds, n1, False)
+                print("{0}\t{1}\t{2}\t{3}\t{4}\t{5}\t{6}\t{7}".format(scf1, dir1, scf2, dir2, gap, std_dev_score, span_score, n), file=score_file)
     print('Number of significantly spurious edges:', 0, file=Information)
 
 
@@ -429,13 +341,12 @@ def graph_build_distributed(engine, table, params, batch, rank, world):
 
 
 def PE(Contigs, Scaffolds, Information, C_dict, param, small_contigs, small_scaffolds, bam_file, engine=None):
+    from .csr_post import CsrGraphs
     bam_file = as_file(bam_file)   # a path: decoded once by the native ingest library (shared with get_metrics)
-    G = _new_graph()
-    G_prime = _new_graph()
     print('Parsing BAM file...', file=Information)
     if param.first_lib:
         start = time()
-        InitializeObjects(bam_file, Contigs, Scaffolds, param, Information, G_prime, small_contigs, small_scaffolds, C_dict)
+        InitializeObjects(bam_file, Contigs, Scaffolds, param, Information, None, small_contigs, small_scaffolds, C_dict)
         print('Time initializing BESST objects: ', time() - start, file=Information)
     else:
         start = time()
@@ -445,18 +356,14 @@ def PE(Contigs, Scaffolds, Information, C_dict, param, small_contigs, small_scaf
     if len(Scaffolds) == 0:
         if not os.path.isfile(param.output_directory + '/repeats.fa'):
             open(param.output_directory + '/repeats.fa', 'w').close()
-        return (G, G_prime)
+        return (_new_graph(), _new_graph())
 
+    # InitializeGraph (:85-96) happens at materialisation; its progress lines go out here
     start = time()
-    if param.no_score:
-        InitializeGraph(small_scaffolds, G_prime, Information)
-        InitializeGraph(Scaffolds, G_prime, Information)
-    elif param.extend_paths:
-        InitializeGraph(Scaffolds, G, Information)
-        InitializeGraph(small_scaffolds, G_prime, Information)
-        InitializeGraph(Scaffolds, G_prime, Information)
-    else:
-        InitializeGraph(Scaffolds, G, Information)
+    for d in ((small_scaffolds, Scaffolds) if param.no_score else
+              (Scaffolds, small_scaffolds, Scaffolds) if param.extend_paths else (Scaffolds,)):
+        for cnt in range(100000, len(d) + 1, 100000):
+            print('Total nr of keys added: ', cnt, 'Time for adding last 100 000 keys: ', time() - start, file=Information)
     print('Total time elapsed for initializing Graph: ', time() - start, file=Information)
 
     print('Reading bam file and creating scaffold graph...', file=Information)
@@ -471,15 +378,15 @@ def PE(Contigs, Scaffolds, Information, C_dict, param, small_contigs, small_scaf
         res = graph_build_distributed(engine, table, engine_params(param), batch, rank, world)
     else:
         res = engine.graph_build(table, engine_params(param), batch, view=True)   # consumed below, before the next build
-    _populate(G, G_prime, res, table, param)
+    graphs = CsrGraphs(res, table, param)   # (G, G_prime) as masks over the CSR edge list
     cnt = res.counters
     print('ELAPSED reading file:', time() - start, file=Information)
     print('NR OF FISHY READ LINKS: ', int(cnt[abi.CNT_FISHY]), file=Information)
     print('Number of USEFUL READS (reads mapping to different contigs uniquly): ', int(cnt[abi.CNT_COUNT]), file=Information)
     print('Number of non unique reads (at least one read non-unique in read pair) that maps to different contigs (filtered out from scaffolding): ', int(cnt[abi.CNT_NON_UNIQUE]), file=Information)
     print('Reads with too large insert size from "USEFUL READS" (filtered out): ', int(cnt[abi.CNT_TOO_LONG]), file=Information)
-    print('Initial number of edges in G (the graph with large contigs): ', G.number_of_edges(), file=Information)
-    print('Initial number of edges in G_prime (the full graph of all contigs before removal of repats): ', G_prime.number_of_edges(), file=Information)
+    print('Initial number of edges in G (the graph with large contigs): ', graphs.number_of_edges("G"), file=Information)
+    print('Initial number of edges in G_prime (the full graph of all contigs before removal of repats): ', graphs.number_of_edges("G_prime"), file=Information)
     if param.detect_duplicate:
         print('Number of duplicated reads indicated and removed: ', int(cnt[abi.CNT_DUPLICATES]), file=Information)
 
@@ -492,28 +399,34 @@ def PE(Contigs, Scaffolds, Information, C_dict, param, small_contigs, small_scaf
             c.coverage = aligned / float(c.length)
 
     if param.first_lib and param.lower_cov_cutoff:
-        filter_low_coverage_contigs(Contigs, Scaffolds, G, param, G_prime, small_contigs, small_scaffolds, Information)
+        filter_low_coverage_contigs(Contigs, Scaffolds, graphs, param, small_contigs, small_scaffolds, Information)
 
     param.mean_coverage, param.std_dev_coverage = CalculateMeanCoverage(Contigs, Information, param)
     if param.first_lib:
-        Contigs, Scaffolds, G = RepeatDetector(Contigs, Scaffolds, G, param, G_prime, small_contigs, small_scaffolds, Information)
-    print('Number of edges in G (after repeat removal): ', G.number_of_edges(), file=Information)
-    print('Number of edges in G_prime (after repeat removal): ', G_prime.number_of_edges(), file=Information)
+        RepeatDetector(Contigs, Scaffolds, graphs, param, small_contigs, small_scaffolds, Information)
+    print('Number of edges in G (after repeat removal): ', graphs.number_of_edges("G"), file=Information)
+    print('Number of edges in G_prime (after repeat removal): ', graphs.number_of_edges("G_prime"), file=Information)
 
-    RemoveBugEdges(G, G_prime, res, table, param, Information)
-    print('Number of edges in G (after filtering for buggy flag stats reporting): ', G.number_of_edges(), file=Information)
-    print('Number of edges in G_prime  (after filtering for buggy flag stats reporting): ', G_prime.number_of_edges(), file=Information)
+    print('Number of BWA buggy edges removed: ', graphs.remove_bug_edges(), file=Information)
+    print('Number of edges in G (after filtering for buggy flag stats reporting): ', graphs.number_of_edges("G"), file=Information)
+    print('Number of edges in G_prime  (after filtering for buggy flag stats reporting): ', graphs.number_of_edges("G_prime"), file=Information)
 
-    infer_spurious_link_count_threshold(G_prime, param)
+    infer_spurious_link_count_threshold(graphs, param)
     if not param.edgesupport:
         param.edgesupport = 5
         print('Letting -e be {0} for this library.'.format(param.edgesupport), file=Information)
     else:
         print('User has set -e to be {0} for this library.'.format(param.edgesupport), file=Information)
-    removed = _drop_low_support(G, param.edgesupport)
+    removed = graphs.drop_low_support("G", param.edgesupport)
     print('Removed {0} edges from graph G of border contigs.'.format(removed), file=Information)
-    remove_edges_below_threshold(G_prime, param)
+    remove_edges_below_threshold(graphs, param)
 
+    if not param.no_score and param.lognormal:
+        raise NotImplementedError("lognormal libraries: the reference's scoring branch (CreateGraph.py:485-493) "
+                                  "is a 'next' row (SURVEY.md 8f rank 3)")
+    # networkx objects for the surviving edges only, with CreateEdge's attributes and GiveScoreOnEdges' gap / score
+    G, G_prime = graphs.materialise(_new_graph, Scaffolds, small_scaffolds,
+                                    lazy_observations=bool(getattr(param, 'lazy_observations', False)))
     if not param.no_score:
         GiveScoreOnEdges(G, res, table, param, Information, Scaffolds)
     print('Number of edges in G_prime  (after removing edges under -e threshold (if not specified, default is -e 3): ', G_prime.number_of_edges(), file=Information)

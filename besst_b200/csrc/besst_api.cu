@@ -380,6 +380,19 @@ extern "C" int besst_runs_to_graph(besst_ctx* ctx, const besst_lib_params* param
     return BESST_OK;
 }
 
+extern "C" int64_t besst_csr_prune_dense(int64_t n_weak, const uint32_t* weak_u, const uint32_t* weak_v, int32_t* degree,
+                                         int32_t min_neighbours, uint8_t* dropped) {
+    if (n_weak < 0 || (n_weak > 0 && (!weak_u || !weak_v || !degree || !dropped))) return BESST_E_INVALID;
+    int64_t removed = 0;
+    for (int64_t i = 0; i < n_weak; ++i) {
+        const uint32_t u = weak_u[i], v = weak_v[i];
+        const bool drop = degree[u] > min_neighbours && degree[v] > min_neighbours;
+        dropped[i] = drop ? 1 : 0;
+        if (drop) { --degree[u]; --degree[v]; ++removed; }
+    }
+    return removed;
+}
+
 extern "C" int besst_set_stream(besst_ctx* ctx, void* cuda_stream) {
     if (!ctx) return BESST_E_INVALID;
     cudaSetDevice(ctx->device);

@@ -321,6 +321,15 @@ int besst_gapest_func_batch(besst_ctx* ctx, const besst_lib_params* params, cons
 int besst_trsk_sd_batch(besst_ctx* ctx, const besst_lib_params* params, const double* gap, const double* len1,
                         const double* len2, int64_t n, double* sd_out);
 
+/* Order-dependent pruning of G_prime in high-density regions (remove_edges_below_threshold, CreateGraph.py:355-374)
+ * on the CSR edge list, host side: the weak edges (nr_links < expected_links) arrive in the order networkx's
+ * G.edges() would yield them; an edge is dropped iff BOTH endpoints still have more than `min_neighbours`
+ * neighbours at that moment, and dropping it lowers both degrees.  degree[] (per node id, in/out) counts the
+ * intra-scaffold edge as well.  dropped[i] = 1 for the removed edges.  Returns how many were removed.
+ * No ctx, no device: a sequential O(n_weak) loop that does not belong in Python at 1e6 edges. */
+int64_t besst_csr_prune_dense(int64_t n_weak, const uint32_t* weak_u, const uint32_t* weak_v, int32_t* degree,
+                              int32_t min_neighbours, uint8_t* dropped);
+
 /* run all work of this ctx on a caller-owned CUDA stream (a cudaStream_t passed as void*; NULL
  * restores the ctx's own non-blocking stream; pass cudaStreamLegacy (0x1) for the legacy default stream).  Lets a host framework order the library's kernels with its own
  * work (NCCL collectives, CUDA-event timing) without device-wide synchronisation. */

@@ -233,7 +233,7 @@ class FakeSeq(object):
         return "N"
 
 
-def run_dropin(batch, opts, engine, state=None, run_libmetrics=True, fasta_lengths=None, bam_path=None):
+def run_dropin(batch, opts, engine, state=None, run_libmetrics=True, fasta_lengths=None, bam_path=None, param_overrides=None):
     """One library pass through the drop-in entry points (besst_b200.libmetrics.get_metrics
     + besst_b200.CreateGraph.PE) with `engine` behind them.  Mirrors
     oracle/ref_harness.run_reference so that the two outputs compare field by field."""
@@ -245,6 +245,8 @@ def run_dropin(batch, opts, engine, state=None, run_libmetrics=True, fasta_lengt
     info = io.StringIO()
     param = Param(outdir, info, **opts)
     param.first_lib = state is None
+    for k, v in (param_overrides or {}).items():
+        setattr(param, k, v)
     if fasta_lengths is None:
         fasta_lengths = dict(zip(batch.references, batch.lengths))
     C_dict = {name: FakeSeq(n) for name, n in fasta_lengths.items()}
