@@ -182,6 +182,63 @@ class Library(object):
                 "contamination": self.cont, "records_this_rank": self.n_rec, "contig_table": self.state}
 
 
+class _Seq(object):
+    """contig sequence stand-in for the PE-level leg: only len() is used on this path"""
+    __slots__ = ("n",)
+
+    def __init__(self, n):
+        self.n = int(n)
+
+    def __len__(self):
+        return self.n
+
+
+class _RunParam(object):
+    """what runBESST:88-158 sets on its parameter object for one library run without -m/-s"""
+
+    def __init__(self, orientation, outdir, info, lazy):
+        self.scaffold_indexer, self.no_score, self.min_mapq, self.max_contig_overlap = 1, False, 11, 200
+        self.cov_cutoff, self.lower_cov_cutoff, self.plots, self.development, self.print_scores = None, 0.001, False, False, False
+        self.first_lib, self.pass_number, self.bamfile, self.orientation = True, 1, "in_memory.bam", orientation
+        self.mean_ins_size = self.std_dev_ins_size = self.ins_size_threshold = self.contig_threshold = None
+        self.edgesupport = self.read_len = None
+        self.output_directory, self.information_file = outdir, info
+        self.detect_haplotype, self.hapl_ratio, self.hapl_threshold = False, 1.3, 3
+        self.detect_duplicate, self.extend_paths, self.lognormal = True, True, False
+        self.contamination_ratio = self.tot_assembly_length = None
+        self.lazy_observations = lazy
+
+
+def pe_level_leg(eng, L, host_cols, lazy):
+    """The reference-facing entry points end to end for one library (runBESST:168,182): get_metrics (library
+    parameters estimated, no -m/-s) + CreateGraph.PE from host records to the two networkx graphs."""
+    import io
+    import tempfile
+    from besst_b200 import CreateGraph as CG, libmetrics
+    from besst_b200.records import BatchFile, RecordBatch
+    arrs = {k: v[:L.n_rec].numpy() for k, v in host_cols.items()}
+    arrs["flag"] = arrs["flag"].view(np.uint16)
+    names = ["c%d" % i for i in range(L.lengths.shape[0])]
+    batch = RecordBatch(references=names, lengths=[int(x) for x in L.lengths.tolist()],
+                        rlen=np.full(min(L.n_rec, 1000), 100, np.int32), alen=np.full(min(L.n_rec, 1000), 100, np.int32), **arrs)
+    bam = BatchFile(batch)
+    info = io.StringIO()
+    param = _RunParam(L.orientation, tempfile.mkdtemp(prefix="besst_bench_"), info, lazy)
+    C_dict = {n: _Seq(x) for n, x in zip(names, batch.lengths)}
+    Contigs, Scaffolds, small_contigs, small_scaffolds = {}, {}, {}, {}
+    import contextlib
+    t0 = time.perf_counter()
+    with contextlib.redirect_stdout(io.StringIO()):
+        libmetrics.get_metrics(bam, param, info, engine=eng)
+        t1 = time.perf_counter()
+        G, G_prime = CG.PE(Contigs, Scaffolds, info, C_dict, param, small_contigs, small_scaffolds, bam, engine=eng)
+    t2 = time.perf_counter()
+    return {"get_metrics_s": round(t1 - t0, 3), "PE_s": round(t2 - t1, 3), "read_pairs_per_s": L.n_rec / 2.0 / (t2 - t0),
+            "G_edges": G.number_of_edges(), "G_prime_edges": G_prime.number_of_edges(),
+            "estimated": {"mean_ins_size": param.mean_ins_size, "std_dev_ins_size": param.std_dev_ins_size},
+            "observations": "lazy views (param.lazy_observations)" if lazy else "python lists (as the reference stores them)"}
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -385,6 +442,7 @@ def run_ours(args):
     e2e = None
     cpu_baseline = None
     parity = None
+    pe_level = None
     try:
         max_rec = max(L.n_rec for L in libs)
         host = {k: torch.empty((max_rec,), dtype=v.dtype, pin_memory=True) for k, v in libs[0].cols.items()}
@@ -452,6 +510,24 @@ def run_ours(args):
                         oracle_s += want["seconds"]
                     oracle_pairs += L.n_rec / 2.0
                 del batch
+            # ---- the reference-facing entry points end to end (N=1, first library): get_metrics + PE ----------------
+            if world == 1 and L.index == 0 and L.tlen is not None and args.pe_level:
+                try:
+                    hc = dict(host)
+                    hc["tlen"] = torch.empty((L.n_rec,), dtype=torch.int32, pin_memory=True)
+                    hc["tlen"].copy_(L.tlen)
+                    torch.cuda.synchronize()
+                    pe_level = {"lazy": pe_level_leg(eng, L, hc, True)}
+                    if L.n_rec <= 60_000_000:   # python lists of every observation: minutes and tens of GB beyond that
+                        pe_level["lists"] = pe_level_leg(eng, L, hc, False)
+                    del hc
+                    for Lk in libs:   # PE uploaded its own contig table into the current slot
+                        eng.select_table(Lk.index)
+                        eng.set_contigs(Lk.rows, Lk.n_scaf, Lk.n_large)
+                except Exception as exc:
+                    import traceback
+                    traceback.print_exc(file=sys.stderr)
+                    pe_level = {"error": repr(exc)}
         if not args.no_e2e:
             if world > 1:
                 t = torch.tensor([e2e_time], device=dev, dtype=torch.float64)
@@ -500,7 +576,7 @@ def run_ours(args):
             "wall_ms_per_step": round(1e3 * wall / args.steps, 4),
             "timing": "CUDA events on the launching stream (the library runs on torch's current stream), max over ranks",
             "dist_phases_ms": dist_phases,
-            "roofline": roofline, "kernels": kernels, "libmetrics": libmetrics, "cpu_baseline": cpu_baseline, "parity": parity,
+            "roofline": roofline, "kernels": kernels, "libmetrics": libmetrics, "pe_level": pe_level, "cpu_baseline": cpu_baseline, "parity": parity,
             "generate_s": round(t_gen, 2), "impl": "ours",
         }
         print(json.dumps(line))
@@ -572,6 +648,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline / parity leg")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (profiler runs only)")
     ap.add_argument("--no-libmetrics", action="store_true", help="skip the library-metrics leg")
+    ap.add_argument("--pe-level", action="store_true", help="also time get_metrics + CreateGraph.PE (host records -> networkx graphs), N=1")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
