@@ -308,6 +308,68 @@ def GiveScoreOnEdges(G, res, table, param, Information, Scaffolds=None):
     print('Number of significantly spurious edges:', 0, file=Information)
 
 
+def get_conditional_stddevs(steps, empirical_isize_distr, max_isize):
+    """sd of the insert-size distribution conditioned on spanning a gap, per gap size (CreateGraph.py:436-468):
+    density f(x) * max(0, x - gap + 1) for every gap in `steps`, each value repeated up to the next step."""
+    xs = np.fromiter(empirical_isize_distr.keys(), dtype=np.int64, count=len(empirical_isize_distr))
+    fx = np.fromiter(empirical_isize_distr.values(), dtype=np.float64, count=len(empirical_isize_distr))
+    out, previous_gap = [], 0
+    for gap in steps:
+        dens = np.zeros(max_isize + 1, dtype=np.float64)
+        w = np.maximum(0, xs - gap + 1)
+        dens[xs[w > 0]] = (fx * w)[w > 0]
+        tot = float(dens.sum())
+        idx = np.arange(max_isize + 1, dtype=np.float64)
+        mu_c = float((idx * dens).sum()) / tot
+        sd_c = float(np.sqrt((((idx - mu_c) ** 2) * dens).sum() / tot))
+        out.extend([sd_c] if gap == 0 else [sd_c] * (gap - previous_gap))
+        previous_gap = gap
+    return out
+
+
+def lognormal_rescore(res, table, param, engine):
+    """The lognormal branch of GiveScoreOnEdges (CreateGraph.py:485-493, 523-531, 549-553) on the CSR result:
+    the gap of every scored edge between two long scaffolds comes from the lognormal ML estimator over the
+    edge's raw observations (one warp per edge, besst_gapest_lognormal_batch), capped at the end of the
+    conditional-sd table, and the model sd is that table's entry; sample sd and KS statistic are the ones the
+    build computed.  The reference's own branch only runs under Python 2 (`range` with a float step, :490):
+    `max_isize / 50` is read as the integer division it was there."""
+    emp = param.empirical_distribution
+    max_isize = max(emp.keys())
+    steps = list(range(0, int(max_isize * 0.8), max(1, max_isize // 50)))
+    cond = np.asarray(get_conditional_stddevs(steps, emp, max_isize), dtype=np.float64)
+    log_norm_max_gap = cond.shape[0] - 1
+    scored = np.nonzero(res.flags & abi.EDGE_SCORED)[0]
+    if scored.shape[0] == 0:
+        return
+    big = (res.flags[scored] & abi.EDGE_BIG) != 0
+    n = res.nr_links[scored].astype(np.float64)
+    len1 = table.scaffold_lengths[res.edge_u[scored] >> 1].astype(np.float64)
+    len2 = table.scaffold_lengths[res.edge_v[scored] >> 1].astype(np.float64)
+    gap = (n * param.mean_ins_size - res.obs_sum[scored]) / n                     # data_observation (:511)
+    if big.any():
+        eb = scored[big]
+        nr = res.nr_links[eb].astype(np.int64)
+        rp = np.concatenate([[0], np.cumsum(nr)])
+        idx = np.repeat(res.row_ptr[eb] - rp[:-1], nr) + np.arange(int(rp[-1]), dtype=np.int64)
+        samples = (res.obs_u[idx].astype(np.int64) + res.obs_v[idx]).astype(np.int32)
+        g = engine.gapest_lognormal_batch(param.lognormal_mean, param.lognormal_sigma, param.read_len, samples, rp, len1[big], len2[big])
+        gap[big] = np.minimum(g, log_norm_max_gap)                               # :526-528
+    neg = (-gap > len1) | (-gap > len2)                                           # :542
+    sd0 = np.full(scored.shape[0], 4294967296.0)
+    sd0[big] = cond[np.where(gap[big] > 0, gap[big].astype(np.int64), 0)]         # :549-553
+    sd, ks = res.sd_obs[scored], res.ks[scored]
+    with np.errstate(divide="ignore", invalid="ignore"):
+        sds = np.where((sd0 == 0) | (sd == 0) | np.isnan(sd), 0.0, np.minimum(sd / sd0, sd0 / sd))
+    span = np.where(n < 5, 0.0, 1 - ks)
+    score = np.where((sds > 0.5) & (span > 0.5), sds + span, 0.0)
+    score[neg] = 0.0
+    res.gap[scored] = np.trunc(gap).astype(np.int32)                              # int(gap) :541
+    res.score[scored] = score
+    res.sd_model[scored] = np.where(neg, np.nan, sd0)
+    res.flags[scored] = (res.flags[scored] & ~np.uint8(abi.EDGE_NEGGAP)) | np.where(neg, abi.EDGE_NEGGAP, 0).astype(np.uint8)
+
+
 def engine_params(param, halo=(-1, -1)):
     return abi.make_params(param.orientation, param.min_mapq, param.read_len, param.mean_ins_size,
                            param.std_dev_ins_size, param.ins_size_threshold,
@@ -422,8 +484,10 @@ def PE(Contigs, Scaffolds, Information, C_dict, param, small_contigs, small_scaf
     remove_edges_below_threshold(graphs, param)
 
     if not param.no_score and param.lognormal:
-        raise NotImplementedError("lognormal libraries: the reference's scoring branch (CreateGraph.py:485-493) "
-                                  "is a 'next' row (SURVEY.md 8f rank 3)")
+        for f in ("gap", "score", "sd_model", "flags"):   # overwritten in place below
+            if not getattr(res, f).flags.writeable:
+                setattr(res, f, getattr(res, f).copy())
+        lognormal_rescore(res, table, param, engine)
     # networkx objects for the surviving edges only, with CreateEdge's attributes and GiveScoreOnEdges' gap / score
     G, G_prime = graphs.materialise(_new_graph, Scaffolds, small_scaffolds,
                                     lazy_observations=bool(getattr(param, 'lazy_observations', False)))

@@ -557,6 +557,34 @@ extern "C" int besst_gapest_batch(besst_ctx* ctx, const besst_lib_params* params
                      });
 }
 
+extern "C" int besst_gapest_lognormal_batch(besst_ctx* ctx, double mu_ln, double sigma_ln, double read_len, const int32_t* samples,
+                                            const int64_t* row_ptr, const double* len1, const double* len2, int64_t n, int32_t* gap_out) {
+    if (!ctx) return BESST_E_INVALID;
+    if (n < 0 || (n > 0 && (!samples || !row_ptr || !len1 || !len2 || !gap_out)) || !(sigma_ln > 0)) { ctx->err = "gapest_lognormal_batch: bad arguments"; return BESST_E_INVALID; }
+    if (n == 0) return BESST_OK;
+    const int64_t total = row_ptr[n];
+    for (int64_t i = 0; i < n; ++i)
+        if (row_ptr[i + 1] <= row_ptr[i] || row_ptr[i] < 0) { ctx->err = "gapest_lognormal_batch: every edge needs at least one observation"; return BESST_E_INVALID; }
+    cudaSetDevice(ctx->device);
+    const size_t nn = (size_t)n, tt = (size_t)total;
+    BESST_CUDA_TRY(ctx, ctx->misc.ensure(8 * (nn + 1) + 16 * nn + 4 * nn + 4 * tt + 64));
+    unsigned char* base = ctx->misc.as<unsigned char>();
+    int64_t* d_rp = reinterpret_cast<int64_t*>(base);
+    double* d_l1 = reinterpret_cast<double*>(base + 8 * (nn + 1));
+    double* d_l2 = d_l1 + nn;
+    int32_t* d_gap = reinterpret_cast<int32_t*>(d_l2 + nn);
+    int32_t* d_s = d_gap + nn;
+    BESST_CUDA_TRY(ctx, cudaMemcpyAsync(d_rp, row_ptr, 8 * (nn + 1), cudaMemcpyHostToDevice, ctx->stream));
+    BESST_CUDA_TRY(ctx, cudaMemcpyAsync(d_l1, len1, 8 * nn, cudaMemcpyHostToDevice, ctx->stream));
+    BESST_CUDA_TRY(ctx, cudaMemcpyAsync(d_l2, len2, 8 * nn, cudaMemcpyHostToDevice, ctx->stream));
+    BESST_CUDA_TRY(ctx, cudaMemcpyAsync(d_s, samples, 4 * tt, cudaMemcpyHostToDevice, ctx->stream));
+    const int rc = besst_launch_gapest_lognormal(ctx, mu_ln, sigma_ln, read_len, d_s, d_rp, d_l1, d_l2, n, d_gap);
+    if (rc) return rc;
+    BESST_CUDA_TRY(ctx, cudaMemcpyAsync(gap_out, d_gap, 4 * nn, cudaMemcpyDeviceToHost, ctx->stream));
+    BESST_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return BESST_OK;
+}
+
 extern "C" int besst_libmetrics(besst_ctx* ctx, const besst_lib_params* params, const besst_records* records,
                                 const int64_t* ref_lengths, int64_t n_refs, int32_t want_isize, besst_libmetrics_out* out,
                                 double* adjusted_distribution, int64_t cap) {

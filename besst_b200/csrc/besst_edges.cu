@@ -902,18 +902,21 @@ __global__ void __launch_bounds__(128) k_edge_finalize(const ScoreArgs A) {
     const double sd_ml = tr_sk_std_dev_quad(c, len1, len2, gap);
     if (!ll || (threadIdx.x & 3) != 0) return;
     const double nan = __longlong_as_double(0x7ff8000000000000ll);
-    double score = 0.0, ks_out = nan, sd_obs_out = nan, sd_model_out = nan;
+    double score = 0.0, sd_model_out = nan;
+    // the sample sd and the KS statistic are reported for every scored edge, also when the score is skipped
+    // (:542-544): diagnostics, and what the lognormal scoring branch re-derives its verdict from
+    double std_dev;
+    if (n - 1 == 0) std_dev = 4294967296.0;                                           // :563-564
+    else {
+        const double q = ((double)obs_sq - (double)n * (mean_ * mean_)) / (double)(n - 1);
+        if (q < 0) { std_dev = nan; flags |= BESST_EDGE_CPLX; }
+        else std_dev = sqrt(q);                                                       // :561
+    }
+    const double ks_out = dmax, sd_obs_out = std_dev;
     if (neg) {
         flags |= BESST_EDGE_NEGGAP;
     } else {
         const double std_dev_d_eq_0 = big ? sd_ml : 4294967296.0;                    // :548-558
-        double std_dev;
-        if (n - 1 == 0) std_dev = 4294967296.0;                                       // :563-564
-        else {
-            const double q = ((double)obs_sq - (double)n * (mean_ * mean_)) / (double)(n - 1);
-            if (q < 0) { std_dev = nan; flags |= BESST_EDGE_CPLX; }
-            else std_dev = sqrt(q);                                                   // :561
-        }
         const double span_score = n < 5 ? 0.0 : 1 - dmax;                             // :603-606
         double std_dev_score;
         if (std_dev_d_eq_0 == 0.0 || std_dev == 0.0 || std_dev != std_dev) std_dev_score = 0.0;
@@ -922,7 +925,7 @@ __global__ void __launch_bounds__(128) k_edge_finalize(const ScoreArgs A) {
             std_dev_score = y < x ? y : x;
         }
         score = (std_dev_score > 0.5 && span_score > 0.5) ? std_dev_score + span_score : 0.0;  // :614
-        ks_out = dmax; sd_obs_out = std_dev; sd_model_out = std_dev_d_eq_0;
+        sd_model_out = std_dev_d_eq_0;
     }
     A.E.gap[e] = gap_int;
     A.E.score[e] = score;
@@ -1340,6 +1343,78 @@ __global__ void __launch_bounds__(128)
     if (active && (threadIdx.x & 3) == 0) out[quad] = d + aofd * c.sd2;
 }
 
+// ---- lognormal GapEstimator (mathstats.log_normal_param_est, restated from the model: see the oracle) ---------
+// one warp per edge: the lanes share the pass over the edge's observations (32 strided partial sums combined by
+// a butterfly -- the summation order the oracle reproduces), g(d) in closed form from the partial moments of the
+// lognormal, integer ternary search for the maximum of the log-likelihood
+__device__ __forceinline__ double ln_Phi_dev(double z) { return 0.5 * erfc(-z / sqrt(2.0)); }
+__device__ __forceinline__ double ln_F0_dev(double x, double mu, double sigma) { return x > 0 ? ln_Phi_dev((log(x) - mu) / sigma) : 0.0; }
+__device__ __forceinline__ double ln_F1_dev(double x, double mu, double sigma) {
+    return x > 0 ? exp(mu + sigma * sigma / 2.0) * ln_Phi_dev((log(x) - mu - sigma * sigma) / sigma) : 0.0;
+}
+__device__ __forceinline__ double ln_g_dev(double d, double mu, double sigma, double c_min, double c_max, double r) {
+    const double A = d + 2 * r - 1, B = d + c_min + r, C = d + c_max + r, D = d + c_min + c_max + 1;
+    const double f0A = ln_F0_dev(A, mu, sigma), f0B = ln_F0_dev(B, mu, sigma), f0C = ln_F0_dev(C, mu, sigma), f0D = ln_F0_dev(D, mu, sigma);
+    const double f1A = ln_F1_dev(A, mu, sigma), f1B = ln_F1_dev(B, mu, sigma), f1C = ln_F1_dev(C, mu, sigma), f1D = ln_F1_dev(D, mu, sigma);
+    const double piece1 = -(d + 2 * r - 1) * (f0B - f0A) + (f1B - f1A);
+    const double piece2 = (c_min - r + 1) * (f0C - f0B);
+    const double piece3 = (d + c_min + c_max + 1) * (f0D - f0C) - (f1D - f1C);
+    return piece1 + piece2 + piece3;
+}
+__device__ __forceinline__ double ln_loglik_warp(long long d, double mu, double sigma, const int* __restrict__ samples, long long n,
+                                                 double c_min, double c_max, double r, int lane) {
+    const double g = ln_g_dev((double)d, mu, sigma, c_min, c_max, r);
+    if (!(g > 0)) return -__longlong_as_double(0x7ff0000000000000ll);   // -inf
+    double partial = 0.0;
+    const double v2 = 2.0 * sigma * sigma;
+    for (long long k = lane; k < n; k += 32) {
+        const double lx = log((double)((long long)__ldg(samples + k) + d));
+        partial += -lx - (lx - mu) * (lx - mu) / v2;
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) partial += __shfl_xor_sync(0xffffffffu, partial, off);
+    return partial - (double)n * log(g);
+}
+
+__global__ void __launch_bounds__(256)
+    k_gapest_lognormal(double mu, double sigma, double r, const int* __restrict__ samples, const long long* __restrict__ row_ptr,
+                       const double* __restrict__ len1, const double* __restrict__ len2, long long n_edges, int* gap_out) {
+    const int lane = threadIdx.x & 31;
+    const long long warp_global = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
+    for (long long e = warp_global; e < n_edges; e += n_warps) {
+        const long long b = row_ptr[e], n = row_ptr[e + 1] - b;
+        const int* s = samples + b;
+        const double c1 = len1[e], c2 = len2[e];
+        const double c_min = c1 < c2 ? c1 : c2, c_max = c1 < c2 ? c2 : c1;
+        int o_min = 2147483647;
+        for (long long k = lane; k < n; k += 32) { const int v = __ldg(s + k); o_min = v < o_min ? v : o_min; }
+        o_min = __reduce_min_sync(0xffffffffu, o_min);
+        const double mean_x = exp(mu + sigma * sigma / 2.0);
+        const double sd_x = sqrt((exp(sigma * sigma) - 1.0) * exp(2.0 * mu + sigma * sigma));
+        long long lo = (long long)(-c_min);
+        const long long alt = 1 - (long long)o_min;
+        if (alt > lo) lo = alt;
+        long long hi = (long long)(mean_x + 4.0 * sd_x);
+        long long best = lo;
+        if (hi > lo && n > 0) {
+            while (hi - lo > 2) {
+                const long long third = (hi - lo) / 3, m1 = lo + third, m2 = hi - third;
+                const double a = ln_loglik_warp(m1, mu, sigma, s, n, c_min, c_max, r, lane);
+                const double bb = ln_loglik_warp(m2, mu, sigma, s, n, c_min, c_max, r, lane);
+                if (a < bb) lo = m1 + 1; else hi = m2 - 1;
+            }
+            best = lo;
+            double best_l = ln_loglik_warp(lo, mu, sigma, s, n, c_min, c_max, r, lane);
+            for (long long d = lo + 1; d <= hi; ++d) {
+                const double v = ln_loglik_warp(d, mu, sigma, s, n, c_min, c_max, r, lane);
+                if (v > best_l) { best = d; best_l = v; }
+            }
+        }
+        if (lane == 0) gap_out[e] = (int)best;
+    }
+}
+
 int bits_for(uint64_t max_value) {
     int b = 1;
     while (b < 32 && (max_value >> b)) ++b;
@@ -1369,6 +1444,17 @@ int besst_launch_gapest(besst_ctx* ctx, const besst_lib_params& p, const double*
     const long long threads = n * 4;
     const int grid = (int)((threads + 127) / 128);
     { KTimer kt(ctx, BESST_K_GAPEST); k_gapest_batch<<<grid, 128, 0, ctx->stream>>>(c, d_mean_obs, d_len1, d_len2, n, d_gap, d_sd); }
+    BESST_CUDA_TRY(ctx, cudaGetLastError());
+    return BESST_OK;
+}
+
+int besst_launch_gapest_lognormal(besst_ctx* ctx, double mu, double sigma, double r, const int32_t* d_samples, const int64_t* d_row_ptr,
+                                  const double* d_len1, const double* d_len2, int64_t n, int32_t* d_gap) {
+    if (n == 0) return BESST_OK;
+    long long grid = (n * 32 + 255) / 256;
+    if (grid > (long long)ctx->sm_count * 16) grid = (long long)ctx->sm_count * 16;
+    { KTimer kt(ctx, BESST_K_GAPEST);
+      k_gapest_lognormal<<<(unsigned)grid, 256, 0, ctx->stream>>>(mu, sigma, r, d_samples, reinterpret_cast<const long long*>(d_row_ptr), d_len1, d_len2, n, d_gap); }
     BESST_CUDA_TRY(ctx, cudaGetLastError());
     return BESST_OK;
 }

@@ -218,6 +218,8 @@ int besst_launch_trsk_sd(besst_ctx* ctx, const besst_lib_params& p, const double
                          const double* d_len2, int64_t n, double* d_sd);
 int besst_launch_func_of_d(besst_ctx* ctx, const besst_lib_params& p, const double* d_d, const double* d_len1,
                            const double* d_len2, int64_t n, double* d_out);
+int besst_launch_gapest_lognormal(besst_ctx* ctx, double mu, double sigma, double r, const int32_t* d_samples, const int64_t* d_row_ptr,
+                                  const double* d_len1, const double* d_len2, int64_t n, int32_t* d_gap);
 int besst_launch_partition(besst_ctx* ctx, int world, besst_link_tuple* out_tuples, uint32_t* out_ordinals,
                            uint64_t* out_fishy, int64_t* tuple_counts, int64_t* fishy_counts);
 

@@ -231,6 +231,19 @@ class CudaEngine(object):
                     "besst_gapest_batch")
         return gap, sd
 
+    def gapest_lognormal_batch(self, mu, sigma, read_len, samples, row_ptr, len1, len2):
+        """ML gaps under the lognormal model from the raw observations of every edge (CSR layout)."""
+        samples = np.ascontiguousarray(samples, dtype=np.int32)
+        row_ptr = np.ascontiguousarray(row_ptr, dtype=np.int64)
+        len1 = np.ascontiguousarray(len1, dtype=np.float64)
+        len2 = np.ascontiguousarray(len2, dtype=np.float64)
+        n = row_ptr.shape[0] - 1
+        gap = np.zeros(n, dtype=np.int32)
+        self._check(self._L.besst_gapest_lognormal_batch(self._ctx, float(mu), float(sigma), float(read_len), samples.ctypes.data,
+                                                         row_ptr.ctypes.data, len1.ctypes.data, len2.ctypes.data, n, gap.ctypes.data),
+                    "besst_gapest_lognormal_batch")
+        return gap
+
     def func_of_d_batch(self, params, d, len1, len2):
         d = np.ascontiguousarray(d, dtype=np.float64)
         len1 = np.ascontiguousarray(len1, dtype=np.float64)

@@ -89,3 +89,65 @@ def PreCalcMLvaluesOfdLongContigs(mean, stdDev, readLen, engine=None):
                 table[prev_obs + i + 1] = d
         prev_obs = obs
     return table
+
+
+def update_info_gaps_batch(mean, sigma, read_len, sum_obs, nr_links, c1_len, c2_len, dValuesTable=None, engine=None):
+    """The gap `MakeScaffolds.UpdateInfo` assigns between two joined scaffolds (MakeScaffolds.py:428-466), for
+    arrays of edges at once: with a library sd and >= 5 links, two contigs longer than mean + 4 sd take the
+    pre-calculated table (`PreCalcMLvaluesOfdLongContigs`, :68; a miss falls back to the bisection), two
+    contigs longer than sd + read_len take `GapEstimator`, everything else the naive
+    int((n * mean - sum_obs) / n).  All bisections of the batch run in ONE kernel launch.
+    -> (avg_gap int64[n] before UpdateInfo's `<= 1 -> 1` clamp (:470-471), naive bool[n]: the entries the
+    reference appends to param.gap_estimations)"""
+    sum_obs = np.atleast_1d(np.asarray(sum_obs, dtype=np.float64))
+    nr = np.broadcast_to(np.asarray(nr_links, dtype=np.float64), sum_obs.shape)
+    c1 = np.broadcast_to(np.asarray(c1_len, dtype=np.float64), sum_obs.shape)
+    c2 = np.broadcast_to(np.asarray(c2_len, dtype=np.float64), sum_obs.shape)
+    data_observation = (nr * mean - sum_obs) / nr                      # :430
+    mean_obs = sum_obs / nr                                            # :432
+    fancy = bool(sigma) & (nr >= 5)                                     # :442
+    long_pair = fancy & (c1 > mean + 4 * sigma) & (c2 > mean + 4 * sigma)          # :444
+    mid_pair = fancy & ~long_pair & (c1 > sigma + read_len) & (c2 > sigma + read_len)   # :452
+    naive = ~(long_pair | mid_pair)
+    gap = np.trunc(data_observation).astype(np.int64)                  # int(data_observation) :455,462
+    search = mid_pair.copy()
+    if long_pair.any():
+        keys = np.rint(data_observation[long_pair]).astype(np.int64)   # int(round(x, 0)): half to even, like Python 3
+        table = dValuesTable or {}
+        looked = np.array([table.get(int(k), None) for k in keys.tolist()], dtype=object)
+        miss = np.array([v is None for v in looked], dtype=bool)
+        idx = np.nonzero(long_pair)[0]
+        gap[idx[~miss]] = np.array([int(v) for v in looked[~miss]], dtype=np.int64)
+        search[idx[miss]] = True                                       # :448-449 KeyError -> bisection
+    if search.any():
+        g, _ = gap_estimator_batch(mean, sigma, read_len, mean_obs[search], c1[search], c2[search], engine=engine)
+        gap[search] = g
+    return gap, (~fancy) | (fancy & naive)
+
+
+def lp_expected_means_batch(mean, sigma, read_len, mean_obs, c1_len, c2_len, engine=None):
+    """`mean_obs + GapEstimator(...)` for every observation of a path (order_contigs.py:294-310, the constants of
+    the gap LP) in one launch; call once per library parameter set (the PE-contamination links use
+    contamination_mean / contamination_stddev, :299-300)."""
+    mean_obs = np.atleast_1d(np.asarray(mean_obs, dtype=np.float64))
+    g, _ = gap_estimator_batch(mean, sigma, read_len, mean_obs, c1_len, c2_len, engine=engine)
+    return mean_obs + g
+
+
+def lognormal_gap_estimator_batch(mu_ln, sigma_ln, read_len, samples, row_ptr, c1_len, c2_len=None, engine=None):
+    """Drop-in for `mathstats.log_normal_param_est.GapEstimator` over many edges at once (CreateGraph.py:526,
+    MakeScaffolds.py:425-426, order_contigs.py:304-306): samples[row_ptr[i]:row_ptr[i+1]] are the raw
+    observations of edge i -- exactly the `observations` payload of the CSR the graph build returns.
+    One warp per edge on the device.  -> gap int32[n]"""
+    row_ptr = np.asarray(row_ptr, dtype=np.int64)
+    n = row_ptr.shape[0] - 1
+    c1 = np.broadcast_to(np.asarray(c1_len, dtype=np.float64), (n,))
+    c2 = c1 if c2_len is None else np.broadcast_to(np.asarray(c2_len, dtype=np.float64), (n,))
+    return _engine(engine).gapest_lognormal_batch(mu_ln, sigma_ln, read_len, samples, row_ptr, c1, c2)
+
+
+def LognormalGapEstimator(mu, sigma, read_length, samples, c1_len, c2_len=None, engine=None):
+    """scalar form, same signature as mathstats.log_normal_param_est.GapEstimator"""
+    samples = np.asarray(samples, dtype=np.int32)
+    return int(lognormal_gap_estimator_batch(mu, sigma, read_length, samples, [0, samples.shape[0]], [c1_len],
+                                             None if c2_len is None else [c2_len], engine=engine)[0])

@@ -24,6 +24,7 @@
  *                            order_contigs.py:300,308; pathgaps.py:108,204
  *   besst_libmetrics returns 1 (not an error) when fewer than 1001 insert-size
  *   samples exist (libmetrics.py:311-314).
+ *   besst_gapest_lognormal_batch  mathstats log_normal_param_est.GapEstimator (lognormal libraries)
  *   besst_trsk_sd_batch      param_est.tr_sk_std_dev at a caller-given gap
  *                            (CreateGraph.py:555 signature)
  *   besst_graph_view         the same result as views of pinned buffers owned by the ctx
@@ -316,6 +317,13 @@ int besst_gapest_batch(besst_ctx* ctx, const besst_lib_params* params, const dou
  * (mathstats funcDGeneral), what PreCalcMLvaluesOfdLongContigs tabulates (MakeScaffolds.py:68) */
 int besst_gapest_func_batch(besst_ctx* ctx, const besst_lib_params* params, const double* d, const double* len1,
                             const double* len2, int64_t n, double* func_out);
+
+/* lognormal GapEstimator (mathstats.log_normal_param_est.GapEstimator; CreateGraph.py:526, MakeScaffolds.py:425-426,
+ * order_contigs.py:304-306): the ML gap of every edge from its RAW observations (the `observations` payload of
+ * the CSR: samples[row_ptr[i] .. row_ptr[i+1])), one warp per edge.  mu_ln / sigma_ln = param.lognormal_mean /
+ * param.lognormal_sigma (libmetrics.py:385-388).  Host arrays in and out. */
+int besst_gapest_lognormal_batch(besst_ctx* ctx, double mu_ln, double sigma_ln, double read_len, const int32_t* samples,
+                                 const int64_t* row_ptr, const double* len1, const double* len2, int64_t n, int32_t* gap_out);
 
 /* tr_sk_std_dev(mean, sigma, read_len, len1[i], len2[i], gap[i]) (host arrays in/out) */
 int besst_trsk_sd_batch(besst_ctx* ctx, const besst_lib_params* params, const double* gap, const double* len1,

@@ -132,6 +132,77 @@ int besst_oracle_gapest_batch(const besst_lib_params* p, const double* mean_obs,
 }
 
 /* ------------------------------------------------------------------------- */
+/* mathstats.log_normal_param_est.GapEstimator (restated from the model, see
+ * oracle/mathstats_restated/mathstats/log_normal_param_est.py; call sites
+ * CreateGraph.py:526, MakeScaffolds.py:425-426, order_contigs.py:304-306)     */
+
+static double ln_Phi(double z) { return 0.5 * erfc(-z / sqrt(2.0)); }
+static double ln_F0(double x, double mu, double sigma) { return x > 0 ? ln_Phi((log(x) - mu) / sigma) : 0.0; }
+static double ln_F1(double x, double mu, double sigma) {
+    return x > 0 ? exp(mu + sigma * sigma / 2.0) * ln_Phi((log(x) - mu - sigma * sigma) / sigma) : 0.0;
+}
+
+double besst_oracle_lognormal_g(double d, double mu, double sigma, double c_min, double c_max, double r) {
+    double A = d + 2 * r - 1, B = d + c_min + r, C = d + c_max + r, D = d + c_min + c_max + 1;
+    double f0A = ln_F0(A, mu, sigma), f0B = ln_F0(B, mu, sigma), f0C = ln_F0(C, mu, sigma), f0D = ln_F0(D, mu, sigma);
+    double f1A = ln_F1(A, mu, sigma), f1B = ln_F1(B, mu, sigma), f1C = ln_F1(C, mu, sigma), f1D = ln_F1(D, mu, sigma);
+    double piece1 = -(d + 2 * r - 1) * (f0B - f0A) + (f1B - f1A);
+    double piece2 = (c_min - r + 1) * (f0C - f0B);
+    double piece3 = (d + c_min + c_max + 1) * (f0D - f0C) - (f1D - f1C);
+    return piece1 + piece2 + piece3;
+}
+
+static double ln_loglik(int64_t d, double mu, double sigma, const int32_t* samples, int64_t n, double c_min, double c_max, double r) {
+    double g = besst_oracle_lognormal_g((double)d, mu, sigma, c_min, c_max, r);
+    if (!(g > 0)) return -INFINITY;
+    double partial[32];
+    for (int l = 0; l < 32; ++l) partial[l] = 0.0;
+    double v2 = 2.0 * sigma * sigma;
+    for (int64_t k = 0; k < n; ++k) {   /* 32 strided partial sums, then a butterfly: the order a warp sums in */
+        double lx = log((double)((int64_t)samples[k] + d));
+        partial[k & 31] += -lx - (lx - mu) * (lx - mu) / v2;
+    }
+    for (int off = 16; off > 0; off >>= 1) {
+        double q[32];
+        for (int l = 0; l < 32; ++l) q[l] = partial[l] + partial[l ^ off];
+        for (int l = 0; l < 32; ++l) partial[l] = q[l];
+    }
+    return partial[0] - (double)n * log(g);
+}
+
+int32_t besst_oracle_lognormal_gap_estimator(double mu, double sigma, double r, const int32_t* samples, int64_t n, double c1,
+                                             double c2) {
+    double c_min = c1 < c2 ? c1 : c2, c_max = c1 < c2 ? c2 : c1;
+    int32_t o_min = samples[0];
+    for (int64_t k = 1; k < n; ++k) if (samples[k] < o_min) o_min = samples[k];
+    double mean_x = exp(mu + sigma * sigma / 2.0);
+    double sd_x = sqrt((exp(sigma * sigma) - 1.0) * exp(2.0 * mu + sigma * sigma));
+    int64_t lo = (int64_t)(-c_min), alt = 1 - (int64_t)o_min;
+    if (alt > lo) lo = alt;
+    int64_t hi = (int64_t)(mean_x + 4.0 * sd_x);
+    if (hi <= lo) return (int32_t)lo;
+    while (hi - lo > 2) {
+        int64_t third = (hi - lo) / 3, m1 = lo + third, m2 = hi - third;
+        if (ln_loglik(m1, mu, sigma, samples, n, c_min, c_max, r) < ln_loglik(m2, mu, sigma, samples, n, c_min, c_max, r)) lo = m1 + 1;
+        else hi = m2 - 1;
+    }
+    int64_t best = lo;
+    double best_l = ln_loglik(lo, mu, sigma, samples, n, c_min, c_max, r);
+    for (int64_t d = lo + 1; d <= hi; ++d) {
+        double v = ln_loglik(d, mu, sigma, samples, n, c_min, c_max, r);
+        if (v > best_l) { best = d; best_l = v; }
+    }
+    return (int32_t)best;
+}
+
+int besst_oracle_gapest_lognormal_batch(double mu, double sigma, double r, const int32_t* samples, const int64_t* row_ptr,
+                                        const double* len1, const double* len2, int64_t n, int32_t* gap_out) {
+    for (int64_t i = 0; i < n; ++i)
+        gap_out[i] = besst_oracle_lognormal_gap_estimator(mu, sigma, r, samples + row_ptr[i], row_ptr[i + 1] - row_ptr[i], len1[i], len2[i]);
+    return 0;
+}
+
+/* ------------------------------------------------------------------------- */
 /* scipy.stats.ks_2samp(...).statistic as used at CreateGraph.py:595           */
 
 static int cmp_double(const void* a, const void* b) {
@@ -375,9 +446,11 @@ static void score_edge(const besst_lib_params* p, int64_t n, int64_t obs, int64_
     else gap = data_observation;
     *gap_out = (int32_t)gap; /* :541 int() */
     *ks_out = NAN; *sd_obs_out = NAN; *sd_model_out = NAN;
-    if (-gap > len1 || -gap > len2) { *score_out = 0.0; *flags |= BESST_EDGE_NEGGAP; return; } /* :542-544 */
-    double std_dev_d_eq_0 = big ? besst_oracle_tr_sk_std_dev(mu, sigma, r, len1, len2, gap, p->erf_variant)
-                                : 4294967296.0;                         /* :548-558 */
+    int neg = (-gap > len1 || -gap > len2);                               /* :542-544: score = 0, the rest is skipped; ks and
+                                                                             sd_obs are still reported (diagnostics; the lognormal
+                                                                             scoring branch re-derives the verdict from them) */
+    double std_dev_d_eq_0 = (big && !neg) ? besst_oracle_tr_sk_std_dev(mu, sigma, r, len1, len2, gap, p->erf_variant)
+                                          : 4294967296.0;               /* :548-558 */
     double std_dev;
     if (n - 1 == 0) std_dev = 4294967296.0;                               /* :563-564 */
     else {
@@ -401,8 +474,10 @@ static void score_edge(const besst_lib_params* p, int64_t n, int64_t obs, int64_
     double std_dev_score;
     if (std_dev_d_eq_0 == 0.0 || std_dev == 0.0 || isnan(std_dev)) std_dev_score = 0.0; /* ZeroDivisionError :610-611 */
     else { double x = std_dev / std_dev_d_eq_0, y = std_dev_d_eq_0 / std_dev; std_dev_score = y < x ? y : x; }
+    *ks_out = ks; *sd_obs_out = std_dev;
+    if (neg) { *score_out = 0.0; *flags |= BESST_EDGE_NEGGAP; return; }
     *score_out = (std_dev_score > 0.5 && span_score > 0.5) ? std_dev_score + span_score : 0.0; /* :614 */
-    *ks_out = ks; *sd_obs_out = std_dev; *sd_model_out = std_dev_d_eq_0;
+    *sd_model_out = std_dev_d_eq_0;
 }
 
 /* CreateGraph.PE record loop :111-211 + per-edge scoring :498-614 */

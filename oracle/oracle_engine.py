@@ -21,3 +21,6 @@ class OracleEngine(object):
 
     def gapest_batch(self, params, mean_obs, len1, len2):
         return oracle_lib.gapest_batch(params, mean_obs, len1, len2)
+
+    def gapest_lognormal_batch(self, mu, sigma, read_len, samples, row_ptr, len1, len2):
+        return oracle_lib.gapest_lognormal_batch(mu, sigma, read_len, samples, row_ptr, len1, len2)

@@ -77,6 +77,21 @@ def graph_build(rows, n_scaffolds, params, batch):
     return abi.graph_result(out, arrays), tuples, dict(zip(fk.tolist(), fc.tolist())), bool(cons.value)
 
 
+def gapest_lognormal_batch(mu, sigma, read_len, samples, row_ptr, len1, len2):
+    L = lib()
+    samples = np.ascontiguousarray(samples, dtype=np.int32)
+    row_ptr = np.ascontiguousarray(row_ptr, dtype=np.int64)
+    len1 = np.ascontiguousarray(len1, dtype=np.float64)
+    len2 = np.ascontiguousarray(len2, dtype=np.float64)
+    n = row_ptr.shape[0] - 1
+    gap = np.zeros(n, dtype=np.int32)
+    L.besst_oracle_gapest_lognormal_batch.argtypes = [C.c_double, C.c_double, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p,
+                                                      C.c_void_p, C.c_int64, C.c_void_p]
+    L.besst_oracle_gapest_lognormal_batch(float(mu), float(sigma), float(read_len), samples.ctypes.data, row_ptr.ctypes.data,
+                                          len1.ctypes.data, len2.ctypes.data, n, gap.ctypes.data)
+    return gap
+
+
 def libmetrics(rows, params, batch, ref_lengths, want_isize, cap=1 << 20):
     L = lib()
     rows = np.ascontiguousarray(rows)

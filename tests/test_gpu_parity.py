@@ -560,3 +560,42 @@ def test_distributed_nccl_equals_oracle():
                           "--master-addr", "127.0.0.1", "--master-port", "29517", os.path.join(here, "dist_check.py")],
                          capture_output=True, text=True, timeout=600)
     assert out.returncode == 0 and "DIST_CHECK_OK" in out.stdout, out.stdout[-2000:] + out.stderr[-4000:]
+
+
+def test_lognormal_gapest_batch_matches_oracle(cuda_engine):
+    """besst_gapest_lognormal_batch (one warp per edge over the raw observations) against the C restatement:
+    ragged edges from 1 to 3000 observations, short and long contigs, negative and large gaps."""
+    rng = np.random.default_rng(12)
+    mu, sigma, r = 8.0, 0.25, 100.0
+    samples, row_ptr, l1, l2 = [], [0], [], []
+    for i in range(300):
+        n = int(rng.choice([1, 2, 5, 31, 32, 33, 100, 700, 3000]))
+        d = int(rng.integers(-150, 3000))
+        s = np.clip(np.rint(rng.lognormal(mu, sigma, n) - d), 210, None).astype(np.int64)
+        samples += s.tolist()
+        row_ptr.append(len(samples))
+        l1.append(float(rng.integers(1200, 40000)))
+        l2.append(float(rng.integers(1200, 40000)) + 0.5 * (i % 2))
+    got = cuda_engine.gapest_lognormal_batch(mu, sigma, r, samples, row_ptr, l1, l2)
+    want = oracle_lib.gapest_lognormal_batch(mu, sigma, r, samples, row_ptr, l1, l2)
+    assert np.array_equal(got, want), np.nonzero(got != want)[0][:10]
+
+
+def test_lognormal_scoring_branch_cuda_equals_oracle(cuda_engine):
+    """CreateGraph.lognormal_rescore (CreateGraph.py:485-493,523-531) with the CUDA engine against the oracle engine"""
+    import math
+    from oracle_engine import OracleEngine
+    from besst_b200 import CreateGraph as CG
+    lib, batch, params, table = _setup("small_mp")
+
+    class P(object):
+        mean_ins_size, read_len = lib.mu, 100.0
+        lognormal_sigma = 0.17
+        lognormal_mean = math.log(lib.mu) - 0.17 ** 2 / 2
+        empirical_distribution = {x: math.exp(-((x - lib.mu) / lib.sigma) ** 2 / 2) for x in range(200, 6001)}
+    got = cuda_engine.graph_build(table, params, batch)
+    want = OracleEngine().graph_build(table, params, batch)
+    CG.lognormal_rescore(got, table, P, cuda_engine)
+    CG.lognormal_rescore(want, table, P, OracleEngine())
+    helpers.assert_graph_equal(got, want, label="lognormal")
+    assert (got.gap[(got.flags & abi.EDGE_BIG) != 0] != 0).any()

@@ -4,6 +4,7 @@ the closed forms against numerical quadrature of the published GapEst model, the
 C restatement against the Python restatement bit for bit, KS against scipy, the
 inverse normal CDF against scipy within its published error, and e_nr_links
 against the reference module's value recorded in SURVEY.md 8c."""
+import ctypes
 import math
 import os
 import sys
@@ -124,3 +125,141 @@ def test_expected_links_known_answer():
             a = e_nr_links.ExpectedLinks(args[0], args[1], args[2], e_nr_links.Param(*args[3]))
             b = mod.ExpectedLinks(args[0], args[1], args[2], mod.Param(*args[3]))
             assert a == b
+
+
+def test_update_info_gap_batch_follows_the_reference_guards():
+    """MakeScaffolds.UpdateInfo's gap choice (:428-466) replayed edge by edge with the restated mathstats against the
+    batched form (one launch for all bisections); estimated, non-integral library parameters as get_metrics leaves them."""
+    GC = ms_pe
+    from besst_b200 import param_est
+    from oracle_engine import OracleEngine
+    mean, sd, r = 2987.4142135, 512.7182818, 99.37
+    table = GC.PreCalcMLvaluesOfdLongContigs(mean, sd, r)
+    rng = np.random.default_rng(8)
+    n = 400
+    nr = rng.integers(1, 60, n)
+    c1 = rng.choice([300, 700, 2000, 6000, 9000], n).astype(np.float64)
+    c2 = rng.choice([450, 800, 5100, 5200, 12000], n).astype(np.float64)
+    mean_obs = rng.uniform(300.0, 4200.0, n)       # includes observations outside the table's range
+    sum_obs = np.floor(mean_obs * nr)
+    want, naive = [], []
+    for i in range(n):
+        data_observation = (nr[i] * mean - sum_obs[i]) / float(nr[i])
+        mo = sum_obs[i] / float(nr[i])
+        is_naive = False
+        if sd and nr[i] >= 5:
+            if c1[i] > mean + 4 * sd and c2[i] > mean + 4 * sd:
+                try:
+                    g = table[int(round(data_observation, 0))]
+                except KeyError:
+                    g = GC.GapEstimator(mean, sd, r, mo, c1[i], c2[i])
+            elif c1[i] > sd + r and c2[i] > sd + r:
+                g = GC.GapEstimator(mean, sd, r, mo, c1[i], c2[i])
+            else:
+                g, is_naive = int(data_observation), True
+        else:
+            g, is_naive = int(data_observation), True
+        want.append(g)
+        naive.append(is_naive)
+    got, got_naive = param_est.update_info_gaps_batch(mean, sd, r, sum_obs, nr, c1, c2, table, engine=OracleEngine())
+    assert got.tolist() == want and got_naive.tolist() == naive
+    assert 20 < sum(naive) < n - 50
+    lp = param_est.lp_expected_means_batch(mean, sd, r, mean_obs[:50], c1[:50] + 1000, c2[:50] + 1000, engine=OracleEngine())
+    assert lp.tolist() == [mean_obs[i] + GC.GapEstimator(mean, sd, r, mean_obs[i], c1[i] + 1000, c2[i] + 1000) for i in range(50)]
+
+
+# ---- lognormal GapEstimator (mathstats.log_normal_param_est, restated from the model) ----------------------------------
+from mathstats import log_normal_param_est as ms_ln  # noqa: E402
+
+
+def _trapezoid_weight(o, c_min, c_max, r):
+    return np.clip(np.minimum(np.minimum(o - 2 * r + 1, c_min - r + 1), c_min + c_max + 1 - o), 0, None)
+
+
+@pytest.mark.parametrize("d,c1,c2", [(500, 6000, 8000), (1500, 2500, 9000), (-40, 3000, 3000), (2500, 20000, 30000)])
+def test_lognormal_g_closed_form_equals_quadrature(d, c1, c2):
+    mu, sigma, r = 8.0, 0.25, 100
+    c_min, c_max = min(c1, c2), max(c1, c2)
+    xs = np.linspace(1, 60000, 2000001)
+    f = np.exp(-(np.log(xs) - mu) ** 2 / (2 * sigma ** 2)) / (xs * sigma * np.sqrt(2 * np.pi))
+    quad = np.trapezoid(_trapezoid_weight(xs - d, c_min, c_max, r) * f, xs)
+    assert ms_ln.g_of_d(d, mu, sigma, c_min, c_max, r) == pytest.approx(quad, rel=1e-9)
+    L = oracle_lib.lib()
+    L.besst_oracle_lognormal_g.restype = ctypes.c_double
+    L.besst_oracle_lognormal_g.argtypes = [ctypes.c_double] * 6
+    assert L.besst_oracle_lognormal_g(d, mu, sigma, c_min, c_max, r) == ms_ln.g_of_d(d, mu, sigma, c_min, c_max, r)
+
+
+def _simulate(rng, mu, sigma, r, c1, c2, d, n):
+    c_min, c_max = min(c1, c2), max(c1, c2)
+    out = []
+    while len(out) < n:
+        o = np.rint(rng.lognormal(mu, sigma, 4000) - d)
+        acc = rng.random(4000) * (c_min - r + 1) < _trapezoid_weight(o, c_min, c_max, r)
+        out += [int(v) for v in o[acc]]
+    return out[:n]
+
+
+def test_lognormal_estimator_recovers_the_simulated_gap_and_c_equals_python():
+    rng = np.random.default_rng(1)
+    mu, sigma, r = 8.0, 0.25, 100
+    samples, row_ptr, l1, l2, truth = [], [0], [], [], []
+    for (c1, c2, d, n) in ((6000, 8000, 500, 300), (2500, 9000, 1500, 200), (3000, 3000, -40, 400), (20000, 30000, 2500, 60)):
+        for _ in range(12):
+            samples += _simulate(rng, mu, sigma, r, c1, c2, d, n)
+            row_ptr.append(len(samples)); l1.append(c1); l2.append(c2); truth.append(d)
+    got = oracle_lib.gapest_lognormal_batch(mu, sigma, r, samples, row_ptr, l1, l2)
+    want = [ms_ln.GapEstimator(mu, sigma, r, samples[row_ptr[i]:row_ptr[i + 1]], l1[i], l2[i]) for i in range(len(l1))]
+    assert got.tolist() == want                       # C restatement == Python restatement, bit for bit
+    err = got.reshape(4, 12).mean(axis=1) - np.array([500, 1500, -40, 2500])
+    naive = np.array([np.exp(mu + sigma ** 2 / 2) - np.mean(samples[row_ptr[12 * k]:row_ptr[12 * k + 12]]) for k in range(4)]) - np.array([500, 1500, -40, 2500])
+    # within 4 standard errors of the truth (sd of one estimate ~ 41 / 108 / 40 / 226 bp), where the naive estimate is 300-900 bp off
+    assert np.all(np.abs(err) < np.array([48, 125, 48, 260])) and np.all(np.abs(err[[0, 1, 3]]) < 0.3 * np.abs(naive[[0, 1, 3]]))
+
+
+def test_lognormal_scoring_branch_vectorised_equals_scalar_replay():
+    """besst_b200.CreateGraph.lognormal_rescore against an edge-by-edge replay of the reference's branch
+    (CreateGraph.py:485-493,523-531,542-614) with the restated estimator."""
+    import helpers
+    from oracle_engine import OracleEngine
+    from besst_b200 import CreateGraph as CG, synth
+    lib = synth.make_config("small_mp")
+    batch = lib.to_batch()
+    params = abi.make_params("rf", 11, 100.0, 3000.0, 500.0, 6000.0)
+    table = helpers.table_for(batch, helpers.first_library_objects(batch.references, batch.lengths, 5000.0))
+    eng = OracleEngine()
+    res = eng.graph_build(table, params, batch)
+    base_gap, base_score = res.gap.copy(), res.score.copy()
+
+    class P(object):
+        mean_ins_size, read_len = 3000.0, 100.0
+        lognormal_sigma = 0.17
+        lognormal_mean = math.log(3000.0) - 0.17 ** 2 / 2
+        empirical_distribution = {x: math.exp(-((x - 3000.0) / 500.0) ** 2 / 2) for x in range(200, 6001)}
+    CG.lognormal_rescore(res, table, P, eng)
+    emp, max_isize = P.empirical_distribution, 6000
+    cond = CG.get_conditional_stddevs(list(range(0, int(max_isize * 0.8), max_isize // 50)), emp, max_isize)
+    changed = 0
+    for e in np.nonzero(res.flags & abi.EDGE_SCORED)[0].tolist():
+        n = int(res.nr_links[e])
+        len1, len2 = float(table.scaffold_lengths[res.edge_u[e] >> 1]), float(table.scaffold_lengths[res.edge_v[e] >> 1])
+        samples = (res.obs_u[res.row_ptr[e]:res.row_ptr[e + 1]].astype(np.int64) + res.obs_v[res.row_ptr[e]:res.row_ptr[e + 1]]).tolist()
+        if 2 * 500.0 < len1 and 2 * 500.0 < len2:
+            gap = ms_ln.GapEstimator(P.lognormal_mean, P.lognormal_sigma, P.read_len, samples, len1, c2_len=len2)
+            gap = min(gap, len(cond) - 1)
+            sd0 = cond[int(gap)] if gap > 0 else cond[0]
+        else:
+            gap = (n * P.mean_ins_size - int(res.obs_sum[e])) / float(n)
+            sd0 = 2 ** 32
+        assert int(res.gap[e]) == int(gap)
+        if -gap > len1 or -gap > len2:
+            assert res.score[e] == 0 and res.flags[e] & abi.EDGE_NEGGAP
+            continue
+        assert not res.flags[e] & abi.EDGE_NEGGAP
+        sd = float(res.sd_obs[e])
+        sds = 0 if (sd == 0 or sd != sd) else min(sd / sd0, sd0 / sd)
+        span = 0 if n < 5 else 1 - float(res.ks[e])
+        want = sds + span if sds > 0.5 and span > 0.5 else 0
+        assert res.score[e] == want
+        changed += int(res.gap[e] != base_gap[e])
+    assert changed > 20   # the lognormal estimator really replaced the normal one
