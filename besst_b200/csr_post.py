@@ -177,14 +177,24 @@ class CsrGraphs(object):
         res, table, param = self.res, self.table, self.param
         G, G_prime = new_graph(), new_graph()
         names = table.scaffold_names
-        slen = table.scaffold_lengths
+        slen = table.scaffold_lengths.tolist()
+
+        def internals(graph):
+            # the node / adjacency dicts behind the Graph object (networkx >= 2: _node/_adj; 1.x: node/adj ARE the dicts).
+            # Filling them directly is what add_node / add_edge do, minus ~1 us of argument handling per call --
+            # seconds for the 1e5..1e6 nodes and edges of a real assembly.
+            return (graph._node, graph._adj) if hasattr(graph, "_adj") else (graph.node, graph.adj)
 
         def add_nodes(graph, idxs):
+            node, adj = internals(graph)
             for i in idxs:
-                name, length = names[i], int(slen[i])
-                graph.add_node((name, 'L'), length=length)
-                graph.add_node((name, 'R'), length=length)
-                graph.add_edge((name, 'L'), (name, 'R'), nr_links=None)
+                name, length = names[i], slen[i]
+                nl_, nr_ = (name, 'L'), (name, 'R')
+                node[nl_] = {'length': length}
+                node[nr_] = {'length': length}
+                d = {'nr_links': None}
+                adj[nl_] = {nr_: d}
+                adj[nr_] = {nl_: d}
         nl, S = self.n_large, table.n_scaffolds
         add_nodes(G, np.nonzero(self.node_G[:nl])[0].tolist())
         add_nodes(G_prime, (np.nonzero(self.node_GP[nl:])[0] + nl).tolist())
@@ -200,28 +210,31 @@ class CsrGraphs(object):
             tot_all = res.obs_u.astype(np.int64) + res.obs_v
             total = lambda b, t: tot_all[b:t].tolist()                     # noqa: E731
             one = lambda a, b, t: a[b:t].tolist()                          # noqa: E731
-        row_ptr = res.row_ptr
         scoring = not param.no_score
-        for e in order.tolist():
-            u, v = int(res.edge_u[e]), int(res.edge_v[e])
-            nu = (names[u >> 1], 'R' if u & 1 else 'L')
-            nv = (names[v >> 1], 'R' if v & 1 else 'L')
-            b, t = int(row_ptr[e]), int(row_ptr[e + 1])
-            nr, obs, obs_sq = int(res.nr_links[e]), int(res.obs_sum[e]), int(res.obs_sq[e])
-            if alive_G[e]:
-                G.add_edge(nv, nu, nr_links=nr, obs=obs, obs_sq=obs_sq, observations=total(b, t))
+        _, adj_G = internals(G)
+        _, adj_GP = internals(G_prime)
+        side = ('L', 'R')
+        cols = zip(res.edge_u[order].tolist(), res.edge_v[order].tolist(), res.row_ptr[order].tolist(), res.row_ptr[order + 1].tolist(),
+                   res.nr_links[order].tolist(), res.obs_sum[order].tolist(), res.obs_sq[order].tolist(), alive_G[order].tolist(),
+                   alive_GP[order].tolist(), res.flags[order].tolist(), res.gap[order].tolist(), res.score[order].tolist())
+        for u, v, b, t, nr, obs, obs_sq, in_G, in_GP, flags, gap, score in cols:
+            nu = (names[u >> 1], side[u & 1])
+            nv = (names[v >> 1], side[v & 1])
+            if in_G:
+                d = {'nr_links': nr, 'obs': obs, 'obs_sq': obs_sq, 'observations': total(b, t)}
                 if scoring:
-                    d = G[nu][nv]
-                    flags = int(res.flags[e])
                     if flags & abi.EDGE_NEGGAP:   # score skipped: the per-scaffold lists stay (:542-544, 848-849)
                         d[nu[0]] = one(res.obs_u, b, t)
                         d[nv[0]] = one(res.obs_v, b, t)
-                        d['gap'] = int(res.gap[e])
+                        d['gap'] = gap
                         d['score'] = 0
                     else:
-                        d['gap'] = int(res.gap[e])
-                        s = float(res.score[e])
-                        d['score'] = s if s != 0.0 else 0
-            if alive_GP[e]:
-                G_prime.add_edge(nv, nu, nr_links=nr, obs=obs, obs_sq=obs_sq, observations=total(b, t))
+                        d['gap'] = gap
+                        d['score'] = score if score != 0.0 else 0
+                adj_G[nv][nu] = d
+                adj_G[nu][nv] = d
+            if in_GP:
+                d = {'nr_links': nr, 'obs': obs, 'obs_sq': obs_sq, 'observations': total(b, t)}
+                adj_GP[nv][nu] = d
+                adj_GP[nu][nv] = d
         return G, G_prime

@@ -224,7 +224,7 @@ extern "C" int besst_links_extract(besst_ctx* ctx, const besst_lib_params* param
     ctx->have_links = ctx->have_graph = ctx->have_runs = false;
     ctx->extract_params = *params;
     ctx->n_stage_marks = 0;
-    ctx->prof_used = 0;
+    if (!ctx->prof_accumulate) ctx->prof_used = 0;
     besst_mark(ctx);
     DeviceRecords d;
     if (records && !records->on_device && records->n > ctx->slice_records) {
@@ -621,6 +621,7 @@ extern "C" int besst_kernel_launches(besst_ctx* ctx, int64_t* n_launches) {
 extern "C" int besst_set_profiling(besst_ctx* ctx, int enabled) {
     if (!ctx) return BESST_E_INVALID;
     ctx->prof = enabled != 0;
+    ctx->prof_accumulate = enabled == 2;
     ctx->prof_used = 0;
     return BESST_OK;
 }
@@ -634,5 +635,6 @@ extern "C" int besst_kernel_profile(besst_ctx* ctx, int32_t* kernel_ids, float* 
         kernel_ids[n] = ctx->prof_pool[i].id;
         BESST_CUDA_TRY(ctx, cudaEventElapsedTime(&ms[n], ctx->prof_pool[i].a, ctx->prof_pool[i].b));
     }
+    if (ctx->prof_accumulate) ctx->prof_used = 0;   // read once: the next builds start a new series
     return n;
 }

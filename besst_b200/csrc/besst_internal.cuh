@@ -145,6 +145,7 @@ struct besst_ctx {
 
     // per-kernel profiling (optional)
     bool prof = false;
+    bool prof_accumulate = false;   // keep the launches of several builds until besst_kernel_profile reads them
     struct ProfEntry { int id; cudaEvent_t a, b; };
     std::vector<ProfEntry> prof_pool;
     size_t prof_used = 0;

@@ -372,6 +372,12 @@ class DistributedGraphBuild(object):
                     p = _copy_params(params, halos[rank])
                 continue
             break
+        # coverage + counters are final once the extraction is: their all-reduce runs on the collective's own stream
+        # WHILE the runs are exchanged and the graph is built, and is waited for at the end of the step
+        aligned, counters = self.b.partial_tensors()
+        counters[abi.CNT_LAST_OBS1:] = 0   # per-rank slots (last / first call): not sums
+        pending = [dist.all_reduce(aligned, op=dist.ReduceOp.SUM, group=self.group, async_op=True),
+                   dist.all_reduce(counters, op=dist.ReduceOp.SUM, group=self.group, async_op=True)]
         n_by_rank = M[:, 1]
         LC, RC, FC = M[:, 7:7 + world], M[:, 7 + world:7 + 2 * world], M[:, 7 + 2 * world:7 + 3 * world]
         rl, rr, rf = LC[:, rank], RC[:, rank], FC[:, rank]
@@ -398,11 +404,9 @@ class DistributedGraphBuild(object):
         first_base = np.concatenate([[0], np.cumsum(n_by_rank)[:-1]])
         sizes = self.b.runs_to_graph(p, recv_obs, recv_desc, world, block_bits, rr, rl, first_base, recv_f)
         self._mark("runs_to_graph")
-        aligned, counters = self.b.partial_tensors()
-        counters[abi.CNT_LAST_OBS1:] = 0   # per-rank slots (last / first call): not sums
-        dist.all_reduce(aligned, op=dist.ReduceOp.SUM, group=self.group)
-        dist.all_reduce(counters, op=dist.ReduceOp.SUM, group=self.group)
-        self._mark("all_reduce")
+        for w in pending:
+            w.wait()
+        self._mark("all_reduce (tail not hidden)")
         self.last = dict(sizes=sizes, global_first=True, n_tuples_by_rank=n_by_rank.tolist(), aligned=aligned, counters=counters,
                          last_call=global_last, first_call=global_first, halo=halos[rank])
         return sizes

@@ -269,10 +269,10 @@ class CudaEngine(object):
         self._check(self._L.besst_last_timing(self._ctx, C.byref(total), stages), "besst_last_timing")
         return total.value, dict(zip(STAGE_NAMES, list(stages)[:len(STAGE_NAMES)]))
 
-    def set_profiling(self, on):
-        self._check(self._L.besst_set_profiling(self._ctx, int(bool(on))), "besst_set_profiling")
+    def set_profiling(self, on, accumulate=False):
+        self._check(self._L.besst_set_profiling(self._ctx, 2 if (on and accumulate) else int(bool(on))), "besst_set_profiling")
 
-    def kernel_profile(self, cap=256):
+    def kernel_profile(self, cap=1 << 16):
         """[(kernel name, ms)] per launch of the last build (needs set_profiling(True))."""
         ids = np.zeros(cap, dtype=np.int32)
         ms = np.zeros(cap, dtype=np.float32)

@@ -372,6 +372,7 @@ int besst_kernel_launches(besst_ctx* ctx, int64_t* n_launches);
 #define BESST_K_RUNS 16        /* k_run_count/k_scan_blocks64/k_run_write: heads and offsets over the sorted runs (K3') */
 #define BESST_K_KS_BLOCK 17    /* k_ks_block: in-block sort + KS evaluation of the edges with <= 2048 links (K5') */
 #define BESST_N_KERNEL_IDS 18
+/* enabled: 0 off, 1 the launches of the LAST build, 2 accumulate over builds until besst_kernel_profile reads (and clears) them */
 int besst_set_profiling(besst_ctx* ctx, int enabled);
 int besst_kernel_profile(besst_ctx* ctx, int32_t* kernel_ids, float* ms, int32_t cap);
 
