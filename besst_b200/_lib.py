@@ -18,7 +18,7 @@ EXPORTS = ["besst_abi_version", "besst_create", "besst_destroy", "besst_last_err
            "besst_gapest_batch", "besst_last_timing", "besst_kernel_launches", "besst_set_profiling",
            "besst_kernel_profile", "besst_links_partials_device", "besst_links_fetch", "besst_links_partition",
            "besst_trsk_sd_batch", "besst_set_stream", "besst_graph_view", "besst_links_group", "besst_runs_route",
-           "besst_runs_pack", "besst_runs_to_graph", "besst_runs_pack_peer", "besst_gapest_func_batch", "besst_runs_obs_bytes", "besst_contigs_select", "besst_csr_prune_dense", "besst_gapest_lognormal_batch"]
+           "besst_runs_pack", "besst_runs_to_graph", "besst_runs_pack_peer", "besst_gapest_func_batch", "besst_runs_obs_bytes", "besst_contigs_select", "besst_csr_prune_dense", "besst_gapest_lognormal_batch", "besst_exchange_prepare"]
 
 _lib = None
 
@@ -48,6 +48,7 @@ def load():
     L.besst_last_error.argtypes = [vp]
     L.besst_set_contigs.argtypes = [vp, vp, i64, i64, i64]
     L.besst_contigs_select.argtypes = [vp, i32]
+    L.besst_exchange_prepare.argtypes = [vp, i32, vp, vp, vp, vp, vp]
     L.besst_gapest_lognormal_batch.argtypes = [vp, C.c_double, C.c_double, C.c_double, vp, vp, vp, vp, i64, vp]
     L.besst_csr_prune_dense.restype = i64
     L.besst_csr_prune_dense.argtypes = [i64, vp, vp, vp, i32, vp]

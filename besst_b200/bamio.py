@@ -41,7 +41,7 @@ class BamStats(C.Structure):
 
 WINDOW_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.POINTER(_Columns), C.c_int64)
 
-BAMIO_EXPORTS = ["besst_bamio_abi_version", "besst_bam_read", "besst_bam_stream", "besst_bam_n_refs", "besst_bam_ref_name", "besst_bam_ref_length",
+BAMIO_EXPORTS = ["besst_bamio_abi_version", "besst_bam_read", "besst_bam_stream", "besst_bam_stopped", "besst_bam_n_refs", "besst_bam_ref_name", "besst_bam_ref_length",
                  "besst_bam_get_columns", "besst_bam_get_stats", "besst_bam_close"]
 
 
@@ -65,6 +65,7 @@ def load_bamio():
     L.besst_bam_get_columns.argtypes = [C.c_void_p, C.POINTER(_Columns)]
     L.besst_bam_get_stats.argtypes = [C.c_void_p, C.POINTER(BamStats)]
     L.besst_bam_close.argtypes = [C.c_void_p]
+    L.besst_bam_stopped.argtypes = [C.c_void_p]
     _bamio = L
     return L
 
@@ -209,7 +210,8 @@ def read_fasta_lengths(path):
 def stream_bam_native(path, on_window, threads=0, max_records=None, head_records=1000):
     """Decode the file window by window: on_window(columns, first_record, references, lengths) is called for each
     window with a dict of numpy views (tid, mtid, pos, mpos, tlen, qlen, flag, mapq) that are valid only during the
-    call -- copy (or upload) what you need.  Returning a true value stops the pass.  -> stats dict.
+    call -- copy (or upload) what you need.  Returning a true value stops the pass (stats['stopped'] is then True).
+    -> stats dict.
     Memory stays bounded for files of any size; this is the hook for overlapping ingest with the sliced upload of
     besst_graph_build."""
     L = load_bamio()
@@ -246,11 +248,11 @@ def stream_bam_native(path, on_window, threads=0, max_records=None, head_records
             L.besst_bam_close(ptr)
         raise failure[0]
     if not ptr:
-        msg = err.value.decode(errors="replace")
-        if "stopped by the window callback" in msg:
-            return None
-        raise IOError("besst_bam_stream: %s" % msg)
+        raise IOError("besst_bam_stream: %s" % err.value.decode(errors="replace"))
     st = BamStats()
     L.besst_bam_get_stats(ptr, C.byref(st))
+    stopped = bool(L.besst_bam_stopped(ptr))
     L.besst_bam_close(ptr)
-    return {k: getattr(st, k) for k, _ in BamStats._fields_}
+    stats = {k: getattr(st, k) for k, _ in BamStats._fields_}
+    stats["stopped"] = stopped   # on_window returned a true value before the end of the file
+    return stats

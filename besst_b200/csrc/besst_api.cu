@@ -324,6 +324,66 @@ extern "C" int besst_links_group(besst_ctx* ctx, int64_t* n_runs) {
     return BESST_OK;
 }
 
+// group + route counts + fishy partition queued back to back, ONE host read for all sizes
+extern "C" int besst_exchange_prepare(besst_ctx* ctx, int32_t world, uint64_t* out_fishy_device, int64_t* summary,
+                                      int64_t* link_counts, int64_t* run_counts, int64_t* fishy_counts) {
+    if (!ctx || !ctx->have_links) { if (ctx) ctx->err = "no extracted links"; return BESST_E_STATE; }
+    if (world < 1 || world > 16 || !summary || !link_counts || !run_counts || !fishy_counts || (ctx->n_fishy_keys > 0 && !out_fishy_device)) {
+        ctx->err = "exchange_prepare: bad arguments";
+        return BESST_E_INVALID;
+    }
+    cudaSetDevice(ctx->device);
+    ctx->have_runs = false;
+    int bv = 1;
+    {
+        const uint64_t m = (uint64_t)(2 * ctx->n_scaffolds > 0 ? 2 * ctx->n_scaffolds - 1 : 1);
+        while (bv < 32 && (m >> bv)) ++bv;
+    }
+    const int64_t n = ctx->n_tuples;
+    const int64_t blocks = (n + 2047) / 2048;
+    int bb = 1;
+    while (bb < 32 && ((uint64_t)(blocks > 1 ? blocks - 1 : 1) >> bb)) ++bb;
+    const bool keys_fit = 2 * bv + bb <= 64;
+    const int64_t run_cap = n / 8 > (1 << 16) ? n / 8 : (1 << 16);
+    int rc;
+    if (keys_fit) {
+        rc = besst_group_tuples(ctx, nullptr, n, bv, bb, nullptr, nullptr);
+        if (rc) return rc;
+        rc = besst_launch_runs_route_async(ctx, world, bb, run_cap);
+        if (rc) return rc;
+    }
+    const uint64_t* fishy_totals = nullptr;
+    rc = besst_launch_partition_fishy_async(ctx, world, out_fishy_device, &fishy_totals);
+    if (rc) return rc;
+    uint64_t* const h = ctx->host_scalars();
+    if (!h) { ctx->err = "pinned host scratch allocation failed"; return BESST_E_NOMEM; }
+    memset(h, 0, 64 * sizeof(uint64_t));
+    BESST_CUDA_TRY(ctx, cudaMemcpyAsync(h, ctx->counters.p, 8 * BESST_N_COUNTERS, cudaMemcpyDeviceToHost, ctx->stream));
+    if (keys_fit) {
+        BESST_CUDA_TRY(ctx, cudaMemcpyAsync(h + 16, ctx->run_state.p, 8, cudaMemcpyDeviceToHost, ctx->stream));                          // runs, overflow flags
+        BESST_CUDA_TRY(ctx, cudaMemcpyAsync(h + 17, ctx->run_state.as<uint32_t>() + 16, 4 * 32, cudaMemcpyDeviceToHost, ctx->stream));    // route counts
+    }
+    if (fishy_totals) BESST_CUDA_TRY(ctx, cudaMemcpyAsync(h + 33, fishy_totals, 8 * (size_t)world, cudaMemcpyDeviceToHost, ctx->stream));
+    BESST_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    const uint32_t* gs = reinterpret_cast<const uint32_t*>(h + 16);
+    const uint32_t* route = reinterpret_cast<const uint32_t*>(h + 17);
+    const int64_t R = gs[0];
+    const bool ok = keys_fit && gs[1] == 0 && R <= run_cap;
+    summary[0] = ok ? 1 : 0;
+    summary[1] = ok ? R : 0;
+    summary[2] = (int64_t)h[BESST_CNT_CALLS];
+    summary[3] = (int64_t)h[BESST_CNT_LAST_OBS1]; summary[4] = (int64_t)h[BESST_CNT_LAST_OBS2];
+    summary[5] = (int64_t)h[BESST_CNT_FIRST_OBS1]; summary[6] = (int64_t)h[BESST_CNT_FIRST_OBS2];
+    summary[7] = n;
+    for (int d = 0; d < world; ++d) {
+        link_counts[d] = ok ? route[d] : 0;
+        run_counts[d] = ok ? route[16 + d] : 0;
+        fishy_counts[d] = (int64_t)h[33 + d];
+    }
+    if (ok) { ctx->n_runs = R; ctx->run_block_bits = bb; ctx->have_runs = true; }
+    return BESST_OK;
+}
+
 extern "C" int besst_runs_route(besst_ctx* ctx, int32_t world, int64_t* link_counts, int64_t* run_counts) {
     if (!ctx || !ctx->have_runs) { if (ctx) ctx->err = "no grouped runs (besst_links_group)"; return BESST_E_STATE; }
     if (world < 1 || world > 16 || !link_counts || !run_counts) { ctx->err = "runs_route: bad arguments"; return BESST_E_INVALID; }

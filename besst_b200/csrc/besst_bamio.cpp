@@ -32,6 +32,7 @@ struct Block {
     uint64_t cdata;   // file offset of the deflate stream
     uint32_t clen;    // its length
     uint32_t usize;   // inflated size (ISIZE)
+    uint32_t crc;     // CRC32 of the inflated data (gzip trailer)
 };
 
 template <typename T>
@@ -70,6 +71,7 @@ struct besst_bam {
     Column<uint16_t> flag;
     Column<uint8_t> mapq;
     int64_t n = 0, n_head = 0;
+    int32_t stopped = 0;   // the window callback of besst_bam_stream asked to stop
     besst_bam_stats stats;
 };
 
@@ -102,6 +104,7 @@ bool scan_blocks(const unsigned char* f, uint64_t size, std::vector<Block>* out,
         b.cdata = o + 12 + xlen;
         b.clen = bsize - 12 - xlen - 8;
         b.usize = rd32(f + o + bsize - 4);
+        b.crc = rd32(f + o + bsize - 8);
         out->push_back(b);
         o += bsize;
     }
@@ -116,7 +119,9 @@ struct Inflater {
         ok = inflateInit2(&zs, -15) == Z_OK;
     }
     ~Inflater() { if (ok) inflateEnd(&zs); }
-    bool run(const unsigned char* src, uint32_t clen, unsigned char* dst, uint32_t usize) {
+    // check_crc: compare the gzip trailer's CRC32 with the inflated bytes (a damaged block with an intact ISIZE
+    // would otherwise decode into plausible garbage records)
+    bool run(const unsigned char* src, uint32_t clen, unsigned char* dst, uint32_t usize, uint32_t crc, bool check_crc) {
         if (usize == 0) return true;
         if (inflateReset(&zs) != Z_OK) return false;
         zs.next_in = const_cast<unsigned char*>(src);
@@ -124,7 +129,8 @@ struct Inflater {
         zs.next_out = dst;
         zs.avail_out = usize;
         const int rc = inflate(&zs, Z_FINISH);
-        return rc == Z_STREAM_END && zs.avail_out == 0;
+        if (!(rc == Z_STREAM_END && zs.avail_out == 0)) return false;
+        return !check_crc || (uint32_t)crc32(crc32(0L, Z_NULL, 0), dst, usize) == crc;
     }
 };
 
@@ -226,6 +232,8 @@ static besst_bam* read_impl(const char* path, int32_t n_threads, int64_t max_rec
     std::vector<Inflater> inflaters((size_t)n_threads);
     for (auto& z : inflaters) if (!z.ok) return fail("zlib inflateInit2 failed");
     bool header_done = false, stop = false;
+    const char* nocrc = getenv("BESST_BAMIO_NOCRC");
+    const bool check_crc = !(nocrc && nocrc[0] == '1');
     size_t next_block = 0;
     while (next_block < blocks.size() && !stop) {
         // ---- inflate one window of blocks behind the leftover bytes --------------------------------
@@ -247,7 +255,7 @@ static besst_bam* read_impl(const char* path, int32_t n_threads, int64_t max_rec
             for (;;) {
                 const size_t k = ticket.fetch_add(1);
                 if (k >= b1) break;
-                if (!inflaters[(size_t)t].run(f + blocks[k].cdata, blocks[k].clen, pend.data() + dst_off[k - b0], blocks[k].usize)) bad.store(1);
+                if (!inflaters[(size_t)t].run(f + blocks[k].cdata, blocks[k].clen, pend.data() + dst_off[k - b0], blocks[k].usize, blocks[k].crc, check_crc)) bad.store(1);
             }
         };
         {
@@ -256,7 +264,7 @@ static besst_bam* read_impl(const char* path, int32_t n_threads, int64_t max_rec
             inflate_worker(0);
             for (auto& x : th) x.join();
         }
-        if (bad.load()) return fail("inflate failed: corrupt BGZF block");
+        if (bad.load()) return fail("inflate failed: corrupt BGZF block (bad deflate stream or CRC32 mismatch)");
         B->stats.seconds_inflate += now() - t0;
         B->stats.uncompressed_bytes += (int64_t)usum;
 
@@ -419,9 +427,10 @@ static besst_bam* read_impl(const char* path, int32_t n_threads, int64_t max_rec
         if (window_fn) {   // streaming: hand the window over, then reuse the column space
             besst_bam_columns w;
             besst_bam_get_columns(B, &w);
-            if (window_fn(user, B, &w, base_total) != 0) return fail("stopped by the window callback");
+            const bool go_on = window_fn(user, B, &w, base_total) == 0;
             base_total += B->n;
             B->n = 0;
+            if (!go_on) { B->stopped = 1; stop = true; }   // the consumer has seen enough: not an error, the handle and its statistics are returned
         }
         // keep the unconsumed tail (a partial record) for the next window
         if (cur < pend.size()) memmove(pend.data(), pend.data() + cur, pend.size() - cur);
@@ -434,6 +443,8 @@ static besst_bam* read_impl(const char* path, int32_t n_threads, int64_t max_rec
     B->stats.seconds_total = now() - t_start;
     return B;
 }
+
+extern "C" int besst_bam_stopped(const besst_bam* b) { return b ? b->stopped : 0; }
 
 extern "C" besst_bam* besst_bam_read(const char* path, int32_t n_threads, int64_t max_records, int64_t head_records,
                                      char* err, int32_t err_len) {

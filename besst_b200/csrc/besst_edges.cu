@@ -1485,8 +1485,7 @@ int besst_launch_trsk_sd(besst_ctx* ctx, const besst_lib_params& p, const double
 // (a block with more than GB_DMAX edges, or more runs than n/8) -- use the radix bucket
 int besst_group_tuples(besst_ctx* ctx, const besst_link_tuple* d_tuples, int64_t n, int bv, int block_bits, int64_t* n_runs,
                        int* overflow) {
-    *n_runs = 0;
-    *overflow = 0;
+    if (n_runs) { *n_runs = 0; *overflow = 0; }
     const size_t nz = (size_t)(n > 0 ? n : 1);
     const int64_t n_gblocks = (n + GB_TILE - 1) / GB_TILE;
     const int64_t run_cap64 = std::max<int64_t>(n / 8, 1 << 16);
@@ -1500,9 +1499,9 @@ int besst_group_tuples(besst_ctx* ctx, const besst_link_tuple* d_tuples, int64_t
     BESST_CUDA_TRY(ctx, ctx->run_first.ensure(4 * (size_t)run_cap)); BESST_CUDA_TRY(ctx, ctx->run_off.ensure(4 * (size_t)run_cap));
     BESST_CUDA_TRY(ctx, ctx->run_src.ensure(4 * (size_t)run_cap)); BESST_CUDA_TRY(ctx, ctx->run_len.ensure(4 * (size_t)run_cap));
     BESST_CUDA_TRY(ctx, ctx->run_state.ensure(512));
-    if (n == 0) return BESST_OK;
     u32* gstate = ctx->run_state.as<u32>();
     BESST_CUDA_TRY(ctx, cudaMemsetAsync(gstate, 0, 64, ctx->stream));
+    if (n == 0) return BESST_OK;
     if (!ctx->attr_group_done) {   // per ctx (= per device): function attributes are set on the current device
         cudaFuncSetAttribute(k_group_blocks<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(GroupSmem));
         cudaFuncSetAttribute(k_group_blocks<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(GroupSmem));
@@ -1521,6 +1520,7 @@ int besst_group_tuples(besst_ctx* ctx, const besst_link_tuple* d_tuples, int64_t
                 ctx->tile_state.as<u64>(), ctx->n_rec_tiles, ctx->block_tile0.as<u32>());
     }
     BESST_CUDA_TRY(ctx, cudaGetLastError());
+    if (!n_runs) return BESST_OK;   // queued only: the caller reads run_state[0..1] together with its other sizes
     u32* const hs = reinterpret_cast<u32*>(ctx->host_scalars());
     if (!hs) { ctx->err = "pinned host scratch allocation failed"; return BESST_E_NOMEM; }
     BESST_CUDA_TRY(ctx, cudaMemcpyAsync(hs, gstate, 8, cudaMemcpyDeviceToHost, ctx->stream));
@@ -1537,13 +1537,14 @@ constexpr int RX_MAX_WORLD = 16;
 struct PackDst { void* obs[RX_MAX_WORLD]; besst_run_desc* desc[RX_MAX_WORLD]; };   // obs: int2 or (PACK16) u32 per link
 
 // state: [0..15] links per destination, [16..31] runs per destination
+// R_dev != nullptr: the number of runs is still on the device (run_state[0], capped at run_cap by the caller's check later)
 __global__ void __launch_bounds__(256) k_runs_route_count(const u64* __restrict__ run_key, const u32* __restrict__ run_cnt, long long R,
-                                                          int block_bits, int bv, int world, u32* state) {
+                                                          const u32* __restrict__ R_dev, long long run_cap, int block_bits, int bv, int world, u32* state) {
     __shared__ u32 s_l[RX_MAX_WORLD], s_r[RX_MAX_WORLD];
     if (threadIdx.x < RX_MAX_WORLD) { s_l[threadIdx.x] = 0; s_r[threadIdx.x] = 0; }
     __syncthreads();
-    const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (r < R) {
+    if (R_dev) { R = (long long)*R_dev; if (R > run_cap) R = run_cap; }
+    for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < R; r += (long long)gridDim.x * blockDim.x) {
         const u64 key = run_key[r] >> block_bits;
         const u32 d = besst_edge_dest((u32)(key >> bv), (u32)(key & ((1ull << bv) - 1ull)), world);
         atomicAdd(&s_l[d], run_cnt[r]);
@@ -1611,6 +1612,18 @@ __global__ void __launch_bounds__(256) k_runs_import(const besst_run_desc* __res
     run_first[r] = B.first_base[src] + ds.first;
 }
 
+// the route counts of runs whose number is still on the device (queued behind k_group_blocks, no host read)
+int besst_launch_runs_route_async(besst_ctx* ctx, int world, int block_bits, int64_t run_cap) {
+    const int bv = bits_for((uint64_t)(2 * ctx->n_scaffolds > 0 ? 2 * ctx->n_scaffolds - 1 : 1));
+    u32* state = ctx->run_state.as<u32>() + 16;   // [16..47]: route counts, [48..79]: pack cursors
+    BESST_CUDA_TRY(ctx, cudaMemsetAsync(state, 0, 4 * 4 * RX_MAX_WORLD, ctx->stream));
+    { KTimer kt(ctx, BESST_K_PARTITION);
+      k_runs_route_count<<<(unsigned)(ctx->sm_count * 8), 256, 0, ctx->stream>>>(ctx->run_key[0].as<u64>(), ctx->run_cnt.as<u32>(), 0,
+                                                                                 ctx->run_state.as<u32>(), run_cap, block_bits, bv, world, state); }
+    BESST_CUDA_TRY(ctx, cudaGetLastError());
+    return BESST_OK;
+}
+
 int besst_launch_runs_route(besst_ctx* ctx, int world, int64_t* link_counts, int64_t* run_counts) {
     for (int d = 0; d < world; ++d) link_counts[d] = run_counts[d] = 0;
     const int64_t R = ctx->n_runs;
@@ -1619,8 +1632,10 @@ int besst_launch_runs_route(besst_ctx* ctx, int world, int64_t* link_counts, int
     u32* state = ctx->run_state.as<u32>() + 16;   // [16..47]: route counts, [48..79]: pack cursors
     BESST_CUDA_TRY(ctx, cudaMemsetAsync(state, 0, 4 * 4 * RX_MAX_WORLD, ctx->stream));
     { KTimer kt(ctx, BESST_K_PARTITION);
-      k_runs_route_count<<<(unsigned)((R + 255) / 256), 256, 0, ctx->stream>>>(ctx->run_key[0].as<u64>(), ctx->run_cnt.as<u32>(), R,
-                                                                               ctx->run_block_bits, bv, world, state); }
+      long long rgrid = (R + 255) / 256;
+      if (rgrid > (long long)ctx->sm_count * 8) rgrid = (long long)ctx->sm_count * 8;
+      k_runs_route_count<<<(unsigned)rgrid, 256, 0, ctx->stream>>>(ctx->run_key[0].as<u64>(), ctx->run_cnt.as<u32>(), R, nullptr, R,
+                                                                   ctx->run_block_bits, bv, world, state); }
     BESST_CUDA_TRY(ctx, cudaGetLastError());
     u32 h[2 * RX_MAX_WORLD];
     BESST_CUDA_TRY(ctx, cudaMemcpyAsync(h, state, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));

@@ -195,6 +195,8 @@ static inline int besst_obs_bytes(const besst_lib_params& p) {
 int besst_launch_graph_from_runs(besst_ctx* ctx, const besst_lib_params& p, int64_t n_links, const BesstRunInput& runs,
                                  const uint64_t* d_fishy, int64_t n_fishy);
 int besst_launch_runs_route(besst_ctx* ctx, int world, int64_t* link_counts, int64_t* run_counts);
+int besst_launch_runs_route_async(besst_ctx* ctx, int world, int block_bits, int64_t run_cap);
+int besst_launch_partition_fishy_async(besst_ctx* ctx, int world, uint64_t* out_fishy, const uint64_t** totals_device);
 int besst_launch_runs_pack(besst_ctx* ctx, int world, int32_t* out_obs, besst_run_desc* out_desc, int32_t* const* obs_ptrs,
                            besst_run_desc* const* desc_ptrs);
 int besst_launch_runs_import(besst_ctx* ctx, const besst_run_desc* desc, int64_t n_runs, int world, int block_bits,

@@ -886,7 +886,7 @@ __global__ void __launch_bounds__(PT_THREADS) k_partition_scatter(const void* __
 
 template <bool TUPLES>
 int partition_impl(besst_ctx* ctx, const void* in, int64_t n, int world, void* out, u32* ord_out, int64_t* counts_host) {
-    for (int d = 0; d < world; ++d) counts_host[d] = 0;
+    if (counts_host) for (int d = 0; d < world; ++d) counts_host[d] = 0;
     if (n == 0) return BESST_OK;
     const int n_tiles = (int)((n + PT_TILE - 1) / PT_TILE);
     BESST_CUDA_TRY(ctx, ctx->part_state.ensure(4 * (size_t)n_tiles * world + 16 * PT_MAX_WORLD + 64));
@@ -897,6 +897,7 @@ int partition_impl(besst_ctx* ctx, const void* in, int64_t n, int world, void* o
     { KTimer kt(ctx, BESST_K_PARTITION); k_partition_scan<<<1, 1024, 0, ctx->stream>>>(counts, n_tiles, world, starts, totals); }
     { KTimer kt(ctx, BESST_K_PARTITION); k_partition_scatter<TUPLES><<<n_tiles, PT_THREADS, 0, ctx->stream>>>(in, n, world, counts, n_tiles, starts, out, ord_out); }
     BESST_CUDA_TRY(ctx, cudaGetLastError());
+    if (!counts_host) return BESST_OK;   // queued only: the totals stay in part_state[PT_MAX_WORLD ..] for the caller's one read
     u64 h[PT_MAX_WORLD];
     BESST_CUDA_TRY(ctx, cudaMemcpyAsync(h, totals, 8 * world, cudaMemcpyDeviceToHost, ctx->stream));
     BESST_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
@@ -905,6 +906,16 @@ int partition_impl(besst_ctx* ctx, const void* in, int64_t n, int world, void* o
 }
 
 }  // namespace
+
+// the fishy keys only, queued without a host read; *totals_device: u64[world] bucket sizes (valid once the stream gets there)
+int besst_launch_partition_fishy_async(besst_ctx* ctx, int world, uint64_t* out_fishy, const uint64_t** totals_device) {
+    *totals_device = nullptr;
+    if (ctx->n_fishy_keys == 0) return BESST_OK;
+    const int rc = partition_impl<false>(ctx, ctx->fishy_keys.p, ctx->n_fishy_keys, world, out_fishy, nullptr, nullptr);
+    if (rc) return rc;
+    *totals_device = reinterpret_cast<const uint64_t*>(ctx->part_state.as<u64>() + PT_MAX_WORLD);
+    return BESST_OK;
+}
 
 int besst_launch_partition(besst_ctx* ctx, int world, besst_link_tuple* out_tuples, uint32_t* out_ordinals,
                            uint64_t* out_fishy, int64_t* tuple_counts, int64_t* fishy_counts) {

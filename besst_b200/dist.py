@@ -141,6 +141,15 @@ class CudaBackend(object):
         _, fc = self.engine.links_partition(world, None, send_f.data_ptr(), None)
         return send_f[:nf], fc
 
+    def prepare_exchange(self, world, n_local):
+        """call_summary + group + route + partition_fishy in one engine call with ONE host read.
+        -> (calls, last, first, n_runs or None, link_counts, run_counts, send_f, fishy_counts)"""
+        torch = self.torch
+        _, nf = self.engine.fishy_device()
+        send_f = self._buf("send_f", nf, torch.int64)
+        s, lc, rc, fc = self.engine.exchange_prepare(world, send_f.data_ptr() if nf else None)
+        return (int(s[2]), (int(s[3]), int(s[4])), (int(s[5]), int(s[6])), int(s[1]) if s[0] else None, lc, rc, send_f[:nf], fc)
+
     def obs_words(self, params):
         """int32 words per exchanged link: 1 (two 16-bit observations) or 2"""
         return self.engine.runs_obs_bytes(params) // 4
@@ -337,13 +346,18 @@ class DistributedGraphBuild(object):
             if need_extract:
                 n_local = self.b.extract(p, rec)
                 self._mark("extract")
-                calls, last, first = self.b.call_summary()
-                n_runs = self.b.group()
-                self._mark("group")
-                ok = n_runs is not None
-                lc, rc = self.b.route(world) if ok else (np.zeros(world, np.int64), np.zeros(world, np.int64))
-                send_f, fc = self.b.partition_fishy(world)
-                self._mark("route+fishy")
+                if hasattr(self.b, "prepare_exchange"):   # one engine call, one host read
+                    calls, last, first, n_runs, lc, rc, send_f, fc = self.b.prepare_exchange(world, n_local)
+                    ok = n_runs is not None
+                    self._mark("group+route+fishy")
+                else:
+                    calls, last, first = self.b.call_summary()
+                    n_runs = self.b.group()
+                    self._mark("group")
+                    ok = n_runs is not None
+                    lc, rc = self.b.route(world) if ok else (np.zeros(world, np.int64), np.zeros(world, np.int64))
+                    send_f, fc = self.b.partition_fishy(world)
+                    self._mark("route+fishy")
             mine = self.b.counts_tensor([1 if ok else 0, n_local, 1 if calls > 0 else 0, last[0], last[1], first[0], first[1]]
                                         + lc.tolist() + rc.tolist() + fc.tolist())
             # ONE collective and ONE device->host read for the whole W x (7 + 3W) matrix

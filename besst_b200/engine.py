@@ -160,6 +160,14 @@ class CudaEngine(object):
         rc = self._check(self._L.besst_links_group(self._ctx, C.byref(n)), "besst_links_group")
         return None if rc == 1 else n.value
 
+    def exchange_prepare(self, world, out_fishy_ptr):
+        """group + route counts + fishy partition with one host read.  -> (summary int64[8], link_counts, run_counts, fishy_counts)"""
+        summary = np.zeros(8, dtype=np.int64)
+        lc, rc_, fc = (np.zeros(world, dtype=np.int64) for _ in range(3))
+        self._check(self._L.besst_exchange_prepare(self._ctx, int(world), out_fishy_ptr, summary.ctypes.data, lc.ctypes.data,
+                                                   rc_.ctypes.data, fc.ctypes.data), "besst_exchange_prepare")
+        return summary, lc, rc_, fc
+
     def runs_route(self, world):
         lc = np.zeros(world, dtype=np.int64)
         rc = np.zeros(world, dtype=np.int64)

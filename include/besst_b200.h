@@ -277,6 +277,13 @@ typedef struct besst_run_desc {
     uint32_t block;   /* block of the source's stream it comes from: BAM order among the runs of one edge */
 } besst_run_desc;
 int besst_links_group(besst_ctx* ctx, int64_t* n_runs);
+/* besst_links_group + besst_runs_route + the fishy-key half of besst_links_partition queued back to back with ONE host
+ * read for all the sizes a rank contributes to the exchange's count matrix (a host round trip costs as much as the small
+ * kernels in between).  summary[8] = { runs usable (0: the stream has no local order, take the tuple path), runs,
+ * CreateEdge calls, last obs1, last obs2, first obs1, first obs2, accepted links }; *_counts[world] per destination;
+ * out_fishy_device (n_fishy keys, may be NULL when there are none) receives the keys bucketed by destination. */
+int besst_exchange_prepare(besst_ctx* ctx, int32_t world, uint64_t* out_fishy_device, int64_t* summary,
+                           int64_t* link_counts, int64_t* run_counts, int64_t* fishy_counts);
 /* bytes per link of the exchanged observations: 4 (obs_u | obs_v << 16) when 0 < ins_size_threshold <= 65535
  * -- every accepted observation is below the threshold, CreateGraph.py:840 -- else 8 (two int32) */
 int besst_runs_obs_bytes(const besst_lib_params* params);

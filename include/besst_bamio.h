@@ -61,8 +61,10 @@ besst_bam* besst_bam_read(const char* path, int32_t n_threads, int64_t max_recor
  * consumer can move window k on (copy it to pinned staging and start its upload) before window k+1 is inflated.
  * window->n records starting at ordinal first_record; the pointers are valid only during the call (the call runs
  * on the caller's thread, between windows); b gives access to the header (besst_bam_n_refs ...) from the first
- * call on.  A non-zero return stops the pass (NULL is returned).  The returned handle holds the header, the
- * statistics and rlen/alen of the first head_records records, but no record columns. */
+ * call on.  A non-zero return stops the pass: not an error, the handle is returned as usual and
+ * besst_bam_stopped() says so (NULL always means a real failure, with the message in err).  The returned handle
+ * holds the header, the statistics and rlen/alen of the first head_records records, but no record columns.
+ * Every BGZF block's CRC32 is checked against the inflated bytes (BESST_BAMIO_NOCRC=1 skips the check). */
 typedef int (*besst_bam_window_fn)(void* user, const besst_bam* b, const besst_bam_columns* window, int64_t first_record);
 besst_bam* besst_bam_stream(const char* path, int32_t n_threads, int64_t max_records, int64_t head_records,
                             besst_bam_window_fn window_fn, void* user, char* err, int32_t err_len);
@@ -72,6 +74,7 @@ const char* besst_bam_ref_name(const besst_bam* b, int64_t i);
 int64_t besst_bam_ref_length(const besst_bam* b, int64_t i);
 int besst_bam_get_columns(const besst_bam* b, besst_bam_columns* out);
 int besst_bam_get_stats(const besst_bam* b, besst_bam_stats* out);
+int besst_bam_stopped(const besst_bam* b);   /* 1: the window callback stopped the pass early */
 void besst_bam_close(besst_bam* b);
 
 #ifdef __cplusplus

@@ -190,7 +190,40 @@ def test_streamed_windows_concatenate_to_the_full_read(tmp_path, monkeypatch):
     assert all(r == (tuple(full.references), tuple(full.lengths)) for r in seen_refs)
     for f in ("tid", "mtid", "pos", "mpos", "tlen", "qlen", "flag", "mapq"):
         assert np.array_equal(np.concatenate([p[f] for p in parts]), getattr(full, f)), f
-    # a callback can stop the pass; an exception inside it surfaces in Python
-    assert bamio.stream_bam_native(path, lambda *a: True, threads=2) is None
+    assert stats["stopped"] is False
+    # a callback can stop the pass: not an error, the statistics come back with the flag set
+    early = bamio.stream_bam_native(path, lambda *a: True, threads=2)
+    assert early["stopped"] is True and 0 < early["records"] < len(full) and early["blocks"] == stats["blocks"]
     with pytest.raises(ZeroDivisionError):
         bamio.stream_bam_native(path, lambda *a: 1 // 0, threads=2)
+
+
+def test_corrupted_block_is_caught_by_its_crc(tmp_path, monkeypatch):
+    """A flipped byte inside a STORED deflate block leaves the stream and ISIZE valid: only the CRC32 of the
+    gzip trailer can tell.  The reader checks it (BESST_BAMIO_NOCRC=1 turns the check off)."""
+    rng = np.random.default_rng(5)
+    refs = [("c%d" % i, 4000 + i) for i in range(5)]
+    raw_path = str(tmp_path / "ok.bam")
+    write_bam(raw_path, refs, _random_records(rng, 800, len(refs)), block_bytes=4000)
+    data = bytearray(open(raw_path, "rb").read())
+    # re-write the second block as a stored (uncompressed) deflate block and damage one payload byte
+    def blocks(buf):
+        o = 0
+        while o < len(buf):
+            bsize = struct.unpack_from("<H", buf, o + 16)[0] + 1
+            yield o, bsize
+            o += bsize
+    offs = list(blocks(data))
+    o, bsize = offs[1]
+    payload = zlib.decompress(bytes(data[o + 18:o + bsize - 8]), -15)
+    stored = b"\x01" + struct.pack("<HH", len(payload), len(payload) ^ 0xffff) + payload
+    damaged = bytearray(stored)
+    damaged[5 + len(payload) // 2 + 3] ^= 0x01   # inside a record's name/sequence bytes: lengths stay consistent
+    new_block = (b"\x1f\x8b\x08\x04" + b"\0\0\0\0" + b"\0\xff" + struct.pack("<H", 6) + b"BC" + struct.pack("<HH", 2, 12 + 6 + len(damaged) + 8 - 1)
+                 + bytes(damaged) + struct.pack("<II", zlib.crc32(payload) & 0xffffffff, len(payload)))
+    bad_path = str(tmp_path / "bad.bam")
+    open(bad_path, "wb").write(bytes(data[:o]) + new_block + bytes(data[o + bsize:]))
+    with pytest.raises(IOError, match="CRC32"):
+        bamio.read_bam_native(bad_path, threads=2)
+    monkeypatch.setenv("BESST_BAMIO_NOCRC", "1")
+    assert len(bamio.read_bam_native(bad_path, threads=2)) == 800   # accepted silently without the check
