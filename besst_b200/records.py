@@ -92,9 +92,25 @@ class RecordBatch:
             alen=np.zeros(0, np.int32) if self.alen is None else self.alen[:1000],
             **self.device_arrays())
 
+    def save_compact(self, path):
+        """Smaller fixture files for coordinate-sorted input: narrow dtypes, positions as differences."""
+        np.savez_compressed(
+            path, compact=np.array([1]), references=np.array(list(self.references)), lengths=np.asarray(self.lengths, dtype=np.int64),
+            rlen=np.zeros(0, np.int32) if self.rlen is None else self.rlen[:1000],
+            alen=np.zeros(0, np.int32) if self.alen is None else self.alen[:1000],
+            tid=self.tid.astype(np.int32), mtid=self.mtid.astype(np.int32), dpos=np.diff(self.pos, prepend=np.int32(0)).astype(np.int32),
+            dmpos=(self.mpos - self.pos).astype(np.int32), tlen=self.tlen, qlen=self.qlen, flag=self.flag, mapq=self.mapq)
+
     @staticmethod
     def load(path):
         z = np.load(path, allow_pickle=False)
+        if "compact" in z.files:
+            pos = np.cumsum(z["dpos"].astype(np.int64)).astype(np.int32)
+            kw = dict(tid=z["tid"], mtid=z["mtid"], pos=pos, mpos=(pos + z["dmpos"]).astype(np.int32), tlen=z["tlen"], qlen=z["qlen"],
+                      flag=z["flag"], mapq=z["mapq"])
+            rlen = z["rlen"] if z["rlen"].size else None
+            alen = z["alen"] if z["alen"].size else None
+            return RecordBatch(references=[str(x) for x in z["references"]], lengths=[int(x) for x in z["lengths"]], rlen=rlen, alen=alen, **kw)
         kw = {name: z[name] for name, _ in _DEVICE_FIELDS}
         rlen = z["rlen"] if z["rlen"].size else None
         alen = z["alen"] if z["alen"].size else None

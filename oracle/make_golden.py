@@ -43,6 +43,9 @@ CASES = {
     "testset1_travis": ("testset1", dict(orientation="fr", mean=4000, stddev=500, minsize=3000, threshold=6000), None, True),
     "testset1_travis_no_score": ("testset1", dict(orientation="fr", mean=4000, stddev=500, minsize=3000, threshold=6000, no_score=True), None, True),
     "testset1_auto": ("testset1", dict(orientation="fr"), None, True),
+    # BASELINE config 1 in full: all 1,999,958 records of testdata/testset1/mapped.bam with the Travis command lines
+    "testset1_full_travis": ("testset1_full", dict(orientation="fr", mean=4000, stddev=500, minsize=3000, threshold=6000), None, True),
+    "testset1_full_travis_no_score": ("testset1_full", dict(orientation="fr", mean=4000, stddev=500, minsize=3000, threshold=6000, no_score=True), None, True),
     "testset2_auto": ("testset2", dict(orientation="fr"), None, True),
     "testset2_given": ("testset2", dict(orientation="fr", mean=2800, stddev=350, minsize=4600, threshold=4500), None, True),
     "small_pe_auto": ("small_pe", dict(orientation="fr"), None, True),
@@ -58,6 +61,9 @@ CASES = {
 
 
 def load_input(name):
+    if name == "testset1_full":
+        from besst_b200.records import RecordBatch
+        return RecordBatch.load(os.path.join(GOLDEN, "testset1_full.npz"))
     if name in ("testset1", "testset2"):
         path = os.path.join(GOLDEN, name + "_head.npz")
         from besst_b200.records import RecordBatch
@@ -69,6 +75,7 @@ def make_testset1_fixture():
     bam = os.path.join(ref_harness.REFERENCE_ROOT, "testdata", "testset1", "mapped.bam")
     batch = bamio.read_bam(bam, max_records=TESTSET1_RECORDS)
     batch.save(os.path.join(GOLDEN, "testset1_head.npz"))
+    bamio.read_bam_native(bam).save_compact(os.path.join(GOLDEN, "testset1_full.npz"))   # every record (native reader == read_bam, tests/test_bamio.py)
     bam2 = os.path.join(ref_harness.REFERENCE_ROOT, "testdata", "testset2", "mapped.bam")
     bamio.read_bam(bam2, max_records=TESTSET2_RECORDS).save(os.path.join(GOLDEN, "testset2_head.npz"))
     return batch

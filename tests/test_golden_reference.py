@@ -40,7 +40,9 @@ _inputs = {}
 
 def load_input(name):
     if name not in _inputs:
-        if name in ("testset1", "testset2"):
+        if name == "testset1_full":
+            _inputs[name] = RecordBatch.load(os.path.join(GOLDEN, "testset1_full.npz"))
+        elif name in ("testset1", "testset2"):
             _inputs[name] = RecordBatch.load(os.path.join(GOLDEN, name + "_head.npz"))
         else:
             _inputs[name] = synth.make_config(name).to_batch()
