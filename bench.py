@@ -148,7 +148,7 @@ def result_bytes(res, abi):
 class Library(object):
     """One library of the workload on this rank: device-resident record columns + its contig table slot."""
 
-    def __init__(self, index, spec, n_contigs, world, rank, dev, synth, abi, first_library_rows, legacy_single):
+    def __init__(self, index, spec, n_contigs, world, rank, dev, synth, abi, first_library_rows, legacy_single, packed):
         import torch
         orientation, mu, sigma, cont, n_pairs = spec
         self.index, self.orientation, self.mu, self.sigma, self.cont = index, orientation, mu, sigma, cont
@@ -158,8 +158,14 @@ class Library(object):
         else:
             lib = synth.make_library_slice(n_contigs, n_pairs, orientation, mu, sigma, cont, synth.SEED0 + 2, rank, world, device=dev,
                                            read_seed=index)
-        self.cols = {k: v for k, v in lib.cols.items() if k != "tlen"}
         self.tlen = lib.cols["tlen"] if index == 0 and world == 1 else None   # only the libmetrics leg reads it
+        self.plain = {k: lib.cols[k] for k in ("flag", "mapq", "qlen")} if (self.tlen is not None or not packed) else None
+        if packed:   # flag | mapq << 12 | qlen << 20: the one column the ingest library writes for the graph build (20 B/record)
+            pk = (lib.cols["flag"].to(torch.int32) & 0xfff) | (lib.cols["mapq"].to(torch.int32) << 12) | (lib.cols["qlen"] << 20)
+            self.cols = {"tid": lib.cols["tid"], "mtid": lib.cols["mtid"], "pos": lib.cols["pos"], "mpos": lib.cols["mpos"], "packed": pk}
+        else:
+            self.cols = {k: v for k, v in lib.cols.items() if k != "tlen"}
+        self.packed = packed
         self.n_rec = lib.n_records
         self.lengths = lib.lengths.numpy()
         threshold = mu + 4 * sigma
@@ -171,6 +177,8 @@ class Library(object):
             self.state = "later library (runs of 1-3 contigs joined into scaffolds, 1/17 removed)"
         self.params = library_params(abi, orientation, mu, sigma)
         ptrs = {k: v.data_ptr() for k, v in self.cols.items()}
+        if self.plain is not None:
+            ptrs.update({k: v.data_ptr() for k, v in self.plain.items()})
         ptrs["tlen"] = self.tlen.data_ptr() if self.tlen is not None else 0
         ptrs["n"] = self.n_rec
         self.rec_dev = abi.make_records(ptrs, on_device=True)
@@ -222,6 +230,8 @@ def pe_level_leg(eng, L, host_cols, lazy):
     from besst_b200.records import BatchFile, RecordBatch
     arrs = {k: v[:L.n_rec].numpy() for k, v in host_cols.items()}
     arrs["flag"] = arrs["flag"].view(np.uint16)
+    if "packed" in arrs:
+        arrs["packed"] = arrs["packed"].view(np.uint32)
     names = ["c%d" % i for i in range(L.lengths.shape[0])]
     batch = RecordBatch(references=names, lengths=[int(x) for x in L.lengths.tolist()],
                         rlen=np.full(min(L.n_rec, 1000), 100, np.int32), alen=np.full(min(L.n_rec, 1000), 100, np.int32), **arrs)
@@ -267,7 +277,9 @@ def run_ours(args):
     legacy_single = world == 1 and len(specs) == 1
 
     t_gen = time.time()
-    libs = [Library(i, s, n_contigs, world, rank, dev, synth, abi, first_library_rows, legacy_single) for i, s in enumerate(specs)]
+    packed = args.records == "packed"
+    record_bytes = 20 if packed else RECORD_BYTES
+    libs = [Library(i, s, n_contigs, world, rank, dev, synth, abi, first_library_rows, legacy_single, packed) for i, s in enumerate(specs)]
     t_gen = time.time() - t_gen
     n_rec = sum(L.n_rec for L in libs)
     pairs_this_rank = n_rec / 2.0
@@ -372,7 +384,7 @@ def run_ours(args):
     n_launch = {k: len(v) / args.steps for k, v in prof.items()}
     n_tiles = sum((L.n_rec + 127) // 128 for L in libs)
     alg_bytes_step = {   # algorithmic bytes per STEP of each kernel family on this rank (DESIGN.md "Kernels")
-        "k_extract_links": RECORD_BYTES * n_rec + TUPLE_BYTES * (n_links if world == 1 else 0) + 48 * n_tiles,
+        "k_extract_links": record_bytes * n_rec + TUPLE_BYTES * (n_links if world == 1 else 0) + 48 * n_tiles,
         "k_compact_tuples": 2 * TUPLE_BYTES * n_links + 8 * n_tiles,
         "k_radix_sweep": (8 + 8) * n_links,       # packed sort word (key | BAM index): 8 B in, 8 B out per pass
         "k_radix_hist": 8 * n_links,
@@ -469,7 +481,7 @@ def run_ours(args):
             hp = {k: v.data_ptr() for k, v in host.items()}
             hp["tlen"] = 0
             hp["n"] = L.n_rec
-            rec_host = abi.make_records(hp, on_device=True)
+            rec_host = abi.make_records(hp, on_device=True)   # HOST pointers: the flag is flipped below
             rec_host.on_device = 0
 
             def e2e_step():   # host columns in (sliced H2D overlapped with K1 inside the library), this rank's CSR out
@@ -483,13 +495,19 @@ def run_ours(args):
                     res = e2e_step()
                 barrier()
                 e2e_time += time.perf_counter() - t0
-                h2d += RECORD_BYTES * L.n_rec
+                h2d += record_bytes * L.n_rec
                 d2h += result_bytes(res, abi)
             # ---- CPU: the C oracle over the WHOLE library (every rank its own BAM-order slice), then parity ----
             if not args.no_cpu:
                 from besst_b200.records import RecordBatch
-                arrs = {k: host[k][:L.n_rec].numpy() for k in host}
-                arrs["flag"] = arrs["flag"].view(np.uint16)
+                arrs = {k: host[k][:L.n_rec].numpy() for k in host if k != "packed"}
+                if packed:   # the oracle reads the three plain columns
+                    pk = host["packed"][:L.n_rec].numpy().view(np.uint32)
+                    arrs["flag"] = (pk & np.uint32(0xfff)).astype(np.uint16)
+                    arrs["mapq"] = ((pk >> np.uint32(12)) & np.uint32(0xff)).astype(np.uint8)
+                    arrs["qlen"] = (pk >> np.uint32(20)).astype(np.int32)
+                else:
+                    arrs["flag"] = arrs["flag"].view(np.uint16)
                 batch = RecordBatch(tlen=np.zeros(L.n_rec, np.int32), **arrs)
                 if world == 1:
                     t0 = time.perf_counter()
@@ -519,9 +537,12 @@ def run_ours(args):
             # ---- the reference-facing entry points end to end (N=1, first library): get_metrics + PE ----------------
             if world == 1 and L.index == 0 and L.tlen is not None and args.pe_level:
                 try:
-                    hc = dict(host)
-                    hc["tlen"] = torch.empty((L.n_rec,), dtype=torch.int32, pin_memory=True)
-                    hc["tlen"].copy_(L.tlen)
+                    hc = {k: v for k, v in host.items() if k != "packed"}
+                    for k, v in dict(L.plain, tlen=L.tlen).items():
+                        hc[k] = torch.empty((L.n_rec,), dtype=v.dtype, pin_memory=True)
+                        hc[k].copy_(v)
+                    if packed:
+                        hc["packed"] = host["packed"]
                     torch.cuda.synchronize()
                     pe_level = {"lazy": pe_level_leg(eng, L, hc, True)}
                     if L.n_rec <= 60_000_000:   # python lists of every observation: minutes and tens of GB beyond that
@@ -574,7 +595,9 @@ def run_ours(args):
                        "contigs": n_contigs, "pairs_per_step": int(total_pairs), "records_per_step": n_rec_total,
                        "libraries": [L.describe() for L in libs],
                        "accepted_links": g_links, "edges": g_edges, "scored_links": g_ll,
-                       "l2_policy": "inputs (%.1f GB per rank) larger than the 126 MB L2" % (RECORD_BYTES * n_rec / 1e9),
+                       "record_format": ("packed: tid, mtid, pos, mpos int32 + one uint32 flag|mapq<<12|qlen<<20 = 20 B/record (besst_records.packed, "
+                                         "written by the ingest library)") if packed else "plain: tid, mtid, pos, mpos, qlen int32 + flag u16 + mapq u8 = 23 B/record",
+                       "l2_policy": "inputs (%.1f GB per rank) larger than the 126 MB L2" % (record_bytes * n_rec / 1e9),
                        "parallelism": ("1 process per GPU; every library ONE global BAM range-partitioned over the ranks; runs of links "
                                        "routed by edge hash and stored into the destination GPU's memory by the pack kernel (NVLink peer "
                                        "stores), one all_gather of sizes, one all_reduce of coverage+counters") if world > 1 else "single GPU"},
@@ -650,6 +673,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=None, choices=sorted(WORKLOADS),
                     help="default: config3 at 1 and 2 GPUs, config4 at 4, config5 at 8 (BASELINE.json configs)")
+    ap.add_argument("--records", default="packed", choices=["packed", "plain"],
+                    help="record layout handed to the graph build: packed = 20 B/record (default), plain = the 23 B/record columns of round 1")
     ap.add_argument("--scale", type=float, default=1.0, help="debug: shrink the workload")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline / parity leg")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (profiler runs only)")

@@ -35,7 +35,17 @@ LINK_TUPLE_DTYPE = np.dtype([("u", "<u4"), ("v", "<u4"), ("obs_u", "<i4"), ("obs
 class Records(C.Structure):
     _fields_ = [("n", C.c_int64), ("tid", C.c_void_p), ("mtid", C.c_void_p), ("pos", C.c_void_p),
                 ("mpos", C.c_void_p), ("tlen", C.c_void_p), ("qlen", C.c_void_p), ("flag", C.c_void_p),
-                ("mapq", C.c_void_p), ("on_device", C.c_int32), ("reserved", C.c_int32)]
+                ("mapq", C.c_void_p), ("on_device", C.c_int32), ("reserved", C.c_int32), ("packed", C.c_void_p)]
+
+
+def pack_record_columns(flag, mapq, qlen):
+    """flag | mapq << 12 | qlen << 20 (include/besst_b200.h BESST_PACK_RECORD): the one column the graph build reads
+    instead of the three.  None when a value does not fit (flag >= 4096 or qlen >= 4096)."""
+    flag = np.asarray(flag).astype(np.uint32)
+    qlen = np.asarray(qlen)
+    if flag.size and (int(flag.max()) >= 4096 or int(qlen.max()) >= 4096 or int(qlen.min()) < 0):
+        return None
+    return flag | (np.asarray(mapq).astype(np.uint32) << np.uint32(12)) | (qlen.astype(np.uint32) << np.uint32(20))
 
 
 class LibParams(C.Structure):
@@ -140,7 +150,8 @@ def make_records(batch_or_arrays, on_device=False, keepalive=None):
     if on_device:
         r.n = int(batch_or_arrays["n"])
         for name in ("tid", "mtid", "pos", "mpos", "tlen", "qlen", "flag", "mapq"):
-            setattr(r, name, int(batch_or_arrays[name]))
+            setattr(r, name, int(batch_or_arrays.get(name) or 0) or None)
+        r.packed = int(batch_or_arrays.get("packed") or 0) or None
         r.on_device = 1
         return r
     arrs = batch_or_arrays.device_arrays() if hasattr(batch_or_arrays, "device_arrays") else batch_or_arrays
@@ -151,6 +162,12 @@ def make_records(batch_or_arrays, on_device=False, keepalive=None):
         setattr(r, name, a.ctypes.data)
         if keepalive is not None:
             keepalive.append(a)
+    packed = getattr(batch_or_arrays, "packed", None) if not isinstance(batch_or_arrays, dict) else batch_or_arrays.get("packed")
+    if packed is not None:
+        assert packed.flags["C_CONTIGUOUS"] and packed.dtype == np.uint32 and packed.shape[0] == r.n
+        r.packed = packed.ctypes.data
+        if keepalive is not None:
+            keepalive.append(packed)
     r.on_device = 0
     return r
 

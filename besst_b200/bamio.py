@@ -30,7 +30,7 @@ _bamio = None
 
 class _Columns(C.Structure):
     _fields_ = [("n", C.c_int64)] + [(k, C.c_void_p) for k in ("tid", "mtid", "pos", "mpos", "tlen", "qlen", "flag", "mapq",
-                                                               "rlen", "alen")] + [("n_head", C.c_int64)]
+                                                               "rlen", "alen")] + [("n_head", C.c_int64), ("packed", C.c_void_p)]
 
 
 class BamStats(C.Structure):
@@ -115,7 +115,7 @@ def read_bam_native(path, threads=0, max_records=None, head_records=1000):
     batch = RecordBatch(tid=view(cols.tid, n, np.int32), mtid=view(cols.mtid, n, np.int32), pos=view(cols.pos, n, np.int32),
                         mpos=view(cols.mpos, n, np.int32), tlen=view(cols.tlen, n, np.int32), qlen=view(cols.qlen, n, np.int32),
                         flag=view(cols.flag, n, np.uint16), mapq=view(cols.mapq, n, np.uint8), references=references,
-                        lengths=lengths, rlen=rlen, alen=alen)
+                        lengths=lengths, rlen=rlen, alen=alen, packed=view(cols.packed, n, np.uint32) if cols.packed else None)
     st = BamStats()
     L.besst_bam_get_stats(ptr, C.byref(st))
     batch.stats = {k: getattr(st, k) for k, _ in BamStats._fields_}

@@ -47,7 +47,7 @@ extern "C" void besst_destroy(besst_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    DBuf* bufs[] = {&ctx->rows, &ctx->rows_packed, &ctx->scratch_tuples, &ctx->block_tile0, &ctx->tile_aggs, &ctx->part_state, &ctx->scaf_len, &ctx->rec_flag, &ctx->rec_mapq, &ctx->tuples, &ctx->fishy_keys, &ctx->aligned,
+    DBuf* bufs[] = {&ctx->rows, &ctx->rows_packed, &ctx->scratch_tuples, &ctx->block_tile0, &ctx->tile_aggs, &ctx->part_state, &ctx->scaf_len, &ctx->rec_flag, &ctx->rec_mapq, &ctx->rec_packed, &ctx->tuples, &ctx->fishy_keys, &ctx->aligned,
                     &ctx->counters, &ctx->tile_state, &ctx->misc, &ctx->key_a, &ctx->key_b, &ctx->idx_a, &ctx->idx_b, &ctx->hist,
                     &ctx->sort_state, &ctx->fishy_sorted, &ctx->fishy_tmp, &ctx->heads, &ctx->block_sums, &ctx->e_u, &ctx->e_v,
                     &ctx->e_nr, &ctx->e_obs, &ctx->e_obs_sq, &ctx->e_first, &ctx->e_row_ptr, &ctx->e_gap, &ctx->e_score,
@@ -126,18 +126,21 @@ extern "C" int besst_contigs_select(besst_ctx* ctx, int32_t slot) {
 static int stage_records(besst_ctx* ctx, const besst_records* r, DeviceRecords* d, bool need_tlen, bool need_graph_cols) {
     if (!r || r->n < 0) { ctx->err = "records: null or negative n"; return BESST_E_INVALID; }
     d->n = r->n;
-    if (r->n > 0 && (!r->tid || !r->mtid || !r->flag || !r->mapq || (need_tlen && !r->tlen) ||
-                     (need_graph_cols && (!r->pos || !r->mpos || !r->qlen)))) {
+    const bool packed = need_graph_cols && r->packed != nullptr;   // the graph build takes flag / mapq / qlen from the packed column
+    if (r->n > 0 && (!r->tid || !r->mtid || (!packed && (!r->flag || !r->mapq)) || (need_tlen && !r->tlen) ||
+                     (need_graph_cols && (!r->pos || !r->mpos || (!packed && !r->qlen))))) {
         ctx->err = "records: missing column";
         return BESST_E_INVALID;
     }
+    d->packed = nullptr;
     if (r->on_device) {
         d->tid = r->tid; d->mtid = r->mtid; d->pos = r->pos; d->mpos = r->mpos; d->tlen = r->tlen; d->qlen = r->qlen;
         d->flag = r->flag; d->mapq = r->mapq;
+        if (packed) d->packed = r->packed;
         return BESST_OK;
     }
     const size_t n = (size_t)r->n, nz = n ? n : 1;
-    const int32_t* src[6] = {r->tid, r->mtid, r->pos, r->mpos, r->tlen, r->qlen};
+    const int32_t* src[6] = {r->tid, r->mtid, r->pos, r->mpos, r->tlen, packed ? nullptr : r->qlen};
     const int32_t** dst[6] = {&d->tid, &d->mtid, &d->pos, &d->mpos, &d->tlen, &d->qlen};
     for (int k = 0; k < 6; ++k) {
         *dst[k] = nullptr;
@@ -145,6 +148,13 @@ static int stage_records(besst_ctx* ctx, const besst_records* r, DeviceRecords* 
         BESST_CUDA_TRY(ctx, ctx->rec_i32[k].ensure(4 * nz));
         if (n) BESST_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->rec_i32[k].p, src[k], 4 * n, cudaMemcpyHostToDevice, ctx->stream));
         *dst[k] = ctx->rec_i32[k].as<int32_t>();
+    }
+    if (packed) {
+        BESST_CUDA_TRY(ctx, ctx->rec_packed.ensure(4 * nz));
+        if (n) BESST_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->rec_packed.p, r->packed, 4 * n, cudaMemcpyHostToDevice, ctx->stream));
+        d->packed = ctx->rec_packed.as<uint32_t>();
+        d->flag = nullptr; d->mapq = nullptr;
+        return BESST_OK;
     }
     BESST_CUDA_TRY(ctx, ctx->rec_flag.ensure(2 * nz));
     BESST_CUDA_TRY(ctx, ctx->rec_mapq.ensure(nz));
@@ -161,12 +171,13 @@ static int stage_records(besst_ctx* ctx, const besst_records* r, DeviceRecords* 
 // the record kernel works on the slices that have arrived (an event per slice orders the two
 // streams), so the call costs max(PCIe, K1) instead of their sum.
 static int extract_host_pipelined(besst_ctx* ctx, const besst_lib_params* params, const besst_records* r, DeviceRecords* d) {
-    if (r->n < 0 || !r->tid || !r->mtid || !r->flag || !r->mapq || !r->pos || !r->mpos || !r->qlen) {
+    const bool packed = r->packed != nullptr;
+    if (r->n < 0 || !r->tid || !r->mtid || !r->pos || !r->mpos || (!packed && (!r->flag || !r->mapq || !r->qlen))) {
         ctx->err = "records: missing column";
         return BESST_E_INVALID;
     }
     const size_t n = (size_t)r->n;
-    const int32_t* src[6] = {r->tid, r->mtid, r->pos, r->mpos, nullptr, r->qlen};
+    const int32_t* src[6] = {r->tid, r->mtid, r->pos, r->mpos, nullptr, packed ? nullptr : r->qlen};
     const int32_t** dst[6] = {&d->tid, &d->mtid, &d->pos, &d->mpos, &d->tlen, &d->qlen};
     for (int k = 0; k < 6; ++k) {
         *dst[k] = nullptr;
@@ -174,10 +185,16 @@ static int extract_host_pipelined(besst_ctx* ctx, const besst_lib_params* params
         BESST_CUDA_TRY(ctx, ctx->rec_i32[k].ensure(4 * n));
         *dst[k] = ctx->rec_i32[k].as<int32_t>();
     }
-    BESST_CUDA_TRY(ctx, ctx->rec_flag.ensure(2 * n));
-    BESST_CUDA_TRY(ctx, ctx->rec_mapq.ensure(n));
-    d->flag = ctx->rec_flag.as<uint16_t>();
-    d->mapq = ctx->rec_mapq.as<uint8_t>();
+    d->packed = nullptr; d->flag = nullptr; d->mapq = nullptr;
+    if (packed) {
+        BESST_CUDA_TRY(ctx, ctx->rec_packed.ensure(4 * n));
+        d->packed = ctx->rec_packed.as<uint32_t>();
+    } else {
+        BESST_CUDA_TRY(ctx, ctx->rec_flag.ensure(2 * n));
+        BESST_CUDA_TRY(ctx, ctx->rec_mapq.ensure(n));
+        d->flag = ctx->rec_flag.as<uint16_t>();
+        d->mapq = ctx->rec_mapq.as<uint8_t>();
+    }
     d->n = r->n;
     const int64_t S = ctx->slice_records;
     const int64_t n_slices = (r->n + S - 1) / S;
@@ -196,8 +213,12 @@ static int extract_host_pipelined(besst_ctx* ctx, const besst_lib_params* params
         for (int k = 0; k < 6; ++k)
             if (src[k])
                 BESST_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->rec_i32[k].as<int32_t>() + r0, src[k] + r0, 4 * m, cudaMemcpyHostToDevice, ctx->copy_stream));
-        BESST_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->rec_flag.as<uint16_t>() + r0, r->flag + r0, 2 * m, cudaMemcpyHostToDevice, ctx->copy_stream));
-        BESST_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->rec_mapq.as<uint8_t>() + r0, r->mapq + r0, m, cudaMemcpyHostToDevice, ctx->copy_stream));
+        if (packed) {
+            BESST_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->rec_packed.as<uint32_t>() + r0, r->packed + r0, 4 * m, cudaMemcpyHostToDevice, ctx->copy_stream));
+        } else {
+            BESST_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->rec_flag.as<uint16_t>() + r0, r->flag + r0, 2 * m, cudaMemcpyHostToDevice, ctx->copy_stream));
+            BESST_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->rec_mapq.as<uint8_t>() + r0, r->mapq + r0, m, cudaMemcpyHostToDevice, ctx->copy_stream));
+        }
         BESST_CUDA_TRY(ctx, cudaEventRecord(ctx->slice_events[(size_t)s], ctx->copy_stream));
         BESST_CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream, ctx->slice_events[(size_t)s], 0));
         rc = besst_extract_slice(ctx, *params, *d, (int64_t)r0, (int64_t)r1);

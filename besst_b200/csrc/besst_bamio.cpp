@@ -70,6 +70,8 @@ struct besst_bam {
     Column<int32_t> tid, mtid, pos, mpos, tlen, qlen, rlen, alen;
     Column<uint16_t> flag;
     Column<uint8_t> mapq;
+    Column<uint32_t> packed;          // flag | mapq << 12 | qlen << 20 (besst_records.packed)
+    std::atomic<int> unpackable{0};   // some record has flag >= 4096 or qlen >= 4096: the packed column is not handed out
     int64_t n = 0, n_head = 0;
     int32_t stopped = 0;   // the window callback of besst_bam_stream asked to stop
     besst_bam_stats stats;
@@ -164,7 +166,7 @@ inline void cigar_lengths(const unsigned char* cig, uint32_t n_cigar, int32_t l_
 
 }  // namespace
 
-extern "C" int besst_bamio_abi_version(void) { return 1; }
+extern "C" int besst_bamio_abi_version(void) { return 2; }
 
 // window_fn == nullptr: all records accumulate in the handle's columns (besst_bam_read); else every decoded window is
 // handed to window_fn and its column space reused (besst_bam_stream)
@@ -382,7 +384,8 @@ static besst_bam* read_impl(const char* path, int32_t n_threads, int64_t max_rec
         }
         const int64_t m = tbase[(size_t)n_threads];
         if (!B->tid.ensure(n0 + m, n0) || !B->mtid.ensure(n0 + m, n0) || !B->pos.ensure(n0 + m, n0) || !B->mpos.ensure(n0 + m, n0) ||
-            !B->tlen.ensure(n0 + m, n0) || !B->qlen.ensure(n0 + m, n0) || !B->flag.ensure(n0 + m, n0) || !B->mapq.ensure(n0 + m, n0))
+            !B->tlen.ensure(n0 + m, n0) || !B->qlen.ensure(n0 + m, n0) || !B->flag.ensure(n0 + m, n0) || !B->mapq.ensure(n0 + m, n0) ||
+            !B->packed.ensure(n0 + m, n0))
             return fail("out of memory for the record columns");
         const int64_t head_new = std::min<int64_t>(head_records, base_total + n0 + m);
         if (!B->rlen.ensure(head_new > 0 ? head_new : 1, B->n_head) || !B->alen.ensure(head_new > 0 ? head_new : 1, B->n_head))
@@ -411,6 +414,11 @@ static besst_bam* read_impl(const char* path, int32_t n_threads, int64_t max_rec
                 int32_t ql, al;
                 cigar_lengths(p + 36 + l_read_name, n_cigar, l_seq, &ql, &al);
                 B->qlen.p[g] = ql;
+                {
+                    const uint32_t fl = rd16(p + 18);
+                    if (fl >= 4096u || ql < 0 || ql >= 4096) B->unpackable.store(1);
+                    B->packed.p[g] = (fl & 0xfffu) | ((uint32_t)p[13] << 12) | ((uint32_t)ql << 20);
+                }
                 if (base_total + g < head_records) { B->rlen.p[base_total + g] = l_seq; B->alen.p[base_total + g] = al; }
             }
         };
@@ -469,6 +477,7 @@ extern "C" int besst_bam_get_columns(const besst_bam* b, besst_bam_columns* out)
     out->n = b->n;
     out->tid = b->tid.p; out->mtid = b->mtid.p; out->pos = b->pos.p; out->mpos = b->mpos.p; out->tlen = b->tlen.p;
     out->qlen = b->qlen.p; out->flag = b->flag.p; out->mapq = b->mapq.p; out->rlen = b->rlen.p; out->alen = b->alen.p;
+    out->packed = b->unpackable.load() ? nullptr : b->packed.p;
     out->n_head = b->n_head;
     return 0;
 }

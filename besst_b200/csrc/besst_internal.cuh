@@ -68,6 +68,7 @@ struct DeviceRecords {
     const int32_t *tid, *mtid, *pos, *mpos, *tlen, *qlen;
     const uint16_t* flag;
     const uint8_t* mapq;
+    const uint32_t* packed = nullptr;   // flag | mapq << 12 | qlen << 20 (replaces the three columns in the graph build)
 };
 
 // scalar constants of the per-edge scoring math, evaluated once on the host
@@ -101,7 +102,7 @@ struct besst_ctx {
 
     // staged records (host-pointer calls); the copies run on copy_stream, slice by slice, overlapped
     // with the record kernel on `stream`
-    DBuf rec_i32[6], rec_flag, rec_mapq;
+    DBuf rec_i32[6], rec_flag, rec_mapq, rec_packed;
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t ev_fork = nullptr;
     std::vector<cudaEvent_t> slice_events;

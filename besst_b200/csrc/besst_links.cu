@@ -208,7 +208,9 @@ __device__ __forceinline__ void mbar_wait(u32 bar, u32 parity) {
     } while (!done);
 }
 
-template <bool INT_RL>
+// PACKED: flag | mapq << 12 | qlen << 20 arrive as ONE 32-bit column (besst_records.packed) staged where the qlen
+// column would be: 20 instead of 23 bytes per record over PCIe and out of HBM
+template <bool INT_RL, bool PACKED>
 __global__ void __launch_bounds__(K1T_THREADS, K1T_MIN_CTAS) k_extract_links_tma(const K1Params P, const int vec_ok) {
     extern __shared__ __align__(128) unsigned char k1_smem[];
     __shared__ u64 s_cnt[8];
@@ -244,13 +246,19 @@ __global__ void __launch_bounds__(K1T_THREADS, K1T_MIN_CTAS) k_extract_links_tma
             const int4 a = *reinterpret_cast<const int4*>(&B.tid[lane * WT_ITEMS]);
             const int4 b = *reinterpret_cast<const int4*>(&B.mtid[lane * WT_ITEMS]);
             const int4 c = *reinterpret_cast<const int4*>(&B.qlen[lane * WT_ITEMS]);
-            const uint2 f = *reinterpret_cast<const uint2*>(&B.flag[lane * WT_ITEMS]);
-            const u32 m = *reinterpret_cast<const u32*>(&B.mapq[lane * WT_ITEMS]);
             tid[0] = a.x; tid[1] = a.y; tid[2] = a.z; tid[3] = a.w;
             mtid[0] = b.x; mtid[1] = b.y; mtid[2] = b.z; mtid[3] = b.w;
-            qlen[0] = c.x; qlen[1] = c.y; qlen[2] = c.z; qlen[3] = c.w;
-            flag[0] = f.x & 0xffffu; flag[1] = f.x >> 16; flag[2] = f.y & 0xffffu; flag[3] = f.y >> 16;
-            mapq[0] = m & 0xffu; mapq[1] = (m >> 8) & 0xffu; mapq[2] = (m >> 16) & 0xffu; mapq[3] = m >> 24;
+            if (PACKED) {
+                const u32 w[WT_ITEMS] = {(u32)c.x, (u32)c.y, (u32)c.z, (u32)c.w};
+#pragma unroll
+                for (int i = 0; i < WT_ITEMS; ++i) { flag[i] = w[i] & 0xfffu; mapq[i] = (w[i] >> 12) & 0xffu; qlen[i] = (int)(w[i] >> 20); }
+            } else {
+                const uint2 f = *reinterpret_cast<const uint2*>(&B.flag[lane * WT_ITEMS]);
+                const u32 m = *reinterpret_cast<const u32*>(&B.mapq[lane * WT_ITEMS]);
+                qlen[0] = c.x; qlen[1] = c.y; qlen[2] = c.z; qlen[3] = c.w;
+                flag[0] = f.x & 0xffffu; flag[1] = f.x >> 16; flag[2] = f.y & 0xffffu; flag[3] = f.y >> 16;
+                mapq[0] = m & 0xffu; mapq[1] = (m >> 8) & 0xffu; mapq[2] = (m >> 16) & 0xffu; mapq[3] = m >> 24;
+            }
         }
 
         // ---- per-record classification (CreateGraph.py:118-206); only word 0 of a contig row is needed:
@@ -366,8 +374,9 @@ __global__ void __launch_bounds__(K1T_THREADS, K1T_MIN_CTAS) k_extract_links_tma
                 bool mq0 = false, both_large = false;
                 if (active) {
                     const int j = W.cand[k];
-                    const u32 fl = B.flag[j];
-                    mq0 = B.mapq[j] == 0;
+                    const u32 pw = PACKED ? (u32)B.qlen[j] : 0u;
+                    const u32 fl = PACKED ? (pw & 0xfffu) : (u32)B.flag[j];
+                    mq0 = PACKED ? (((pw >> 12) & 0xffu) == 0u) : (B.mapq[j] == 0);
                     const int4 r1 = __ldg(P.rows + B.tid[j]);   // L1 hits: word 0 was gathered a moment ago
                     const int4 r2 = __ldg(P.rows + B.mtid[j]);
                     both_large = (((u32)r1.x | (u32)r2.x) & 3u) == (u32)BESST_CTG_LARGE;   // neither is absent here
@@ -440,16 +449,19 @@ __global__ void __launch_bounds__(K1T_THREADS, K1T_MIN_CTAS) k_extract_links_tma
             const long long r0 = tile * WT;
             const u32 bar = bar0 + 8u * s;
             const u32 dst = smem_u32(&W.buf[s]);
-            mbar_expect_tx(bar, TILE_BYTES_NOPOS + (want_pos ? TILE_BYTES_POS : 0u));
+            mbar_expect_tx(bar, (PACKED ? 3u * 4u * WT : TILE_BYTES_NOPOS) + (want_pos ? TILE_BYTES_POS : 0u));
             bulk_g2s(dst + 0 * 4 * WT, P.rec.tid + r0, 4 * WT, bar);
             bulk_g2s(dst + 1 * 4 * WT, P.rec.mtid + r0, 4 * WT, bar);
-            bulk_g2s(dst + 2 * 4 * WT, P.rec.qlen + r0, 4 * WT, bar);
+            if (PACKED) bulk_g2s(dst + 2 * 4 * WT, P.rec.packed + r0, 4 * WT, bar);
+            else bulk_g2s(dst + 2 * 4 * WT, P.rec.qlen + r0, 4 * WT, bar);
             if (want_pos) {
                 bulk_g2s(dst + 3 * 4 * WT, P.rec.pos + r0, 4 * WT, bar);
                 bulk_g2s(dst + 4 * 4 * WT, P.rec.mpos + r0, 4 * WT, bar);
             }
-            bulk_g2s(dst + 5 * 4 * WT, P.rec.flag + r0, 2 * WT, bar);
-            bulk_g2s(dst + 5 * 4 * WT + 2 * WT, P.rec.mapq + r0, WT, bar);
+            if (!PACKED) {
+                bulk_g2s(dst + 5 * 4 * WT, P.rec.flag + r0, 2 * WT, bar);
+                bulk_g2s(dst + 5 * 4 * WT + 2 * WT, P.rec.mapq + r0, WT, bar);
+            }
         }
     };
     u32* const ticket = reinterpret_cast<u32*>(P.globals + 2);
@@ -491,11 +503,15 @@ __global__ void __launch_bounds__(K1T_THREADS, K1T_MIN_CTAS) k_extract_links_tma
             const int q = lane * WT_ITEMS + i;
             B.tid[q] = in ? __ldg(P.rec.tid + r) : -1;
             B.mtid[q] = in ? __ldg(P.rec.mtid + r) : -1;
-            B.qlen[q] = in ? __ldg(P.rec.qlen + r) : 0;
             B.pos[q] = in ? __ldg(P.rec.pos + r) : 0;
             B.mpos[q] = in ? __ldg(P.rec.mpos + r) : 0;
-            B.flag[q] = in ? __ldg(P.rec.flag + r) : (unsigned short)0;
-            B.mapq[q] = in ? __ldg(P.rec.mapq + r) : (unsigned char)0;
+            if (PACKED) {
+                B.qlen[q] = in ? (int)__ldg(P.rec.packed + r) : 0;
+            } else {
+                B.qlen[q] = in ? __ldg(P.rec.qlen + r) : 0;
+                B.flag[q] = in ? __ldg(P.rec.flag + r) : (unsigned short)0;
+                B.mapq[q] = in ? __ldg(P.rec.mapq + r) : (unsigned char)0;
+            }
         }
         __syncwarp();
         process(t, B, true, false);
@@ -963,9 +979,11 @@ int besst_extract_slice(besst_ctx* ctx, const besst_lib_params& p, const DeviceR
     K1Params P;
     P.rec.n = r1 - r0;
     P.rec.tid = rec.tid + r0; P.rec.mtid = rec.mtid + r0; P.rec.pos = rec.pos + r0; P.rec.mpos = rec.mpos + r0;
-    P.rec.qlen = rec.qlen + r0; P.rec.flag = rec.flag + r0; P.rec.mapq = rec.mapq + r0; P.rec.tlen = nullptr;
+    const bool packed = rec.packed != nullptr;
+    P.rec.qlen = packed ? nullptr : rec.qlen + r0; P.rec.flag = packed ? nullptr : rec.flag + r0; P.rec.mapq = packed ? nullptr : rec.mapq + r0;
+    P.rec.packed = packed ? rec.packed + r0 : nullptr; P.rec.tlen = nullptr;
     bool vec = true;
-    const void* ptrs[] = {P.rec.tid, P.rec.mtid, P.rec.pos, P.rec.mpos, P.rec.qlen, P.rec.flag, P.rec.mapq};
+    const void* ptrs[] = {P.rec.tid, P.rec.mtid, P.rec.pos, P.rec.mpos, P.rec.qlen, P.rec.flag, P.rec.mapq, P.rec.packed};
     for (const void* q : ptrs) vec = vec && ((reinterpret_cast<uintptr_t>(q) & 15u) == 0);
     const bool int_rl = p.read_len >= 0 && p.read_len < 1e9 && p.read_len == (double)(long long)p.read_len;
     P.rows = ctx->rows_packed.as<int4>();
@@ -990,7 +1008,8 @@ int besst_extract_slice(besst_ctx* ctx, const besst_lib_params& p, const DeviceR
     P.n_tiles = n_tiles;
 
     typedef void (*K1Fn)(const K1Params, const int);
-    const K1Fn k1 = int_rl ? k_extract_links_tma<true> : k_extract_links_tma<false>;
+    const K1Fn k1 = packed ? (int_rl ? k_extract_links_tma<true, true> : k_extract_links_tma<false, true>)
+                           : (int_rl ? k_extract_links_tma<true, false> : k_extract_links_tma<false, false>);
     const size_t smem = sizeof(WarpSmem) * K1T_WARPS;
     int per_sm = 0;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k1, K1T_THREADS, smem);

@@ -55,6 +55,9 @@ class RecordBatch:
     lengths: Sequence[int] = field(default_factory=list)
     rlen: Optional[np.ndarray] = None   # only the first 1000 are ever read
     alen: Optional[np.ndarray] = None
+    # optional: flag | mapq << 12 | qlen << 20 in one uint32 column (besst_records.packed): what the graph build uploads and
+    # reads instead of the three columns (20 instead of 23 bytes per record).  The native ingest fills it while decoding.
+    packed: Optional[np.ndarray] = None
 
     def __post_init__(self):
         for name, dt in _DEVICE_FIELDS:
@@ -73,7 +76,15 @@ class RecordBatch:
         kw = {name: getattr(self, name)[lo:hi] for name, _ in _DEVICE_FIELDS}
         return RecordBatch(references=self.references, lengths=self.lengths,
                            rlen=None if self.rlen is None else self.rlen[lo:hi],
-                           alen=None if self.alen is None else self.alen[lo:hi], **kw)
+                           alen=None if self.alen is None else self.alen[lo:hi],
+                           packed=None if self.packed is None else self.packed[lo:hi], **kw)
+
+    def with_packed(self):
+        """Fill `packed` from flag / mapq / qlen (no-op when it exists or a value does not fit)."""
+        if self.packed is None:
+            from .abi import pack_record_columns
+            self.packed = pack_record_columns(self.flag, self.mapq, self.qlen)
+        return self
 
     def select(self, mask):
         kw = {name: getattr(self, name)[mask] for name, _ in _DEVICE_FIELDS}

@@ -98,7 +98,12 @@ typedef struct besst_records {
                              respect to the ctx's stream: synchronise the producing stream first, or make the
                              ctx run on it (besst_set_stream) */
     int32_t reserved;
+    const uint32_t* packed; /* optional: flag | mapq << 12 | qlen << 20 in ONE column (BESST_PACK_RECORD).  When given, the
+                               graph build reads it INSTEAD of flag / mapq / qlen: 20 instead of 23 bytes per record over
+                               PCIe and out of HBM (the ingest library writes it while decoding).  Needs flag < 4096 (all
+                               SAM flag bits) and qlen < 4096; besst_libmetrics still reads the three plain columns. */
 } besst_records;
+#define BESST_PACK_RECORD(flag, mapq, qlen) (((uint32_t)(flag) & 0xfffu) | ((uint32_t)(mapq) << 12) | ((uint32_t)(qlen) << 20))
 
 #define BESST_ORIENT_FR 0
 #define BESST_ORIENT_RF 1

@@ -39,6 +39,9 @@ typedef struct besst_bam_columns {
     const int32_t* rlen;  /* [min(n, head)] */
     const int32_t* alen;  /* [min(n, head)] */
     int64_t n_head;       /* records for which rlen / alen were kept */
+    const uint32_t* packed; /* flag | mapq << 12 | qlen << 20 (besst_records.packed, include/besst_b200.h): what the graph
+                               build uploads instead of flag / mapq / qlen.  NULL when some record does not fit
+                               (flag >= 4096 or qlen >= 4096) */
 } besst_bam_columns;
 
 typedef struct besst_bam_stats {

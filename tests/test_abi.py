@@ -46,7 +46,7 @@ def test_bamio_library_exports_every_declared_symbol():
         assert hasattr(L, name), "libbesst_bamio.so does not export %s" % name
     assert sorted(bamio.BAMIO_EXPORTS) == names
     L.besst_bamio_abi_version.restype = C.c_int
-    assert L.besst_bamio_abi_version() == 1
+    assert L.besst_bamio_abi_version() == 2
 
 
 def test_ctypes_structs_match_c_layout():

@@ -10,6 +10,7 @@ import numpy as np
 import pytest
 
 from besst_b200 import bamio
+from besst_b200.abi import pack_record_columns as abi_pack
 
 REF_BAM = "/root/reference/testdata/testset1/mapped.bam"
 
@@ -76,6 +77,8 @@ def test_native_reader_equals_python_reader(tmp_path, n, block_bytes, threads):
     assert len(nat) == n
     _assert_same(nat, py)
     assert nat.stats["records"] == n and nat.stats["blocks"] >= 1
+    if n:   # the packed column the graph build uploads: flag | mapq << 12 | qlen << 20
+        assert nat.packed is not None and np.array_equal(nat.packed, abi_pack(py.flag, py.mapq, py.qlen))
     if n > 100:
         part = bamio.read_bam_native(path, threads=threads, max_records=100)
         assert len(part) == 100 and np.array_equal(part.pos, py.pos[:100])

@@ -599,3 +599,37 @@ def test_lognormal_scoring_branch_cuda_equals_oracle(cuda_engine):
     CG.lognormal_rescore(want, table, P, OracleEngine())
     helpers.assert_graph_equal(got, want, label="lognormal")
     assert (got.gap[(got.flags & abi.EDGE_BIG) != 0] != 0).any()
+
+
+@pytest.mark.parametrize("config", ["small_mp_cont", "small_pe"])
+def test_packed_record_column_equals_plain_columns(cuda_engine, config):
+    """besst_records.packed (flag | mapq << 12 | qlen << 20, 20 B/record) through K1's TMA path, its ragged leftover
+    path, the sliced host upload and device-resident pointers: identical to the three plain columns and to the oracle."""
+    import torch
+    from besst_b200.records import RecordBatch
+    lib, batch, params, table = _setup(config)
+    rng = np.random.default_rng(3)
+    batch.qlen = rng.integers(30, 151, len(batch)).astype(np.int32)   # ragged read lengths: the coverage sums depend on them
+    want = cuda_engine.graph_build(table, params, batch)
+    ref, _, _, _ = oracle_lib.graph_build(table.rows, table.n_scaffolds, params, batch)
+    helpers.assert_graph_equal(want, ref, label="plain")
+    packed = RecordBatch(references=batch.references, lengths=batch.lengths, **batch.device_arrays()).with_packed()
+    assert packed.packed is not None and packed.packed.dtype == np.uint32
+    got = cuda_engine.graph_build(table, params, packed)
+    helpers.assert_graph_equal(got, want, label="packed host")
+    # only the packed column and the four coordinates are touched: poison the plain ones
+    poisoned = RecordBatch(references=batch.references, lengths=batch.lengths, packed=packed.packed, **batch.device_arrays())
+    poisoned.flag = np.zeros_like(batch.flag); poisoned.mapq = np.zeros_like(batch.mapq); poisoned.qlen = np.zeros_like(batch.qlen)
+    helpers.assert_graph_equal(cuda_engine.graph_build(table, params, poisoned), want, label="packed only")
+    # device-resident, unaligned start (leftover path) and a ragged tail
+    cols = {k: torch.from_numpy(np.ascontiguousarray(getattr(packed, k)[3:-5])).cuda() for k in ("tid", "mtid", "pos", "mpos")}
+    cols["packed"] = torch.from_numpy(packed.packed[3:-5].view(np.int32).copy()).cuda()
+    ptrs = {k: v.data_ptr() for k, v in cols.items()}
+    ptrs["n"] = len(batch) - 8
+    torch.cuda.synchronize()
+    cuda_engine.set_table(table)
+    dev = cuda_engine.fetch(cuda_engine.build(params, abi.make_records(ptrs, on_device=True)))
+    sub = batch.slice(3, len(batch) - 5)
+    helpers.assert_graph_equal(dev, cuda_engine.graph_build(table, params, sub), label="packed device")
+    assert abi.pack_record_columns(np.array([4096]), np.array([0]), np.array([100])) is None
+    assert abi.pack_record_columns(np.array([99]), np.array([60]), np.array([5000])) is None
