@@ -303,8 +303,16 @@ def run_ours(args):
         eng.select_table(L.index)
         return runner.step(L.params, rec) if runner is not None else eng.build(L.params, rec)
 
+    pos_tiles = {}   # per library: record tiles whose pos / mpos columns K1 fetched (BESST_CNT_POS_TILES)
+
     def step():
-        return [build(L, L.rec_dev) for L in libs]
+        out = []
+        for L in libs:
+            out.append(build(L, L.rec_dev))
+            if L.index not in pos_tiles:
+                torch.cuda.synchronize()   # N>1: the counters are all-reduced in place (sum over ranks)
+                pos_tiles[L.index] = int(eng.links_counters()[abi.CNT_POS_TILES]) // world
+        return out
 
     def barrier():
         if world > 1:
@@ -384,7 +392,9 @@ def run_ours(args):
     n_launch = {k: len(v) / args.steps for k, v in prof.items()}
     n_tiles = sum((L.n_rec + 127) // 128 for L in libs)
     alg_bytes_step = {   # algorithmic bytes per STEP of each kernel family on this rank (DESIGN.md "Kernels")
-        "k_extract_links": record_bytes * n_rec + TUPLE_BYTES * (n_links if world == 1 else 0) + 48 * n_tiles,
+        # K1 reads tid / mtid / flags of every record, pos / mpos only of the tiles that can hold a CreateEdge candidate
+        # (counted by the kernel), writes one tuple per accepted link and one aggregate per tile
+        "k_extract_links": (record_bytes - 8) * n_rec + 8 * 128 * sum(pos_tiles.values()) + TUPLE_BYTES * (n_links if world == 1 else 0) + 48 * n_tiles,
         "k_compact_tuples": 2 * TUPLE_BYTES * n_links + 8 * n_tiles,
         "k_radix_sweep": (8 + 8) * n_links,       # packed sort word (key | BAM index): 8 B in, 8 B out per pass
         "k_radix_hist": 8 * n_links,
@@ -595,6 +605,7 @@ def run_ours(args):
                        "contigs": n_contigs, "pairs_per_step": int(total_pairs), "records_per_step": n_rec_total,
                        "libraries": [L.describe() for L in libs],
                        "accepted_links": g_links, "edges": g_edges, "scored_links": g_ll,
+                       "record_tiles_with_positions": "%d of %d on rank 0" % (sum(pos_tiles.values()), n_tiles),
                        "record_format": ("packed: tid, mtid, pos, mpos int32 + one uint32 flag|mapq<<12|qlen<<20 = 20 B/record (besst_records.packed, "
                                          "written by the ingest library)") if packed else "plain: tid, mtid, pos, mpos, qlen int32 + flag u16 + mapq u8 = 23 B/record",
                        "l2_policy": "inputs (%.1f GB per rank) larger than the 126 MB L2" % (record_bytes * n_rec / 1e9),

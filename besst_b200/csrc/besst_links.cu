@@ -222,6 +222,7 @@ __global__ void __launch_bounds__(K1T_THREADS, K1T_MIN_CTAS) k_extract_links_tma
     WarpSmem& W = reinterpret_cast<WarpSmem*>(k1_smem)[warp];
     const u32 bar0 = smem_u32(&W.bar[0]);
     int c_count = 0, c_nonuniq = 0, c_nonuniq_scaf = 0, c_dups = 0, c_toolong = 0, c_fishy = 0, c_calls = 0, c_valid = 0;
+    int c_postiles = 0;   // warp-uniform: tiles whose pos / mpos columns were fetched (the kernel's real input bytes)
     if (threadIdx.x < 8) s_cnt[threadIdx.x] = 0;
     if (lane == 0) {
         mbar_init(bar0, 1); mbar_init(bar0 + 8, 1); mbar_init(bar0 + 16, 1);
@@ -358,6 +359,7 @@ __global__ void __launch_bounds__(K1T_THREADS, K1T_MIN_CTAS) k_extract_links_tma
                 }
                 mbar_wait(bar0 + 16u, demand_par);
                 demand_par ^= 1u;
+                ++c_postiles;
             }
             __syncwarp();
 
@@ -445,6 +447,7 @@ __global__ void __launch_bounds__(K1T_THREADS, K1T_MIN_CTAS) k_extract_links_tma
     // a quarter of the warp slots idle towards the end.  The next batch's ticket is requested a batch ahead.
     const long long n_full = vec_ok ? n / WT : 0;
     auto issue = [&](const long long tile, const int s, const bool want_pos) {
+        c_postiles += want_pos ? 1 : 0;
         if (elect_one()) {
             const long long r0 = tile * WT;
             const u32 bar = bar0 + 8u * s;
@@ -514,8 +517,10 @@ __global__ void __launch_bounds__(K1T_THREADS, K1T_MIN_CTAS) k_extract_links_tma
             }
         }
         __syncwarp();
+        ++c_postiles;
         process(t, B, true, false);
     }
+    if (lane == 0 && c_postiles) atomicAdd(&P.counters[BESST_CNT_POS_TILES], (u64)c_postiles);
 
     // ---- flush the per-thread counters ------------------------------------------------------------
     __syncthreads();

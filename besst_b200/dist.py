@@ -310,7 +310,7 @@ class DistributedGraphBuild(object):
         n_all = [self.b.counts_tensor([0]) for _ in range(world)]
         dist.all_gather(n_all, self.b.counts_tensor([n_local]), group=self.group)
         ends = counters[[abi.CNT_CALLS, abi.CNT_LAST_OBS1, abi.CNT_LAST_OBS2, abi.CNT_FIRST_OBS1, abi.CNT_FIRST_OBS2]].clone()
-        counters[abi.CNT_LAST_OBS1:] = 0
+        counters[abi.CNT_LAST_OBS1:abi.CNT_FIRST_OBS2 + 1] = 0
         dist.all_reduce(aligned, op=dist.ReduceOp.SUM, group=self.group)
         dist.all_reduce(counters, op=dist.ReduceOp.SUM, group=self.group)
         all_ends = [ends.clone() for _ in range(world)]
@@ -389,7 +389,7 @@ class DistributedGraphBuild(object):
         # coverage + counters are final once the extraction is: their all-reduce runs on the collective's own stream
         # WHILE the runs are exchanged and the graph is built, and is waited for at the end of the step
         aligned, counters = self.b.partial_tensors()
-        counters[abi.CNT_LAST_OBS1:] = 0   # per-rank slots (last / first call): not sums
+        counters[abi.CNT_LAST_OBS1:abi.CNT_FIRST_OBS2 + 1] = 0   # per-rank slots (last / first call): not sums
         pending = [dist.all_reduce(aligned, op=dist.ReduceOp.SUM, group=self.group, async_op=True),
                    dist.all_reduce(counters, op=dist.ReduceOp.SUM, group=self.group, async_op=True)]
         n_by_rank = M[:, 1]

@@ -140,6 +140,8 @@ typedef struct besst_lib_params {
 #define BESST_CNT_LAST_OBS2 9       /*   -1,-1 if none: the next rank's halo     */
 #define BESST_CNT_FIRST_OBS1 10     /* (obs1,obs2) of the FIRST CreateEdge call (valid if CALLS > 0): lets the  */
 #define BESST_CNT_FIRST_OBS2 11     /*   multi-GPU driver check a slice against its halo without a tail pass   */
+#define BESST_CNT_POS_TILES 12      /* 128-record tiles whose pos / mpos columns the record kernel fetched (its real input: tiles
+                                       without a CreateEdge candidate are classified from tid / mtid / flags alone) */
 #define BESST_N_COUNTERS 16
 
 /* edge flags */
