@@ -17,6 +17,7 @@ ERF_AS7126, ERF_LIBM = 0, 1
 CNT_COUNT, CNT_NON_UNIQUE, CNT_NON_UNIQUE_SCAF, CNT_DUPLICATES, CNT_TOO_LONG = 0, 1, 2, 3, 4
 CNT_FISHY, CNT_CALLS, CNT_VALID, CNT_LAST_OBS1, CNT_LAST_OBS2 = 5, 6, 7, 8, 9
 CNT_FIRST_OBS1, CNT_FIRST_OBS2 = 10, 11
+CNT_POS_TILES = 12
 N_COUNTERS = 16
 N_STAGES = 8
 

@@ -413,6 +413,9 @@ class DistributedGraphBuild(object):
             dist.all_to_all_single(recv_desc, send_desc, output_split_sizes=rr.tolist(), input_split_sizes=rc.tolist(), group=self.group)
             dist.all_to_all_single(recv_f, send_f, output_split_sizes=rf.tolist(), input_split_sizes=fc.tolist(), group=self.group)
             self._mark("all_to_all")
+        # what this rank puts on the wire: observations (4 or 8 B per link) + 24 B per run + 8 B per fishy key to OTHER ranks
+        others = np.arange(world) != rank
+        self.exchange_bytes_out = int(4 * w * LC[rank][others].sum() + 24 * RC[rank][others].sum() + 8 * FC[rank][others].sum())
         max_blocks = int(((n_by_rank + abi.RUN_BLOCK - 1) // abi.RUN_BLOCK).max())
         block_bits = max(1, int(max(max_blocks - 1, 1)).bit_length())
         first_base = np.concatenate([[0], np.cumsum(n_by_rank)[:-1]])
