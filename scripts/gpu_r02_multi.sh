@@ -11,7 +11,7 @@ PORT=29540
 for mode in ${MODES:-peer runs tuples}; do
   PORT=$((PORT+1))
   BESST_DIST_EXCHANGE=$mode run $PORT tests/dist_check.py small_mp_cont > $OUT/dist_check_${mode}.log 2>&1
-  echo "$mode: $(grep -E 'DIST_CHECK_OK|Error|error|unavailable' $OUT/dist_check_${mode}.log | tail -2)"
+  echo "$mode: $(grep -E 'DIST_CHECK_OK|DIST_PE_OK|Error|error|unavailable' $OUT/dist_check_${mode}.log | tail -3)"
 done
 show() { python - <<PY
 import json

@@ -61,6 +61,14 @@ def main():
         helpers.assert_graph_equal(merged, want, label="dist world=%d %s" % (world, config))
         print("DIST_CHECK_OK world=%d %s: %d edges, %d links" % (world, config, merged.n_edges, merged.n_links))
     dist.barrier()
+    # the reference-facing entry point itself under the process group: besst_b200.CreateGraph.PE takes the multi-GPU build
+    # (every rank its BAM-order slice, merged CSR on every rank) and must leave the reference's graphs on EVERY rank
+    import test_golden_reference as tg
+    for case in ("small_mp_given", "small_pe_later", "testset1_travis"):
+        tg.check_case(case, eng)
+    dist.barrier()
+    if rank == 0:
+        print("DIST_PE_OK world=%d: CreateGraph.PE == reference goldens on every rank" % world)
     dist.destroy_process_group()
 
 
