@@ -48,7 +48,7 @@ extern "C" void besst_destroy(besst_ctx* ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     DBuf* bufs[] = {&ctx->rows, &ctx->rows_packed, &ctx->scratch_tuples, &ctx->block_tile0, &ctx->tile_aggs, &ctx->part_state, &ctx->scaf_len, &ctx->rec_flag, &ctx->rec_mapq, &ctx->rec_packed, &ctx->tuples, &ctx->fishy_keys, &ctx->aligned,
-                    &ctx->counters, &ctx->tile_state, &ctx->misc, &ctx->key_a, &ctx->key_b, &ctx->idx_a, &ctx->idx_b, &ctx->hist,
+                    &ctx->tile_state, &ctx->misc, &ctx->key_a, &ctx->key_b, &ctx->idx_a, &ctx->idx_b, &ctx->hist,
                     &ctx->sort_state, &ctx->fishy_sorted, &ctx->fishy_tmp, &ctx->heads, &ctx->block_sums, &ctx->e_u, &ctx->e_v,
                     &ctx->e_nr, &ctx->e_obs, &ctx->e_obs_sq, &ctx->e_first, &ctx->e_row_ptr, &ctx->e_gap, &ctx->e_score,
                     &ctx->e_ks, &ctx->e_sd_obs, &ctx->e_sd_model, &ctx->e_fishy, &ctx->e_flags, &ctx->l_obs_u, &ctx->l_obs_v,

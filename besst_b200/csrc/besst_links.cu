@@ -961,16 +961,19 @@ int besst_extract_begin(besst_ctx* ctx, const besst_lib_params& p, int64_t n) {
     const int64_t n_tiles = tiles_of(n);
     const int64_t n_chunks = (n_tiles + SC_THREADS - 1) / SC_THREADS;
     if (n_chunks > 0x7fffffff) { ctx->err = "too many records for one call"; return BESST_E_INVALID; }
-    BESST_CUDA_TRY(ctx, ctx->aligned.ensure(sizeof(u64) * (size_t)(ctx->n_contigs + 1)));
-    BESST_CUDA_TRY(ctx, ctx->counters.ensure(sizeof(u64) * (BESST_N_COUNTERS + 8)));
+    // coverage and counters share ONE allocation (aligned_len[C + 1] followed by the counters): one memset here, and a
+    // multi-GPU driver reduces both with a single all-reduce over the contiguous span
+    const size_t c1 = (size_t)(ctx->n_contigs + 1);
+    BESST_CUDA_TRY(ctx, ctx->aligned.ensure(sizeof(u64) * (c1 + BESST_N_COUNTERS + 8)));
+    ctx->counters.p = ctx->aligned.as<u64>() + c1;   // a view: never freed on its own
+    ctx->counters.cap = 0;
     BESST_CUDA_TRY(ctx, ctx->tile_aggs.ensure(sizeof(Agg) * (size_t)(n_tiles + n_chunks + 2)));
     BESST_CUDA_TRY(ctx, ctx->tile_state.ensure(sizeof(u64) * (size_t)(n_tiles + 2) + sizeof(ChunkIn) * (size_t)(n_chunks + 1)));
     BESST_CUDA_TRY(ctx, ctx->scratch_tuples.ensure(sizeof(besst_link_tuple) * (size_t)(n_tiles > 0 ? n_tiles : 1) * WT));
     BESST_CUDA_TRY(ctx, ctx->block_tile0.ensure(sizeof(u32) * (size_t)(n_tiles / 16 + 4)));   // one entry per 2048 accepted tuples
     if (ctx->fishy_cap == 0) ctx->fishy_cap = n / 8 + 4096;
     BESST_CUDA_TRY(ctx, ctx->fishy_keys.ensure(sizeof(u64) * (size_t)ctx->fishy_cap));
-    BESST_CUDA_TRY(ctx, cudaMemsetAsync(ctx->aligned.p, 0, sizeof(u64) * (size_t)(ctx->n_contigs + 1), ctx->stream));
-    BESST_CUDA_TRY(ctx, cudaMemsetAsync(ctx->counters.p, 0, sizeof(u64) * (BESST_N_COUNTERS + 8), ctx->stream));
+    BESST_CUDA_TRY(ctx, cudaMemsetAsync(ctx->aligned.p, 0, sizeof(u64) * (c1 + BESST_N_COUNTERS + 8), ctx->stream));
     return BESST_OK;
 }
 

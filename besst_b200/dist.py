@@ -206,6 +206,16 @@ class CudaBackend(object):
         return (_wrap_device_i64(self.torch, a_ptr, self.engine._n_contigs, self.device),
                 _wrap_device_i64(self.torch, c_ptr, abi.N_COUNTERS, self.device))
 
+    def partial_span(self):
+        """aligned_len[C], one spare word and counters[16] as ONE contiguous tensor (they share an allocation), with views of
+        the two parts: a single all-reduce covers both.  -> (span, aligned, counters)"""
+        a_ptr, c_ptr = self.engine.links_partials_device()
+        C_ = self.engine._n_contigs
+        if not a_ptr or c_ptr != a_ptr + 8 * (C_ + 1):
+            return None
+        span = _wrap_device_i64(self.torch, a_ptr, C_ + 1 + abi.N_COUNTERS, self.device)
+        return span, span[:C_], span[C_ + 1:]
+
     def counts_tensor(self, values):
         return self.torch.tensor(values, dtype=self.torch.int64, device=self.device)
 
@@ -386,12 +396,13 @@ class DistributedGraphBuild(object):
                     p = _copy_params(params, halos[rank])
                 continue
             break
-        # coverage + counters are final once the extraction is: their all-reduce runs on the collective's own stream
-        # WHILE the runs are exchanged and the graph is built, and is waited for at the end of the step
-        aligned, counters = self.b.partial_tensors()
-        counters[abi.CNT_LAST_OBS1:abi.CNT_FIRST_OBS2 + 1] = 0   # per-rank slots (last / first call): not sums
-        pending = [dist.all_reduce(aligned, op=dist.ReduceOp.SUM, group=self.group, async_op=True),
-                   dist.all_reduce(counters, op=dist.ReduceOp.SUM, group=self.group, async_op=True)]
+        # coverage + counters: one allocation, reduced with ONE all-reduce at the end of the step (launching it early on
+        # NCCL's own stream was slower: its CTAs spin on the slowest rank's extraction and take SMs from the build)
+        span = self.b.partial_span() if hasattr(self.b, "partial_span") else None
+        if span is not None:
+            span, aligned, counters = span
+        else:
+            aligned, counters = self.b.partial_tensors()
         n_by_rank = M[:, 1]
         LC, RC, FC = M[:, 7:7 + world], M[:, 7 + world:7 + 2 * world], M[:, 7 + 2 * world:7 + 3 * world]
         rl, rr, rf = LC[:, rank], RC[:, rank], FC[:, rank]
@@ -421,9 +432,13 @@ class DistributedGraphBuild(object):
         first_base = np.concatenate([[0], np.cumsum(n_by_rank)[:-1]])
         sizes = self.b.runs_to_graph(p, recv_obs, recv_desc, world, block_bits, rr, rl, first_base, recv_f)
         self._mark("runs_to_graph")
-        for w in pending:
-            w.wait()
-        self._mark("all_reduce (tail not hidden)")
+        counters[abi.CNT_LAST_OBS1:abi.CNT_FIRST_OBS2 + 1] = 0   # per-rank slots (last / first call): not sums
+        if span is not None:
+            dist.all_reduce(span, op=dist.ReduceOp.SUM, group=self.group)
+        else:
+            dist.all_reduce(aligned, op=dist.ReduceOp.SUM, group=self.group)
+            dist.all_reduce(counters, op=dist.ReduceOp.SUM, group=self.group)
+        self._mark("all_reduce")
         self.last = dict(sizes=sizes, global_first=True, n_tuples_by_rank=n_by_rank.tolist(), aligned=aligned, counters=counters,
                          last_call=global_last, first_call=global_first, halo=halos[rank])
         return sizes

@@ -251,7 +251,9 @@ int besst_links_tuples_device(besst_ctx* ctx, const besst_link_tuple** tuples, i
 int besst_links_fishy_device(besst_ctx* ctx, const uint64_t** keys, int64_t* n_keys);
 int besst_links_partials(besst_ctx* ctx, int64_t* aligned_len_host /*[C]*/, int64_t* counters_host /*[16]*/);
 /* device views of the same partial sums (aligned_len[C], counters[16], int64) for an in-place
- * NCCL all-reduce; valid until the next extract */
+ * NCCL all-reduce; valid until the next extract.  The two live in ONE allocation, counters_device ==
+ * aligned_len_device + C + 1: a single all-reduce over C + 1 + 16 words covers both (zero the per-rank
+ * slots BESST_CNT_LAST_OBS1 .. BESST_CNT_FIRST_OBS2 first). */
 int besst_links_partials_device(besst_ctx* ctx, int64_t** aligned_len_device, int64_t** counters_device);
 /* host copies of the extracted tuple stream / fishy keys (tests, debugging); either may be NULL */
 int besst_links_fetch(besst_ctx* ctx, besst_link_tuple* tuples_host, uint64_t* fishy_keys_host);
