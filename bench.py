@@ -440,7 +440,7 @@ def run_ours(args):
     try:   # DRAM bytes per launch from the committed ncu capture of this workload (profiles/ncu_traffic.json)
         with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as fh:
             tj = json.load(fh)
-        if tj.get("workload") == name and args.scale == 1.0 and world == 1:
+        if tj.get("workload") == name and args.scale == 1.0 and world == 1 and tj.get("records", "plain") == args.records:
             traffic = tj
     except Exception:
         pass
@@ -718,7 +718,8 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline / parity leg")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (profiler runs only)")
     ap.add_argument("--no-libmetrics", action="store_true", help="skip the library-metrics leg")
-    ap.add_argument("--pe-level", action="store_true", help="also time get_metrics + CreateGraph.PE (host records -> networkx graphs), N=1")
+    ap.add_argument("--no-pe-level", dest="pe_level", action="store_false",
+                    help="skip the leg that times get_metrics + CreateGraph.PE (host records -> networkx graphs) at N=1")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -12,6 +12,6 @@ print("$2", d["ms_per_step"], "%.4g"%d["value"], "e2e", d["e2e"], "roofline", d[
 print({k: v["ms_per_step"] for k, v in d["kernels"].items()})
 PY
 }
-timeout 900 python bench.py --pe-level > $OUT/bench.json 2> $OUT/bench.err; show $OUT/bench.json packed; tail -3 $OUT/bench.err
+timeout 900 python bench.py > $OUT/bench.json 2> $OUT/bench.err; show $OUT/bench.json packed; tail -3 $OUT/bench.err
 timeout 900 python bench.py --records plain --no-cpu > $OUT/bench_plain.json 2> $OUT/bench_plain.err; show $OUT/bench_plain.json plain; tail -3 $OUT/bench_plain.err
-timeout 900 python bench.py --workload config2 --pe-level > $OUT/bench_config2.json 2> $OUT/bench_config2.err; show $OUT/bench_config2.json config2; tail -3 $OUT/bench_config2.err
+timeout 900 python bench.py --workload config2 > $OUT/bench_config2.json 2> $OUT/bench_config2.err; show $OUT/bench_config2.json config2; tail -3 $OUT/bench_config2.err
