@@ -272,6 +272,26 @@ def pe_level_leg(eng, L, host_cols, lazy):
             "observations": "lazy views (param.lazy_observations)" if lazy else "python lists (as the reference stores them)"}
 
 
+_T0 = time.time()
+
+
+def crumb(msg):
+    """progress line on stderr (rank 0): says where a run was when something outside this program stopped it"""
+    if int(os.environ.get("RANK", "0")) == 0:
+        sys.stderr.write("[bench %6.1fs] %s\n" % (time.time() - _T0, msg))
+        sys.stderr.flush()
+
+
+def arm_watchdog(seconds):
+    """A collective that never completes (a peer died, the fabric hiccuped) blocks inside C where no Python handler runs:
+    let the kernel end the process instead (SIGALRM, default action), so the launcher tears the job down and the GPUs are
+    released within a bounded time."""
+    import signal
+    if seconds > 0:
+        signal.signal(signal.SIGALRM, signal.SIG_DFL)
+        signal.alarm(int(seconds))
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -285,9 +305,11 @@ def run_ours(args):
     args.gpus = world
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    crumb("start: world %d" % world)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
         host_group = dist.new_group(backend="gloo")   # host-side object gathers of the parity leg
+        crumb("process groups up")
     name = args.workload or DEFAULT_WORKLOAD.get(world, "config3")
     W = WORKLOADS[name]
     mult = world if W["weak"] else 1
@@ -300,6 +322,7 @@ def run_ours(args):
     record_bytes = 20 if packed else RECORD_BYTES
     libs = [Library(i, s, n_contigs, world, rank, dev, synth, abi, first_library_rows, legacy_single, packed) for i, s in enumerate(specs)]
     t_gen = time.time() - t_gen
+    crumb("libraries generated (%.1f s)" % t_gen)
     n_rec = sum(L.n_rec for L in libs)
     pairs_this_rank = n_rec / 2.0
 
@@ -342,6 +365,7 @@ def run_ours(args):
     for _ in range(args.warmup):
         sizes = step()
     barrier()
+    crumb("warm-up done")
     launches_warm = eng.kernel_launches()
     sampler = ClockSampler(local_rank)
     sampler.start()
@@ -362,6 +386,7 @@ def run_ours(args):
     for kname, ms in eng.kernel_profile():
         prof.setdefault(kname, []).append(ms)
     eng.set_profiling(True)
+    crumb("timed region done: %.3f ms/step on this rank" % (1e3 * (t1 - t0) / args.steps))
     exchange = None
     if world > 1 and rank == 0:   # NVLink traffic of the timed region (hardware counters of GPU 0) against the exchange's byte model
         nvl1 = nvlink_counters(local_rank)
@@ -512,6 +537,7 @@ def run_ours(args):
                 oracle_lib.build()
             barrier()
         for L in libs:
+            crumb("library %d: e2e / cpu / parity legs" % L.index)
             for k in host:
                 host[k][:L.n_rec].copy_(L.cols[k])
             torch.cuda.synchronize()
@@ -622,6 +648,7 @@ def run_ours(args):
         traceback.print_exc(file=sys.stderr)
         e2e = e2e or {"value": None, "unit": "read-pairs/s", "error": repr(exc)}
 
+    crumb("legs done")
     if rank == 0:
         line = {
             "metric": "read-pairs/s through graph-build+GapEst", "value": value, "unit": "read-pairs/s",
@@ -720,7 +747,9 @@ def main():
     ap.add_argument("--no-libmetrics", action="store_true", help="skip the library-metrics leg")
     ap.add_argument("--no-pe-level", dest="pe_level", action="store_false",
                     help="skip the leg that times get_metrics + CreateGraph.PE (host records -> networkx graphs) at N=1")
+    ap.add_argument("--watchdog", type=int, default=900, help="seconds after which a stuck run ends itself (0: never)")
     args = ap.parse_args()
+    arm_watchdog(args.watchdog)
     if args.impl == "reference":
         run_reference(args)
     else:
