@@ -125,25 +125,6 @@ class ClockSampler(threading.Thread):
                 "samples": len(sm)}
 
 
-def nvlink_counters(index):
-    """(tx_bytes, rx_bytes) summed over the NVLinks of GPU `index` (nvidia-smi nvlink -gt d), None if unavailable"""
-    try:
-        out = subprocess.run(["nvidia-smi", "nvlink", "-gt", "d", "-i", str(index)], capture_output=True, text=True, timeout=20).stdout
-        tx = rx = 0
-        seen = False
-        for line in out.splitlines():
-            f = line.replace(":", " ").split()
-            if "Tx" in f and "KiB" in f:
-                tx += int(f[f.index("KiB") - 1]) * 1024
-                seen = True
-            if "Rx" in f and "KiB" in f:
-                rx += int(f[f.index("KiB") - 1]) * 1024
-                seen = True
-        return (tx, rx) if seen else None
-    except Exception:
-        return None
-
-
 def library_params(abi, orientation, mu, sigma):
     return abi.make_params(orientation=orientation, min_mapq=11, read_len=100.0, mean_ins_size=mu,
                            std_dev_ins_size=sigma, ins_size_threshold=mu + 6 * sigma)
@@ -373,7 +354,6 @@ def run_ours(args):
     prof = {}
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     eng.kernel_profile()   # drop the warm-up launches
-    nvl0 = nvlink_counters(local_rank) if (world > 1 and rank == 0) else None
     barrier()
     t0 = time.perf_counter()
     ev0.record()
@@ -388,12 +368,9 @@ def run_ours(args):
     eng.set_profiling(True)
     crumb("timed region done: %.3f ms/step on this rank" % (1e3 * (t1 - t0) / args.steps))
     exchange = None
-    if world > 1 and rank == 0:   # NVLink traffic of the timed region (hardware counters of GPU 0) against the exchange's byte model
-        nvl1 = nvlink_counters(local_rank)
+    if world > 1 and rank == 0:   # what the exchange puts on NVLink, from the count matrix (`nvidia-smi nvlink -gt d` reports nothing on these boxes)
         exchange = {"model_bytes_out_per_library_rank0": int(getattr(runner, "exchange_bytes_out", 0)),
-                    "model": "4 B (2 x u16) or 8 B per link + 24 B per run + 8 B per fishy key to other ranks; plus NCCL: count matrix, coverage + counter all-reduce",
-                    "nvlink_tx_bytes_per_step": None if not (nvl0 and nvl1) else (nvl1[0] - nvl0[0]) / args.steps,
-                    "nvlink_rx_bytes_per_step": None if not (nvl0 and nvl1) else (nvl1[1] - nvl0[1]) / args.steps}
+                    "model": "4 B (2 x u16) or 8 B per link + 24 B per run + 8 B per fishy key to other ranks; plus NCCL: count matrix, coverage + counter all-reduce"}
     launches_timed = eng.kernel_launches() - launches_warm   # kernels of this library inside the timed region
     # nvidia-smi samples every 100 ms and the timed region lasts a few tens of ms: keep the same load running
     # (untimed) until there are enough clock samples under load
