@@ -103,3 +103,24 @@ def test_lazy_observation_lists_are_list_equivalent():
     o = ObsList(np.array([3, 4, 5], np.int32), np.array([10, 20, 30], np.int32))
     assert len(o) == 3 and list(o) == [13, 24, 35] and o[1] == 24 and o == [13, 24, 35] and [a + b for a, b in zip(o, o)] == [26, 48, 70]
     assert all(type(x) is int for x in o)
+
+
+def test_PE_with_a_lognormal_library_scores_through_the_lognormal_branch():
+    """param.lognormal (libmetrics.py:360-390): PE takes the lognormal scoring branch (CreateGraph.py:485-493,523-531)
+    instead of raising; gaps of the long-scaffold edges change, the graph structure does not."""
+    import math
+    from oracle_engine import OracleEngine
+    from besst_b200 import synth
+    batch = synth.make_config("small_mp").to_batch()
+    opts = dict(orientation="rf", mean=3000.0, stddev=500.0, readlen=100)
+    opts.update(threshold=6000.0, minsize=5000.0)   # get_metrics would reset param.lognormal (libmetrics.py:235): skip it
+    normal = helpers.run_dropin(batch, opts, OracleEngine(), run_libmetrics=False)
+    over = dict(lognormal=True, lognormal_sigma=0.17, lognormal_mean=math.log(3000.0) - 0.17 ** 2 / 2,
+                empirical_distribution={x: math.exp(-((x - 3000.0) / 500.0) ** 2 / 2) for x in range(200, 6001)})
+    logn = helpers.run_dropin(batch, opts, OracleEngine(), param_overrides=over, run_libmetrics=False)
+    assert logn["G_prime"] == normal["G_prime"]
+    assert [(e["u"], e["v"], e["nr_links"]) for e in logn["G"]["edges"]] == [(e["u"], e["v"], e["nr_links"]) for e in normal["G"]["edges"]]
+    gaps_n = [e.get("gap") for e in normal["G"]["edges"] if e["nr_links"] is not None]
+    gaps_l = [e.get("gap") for e in logn["G"]["edges"] if e["nr_links"] is not None]
+    assert all(g is not None for g in gaps_l) and sum(a != b for a, b in zip(gaps_n, gaps_l)) > 20
+    assert all("score" in e for e in logn["G"]["edges"] if e["nr_links"] is not None)

@@ -633,3 +633,25 @@ def test_packed_record_column_equals_plain_columns(cuda_engine, config):
     helpers.assert_graph_equal(dev, cuda_engine.graph_build(table, params, sub), label="packed device")
     assert abi.pack_record_columns(np.array([4096]), np.array([0]), np.array([100])) is None
     assert abi.pack_record_columns(np.array([99]), np.array([60]), np.array([5000])) is None
+
+
+def test_resident_contig_tables_switch_without_reupload(cuda_engine):
+    """besst_contigs_select: the libraries of a run keep their contig tables side by side in HBM (runBESST:143-231:
+    library k+1 sees the scaffolds built from library k); switching back and forth gives the results of fresh uploads."""
+    lib, batch, params, first = _setup("small_mp", objects="first")
+    _, _, _, later = _setup("small_mp", objects="later")
+    want_first = cuda_engine.graph_build(first, params, batch)
+    want_later = cuda_engine.graph_build(later, params, batch)
+    assert want_first.n_edges != want_later.n_edges
+    keep = []
+    rec = abi.make_records(batch, keepalive=keep)
+    try:
+        cuda_engine.select_table(1); cuda_engine.set_table(first)
+        cuda_engine.select_table(2); cuda_engine.set_table(later)
+        for slot, want in ((1, want_first), (2, want_later), (1, want_first), (2, want_later)):
+            cuda_engine.select_table(slot)
+            helpers.assert_graph_equal(cuda_engine.fetch(cuda_engine.build(params, rec)), want, label="slot %d" % slot)
+        with pytest.raises(Exception):
+            cuda_engine.select_table(8)
+    finally:
+        cuda_engine.select_table(0)
