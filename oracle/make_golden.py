@@ -106,6 +106,46 @@ def run_case(name):
     return golden
 
 
+SEQUENCE_SEED = 41
+
+
+def sequence_library(kind):
+    """the two libraries of the PE -> MP sequence case: same contigs (same seed), different inserts"""
+    mu, sigma, orient = {"pe": (550.0, 50.0, "fr"), "mp": (3000.0, 500.0, "rf")}[kind]
+    return synth.make_library(400, 200000, orient, mu, sigma, 0.0, seed=SEQUENCE_SEED).to_batch(), dict(orientation=orient, mean=mu, stddev=sigma, readlen=100)
+
+
+def run_sequence_case():
+    """Library 2 of a run whose library 1 went through the reference's REAL scaffolding pass: get_metrics + PE +
+    MakeScaffolds.Algorithm (runBESST:168-199) on a PE library, then the golden of get_metrics + PE of an MP library that
+    starts from the scaffolds that pass built (CleanObjects :788-810, multi-contig PosDir cases :1031-1048).  The state
+    between the two libraries is stored in the golden, so the test needs no reference."""
+    import io
+    import numpy as np
+    ref = ref_harness.load_reference()
+    import BESST.MakeScaffolds as MS
+    import BESST.lp_solve as lps
+    for name in ("Inf", "NaN"):   # numpy 2 dropped the aliases lp_solve.py star-imports
+        if not hasattr(lps, name):
+            setattr(lps, name, getattr(np, name.lower()))
+    lib1, opts1 = sequence_library("pe")
+    lib2, opts2 = sequence_library("mp")
+    out1 = ref_harness.run_reference(lib1, opts1)
+    o = out1["objects"]
+    MS.Algorithm(o["G"], o["G_prime"], o["Contigs"], o["small_contigs"], o["Scaffolds"], o["small_scaffolds"], io.StringIO(), o["param"])
+    snap = helpers.state_snapshot(o["Contigs"], o["Scaffolds"], o["small_contigs"], o["small_scaffolds"], o["param"])
+    assert any(len(members) > 1 for _, members, _ in snap["Scaffolds"])
+    out2 = ref_harness.run_reference(lib2, opts2, state=helpers.state_from_snapshot(snap))
+    objs = out2["objects"]
+    return {
+        "case": "sequence_mp_after_real_pass", "input": "sequence:mp", "options": opts2, "later_seed": None, "state": snap,
+        "G": helpers.graph_signature(objs["G"]), "G_prime": helpers.graph_signature(objs["G_prime"]),
+        "param": helpers.param_signature(objs["param"]),
+        "objects": helpers.object_signature(objs["Contigs"], objs["Scaffolds"], objs["small_contigs"], objs["small_scaffolds"]),
+        "counters": out2["counters"], "n_records": len(lib2),
+    }
+
+
 def main():
     if not ref_harness.reference_available():
         sys.exit("reference tree not found: golden fixtures can only be minted where /root/reference exists")
@@ -118,6 +158,11 @@ def main():
             fh.write(json.dumps(g, sort_keys=True).encode())
         print("%-28s G %5d edges  G_prime %6d edges  %s" % (name, len(g["G"]["edges"]), len(g["G_prime"]["edges"]),
                                                             {k: g["counters"][k] for k in ("count", "duplicates", "fishy")}))
+    g = run_sequence_case()
+    with gzip.GzipFile(os.path.join(GOLDEN, g["case"] + ".json.gz"), "wb", mtime=0) as fh:
+        fh.write(json.dumps(g, sort_keys=True).encode())
+    print("%-28s G %5d edges  G_prime %6d edges  %d multi-contig scaffolds in the state" % (
+        g["case"], len(g["G"]["edges"]), len(g["G_prime"]["edges"]), sum(len(m) > 1 for _, m, _ in g["state"]["Scaffolds"])))
 
 
 if __name__ == "__main__":

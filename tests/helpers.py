@@ -274,3 +274,36 @@ def state_for_later_library(batch, contig_threshold, seed):
     n = max(list(Scaffolds) + list(small_scaffolds)) + 1
     return dict(Contigs=Contigs, Scaffolds=Scaffolds, small_contigs=small_contigs, small_scaffolds=small_scaffolds,
                 scaffold_indexer=n, tot_assembly_length=int(sum(batch.lengths)))
+
+
+def state_snapshot(Contigs, Scaffolds, small_contigs, small_scaffolds, param):
+    """JSON-able picture of the four object dicts (dict ORDER kept: it defines the scaffold numbering and the node
+    insertion order) as a scaffolding pass leaves them for the next library (runBESST:199-231)."""
+    def crows(d):
+        return [[name, c.scaffold, bool(c.direction), int(c.position), int(c.length)] for name, c in d.items()]
+
+    def srows(d):
+        return [[name, [c.name for c in s.contigs], int(s.s_length)] for name, s in d.items()]
+    return {"Contigs": crows(Contigs), "small_contigs": crows(small_contigs), "Scaffolds": srows(Scaffolds),
+            "small_scaffolds": srows(small_scaffolds), "scaffold_indexer": int(param.scaffold_indexer),
+            "tot_assembly_length": int(param.tot_assembly_length)}
+
+
+def state_from_snapshot(snap):
+    """-> the `state` argument of run_dropin / ref_harness.run_reference (fresh objects, BESST's own classes when importable)"""
+    from besst_b200.objects import classes
+    contig_cls, scaffold_cls = classes()
+    objs = {}
+    out = {"Contigs": {}, "small_contigs": {}, "Scaffolds": {}, "small_scaffolds": {}}
+    for key in ("Contigs", "small_contigs"):
+        for name, scaf, direction, position, length in snap[key]:
+            c = contig_cls(name, contig_scaffold=scaf, contig_direction=direction, contig_position=position, contig_length=length)
+            c.sequence = FakeSeq(length)
+            objs[name] = c
+            out[key][name] = c
+    for key in ("Scaffolds", "small_scaffolds"):
+        for name, members, s_length in snap[key]:
+            out[key][name] = scaffold_cls(name, [objs[m] for m in members], s_length)
+    out["scaffold_indexer"] = snap["scaffold_indexer"]
+    out["tot_assembly_length"] = snap["tot_assembly_length"]
+    return out

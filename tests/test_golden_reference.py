@@ -40,7 +40,10 @@ _inputs = {}
 
 def load_input(name):
     if name not in _inputs:
-        if name == "testset1_full":
+        if name.startswith("sequence:"):   # the libraries of the PE -> MP sequence case (oracle/make_golden.py:sequence_library)
+            mu, sigma, orient = {"pe": (550.0, 50.0, "fr"), "mp": (3000.0, 500.0, "rf")}[name.split(":")[1]]
+            _inputs[name] = synth.make_library(400, 200000, orient, mu, sigma, 0.0, seed=41).to_batch()
+        elif name == "testset1_full":
             _inputs[name] = RecordBatch.load(os.path.join(GOLDEN, "testset1_full.npz"))
         elif name in ("testset1", "testset2"):
             _inputs[name] = RecordBatch.load(os.path.join(GOLDEN, name + "_head.npz"))
@@ -68,7 +71,9 @@ def check_case(case, engine):
     assert len(batch) == g["n_records"]
     opts = g["options"]
     state = None
-    if g["later_seed"] is not None:
+    if g.get("state") is not None:     # the state a REAL scaffolding pass of the reference left behind
+        state = helpers.state_from_snapshot(g["state"])
+    elif g["later_seed"] is not None:
         state = helpers.state_for_later_library(batch, contig_threshold_for(opts), g["later_seed"])
     out = helpers.run_dropin(batch, opts, engine, state=state)
     helpers.assert_param_equal(out["param"], g["param"], label=case)
