@@ -425,7 +425,7 @@ def PE(Contigs, Scaffolds, Information, C_dict, param, small_contigs, small_scaf
 
 def _PE(Contigs, Scaffolds, Information, C_dict, param, small_contigs, small_scaffolds, bam_file, engine=None):
     from .csr_post import CsrGraphs
-    bam_file = as_file(bam_file)   # a path: decoded once by the native ingest library (shared with get_metrics)
+    bam_file = as_file(bam_file, engine)   # a path: decoded once by the native ingest library (shared with get_metrics)
     print('Parsing BAM file...', file=Information)
     if param.first_lib:
         start = time()

@@ -18,7 +18,9 @@ EXPORTS = ["besst_abi_version", "besst_create", "besst_destroy", "besst_last_err
            "besst_gapest_batch", "besst_last_timing", "besst_kernel_launches", "besst_set_profiling",
            "besst_kernel_profile", "besst_links_partials_device", "besst_links_fetch", "besst_links_partition",
            "besst_trsk_sd_batch", "besst_set_stream", "besst_graph_view", "besst_links_group", "besst_runs_route",
-           "besst_runs_pack", "besst_runs_to_graph", "besst_runs_pack_peer", "besst_gapest_func_batch", "besst_runs_obs_bytes", "besst_contigs_select", "besst_csr_prune_dense", "besst_gapest_lognormal_batch", "besst_exchange_prepare"]
+           "besst_runs_pack", "besst_runs_to_graph", "besst_runs_pack_peer", "besst_gapest_func_batch", "besst_runs_obs_bytes", "besst_contigs_select", "besst_csr_prune_dense", "besst_gapest_lognormal_batch", "besst_exchange_prepare",
+           "besst_bam_ingest", "besst_bam_ingest_n_refs", "besst_bam_ingest_ref_name", "besst_bam_ingest_ref_length",
+           "besst_bam_ingest_head", "besst_device_read"]
 
 _lib = None
 
@@ -80,6 +82,16 @@ def load():
     L.besst_gapest_func_batch.argtypes = [vp, C.POINTER(abi.LibParams), vp, vp, vp, i64, vp]
     L.besst_runs_to_graph.argtypes = [vp, C.POINTER(abi.LibParams), vp, i64, vp, i64, i32, i32, vp, vp, vp, vp, i64,
                                       C.POINTER(abi.GraphSizes)]
+    L.besst_bam_ingest.argtypes = [vp, C.c_char_p, i64, i32, C.POINTER(abi.Records), C.POINTER(abi.BamIngestStats)]
+    L.besst_bam_ingest_n_refs.restype = i64
+    L.besst_bam_ingest_n_refs.argtypes = [vp]
+    L.besst_bam_ingest_ref_name.restype = C.c_char_p
+    L.besst_bam_ingest_ref_name.argtypes = [vp, i64]
+    L.besst_bam_ingest_ref_length.restype = i64
+    L.besst_bam_ingest_ref_length.argtypes = [vp, i64]
+    L.besst_bam_ingest_head.restype = i64
+    L.besst_bam_ingest_head.argtypes = [vp, vp, vp, i64]
+    L.besst_device_read.argtypes = [vp, vp, vp, i64]
     if L.besst_abi_version() != abi.ABI_VERSION:
         raise BesstLibraryError("ABI version mismatch: library %d, binding %d" % (L.besst_abi_version(), abi.ABI_VERSION))
     _lib = L

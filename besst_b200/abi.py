@@ -8,7 +8,7 @@ from dataclasses import dataclass
 
 import numpy as np
 
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 CTG_ABSENT, CTG_LARGE, CTG_SMALL = 0, 1, 2
 ORIENT_FR, ORIENT_RF = 0, 1
@@ -54,6 +54,17 @@ class LibParams(C.Structure):
                 ("extend_paths", C.c_int32), ("no_score", C.c_int32), ("erf_variant", C.c_int32),
                 ("read_len", C.c_double), ("mean_ins_size", C.c_double), ("std_dev_ins_size", C.c_double),
                 ("ins_size_threshold", C.c_double), ("halo_prev_obs1", C.c_int32), ("halo_prev_obs2", C.c_int32)]
+
+
+class BamIngestStats(C.Structure):
+    """besst_bam_ingest_stats (include/besst_b200.h)"""
+    _fields_ = [("compressed_bytes", C.c_int64), ("uncompressed_bytes", C.c_int64), ("blocks", C.c_int64),
+                ("records", C.c_int64), ("windows", C.c_int64), ("rescans", C.c_int64), ("seconds_total", C.c_double),
+                ("seconds_read", C.c_double), ("ms_inflate", C.c_float), ("ms_scan", C.c_float), ("ms_decode", C.c_float),
+                ("crc_checked", C.c_int32)]
+
+
+BAM_NO_CRC, BAM_BLIND_SEEDS = 1, 2
 
 
 class GraphSizes(C.Structure):
@@ -147,6 +158,8 @@ def graph_result(out, arrays):
 def make_records(batch_or_arrays, on_device=False, keepalive=None):
     """Fill a Records struct from a RecordBatch (host numpy) or from a dict of
     raw device pointers (`{name: int_ptr, 'n': N}`) when on_device."""
+    if hasattr(batch_or_arrays, "abi_records"):   # a DeviceRecordBatch: columns the engine already holds in HBM
+        return batch_or_arrays.abi_records
     r = Records()
     if on_device:
         r.n = int(batch_or_arrays["n"])

@@ -256,3 +256,77 @@ def stream_bam_native(path, on_window, threads=0, max_records=None, head_records
     stats = {k: getattr(st, k) for k, _ in BamStats._fields_}
     stats["stopped"] = stopped   # on_window returned a true value before the end of the file
     return stats
+
+
+_REC_DTYPE = np.dtype([("bs", "<i4"), ("tid", "<i4"), ("pos", "<i4"), ("l_name", "u1"), ("mapq", "u1"), ("bin", "<u2"),
+                       ("n_cig", "<u2"), ("flag", "<u2"), ("l_seq", "<i4"), ("mtid", "<i4"), ("mpos", "<i4"), ("tlen", "<i4"),
+                       ("name", "S12"), ("cig", "<u4", (2,)), ("seq", "u1", (50,)), ("qual", "u1", (100,))])
+BGZF_MAX_INPUT = 0xff00   # htslib's BGZF_BLOCK_SIZE: bytes of input per block
+
+
+def bgzf_block(data, level=6):
+    import zlib
+    comp = zlib.compressobj(level, zlib.DEFLATED, -15)
+    c = comp.compress(data) + comp.flush()
+    bsize = 12 + 6 + len(c) + 8
+    hdr = b"\x1f\x8b\x08\x04" + b"\0\0\0\0" + b"\0\xff" + struct.pack("<H", 6) + b"BC" + struct.pack("<HH", 2, bsize - 1)
+    return hdr + c + struct.pack("<II", zlib.crc32(data) & 0xffffffff, len(data))
+
+
+def write_bam_columns(path, batch, level=1, style="htslib", seed=0, chunk_records=1 << 18, threads=0):
+    """RecordBatch -> sorted BAM file, vectorised (bench / test tooling: the synthetic libraries as FILES for the ingest
+    paths).  Every record is 206 bytes: 100 bases of random sequence, skewed random qualities (a realistic literal / match
+    mix: the file compresses about 3x like sequencer output), a two-operation CIGAR whose soft clip carries qlen
+    (`(100 - qlen)S qlen M`, or `aM bM` without clipping), read name r<ordinal>.  style 'htslib': no record is split
+    across BGZF blocks (bgzf_flush_try); 'packed': blocks are cut every 65280 bytes wherever that falls (htsjdk)."""
+    n = len(batch)
+    text = b"@HD\tVN:1.0\tSO:coordinate\n"
+    head = b"BAM\x01" + struct.pack("<i", len(text)) + text + struct.pack("<i", len(batch.references))
+    parts = [head]
+    for name, ln in zip(batch.references, batch.lengths):
+        nm = name.encode() + b"\0"
+        parts.append(struct.pack("<i", len(nm)) + nm + struct.pack("<i", int(ln)))
+    head = b"".join(parts)
+    rng = np.random.default_rng(seed)
+    qual_levels = np.array([2, 11, 25, 37, 37, 37, 37, 37], np.uint8)
+    rs = _REC_DTYPE.itemsize
+    per_block = BGZF_MAX_INPUT // rs
+    from concurrent.futures import ThreadPoolExecutor
+    import os as _os
+    pool = ThreadPoolExecutor(threads or min(32, _os.cpu_count() or 1))   # zlib releases the GIL: blocks compress in parallel
+
+    def emit(fh, payloads):
+        for blk in pool.map(lambda d: bgzf_block(d, level), payloads):
+            fh.write(blk)
+    with open(path, "wb") as fh:
+        for o in range(0, len(head), BGZF_MAX_INPUT):   # htslib flushes after the header: records start a fresh block
+            fh.write(bgzf_block(head[o:o + BGZF_MAX_INPUT], level))
+        pend = b""
+        for r0 in range(0, n, chunk_records):
+            r1 = min(n, r0 + chunk_records)
+            m = r1 - r0
+            rec = np.zeros(m, _REC_DTYPE)
+            rec["bs"] = rs - 4
+            for f in ("tid", "pos", "mapq", "flag", "mtid", "mpos", "tlen"):
+                rec[f] = getattr(batch, f)[r0:r1]
+            rec["l_name"], rec["bin"], rec["n_cig"], rec["l_seq"] = 12, 4680, 2, 100
+            rec["name"] = np.char.add("r", np.char.zfill(np.arange(r0, r1).astype("U10"), 10)).astype("S12")
+            q = np.clip(batch.qlen[r0:r1].astype(np.int64), 0, 100)
+            clip = 100 - q
+            rec["cig"][:, 0] = np.where(clip > 0, (clip << 4) | 4, ((q // 2) << 4) | 0)
+            rec["cig"][:, 1] = np.where(clip > 0, (q << 4) | 0, ((q - q // 2) << 4) | 0)
+            rec["seq"] = rng.integers(0, 4, (m, 50), dtype=np.uint8) * 17 % 9 * 16 + (1 << rng.integers(0, 4, (m, 50), dtype=np.uint8))
+            rec["qual"] = qual_levels[rng.integers(0, 8, (m, 100), dtype=np.uint8)]
+            raw = rec.tobytes()
+            if style == "htslib":
+                step = per_block * rs
+                emit(fh, [raw[o:o + step] for o in range(0, len(raw), step)])
+            else:
+                raw = pend + raw
+                full = len(raw) // BGZF_MAX_INPUT * BGZF_MAX_INPUT
+                emit(fh, [raw[o:o + BGZF_MAX_INPUT] for o in range(0, full, BGZF_MAX_INPUT)])
+                pend = raw[full:]
+        if pend:
+            fh.write(bgzf_block(pend, level))
+        fh.write(bgzf_block(b"", level))   # EOF marker
+    pool.shutdown()

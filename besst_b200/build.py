@@ -13,7 +13,7 @@ ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
 # per-file extra flags: the scoring math must round like the reference (no FMA contraction)
 SOURCES = [("besst_api.cu", []), ("besst_links.cu", []), ("besst_sort.cu", []),
-           ("besst_edges.cu", ["-fmad=false"]), ("besst_metrics.cu", [])]
+           ("besst_edges.cu", ["-fmad=false"]), ("besst_metrics.cu", []), ("besst_bamdev.cu", [])]
 
 
 BAMIO_SO = os.path.join(HERE, "libbesst_bamio.so")
@@ -33,6 +33,23 @@ def build_bamio(force=False):
     return BAMIO_SO
 
 
+HOSTCHECK_SO = os.path.join(HERE, "libbesst_bgzf_hostcheck.so")
+
+
+def build_hostcheck(force=False):
+    """TEST TOOLING: the device ingest's inflate / CRC / record scan / window loop compiled for the host (lane-serial),
+    so the CPU suite can check the code the GPU runs against zlib.  No product path loads it."""
+    deps = [os.path.join(CSRC, f) for f in ("bgzf_hostcheck.cpp", "bgzf_core.cuh", "bam_ingest.hpp")]
+    if force or _stale(HOSTCHECK_SO, deps):
+        cxx = os.environ.get("CXX", "g++")
+        cmd = [cxx, "-O2", "-std=c++17", "-shared", "-fPIC", "-Wall", "-Wextra", "-o", HOSTCHECK_SO, deps[0]]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            sys.stderr.write(r.stdout + r.stderr)
+            raise RuntimeError("g++ failed on bgzf_hostcheck.cpp")
+    return HOSTCHECK_SO
+
+
 def _stale(target, deps):
     if not os.path.exists(target):
         return True
@@ -42,7 +59,8 @@ def _stale(target, deps):
 
 def build(force=False, verbose=False):
     nvcc = os.environ.get("NVCC", "nvcc")
-    headers = [os.path.join(CSRC, "besst_internal.cuh"), os.path.join(HERE, "..", "include", "besst_b200.h")]
+    headers = [os.path.join(CSRC, "besst_internal.cuh"), os.path.join(HERE, "..", "include", "besst_b200.h"),
+               os.path.join(CSRC, "bgzf_core.cuh"), os.path.join(CSRC, "bam_ingest.hpp")]
     objdir = os.path.join(CSRC, "_obj")
     os.makedirs(objdir, exist_ok=True)
     objs, log = [], []
@@ -68,6 +86,7 @@ def build(force=False, verbose=False):
     with open(os.path.join(objdir, "ptxas.log"), "a") as fh:
         fh.write("".join(log))
     build_bamio(force)
+    build_hostcheck(force)
     return SO
 
 

@@ -47,6 +47,7 @@ extern "C" void besst_destroy(besst_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    besst_bamdev_release(ctx);
     DBuf* bufs[] = {&ctx->rows, &ctx->rows_packed, &ctx->scratch_tuples, &ctx->block_tile0, &ctx->tile_aggs, &ctx->part_state, &ctx->scaf_len, &ctx->rec_flag, &ctx->rec_mapq, &ctx->rec_packed, &ctx->tuples, &ctx->fishy_keys, &ctx->aligned,
                     &ctx->tile_state, &ctx->misc, &ctx->key_a, &ctx->key_b, &ctx->idx_a, &ctx->idx_b, &ctx->hist,
                     &ctx->sort_state, &ctx->fishy_sorted, &ctx->fishy_tmp, &ctx->heads, &ctx->block_sums, &ctx->e_u, &ctx->e_v,

@@ -85,8 +85,11 @@ struct ScoreConsts {
     int erf_variant;
 };
 
+struct BesstBamIngest;   // besst_bamdev.cu: columns and window buffers of besst_bam_ingest
+
 struct besst_ctx {
     int device = 0;
+    BesstBamIngest* ingest = nullptr;
     int sm_count = 148;
     cudaStream_t stream = nullptr;      // the stream all work is ordered on
     cudaStream_t own_stream = nullptr;  // created by besst_create
@@ -167,6 +170,8 @@ __device__ __forceinline__ unsigned int besst_edge_dest(unsigned int u, unsigned
     return (unsigned int)(x % (unsigned long long)world);
 }
 #endif
+
+void besst_bamdev_release(besst_ctx* ctx);
 
 // ---- launchers (one per translation unit) ----------------------------------
 // links: records -> accepted link tuples (BAM order), coverage, fishy keys, counters

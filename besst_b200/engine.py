@@ -212,6 +212,33 @@ class CudaEngine(object):
                                                  int(n_fishy), C.byref(sizes)), "besst_links_to_graph")
         return sizes
 
+    # -- BAM ingest on the device -----------------------------------------------------------
+    def ingest_bam(self, path, head_records=1000, check_crc=True, blind_seeds=False):
+        """BAM file -> DeviceRecordBatch: BGZF inflate and record decode on the GPU, the columns stay in HBM (owned by the
+        engine, valid until the next ingest_bam / close).  Pass the batch to libmetrics / graph_build like a RecordBatch."""
+        import os
+        from .records import DeviceRecordBatch
+        rec, st = abi.Records(), abi.BamIngestStats()
+        flags = (0 if check_crc else abi.BAM_NO_CRC) | (abi.BAM_BLIND_SEEDS if blind_seeds else 0)
+        self._check(self._L.besst_bam_ingest(self._ctx, os.fsencode(path), int(head_records), flags, C.byref(rec), C.byref(st)),
+                    "besst_bam_ingest")
+        n_ref = int(self._L.besst_bam_ingest_n_refs(self._ctx))
+        references = [self._L.besst_bam_ingest_ref_name(self._ctx, i).decode("ascii") for i in range(n_ref)]
+        lengths = [int(self._L.besst_bam_ingest_ref_length(self._ctx, i)) for i in range(n_ref)]
+        nh = min(int(rec.n), int(head_records))
+        rlen, alen = np.zeros(nh, np.int32), np.zeros(nh, np.int32)
+        got = self._L.besst_bam_ingest_head(self._ctx, rlen.ctypes.data, alen.ctypes.data, nh)
+        if got != nh:
+            raise BesstLibraryError("besst_bam_ingest_head returned %d, expected %d" % (got, nh))
+        return DeviceRecordBatch(self, rec, references, lengths, rlen, alen, {k: getattr(st, k) for k, _ in abi.BamIngestStats._fields_})
+
+    def device_read(self, ptr, count, dtype):
+        """numpy copy of `count` elements at device address `ptr` (columns the engine owns)."""
+        out = np.empty(int(count), dtype=dtype)
+        if count:
+            self._check(self._L.besst_device_read(self._ctx, ptr, out.ctypes.data, out.nbytes), "besst_device_read")
+        return out
+
     # -- library metrics ------------------------------------------------------------------
     def libmetrics(self, rows, params, batch, ref_lengths, want_isize, cap=1 << 20, records=None):
         """-> (rc, abi.LibMetricsOut, adjusted_distribution).  rc == 1: fewer than
@@ -295,7 +322,8 @@ class CudaEngine(object):
 
 KERNEL_NAMES = ["k_extract_links", "k_radix_hist", "k_radix_scan_hist", "k_radix_sweep", "k_heads", "k_edge_reduce",
                 "k_score_keys", "k_fishy_rekey", "k_metrics", "k_gapest", "k_tile_scan", "k_compact_tuples",
-                "k_partition", "k_ks_eval", "k_ks_sort", "k_group_blocks", "k_runs", "k_ks_block"]
+                "k_partition", "k_ks_eval", "k_ks_sort", "k_group_blocks", "k_runs", "k_ks_block", "k_bgzf_inflate", "k_bam_scan",
+                "k_bam_decode"]
 
 _default = None
 

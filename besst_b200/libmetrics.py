@@ -69,7 +69,7 @@ def metric_rows(lengths):
 
 
 def get_metrics(bam_file, param, Information, engine=None):
-    bam_file = as_file(bam_file)   # a path: decoded once by the native ingest library
+    bam_file = as_file(bam_file, engine)   # a path: decoded once by the native ingest library
     cont_names = bam_file.references
     cont_lengths = [int(x) for x in bam_file.lengths]
     param.lognormal = False

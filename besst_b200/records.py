@@ -150,6 +150,50 @@ def from_alignments(reads, references, lengths):
                        alen=np.asarray(cols.pop("alen"), np.int32), **cols)
 
 
+class DeviceRecordBatch(object):
+    """Record columns resident in HBM, as the device BAM ingest leaves them (CudaEngine.ingest_bam /
+    besst_bam_ingest): the engine's entry points take it wherever they take a RecordBatch (abi.make_records hands
+    out `abi_records`, device pointers with on_device = 1).  Host side: the header tables and rlen / alen of the first
+    records (all that libmetrics.py:246-266 reads).  The columns belong to the engine and are valid until its next
+    ingest_bam / close; to_host() copies them out (tests, the multi-GPU slicing)."""
+
+    def __init__(self, engine, abi_records, references, lengths, rlen, alen, stats):
+        self.engine = engine
+        self.abi_records = abi_records
+        self.references = list(references)
+        self.lengths = list(lengths)
+        self.rlen, self.alen = rlen, alen
+        self.stats = stats
+
+    def __len__(self):
+        return int(self.abi_records.n)
+
+    def to_host(self):
+        r, n = self.abi_records, len(self)
+        cols = {name: self.engine.device_read(getattr(r, name), n, dt) for name, dt in _DEVICE_FIELDS}
+        packed = self.engine.device_read(r.packed, n, np.uint32) if r.packed else None
+        rlen, alen = np.zeros(n, np.int32), np.zeros(n, np.int32)
+        rlen[:self.rlen.shape[0]] = self.rlen
+        alen[:self.alen.shape[0]] = self.alen
+        return RecordBatch(references=self.references, lengths=self.lengths, rlen=rlen, alen=alen, packed=packed, **cols)
+
+
+def ingest_mode():
+    """'device' (BGZF inflate + decode on the GPU, columns stay in HBM) or 'host' (libbesst_bamio.so, host threads):
+    how the entry points turn a BAM path into records.  BESST_B200_INGEST overrides; under a process group (one
+    library range-partitioned over ranks) the host reader is used, the ranks slice its columns."""
+    import os
+    mode = os.environ.get("BESST_B200_INGEST", DEFAULT_INGEST)
+    if mode not in ("device", "host"):
+        raise ValueError("BESST_B200_INGEST must be 'device' or 'host', not %r" % mode)
+    if mode == "device" and int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        return "host"
+    return mode
+
+
+DEFAULT_INGEST = "host"
+
+
 class BatchFile(object):
     """Minimal `pysam.Samfile` look-alike over a decoded RecordBatch: what the
     drop-in entry points read from their `bam_file` argument (`references`,
@@ -173,10 +217,11 @@ class BatchFile(object):
 _open_cache = {}
 
 
-def as_file(bam_file):
+def as_file(bam_file, engine=None):
     """What the drop-in entry points do with their `bam_file` argument first: a path becomes a
-    BatchFile over the natively decoded records (libbesst_bamio.so) -- cached per path, because
-    runBESST hands the same library to get_metrics and then to PE -- anything else passes through."""
+    BatchFile over the decoded records -- on the device (CudaEngine.ingest_bam) or by the host-thread
+    reader (libbesst_bamio.so), see ingest_mode -- cached per path, because runBESST hands the same
+    library to get_metrics and then to PE -- anything else passes through."""
     if isinstance(bam_file, (str, bytes)) or hasattr(bam_file, "__fspath__"):
         import os
         key = os.path.abspath(os.fsdecode(bam_file))
@@ -184,9 +229,15 @@ def as_file(bam_file):
         stamp = (st.st_size, st.st_mtime_ns)
         hit = _open_cache.get(key)
         if hit is None or hit[0] != stamp:
-            from .bamio import read_bam_native
             _open_cache.clear()   # one library at a time, like the reference's loop (runBESST:143-231)
-            hit = (stamp, BatchFile(read_bam_native(key)))
+            if ingest_mode() == "device":
+                if engine is None:
+                    from .engine import default_engine
+                    engine = default_engine()
+                hit = (stamp, BatchFile(engine.ingest_bam(key)))
+            else:
+                from .bamio import read_bam_native
+                hit = (stamp, BatchFile(read_bam_native(key)))
             _open_cache[key] = hit
         return hit[1]
     return bam_file
@@ -195,7 +246,7 @@ def as_file(bam_file):
 def as_batch(bam_file):
     """RecordBatch behind a `bam_file` argument: a RecordBatch, a path to a BAM file (decoded by
     libbesst_bamio.so), anything carrying `.record_batch`, or a pysam-like iterable of AlignedRead."""
-    if isinstance(bam_file, RecordBatch):
+    if isinstance(bam_file, (RecordBatch, DeviceRecordBatch)):
         return bam_file
     if isinstance(bam_file, (str, bytes)) or hasattr(bam_file, "__fspath__"):   # a path: native threaded ingest
         from .bamio import read_bam_native

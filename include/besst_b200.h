@@ -39,6 +39,8 @@
  *                            merges runs into its share of the CSR
  *   besst_links_partition /  the tuple-level variant of the same exchange (fallback for
  *   besst_links_to_graph     link streams without local order; any caller-made tuple array)
+ *   besst_bam_ingest         the pysam.Samfile iteration itself (runBESST:162, libmetrics.py:63,257,293,
+ *                            CreateGraph.py:111): BGZF inflate + record decode on the GPU, columns left in HBM
  *
  * Conventions: plain C; all pointers are caller-owned for the duration of the
  * call; nothing is retained after return except inside the ctx; return 0 on
@@ -55,7 +57,7 @@
 extern "C" {
 #endif
 
-#define BESST_ABI_VERSION 4
+#define BESST_ABI_VERSION 5
 
 #define BESST_OK 0
 #define BESST_E_INVALID -1  /* bad argument */
@@ -354,6 +356,37 @@ int besst_trsk_sd_batch(besst_ctx* ctx, const besst_lib_params* params, const do
 int64_t besst_csr_prune_dense(int64_t n_weak, const uint32_t* weak_u, const uint32_t* weak_v, int32_t* degree,
                               int32_t min_neighbours, uint8_t* dropped);
 
+/* ---- BAM ingest on the device ----------------------------------------------------------------
+ * Sorted BAM file -> the record columns of besst_records RESIDENT IN HBM.  The file crosses PCIe compressed (windows of
+ * BGZF blocks, double-buffered against the kernels); every BGZF block is inflated by one warp, its CRC-32 checked, record
+ * boundaries are found per block and verified on the host in O(blocks), the fixed-core fields and the CIGAR-derived
+ * lengths (pysam 0.8.4's qlen) are decoded straight into the columns.  `out` receives DEVICE pointers
+ * (on_device = 1; packed is NULL when a record does not fit the packed column) owned by the ctx and valid until the next
+ * besst_bam_ingest / besst_destroy: hand it to besst_libmetrics / besst_graph_build as is -- no record visits host memory.
+ * Handles records that straddle BGZF blocks and windows (any BGZF writer, not only htslib's).  There is no host fallback:
+ * without a device the call fails like every other entry point; the host-thread ingest is libbesst_bamio.so. */
+#define BESST_BAM_NO_CRC 1       /* flags: skip the CRC-32 check of the inflated blocks */
+#define BESST_BAM_BLIND_SEEDS 2  /* flags (testing): seed every block's record hop at its first byte, so that the host
+                                    verification has to repair every block that starts inside a record */
+typedef struct besst_bam_ingest_stats {
+    int64_t compressed_bytes, uncompressed_bytes, blocks, records, windows;
+    int64_t rescans;          /* blocks whose seed the verification rejected and re-hopped */
+    double seconds_total;     /* host wall clock of the call */
+    double seconds_read;      /* of which: file -> pinned staging (host threads) */
+    float ms_inflate, ms_scan, ms_decode;   /* device time (CUDA events), summed over the windows */
+    int32_t crc_checked;
+} besst_bam_ingest_stats;
+int besst_bam_ingest(besst_ctx* ctx, const char* path, int64_t head_records, int32_t flags, besst_records* out,
+                     besst_bam_ingest_stats* stats /* may be NULL */);
+/* header of the last ingested file, and rlen (l_seq) / alen (reference span) of its first head_records records (what
+ * libmetrics.py:246-266 reads); besst_bam_ingest_head returns how many were written (<= cap) */
+int64_t besst_bam_ingest_n_refs(besst_ctx* ctx);
+const char* besst_bam_ingest_ref_name(besst_ctx* ctx, int64_t i);
+int64_t besst_bam_ingest_ref_length(besst_ctx* ctx, int64_t i);
+int64_t besst_bam_ingest_head(besst_ctx* ctx, int32_t* rlen, int32_t* alen, int64_t cap);
+/* device -> host copy on the ctx's stream (tests and debugging: read back columns the ctx owns) */
+int besst_device_read(besst_ctx* ctx, const void* device_ptr, void* host_ptr, int64_t bytes);
+
 /* run all work of this ctx on a caller-owned CUDA stream (a cudaStream_t passed as void*; NULL
  * restores the ctx's own non-blocking stream; pass cudaStreamLegacy (0x1) for the legacy default stream).  Lets a host framework order the library's kernels with its own
  * work (NCCL collectives, CUDA-event timing) without device-wide synchronisation. */
@@ -387,7 +420,10 @@ int besst_kernel_launches(besst_ctx* ctx, int64_t* n_launches);
 #define BESST_K_GROUP 15       /* k_group_blocks: block-local grouping of the tuple stream (K3') */
 #define BESST_K_RUNS 16        /* k_run_count/k_scan_blocks64/k_run_write: heads and offsets over the sorted runs (K3') */
 #define BESST_K_KS_BLOCK 17    /* k_ks_block: in-block sort + KS evaluation of the edges with <= 2048 links (K5') */
-#define BESST_N_KERNEL_IDS 18
+#define BESST_K_BAM_INFLATE 18 /* k_bgzf_inflate: one warp per BGZF block, raw deflate + CRC-32 (besst_bam_ingest) */
+#define BESST_K_BAM_SCAN 19    /* k_bam_scan / k_bam_rescan: record boundaries per BGZF block */
+#define BESST_K_BAM_DECODE 20  /* k_bam_decode: fixed core + CIGAR lengths -> record columns */
+#define BESST_N_KERNEL_IDS 21
 /* enabled: 0 off, 1 the launches of the LAST build, 2 accumulate over builds until besst_kernel_profile reads (and clears) them */
 int besst_set_profiling(besst_ctx* ctx, int enabled);
 int besst_kernel_profile(besst_ctx* ctx, int32_t* kernel_ids, float* ms, int32_t cap);
