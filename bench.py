@@ -253,6 +253,67 @@ def pe_level_leg(eng, L, host_cols, lazy):
             "observations": "lazy views (param.lazy_observations)" if lazy else "python lists (as the reference stores them)"}
 
 
+def ingest_leg(eng, pairs):
+    """FILE -> graph (N=1): a synthetic MP library of `pairs` read pairs written as a sorted BAM (write_bam_columns:
+    206-byte records, htslib block layout, compresses ~2.3x), then
+      device         besst_bam_ingest: compressed file -> PCIe -> one warp per BGZF block -> record columns in HBM
+      host_threads   libbesst_bamio.so (zlib on every host core) -> host columns         [the round-1 ingest]
+      file_to_graph  device ingest + besst_libmetrics + besst_graph_build + result views: no record in host memory
+    Wall clock of the calls (the file sits in the page cache on every leg: disk speed is not measured)."""
+    import tempfile
+    from besst_b200 import abi, bamio, synth
+    from besst_b200.contig_table import first_library_rows
+    from besst_b200.libmetrics import metric_rows
+    lib = synth.make_library(max(50, pairs // 2000), pairs, "rf", 3000.0, 500.0, 0.0, seed=20261099)
+    batch = lib.to_batch()
+    n = len(batch)
+    path = os.path.join(tempfile.mkdtemp(prefix="besst_bench_"), "library.bam")
+    t0 = time.perf_counter()
+    bamio.write_bam_columns(path, batch)
+    t_write = time.perf_counter() - t0
+    eng.ingest_bam(path)   # warm-up: page cache, window buffers, column allocation
+    runs = [dict(eng.ingest_bam(path).stats) for _ in range(3)]
+    best = min(runs, key=lambda r: r["seconds_total"])
+    t0 = time.perf_counter()
+    nat = bamio.read_bam_native(path)
+    t_host = time.perf_counter() - t0
+    lengths = np.asarray(batch.lengths, dtype=np.int64)
+    mrows = metric_rows(lengths)
+    eng.select_table(7)
+
+    def file_to_graph():
+        t0 = time.perf_counter()
+        dev = eng.ingest_bam(path)
+        t1 = time.perf_counter()
+        rc, m, _ = eng.libmetrics(mrows, abi.make_params("rf", 11, 100.0, 0.0, 0.0, 0.0), dev, lengths, True)
+        t2 = time.perf_counter()
+        mu, sd = m.mu_adj, m.sigma_adj
+        rows, n_scaf, n_large = first_library_rows(lengths, mu + 4 * sd)
+        eng.set_contigs(rows, n_scaf, n_large)
+        params = abi.make_params("rf", 11, 100.0, mu, sd, mu + 6 * sd)
+        res = eng.fetch_view(eng.build(params, dev.abi_records))
+        t3 = time.perf_counter()
+        return {"ingest_ms": round(1e3 * (t1 - t0), 2), "libmetrics_ms": round(1e3 * (t2 - t1), 2), "graph_build_fetch_ms": round(1e3 * (t3 - t2), 2),
+                "total_ms": round(1e3 * (t3 - t0), 2), "read_pairs_per_s": n / 2.0 / (t3 - t0), "edges": res.n_edges, "links": res.n_links,
+                "estimated": {"mean_ins_size": mu, "std_dev_ins_size": sd}}
+    file_to_graph()
+    ftg = min((file_to_graph() for _ in range(3)), key=lambda r: r["total_ms"])
+    same = all(np.array_equal(getattr(nat, f), getattr(batch, f)) for f in ("tid", "mtid", "pos", "mpos", "tlen", "qlen", "flag", "mapq"))
+    dev_host = eng.ingest_bam(path).to_host()
+    same_dev = all(np.array_equal(getattr(dev_host, f), getattr(batch, f)) for f in ("tid", "mtid", "pos", "mpos", "tlen", "qlen", "flag", "mapq"))
+    os.remove(path)
+    return {"file": {"records": n, "compressed_MB": round(best["compressed_bytes"] / 1e6, 1), "inflated_MB": round(best["uncompressed_bytes"] / 1e6, 1),
+                     "bgzf_blocks": best["blocks"], "write_s": round(t_write, 2)},
+            "device": {"wall_ms": round(1e3 * best["seconds_total"], 2), "records_per_s": n / best["seconds_total"],
+                       "host_read_ms": round(1e3 * best["seconds_read"], 2), "inflate_ms": round(best["ms_inflate"], 3),
+                       "inflate_GBps_out": round(best["uncompressed_bytes"] / 1e6 / max(best["ms_inflate"], 1e-9), 2),
+                       "scan_ms": round(best["ms_scan"], 3), "decode_ms": round(best["ms_decode"], 3), "windows": best["windows"],
+                       "crc_checked": bool(best["crc_checked"]), "columns_equal_source": bool(same_dev)},
+            "host_threads": {"wall_ms": round(1e3 * t_host, 2), "records_per_s": n / t_host, "threads": int(nat.stats["threads"]),
+                             "columns_equal_source": bool(same)},
+            "file_to_graph": ftg}
+
+
 _T0 = time.time()
 
 
@@ -625,6 +686,17 @@ def run_ours(args):
         traceback.print_exc(file=sys.stderr)
         e2e = e2e or {"value": None, "unit": "read-pairs/s", "error": repr(exc)}
 
+    ingest = None
+    if world == 1 and args.ingest_pairs > 0:
+        crumb("ingest leg")
+        try:
+            ingest = ingest_leg(eng, int(args.ingest_pairs))
+            for Lk in libs:   # the leg used table slot 7 and the current-slot selection
+                eng.select_table(Lk.index)
+        except Exception as exc:
+            import traceback
+            traceback.print_exc(file=sys.stderr)
+            ingest = {"error": repr(exc)}
     crumb("legs done")
     if rank == 0:
         line = {
@@ -648,7 +720,7 @@ def run_ours(args):
             "wall_ms_per_step": round(1e3 * wall / args.steps, 4),
             "timing": "CUDA events on the launching stream (the library runs on torch's current stream), max over ranks",
             "dist_phases_ms": dist_phases, "exchange": exchange,
-            "roofline": roofline, "kernels": kernels, "libmetrics": libmetrics, "pe_level": pe_level, "cpu_baseline": cpu_baseline, "parity": parity,
+            "roofline": roofline, "kernels": kernels, "libmetrics": libmetrics, "pe_level": pe_level, "ingest": ingest, "cpu_baseline": cpu_baseline, "parity": parity,
             "generate_s": round(t_gen, 2), "impl": "ours",
         }
         print(json.dumps(line))
@@ -724,6 +796,8 @@ def main():
     ap.add_argument("--no-libmetrics", action="store_true", help="skip the library-metrics leg")
     ap.add_argument("--no-pe-level", dest="pe_level", action="store_false",
                     help="skip the leg that times get_metrics + CreateGraph.PE (host records -> networkx graphs) at N=1")
+    ap.add_argument("--ingest-pairs", type=int, default=2000000,
+                    help="N=1: read pairs of the BAM file written for the file -> graph leg (0: skip the leg)")
     ap.add_argument("--watchdog", type=int, default=900, help="seconds after which a stuck run ends itself (0: never)")
     args = ap.parse_args()
     arm_watchdog(args.watchdog)

@@ -49,8 +49,8 @@ struct DecodeEntry {     // per block, made by the host verification
 };
 
 struct Options {
-    int64_t window_bytes = 256ll << 20;    // compressed bytes per window
-    int64_t max_inflated = 1536ll << 20;   // inflated bytes per window (offsets are 32-bit)
+    int64_t window_bytes = 512ll << 20;    // compressed bytes per window (~25 k BGZF blocks: 3.5 waves of one warp per block)
+    int64_t max_inflated = 3072ll << 20;   // inflated bytes per window (offsets are 32-bit)
     int64_t carry_max = 4ll << 20;         // longest record tail a window may hand to the next one
     int64_t head_records = 1000;
     bool check_crc = true;

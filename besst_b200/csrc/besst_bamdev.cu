@@ -30,66 +30,87 @@
 
 namespace {
 
-constexpr int INFLATE_WARPS = 8;
+// lanes that work on one BGZF block (tuning knob): with BGZF_GROUP < 32 a warp decodes 32 / BGZF_GROUP blocks at once, the
+// leader lanes of the groups running the serial symbol decode side by side and the placement rounds / CRC using group-wide
+// shuffles.  The kernel is issue-bound (ncu, one block per warp: 71 % SM throughput, 2.85 IPC, 18.4 G warp instructions for
+// 618 MB of output), but sharing issue slots between leaders does NOT pay: measured on a 4.04 M-record file (832 MB
+// inflated), inflate time 30.9 ms with 32 lanes per block, 38.8 / 53.0 ms with 16 / 8 (fewer warps per SM for the same
+// shared-memory footprint: latency-bound), 31.6 / 38.3 / 58.4 ms with 16 / 8 / 4 and the small tables (2^9 / 2^7 entries,
+// 16 blocks per CTA) -- profiles/r02/ingest_variants.md.  One warp per block stays.
+#ifndef BGZF_GROUP
+#define BGZF_GROUP 32
+#endif
+constexpr int GROUP = BGZF_GROUP;
+#ifndef BGZF_BLOCKS_PER_CTA
+#define BGZF_BLOCKS_PER_CTA 8
+#endif
+constexpr int INFLATE_BLOCKS_PER_CTA = BGZF_BLOCKS_PER_CTA;     // BGZF blocks per CTA (3.6 KB of tables each, 5 KB of CRC tables per CTA)
+constexpr int INFLATE_THREADS = INFLATE_BLOCKS_PER_CTA * GROUP;
 constexpr int E_CRC = -10;
+static_assert(GROUP == 32 || GROUP == 16 || GROUP == 8 || GROUP == 4, "BGZF_GROUP");
+static_assert(INFLATE_THREADS % 32 == 0, "whole warps");
 
 // ---- the warp primitives of bgzf::inflate_block on the device -----------------------------------------------------------
 struct DevWarp {
-    int lane;
-    __device__ __forceinline__ bool leader() const { return lane == 0; }
+    int gl;          // lane inside the group
+    unsigned gmask;  // the group's lanes inside the warp
+    int gshift;      // first lane of the group
+    __device__ __forceinline__ int width() const { return GROUP; }
+    __device__ __forceinline__ bool leader() const { return gl == 0; }
     __device__ __forceinline__ int bcast(int v) const {
-        __syncwarp();
-        return __shfl_sync(0xffffffffu, v, 0);
+        __syncwarp(gmask);
+        return __shfl_sync(gmask, v, 0, GROUP);
     }
     // the queue's n symbols -> out[pos ..): literals first (one store per lane), then the matches in queue order, each a
-    // warp-wide copy.  A match may read what an earlier symbol of the same queue wrote (literals are all in place, earlier
+    // group-wide copy.  A match may read what an earlier symbol of the same queue wrote (literals are all in place, earlier
     // matches are complete); with dist < len the source repeats with period dist, all of it in front of the match.
     __device__ __forceinline__ int place(bgzf::WarpTables* T, int n, uint8_t* out, uint32_t pos, uint32_t usize) const {
         uint32_t D = 0, L = 0, lit = 0;
-        if (lane < n) {
-            D = T->q_dist[lane];
-            lit = T->q_len[lane];
+        if (gl < n) {
+            const uint32_t q = T->queue[gl];
+            D = q >> 16;
+            lit = q & 0xffffu;
             L = D ? lit : 1u;
         }
         uint32_t x = L;
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
-            if (lane >= o) x += y;
+        for (int o = 1; o < GROUP; o <<= 1) {
+            const uint32_t y = __shfl_up_sync(gmask, x, o, GROUP);
+            if (gl >= o) x += y;
         }
         const uint32_t P = pos + x - L;
-        const uint32_t total = __shfl_sync(0xffffffffu, x, 31);
-        const bool bad = lane < n && (P + L > usize || D > P);
-        if (__any_sync(0xffffffffu, bad)) return -1;
-        if (lane < n && D == 0) out[P] = (uint8_t)lit;
-        __syncwarp();
-        unsigned m = __ballot_sync(0xffffffffu, lane < n && D != 0);
+        const uint32_t total = __shfl_sync(gmask, x, GROUP - 1, GROUP);
+        const bool bad = gl < n && (P + L > usize || D > P);
+        if (__any_sync(gmask, bad)) return -1;
+        if (gl < n && D == 0) out[P] = (uint8_t)lit;
+        __syncwarp(gmask);
+        unsigned m = (__ballot_sync(gmask, gl < n && D != 0) & gmask) >> gshift;
         while (m) {
             const int s = __ffs(m) - 1;
             m &= m - 1;
-            const uint32_t Ps = __shfl_sync(0xffffffffu, P, s), Ls = __shfl_sync(0xffffffffu, L, s), Ds = __shfl_sync(0xffffffffu, D, s);
+            const uint32_t Ps = __shfl_sync(gmask, P, s, GROUP), Ls = __shfl_sync(gmask, L, s, GROUP), Ds = __shfl_sync(gmask, D, s, GROUP);
             const uint8_t* src = out + Ps - Ds;
             if (Ds >= Ls) {
-                for (uint32_t i = lane; i < Ls; i += 32) out[Ps + i] = src[i];
+                for (uint32_t i = gl; i < Ls; i += GROUP) out[Ps + i] = src[i];
             } else {
-                for (uint32_t i = lane; i < Ls; i += 32) out[Ps + i] = src[i % Ds];
+                for (uint32_t i = gl; i < Ls; i += GROUP) out[Ps + i] = src[i % Ds];
             }
-            __syncwarp();
+            __syncwarp(gmask);
         }
         return (int)total;
     }
     __device__ __forceinline__ void copy_in(uint8_t* dst, const uint8_t* src, uint32_t n) const {
-        for (uint32_t i = lane; i < n; i += 32) dst[i] = src[i];
-        __syncwarp();
+        for (uint32_t i = gl; i < n; i += GROUP) dst[i] = src[i];
+        __syncwarp(gmask);
     }
 };
 
 // err[0] blocks whose inflate failed, err[1] first such block (min), err[2] its code, err[3] CRC mismatches,
 // err[4] records whose name/CIGAR overrun the record, err[5] records that do not fit the packed column
-__global__ void __launch_bounds__(INFLATE_WARPS * 32)
+__global__ void __launch_bounds__(INFLATE_THREADS)
 k_bgzf_inflate(const uint32_t* __restrict__ cwords, const bamingest::BlockEntry* __restrict__ blocks, int n_blocks, uint8_t* ubuf,
                const bgzf::CrcTables* __restrict__ crc_tab, int check_crc, int* err) {
-    __shared__ bgzf::WarpTables tables[INFLATE_WARPS];
+    __shared__ bgzf::WarpTables tables[INFLATE_BLOCKS_PER_CTA];
     __shared__ bgzf::CrcTables crc;
     if (check_crc) {
         const uint32_t* s = reinterpret_cast<const uint32_t*>(crc_tab);
@@ -97,23 +118,32 @@ k_bgzf_inflate(const uint32_t* __restrict__ cwords, const bamingest::BlockEntry*
         for (int i = threadIdx.x; i < (int)(sizeof(bgzf::CrcTables) / 4); i += blockDim.x) d[i] = s[i];
         __syncthreads();
     }
-    const int warp = threadIdx.x >> 5;
-    const int k = blockIdx.x * INFLATE_WARPS + warp;
-    if (k >= n_blocks) return;
-    DevWarp wp{(int)(threadIdx.x & 31)};
+    const int slot = threadIdx.x / GROUP;   // which of the CTA's blocks
+    const int k = blockIdx.x * INFLATE_BLOCKS_PER_CTA + slot;
+    if (k >= n_blocks) return;              // whole groups leave; the others only ever synchronise inside their group
+    const int lane = threadIdx.x & 31;
+    DevWarp wp;
+    wp.gl = lane % GROUP;
+    wp.gshift = lane - wp.gl;
+    wp.gmask = (GROUP == 32 ? 0xffffffffu : ((1u << (GROUP & 31)) - 1u)) << wp.gshift;
     const bamingest::BlockEntry b = blocks[k];
-    int rc = bgzf::inflate_block(wp, cwords, (uint64_t)b.cin, b.clen, ubuf + b.out, b.usize, &tables[warp]);
-    __syncwarp();
+    int rc = bgzf::inflate_block(wp, cwords, (uint64_t)b.cin, b.clen, ubuf + b.out, b.usize, &tables[slot]);
+    __syncwarp(wp.gmask);
     if (rc == 0 && check_crc) {
+        // 32 virtual lanes (one per word of a 128-byte row), 32 / GROUP of them per lane
         const uint32_t* u = reinterpret_cast<const uint32_t*>(ubuf);
         const uint32_t rounds = b.usize / 128;
         uint32_t folded = 0;
         if (rounds) {
-            folded = bgzf::crc_fold_lane(bgzf::crc_lane_rows(&crc, u, b.out, rounds, wp.lane), wp.lane);
 #pragma unroll
-            for (int o = 16; o; o >>= 1) folded ^= __shfl_xor_sync(0xffffffffu, folded, o);
+            for (int v = 0; v < 32 / GROUP; ++v) {
+                const int vl = wp.gl + v * GROUP;
+                folded ^= bgzf::crc_fold_lane(bgzf::crc_lane_rows(&crc, u, b.out, rounds, vl), vl);
+            }
+#pragma unroll
+            for (int o = GROUP / 2; o; o >>= 1) folded ^= __shfl_xor_sync(wp.gmask, folded, o, GROUP);
         }
-        if (wp.lane == 0) {
+        if (wp.gl == 0) {
             uint32_t st = bgzf::crc_with_init(folded, 128ull * rounds);
             st = bgzf::crc_tail(&crc, st, u, b.out + 128ull * rounds, b.usize - 128 * rounds) ^ 0xffffffffu;
             if (st != b.crc) {
@@ -122,7 +152,7 @@ k_bgzf_inflate(const uint32_t* __restrict__ cwords, const bamingest::BlockEntry*
             }
         }
     }
-    if (wp.lane == 0 && rc != 0 && rc != E_CRC) {
+    if (wp.gl == 0 && rc != 0 && rc != E_CRC) {
         atomicAdd(&err[0], 1);
         if (atomicMin(&err[1], k) > k) err[2] = rc;
     }
@@ -329,7 +359,7 @@ struct DevBackend {
         tick(0, &done);
         {
             KTimer kt(ctx, BESST_K_BAM_INFLATE);
-            k_bgzf_inflate<<<(nb + INFLATE_WARPS - 1) / INFLATE_WARPS, INFLATE_WARPS * 32, 0, ctx->stream>>>(
+            k_bgzf_inflate<<<(nb + INFLATE_BLOCKS_PER_CTA - 1) / INFLATE_BLOCKS_PER_CTA, INFLATE_THREADS, 0, ctx->stream>>>(
                 S->cbuf[buf].as<uint32_t>(), S->tbl_d[buf].as<bamingest::BlockEntry>(), nb, S->ubuf[buf].as<uint8_t>(),
                 S->crc_d.as<bgzf::CrcTables>(), check_crc ? 1 : 0, S->err_d.as<int>());
         }

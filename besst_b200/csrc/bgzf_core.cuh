@@ -28,9 +28,15 @@
 
 namespace bgzf {
 
-constexpr int LIT_BITS = 10;    // index bits of the literal/length lookup table
-constexpr int DIST_BITS = 8;    // index bits of the distance lookup table
-constexpr int QUEUE = 32;       // decoded symbols per placement round (one per lane)
+#ifndef BGZF_LIT_BITS
+#define BGZF_LIT_BITS 10
+#endif
+#ifndef BGZF_DIST_BITS
+#define BGZF_DIST_BITS 8
+#endif
+constexpr int LIT_BITS = BGZF_LIT_BITS;     // index bits of the literal/length lookup table
+constexpr int DIST_BITS = BGZF_DIST_BITS;   // index bits of the distance lookup table (>= 7: the code-length code borrows it)
+constexpr int QUEUE = 32;       // capacity of the symbol queue; a placement round takes one symbol per lane of the group
 
 // error codes of inflate_block (negative), 0 = ok
 constexpr int E_BTYPE = -1, E_STORED = -2, E_CODELEN = -3, E_LITCODE = -4, E_DISTCODE = -5, E_SYMBOL = -6, E_OVERRUN = -7,
@@ -44,29 +50,32 @@ struct WarpTables {
     uint16_t dist_sym[32];
     uint16_t lit_cnt[16];               // codes per length
     uint16_t dist_cnt[16];
-    uint16_t q_len[QUEUE];              // queue: literal byte (q_dist == 0) or match length
-    uint16_t q_dist[QUEUE];
+    uint32_t queue[QUEUE];              // literal byte, or match length | distance << 16
     uint8_t lens[320];                  // code lengths while a dynamic header is read
 };
 
 // LSB-first bit reader over 32-bit words (the compressed bytes sit at an arbitrary byte offset of a word-aligned buffer;
-// up to 8 bytes past the end of the stream may be read -- the caller pads its buffer -- and are never interpreted: `used`
-// is checked against the stream length)
+// up to 8 bytes past the end of the stream may be read -- the caller pads its buffer -- and are never interpreted: the
+// bit position is checked against the end of the stream once per queue)
 struct BitReader {
     const uint32_t* w;
     uint32_t next;      // next word to load
     uint64_t buf;
     int nbits;
-    int64_t used, total;
-    BGZF_HD void init(const uint32_t* words, uint64_t byte_off, int64_t n_bytes) {
-        w = words;
+    uint64_t end_bit;   // first bit past the stream, counted from the word base
+    BGZF_HD void seek(uint64_t byte_off) {
         next = (uint32_t)(byte_off >> 2);
         const int skip = (int)(byte_off & 3) * 8;
         buf = (uint64_t)(w[next++] >> skip);
         nbits = 32 - skip;
-        used = 0;
-        total = n_bytes * 8;
     }
+    BGZF_HD void init(const uint32_t* words, uint64_t byte_off, int64_t n_bytes) {
+        w = words;
+        end_bit = (byte_off + (uint64_t)n_bytes) * 8;
+        seek(byte_off);
+    }
+    BGZF_HD uint64_t bit_pos() const { return (uint64_t)next * 32 - (uint64_t)nbits; }
+    BGZF_HD bool overrun() const { return bit_pos() > end_bit; }
     BGZF_HD void refill() {
         if (nbits <= 32) {
             buf |= (uint64_t)w[next++] << nbits;
@@ -77,7 +86,6 @@ struct BitReader {
     BGZF_HD void drop(int n) {
         buf >>= n;
         nbits -= n;
-        used += n;
     }
     BGZF_HD uint32_t bits(int n) {
         const uint32_t v = peek(n);
@@ -205,7 +213,7 @@ BGZF_HD int dynamic_tables(BitReader& br, WarpTables* T) {
             if (i + rep > n) return E_CODELEN;
             while (rep--) T->lens[i++] = (uint8_t)val;
         }
-        if (br.used > br.total) return E_OVERRUN;
+        if (br.overrun()) return E_OVERRUN;
     }
     if (T->lens[256] == 0) return E_CODELEN;   // no end-of-block code
     // the literal/length lengths are lens[0 .. hlit), the distance lengths follow: build the distance code first from a
@@ -217,18 +225,16 @@ BGZF_HD int dynamic_tables(BitReader& br, WarpTables* T) {
     return 0;
 }
 
-// leader lane: decode up to QUEUE symbols into the queue.  *state: 0 more to come, 1 end of block, < 0 error
-BGZF_HD int decode_batch(BitReader& br, WarpTables* T, int* state) {
+// leader lane: decode up to `cap` (<= QUEUE) symbols into the queue.  *state: 0 more to come, 1 end of block, < 0 error
+BGZF_HD int decode_batch(BitReader& br, WarpTables* T, int cap, int* state) {
     int n = 0;
     *state = 0;
-    while (n < QUEUE) {
+    while (n < cap) {
         br.refill();
         const int s = decode_symbol(br, T->lit_lut, LIT_BITS, T->lit_cnt, T->lit_sym);
         if (s < 0) { *state = E_SYMBOL; break; }
         if (s < 256) {
-            T->q_len[n] = (uint16_t)s;
-            T->q_dist[n] = 0;
-            ++n;
+            T->queue[n++] = (uint32_t)s;
             continue;
         }
         if (s == 256) { *state = 1; break; }
@@ -250,16 +256,15 @@ BGZF_HD int decode_batch(BitReader& br, WarpTables* T, int* state) {
             const int eb = (d >> 1) - 1;
             dist = 1 + ((2 + (d & 1)) << eb) + (int)br.bits(eb);
         }
-        T->q_len[n] = (uint16_t)len;
-        T->q_dist[n] = (uint16_t)dist;
-        ++n;
+        T->queue[n++] = (uint32_t)len | (uint32_t)dist << 16;
     }
-    if (br.used > br.total) *state = E_OVERRUN;
+    if (br.overrun()) *state = E_OVERRUN;
     return n;
 }
 
 // One BGZF block: the raw-deflate stream of `clen` bytes at byte offset `coff` of the word-aligned buffer `cwords`
 // -> `usize` bytes at out.  Warp policy W:
+//   width()                          lanes of the group that works on this block (symbols per placement round)
 //   leader()                         true on the lane that runs the serial part
 //   bcast(v)                         the leader's v on every lane; orders the leader's shared-memory writes before it
 //   place(T, n, out, pos, usize)     put the n queued symbols at out[pos ..): -> bytes written, or -1 (range error)
@@ -268,7 +273,7 @@ BGZF_HD int decode_batch(BitReader& br, WarpTables* T, int* state) {
 template <class W>
 BGZF_HD int inflate_block(W& wp, const uint32_t* cwords, uint64_t coff, uint32_t clen, uint8_t* out, uint32_t usize, WarpTables* T) {
     BitReader br;
-    br.w = cwords; br.next = 0; br.buf = 0; br.nbits = 0; br.used = 0; br.total = 0;
+    br.w = cwords; br.next = 0; br.buf = 0; br.nbits = 0; br.end_bit = 0;
     if (wp.leader()) br.init(cwords, coff, clen);
     uint32_t pos = 0;
     for (;;) {
@@ -287,7 +292,7 @@ BGZF_HD int inflate_block(W& wp, const uint32_t* cwords, uint64_t coff, uint32_t
                 if ((len ^ nlen) != 0xffffu) rc = E_STORED;
                 stored_len = len;
                 stored_src = br.byte_pos();
-                if (br.used + 8ll * len > br.total) rc = E_OVERRUN;
+                if (br.bit_pos() + 8ull * len > br.end_bit) rc = E_OVERRUN;
             } else if (btype == 1) {
                 rc = fixed_tables(T);
             } else if (btype == 2) {
@@ -308,16 +313,11 @@ BGZF_HD int inflate_block(W& wp, const uint32_t* cwords, uint64_t coff, uint32_t
             if (pos + stored_len > usize) return E_RANGE;
             wp.copy_in(out + pos, reinterpret_cast<const uint8_t*>(cwords) + stored_src, stored_len);
             pos += stored_len;
-            if (wp.leader()) {
-                const int64_t used = br.used + 8ll * stored_len, total = br.total;
-                br.init(cwords, stored_src + stored_len, 0);
-                br.used = used;
-                br.total = total;
-            }
+            if (wp.leader()) br.seek(stored_src + stored_len);
         } else {
             for (;;) {
                 int n = 0, st = 0;
-                if (wp.leader()) n = decode_batch(br, T, &st);
+                if (wp.leader()) n = decode_batch(br, T, wp.width(), &st);
                 const int packed = wp.bcast((n & 0xff) + st * 256);
                 n = packed & 0xff;
                 st = packed >> 8;   // arithmetic shift: negative states survive

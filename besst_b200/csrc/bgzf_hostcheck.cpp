@@ -21,26 +21,30 @@ namespace {
 
 // the warp primitives, one lane after the other: same order of effects as the device versions (literals of a queue first,
 // then its matches in queue order with period-`dist` source indexing)
+int g_width = 32;
+
 struct HostWarp {
+    int w = g_width;   // lanes of the group that works on one block: the device build runs BGZF_GROUP of 32, 16, 8 or 4
+    int width() const { return w; }
     bool leader() const { return true; }
     int bcast(int v) const { return v; }
     int place(bgzf::WarpTables* T, int n, uint8_t* out, uint32_t pos, uint32_t usize) const {
         uint32_t P[bgzf::QUEUE], L[bgzf::QUEUE], D[bgzf::QUEUE];
         uint32_t p = pos;
         for (int i = 0; i < n; ++i) {
-            D[i] = T->q_dist[i];
-            L[i] = D[i] ? T->q_len[i] : 1;
+            D[i] = T->queue[i] >> 16;
+            L[i] = D[i] ? (T->queue[i] & 0xffffu) : 1;
             P[i] = p;
             p += L[i];
             if (P[i] + L[i] > usize || D[i] > P[i]) return -1;
         }
         for (int i = 0; i < n; ++i)
-            if (!D[i]) out[P[i]] = (uint8_t)T->q_len[i];
+            if (!D[i]) out[P[i]] = (uint8_t)T->queue[i];
         for (int i = 0; i < n; ++i)
             if (D[i])
-                for (int round = 0; round < (int)L[i]; round += 32) {   // 32 lanes at a time, sources read before the stores
+                for (int round = 0; round < (int)L[i]; round += w) {   // one group of lanes at a time, sources read before the stores
                     uint8_t tmp[32];
-                    const int m = std::min<int>(32, (int)L[i] - round);
+                    const int m = std::min<int>(w, (int)L[i] - round);
                     for (int l = 0; l < m; ++l) {
                         const uint32_t k = (uint32_t)(round + l);
                         tmp[l] = out[P[i] - D[i] + (D[i] >= L[i] ? k : k % D[i])];
@@ -206,6 +210,9 @@ struct Handle {
 }  // namespace
 
 extern "C" {
+
+// lanes per block of the emulated placement rounds (the device build's BGZF_GROUP)
+void bgzf_hc_set_width(int w) { g_width = (w == 4 || w == 8 || w == 16) ? w : 32; }
 
 // raw-deflate stream -> usize bytes, through the device decoder's code path; `misalign` (0..3) shifts the stream inside the
 // word buffer.  -> 0 or a bgzf::E_* code

@@ -191,7 +191,7 @@ def ingest_mode():
     return mode
 
 
-DEFAULT_INGEST = "host"
+DEFAULT_INGEST = "device"
 
 
 class BatchFile(object):
@@ -230,10 +230,10 @@ def as_file(bam_file, engine=None):
         hit = _open_cache.get(key)
         if hit is None or hit[0] != stamp:
             _open_cache.clear()   # one library at a time, like the reference's loop (runBESST:143-231)
-            if ingest_mode() == "device":
-                if engine is None:
-                    from .engine import default_engine
-                    engine = default_engine()
+            if ingest_mode() == "device" and engine is None:
+                from .engine import default_engine
+                engine = default_engine()   # raises without a GPU: the product path has no CPU fallback
+            if ingest_mode() == "device" and hasattr(engine, "ingest_bam"):
                 hit = (stamp, BatchFile(engine.ingest_bam(key)))
             else:
                 from .bamio import read_bam_native

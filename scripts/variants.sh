@@ -8,7 +8,7 @@ mkdir -p besst_b200/variants
 while [ $# -ge 2 ]; do
   name=$1; defs=$2; shift 2
   objs=""
-  for f in besst_api besst_links besst_sort besst_edges besst_metrics; do
+  for f in besst_api besst_links besst_sort besst_edges besst_metrics besst_bamdev; do
     extra=""; [ $f == besst_edges ] && extra="-fmad=false"
     nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC $extra $defs -c besst_b200/csrc/$f.cu -o /tmp/var_${name}_$f.o &
     objs="$objs /tmp/var_${name}_$f.o"
