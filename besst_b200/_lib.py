@@ -19,7 +19,7 @@ EXPORTS = ["besst_abi_version", "besst_create", "besst_destroy", "besst_last_err
            "besst_kernel_profile", "besst_links_partials_device", "besst_links_fetch", "besst_links_partition",
            "besst_trsk_sd_batch", "besst_set_stream", "besst_graph_view", "besst_links_group", "besst_runs_route",
            "besst_runs_pack", "besst_runs_to_graph", "besst_runs_pack_peer", "besst_gapest_func_batch", "besst_runs_obs_bytes", "besst_contigs_select", "besst_csr_prune_dense", "besst_gapest_lognormal_batch", "besst_exchange_prepare",
-           "besst_bam_ingest", "besst_bam_ingest_n_refs", "besst_bam_ingest_ref_name", "besst_bam_ingest_ref_length",
+           "besst_bam_ingest", "besst_bam_ingest_part", "besst_bam_ingest_n_refs", "besst_bam_ingest_ref_name", "besst_bam_ingest_ref_length",
            "besst_bam_ingest_head", "besst_device_read"]
 
 _lib = None
@@ -83,6 +83,8 @@ def load():
     L.besst_runs_to_graph.argtypes = [vp, C.POINTER(abi.LibParams), vp, i64, vp, i64, i32, i32, vp, vp, vp, vp, i64,
                                       C.POINTER(abi.GraphSizes)]
     L.besst_bam_ingest.argtypes = [vp, C.c_char_p, i64, i32, C.POINTER(abi.Records), C.POINTER(abi.BamIngestStats)]
+    L.besst_bam_ingest_part.argtypes = [vp, C.c_char_p, i64, i32, i32, i32, i64, C.POINTER(abi.Records), C.POINTER(abi.BamIngestStats),
+                                        C.POINTER(i64), C.POINTER(i64)]
     L.besst_bam_ingest_n_refs.restype = i64
     L.besst_bam_ingest_n_refs.argtypes = [vp]
     L.besst_bam_ingest_ref_name.restype = C.c_char_p

@@ -159,15 +159,15 @@ k_bgzf_inflate(const uint32_t* __restrict__ cwords, const bamingest::BlockEntry*
 }
 
 __global__ void __launch_bounds__(256)
-k_bam_scan(const uint32_t* __restrict__ u, const bamingest::BlockEntry* __restrict__ blocks, int n_blocks, uint64_t cur, uint64_t wend,
-           int32_t n_ref, int blind, uint32_t* __restrict__ offs, bamingest::ScanEntry* __restrict__ out) {
+k_bam_scan(const uint32_t* __restrict__ u, const bamingest::BlockEntry* __restrict__ blocks, int n_blocks, int have_cur, uint64_t cur,
+           uint64_t wend, int32_t n_ref, int blind, uint32_t* __restrict__ offs, bamingest::ScanEntry* __restrict__ out) {
     const int k = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
     if (k >= n_blocks) return;
     const uint64_t b0 = blocks[k].out, b1 = b0 + blocks[k].usize;
     uint64_t seed = ~0ull;
-    if ((cur >= b0 && cur < b1) || (k == 0 && cur < b0)) {
+    if (have_cur && ((cur >= b0 && cur < b1) || (k == 0 && cur < b0))) {
         seed = cur;
-    } else if (cur < b0) {
+    } else if (!have_cur || cur < b0) {   // no known start (a part behind the header): every block guesses
         if (blind) {
             seed = b0;
         } else {
@@ -384,7 +384,8 @@ struct DevBackend {
         {
             KTimer kt(ctx, BESST_K_BAM_SCAN);
             k_bam_scan<<<(nb + 7) / 8, 256, 0, ctx->stream>>>(S->ubuf[buf].as<uint32_t>(), S->tbl_d[buf].as<bamingest::BlockEntry>(), nb,
-                                                              (uint64_t)cur, (uint64_t)wend, n_ref, (flags & BESST_BAM_BLIND_SEEDS) ? 1 : 0,
+                                                              cur >= 0 ? 1 : 0, (uint64_t)(cur >= 0 ? cur : 0), (uint64_t)wend, n_ref,
+                                                              (flags & BESST_BAM_BLIND_SEEDS) ? 1 : 0,
                                                               S->offs[buf].as<uint32_t>(), S->scan_d[buf].as<bamingest::ScanEntry>());
         }
         cudaEventRecord(done, ctx->stream);
@@ -394,8 +395,7 @@ struct DevBackend {
         return ok(cudaEventRecord(S->ev_scan[buf], ctx->stream), "cudaEventRecord");
     }
 
-    bool scan_results(int buf, const bamingest::Window&, bamingest::ScanEntry** entries, std::string* why) {
-        if (!ok(cudaEventSynchronize(S->ev_scan[buf]), "cudaEventSynchronize(scan)")) { *why = err; return false; }
+    bool verdict(std::string* why) {
         const int* e = static_cast<const int*>(S->err_h.p);
         if (e[0]) {
             *why = "inflate failed on the device: corrupt deflate stream in " + std::to_string(e[0]) + " BGZF block(s) (first: block " +
@@ -403,10 +403,20 @@ struct DevBackend {
             return false;
         }
         if (e[3]) { *why = "CRC32 mismatch in " + std::to_string(e[3]) + " BGZF block(s)"; return false; }
+        return true;
+    }
+    bool inflate_verdict(int, std::string* why) {   // a part's header window: no scan follows it
+        if (!ok(cudaMemcpyAsync(S->err_h.p, S->err_d.p, 8 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream), "D2H status") ||
+            !ok(cudaStreamSynchronize(ctx->stream), "cudaStreamSynchronize")) { *why = err; return false; }
+        return verdict(why);
+    }
+
+    bool scan_results(int buf, const bamingest::Window&, bamingest::ScanEntry** entries, std::string* why) {
+        if (!ok(cudaEventSynchronize(S->ev_scan[buf]), "cudaEventSynchronize(scan)")) { *why = err; return false; }
+        if (!verdict(why)) return false;
         *entries = static_cast<bamingest::ScanEntry*>(S->scan_h[buf].p);
         return true;
     }
-
     bool rescan(int buf, const bamingest::Window&, int64_t k, int64_t start, int64_t wend, bamingest::ScanEntry* e) {
         {
             KTimer kt(ctx, BESST_K_BAM_SCAN);
@@ -473,14 +483,14 @@ struct DevBackend {
         return ok(cudaMemcpyAsync(S->ubuf[to].as<uint8_t>() + dst, S->ubuf[from].as<uint8_t>() + src, (size_t)n, cudaMemcpyDeviceToDevice, ctx->stream), "D2D carry");
     }
 
-    bool finish(std::string* why) {
+    bool finish(std::string* why, bool* bad_records) {
         if (!ok(cudaMemcpyAsync(S->err_h.p, S->err_d.p, 8 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream), "D2H status") ||
             !ok(cudaStreamSynchronize(ctx->stream), "cudaStreamSynchronize") || !ok(cudaStreamSynchronize(ctx->copy_stream), "cudaStreamSynchronize")) {
             *why = err;
             return false;
         }
         const int* e = static_cast<const int*>(S->err_h.p);
-        if (e[4]) { *why = "corrupt BAM record (name/CIGAR longer than the record) in " + std::to_string(e[4]) + " record(s)"; return false; }
+        *bad_records = e[4] != 0;
         S->unpackable = e[5] != 0;
         return true;
     }
@@ -490,8 +500,15 @@ struct DevBackend {
 
 extern "C" int besst_bam_ingest(besst_ctx* ctx, const char* path, int64_t head_records, int32_t flags, besst_records* out,
                                 besst_bam_ingest_stats* stats) {
+    return besst_bam_ingest_part(ctx, path, head_records, flags, 0, 1, -1, out, stats, nullptr, nullptr);
+}
+
+extern "C" int besst_bam_ingest_part(besst_ctx* ctx, const char* path, int64_t head_records, int32_t flags, int32_t part, int32_t n_parts,
+                                     int64_t start_voffset, besst_records* out, besst_bam_ingest_stats* stats, int64_t* first_voffset,
+                                     int64_t* landing_voffset) {
     if (!ctx) return BESST_E_INVALID;
     if (!path || !out) { ctx->err = "besst_bam_ingest: null argument"; return BESST_E_INVALID; }
+    if (n_parts < 1 || part < 0 || part >= n_parts) { ctx->err = "besst_bam_ingest_part: part out of range"; return BESST_E_INVALID; }
     BESST_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     const double t_start = now_s();
     if (!ctx->ingest) ctx->ingest = new BesstBamIngest();
@@ -530,6 +547,10 @@ extern "C" int besst_bam_ingest(besst_ctx* ctx, const char* path, int64_t head_r
     bamingest::Options opt;
     opt.head_records = head_records;
     opt.check_crc = !(flags & BESST_BAM_NO_CRC);
+    opt.part = part;
+    opt.n_parts = n_parts;
+    opt.start_voffset = start_voffset;
+    if (const char* e = getenv("BESST_BAM_TAIL")) { const long long v = atoll(e); if (v >= 0) opt.tail_bytes = v; }
     if (const char* e = getenv("BESST_BAM_WINDOW")) { const long long v = atoll(e); if (v >= 1024) opt.window_bytes = v; }
     if (const char* e = getenv("BESST_BAM_MAX_INFLATED")) { const long long v = atoll(e); if (v >= 65536) opt.max_inflated = v; }
     if (const char* e = getenv("BESST_BAM_CARRY")) { const long long v = atoll(e); if (v >= 64) opt.carry_max = (v + 3) / 4 * 4; }
@@ -588,6 +609,8 @@ extern "C" int besst_bam_ingest(besst_ctx* ctx, const char* path, int64_t head_r
     s.seconds_total = now_s() - t_start;
     s.crc_checked = opt.check_crc ? 1 : 0;
     if (stats) *stats = s;
+    if (first_voffset) *first_voffset = res.first_voffset;
+    if (landing_voffset) *landing_voffset = res.landing_voffset;
     memset(out, 0, sizeof(*out));
     out->n = S->n;
     out->tid = S->col_i32[0].as<int32_t>(); out->mtid = S->col_i32[1].as<int32_t>(); out->pos = S->col_i32[2].as<int32_t>();

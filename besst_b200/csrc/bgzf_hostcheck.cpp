@@ -145,15 +145,21 @@ struct HostBackend {
             const uint64_t b0 = W.blocks[k].out, b1 = b0 + W.blocks[k].usize;
             bamingest::ScanEntry& e = scan_out[buf][k];
             uint64_t seed = ~0ull;
-            if (((uint64_t)cur >= b0 && (uint64_t)cur < b1) || (k == 0 && (uint64_t)cur < b0)) seed = (uint64_t)cur;
-            else if ((uint64_t)cur < b0 && blind) seed = b0;
-            else if ((uint64_t)cur < b0)
+            const bool have_cur = cur >= 0;
+            if (have_cur && (((uint64_t)cur >= b0 && (uint64_t)cur < b1) || (k == 0 && (uint64_t)cur < b0))) seed = (uint64_t)cur;
+            else if ((!have_cur || (uint64_t)cur < b0) && blind) seed = b0;
+            else if (!have_cur || (uint64_t)cur < b0)
                 for (uint64_t o = b0; o < b1; ++o)
                     if (bgzf::record_plausible(u, o, (uint64_t)wend, n_ref)) { seed = o; break; }
             if (seed == ~0ull) { e.seed = 0xffffffffu; e.land = 0xffffffffu; e.count = 0; e.flags = 0; continue; }
             e.seed = (uint32_t)seed;
             e.land = (uint32_t)bgzf::hop_block(u, seed, b1, (uint64_t)wend, offs[buf].data() + k * bgzf::MAX_RECORDS_PER_BLOCK, &e.count, &e.flags);
         }
+        return true;
+    }
+    bool inflate_verdict(int buf, std::string* why) {
+        if (inflate_err[buf]) { *why = "inflate failed: corrupt deflate stream in BGZF block (code " + std::to_string(inflate_err[buf]) + ")"; return false; }
+        if (crc_bad[buf]) { *why = "CRC32 mismatch in " + std::to_string(crc_bad[buf]) + " BGZF block(s)"; return false; }
         return true;
     }
     bool scan_results(int buf, const bamingest::Window&, bamingest::ScanEntry** entries, std::string* why) {
@@ -195,8 +201,9 @@ struct HostBackend {
         memmove(reinterpret_cast<unsigned char*>(ubuf[to].data()) + dst, reinterpret_cast<const unsigned char*>(ubuf[from].data()) + src, (size_t)n);
         return true;
     }
-    bool finish(std::string* why) {
-        if (decode_bad) { *why = "corrupt BAM record (name/CIGAR longer than the record)"; return false; }
+    bool finish(std::string*, bool* bad_records) {
+        *bad_records = decode_bad != 0;
+        decode_bad = 0;
         return true;
     }
 };
@@ -230,8 +237,17 @@ uint32_t bgzf_hc_crc32(const uint8_t* data, uint32_t n, int misalign) {
     return crc_lanes(words.data(), (uint64_t)misalign, n);
 }
 
+void* bgzf_hc_ingest_part(const char* path, int64_t window_bytes, int64_t max_inflated, int64_t carry_max, int check_crc, int blind,
+                          int64_t head_records, int part, int n_parts, int64_t start_voffset, int64_t tail_bytes, char* err, int err_len);
+
 void* bgzf_hc_ingest(const char* path, int64_t window_bytes, int64_t max_inflated, int64_t carry_max, int check_crc, int blind, int64_t head_records,
                      char* err, int err_len) {
+    return bgzf_hc_ingest_part(path, window_bytes, max_inflated, carry_max, check_crc, blind, head_records, 0, 1, -1, 0, err, err_len);
+}
+
+// one part of the file (the multi-GPU ingest's per-rank call): see bamingest::Options
+void* bgzf_hc_ingest_part(const char* path, int64_t window_bytes, int64_t max_inflated, int64_t carry_max, int check_crc, int blind,
+                          int64_t head_records, int part, int n_parts, int64_t start_voffset, int64_t tail_bytes, char* err, int err_len) {
     Handle* h = new Handle();
     auto fail = [&](const std::string& m) -> void* {
         if (err && err_len > 0) { strncpy(err, m.c_str(), (size_t)err_len - 1); err[err_len - 1] = 0; }
@@ -251,6 +267,10 @@ void* bgzf_hc_ingest(const char* path, int64_t window_bytes, int64_t max_inflate
     if (carry_max > 0) opt.carry_max = carry_max;
     opt.check_crc = check_crc != 0;
     opt.head_records = head_records;
+    opt.part = part;
+    opt.n_parts = n_parts;
+    opt.start_voffset = start_voffset;
+    if (tail_bytes > 0) opt.tail_bytes = tail_bytes;
     std::string why;
     for (;;) {
         h->B.opt = opt;
@@ -273,9 +293,11 @@ int64_t bgzf_hc_n_refs(void* h) { return (int64_t)static_cast<Handle*>(h)->res.r
 const char* bgzf_hc_ref_name(void* h, int64_t i) { return static_cast<Handle*>(h)->res.ref_names[(size_t)i].c_str(); }
 int64_t bgzf_hc_ref_length(void* h, int64_t i) { return static_cast<Handle*>(h)->res.ref_lengths[(size_t)i]; }
 int64_t bgzf_hc_stat(void* h, int which) {
-    const bamingest::Stats& s = static_cast<Handle*>(h)->res.stats;
-    const int64_t v[] = {s.compressed_bytes, s.uncompressed_bytes, s.blocks, s.records, s.windows, s.rescans, static_cast<Handle*>(h)->B.unpackable};
-    return which >= 0 && which < 7 ? v[which] : -1;
+    const bamingest::Result& r = static_cast<Handle*>(h)->res;
+    const bamingest::Stats& s = r.stats;
+    const int64_t v[] = {s.compressed_bytes, s.uncompressed_bytes, s.blocks, s.records, s.windows, s.rescans, static_cast<Handle*>(h)->B.unpackable,
+                         r.first_voffset, r.landing_voffset};
+    return which >= 0 && which < 9 ? v[which] : -1;
 }
 const void* bgzf_hc_column(void* hp, int which) {
     HostBackend& B = static_cast<Handle*>(hp)->B;

@@ -520,3 +520,45 @@ def merge_graph_results(parts):
         fields[f] = np.concatenate([getattr(p, f) for p in parts])[order]
     return abi.GraphResult(row_ptr=row_ptr, obs_u=obs_u_all[idx], obs_v=obs_v_all[idx], aligned_len=first.aligned_len,
                            counters=first.counters, **fields)
+
+
+def ingest_bam_distributed(engine, path, rank, world, group=None, **ingest_kw):
+    """Multi-GPU BAM ingest (SURVEY.md 8e + 8f rank 1): rank r inflates and decodes the r-th part of the file on its own
+    GPU (besst_bam_ingest_part: the BGZF blocks starting in its byte range, the records starting in those blocks), so a
+    library arrives in HBM already range-partitioned in BAM order -- the layout DistributedGraphBuild.step takes -- at
+    `world` times the single-GPU inflate rate and without the file's records ever being in one place.
+
+    A part behind the header finds its first record by a plausibility test nothing inside the part can verify.  The ranks
+    therefore exchange (first record, landing of the last record) as BGZF virtual offsets -- ONE small all_gather -- and
+    every part whose first record is not where the chain of the preceding parts landed is read again from the right
+    offset (rare: a false positive needs a byte pattern that passes the record checks inside another record; repeated at
+    most once per part).  -> (DeviceRecordBatch of this rank, {"counts": records per rank, "record_base": ordinal of this
+    rank's first record in the file, "repeats": parts read again})"""
+    import torch.distributed as dist
+    dev = engine.ingest_bam(path, part=(rank, world), **ingest_kw)
+    forced = {}
+    repeats = 0
+    for _ in range(world + 2):
+        mine = (int(dev.first_voffset), int(dev.landing_voffset), len(dev))
+        rows = [None] * world
+        if world > 1:
+            dist.all_gather_object(rows, mine, group=group)
+        else:
+            rows = [mine]
+        prev, redo = -1, None
+        for r, (first, landing, _n) in enumerate(rows):
+            if r > 0 and prev >= 0 and first != prev and forced.get(r) != prev and redo is None:
+                redo = (r, prev)
+            if landing >= 0:
+                prev = landing
+        if redo is None:
+            break
+        r, start = redo
+        forced[r] = start   # every rank keeps the same book: the loop ends after at most `world` repeats
+        repeats += 1
+        if r == rank:
+            dev = engine.ingest_bam(path, part=(rank, world), start_voffset=start, **ingest_kw)
+    else:
+        raise RuntimeError("ingest_bam_distributed: the parts' record chains do not meet (%r)" % (rows,))
+    counts = [int(n) for _, _, n in rows]
+    return dev, {"counts": counts, "record_base": int(sum(counts[:rank])), "repeats": repeats}

@@ -213,15 +213,20 @@ class CudaEngine(object):
         return sizes
 
     # -- BAM ingest on the device -----------------------------------------------------------
-    def ingest_bam(self, path, head_records=1000, check_crc=True, blind_seeds=False):
+    def ingest_bam(self, path, head_records=1000, check_crc=True, blind_seeds=False, part=(0, 1), start_voffset=-1):
         """BAM file -> DeviceRecordBatch: BGZF inflate and record decode on the GPU, the columns stay in HBM (owned by the
-        engine, valid until the next ingest_bam / close).  Pass the batch to libmetrics / graph_build like a RecordBatch."""
+        engine, valid until the next ingest_bam / close).  Pass the batch to libmetrics / graph_build like a RecordBatch.
+        part = (r, n): only the r-th of n parts of the file (multi-GPU ingest, besst_bam_ingest_part); the batch then
+        carries first_voffset / landing_voffset for the consistency check between neighbouring parts
+        (besst_b200.dist.ingest_bam_distributed does the whole protocol)."""
         import os
         from .records import DeviceRecordBatch
         rec, st = abi.Records(), abi.BamIngestStats()
         flags = (0 if check_crc else abi.BAM_NO_CRC) | (abi.BAM_BLIND_SEEDS if blind_seeds else 0)
-        self._check(self._L.besst_bam_ingest(self._ctx, os.fsencode(path), int(head_records), flags, C.byref(rec), C.byref(st)),
-                    "besst_bam_ingest")
+        first, landing = C.c_int64(-1), C.c_int64(-1)
+        self._check(self._L.besst_bam_ingest_part(self._ctx, os.fsencode(path), int(head_records), flags, int(part[0]), int(part[1]),
+                                                  int(start_voffset), C.byref(rec), C.byref(st), C.byref(first), C.byref(landing)),
+                    "besst_bam_ingest_part")
         n_ref = int(self._L.besst_bam_ingest_n_refs(self._ctx))
         references = [self._L.besst_bam_ingest_ref_name(self._ctx, i).decode("ascii") for i in range(n_ref)]
         lengths = [int(self._L.besst_bam_ingest_ref_length(self._ctx, i)) for i in range(n_ref)]
@@ -230,7 +235,9 @@ class CudaEngine(object):
         got = self._L.besst_bam_ingest_head(self._ctx, rlen.ctypes.data, alen.ctypes.data, nh)
         if got != nh:
             raise BesstLibraryError("besst_bam_ingest_head returned %d, expected %d" % (got, nh))
-        return DeviceRecordBatch(self, rec, references, lengths, rlen, alen, {k: getattr(st, k) for k, _ in abi.BamIngestStats._fields_})
+        batch = DeviceRecordBatch(self, rec, references, lengths, rlen, alen, {k: getattr(st, k) for k, _ in abi.BamIngestStats._fields_})
+        batch.first_voffset, batch.landing_voffset = int(first.value), int(landing.value)
+        return batch
 
     def device_read(self, ptr, count, dtype):
         """numpy copy of `count` elements at device address `ptr` (columns the engine owns)."""

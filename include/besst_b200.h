@@ -378,6 +378,19 @@ typedef struct besst_bam_ingest_stats {
 } besst_bam_ingest_stats;
 int besst_bam_ingest(besst_ctx* ctx, const char* path, int64_t head_records, int32_t flags, besst_records* out,
                      besst_bam_ingest_stats* stats /* may be NULL */);
+/* One PART of the file, for a multi-GPU ingest (rank `part` of `n_parts`, one ctx / GPU each): with D = the file offset of
+ * the BGZF block in which the header ends, the part owns the blocks that start inside
+ * [D + (size - D) part / n_parts, D + (size - D) (part + 1) / n_parts) and the records that start in them; its last record
+ * may end in the next part's first blocks (up to 1 MB of them are inflated along, BESST_BAM_TAIL).  Every part reads the
+ * header itself.  BGZF virtual offsets (block file offset << 16 | offset in the inflated block) tie the parts together:
+ * *landing_voffset = the first record behind the part, *first_voffset = the part's first record (-1 / -1: no record
+ * starts in the part).  A part behind the header finds its first record by a plausibility test that nothing inside the
+ * part can verify: the caller compares first_voffset[r] with landing_voffset[r - 1] (one all_gather) and repeats a
+ * mismatching part with start_voffset = landing_voffset[r - 1] (-1: not known).  The concatenation of the parts' columns
+ * in part order is the whole file's.  besst_bam_ingest is part 0 of 1. */
+int besst_bam_ingest_part(besst_ctx* ctx, const char* path, int64_t head_records, int32_t flags, int32_t part, int32_t n_parts,
+                          int64_t start_voffset, besst_records* out, besst_bam_ingest_stats* stats /* may be NULL */,
+                          int64_t* first_voffset /* may be NULL */, int64_t* landing_voffset /* may be NULL */);
 /* header of the last ingested file, and rlen (l_seq) / alen (reference span) of its first head_records records (what
  * libmetrics.py:246-266 reads); besst_bam_ingest_head returns how many were written (<= cap) */
 int64_t besst_bam_ingest_n_refs(besst_ctx* ctx);

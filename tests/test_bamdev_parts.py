@@ -1,0 +1,186 @@
+"""The multi-GPU BAM ingest: besst_bam_ingest_part (rank r of n inflates and decodes its part of the file) and the
+neighbour check of besst_b200.dist.ingest_bam_distributed.
+
+CPU: the part logic is the window loop of bam_ingest.hpp, run here through the host rendering of the kernels
+(libbesst_bgzf_hostcheck.so, test tooling): the concatenation of the parts equals the whole file for 1..16 parts, ragged
+files with records straddling BGZF blocks, windows and part boundaries, header longer than a part; the virtual-offset
+chain is consistent; with blind seeds (every guess wrong where a block starts inside a record) the world-2/3 gloo run of
+ingest_bam_distributed repairs the parts.  GPU (-m gpu): the same through the C ABI on one device, part after part."""
+import ctypes as C
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+
+import test_bamdev as t
+import test_bamio as tb
+from besst_b200 import bamio, synth
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+
+
+class _HostPart(object):
+    def __init__(self, cols, first, landing):
+        self.cols, self.first_voffset, self.landing_voffset = cols, first, landing
+
+    def __len__(self):
+        return int(self.cols["tid"].shape[0])
+
+
+class HostcheckEngine(object):
+    """stand-in for CudaEngine.ingest_bam over the host rendering of the ingest (tests only)"""
+
+    def __init__(self, window=0, carry=0, tail=0):
+        self.window, self.carry, self.tail = window, carry, tail
+        self.calls = []
+
+    def ingest_bam(self, path, part=(0, 1), start_voffset=-1, blind_seeds=False, head_records=1000, check_crc=True):
+        L = t.hostcheck()
+        L.bgzf_hc_ingest_part.restype = C.c_void_p
+        L.bgzf_hc_ingest_part.argtypes = [C.c_char_p, C.c_int64, C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_int64, C.c_int, C.c_int,
+                                          C.c_int64, C.c_int64, C.c_char_p, C.c_int]
+        err = C.create_string_buffer(512)
+        h = L.bgzf_hc_ingest_part(os.fsencode(path), self.window, 0, self.carry, int(check_crc), int(blind_seeds), head_records, part[0], part[1],
+                                  start_voffset, self.tail, err, 512)
+        if not h:
+            raise IOError(err.value.decode())
+        n = L.bgzf_hc_n(h)
+        cols = {}
+        for i, (k, dt) in enumerate(t.COLS):
+            p = L.bgzf_hc_column(h, i)
+            cols[k] = np.frombuffer((C.c_char * (n * np.dtype(dt).itemsize)).from_address(p), dtype=dt, count=n).copy() if n else np.zeros(0, dt)
+        out = _HostPart(cols, int(L.bgzf_hc_stat(h, 7)), int(L.bgzf_hc_stat(h, 8)))
+        L.bgzf_hc_close(h)
+        self.calls.append((part, start_voffset))
+        return out
+
+
+def _ragged_file(path, n, block_bytes, n_refs=37):
+    rng = np.random.default_rng(n + block_bytes)
+    refs = [("c%d,pos:%d-%d,rc:0" % (i, i * 1000, i * 1000 + 900), 900 + i) for i in range(n_refs)]
+    tb.write_bam(path, refs, tb._random_records(rng, n, len(refs)), block_bytes)
+    return bamio.read_bam(path)
+
+
+def _check_parts(parts, want):
+    land = None
+    for q in parts:
+        if q.first_voffset >= 0 and land is not None:
+            assert q.first_voffset == land
+        if q.landing_voffset >= 0:
+            land = q.landing_voffset
+    for k, _ in t.COLS[:8]:
+        assert np.array_equal(np.concatenate([q.cols[k] for q in parts]), getattr(want, k)), k
+
+
+@pytest.mark.parametrize("n,block_bytes,n_refs", [(5000, 700, 37), (5000, 65000, 37), (20000, 3000, 37), (300, 3000, 37), (300, 700, 400)])
+def test_parts_concatenate_to_the_whole_file(tmp_path, n, block_bytes, n_refs):
+    """(300, 700, 400): the header is longer than several parts -- they own no record and say so"""
+    path = str(tmp_path / "t.bam")
+    want = _ragged_file(path, n, block_bytes, n_refs)
+    for n_parts in (1, 2, 3, 5, 8, 16):
+        for window, carry in ((0, 0), (70000, 2048)):
+            eng = HostcheckEngine(window, carry, tail=200000)
+            parts = [eng.ingest_bam(path, part=(p, n_parts)) for p in range(n_parts)]
+            _check_parts(parts, want)
+            assert sum(len(q) for q in parts) == n
+
+
+def test_a_record_longer_than_the_tail_is_an_error(tmp_path):
+    path = str(tmp_path / "t.bam")
+    _ragged_file(path, 5000, 700)
+    eng = HostcheckEngine(tail=64)   # 64 bytes of tail: the record cut by the part boundary cannot be completed
+    with pytest.raises(IOError, match="range tail"):
+        for p in range(4):
+            eng.ingest_bam(path, part=(p, 4))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _worker(rank, world, port, path, blind, out_dir):
+    for p in (ROOT, os.path.join(ROOT, "oracle"), HERE):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    import torch.distributed as dist
+    from besst_b200.dist import ingest_bam_distributed
+    dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%d" % port, rank=rank, world_size=world)
+    try:
+        eng = HostcheckEngine(tail=200000)
+        dev, info = ingest_bam_distributed(eng, path, rank, world, blind_seeds=blind)
+        np.savez(os.path.join(out_dir, "part%d.npz" % rank), repeats=info["repeats"], record_base=info["record_base"],
+                 counts=np.asarray(info["counts"]), calls=len(eng.calls), **dev.cols)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,blind", [(2, False), (3, False), (3, True)])
+def test_distributed_ingest_protocol_gloo(tmp_path, world, blind):
+    """blind seeds: every part behind the first starts its chain at the first byte of its first block -- inside a record for
+    this file -- so the neighbour check has to catch it and the part is read again from the previous part's landing"""
+    import torch.multiprocessing as mp
+    path = str(tmp_path / "t.bam")
+    want = _ragged_file(path, 20000, 3000)
+    mp.spawn(_worker, args=(world, _free_port(), path, blind, str(tmp_path)), nprocs=world, join=True)
+    parts = [np.load(str(tmp_path / ("part%d.npz" % r))) for r in range(world)]
+    for k, _ in t.COLS[:8]:
+        assert np.array_equal(np.concatenate([q[k] for q in parts]), getattr(want, k)), k
+    assert [int(q["record_base"]) for q in parts] == list(np.cumsum([0] + [len(q["tid"]) for q in parts[:-1]]))
+    repeats = int(parts[0]["repeats"])
+    assert all(int(q["repeats"]) == repeats for q in parts)
+    assert (repeats > 0) == blind
+    if blind:
+        assert sum(int(q["calls"]) for q in parts) == world + repeats
+
+
+# ---- GPU ------------------------------------------------------------------------------------------------------------------
+
+@pytest.fixture(scope="module")
+def engine():
+    from besst_b200.engine import CudaEngine
+    eng = CudaEngine(0)
+    yield eng
+    eng.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n,block_bytes", [(5000, 700), (20000, 3000)])
+def test_device_parts_concatenate_to_the_whole_file(tmp_path, engine, n, block_bytes):
+    path = str(tmp_path / "t.bam")
+    want = _ragged_file(path, n, block_bytes)
+    for n_parts in (2, 3, 8):
+        for env in ({"BESST_BAM_TAIL": 200000}, {"BESST_BAM_TAIL": 200000, "BESST_BAM_WINDOW": 70000, "BESST_BAM_CARRY": 2048}):
+            parts = []
+            for p in range(n_parts):
+                dev = t._with_env(env, lambda: engine.ingest_bam(path, part=(p, n_parts)))
+                host = dev.to_host()
+                parts.append(_HostPart({k: getattr(host, k) for k, _ in t.COLS[:8]}, dev.first_voffset, dev.landing_voffset))
+            _check_parts(parts, want)
+
+
+@pytest.mark.gpu
+def test_device_parts_of_a_synthetic_library_and_a_forced_start(tmp_path, engine):
+    lib = synth.make_library(200, 150000, "rf", 3000.0, 500.0, 0.0, seed=13)
+    batch = lib.to_batch()
+    path = str(tmp_path / "lib.bam")
+    bamio.write_bam_columns(path, batch, style="packed")
+    parts = []
+    for p in range(4):
+        dev = engine.ingest_bam(path, part=(p, 4))
+        host = dev.to_host()
+        parts.append(_HostPart({k: getattr(host, k) for k, _ in t.COLS[:8]}, dev.first_voffset, dev.landing_voffset))
+    _check_parts(parts, t.batch_with_lengths(batch))
+    # blind seeds put part 2's first record in the wrong place; the previous part's landing as start_voffset repairs it
+    wrong = engine.ingest_bam(path, part=(2, 4), blind_seeds=True)
+    assert wrong.first_voffset != parts[1].landing_voffset
+    right = engine.ingest_bam(path, part=(2, 4), blind_seeds=True, start_voffset=parts[1].landing_voffset)
+    assert right.first_voffset == parts[1].landing_voffset and len(right) == len(parts[2])
+    assert np.array_equal(right.to_host().pos, parts[2].cols["pos"])
