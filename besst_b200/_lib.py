@@ -20,7 +20,8 @@ EXPORTS = ["besst_abi_version", "besst_create", "besst_destroy", "besst_last_err
            "besst_trsk_sd_batch", "besst_set_stream", "besst_graph_view", "besst_links_group", "besst_runs_route",
            "besst_runs_pack", "besst_runs_to_graph", "besst_runs_pack_peer", "besst_gapest_func_batch", "besst_runs_obs_bytes", "besst_contigs_select", "besst_csr_prune_dense", "besst_gapest_lognormal_batch", "besst_exchange_prepare",
            "besst_bam_ingest", "besst_bam_ingest_part", "besst_bam_ingest_n_refs", "besst_bam_ingest_ref_name", "besst_bam_ingest_ref_length",
-           "besst_bam_ingest_head", "besst_device_read"]
+           "besst_bam_ingest_head", "besst_device_read",
+           "besst_paths_between", "besst_paths_count", "besst_paths_hit_threshold", "besst_paths_pops", "besst_paths_arrays", "besst_paths_free"]
 
 _lib = None
 
@@ -94,6 +95,15 @@ def load():
     L.besst_bam_ingest_head.restype = i64
     L.besst_bam_ingest_head.argtypes = [vp, vp, vp, i64]
     L.besst_device_read.argtypes = [vp, vp, vp, i64]
+    L.besst_paths_between.restype = vp
+    L.besst_paths_between.argtypes = [i64, vp, vp, vp, vp, vp, i64, i64, C.c_double, i32, i32, i32]
+    L.besst_paths_count.restype = i64
+    L.besst_paths_count.argtypes = [vp]
+    L.besst_paths_hit_threshold.argtypes = [vp]
+    L.besst_paths_pops.restype = i64
+    L.besst_paths_pops.argtypes = [vp]
+    L.besst_paths_arrays.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
+    L.besst_paths_free.argtypes = [vp]
     if L.besst_abi_version() != abi.ABI_VERSION:
         raise BesstLibraryError("ABI version mismatch: library %d, binding %d" % (L.besst_abi_version(), abi.ABI_VERSION))
     _lib = L

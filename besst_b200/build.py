@@ -13,7 +13,7 @@ ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
 # per-file extra flags: the scoring math must round like the reference (no FMA contraction)
 SOURCES = [("besst_api.cu", []), ("besst_links.cu", []), ("besst_sort.cu", []),
-           ("besst_edges.cu", ["-fmad=false"]), ("besst_metrics.cu", []), ("besst_bamdev.cu", [])]
+           ("besst_edges.cu", ["-fmad=false"]), ("besst_metrics.cu", []), ("besst_bamdev.cu", []), ("besst_paths.cu", [])]
 
 
 BAMIO_SO = os.path.join(HERE, "libbesst_bamio.so")
@@ -60,7 +60,7 @@ def _stale(target, deps):
 def build(force=False, verbose=False):
     nvcc = os.environ.get("NVCC", "nvcc")
     headers = [os.path.join(CSRC, "besst_internal.cuh"), os.path.join(HERE, "..", "include", "besst_b200.h"),
-               os.path.join(CSRC, "bgzf_core.cuh"), os.path.join(CSRC, "bam_ingest.hpp")]
+               os.path.join(CSRC, "bgzf_core.cuh"), os.path.join(CSRC, "bam_ingest.hpp"), os.path.join(CSRC, "paths_core.cuh")]
     objdir = os.path.join(CSRC, "_obj")
     os.makedirs(objdir, exist_ok=True)
     objs, log = [], []

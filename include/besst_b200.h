@@ -400,6 +400,29 @@ int64_t besst_bam_ingest_head(besst_ctx* ctx, int32_t* rlen, int32_t* alen, int6
 /* device -> host copy on the ctx's stream (tests and debugging: read back columns the ctx owns) */
 int besst_device_read(besst_ctx* ctx, const void* device_ptr, void* host_ptr, int64_t bytes);
 
+/* ---- path search between scaffolds ---------------------------------------------------------------
+ * ELS.BetweenScaffolds (ExtendLargeScaffolds.py:665-712) on a CSR rendering of G_prime: for every start node the
+ * reference's default traversal (find_all_paths_for_start_node_DFS_dynamic_programming_ish, :526-663: best-first over a heap
+ * of (nr_links, node, path), one bad-neighbour set per search, head_dict pruning, the --iter cap) and ScorePaths (:28-133)
+ * for the paths it finds.  Node id = 2 * rank(scaffold key) + (side == 'R') with ranks ascending in the key, so that
+ * integer order is the order of the reference's (scaffold, side) tuples; the contig edge id <-> id ^ 1 carries
+ * adj_links = -1.  `order` = the start nodes in the order the reference would pop them from iter_nodes (the searches are
+ * independent given that order: already_visited = the earlier start nodes, end = is_end minus the start nodes up to the
+ * current one) -- they run on n_threads host threads (<= 0: all cores).  No ctx, no device: an irregular best-first walk
+ * per start node.  The result keeps the paths that pass ScorePaths' filter (score >= score_cutoff, len > 2 unless
+ * no_score), in start order then in the order found, with the good / bad link weights of the score (the caller forms
+ * good / bad with the reference's arithmetic; the contamination variant halves good first).  NULL on bad arguments. */
+typedef struct besst_paths besst_paths;
+besst_paths* besst_paths_between(int64_t n_nodes, const int64_t* adj_ptr, const int32_t* adj_node, const int32_t* adj_links,
+                                 const uint8_t* is_end, const int32_t* order, int64_t n_order, int64_t path_threshold,
+                                 double score_cutoff, int32_t no_score, int32_t contamination, int32_t n_threads);
+int64_t besst_paths_count(const besst_paths* p);
+int32_t besst_paths_hit_threshold(const besst_paths* p);   /* param.hit_path_threshold (:561) */
+int64_t besst_paths_pops(const besst_paths* p);            /* heap pops over all searches (work done) */
+int besst_paths_arrays(const besst_paths* p, const int64_t** path_ptr /*[n + 1]*/, const int32_t** nodes, const int64_t** good,
+                       const int64_t** bad, const int32_t** start_index);
+void besst_paths_free(besst_paths* p);
+
 /* run all work of this ctx on a caller-owned CUDA stream (a cudaStream_t passed as void*; NULL
  * restores the ctx's own non-blocking stream; pass cudaStreamLegacy (0x1) for the legacy default stream).  Lets a host framework order the library's kernels with its own
  * work (NCCL collectives, CUDA-event timing) without device-wide synchronisation. */
