@@ -110,3 +110,11 @@ def BetweenScaffolds(G_prime, end, iter_nodes, param, threads=0):
         print(msg)
         print(msg, file=param.information_file)
     return all_paths
+
+
+def WithinScaffolds(G, G_prime, start, end_node, already_visited, max_path_length, param):
+    """The per-pair search inside a new scaffold (ExtendLargeScaffolds.py:714-735) is not restated -- one call per pair would
+    re-extract the CSR of a G_prime that MakeScaffolds mutates between calls; it is passed through to the reference's, so that
+    `from besst_b200 import ExtendLargeScaffolds as ELS` replaces the reference's import as a whole."""
+    from BESST import ExtendLargeScaffolds as _reference
+    return _reference.WithinScaffolds(G, G_prime, start, end_node, already_visited, max_path_length, param)
