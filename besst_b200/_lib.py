@@ -21,7 +21,7 @@ EXPORTS = ["besst_abi_version", "besst_create", "besst_destroy", "besst_last_err
            "besst_runs_pack", "besst_runs_to_graph", "besst_runs_pack_peer", "besst_gapest_func_batch", "besst_runs_obs_bytes", "besst_contigs_select", "besst_csr_prune_dense", "besst_gapest_lognormal_batch", "besst_exchange_prepare",
            "besst_bam_ingest", "besst_bam_ingest_part", "besst_bam_ingest_n_refs", "besst_bam_ingest_ref_name", "besst_bam_ingest_ref_length",
            "besst_bam_ingest_head", "besst_device_read",
-           "besst_paths_between", "besst_paths_count", "besst_paths_hit_threshold", "besst_paths_pops", "besst_paths_arrays", "besst_paths_free"]
+           "besst_paths_between", "besst_paths_count", "besst_paths_hit_threshold", "besst_paths_pops", "besst_paths_arrays", "besst_paths_free", "besst_scaffold_prune_ambiguous"]
 
 _lib = None
 
@@ -104,6 +104,8 @@ def load():
     L.besst_paths_pops.argtypes = [vp]
     L.besst_paths_arrays.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
     L.besst_paths_free.argtypes = [vp]
+    L.besst_scaffold_prune_ambiguous.restype = i64
+    L.besst_scaffold_prune_ambiguous.argtypes = [i64, i64, vp, vp, vp, vp, vp, vp, vp]
     if L.besst_abi_version() != abi.ABI_VERSION:
         raise BesstLibraryError("ABI version mismatch: library %d, binding %d" % (L.besst_abi_version(), abi.ABI_VERSION))
     _lib = L

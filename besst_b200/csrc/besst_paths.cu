@@ -152,3 +152,64 @@ extern "C" int besst_paths_arrays(const besst_paths* p, const int64_t** path_ptr
     return BESST_OK;
 }
 extern "C" void besst_paths_free(besst_paths* p) { delete p; }
+
+// ---- RemoveAmbiguousRegionsUsingScore (MakeScaffolds.py:206-240) with its per-node rule remove_edges (:156-204) on the list
+// of scored link edges of G.  The pass is sequential and order dependent (what survives at a node depends on what its
+// neighbours removed before): the edges arrive in the order G.edges() yields them, `order` is that list sorted by score,
+// descending and stable -- the reference's processing order.  Node ids preserve the order of the reference's (scaffold,
+// side) tuples (ties between equal scores at a node are broken by the neighbour).
+extern "C" int64_t besst_scaffold_prune_ambiguous(int64_t n_nodes, int64_t n_edges, const int32_t* eu, const int32_t* ev, const double* score,
+                                                  const int64_t* order, uint8_t* removed, int64_t* amb_best, int64_t* amb_second) {
+    if (n_nodes < 0 || n_edges < 0 || (n_edges > 0 && (!eu || !ev || !score || !order || !removed || !amb_best || !amb_second))) return -1;
+    std::vector<int64_t> ptr((size_t)n_nodes + 1, 0);
+    for (int64_t e = 0; e < n_edges; ++e) {
+        if (eu[e] < 0 || eu[e] >= n_nodes || ev[e] < 0 || ev[e] >= n_nodes) return -1;
+        ++ptr[(size_t)eu[e] + 1];
+        ++ptr[(size_t)ev[e] + 1];
+        removed[e] = 0;
+    }
+    for (int64_t i = 0; i < n_nodes; ++i) ptr[(size_t)i + 1] += ptr[(size_t)i];
+    std::vector<int64_t> inc((size_t)(2 * n_edges)), fill(ptr.begin(), ptr.end() - 1);
+    for (int64_t e = 0; e < n_edges; ++e) {
+        inc[(size_t)fill[(size_t)eu[e]]++] = e;
+        inc[(size_t)fill[(size_t)ev[e]]++] = e;
+    }
+    struct Item { double s; int32_t nbr; int64_t e; };
+    std::vector<Item> items;
+    int64_t n_amb = 0;
+    auto at_node = [&](int32_t node) {
+        items.clear();
+        for (int64_t a = ptr[(size_t)node]; a < ptr[(size_t)node + 1]; ++a) {
+            const int64_t e = inc[(size_t)a];
+            if (removed[e]) continue;
+            items.push_back(Item{score[e], eu[e] == node ? ev[e] : eu[e], e});
+        }
+        std::sort(items.begin(), items.end(), [](const Item& a, const Item& b) { return a.s < b.s || (a.s == b.s && a.nbr < b.nbr); });
+        // zero-score edges go; of the others all but the best go -- or all of them when the two best are within 0.8 (:178-183)
+        for (size_t k = 0; k < items.size(); ++k) {
+            if (0 < items[k].s) continue;
+            removed[items[k].e] = 1;
+        }
+        std::vector<Item>& nz = items;
+        size_t m = 0;
+        for (size_t k = 0; k < items.size(); ++k)
+            if (0 < items[k].s) nz[m++] = items[k];   // stable partition in place (m <= k)
+        if (m > 1) {
+            if (nz[m - 2].s / nz[m - 1].s > 0.8) {
+                amb_best[n_amb] = nz[m - 1].e;
+                amb_second[n_amb] = nz[m - 2].e;
+                ++n_amb;
+                for (size_t k = 0; k < m; ++k) removed[nz[k].e] = 1;
+            } else {
+                for (size_t k = 0; k + 1 < m; ++k) removed[nz[k].e] = 1;
+            }
+        }
+    };
+    for (int64_t k = 0; k < n_edges; ++k) {
+        const int64_t e = order[k];
+        if (e < 0 || e >= n_edges) return -1;
+        at_node(eu[e]);
+        at_node(ev[e]);
+    }
+    return n_amb;
+}

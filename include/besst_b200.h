@@ -423,6 +423,16 @@ int besst_paths_arrays(const besst_paths* p, const int64_t** path_ptr /*[n + 1]*
                        const int64_t** bad, const int32_t** start_index);
 void besst_paths_free(besst_paths* p);
 
+/* RemoveAmbiguousRegionsUsingScore (MakeScaffolds.py:206-240, per-node rule remove_edges :156-204) on the scored link edges
+ * of G, host side: sequential and order dependent like besst_csr_prune_dense.  The edges arrive in the order G.edges()
+ * yields them; order[] = their indices sorted by score, descending and stable (the reference's processing order); node ids
+ * preserve the order of the (scaffold, side) tuples.  At each endpoint of each edge in turn: the zero-score edges go, of the
+ * others all but the best go -- or all of them when the two best are within a factor 0.8 (logged: amb_best / amb_second
+ * receive the edge indices of every such event, capacity 2 * n_edges).  removed[e] = 1 for the edges to drop from G (and
+ * from G_prime when extend_paths).  Returns the number of ambivalent events, -1 on bad arguments. */
+int64_t besst_scaffold_prune_ambiguous(int64_t n_nodes, int64_t n_edges, const int32_t* eu, const int32_t* ev, const double* score,
+                                       const int64_t* order, uint8_t* removed, int64_t* amb_best, int64_t* amb_second);
+
 /* run all work of this ctx on a caller-owned CUDA stream (a cudaStream_t passed as void*; NULL
  * restores the ctx's own non-blocking stream; pass cudaStreamLegacy (0x1) for the legacy default stream).  Lets a host framework order the library's kernels with its own
  * work (NCCL collectives, CUDA-event timing) without device-wide synchronisation. */
