@@ -11,7 +11,7 @@ python - <<PY
 import json
 d=json.loads(open("$OUT/bench.json").read().strip().splitlines()[-1])
 print("N=1", d["ms_per_step"], "%.4g"%d["value"], "e2e", d["e2e"]["ms_per_step"], "%.4g"%d["e2e"]["value"], "roofline", d["roofline"]["frac"], d["roofline"]["whole_step"]["frac"], "parity", d["parity"]["integers_bit_exact"], d["parity"]["gap_equal"], d["parity"]["score_max_rel_diff"])
-print("pe", d.get("pe_level")); print("libmetrics", d.get("libmetrics")); print("cpu", d["cpu_baseline"]); print(d["clocks"], d["gpu_launches"])
+print("ingest", d.get("ingest")); print("pe", d.get("pe_level")); print("libmetrics", d.get("libmetrics")); print("cpu", d["cpu_baseline"]); print(d["clocks"], d["gpu_launches"])
 print({k: v["ms_per_step"] for k, v in d["kernels"].items()})
 r=json.loads(open("$OUT/bench_reference.json").read().strip().splitlines()[-1]); print("reference arm", "%.4g"%r["value"], r["config"])
 PY
