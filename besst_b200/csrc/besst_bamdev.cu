@@ -281,6 +281,7 @@ struct DevBackend {
     int flags = 0;
     std::string err;
     int read_threads = 4;
+    int64_t chunk_bytes = 32ll << 20;   // file bytes per read + upload step
     double t_read = 0;
     struct Ev { cudaEvent_t a, b; int what; };
     std::vector<Ev> timers;
@@ -301,6 +302,7 @@ struct DevBackend {
     int64_t file_size() const { return fsize; }
     std::string error() const { return err; }
 
+    // file -> pinned staging -> device, chunk by chunk: the host threads read chunk c + 1 while chunk c crosses PCIe
     bool load(int buf, int64_t off, int64_t want, const unsigned char** bytes, int64_t* have) {
         const double t0 = now_s();
         if (S->h2d_pending[buf]) {   // the previous upload out of this staging buffer
@@ -309,24 +311,38 @@ struct DevBackend {
         }
         const int64_t n = std::min<int64_t>(want, fsize - off);
         if (!ok(S->staging[buf].ensure((size_t)n + 64), "cudaHostAlloc(staging)")) return false;
+        if (S->inflated_pending[buf]) {   // the kernel that still reads this compressed buffer / block table
+            if (!ok(cudaStreamWaitEvent(ctx->copy_stream, S->ev_inflated[buf], 0), "cudaStreamWaitEvent")) return false;
+        }
+        // growing a buffer frees the old one: cudaFree synchronises, so a kernel still reading it has finished
+        if (!ok(S->cbuf[buf].ensure((size_t)n + 64), "cudaMalloc(compressed window)")) return false;
         unsigned char* dst = static_cast<unsigned char*>(S->staging[buf].p);
-        const int nt = n >= (8 << 20) ? read_threads : 1;
-        std::vector<std::thread> th;
-        std::vector<int> bad((size_t)nt, 0);
-        auto work = [&](int t) {
-            int64_t a = n * t / nt;
-            const int64_t b = n * (t + 1) / nt;
-            while (a < b) {
-                const ssize_t r = pread(fd, dst + a, (size_t)(b - a), (off_t)(off + a));
-                if (r <= 0) { bad[(size_t)t] = 1; return; }
-                a += r;
-            }
-        };
-        for (int t = 1; t < nt; ++t) th.emplace_back(work, t);
-        work(0);
-        for (auto& x : th) x.join();
-        for (int v : bad) if (v) { err = "read failed"; return false; }
         memset(dst + n, 0, 64);
+        for (int64_t c0 = 0; c0 < n || c0 == 0; c0 += chunk_bytes) {
+            const int64_t c1 = std::min<int64_t>(n, c0 + chunk_bytes), m = c1 - c0;
+            const int nt = m >= (8 << 20) ? read_threads : 1;
+            std::vector<std::thread> th;
+            std::vector<int> bad((size_t)nt, 0);
+            auto work = [&](int t) {
+                int64_t a = c0 + m * t / nt;
+                const int64_t b = c0 + m * (t + 1) / nt;
+                while (a < b) {
+                    const ssize_t r = pread(fd, dst + a, (size_t)(b - a), (off_t)(off + a));
+                    if (r <= 0) { bad[(size_t)t] = 1; return; }
+                    a += r;
+                }
+            };
+            for (int t = 1; t < nt; ++t) th.emplace_back(work, t);
+            work(0);
+            for (auto& x : th) x.join();
+            for (int v : bad) if (v) { err = "read failed"; return false; }
+            const int64_t bytes_now = m + (c1 == n ? 64 : 0);
+            if (!ok(cudaMemcpyAsync(S->cbuf[buf].as<unsigned char>() + c0, dst + c0, (size_t)bytes_now, cudaMemcpyHostToDevice, ctx->copy_stream), "H2D window"))
+                return false;
+            if (c1 >= n) break;
+        }
+        S->h2d_pending[buf] = true;   // staging is in flight from here on; upload() records the event
+        if (!ok(cudaEventRecord(S->ev_h2d[buf], ctx->copy_stream), "cudaEventRecord")) return false;
         *bytes = dst;
         *have = n;
         t_read += now_s() - t0;
@@ -337,13 +353,7 @@ struct DevBackend {
         const size_t nb = W.blocks.size();
         if (!ok(S->tbl_h[buf].ensure(nb * sizeof(bamingest::BlockEntry)), "cudaHostAlloc(block table)")) return false;
         memcpy(S->tbl_h[buf].p, W.blocks.data(), nb * sizeof(bamingest::BlockEntry));
-        if (S->inflated_pending[buf]) {   // the kernel that still reads this compressed buffer / block table
-            if (!ok(cudaStreamWaitEvent(ctx->copy_stream, S->ev_inflated[buf], 0), "cudaStreamWaitEvent")) return false;
-        }
-        // growing a buffer frees the old one: cudaFree synchronises, so a kernel still reading it has finished
-        if (!ok(S->cbuf[buf].ensure((size_t)W.consumed + 64), "cudaMalloc(compressed window)")) return false;
         if (!ok(S->tbl_d[buf].ensure(nb * sizeof(bamingest::BlockEntry)), "cudaMalloc(block table)")) return false;
-        if (!ok(cudaMemcpyAsync(S->cbuf[buf].p, S->staging[buf].p, (size_t)W.consumed + 64, cudaMemcpyHostToDevice, ctx->copy_stream), "H2D window")) return false;
         if (!ok(cudaMemcpyAsync(S->tbl_d[buf].p, S->tbl_h[buf].p, nb * sizeof(bamingest::BlockEntry), cudaMemcpyHostToDevice, ctx->copy_stream), "H2D block table")) return false;
         if (!ok(cudaEventRecord(S->ev_h2d[buf], ctx->copy_stream), "cudaEventRecord")) return false;
         S->h2d_pending[buf] = true;
@@ -554,7 +564,9 @@ extern "C" int besst_bam_ingest_part(besst_ctx* ctx, const char* path, int64_t h
     if (const char* e = getenv("BESST_BAM_WINDOW")) { const long long v = atoll(e); if (v >= 1024) opt.window_bytes = v; }
     if (const char* e = getenv("BESST_BAM_MAX_INFLATED")) { const long long v = atoll(e); if (v >= 65536) opt.max_inflated = v; }
     if (const char* e = getenv("BESST_BAM_CARRY")) { const long long v = atoll(e); if (v >= 64) opt.carry_max = (v + 3) / 4 * 4; }
+    B.read_threads = std::min(12, std::max(4, (int)std::thread::hardware_concurrency()));
     if (const char* e = getenv("BESST_BAM_READ_THREADS")) { const int v = atoi(e); if (v >= 1 && v <= 64) B.read_threads = v; }
+    if (const char* e = getenv("BESST_BAM_CHUNK")) { const long long v = atoll(e); if (v >= 4096) B.chunk_bytes = v; }
     opt.window_bytes = std::min<int64_t>(opt.window_bytes, std::max<int64_t>(B.fsize, 1024));
 
     bamingest::Result res;
