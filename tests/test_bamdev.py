@@ -31,6 +31,7 @@ def hostcheck():
     if _hc is None:
         L = C.CDLL(build.build_hostcheck())
         L.bgzf_hc_inflate.argtypes = [C.c_char_p, C.c_uint32, C.c_int, C.c_void_p, C.c_uint32]
+        L.bgzf_hc_set_width.argtypes = [C.c_int]
         L.bgzf_hc_crc32.restype = C.c_uint32
         L.bgzf_hc_crc32.argtypes = [C.c_char_p, C.c_uint32, C.c_int]
         L.bgzf_hc_ingest.restype = C.c_void_p
@@ -109,6 +110,49 @@ def test_inflate_and_crc_equal_zlib(level):
             assert L.bgzf_hc_inflate(c, len(c), mis, out.ctypes.data, len(data)) == 0
             assert out[:len(data)].tobytes() == data
             assert L.bgzf_hc_crc32(data, len(data), mis) == (zlib.crc32(data) & 0xffffffff)
+
+
+def test_inflate_fuzz_against_zlib():
+    """400 random streams: every zlib level, window size 2^9..2^15, memLevel, the strategies (default, filtered, Huffman-only,
+    RLE, fixed codes), SYNC / FULL flushes in the middle (empty stored blocks, several deflate blocks per stream), payloads
+    from incompressible to one repeated byte; placement rounds of 32 and of 8 lanes"""
+    L = hostcheck()
+    rng = np.random.default_rng(123)
+
+    def payload():
+        kind, n = int(rng.integers(6)), int(rng.integers(1, 65537))
+        if kind == 0:
+            return bytes(rng.integers(0, 256, n, dtype=np.uint8))
+        if kind == 1:
+            return bytes(rng.integers(0, int(rng.integers(2, 20)), n, dtype=np.uint8))
+        if kind == 2:
+            return bytes(np.repeat(rng.integers(0, 256, max(1, n // 50), dtype=np.uint8), 50))[:n]
+        if kind == 3:
+            return (bytes(rng.integers(0, 256, int(rng.integers(1, 300)), dtype=np.uint8)) * 70000)[:n]
+        if kind == 4:
+            return b"".join(b"read%07d\0" % i + bytes(rng.integers(33, 74, 40, dtype=np.uint8)) for i in range(n // 52 + 1))[:n]
+        return bytes(rng.choice(np.array([0, 255, 17, 34], np.uint8), n, p=[0.7, 0.1, 0.1, 0.1]))
+    try:
+        for trial in range(400):
+            L.bgzf_hc_set_width(32 if trial % 2 else 8)
+            data = payload()
+            strategy = [zlib.Z_DEFAULT_STRATEGY, zlib.Z_FILTERED, zlib.Z_HUFFMAN_ONLY, zlib.Z_RLE, zlib.Z_FIXED][int(rng.integers(5))]
+            co = zlib.compressobj(int(rng.integers(0, 10)), zlib.DEFLATED, -int(rng.integers(9, 16)), int(rng.integers(1, 10)), strategy)
+            parts, prev = [], 0
+            for c in sorted(set(int(x) for x in rng.integers(0, len(data) + 1, int(rng.integers(0, 4))))):
+                parts.append(co.compress(data[prev:c]))
+                prev = c
+                if rng.random() < 0.7:
+                    parts.append(co.flush([zlib.Z_SYNC_FLUSH, zlib.Z_FULL_FLUSH, zlib.Z_NO_FLUSH][int(rng.integers(3))]))
+            parts += [co.compress(data[prev:]), co.flush()]
+            c = b"".join(parts)
+            out = np.zeros(len(data) + 8, np.uint8)
+            mis = int(rng.integers(4))
+            assert L.bgzf_hc_inflate(c, len(c), mis, out.ctypes.data, len(data)) == 0, trial
+            assert out[:len(data)].tobytes() == data, trial
+            assert L.bgzf_hc_crc32(data, len(data), mis) == (zlib.crc32(data) & 0xffffffff)
+    finally:
+        L.bgzf_hc_set_width(32)
 
 
 def test_inflate_rejects_damaged_streams():
