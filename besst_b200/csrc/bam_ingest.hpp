@@ -125,11 +125,11 @@ static inline bool scan_block_headers(const unsigned char* f, int64_t have, int6
     }
     w->consumed = o;
     w->last = file_off + o >= range_hi || file_off + o >= file_size;
-    if (o == 0 && have > 0) {
-        *why = file_off + have >= file_size ? "truncated BGZF block at the end of the file" : "BGZF block larger than the window";
+    if (o == 0 && have > 0 && file_off + have >= file_size) {
+        *why = "truncated BGZF block at the end of the file";
         return false;
     }
-    return true;
+    return true;   // consumed == 0 with more file behind: the first block is larger than what was read (the caller reads more)
 }
 
 // BAM header (SAM spec 4.2) from the first `have` inflated bytes.  -> 1 parsed (*end = first record), 0 need more bytes,
@@ -248,9 +248,16 @@ int run(Backend& B, const Options& opt, Result* res, std::string* why) {
             const unsigned char* bytes = nullptr;
             int64_t have = 0;
             // a window that reaches the end of the range takes the tail with it
-            const int64_t want = (foff + window >= own_end || window > rd_end - foff) ? rd_end - foff : window;
+            int64_t want = (foff + window >= own_end || window > rd_end - foff) ? rd_end - foff : window;
             if (!B.load(buf, foff, want, &bytes, &have)) { *why = B.error(); return -1; }
             if (!scan_block_headers(bytes, have, foff, fsize, own_end, BASE, opt, &win[buf], &st.blocks, why)) return -1;
+            if (win[buf].consumed == 0) {   // a window smaller than one BGZF block (<= 64 KB): read a whole block's worth
+                want = fsize - foff < (1ll << 17) ? fsize - foff : (1ll << 17);
+                if (want <= have) { *why = "corrupt BGZF block (longer than 64 KB)"; return -1; }
+                if (!B.load(buf, foff, want, &bytes, &have)) { *why = B.error(); return -1; }
+                if (!scan_block_headers(bytes, have, foff, fsize, own_end, BASE, opt, &win[buf], &st.blocks, why)) return -1;
+                if (win[buf].consumed == 0) { *why = "corrupt BGZF block (longer than 64 KB)"; return -1; }
+            }
             foff += win[buf].consumed;
             if (win[buf].n_owned == 0) {   // nothing but empty blocks (the EOF marker) or tail blocks
                 if (win[buf].last) return 0;

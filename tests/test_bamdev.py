@@ -200,6 +200,34 @@ def test_host_rendered_ingest_equals_python_reader(tmp_path, n, block_bytes):
             assert np.array_equal(got["packed"], py.flag.astype(np.uint32) | (py.mapq.astype(np.uint32) << 12) | (py.qlen.astype(np.uint32) << 20))
 
 
+def _long_record_file(path, block_bytes):
+    """400 records of which five are 150-400 KB long (long reads): each spans several BGZF blocks, whole blocks lie inside a
+    record, flag / qlen do not fit the packed column"""
+    rng = np.random.default_rng(3)
+    refs = [("c%d" % i, 100000 + i) for i in range(9)]
+    recs = tb._random_records(rng, 400, len(refs))
+    for k in (5, 120, 121, 300, 399):
+        n = int(rng.integers(150000, 400000))
+        recs[k] = dict(tid=1, pos=100 + k, mapq=33, flag=99, l_seq=n, mtid=2, mpos=5, tlen=1234, cigar=[(4, 10), (0, n - 30), (4, 20)], name="long%d" % k)
+    tb.write_bam(path, refs, recs, block_bytes)
+    return bamio.read_bam(path)
+
+
+@pytest.mark.parametrize("block_bytes", [65280, 3000])
+def test_host_rendered_ingest_of_records_longer_than_a_block(tmp_path, block_bytes):
+    path = str(tmp_path / "long.bam")
+    py = _long_record_file(path, block_bytes)
+    for window, carry, blind in [(0, 0, False), (0, 0, True), (2048, 1 << 20, False), (2048, 1 << 20, True)]:
+        got = host_ingest(path, window, 0, carry, blind=blind)
+        assert_columns_equal(got, py)
+        assert got["stats"]["unpackable"] == 5
+        assert (got["stats"]["rescans"] > 0) == blind
+        if window:
+            assert got["stats"]["windows"] >= 2
+    with pytest.raises(IOError, match="carry buffer"):
+        host_ingest(path, 2048, 0, 4096)    # a 4 KB carry cannot hold the head of a 150 KB record
+
+
 def test_host_rendered_ingest_errors(tmp_path):
     rng = np.random.default_rng(5)
     refs = [("c%d" % i, 1000 + i) for i in range(5)]
@@ -308,6 +336,22 @@ def test_device_ingest_equals_python_reader(tmp_path, engine, n, block_bytes):
             assert dev.stats["rescans"] == 0
         elif n >= 5000 and block_bytes < 65000:
             assert dev.stats["rescans"] > 0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("block_bytes", [65280, 3000])
+def test_device_ingest_of_records_longer_than_a_block(tmp_path, engine, block_bytes):
+    from besst_b200._lib import BesstLibraryError
+    path = str(tmp_path / "long.bam")
+    py = _long_record_file(path, block_bytes)
+    for env, blind in [({}, False), ({}, True), ({"BESST_BAM_WINDOW": 2048, "BESST_BAM_CARRY": 1 << 20}, False),
+                       ({"BESST_BAM_WINDOW": 2048, "BESST_BAM_CARRY": 1 << 20}, True)]:
+        dev = _with_env(env, lambda: engine.ingest_bam(path, blind_seeds=blind))
+        assert_columns_equal(dev.to_host(), py)
+        assert not dev.abi_records.packed      # flag | mapq | qlen does not fit 32 bits for the long records
+        assert (dev.stats["rescans"] > 0) == blind
+    with pytest.raises(BesstLibraryError, match="carry buffer"):
+        _with_env({"BESST_BAM_WINDOW": 2048, "BESST_BAM_CARRY": 4096}, lambda: engine.ingest_bam(path))
 
 
 @pytest.mark.gpu
