@@ -379,12 +379,8 @@ def engine_params(param, halo=(-1, -1)):
 
 def _world():
     """(rank, world size) of the torch.distributed job this process belongs to, (0, 1) outside one."""
-    if int(os.environ.get("WORLD_SIZE", "1")) <= 1 and "torch.distributed" not in sys.modules:
-        return 0, 1
-    import torch.distributed as dist
-    if not (dist.is_available() and dist.is_initialized()):
-        return 0, 1
-    return dist.get_rank(), dist.get_world_size()
+    from .records import world
+    return world()
 
 
 def graph_build_distributed(engine, table, params, batch, rank, world):
@@ -394,11 +390,15 @@ def graph_build_distributed(engine, table, params, batch, rank, world):
     (fetch_global), so that all processes continue with the identical CSR -- the order-dependent post-filters
     below and BESST's consumers run replicated, as the single-process program would."""
     from .dist import DistributedGraphBuild
-    n = len(batch)
-    bounds = [(n * r // world) - ((n * r // world) % 128) for r in range(world)] + [n]
     backend = engine.make_dist_backend(table)
     runner = DistributedGraphBuild(backend, rank, world)
-    runner.step(params, backend.records(batch.slice(bounds[rank], bounds[rank + 1])))
+    if getattr(batch, "dist_info", None):   # the rank's own part of the file, as the distributed ingest left it (device or host columns)
+        mine = batch
+    else:
+        n = len(batch)
+        bounds = [(n * r // world) - ((n * r // world) % 128) for r in range(world)] + [n]
+        mine = batch.slice(bounds[rank], bounds[rank + 1])
+    runner.step(params, backend.records(mine) if hasattr(backend, "records") else mine)
     return runner.fetch_global()
 
 

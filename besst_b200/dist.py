@@ -522,6 +522,26 @@ def merge_graph_results(parts):
                            counters=first.counters, **fields)
 
 
+_host_group = []
+
+
+def host_group():
+    """A gloo group over all ranks for the small Python-object collectives of the ingest (offsets, library metrics): created
+    once, collectively, at first use; None (the default group) when the job itself runs on gloo."""
+    import torch.distributed as dist
+    if not _host_group:
+        _host_group.append(None if dist.get_backend() == "gloo" else dist.new_group(backend="gloo"))
+    return _host_group[0]
+
+
+def rank0_value(fn, rank, group=None):
+    """fn() evaluated on rank 0, its (picklable) result on every rank"""
+    import torch.distributed as dist
+    box = [fn() if rank == 0 else None]
+    dist.broadcast_object_list(box, src=0, group=group)
+    return box[0]
+
+
 def ingest_bam_distributed(engine, path, rank, world, group=None, **ingest_kw):
     """Multi-GPU BAM ingest (SURVEY.md 8e + 8f rank 1): rank r inflates and decodes the r-th part of the file on its own
     GPU (besst_bam_ingest_part: the BGZF blocks starting in its byte range, the records starting in those blocks), so a

@@ -68,6 +68,13 @@ def metric_rows(lengths):
     return rows
 
 
+def _get_metrics_whole_file(path, param, Information, engine):
+    """the library's head does not lie inside rank 0's part: read the whole file on host threads for this call"""
+    from .bamio import read_bam_native
+    from .records import BatchFile
+    return get_metrics(BatchFile(read_bam_native(path)), param, Information, engine=engine)
+
+
 def get_metrics(bam_file, param, Information, engine=None):
     bam_file = as_file(bam_file, engine)   # a path: decoded once by the native ingest library
     cont_names = bam_file.references
@@ -79,9 +86,20 @@ def get_metrics(bam_file, param, Information, engine=None):
         sys.stderr.write('Need indexed bamfiles, index file should be located in the same directory as the BAM file\nterminating..\n')
         sys.exit(0)
     batch = as_batch(bam_file)
+    parts = getattr(batch, "dist_info", None)   # a process group ingested the file in parts (dist.ingest_bam_distributed)
+    if parts is not None:
+        # the metrics read a BAM-order PREFIX of the library (the first 1000 records, then the capped sampling scans): when
+        # rank 0's part covers that prefix its result is the whole file's and is broadcast; otherwise every rank falls back
+        # to the host reader for this call (PE keeps working on the parts)
+        from .dist import host_group, rank0_value
+        total = sum(parts["counts"])
+        if min(total, 1000) > parts["counts"][0]:
+            return _get_metrics_whole_file(parts["path"], param, Information, engine)
 
     if not param.read_len:
-        read_len = estimate_read_length(batch)
+        read_len = estimate_read_length(batch) if parts is None else rank0_value(lambda: estimate_read_length(batch), parts["rank"], host_group())
+        if parts is not None and read_len is None and total >= 1000:
+            return _get_metrics_whole_file(parts["path"], param, Information, engine)
         if read_len is None:
             sys.stderr.write('Did not get sufficient readmappings to calculate\
              read_length from mappings. Got {0} mappings. Please provide this parameter or more importantly\
@@ -101,8 +119,20 @@ def get_metrics(bam_file, param, Information, engine=None):
                              param.std_dev_ins_size, param.ins_size_threshold,
                              detect_duplicate=param.detect_duplicate, extend_paths=param.extend_paths,
                              no_score=param.no_score)
-    rc, m, adj = engine.libmetrics(metric_rows(cont_lengths), params, batch, cont_lengths, want_isize,
-                                   cap=ISIZE_DICT_CAP)
+    if parts is None:
+        rc, m, adj = engine.libmetrics(metric_rows(cont_lengths), params, batch, cont_lengths, want_isize,
+                                       cap=ISIZE_DICT_CAP)
+    else:
+        def on_rank0():
+            rc0, m0, adj0 = engine.libmetrics(metric_rows(cont_lengths), params, batch, cont_lengths, want_isize, cap=ISIZE_DICT_CAP)
+            # complete: the capped scans stopped inside rank 0's part (or it is the whole file)
+            complete = int(m0.records_scanned) < len(batch) or total == len(batch)
+            return complete, rc0, {f: getattr(m0, f) for f, _ in abi.LibMetricsOut._fields_}, np.array(adj0)
+        complete, rc, fields, adj = rank0_value(on_rank0, parts["rank"], host_group())
+        if not complete:
+            return _get_metrics_whole_file(parts["path"], param, Information, engine)
+        import types
+        m = types.SimpleNamespace(**fields)
 
     if want_isize:
         line = "Estimating insert size from {0} mappings with quality over --min_mapq {1}.".format(m.n_samples + 1, param.min_mapq)

@@ -178,20 +178,35 @@ class DeviceRecordBatch(object):
         return RecordBatch(references=self.references, lengths=self.lengths, rlen=rlen, alen=alen, packed=packed, **cols)
 
 
-def ingest_mode():
-    """'device' (BGZF inflate + decode on the GPU, columns stay in HBM) or 'host' (libbesst_bamio.so, host threads):
-    how the entry points turn a BAM path into records.  BESST_B200_INGEST overrides; under a process group (one
-    library range-partitioned over ranks) the host reader is used, the ranks slice its columns."""
+def world():
+    """(rank, world size) of the torch.distributed job this process belongs to, (0, 1) outside one."""
     import os
-    mode = os.environ.get("BESST_B200_INGEST", DEFAULT_INGEST)
+    import sys
+    if int(os.environ.get("WORLD_SIZE", "1")) <= 1 and "torch.distributed" not in sys.modules:
+        return 0, 1
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()):
+        return 0, 1
+    return dist.get_rank(), dist.get_world_size()
+
+
+def ingest_mode():
+    """How the entry points turn a BAM path into records: 'device' (BGZF inflate + decode on the GPU, columns stay in
+    HBM; under a process group every rank ingests ITS part of the file, dist.ingest_bam_distributed) or 'host'
+    (libbesst_bamio.so on host threads; under a process group every rank decodes the whole file and slices it).
+    BESST_B200_INGEST overrides the default, which is 'device' in a single process and DEFAULT_INGEST_DISTRIBUTED under a
+    process group."""
+    import os
+    mode = os.environ.get("BESST_B200_INGEST")
+    if mode is None:
+        mode = DEFAULT_INGEST if world()[1] <= 1 else DEFAULT_INGEST_DISTRIBUTED
     if mode not in ("device", "host"):
         raise ValueError("BESST_B200_INGEST must be 'device' or 'host', not %r" % mode)
-    if mode == "device" and int(os.environ.get("WORLD_SIZE", "1")) > 1:
-        return "host"
     return mode
 
 
 DEFAULT_INGEST = "device"
+DEFAULT_INGEST_DISTRIBUTED = "host"
 
 
 class BatchFile(object):
@@ -233,7 +248,14 @@ def as_file(bam_file, engine=None):
             if ingest_mode() == "device" and engine is None:
                 from .engine import default_engine
                 engine = default_engine()   # raises without a GPU: the product path has no CPU fallback
-            if ingest_mode() == "device" and hasattr(engine, "ingest_bam"):
+            rank, n_ranks = world()
+            if ingest_mode() == "device" and hasattr(engine, "ingest_bam") and n_ranks > 1:
+                # every rank its part of the file, already in the BAM-order partition the distributed build takes
+                from .dist import host_group, ingest_bam_distributed
+                part, info = ingest_bam_distributed(engine, key, rank, n_ranks, group=host_group())
+                part.dist_info = dict(info, rank=rank, world=n_ranks, path=key)
+                hit = (stamp, BatchFile(part))
+            elif ingest_mode() == "device" and hasattr(engine, "ingest_bam"):
                 hit = (stamp, BatchFile(engine.ingest_bam(key)))
             else:
                 from .bamio import read_bam_native
@@ -246,7 +268,7 @@ def as_file(bam_file, engine=None):
 def as_batch(bam_file):
     """RecordBatch behind a `bam_file` argument: a RecordBatch, a path to a BAM file (decoded by
     libbesst_bamio.so), anything carrying `.record_batch`, or a pysam-like iterable of AlignedRead."""
-    if isinstance(bam_file, (RecordBatch, DeviceRecordBatch)):
+    if isinstance(bam_file, (RecordBatch, DeviceRecordBatch)) or getattr(bam_file, "dist_info", None):
         return bam_file
     if isinstance(bam_file, (str, bytes)) or hasattr(bam_file, "__fspath__"):   # a path: native threaded ingest
         from .bamio import read_bam_native

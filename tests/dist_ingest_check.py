@@ -71,6 +71,27 @@ def main():
             world, len(batch), info["counts"], info["repeats"], merged.n_edges, merged.n_links))
     dist.barrier()
 
+    # ---- the Python entry points on a PATH under the process group: every rank ingests its part on its GPU, rank 0's
+    #      library metrics are broadcast (or the whole file is read when the sampled prefix is not inside part 0), PE builds
+    #      from the parts -- same graphs as with the host reader (every rank decodes the whole file and slices it) ----------
+    from besst_b200 import records
+    lengths = dict(zip(batch.references, [int(x) for x in batch.lengths]))
+    sigs = {}
+    for mode in ("host", "device"):
+        os.environ["BESST_B200_INGEST"] = mode
+        records._open_cache.clear()
+        out = helpers.run_dropin(None, dict(orientation=lib.orientation, mean=None, stddev=None, readlen=None), eng,
+                                 fasta_lengths=lengths, bam_path=small)
+        sigs[mode] = {k: out[k] for k in ("G", "G_prime", "param", "objects")}
+        dist.barrier()
+    os.environ.pop("BESST_B200_INGEST", None)
+    assert sigs["host"] == sigs["device"], "entry points: device parts != host reader"
+    assert len(sigs["device"]["G_prime"]["edges"]) > 0
+    if rank == 0:
+        print("DIST_ENTRY_OK world=%d: get_metrics + PE on a path, ingest in parts on the devices == host reader (%d G_prime edges)" % (
+            world, len(sigs["device"]["G_prime"]["edges"])))
+    dist.barrier()
+
     # ---- aggregate ingest rate -----------------------------------------------------------------------------------------------
     ingest_bam_distributed(eng, big, rank, world, group=host_group)   # warm-up: page cache, buffers
     best = None

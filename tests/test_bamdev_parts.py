@@ -58,6 +58,52 @@ class HostcheckEngine(object):
         return out
 
 
+class _PartEngine(object):
+    """what the entry points need from an engine under a process group, without a GPU: ingest_bam over the host rendering of
+    the device ingest (a RecordBatch of the part's columns + its virtual offsets), library metrics from the C oracle, the
+    numpy backend for the distributed build"""
+
+    def __init__(self):
+        from oracle_engine import OracleEngine
+        self._o = OracleEngine()
+        self.libmetrics = self._o.libmetrics
+        self.gapest_batch = self._o.gapest_batch
+        self.ingest_calls = 0
+
+    def graph_build(self, *a, **k):
+        raise AssertionError("PE must take the distributed build when the process group has more than one rank")
+
+    def make_dist_backend(self, table):
+        from dist_backend_numpy import NumpyBackend
+        return NumpyBackend(table)
+
+    def ingest_bam(self, path, part=(0, 1), start_voffset=-1, **kw):
+        from besst_b200.records import RecordBatch
+        L = t.hostcheck()
+        L.bgzf_hc_ingest_part.restype = C.c_void_p
+        L.bgzf_hc_ingest_part.argtypes = [C.c_char_p, C.c_int64, C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_int64, C.c_int, C.c_int,
+                                          C.c_int64, C.c_int64, C.c_char_p, C.c_int]
+        err = C.create_string_buffer(512)
+        h = L.bgzf_hc_ingest_part(os.fsencode(path), 0, 0, 0, 1, 0, 1000, part[0], part[1], start_voffset, 0, err, 512)
+        if not h:
+            raise IOError(err.value.decode())
+        n, nh = L.bgzf_hc_n(h), L.bgzf_hc_n_head(h)
+
+        def col(i, dt, count):
+            p = L.bgzf_hc_column(h, i)
+            return np.frombuffer((C.c_char * (count * np.dtype(dt).itemsize)).from_address(p), dtype=dt, count=count).copy() if count else np.zeros(0, dt)
+        cols = {k: col(i, dt, n) for i, (k, dt) in enumerate(t.COLS[:8])}
+        rlen, alen = np.zeros(n, np.int32), np.zeros(n, np.int32)
+        rlen[:nh], alen[:nh] = col(9, np.int32, nh), col(10, np.int32, nh)
+        batch = RecordBatch(references=[L.bgzf_hc_ref_name(h, i).decode() for i in range(L.bgzf_hc_n_refs(h))],
+                            lengths=[int(L.bgzf_hc_ref_length(h, i)) for i in range(L.bgzf_hc_n_refs(h))], rlen=rlen, alen=alen,
+                            packed=col(8, np.uint32, n), **cols)
+        batch.first_voffset, batch.landing_voffset = int(L.bgzf_hc_stat(h, 7)), int(L.bgzf_hc_stat(h, 8))
+        L.bgzf_hc_close(h)
+        self.ingest_calls += 1
+        return batch
+
+
 def _ragged_file(path, n, block_bytes, n_refs=37):
     rng = np.random.default_rng(n + block_bytes)
     refs = [("c%d,pos:%d-%d,rc:0" % (i, i * 1000, i * 1000 + 900), 900 + i) for i in range(n_refs)]
@@ -139,6 +185,69 @@ def test_distributed_ingest_protocol_gloo(tmp_path, world, blind):
     assert (repeats > 0) == blind
     if blind:
         assert sum(int(q["calls"]) for q in parts) == world + repeats
+
+
+def _entry_worker(rank, world, port, path, lengths, opts, overrides, out_dir):
+    for p in (ROOT, os.path.join(ROOT, "oracle"), HERE):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    os.environ["BESST_B200_INGEST"] = "device"
+    import json
+    import torch.distributed as dist
+    import helpers
+    dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%d" % port, rank=rank, world_size=world)
+    try:
+        eng = _PartEngine()
+        from besst_b200 import bamio as _bamio
+        whole_file_reads = []
+        real = _bamio.read_bam_native
+        _bamio.read_bam_native = lambda *a, **k: (whole_file_reads.append(1), real(*a, **k))[1]
+        out = helpers.run_dropin(None, opts, eng, fasta_lengths=lengths, bam_path=path, param_overrides=overrides)
+        assert eng.ingest_calls >= 1
+        json.dump(dict({k: out[k] for k in ("G", "G_prime", "param", "objects")}, whole_file_reads=len(whole_file_reads)),
+                  open(os.path.join(out_dir, "rank%d.json" % rank), "w"))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("pairs,world,estimate", [(2400000, 2, True), (150000, 3, True), (150000, 2, False)])
+def test_entry_points_on_a_path_under_a_process_group_ingest_in_parts(tmp_path, pairs, world, estimate):
+    """libmetrics.get_metrics + CreateGraph.PE on a BAM PATH in a gloo job with BESST_B200_INGEST=device: every rank ingests
+    its part (host rendering of the device ingest), rank 0's library metrics are broadcast when its part covers the sampled
+    prefix (2.4 M PE pairs: the 1e6-sample cap is reached after 2.27 M records, inside part 0 of 2) and the whole file is read on host threads otherwise
+    (150 k pairs), PE builds from the parts -- every rank must end with the graphs, parameters and objects of a
+    single-process run on the same file"""
+    import json
+    import torch.multiprocessing as mp
+    import helpers
+    import oracle_lib
+    from oracle_engine import OracleEngine
+    oracle_lib.build()
+    big = pairs > 1000000
+    orient, mu, sd = ("fr", 550.0, 50.0) if big else ("rf", 3000.0, 500.0)
+    lib = synth.make_library(max(50, pairs // 10000), pairs, orient, mu, sd, 0.0, seed=17)
+    batch = lib.to_batch()
+    path = str(tmp_path / "lib.bam")
+    bamio.write_bam_columns(path, batch, level=0 if pairs > 1000000 else 1, style="packed")
+    lengths = dict(zip(batch.references, [int(x) for x in batch.lengths]))
+    opts = dict(orientation=orient, mean=None if estimate else mu, stddev=None if estimate else sd, readlen=None if estimate else 100)
+    overrides = {"no_score": True}   # the numpy backend of the distributed build has no scores
+    os.environ["BESST_B200_INGEST"] = "host"
+    try:
+        from besst_b200 import records
+        records._open_cache.clear()
+        want = helpers.run_dropin(None, opts, OracleEngine(), fasta_lengths=lengths, bam_path=path, param_overrides=overrides)
+    finally:
+        os.environ.pop("BESST_B200_INGEST", None)
+    want = json.loads(json.dumps({k: want[k] for k in ("G", "G_prime", "param", "objects")}))
+    mp.spawn(_entry_worker, args=(world, _free_port(), path, lengths, opts, overrides, str(tmp_path)), nprocs=world, join=True)
+    for r in range(world):
+        got = json.load(open(str(tmp_path / ("rank%d.json" % r))))
+        for k in ("G", "G_prime", "param", "objects"):
+            assert got[k] == want[k], (r, k)
+        if estimate:   # the metrics came from rank 0's part when it holds the sampled prefix, from the whole file otherwise
+            assert got["whole_file_reads"] == (0 if pairs > 1000000 else 1), (r, got["whole_file_reads"])
+    assert len(want["G_prime"]["edges"]) > 0
 
 
 # ---- GPU ------------------------------------------------------------------------------------------------------------------
