@@ -206,7 +206,7 @@ def ingest_mode():
 
 
 DEFAULT_INGEST = "device"
-DEFAULT_INGEST_DISTRIBUTED = "host"
+DEFAULT_INGEST_DISTRIBUTED = "device"
 
 
 class BatchFile(object):

@@ -30,7 +30,7 @@ from besst_b200.engine import CudaEngine  # noqa: E402
 
 
 def main():
-    pairs = int(sys.argv[1]) if len(sys.argv) > 1 else 2000000
+    pairs = int(sys.argv[1]) if len(sys.argv) > 1 else 2400000
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
@@ -43,7 +43,8 @@ def main():
     if rank == 0:
         oracle_lib.build()
         bamio.write_bam_columns(small, batch, style="packed")   # records straddle BGZF blocks and part boundaries
-        bamio.write_bam_columns(big, synth.make_library(max(50, pairs // 2000), pairs, "rf", 3000.0, 500.0, 0.0, seed=5).to_batch())
+        # a PE library whose first half holds the 1e6 insert-size samples of libmetrics (reached after ~2.3 M records)
+        bamio.write_bam_columns(big, synth.make_library(max(50, pairs // 10000), pairs, "fr", 550.0, 50.0, 0.0, seed=17).to_batch())
     dist.barrier()
     eng = CudaEngine(local)
     torch.cuda.set_stream(torch.cuda.Stream(device=dev))
@@ -75,22 +76,32 @@ def main():
     #      library metrics are broadcast (or the whole file is read when the sampled prefix is not inside part 0), PE builds
     #      from the parts -- same graphs as with the host reader (every rank decodes the whole file and slices it) ----------
     from besst_b200 import records
-    lengths = dict(zip(batch.references, [int(x) for x in batch.lengths]))
-    sigs = {}
-    for mode in ("host", "device"):
-        os.environ["BESST_B200_INGEST"] = mode
-        records._open_cache.clear()
-        out = helpers.run_dropin(None, dict(orientation=lib.orientation, mean=None, stddev=None, readlen=None), eng,
-                                 fasta_lengths=lengths, bam_path=small)
-        sigs[mode] = {k: out[k] for k in ("G", "G_prime", "param", "objects")}
+    whole_file_reads = []
+    real_reader = bamio.read_bam_native
+    bamio.read_bam_native = lambda *a, **k: (whole_file_reads.append(1), real_reader(*a, **k))[1]
+    for label, path, orient in (("small", small, lib.orientation), ("big", big, "fr")):
+        hdr = eng.ingest_bam(path, part=(0, max(world, 64)))   # header only (a sliver of the file)
+        lengths = dict(zip(hdr.references, hdr.lengths))
+        sigs, reads = {}, {}
+        for mode in ("host", "device"):
+            os.environ["BESST_B200_INGEST"] = mode
+            records._open_cache.clear()
+            del whole_file_reads[:]
+            out = helpers.run_dropin(None, dict(orientation=orient, mean=None, stddev=None, readlen=None), eng,
+                                     fasta_lengths=lengths, bam_path=path)
+            sigs[mode] = {k: out[k] for k in ("G", "G_prime", "param", "objects")}
+            reads[mode] = len(whole_file_reads)
+            dist.barrier()
+        os.environ.pop("BESST_B200_INGEST", None)
+        assert sigs["host"] == sigs["device"], "entry points on %s: device parts != host reader" % label
+        assert len(sigs["device"]["G_prime"]["edges"]) > 0
+        # small: the sampled prefix is the whole file -> every rank reads it once for the metrics; big (world 2): it lies
+        # inside part 0 -> no rank reads the whole file
+        if rank == 0:
+            print("DIST_ENTRY_OK world=%d %s: get_metrics + PE on a path, ingest in parts on the devices == host reader "
+                  "(%d G_prime edges; whole-file reads in device mode: %d)" % (world, label, len(sigs["device"]["G_prime"]["edges"]), reads["device"]))
         dist.barrier()
-    os.environ.pop("BESST_B200_INGEST", None)
-    assert sigs["host"] == sigs["device"], "entry points: device parts != host reader"
-    assert len(sigs["device"]["G_prime"]["edges"]) > 0
-    if rank == 0:
-        print("DIST_ENTRY_OK world=%d: get_metrics + PE on a path, ingest in parts on the devices == host reader (%d G_prime edges)" % (
-            world, len(sigs["device"]["G_prime"]["edges"])))
-    dist.barrier()
+    bamio.read_bam_native = real_reader
 
     # ---- aggregate ingest rate -----------------------------------------------------------------------------------------------
     ingest_bam_distributed(eng, big, rank, world, group=host_group)   # warm-up: page cache, buffers
