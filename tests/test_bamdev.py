@@ -408,6 +408,20 @@ def test_device_ingest_feeds_the_graph_build_without_leaving_hbm(tmp_path, engin
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("level", [0, 9])
+def test_device_ingest_of_stored_and_best_compression_files(tmp_path, engine, level):
+    """level 0: every BGZF block is a stored deflate block (`samtools view -u`): the warp-wide copy from the compressed
+    stream; level 9: long matches, lazy matching"""
+    lib = synth.make_library(80, 40000, "rf", 3000.0, 500.0, 0.0, seed=19)
+    batch = lib.to_batch()
+    path = str(tmp_path / "lib.bam")
+    bamio.write_bam_columns(path, batch, level=level, style="packed")
+    dev = _with_env({"BESST_BAM_WINDOW": 1 << 20}, lambda: engine.ingest_bam(path))
+    assert dev.stats["windows"] > 1
+    assert_columns_equal(dev.to_host(), batch_with_lengths(batch))
+
+
+@pytest.mark.gpu
 def test_entry_points_on_a_bam_path_with_device_ingest(tmp_path, engine):
     """libmetrics.get_metrics + CreateGraph.PE on a PATH: device ingest == host-thread ingest, graph for graph"""
     lib = synth.make_config("small_mp")
