@@ -21,22 +21,26 @@ from ._lib import load
 def graph_csr(G_prime):
     """networkx G_prime -> (nodes in id order, adj_ptr, adj_node, adj_links).  id = 2 * rank(scaffold key) + (side == 'R')
     with ranks ascending in the key: integer order == tuple order; the contig edge carries -1 (its nr_links is None)."""
-    keys = sorted({n[0] for n in G_prime})
+    adj = getattr(G_prime, "_adj", None)   # the plain dict-of-dicts (networkx >= 2); `adj` itself in 1.x
+    if adj is None:
+        adj = G_prime.adj
+    keys = sorted({n[0] for n in adj})
     rank = {k: i for i, k in enumerate(keys)}
     n_nodes = 2 * len(keys)
-    adj = G_prime.adj if hasattr(G_prime, "adj") else G_prime.edge
-    ptr = np.zeros(n_nodes + 1, dtype=np.int64)
+    counts = np.zeros(n_nodes + 1, dtype=np.int64)
     ids, links = [], []
-    for k in keys:
-        for side, bit in (("L", 0), ("R", 1)):
-            nbrs = adj.get((k, side), {})
+    empty = {}
+    for i, k in enumerate(keys):
+        for bit, side in enumerate(("L", "R")):
+            nbrs = adj.get((k, side), empty)
+            counts[2 * i + bit + 1] = len(nbrs)
             for nb, data in nbrs.items():
                 ids.append(2 * rank[nb[0]] + (nb[1] == "R"))
-                nl = data.get("nr_links")
-                links.append(-1 if nl is None else int(nl))
-            ptr[2 * rank[k] + bit + 1] = len(ids)
+                links.append(data.get("nr_links"))
+    ptr = np.cumsum(counts)
     nodes = [(k, s) for k in keys for s in ("L", "R")]
-    return nodes, rank, ptr, np.asarray(ids, dtype=np.int32), np.asarray(links, dtype=np.int32)
+    links = np.asarray([-1 if x is None else x for x in links], dtype=np.int64).astype(np.int32)
+    return nodes, rank, ptr, np.asarray(ids, dtype=np.int32), links
 
 
 def BetweenScaffolds(G_prime, end, iter_nodes, param, threads=0):
