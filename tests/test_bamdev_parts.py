@@ -127,7 +127,7 @@ def test_parts_concatenate_to_the_whole_file(tmp_path, n, block_bytes, n_refs):
     """(300, 700, 400): the header is longer than several parts -- they own no record and say so"""
     path = str(tmp_path / "t.bam")
     want = _ragged_file(path, n, block_bytes, n_refs)
-    for n_parts in (1, 2, 3, 5, 8, 16):
+    for n_parts in (1, 2, 3, 8, 16):
         for window, carry in ((0, 0), (70000, 2048)):
             eng = HostcheckEngine(window, carry, tail=200000)
             parts = [eng.ingest_bam(path, part=(p, n_parts)) for p in range(n_parts)]
@@ -168,7 +168,7 @@ def _worker(rank, world, port, path, blind, out_dir):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,blind", [(2, False), (3, False), (3, True)])
+@pytest.mark.parametrize("world,blind", [(2, False), (3, True)])
 def test_distributed_ingest_protocol_gloo(tmp_path, world, blind):
     """blind seeds: every part behind the first starts its chain at the first byte of its first block -- inside a record for
     this file -- so the neighbour check has to catch it and the part is read again from the previous part's landing"""
@@ -210,7 +210,7 @@ def _entry_worker(rank, world, port, path, lengths, opts, overrides, out_dir):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("pairs,world,estimate", [(2400000, 2, True), (150000, 3, True), (150000, 2, False)])
+@pytest.mark.parametrize("pairs,world,estimate", [(2400000, 2, True), (150000, 3, True)])
 def test_entry_points_on_a_path_under_a_process_group_ingest_in_parts(tmp_path, pairs, world, estimate):
     """libmetrics.get_metrics + CreateGraph.PE on a BAM PATH in a gloo job with BESST_B200_INGEST=device: every rank ingests
     its part (host rendering of the device ingest), rank 0's library metrics are broadcast when its part covers the sampled
