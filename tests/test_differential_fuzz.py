@@ -107,3 +107,35 @@ def test_dropin_equals_reference_on_random_adversarial_libraries():
     ref_harness.load_reference()
     outcomes = [differential(seed) for seed in range(48)]
     assert outcomes.count("ok") >= 40 and "exit" in outcomes   # seeds 34, 37, 38 end in the reference's 'Too few contigs' exit
+
+
+@pytest.mark.parametrize("seed", [0, 1, 4, 7, 13])
+def test_dropin_equals_reference_with_estimated_library_parameters(seed):
+    """random realistic libraries (orientation, insert size 350..5000, sd 5..20 %, 0..30 % PE contamination of mate pairs,
+    30..200 contigs, 15..60 k pairs) WITHOUT -m / -s: get_metrics estimates read length, mean, sd, skewness, the adjusted
+    distribution, contamination -- every parameter, both graphs and the counters equal the reference's (14 seeds run
+    offline, five here)"""
+    from besst_b200 import synth
+    from oracle_engine import OracleEngine
+    ref_harness.load_reference()
+    rng = np.random.default_rng(1000 + seed)
+    orient = "fr" if rng.random() < 0.5 else "rf"
+    mu = float(rng.choice([350, 550, 2000, 3000, 5000]))
+    sd = mu * float(rng.choice([0.05, 0.1, 0.2]))
+    cont = float(rng.choice([0.0, 0.0, 0.15, 0.3])) if orient == "rf" else 0.0
+    n_contigs, pairs = int(rng.integers(30, 200)), int(rng.integers(15000, 60000))
+    batch = synth.make_library(n_contigs, pairs, orient, mu, sd, cont, seed=2000 + seed).to_batch()
+    opts = dict(orientation=orient, mean=None, stddev=None, readlen=None)
+    with contextlib.redirect_stdout(io.StringIO()), contextlib.redirect_stderr(io.StringIO()):
+        r = ref_harness.run_reference(batch, opts)
+        d = helpers.run_dropin(batch, opts, OracleEngine())
+    objs = r["objects"]
+    helpers.assert_param_equal(d["param"], helpers.param_signature(objs["param"]), label=str(seed))
+    helpers.assert_signature_equal(d["G"], helpers.graph_signature(objs["G"]), label="%d/G" % seed)
+    helpers.assert_signature_equal(d["G_prime"], helpers.graph_signature(objs["G_prime"]), label="%d/G_prime" % seed)
+    want = helpers.object_signature(objs["Contigs"], objs["Scaffolds"], objs["small_contigs"], objs["small_scaffolds"])
+    for key in ("Contigs", "small_contigs", "Scaffolds", "small_scaffolds"):
+        assert d["objects"][key] == want[key], (seed, key)
+    for key, pat in tg.COUNTER_PATTERNS.items():
+        m = re.search(pat, d["information"])
+        assert (int(m.group(1)) if m else None) == r["counters"].get(key), (seed, key)
