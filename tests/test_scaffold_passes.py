@@ -107,16 +107,15 @@ def test_passes_on_graphs_made_to_be_hard(trial):
     Gp1.remove_edges_from(list(Gp1.edges())[5::17])   # G_prime lost some edges in PE's own filtering
     G2, Gp2 = G1.copy(), Gp1.copy()
     i1, i2 = io.StringIO(), io.StringIO()
-    for (G, Gp, info, iso, amb, loops) in ((G1, Gp1, i1, MS.RemoveIsolatedContigs, MS.RemoveAmbiguousRegionsUsingScore, MS.RemoveLoops),
-                                           (G2, Gp2, i2, MSB.RemoveIsolatedContigs, MSB.RemoveAmbiguousRegionsUsingScore, MSB.RemoveLoops)):
+
+    def run(G, Gp, info, iso, amb, loops):
         G = iso(G, info)
         amb(G, Gp, info, _P(), "G")
         G = iso(G, info)
         loops(G, Gp, {}, {}, info, _P())
-        if G is G1 or info is i1:
-            out1 = (G, Gp)
-        else:
-            out2 = (G, Gp)
+        return G, Gp
+    out1 = run(G1, Gp1, i1, MS.RemoveIsolatedContigs, MS.RemoveAmbiguousRegionsUsingScore, MS.RemoveLoops)
+    out2 = run(G2, Gp2, i2, MSB.RemoveIsolatedContigs, MSB.RemoveAmbiguousRegionsUsingScore, MSB.RemoveLoops)
     for X, Y in zip(out1, out2):
         assert list(X.nodes()) == list(Y.nodes())
         assert [(u, v, d.get("nr_links"), d.get("score")) for u, v, d in X.edges(data=True)] == \
