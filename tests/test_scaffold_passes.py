@@ -128,3 +128,25 @@ def test_passes_on_graphs_made_to_be_hard(trial):
     assert i1.getvalue() == i2.getvalue()
     if trial % 2 == 0:
         assert "SCORES AMBVIVALENT" in i1.getvalue()
+
+
+@pytest.mark.parametrize("seed,first", [(2, "pe"), (9, "mp")])
+def test_everything_swapped_at_once(seed, first):
+    """the drop-in get_metrics + PE (oracle engine) AND the drop-in passes + path search inside the reference's Algorithm,
+    two libraries in sequence, against the reference all the way (16 random pipelines of this kind were run offline)"""
+    ref, MS = tcb._consumer()
+    rng = np.random.default_rng(seed)
+    n_contigs, n_pairs = int(rng.integers(60, 500)), int(rng.integers(20000, 150000))
+    second = "mp" if first == "pe" else "pe"
+    lib1, opts1 = tcb._library(first, 500 + seed, n_contigs=n_contigs, n_pairs=n_pairs)
+    lib2, opts2 = tcb._library(second, 500 + seed, n_contigs=n_contigs, n_pairs=n_pairs)
+    a, b = tcb._Pipeline(ref, MS, use_dropin=False), tcb._Pipeline(ref, MS, use_dropin=True)
+    w1 = a.library(lib1, opts1, 1)
+    with swapped(MS):
+        g1 = b.library(lib1, opts1, 1)
+    tcb._assert_same_outcome(w1, g1, "lib1")
+    w2 = a.library(lib2, opts2, 2)
+    with swapped(MS):
+        g2 = b.library(lib2, opts2, 2)
+    tcb._assert_same_outcome(w2, g2, "lib2")
+    assert _info(a) == _info(b)
