@@ -33,26 +33,33 @@ class ContigTable(object):
         self.n_scaffolds = len(self.scaffold_names)
         index = {name: i for i, name in enumerate(self.scaffold_names)}
         self.scaffold_index = index
-        self.scaffold_lengths = np.zeros(self.n_scaffolds, dtype=np.int64)
-        for name, s in Scaffolds.items():
-            self.scaffold_lengths[index[name]] = s.s_length
-        for name, s in small_scaffolds.items():
-            self.scaffold_lengths[index[name]] = s.s_length
-        rows = np.zeros(len(references), dtype=CONTIG_ROW_DTYPE)
+        self.scaffold_lengths = np.fromiter((s.s_length for d in (Scaffolds, small_scaffolds) for s in d.values()),
+                                            dtype=np.int64, count=self.n_scaffolds)
+        n = len(references)
+        rows = np.zeros(n, dtype=CONTIG_ROW_DTYPE)
         mask = largest_reference_mask(lengths)
         rows["in_largest"] = mask
-        for tid, name in enumerate(references):
-            c = Contigs.get(name)
-            if c is not None:
-                state = CTG_LARGE
-            else:
-                c = small_contigs.get(name)
+        # column-wise: one pass per attribute over the contig objects instead of one structured-row assignment per contig
+        get_large, get_small = Contigs.get, small_contigs.get
+        objs = [get_large(name) for name in references]
+        state = np.fromiter((CTG_LARGE if c is not None else 0 for c in objs), dtype=np.int32, count=n)
+        if small_contigs:
+            for tid, c in enumerate(objs):
                 if c is None:
-                    continue
-                state = CTG_SMALL
-            si = index[c.scaffold]
-            rows[tid] = (state, si, 1 if c.direction else 0, int(c.position), int(c.length),
-                         int(self.scaffold_lengths[si]), int(mask[tid]), 0)
+                    c = get_small(references[tid])
+                    if c is not None:
+                        objs[tid] = c
+                        state[tid] = CTG_SMALL
+        present = [c for c in objs if c is not None]
+        where = np.nonzero(state)[0]
+        m = len(present)
+        si = np.fromiter((index[c.scaffold] for c in present), dtype=np.int64, count=m)
+        rows["state"] = state
+        rows["scaffold"][where] = si
+        rows["direction"][where] = np.fromiter((1 if c.direction else 0 for c in present), dtype=np.int32, count=m)
+        rows["position"][where] = np.fromiter((int(c.position) for c in present), dtype=np.int64, count=m)
+        rows["length"][where] = np.fromiter((int(c.length) for c in present), dtype=np.int64, count=m)
+        rows["scaf_length"][where] = self.scaffold_lengths[si]
         self.rows = rows
         self.references = list(references)
 
