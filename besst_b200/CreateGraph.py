@@ -402,6 +402,15 @@ def graph_build_distributed(engine, table, params, batch, rank, world):
     return runner.fetch_global()
 
 
+def _number_of_edges(graph):
+    """graph.number_of_edges() over the raw adjacency dicts (networkx sums a degree VIEW: a Python call per node)"""
+    adj = getattr(graph, "_adj", None)
+    if adj is None:
+        adj = graph.adj
+    loops = sum(1 for u, nbrs in adj.items() if u in nbrs)
+    return (sum(map(len, adj.values())) + loops) // 2
+
+
 class _gc_paused(object):
     """PE allocates a few container objects per contig, scaffold, node and edge -- millions for a real assembly,
     none of them garbage: pause the cyclic collector's generation scans (~40 % of the host time otherwise)."""
@@ -514,7 +523,7 @@ def _PE(Contigs, Scaffolds, Information, C_dict, param, small_contigs, small_sca
                                     lazy_observations=bool(getattr(param, 'lazy_observations', False)))
     if not param.no_score:
         GiveScoreOnEdges(G, res, table, param, Information, Scaffolds)
-    print('Number of edges in G_prime  (after removing edges under -e threshold (if not specified, default is -e 3): ', G_prime.number_of_edges(), file=Information)
+    print('Number of edges in G_prime  (after removing edges under -e threshold (if not specified, default is -e 3): ', _number_of_edges(G_prime), file=Information)
     print("\n -------------------------------------------------------------\n", file=Information)
     print('Nr of contigs/scaffolds included in this pass: ' + str(len(Scaffolds) + len(small_scaffolds)), file=Information)
     print('Out of which {0} acts as border contigs.'.format(len(Scaffolds)), file=Information)
