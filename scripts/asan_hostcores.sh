@@ -12,3 +12,6 @@ export LD_PRELOAD=$(gcc -print-file-name=libasan.so) ASAN_OPTIONS=detect_leaks=0
 python scripts/asan_ingest.py
 python scripts/asan_paths.py
 python scripts/asan_bamio.py
+# ThreadSanitizer over the threaded path search (8 threads, 1000 start nodes, the iteration cap hit)
+unset LD_PRELOAD
+g++ -O1 -g -std=c++17 -fsanitize=thread -pthread -x c++ besst_b200/csrc/besst_paths.cu scripts/tsan_paths.cpp -o /tmp/tsan_paths && /tmp/tsan_paths
